@@ -1,0 +1,194 @@
+/* rsba_cuda.h -- C ABI of the B200-native rolling-shutter bundle-adjustment inner loop.
+ *
+ * This is the drop-in boundary for the Evaluator + LinearSolver that henrique/rsba obtains
+ * from Ceres.  Every entry point states the reference interface it replaces (paths relative
+ * to /root/reference/src/rsba/).  Plain pointers and sizes only; no C++ or torch types.
+ * All functions return RSBA_OK (0) or a negative error code; rsba_cuda_last_error() gives
+ * the message.  No exceptions cross this boundary.  A handle is not thread-safe (like
+ * ceres::Problem).  There is no CPU fallback: without a CUDA device every call fails.
+ *
+ * Parameter-block conventions (mat/cam.h:19-34, VideoSfmBaRs.h:25-35):
+ *   pose   = [angle-axis r(3), camera centre c(3)]                (NUM_POSE_PARAMS 6)
+ *   frame  = pose0[6] | pose1[6]   (first / last scan-line control pose, f.poses[0..1])
+ *   point  = X[3]                                                 (NUM_POINT_PARAMS 3)
+ *   cam    = fx fy k1 k2 p1 p2 k3 cx cy
+ *   shutter: 0 GLOBAL, 1 HORIZONTAL, 2 VERTICAL (mat/cam.h:37-41)
+ * Jacobian layout per observation (30 doubles), Ceres' per-block row-major contract:
+ *   J_pose0[2][6] | J_pose1[2][6] | J_point[2][3]
+ */
+#ifndef RSBA_CUDA_H_
+#define RSBA_CUDA_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct rsba_problem rsba_problem;
+
+enum {
+  RSBA_OK = 0,
+  RSBA_ERR_INVALID_ARGUMENT = -1,
+  RSBA_ERR_CUDA = -2,
+  RSBA_ERR_NO_DEVICE = -3,
+  RSBA_ERR_STATE = -4,
+  RSBA_ERR_EVALUATION_FAILED = -5, /* a functor returned false (mat/cam.h:410-412) */
+  RSBA_ERR_LINEAR_SOLVER = -6,     /* reduced camera matrix not positive definite */
+  RSBA_ERR_NCCL = -7
+};
+
+/* Solver::Options as used by CeresHandler::solve (CeresHandler.h:394-419) and
+ * VideoSfMHandler::BA (VideoSfMHandler.cc:579-583).  rsba_cuda_default_options() fills the
+ * Ceres 1.9.0 defaults. */
+typedef struct rsba_solve_options {
+  int max_num_iterations;           /* 50 (CeresHandler.h:405); callers pass maxIter */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;     /* 1e16 */
+  double min_trust_region_radius;     /* 1e-32 */
+  double min_relative_decrease;       /* 1e-3 */
+  double min_lm_diagonal;             /* 1e-6 */
+  double max_lm_diagonal;             /* 1e32 */
+  double function_tolerance;          /* 1e-6 */
+  double gradient_tolerance;          /* 1e-10 */
+  double parameter_tolerance;         /* 1e-8 */
+  int jacobi_scaling;                 /* 1 */
+  double huber_loss;                  /* 0 = no loss (SfmOptions.h:64, CeresHandler.h:85-90) */
+  int verbose;                        /* minimizer_progress_to_stdout (CeresHandler.h:404) */
+  int dense_cholesky;                 /* 1: ignore the tile occupancy map, factor S fully dense */
+} rsba_solve_options;
+
+/* Solver::Summary fields the reference reads (VideoSfMHandler.cc:593-596, 627-630). */
+typedef struct rsba_solve_summary {
+  int usable;                  /* Summary::IsSolutionUsable() */
+  int termination;             /* 0 convergence, 1 no convergence (max iter), 2 failure */
+  int iterations;              /* LM iterations performed (excluding the initial evaluation) */
+  int num_successful_steps;
+  int num_unsuccessful_steps;
+  int num_jacobian_evaluations;
+  int num_residual_evaluations;
+  long num_residual_blocks;
+  long num_parameters_reduced; /* scalar parameters that are not constant */
+  double initial_cost;
+  double final_cost;
+  double final_radius;
+  double final_gradient_max_norm;
+  double time_total_ms;        /* wall clock of rsba_cuda_solve, copies included */
+  double time_jacobian_ms;     /* device time: residual+Jacobian kernel */
+  double time_residual_ms;     /* device time: cost-only kernel */
+  double time_schur_ms;        /* device time: normal equations + Schur complement */
+  double time_cholesky_ms;     /* device time: reduced-system factorisation + solves */
+  double time_update_ms;       /* device time: back-substitution, step, bookkeeping */
+  double time_allreduce_ms;    /* device time: NCCL allreduce of the reduced system */
+  char message[128];
+} rsba_solve_summary;
+
+/* ------------------------------------------------------------------ lifecycle */
+/* Replaces: construction of CeresHandler / ceres::Problem (CeresHandler.h:83-91). */
+int rsba_cuda_create(rsba_problem** out, int device);
+void rsba_cuda_destroy(rsba_problem* h);
+const char* rsba_cuda_last_error(void);
+/* Optional: run on the caller's CUDA stream (a cudaStream_t); default is a private stream. */
+int rsba_cuda_set_stream(rsba_problem* h, void* cuda_stream);
+void rsba_cuda_default_options(rsba_solve_options* o);
+
+/* ------------------------------------------------------------------ problem construction */
+/* Replaces: the per-residual constants captured by RsBundleAdjustment::Create /
+ * ReprojectionError ctor (VideoSfmBaRs.h:16-22,53-64; video_bundler_free.h:21-29): the
+ * session intrinsics sess.cam, sess.rs, sess.scanlines and opt.model.interpolateRotation. */
+int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter,
+                         const int scanlines[2], int interpolate_rotation);
+
+/* Replaces: RsBundleAdjustment::Create(sess,opt,obs) + problem.AddResidualBlock(cost, loss,
+ * f.poses[0].data(), f.poses[1].data(), t->pt.data())  (CeresHandler.h:250-255).
+ * Block identity is pointer identity, as in Ceres; the caller owns the parameter memory,
+ * which must stay put until the handle is destroyed.  Results are written back in place. */
+int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0,
+                              double* pose1, double* point);
+/* Replaces: problem.SetParameterBlockConstant(double*)  (CeresHandler.h:283,299,344-345). */
+int rsba_cuda_set_block_constant(rsba_problem* h, double* block);
+/* Replaces: problem.SetParameterization(pose, new SubsetParameterization(6, constant))
+ * (CeresHandler.h:350-381): the listed components of a 6-wide pose block are held fixed. */
+int rsba_cuda_set_subset_constant(rsba_problem* h, double* pose_block, int n_constant,
+                                  const int* constant_components);
+
+/* Bulk form of the same construction for callers that already hold flat arrays (the
+ * session <-> SoA marshaller).  Observation i ties frame obs_frame[i] (poses + 12*frame)
+ * to point obs_point[i] (points + 3*point).  Arrays are HOST memory and are copied.
+ * Observations are stably sorted by frame on upload (== the reference's insertion order,
+ * CeresHandler.h:208); outputs are always reported in the caller's order.
+ * const_pose_mask[frame] bit k set => scalar k (0..11) of the frame is constant (may be NULL).
+ * const_point[point] != 0 => point block constant (may be NULL). */
+int rsba_cuda_set_scene(rsba_problem* h, long n_obs, const double* obs_xy, const int* obs_frame,
+                        const int* obs_point, int n_frames, int n_points,
+                        const unsigned short* const_pose_mask, const unsigned char* const_point);
+/* Host -> device copy of the current parameter values (bulk form). */
+int rsba_cuda_set_parameters(rsba_problem* h, const double* poses, const double* points);
+/* Device -> host copy of the current parameter values (bulk form). */
+int rsba_cuda_get_parameters(rsba_problem* h, double* poses, double* points);
+
+/* ------------------------------------------------------------------ evaluation */
+/* Replaces: problem.Evaluate(EvaluateOptions(), &cost, residuals, NULL, jacobian)
+ * (CeresHandler.h:386) == what ceres::ProgramEvaluator does each LM iteration with
+ * AutoDiffCostFunction<RsBundleAdjustment,2,6,6,3> (VideoSfmBaRs.h:58-63).
+ * Outputs are HOST pointers, any may be NULL: cost = 1/2 sum r^2; residuals[2N];
+ * jacobian[30N]; valid[N] (the functor's bool).  Pointer-API problems read the parameter
+ * values from the caller's blocks first.  Returns RSBA_ERR_EVALUATION_FAILED (outputs still
+ * written, invalid rows zero) if any functor returned false. */
+int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double* jacobian,
+                       unsigned char* valid);
+
+/* HBM-resident form: evaluates on the device and leaves everything there.  The returned
+ * device pointers (sorted-by-frame observation order) stay valid until the next scene
+ * change.  with_jacobian = 0 runs the cost-only kernel. */
+int rsba_cuda_evaluate_device(rsba_problem* h, int with_jacobian, double* cost,
+                              long* num_invalid);
+int rsba_cuda_device_buffers(rsba_problem* h, void** residuals, void** jacobian, void** valid,
+                             void** poses, void** points);
+/* Sorted position -> caller's observation index (HOST array of n_obs longs, may be NULL to
+ * query the count). */
+long rsba_cuda_observation_order(rsba_problem* h, long* order);
+
+/* ------------------------------------------------------------------ solve */
+/* Replaces: ceres::Solve(options, &problem, &summary) with linear_solver_type = SPARSE_SCHUR
+ * (CeresHandler.h:403,419): Levenberg-Marquardt trust region; point blocks eliminated by a
+ * Schur complement; reduced camera system factorised by Cholesky on the device; parameters
+ * updated in place (pointer API) or on the device (bulk API; read back with
+ * rsba_cuda_get_parameters). */
+int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_summary* summary);
+
+/* One linearisation at the current parameters, for parity tests and profiling: builds the
+ * normal equations, applies Jacobi scaling + the LM diagonal for `radius`, eliminates the
+ * points, factorises and solves.  HOST outputs, any may be NULL:
+ *   S[n*n] (row-major, n = 12*frames, full symmetric), rhs[n]  -- reduced system in the
+ *     scaled space, constant parameters replaced by identity rows;
+ *   delta_poses[12*frames], delta_points[3*points]            -- unscaled LM step;
+ *   model_cost_change.
+ * Does not move the parameters. */
+int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt, double radius,
+                                 double* S, double* rhs, double* delta_poses,
+                                 double* delta_points, double* model_cost_change);
+
+/* ------------------------------------------------------------------ multi-GPU */
+/* One process per GPU.  Rank 0 obtains an id, the host framework broadcasts the 128 bytes,
+ * every rank calls comm_init.  After that rsba_cuda_solve performs exactly one NCCL
+ * allreduce of [S | rhs | cost terms] per linear solve.  Single-GPU use never touches NCCL. */
+int rsba_cuda_nccl_unique_id(unsigned char id[128]);
+int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigned char id[128]);
+
+/* ------------------------------------------------------------------ introspection */
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+long rsba_cuda_launch_count(rsba_problem* h);
+/* Device time (ms) of the last call of each stage, measured with CUDA events on the
+ * launching stream: 0 jacobian, 1 residual, 2 schur, 3 cholesky, 4 update, 5 allreduce. */
+double rsba_cuda_stage_ms(rsba_problem* h, int stage);
+const char* rsba_cuda_version(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSBA_CUDA_H_ */

@@ -1,0 +1,363 @@
+"""ctypes mirror of the C ABI (``include/rsba_cuda.h``) -- used by tests and ``bench.py``.
+
+The product is ``rsba_b200/lib/librsba_cuda.so``; this module only binds it.  It never
+imports ``oracle`` and has no CPU fallback: if the shared library is missing or no CUDA
+device is present, construction raises.
+
+``Problem`` mirrors the slice of ``ceres::Problem`` that ``CeresHandler`` uses
+(``CeresHandler.h:245-255, 283-300, 335-382, 394-426``):
+
+===============================  =========================================================
+reference call                   here
+===============================  =========================================================
+``RsBundleAdjustment::Create``   ``Problem.add_rs_residual(obs, pose0, pose1, point)``
+ + ``AddResidualBlock``
+``SetParameterBlockConstant``    ``Problem.set_block_constant(block)``
+``SubsetParameterization``       ``Problem.set_subset_constant(pose, [components])``
+``problem.Evaluate``             ``Problem.evaluate()``
+``ceres::Solve``                 ``Problem.solve(options) -> summary``
+===============================  =========================================================
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librsba_cuda.so")
+
+RSBA_OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = -1, -2, -3, -4
+ERR_EVALUATION_FAILED, ERR_LINEAR_SOLVER, ERR_NCCL = -5, -6, -7
+
+# every symbol include/rsba_cuda.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "rsba_cuda_create", "rsba_cuda_destroy", "rsba_cuda_last_error", "rsba_cuda_set_stream",
+    "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_add_rs_residual",
+    "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
+    "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
+    "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
+    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_nccl_unique_id",
+    "rsba_cuda_comm_init", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
+]
+
+
+class SolveOptions(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int),
+        ("initial_trust_region_radius", C.c_double),
+        ("max_trust_region_radius", C.c_double),
+        ("min_trust_region_radius", C.c_double),
+        ("min_relative_decrease", C.c_double),
+        ("min_lm_diagonal", C.c_double),
+        ("max_lm_diagonal", C.c_double),
+        ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double),
+        ("parameter_tolerance", C.c_double),
+        ("jacobi_scaling", C.c_int),
+        ("huber_loss", C.c_double),
+        ("verbose", C.c_int),
+        ("dense_cholesky", C.c_int),
+    ]
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [
+        ("usable", C.c_int),
+        ("termination", C.c_int),
+        ("iterations", C.c_int),
+        ("num_successful_steps", C.c_int),
+        ("num_unsuccessful_steps", C.c_int),
+        ("num_jacobian_evaluations", C.c_int),
+        ("num_residual_evaluations", C.c_int),
+        ("num_residual_blocks", C.c_long),
+        ("num_parameters_reduced", C.c_long),
+        ("initial_cost", C.c_double),
+        ("final_cost", C.c_double),
+        ("final_radius", C.c_double),
+        ("final_gradient_max_norm", C.c_double),
+        ("time_total_ms", C.c_double),
+        ("time_jacobian_ms", C.c_double),
+        ("time_residual_ms", C.c_double),
+        ("time_schur_ms", C.c_double),
+        ("time_cholesky_ms", C.c_double),
+        ("time_update_ms", C.c_double),
+        ("time_allreduce_ms", C.c_double),
+        ("message", C.c_char * 128),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["message"] = self.message.decode(errors="replace")
+        return d
+
+
+class RsbaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"rsba_cuda error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def load_library():
+    """dlopen the product library and declare the signatures.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+            "rsba_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.rsba_cuda_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.rsba_cuda_destroy.argtypes = [vp]
+    lib.rsba_cuda_destroy.restype = None
+    lib.rsba_cuda_last_error.restype = C.c_char_p
+    lib.rsba_cuda_version.restype = C.c_char_p
+    lib.rsba_cuda_set_stream.argtypes = [vp, vp]
+    lib.rsba_cuda_default_options.argtypes = [C.POINTER(SolveOptions)]
+    lib.rsba_cuda_default_options.restype = None
+    lib.rsba_cuda_set_camera.argtypes = [vp, _dp, C.c_int, _ip, C.c_int]
+    lib.rsba_cuda_add_rs_residual.argtypes = [vp, _dp, vp, vp, vp]
+    lib.rsba_cuda_set_block_constant.argtypes = [vp, vp]
+    lib.rsba_cuda_set_subset_constant.argtypes = [vp, vp, C.c_int, _ip]
+    lib.rsba_cuda_set_scene.argtypes = [vp, C.c_long, _dp, _ip, _ip, C.c_int, C.c_int,
+                                        C.POINTER(C.c_ushort), C.POINTER(C.c_ubyte)]
+    lib.rsba_cuda_set_parameters.argtypes = [vp, vp, vp]
+    lib.rsba_cuda_get_parameters.argtypes = [vp, vp, vp]
+    lib.rsba_cuda_evaluate.argtypes = [vp, _dp, vp, vp, vp]
+    lib.rsba_cuda_evaluate_device.argtypes = [vp, C.c_int, _dp, C.POINTER(C.c_long)]
+    lib.rsba_cuda_device_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
+    lib.rsba_cuda_observation_order.argtypes = [vp, vp]
+    lib.rsba_cuda_observation_order.restype = C.c_long
+    lib.rsba_cuda_solve.argtypes = [vp, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
+    lib.rsba_cuda_linearize_and_step.argtypes = [vp, C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp, _dp]
+    lib.rsba_cuda_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
+    lib.rsba_cuda_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
+    lib.rsba_cuda_launch_count.argtypes = [vp]
+    lib.rsba_cuda_launch_count.restype = C.c_long
+    lib.rsba_cuda_stage_ms.argtypes = [vp, C.c_int]
+    lib.rsba_cuda_stage_ms.restype = C.c_double
+    _lib = lib
+    return lib
+
+
+def default_options(**kw) -> SolveOptions:
+    o = SolveOptions()
+    load_library().rsba_cuda_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _addr(a):
+    """Address of a numpy array / torch tensor / int / None, as c_void_p."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+STAGES = ("jacobian", "residual", "schur", "cholesky", "update", "allreduce")
+
+
+class Problem:
+    """One BA problem on one GPU (the analogue of ``ceres::Problem`` + ``ceres::Solve``)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.lib.rsba_cuda_create(C.byref(h), int(device)))
+        self._h = h
+        self._keep = []          # arrays whose memory the pointer API refers to
+        self.num_obs = 0
+        self.num_frames = 0
+        self.num_points = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc, allow=()):
+        if rc != RSBA_OK and rc not in allow:
+            raise RsbaError(rc, self.lib.rsba_cuda_last_error().decode(errors="replace"))
+        return rc
+
+    def close(self):
+        if self._h is not None:
+            self.lib.rsba_cuda_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.rsba_cuda_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # ------------------------------------------------------------------ construction
+    def set_camera(self, cam, shutter, scanlines, interpolate_rotation=True):
+        cam = np.ascontiguousarray(cam, dtype=np.float64)
+        scan = np.ascontiguousarray(scanlines, dtype=np.int32)
+        assert cam.size == 9 and scan.size == 2
+        self._check(self.lib.rsba_cuda_set_camera(self._h, cam.ctypes.data_as(_dp), int(shutter),
+                                                  scan.ctypes.data_as(_ip), int(bool(interpolate_rotation))))
+
+    def add_rs_residual(self, observed, pose0: np.ndarray, pose1: np.ndarray, point: np.ndarray):
+        """``pose0``/``pose1``/``point`` are float64 numpy views; identity = their address."""
+        obs = np.ascontiguousarray(observed, dtype=np.float64)
+        for a in (pose0, pose1, point):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+        self._keep.extend((pose0, pose1, point))
+        self._check(self.lib.rsba_cuda_add_rs_residual(self._h, obs.ctypes.data_as(_dp), _addr(pose0),
+                                                       _addr(pose1), _addr(point)))
+
+    def set_block_constant(self, block: np.ndarray):
+        self._check(self.lib.rsba_cuda_set_block_constant(self._h, _addr(block)))
+
+    def set_subset_constant(self, pose_block: np.ndarray, components):
+        comp = np.ascontiguousarray(components, dtype=np.int32)
+        self._check(self.lib.rsba_cuda_set_subset_constant(self._h, _addr(pose_block), int(comp.size),
+                                                           comp.ctypes.data_as(_ip)))
+
+    def set_scene(self, obs_xy, obs_frame, obs_point, num_frames, num_points, const_pose_mask=None,
+                  const_point=None):
+        xy = np.ascontiguousarray(obs_xy, dtype=np.float64)
+        fr = np.ascontiguousarray(obs_frame, dtype=np.int32)
+        pt = np.ascontiguousarray(obs_point, dtype=np.int32)
+        n = fr.shape[0]
+        assert xy.size == 2 * n and pt.shape[0] == n
+        pm = None if const_pose_mask is None else np.ascontiguousarray(const_pose_mask, dtype=np.uint16)
+        pc = None if const_point is None else np.ascontiguousarray(const_point, dtype=np.uint8)
+        self._check(self.lib.rsba_cuda_set_scene(
+            self._h, n, xy.ctypes.data_as(_dp), fr.ctypes.data_as(_ip), pt.ctypes.data_as(_ip),
+            int(num_frames), int(num_points),
+            None if pm is None else pm.ctypes.data_as(C.POINTER(C.c_ushort)),
+            None if pc is None else pc.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        self.num_obs, self.num_frames, self.num_points = n, int(num_frames), int(num_points)
+
+    def load_scene(self, scene, poses=None, points=None):
+        """Bulk construction from a :class:`rsba_b200.scene.Scene` (frame-constant flags become
+        ``SetParameterBlockConstant`` on both pose blocks, CeresHandler.h:342-346)."""
+        self.set_camera(scene.cam, scene.shutter, scene.scanlines, scene.interpolate_rotation)
+        mask = np.where(np.asarray(scene.const_frames, dtype=bool), 0xFFF, 0).astype(np.uint16)
+        self.set_scene(scene.obs_xy, scene.obs_frame, scene.obs_point, scene.num_frames, scene.num_points,
+                       const_pose_mask=mask)
+        self.set_parameters(scene.poses if poses is None else poses,
+                            scene.points if points is None else points)
+
+    def set_parameters(self, poses, points):
+        """Host arrays (numpy, or pinned torch CPU tensors) -> device."""
+        if isinstance(poses, np.ndarray):
+            poses = np.ascontiguousarray(poses, dtype=np.float64)
+        if isinstance(points, np.ndarray):
+            points = np.ascontiguousarray(points, dtype=np.float64)
+        self._check(self.lib.rsba_cuda_set_parameters(self._h, _addr(poses), _addr(points)))
+
+    def get_parameters(self, poses=None, points=None):
+        if poses is None:
+            poses = np.empty((self.num_frames, 12))
+        if points is None:
+            points = np.empty((self.num_points, 3))
+        self._check(self.lib.rsba_cuda_get_parameters(self._h, _addr(poses), _addr(points)))
+        return poses, points
+
+    # ------------------------------------------------------------------ evaluation
+    def evaluate(self, residuals=True, jacobian=True, valid=True, num_obs=None, check=True):
+        """Host outputs in the caller's observation order.
+        Returns (cost, residuals [N,2], jacobian [N,30], valid [N])."""
+        n = self.num_obs if num_obs is None else num_obs
+        cost = C.c_double(0.0)
+        r = np.zeros((n, 2)) if residuals else None
+        J = np.zeros((n, 30)) if jacobian else None
+        v = np.zeros(n, dtype=np.uint8) if valid else None
+        rc = self.lib.rsba_cuda_evaluate(self._h, C.byref(cost), _addr(r), _addr(J), _addr(v))
+        self._check(rc, allow=() if check else (ERR_EVALUATION_FAILED,))
+        return cost.value, r, J, v
+
+    def evaluate_device(self, with_jacobian=True, fetch=True):
+        """HBM-resident evaluation; with ``fetch`` returns (cost, num_invalid) (synchronises)."""
+        if fetch:
+            cost, bad = C.c_double(0.0), C.c_long(0)
+            self._check(self.lib.rsba_cuda_evaluate_device(self._h, int(with_jacobian), C.byref(cost), C.byref(bad)))
+            return cost.value, bad.value
+        self._check(self.lib.rsba_cuda_evaluate_device(self._h, int(with_jacobian), None, None))
+        return None
+
+    def device_buffers(self):
+        ptrs = [C.c_void_p() for _ in range(5)]
+        self._check(self.lib.rsba_cuda_device_buffers(self._h, *[C.byref(p) for p in ptrs]))
+        return dict(zip(("residuals", "jacobian", "valid", "poses", "points"), [p.value for p in ptrs]))
+
+    def observation_order(self):
+        n = self.lib.rsba_cuda_observation_order(self._h, None)
+        order = np.empty(n, dtype=np.int64)
+        self.lib.rsba_cuda_observation_order(self._h, _addr(order))
+        return order
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, options: SolveOptions | None = None, check=True) -> SolveSummary:
+        if options is None:
+            options = default_options()
+        s = SolveSummary()
+        rc = self.lib.rsba_cuda_solve(self._h, C.byref(options), C.byref(s))
+        if check:
+            self._check(rc)
+        s.rc = rc
+        return s
+
+    def linearize_and_step(self, radius, options: SolveOptions | None = None, want_S=True):
+        """One linearisation + LM step at the current parameters (does not move them).
+        Returns dict(S, rhs, delta_poses, delta_points, model_cost_change)."""
+        if options is None:
+            options = default_options()
+        n = 12 * self.num_frames
+        S = np.zeros((n, n)) if want_S else None
+        rhs = np.zeros(n)
+        dposes = np.zeros((self.num_frames, 12))
+        dpoints = np.zeros((self.num_points, 3))
+        mcc = C.c_double(0.0)
+        self._check(self.lib.rsba_cuda_linearize_and_step(self._h, C.byref(options), float(radius), _addr(S),
+                                                          _addr(rhs), _addr(dposes), _addr(dpoints), C.byref(mcc)))
+        return dict(S=S, rhs=rhs, delta_poses=dposes, delta_points=dpoints, model_cost_change=mcc.value)
+
+    # ------------------------------------------------------------------ multi-GPU / introspection
+    def comm_init(self, rank: int, world_size: int, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.rsba_cuda_comm_init(self._h, int(rank), int(world_size), buf))
+
+    def launch_count(self) -> int:
+        return int(self.lib.rsba_cuda_launch_count(self._h))
+
+    def stage_ms(self, stage) -> float:
+        idx = STAGES.index(stage) if isinstance(stage, str) else int(stage)
+        return float(self.lib.rsba_cuda_stage_ms(self._h, idx))
+
+
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = (C.c_ubyte * 128)()
+    rc = lib.rsba_cuda_nccl_unique_id(buf)
+    if rc != RSBA_OK:
+        raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
+    return bytes(buf)

@@ -1,0 +1,175 @@
+// K1 / K1r -- rolling-shutter reprojection residual and its 2x(6+6+3) Jacobian, FP64.
+//
+// Supersedes, per observation, RsBundleAdjustment::operator() evaluated under
+// ceres::Jet<double,15> by AutoDiffCostFunction<.,2,6,6,3> (VideoSfmBaRs.h:25-35,58-63):
+//   interpolate_rs   mat/cam.h:316-349   tau from observed_x for BOTH shutter directions
+//                                        (the functor passes obs = {x, x}: VideoSfmBaRs.h:31)
+//   interpolate/slerp mat/cam.h:294-311, 251-288   component-wise LINEAR interpolation of the
+//                                        angle-axis vector and of the camera centre
+//   w2c              mat/cam.h:355-366   X - c, then ceres::AngleAxisRotatePoint
+//   w2i              mat/cam.h:401-419   fails (functor returns false) when z < 1e-8
+//   c2i + distort    mat/cam.h:372-395, 49-72
+//   residual         video_bundler_free.h:45-65
+// The Jacobian is the exact chain rule of those formulas (what forward-mode autodiff yields),
+// written out by hand: because tau does not depend on the parameters,
+//   J_pose0 = (1-tau) * J_pose,  J_pose1 = tau * J_pose  (rotation columns: 1 and 0 when
+//   interpolateRotation is off), with J_pose the 2x6 Jacobian w.r.t. the interpolated pose.
+//
+// Data movement (B200): one warp = 32 consecutive observations (sorted by frame).  The
+// frame's control poses are staged once per CTA in shared memory; xy / indices are read
+// coalesced; the 32x30 Jacobian tile is assembled in shared memory and leaves the SM as ONE
+// 7680-byte TMA bulk store (cp.async.bulk.global.shared::cta), so the 240 B/observation
+// write stream -- 85 % of this kernel's HBM traffic -- is fully coalesced.
+#include "common.cuh"
+#include "reproj_math.cuh"
+
+namespace rsba {
+
+namespace {
+
+constexpr int kK1Threads = 128;
+constexpr int kK1Warps = kK1Threads / 32;
+constexpr int kStageFrames = 8;  // control poses staged per CTA (frames spanned by 128 obs)
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Stage the control poses of the frames this CTA's observations span (sorted by frame, so
+// [frame[first], frame[last]]).  Returns the first staged frame, or -1 if the span is too
+// wide and poses must be read through L1 instead.
+__device__ __forceinline__ int stage_poses(const ObsView& obs, const double* __restrict__ poses,
+                                           long base, int cnt, double* s_pose) {
+  const int f_lo = obs.frame[base];
+  const int f_hi = obs.frame[base + cnt - 1];
+  const int span = f_hi - f_lo + 1;
+  if (span > kStageFrames || span <= 0) return -1;
+  for (int i = threadIdx.x; i < span * kFrameParams; i += blockDim.x)
+    s_pose[i] = poses[(long)f_lo * kFrameParams + i];
+  return f_lo;
+}
+
+template <bool JAC>
+__global__ void __launch_bounds__(kK1Threads)
+k1_kernel(const CameraModel cm, const ObsView obs, const double* __restrict__ poses,
+          const double* __restrict__ points, double* __restrict__ residuals,
+          double* __restrict__ jac, unsigned char* __restrict__ valid,
+          double* __restrict__ cost_partials, int* __restrict__ invalid_count) {
+  __shared__ double s_pose[kStageFrames * kFrameParams];
+  __shared__ double s_cost[kK1Warps];
+  extern __shared__ __align__(128) double s_jac[];  // [warps][32][30], JAC only
+
+  const long base = (long)blockIdx.x * kK1Threads;
+  const int cnt = (int)min((long)kK1Threads, obs.n - base);
+  const int staged = stage_poses(obs, poses, base, cnt, s_pose);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long i = base + threadIdx.x;
+  double cost = 0.0;
+  bool bad = false;
+  double* Jrow = JAC ? s_jac + (warp * 32 + lane) * kJacDoubles : nullptr;
+  if (i < obs.n) {
+    const double2 o = obs.xy[i];
+    const int f = obs.frame[i];
+    const int p = obs.point[i];
+    const double* pp = points + 3L * p;
+    const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
+    double pose[kFrameParams];
+    if (staged >= 0) {
+      const double* sp = s_pose + (f - staged) * kFrameParams;
+#pragma unroll
+      for (int k = 0; k < kFrameParams; ++k) pose[k] = sp[k];
+    } else {
+      const double* gp = poses + (long)f * kFrameParams;
+#pragma unroll
+      for (int k = 0; k < kFrameParams; ++k) pose[k] = __ldg(gp + k);
+    }
+    const Proj pr = reproject<JAC>(cm, o.x, o.y, pose, X0, X1, X2, Jrow);
+    cost = pr.r0 * pr.r0 + pr.r1 * pr.r1;
+    bad = !pr.ok;
+    if (residuals) reinterpret_cast<double2*>(residuals)[i] = make_double2(pr.r0, pr.r1);
+    if (valid) valid[i] = pr.ok ? 1 : 0;
+  }
+
+  if (JAC) {
+    // Hand the warp's tile to the async proxy and push it out with one bulk store.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const long wbase = base + warp * 32;
+    if (lane == 0 && wbase < obs.n) {
+      const int wcnt = (int)min(32L, obs.n - wbase);
+      const unsigned bytes = (unsigned)(wcnt * kJacDoubles * sizeof(double));  // multiple of 16
+      const unsigned src = (unsigned)__cvta_generic_to_shared(s_jac + warp * 32 * kJacDoubles);
+      double* dst = jac + wbase * kJacDoubles;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
+                   "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+
+  // cost partial of this CTA (fixed reduction order -> deterministic cost)
+  cost = warp_sum(cost);
+  const unsigned badmask = __ballot_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    s_cost[warp] = cost;
+    if (badmask) atomicAdd(invalid_count, __popc(badmask));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kK1Warps; ++w) t += s_cost[w];
+    cost_partials[blockIdx.x] = t;
+  }
+  if (JAC) {
+    // shared memory must outlive the bulk store's read
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double s[32];
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) t += partials[i];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    t = s[threadIdx.x];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = 0.5 * t;  // cost = 1/2 sum r^2
+  }
+}
+
+}  // namespace
+
+int k1_num_partials(long n) { return (int)((n + kK1Threads - 1) / kK1Threads); }
+
+void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
+               double* residuals, double* jac, unsigned char* valid, double* cost_partials,
+               int* invalid_count, cudaStream_t stream) {
+  if (obs.n <= 0) return;
+  const int grid = k1_num_partials(obs.n);
+  const size_t smem = (size_t)kK1Threads * kJacDoubles * sizeof(double);
+  k1_kernel<true><<<grid, kK1Threads, smem, stream>>>(cm, obs, poses, points, residuals, jac, valid,
+                                                      cost_partials, invalid_count);
+}
+
+void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
+                double /*huber*/, double* cost_partials, int* invalid_count, cudaStream_t stream) {
+  if (obs.n <= 0) return;
+  const int grid = k1_num_partials(obs.n);
+  k1_kernel<false><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, nullptr, nullptr, nullptr,
+                                                    cost_partials, invalid_count);
+}
+
+void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t stream) {
+  reduce_partials_kernel<<<1, 1024, 0, stream>>>(partials, n, out);
+}
+
+}  // namespace rsba

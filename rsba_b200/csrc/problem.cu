@@ -1,0 +1,473 @@
+// C ABI: lifecycle, problem construction, evaluation (include/rsba_cuda.h).
+#include "problem.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace rsba {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file,
+           line, what);
+  set_last_error(buf);
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? RSBA_ERR_NO_DEVICE
+                                                                      : RSBA_ERR_CUDA;
+}
+
+static int fail(int code, const std::string& msg) {
+  set_last_error(msg);
+  return code;
+}
+
+void stage_begin(rsba_problem* h, Stage s) {
+  StageTimer& t = h->timers[s];
+  if (!t.beg) {
+    cudaEventCreate(&t.beg);
+    cudaEventCreate(&t.end);
+  }
+  cudaEventRecord(t.beg, h->stream);
+}
+
+void stage_end(rsba_problem* h, Stage s) {
+  StageTimer& t = h->timers[s];
+  cudaEventRecord(t.end, h->stream);
+  t.pending = true;
+}
+
+double stage_collect(rsba_problem* h, Stage s) {
+  StageTimer& t = h->timers[s];
+  if (t.pending) {
+    cudaEventSynchronize(t.end);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t.beg, t.end);
+    t.last_ms = ms;
+    t.total_ms += ms;
+    t.pending = false;
+  }
+  return t.last_ms;
+}
+
+int ensure_eval_buffers(rsba_problem* h, bool jac) {
+  const size_t n = (size_t)h->n_obs;
+  RSBA_CUDA_TRY(h->d_res.resize(2 * n));
+  RSBA_CUDA_TRY(h->d_valid.resize(n));
+  RSBA_CUDA_TRY(h->d_cost_partials.resize((size_t)k1_num_partials(h->n_obs) + 1));
+  RSBA_CUDA_TRY(h->d_scalars.resize(16));
+  RSBA_CUDA_TRY(h->d_invalid.resize(4));
+  if (jac) RSBA_CUDA_TRY(h->d_jac.resize((size_t)kJacDoubles * n));
+  return RSBA_OK;
+}
+
+int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* points,
+                 double* cost_out_host, long* invalid_out_host) {
+  int rc = ensure_eval_buffers(h, jac);
+  if (rc) return rc;
+  RSBA_CUDA_TRY(cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), h->stream));
+  const Stage st = jac ? kStageJacobian : kStageResidual;
+  stage_begin(h, st);
+  if (jac) {
+    launch_k1(h->cm, h->obs_view(), poses, points, h->d_res.ptr, h->d_jac.ptr, h->d_valid.ptr,
+              h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
+  } else {
+    launch_k1r(h->cm, h->obs_view(), poses, points, 0.0, h->d_cost_partials.ptr, h->d_invalid.ptr,
+               h->stream);
+  }
+  launch_reduce_partials(h->d_cost_partials.ptr, k1_num_partials(h->n_obs), h->d_scalars.ptr,
+                         h->stream);
+  stage_end(h, st);
+  h->launches += 2;
+  RSBA_CUDA_TRY(cudaGetLastError());
+  if (cost_out_host || invalid_out_host) {
+    double c = 0.0;
+    int bad = 0;
+    RSBA_CUDA_TRY(cudaMemcpyAsync(&c, h->d_scalars.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(&bad, h->d_invalid.ptr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (cost_out_host) *cost_out_host = c;
+    if (invalid_out_host) *invalid_out_host = bad;
+  }
+  return RSBA_OK;
+}
+
+// Sort observations by frame (stable: keeps the caller's within-frame order, which is the
+// reference's insertion order, CeresHandler.h:208) and upload the SoA.
+static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr, const int* pt,
+                        int n_frames, int n_points) {
+  for (long i = 0; i < n; ++i) {
+    if (fr[i] < 0 || fr[i] >= n_frames || pt[i] < 0 || pt[i] >= n_points)
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "observation index out of range");
+  }
+  h->order.resize(n);
+  std::iota(h->order.begin(), h->order.end(), 0L);
+  bool sorted = true;
+  for (long i = 1; i < n && sorted; ++i) sorted = fr[i - 1] <= fr[i];
+  if (!sorted)
+    std::stable_sort(h->order.begin(), h->order.end(), [&](long a, long b) { return fr[a] < fr[b]; });
+  std::vector<double2> sxy(n);
+  h->h_obs_frame.resize(n);
+  h->h_obs_point.resize(n);
+  for (long i = 0; i < n; ++i) {
+    const long s = h->order[i];
+    sxy[i] = make_double2(xy[2 * s], xy[2 * s + 1]);
+    h->h_obs_frame[i] = fr[s];
+    h->h_obs_point[i] = pt[s];
+  }
+  h->n_obs = n;
+  h->n_frames = n_frames;
+  h->n_points = n_points;
+  RSBA_CUDA_TRY(h->d_obs_xy.resize(n));
+  RSBA_CUDA_TRY(h->d_obs_frame.resize(n));
+  RSBA_CUDA_TRY(h->d_obs_point.resize(n));
+  RSBA_CUDA_TRY(h->d_poses.resize((size_t)kFrameParams * n_frames));
+  RSBA_CUDA_TRY(h->d_points.resize((size_t)kPointParams * n_points));
+  if (n > 0) {
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_xy.ptr, sxy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame.ptr, h->h_obs_frame.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_point.ptr, h->h_obs_point.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));  // sxy is a local
+  h->scene_set = true;
+  h->params_set = false;
+  if (h->lm) {
+    lm_state_free(h->lm);
+    h->lm = nullptr;
+  }
+  return RSBA_OK;
+}
+
+int finalize_pointer_problem(rsba_problem* h) {
+  if (!h->ptr_mode || !h->ptr_dirty) return RSBA_OK;
+  const long n = (long)h->ptr_obs.size();
+  std::vector<double> xy(2 * n);
+  std::vector<int> fr(n), pt(n);
+  for (long i = 0; i < n; ++i) {
+    xy[2 * i] = h->ptr_obs[i].x;
+    xy[2 * i + 1] = h->ptr_obs[i].y;
+    fr[i] = h->ptr_obs[i].frame;
+    pt[i] = h->ptr_obs[i].point;
+  }
+  int rc = upload_scene(h, n, xy.data(), fr.data(), pt.data(), (int)h->frame_pose0.size(),
+                        (int)h->point_ptr.size());
+  if (rc) return rc;
+  h->pose_mask = h->ptr_pose_mask;
+  h->point_const = h->ptr_point_const;
+  h->pose_mask.resize(h->n_frames, 0);
+  h->point_const.resize(h->n_points, 0);
+  h->ptr_dirty = false;
+  return RSBA_OK;
+}
+
+int gather_pointer_parameters(rsba_problem* h) {
+  std::vector<double> poses((size_t)kFrameParams * h->n_frames), points((size_t)kPointParams * h->n_points);
+  for (int f = 0; f < h->n_frames; ++f) {
+    memcpy(&poses[(size_t)12 * f], h->frame_pose0[f], 6 * sizeof(double));
+    memcpy(&poses[(size_t)12 * f + 6], h->frame_pose1[f], 6 * sizeof(double));
+  }
+  for (int p = 0; p < h->n_points; ++p) memcpy(&points[(size_t)3 * p], h->point_ptr[p], 3 * sizeof(double));
+  return rsba_cuda_set_parameters(h, poses.data(), points.data());
+}
+
+int scatter_pointer_parameters(rsba_problem* h) {
+  std::vector<double> poses((size_t)kFrameParams * h->n_frames), points((size_t)kPointParams * h->n_points);
+  int rc = rsba_cuda_get_parameters(h, poses.data(), points.data());
+  if (rc) return rc;
+  for (int f = 0; f < h->n_frames; ++f) {
+    memcpy(h->frame_pose0[f], &poses[(size_t)12 * f], 6 * sizeof(double));
+    memcpy(h->frame_pose1[f], &poses[(size_t)12 * f + 6], 6 * sizeof(double));
+  }
+  for (int p = 0; p < h->n_points; ++p) memcpy(h->point_ptr[p], &points[(size_t)3 * p], 3 * sizeof(double));
+  return RSBA_OK;
+}
+
+}  // namespace rsba
+
+using namespace rsba;
+
+extern "C" {
+
+const char* rsba_cuda_last_error(void) { return g_last_error.c_str(); }
+const char* rsba_cuda_version(void) { return "rsba_b200 0.1 (sm_100a)"; }
+
+int rsba_cuda_create(rsba_problem** out, int device) {
+  if (!out) return fail(RSBA_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(RSBA_ERR_NO_DEVICE, "no CUDA device: rsba_cuda has no CPU fallback");
+  }
+  if (device < 0 || device >= count) return fail(RSBA_ERR_INVALID_ARGUMENT, "device index out of range");
+  RSBA_CUDA_TRY(cudaSetDevice(device));
+  rsba_problem* h = new rsba_problem;
+  h->device = device;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+  }
+  h->own_stream = true;
+  *out = h;
+  return RSBA_OK;
+}
+
+void rsba_cuda_destroy(rsba_problem* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (h->lm) lm_state_free(h->lm);
+  for (auto& t : h->timers) {
+    if (t.beg) cudaEventDestroy(t.beg);
+    if (t.end) cudaEventDestroy(t.end);
+  }
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int rsba_cuda_set_stream(rsba_problem* h, void* cuda_stream) {
+  if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
+  cudaStreamSynchronize(h->stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)cuda_stream;
+  h->own_stream = false;
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter, const int scanlines[2],
+                         int interpolate_rotation) {
+  if (!h || !cam9 || !scanlines) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (shutter < 0 || shutter > 2) return fail(RSBA_ERR_INVALID_ARGUMENT, "shutter must be 0, 1 or 2");
+  memcpy(h->cm.cam, cam9, sizeof(h->cm.cam));
+  h->cm.shutter = shutter;
+  h->cm.scan0 = (double)scanlines[0];
+  h->cm.scan_span = (double)(scanlines[1] - scanlines[0]);
+  h->cm.interp_rot = interpolate_rotation ? 1 : 0;
+  h->camera_set = true;
+  return RSBA_OK;
+}
+
+int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0, double* pose1,
+                              double* point) {
+  if (!h || !observed || !pose0 || !pose1 || !point) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
+  h->ptr_mode = true;
+  int f;
+  auto it = h->pose0_to_frame.find(pose0);
+  if (it == h->pose0_to_frame.end()) {
+    if (h->pose1_to_frame.count(pose1) || h->pose0_to_frame.count(pose1) || h->pose1_to_frame.count(pose0))
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "pose block already paired with a different frame");
+    f = (int)h->frame_pose0.size();
+    h->pose0_to_frame[pose0] = f;
+    h->pose1_to_frame[pose1] = f;
+    h->frame_pose0.push_back(pose0);
+    h->frame_pose1.push_back(pose1);
+    h->ptr_pose_mask.push_back(0);
+  } else {
+    f = it->second;
+    if (h->frame_pose1[f] != pose1)
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "pose0 block already paired with a different pose1 block");
+  }
+  int p;
+  auto ip = h->point_to_id.find(point);
+  if (ip == h->point_to_id.end()) {
+    p = (int)h->point_ptr.size();
+    h->point_to_id[point] = p;
+    h->point_ptr.push_back(point);
+    h->ptr_point_const.push_back(0);
+  } else {
+    p = ip->second;
+  }
+  h->ptr_obs.push_back({observed[0], observed[1], f, p});
+  h->ptr_dirty = true;
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_block_constant(rsba_problem* h, double* block) {
+  if (!h || !block) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  auto a = h->pose0_to_frame.find(block);
+  if (a != h->pose0_to_frame.end()) { h->ptr_pose_mask[a->second] |= 0x03F; h->ptr_dirty = true; return RSBA_OK; }
+  auto b = h->pose1_to_frame.find(block);
+  if (b != h->pose1_to_frame.end()) { h->ptr_pose_mask[b->second] |= 0xFC0; h->ptr_dirty = true; return RSBA_OK; }
+  auto c = h->point_to_id.find(block);
+  if (c != h->point_to_id.end()) { h->ptr_point_const[c->second] = 1; h->ptr_dirty = true; return RSBA_OK; }
+  return fail(RSBA_ERR_INVALID_ARGUMENT, "unknown parameter block (Ceres would abort here too)");
+}
+
+int rsba_cuda_set_subset_constant(rsba_problem* h, double* pose_block, int n_constant,
+                                  const int* constant_components) {
+  if (!h || !pose_block || (n_constant > 0 && !constant_components))
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  int shift, f;
+  auto a = h->pose0_to_frame.find(pose_block);
+  if (a != h->pose0_to_frame.end()) { f = a->second; shift = 0; }
+  else {
+    auto b = h->pose1_to_frame.find(pose_block);
+    if (b == h->pose1_to_frame.end()) return fail(RSBA_ERR_INVALID_ARGUMENT, "unknown pose block");
+    f = b->second; shift = 6;
+  }
+  for (int i = 0; i < n_constant; ++i) {
+    if (constant_components[i] < 0 || constant_components[i] >= 6)
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "constant component out of range");
+    h->ptr_pose_mask[f] |= (unsigned short)(1u << (shift + constant_components[i]));
+  }
+  h->ptr_dirty = true;
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_scene(rsba_problem* h, long n_obs, const double* obs_xy, const int* obs_frame,
+                        const int* obs_point, int n_frames, int n_points,
+                        const unsigned short* const_pose_mask, const unsigned char* const_point) {
+  if (!h || n_obs < 0 || n_frames < 0 || n_points < 0 || (n_obs > 0 && (!obs_xy || !obs_frame || !obs_point)))
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "bad scene arguments");
+  if (h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds pointer-API residual blocks");
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  int rc = upload_scene(h, n_obs, obs_xy, obs_frame, obs_point, n_frames, n_points);
+  if (rc) return rc;
+  h->pose_mask.assign(n_frames, 0);
+  h->point_const.assign(n_points, 0);
+  if (const_pose_mask) for (int f = 0; f < n_frames; ++f) h->pose_mask[f] = const_pose_mask[f] & 0xFFF;
+  if (const_point) for (int p = 0; p < n_points; ++p) h->point_const[p] = const_point[p] ? 1 : 0;
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_parameters(rsba_problem* h, const double* poses, const double* points) {
+  if (!h || !h->scene_set) return fail(RSBA_ERR_STATE, "no scene");
+  if ((h->n_frames && !poses) || (h->n_points && !points)) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  if (h->n_frames)
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr, poses, h->d_poses.bytes(), cudaMemcpyHostToDevice, h->stream));
+  if (h->n_points)
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_points.ptr, points, h->d_points.bytes(), cudaMemcpyHostToDevice, h->stream));
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->params_set = true;
+  return RSBA_OK;
+}
+
+int rsba_cuda_get_parameters(rsba_problem* h, double* poses, double* points) {
+  if (!h || !h->scene_set || !h->params_set) return fail(RSBA_ERR_STATE, "no parameters on the device");
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  if (poses && h->n_frames)
+    RSBA_CUDA_TRY(cudaMemcpyAsync(poses, h->d_poses.ptr, h->d_poses.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  if (points && h->n_points)
+    RSBA_CUDA_TRY(cudaMemcpyAsync(points, h->d_points.ptr, h->d_points.bytes(), cudaMemcpyDeviceToHost, h->stream));
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return RSBA_OK;
+}
+
+static int prepare(rsba_problem* h) {
+  if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
+  if (!h->camera_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_camera has not been called");
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  if (h->ptr_mode) {
+    int rc = finalize_pointer_problem(h);
+    if (rc) return rc;
+    rc = gather_pointer_parameters(h);
+    if (rc) return rc;
+  }
+  if (!h->scene_set) return fail(RSBA_ERR_STATE, "no residual blocks");
+  if (!h->params_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_parameters has not been called");
+  return RSBA_OK;
+}
+
+int rsba_cuda_evaluate_device(rsba_problem* h, int with_jacobian, double* cost, long* num_invalid) {
+  int rc = prepare(h);
+  if (rc) return rc;
+  return run_evaluate(h, with_jacobian != 0, h->d_poses.ptr, h->d_points.ptr, cost, num_invalid);
+}
+
+int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double* jacobian,
+                       unsigned char* valid) {
+  int rc = prepare(h);
+  if (rc) return rc;
+  const bool jac = jacobian != nullptr;
+  long bad = 0;
+  double c = 0.0;
+  rc = run_evaluate(h, jac || residuals || valid, h->d_poses.ptr, h->d_points.ptr, &c, &bad);
+  if (rc) return rc;
+  if (cost) *cost = c;
+  const long n = h->n_obs;
+  // outputs go back in the caller's observation order
+  bool identity = true;
+  for (long i = 0; i < n && identity; ++i) identity = h->order[i] == i;
+  if (residuals && n) {
+    if (identity) {
+      RSBA_CUDA_TRY(cudaMemcpy(residuals, h->d_res.ptr, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<double> tmp(2 * n);
+      RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_res.ptr, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+      for (long i = 0; i < n; ++i) memcpy(residuals + 2 * h->order[i], &tmp[2 * i], 2 * sizeof(double));
+    }
+  }
+  if (jacobian && n) {
+    if (identity) {
+      RSBA_CUDA_TRY(cudaMemcpy(jacobian, h->d_jac.ptr, (size_t)kJacDoubles * n * sizeof(double), cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<double> tmp((size_t)kJacDoubles * n);
+      RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_jac.ptr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (long i = 0; i < n; ++i)
+        memcpy(jacobian + (size_t)kJacDoubles * h->order[i], &tmp[(size_t)kJacDoubles * i], kJacDoubles * sizeof(double));
+    }
+  }
+  if (valid && n) {
+    if (identity) {
+      RSBA_CUDA_TRY(cudaMemcpy(valid, h->d_valid.ptr, n, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<unsigned char> tmp(n);
+      RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_valid.ptr, n, cudaMemcpyDeviceToHost));
+      for (long i = 0; i < n; ++i) valid[h->order[i]] = tmp[i];
+    }
+  }
+  if (bad > 0) return fail(RSBA_ERR_EVALUATION_FAILED, "a cost functor returned false (point behind camera)");
+  return RSBA_OK;
+}
+
+int rsba_cuda_device_buffers(rsba_problem* h, void** residuals, void** jacobian, void** valid,
+                             void** poses, void** points) {
+  if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
+  if (residuals) *residuals = h->d_res.ptr;
+  if (jacobian) *jacobian = h->d_jac.ptr;
+  if (valid) *valid = h->d_valid.ptr;
+  if (poses) *poses = h->d_poses.ptr;
+  if (points) *points = h->d_points.ptr;
+  return RSBA_OK;
+}
+
+long rsba_cuda_observation_order(rsba_problem* h, long* order) {
+  if (!h) return -1;
+  if (order) memcpy(order, h->order.data(), h->order.size() * sizeof(long));
+  return (long)h->order.size();
+}
+
+long rsba_cuda_launch_count(rsba_problem* h) { return h ? h->launches : 0; }
+
+double rsba_cuda_stage_ms(rsba_problem* h, int stage) {
+  if (!h || stage < 0 || stage >= kNumStages) return -1.0;
+  return stage_collect(h, (Stage)stage);
+}
+
+void rsba_cuda_default_options(rsba_solve_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 50;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->jacobi_scaling = 1;
+  o->huber_loss = 0.0;
+  o->verbose = 0;
+  o->dense_cholesky = 0;
+}
+
+}  // extern "C"

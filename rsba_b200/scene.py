@@ -219,6 +219,35 @@ def make_scene(num_frames: int, num_points: int, obs_per_point: int, seed: int =
                        "noise_px": noise_px, "image": [IMAGE_W, IMAGE_H]})
 
 
-def make_config(name: str, **kw) -> Scene:
+def make_config(name: str, cache: bool = True, **kw) -> Scene:
+    """BASELINE.json config by name.  Large scenes are cached as .npz under
+    $RSBA_SCENE_CACHE (default /tmp/rsba_scene_cache): generation is deterministic."""
+    import os
     F, P, K = CONFIGS[name]
-    return make_scene(F, P, K, name=name, **kw)
+    if kw or not cache or F * P < 1_000_000:
+        return make_scene(F, P, K, name=name, **kw)
+    d = os.environ.get("RSBA_SCENE_CACHE", "/tmp/rsba_scene_cache")
+    path = os.path.join(d, f"{name}_seed{SEED}.npz")
+    if os.path.exists(path):
+        try:
+            g = np.load(path)
+            return Scene(cam=g["cam"], shutter=int(g["shutter"]), scanlines=g["scanlines"],
+                         interpolate_rotation=bool(g["interpolate_rotation"]), poses=g["poses"],
+                         points=g["points"], obs_xy=g["obs_xy"], obs_frame=g["obs_frame"],
+                         obs_point=g["obs_point"], const_frames=g["const_frames"],
+                         poses_true=g["poses_true"], points_true=g["points_true"], name=name,
+                         meta={"seed": SEED, "frames": F, "points": P, "obs_per_point": K})
+        except Exception:
+            pass
+    sc = make_scene(F, P, K, name=name)
+    try:
+        os.makedirs(d, exist_ok=True)
+        tmp = path + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, cam=sc.cam, shutter=np.int32(sc.shutter), scanlines=sc.scanlines,
+                 interpolate_rotation=np.int32(sc.interpolate_rotation), poses=sc.poses, points=sc.points,
+                 obs_xy=sc.obs_xy, obs_frame=sc.obs_frame, obs_point=sc.obs_point,
+                 const_frames=sc.const_frames, poses_true=sc.poses_true, points_true=sc.points_true)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return sc

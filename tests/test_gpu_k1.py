@@ -1,0 +1,143 @@
+"""GPU parity tests for K1 (residual + Jacobian) and K1r (cost only), through the C ABI.
+
+Bar (BASELINE.json north_star): residuals and Jacobians within 1e-6 relative of the
+reference CPU path on identical inputs; valid bits exact.  The checker is the oracle
+(port; oracle/_ref too when its prebuilt .so travelled) and the committed golden vectors.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_block_err
+from helpers import edge_scene, shuffled, small_scene
+from test_oracle_cpu import GOLDEN, scene_from_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6  # relative, north_star
+
+
+@pytest.fixture(scope="module")
+def api():
+    import rsba_b200.api as api
+    api.load_library()
+    return api
+
+
+def gpu_eval(api, sc, **kw):
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        return pb.evaluate(check=False, **kw)
+
+
+def check(sc, got, want, tol=TOL):
+    cost, r, J, v = got
+    r0, J0, v0 = want
+    assert np.array_equal(v, v0), "valid bits differ"
+    ok = v0 == 1
+    assert (np.abs(r - r0) / np.maximum(1.0, np.abs(r0)))[ok].max(initial=0) <= tol
+    if J is not None:
+        assert rel_block_err(J[ok], J0[ok]).max(initial=0) <= tol
+        assert not J[~ok].any()
+    assert not r[~ok].any()
+    want_cost = 0.5 * np.sum(r0[ok] ** 2)
+    assert abs(cost - want_cost) <= 1e-9 * max(1.0, abs(want_cost))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_k1_matches_reference_golden(api, path):
+    sc, g = scene_from_golden(path)
+    check(sc, gpu_eval(api, sc), (g["residuals"], g["jacobian"], g["valid"]))
+
+
+def test_k1_c1_vs_oracle(api, oracle_built):
+    sc = small_scene()
+    want = oracle_built.evaluate(sc, impl="port")
+    check(sc, gpu_eval(api, sc), want)
+    if oracle_built.ref_available():
+        check(sc, gpu_eval(api, sc), oracle_built.evaluate(sc, impl="ref"))
+
+
+@pytest.mark.parametrize("shutter,interp", [(0, True), (1, True), (1, False), (2, True)])
+def test_k1_edge_cases_vs_oracle(api, oracle_built, shutter, interp):
+    sc = edge_scene(shutter, interp)
+    check(sc, gpu_eval(api, sc), oracle_built.evaluate(sc, impl="port"))
+
+
+def test_k1_unsorted_input_is_reported_in_caller_order(api, oracle_built):
+    sc = shuffled(small_scene())
+    check(sc, gpu_eval(api, sc), oracle_built.evaluate(sc, impl="port"))
+
+
+def test_k1_ragged_and_empty(api, oracle_built):
+    from rsba_b200.scene import Scene
+    sc = small_scene()
+    for n in (1, 31, 32, 33, 127, 129, 1000):
+        sub = Scene(**{**sc.__dict__, "obs_xy": sc.obs_xy[:n], "obs_frame": sc.obs_frame[:n],
+                       "obs_point": sc.obs_point[:n]})
+        check(sub, gpu_eval(api, sub), oracle_built.evaluate(sub, impl="port"))
+    with api.Problem(0) as pb:                       # empty problem: cost 0, nothing written
+        pb.set_camera(sc.cam, sc.shutter, sc.scanlines, True)
+        pb.set_scene(np.zeros((0, 2)), np.zeros(0, np.int32), np.zeros(0, np.int32), sc.num_frames, sc.num_points)
+        pb.set_parameters(sc.poses, sc.points)
+        cost, r, J, v = pb.evaluate()
+        assert cost == 0.0 and r.shape == (0, 2)
+
+
+def test_k1_wide_frame_span_uses_global_pose_path(api, oracle_built):
+    """More than 8 frames inside one 128-observation CTA: poses come through L1, not smem."""
+    from rsba_b200.scene import make_scene
+    sc = make_scene(64, 64, 40, name="thin")         # 40 obs per frame
+    check(sc, gpu_eval(api, sc), oracle_built.evaluate(sc, impl="port"))
+
+
+def test_k1r_cost_matches_k1(api, oracle_built):
+    sc = small_scene()
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        c_full, bad_full = pb.evaluate_device(with_jacobian=True)
+        c_res, bad_res = pb.evaluate_device(with_jacobian=False)
+    r0, _, _ = oracle_built.evaluate(sc, impl="port", jac=False)
+    assert bad_full == 0 and bad_res == 0
+    assert c_full == c_res
+    assert abs(c_res - 0.5 * np.sum(r0 ** 2)) <= 1e-9 * c_res
+
+
+def test_k1_pointer_api_matches_bulk(api, oracle_built):
+    """AddResidualBlock-style construction (CeresHandler.h:250-255): block identity is the
+    pointer; insertion order frame-major; results identical to the bulk path."""
+    sc = small_scene()
+    n = 1500
+    poses, points = sc.poses.copy(), sc.points.copy()
+    with api.Problem(0) as pb:
+        pb.set_camera(sc.cam, sc.shutter, sc.scanlines, sc.interpolate_rotation)
+        used_pts = {}
+        for i in range(n):
+            f, p = int(sc.obs_frame[i]), int(sc.obs_point[i])
+            pb.add_rs_residual(sc.obs_xy[i], poses[f, :6], poses[f, 6:], points[p])
+            used_pts[p] = 1
+        pb.set_block_constant(poses[0, :6])
+        pb.set_block_constant(poses[0, 6:])
+        cost, r, J, v = pb.evaluate(num_obs=n)
+    from rsba_b200.scene import Scene
+    sub = Scene(**{**sc.__dict__, "obs_xy": sc.obs_xy[:n], "obs_frame": sc.obs_frame[:n], "obs_point": sc.obs_point[:n]})
+    check(sub, (cost, r, J, v), oracle_built.evaluate(sub, impl="port"))
+
+
+def test_k1_full_size_properties(api, oracle_built):
+    """BASELINE config C2 (100 frames / 20k points / 500k obs): spot-check 4 096 random
+    observations against the oracle, the F3 structure J_pose1*(1-tau) == J_pose0*tau on all of
+    them, and cost == 1/2 sum r^2 of the returned residuals."""
+    from rsba_b200.scene import Scene, make_config
+    sc = make_config("C2")
+    cost, r, J, v = gpu_eval(api, sc)
+    assert v.all()
+    assert abs(cost - 0.5 * np.sum(r * r)) <= 1e-10 * cost
+    tau = np.clip(sc.obs_xy[:, 0] / 1280.0, 0, 1)[:, None]
+    assert np.allclose(J[:, 12:24] * (1 - tau), J[:, :12] * tau, rtol=1e-9, atol=1e-9)
+    idx = np.sort(np.random.default_rng(5).choice(sc.num_obs, 4096, replace=False))
+    sub = Scene(**{**sc.__dict__, "obs_xy": sc.obs_xy[idx], "obs_frame": sc.obs_frame[idx], "obs_point": sc.obs_point[idx]})
+    r0, J0, v0 = oracle_built.evaluate(sub, impl="port")
+    assert (np.abs(r[idx] - r0) / np.maximum(1.0, np.abs(r0))).max() <= TOL
+    assert rel_block_err(J[idx], J0).max() <= TOL
