@@ -1,0 +1,390 @@
+// K2 -- block normal equations and the Schur complement on the point blocks, FP64.
+//
+// Supersedes Ceres' SchurEliminator::Eliminate (third-party, reached through ceres::Solve with
+// linear_solver_type = SPARSE_SCHUR, CeresHandler.h:403,419).  Input is the per-observation
+// Jacobian written by K1 ([N][30] = J_pose0[2][6] | J_pose1[2][6] | J_point[2][3]) and the
+// residuals.  A "frame" is the 12-wide camera block pose0|pose1; every observation couples
+// one frame with one point, so
+//   B_f  = sum_{i in f} Jc_i^T Jc_i        12x12   (frame_blocks)
+//   C_p  = sum_{i in p} Jx_i^T Jx_i         3x3    (point_blocks)
+//   S_ab = [a==b](s B s + D^2) - s_a ( sum_{p seen by a and b} Jc_i^T (Jx_i Cinv_p Jx_j^T) Jc_j ) s_b
+// with Cinv_p = s_p (s_p C_p s_p + D_p^2)^-1 s_p inverted in registers (3x3 Cholesky).  The
+// 2x2 middle factor keeps the pair term at K = 2 instead of materialising the 12x3 E blocks.
+// Jacobi scaling s and the LM diagonal D^2 = clamp(diag)/radius follow
+// LevenbergMarquardtStrategy::ComputeStep / TrustRegionMinimizer (Ceres 1.9.0).
+//
+// Every output element is produced by exactly one thread in a fixed summation order: the
+// normal equations are bit-reproducible from run to run (no floating-point atomics).
+#include "lm.cuh"
+
+namespace rsba {
+namespace {
+
+constexpr int kChunk = 128;        // observations per frame chunk (host builds the chunk table)
+constexpr int kPartial = 168;      // 144 (B) + 12 (gc) + 12 (wf)
+
+// offset of columns 3*t .. 3*t+2 (t = 0..3) of camera row `row` inside a 30-double record
+__device__ __forceinline__ int jc_off(int t, int row) { return ((t & 2) ? 12 : 0) + row * 6 + (t & 1) * 3; }
+
+// ---------------------------------------------------------------- points: C_p, g_p
+__global__ void __launch_bounds__(128)
+point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
+                    const double* __restrict__ jac, const double* __restrict__ res, int n_points,
+                    double* __restrict__ C, double* __restrict__ gp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, g0 = 0, g1 = 0, g2 = 0;
+  const int beg = pt_ptr[p], end = pt_ptr[p + 1];
+  for (int e = beg; e < end; ++e) {
+    const long i = pt_obs[e];
+    const double2* jx = reinterpret_cast<const double2*>(jac + i * kJacDoubles + 24);
+    const double2 q0 = jx[0], q1 = jx[1], q2 = jx[2];   // row0: q0.x q0.y q1.x ; row1: q1.y q2.x q2.y
+    const double2 r = reinterpret_cast<const double2*>(res)[i];
+    const double a0 = q0.x, a1 = q0.y, a2 = q1.x, b0 = q1.y, b1 = q2.x, b2 = q2.y;
+    c0 += a0 * a0 + b0 * b0;
+    c1 += a0 * a1 + b0 * b1;
+    c2 += a0 * a2 + b0 * b2;
+    c3 += a1 * a1 + b1 * b1;
+    c4 += a1 * a2 + b1 * b2;
+    c5 += a2 * a2 + b2 * b2;
+    g0 += a0 * r.x + b0 * r.y;
+    g1 += a1 * r.x + b1 * r.y;
+    g2 += a2 * r.x + b2 * r.y;
+  }
+  double* Cp = C + 6L * p;
+  Cp[0] = c0; Cp[1] = c1; Cp[2] = c2; Cp[3] = c3; Cp[4] = c4; Cp[5] = c5;
+  double* g = gp + 3L * p;
+  g[0] = g0; g[1] = g1; g[2] = g2;
+}
+
+__global__ void point_scale_kernel(int n_points, const double* __restrict__ C,
+                                   const unsigned char* __restrict__ point_const, int enabled,
+                                   double* __restrict__ scale_p) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  const bool cst = point_const[p] != 0;
+  const double* Cp = C + 6L * p;
+  const double d[3] = {Cp[0], Cp[3], Cp[5]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) scale_p[3L * p + k] = (cst || !enabled) ? 1.0 : 1.0 / (1.0 + sqrt(d[k]));
+}
+
+__global__ void frame_scale_kernel(int n_frames, const double* __restrict__ B,
+                                   const unsigned short* __restrict__ pose_mask, int enabled,
+                                   double* __restrict__ scale_c) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_frames * kFrameParams) return;
+  const int f = t / kFrameParams, k = t % kFrameParams;
+  const bool cst = (pose_mask[f] >> k) & 1;
+  scale_c[t] = (cst || !enabled) ? 1.0 : 1.0 / (1.0 + sqrt(B[(long)f * 144 + k * 13]));
+}
+
+// ---------------------------------------------------------------- points: damped inverse
+__global__ void __launch_bounds__(128)
+point_invert_kernel(int n_points, NormalEq ne, LmOptionsDev o) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_points) return;
+  double* Ci = ne.Cinv + 6L * p;
+  double* t = ne.tp + 3L * p;
+  double* d2 = ne.d2_p + 3L * p;
+  if (ne.point_const[p]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Ci[k] = 0.0;
+    t[0] = t[1] = t[2] = 0.0;
+    d2[0] = d2[1] = d2[2] = 1.0;
+    return;
+  }
+  const double* Cp = ne.C + 6L * p;
+  const double s0 = ne.scale_p[3L * p], s1 = ne.scale_p[3L * p + 1], s2 = ne.scale_p[3L * p + 2];
+  double c00 = s0 * Cp[0] * s0, c10 = s1 * Cp[1] * s0, c20 = s2 * Cp[2] * s0;
+  double c11 = s1 * Cp[3] * s1, c21 = s2 * Cp[4] * s1, c22 = s2 * Cp[5] * s2;
+  const double e0 = fmin(fmax(c00, o.min_diag), o.max_diag) / o.radius;
+  const double e1 = fmin(fmax(c11, o.min_diag), o.max_diag) / o.radius;
+  const double e2 = fmin(fmax(c22, o.min_diag), o.max_diag) / o.radius;
+  d2[0] = e0; d2[1] = e1; d2[2] = e2;
+  c00 += e0; c11 += e1; c22 += e2;
+  // 3x3 Cholesky C' = L L^T, M = L^-1, C'^-1 = M^T M  (all in registers)
+  const double l00 = sqrt(c00);
+  const double m00 = 1.0 / l00;
+  const double l10 = c10 * m00, l20 = c20 * m00;
+  const double l11 = sqrt(c11 - l10 * l10);
+  const double m11 = 1.0 / l11;
+  const double l21 = (c21 - l20 * l10) * m11;
+  const double l22 = sqrt(c22 - l20 * l20 - l21 * l21);
+  const double m22 = 1.0 / l22;
+  const double m10 = -l10 * m00 * m11;
+  const double m21 = -l21 * m11 * m22;
+  const double m20 = -(l20 * m00 + l21 * m10) * m22;
+  // inverse (scaled space), then fold the point scaling back in: Cinv'' = s Cinv' s
+  const double i00 = (m00 * m00 + m10 * m10 + m20 * m20) * s0 * s0;
+  const double i10 = (m10 * m11 + m20 * m21) * s1 * s0;
+  const double i20 = (m20 * m22) * s2 * s0;
+  const double i11 = (m11 * m11 + m21 * m21) * s1 * s1;
+  const double i21 = (m21 * m22) * s2 * s1;
+  const double i22 = (m22 * m22) * s2 * s2;
+  Ci[0] = i00; Ci[1] = i10; Ci[2] = i20; Ci[3] = i11; Ci[4] = i21; Ci[5] = i22;
+  const double* g = ne.gp + 3L * p;
+  t[0] = i00 * g[0] + i10 * g[1] + i20 * g[2];
+  t[1] = i10 * g[0] + i11 * g[1] + i21 * g[2];
+  t[2] = i20 * g[0] + i21 * g[1] + i22 * g[2];
+}
+
+// ---------------------------------------------------------------- frames: B_f, g_c, w_f
+// One CTA per chunk (<= 128 observations of one frame).  Thread (grp, tr, tc) owns the 3x3
+// tile (tr, tc) of the 12x12 block over the observations grp, grp+8, ...
+__global__ void __launch_bounds__(128)
+frame_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac,
+                    const double* __restrict__ res, NormalEq ne, int with_wf) {
+  __shared__ __align__(16) double sJ[kChunk * kJacDoubles];  // raw records
+  __shared__ double sR[kChunk * 2];
+  __shared__ double sQ[kChunk * 2];                            // Jx_i t_p
+  const int c = blockIdx.x;
+  const long beg = st.chunk_beg[c];
+  const int cnt = st.chunk_cnt[c];
+  {
+    const double2* src = reinterpret_cast<const double2*>(jac + beg * kJacDoubles);
+    double2* dst = reinterpret_cast<double2*>(sJ);
+    for (int k = threadIdx.x; k < cnt * (kJacDoubles / 2); k += blockDim.x) dst[k] = src[k];
+    for (int k = threadIdx.x; k < cnt * 2; k += blockDim.x) sR[k] = res[beg * 2 + k];
+  }
+  __syncthreads();
+  if (threadIdx.x < cnt) {
+    double q0 = 0.0, q1 = 0.0;
+    if (with_wf) {
+      const int p = obs.point[beg + threadIdx.x];
+      const double* t = ne.tp + 3L * p;
+      const double* jx = sJ + threadIdx.x * kJacDoubles + 24;
+      q0 = jx[0] * t[0] + jx[1] * t[1] + jx[2] * t[2];
+      q1 = jx[3] * t[0] + jx[4] * t[1] + jx[5] * t[2];
+    }
+    sQ[2 * threadIdx.x] = q0;
+    sQ[2 * threadIdx.x + 1] = q1;
+  }
+  __syncthreads();
+  const int grp = threadIdx.x >> 4, tp = threadIdx.x & 15, tr = tp >> 2, tc = tp & 3;
+  double acc[9], ga[3], wa[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  ga[0] = ga[1] = ga[2] = wa[0] = wa[1] = wa[2] = 0.0;
+  for (int o = grp; o < cnt; o += 8) {
+    const double* rec = sJ + o * kJacDoubles;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      const double* pa = rec + jc_off(tr, row);
+      const double* pb = rec + jc_off(tc, row);
+      const double a0 = pa[0], a1 = pa[1], a2 = pa[2];
+      const double b0 = pb[0], b1 = pb[1], b2 = pb[2];
+      acc[0] += a0 * b0; acc[1] += a0 * b1; acc[2] += a0 * b2;
+      acc[3] += a1 * b0; acc[4] += a1 * b1; acc[5] += a1 * b2;
+      acc[6] += a2 * b0; acc[7] += a2 * b1; acc[8] += a2 * b2;
+      if (tc == 0) {
+        const double r = sR[2 * o + row], q = sQ[2 * o + row];
+        ga[0] += a0 * r; ga[1] += a1 * r; ga[2] += a2 * r;
+        wa[0] += a0 * q; wa[1] += a1 * q; wa[2] += a2 * q;
+      }
+    }
+  }
+  __syncthreads();                 // sJ is dead: reuse it for the cross-group reduction
+  double* sAcc = sJ;               // [8][16][15]
+  double* my = sAcc + (grp * 16 + tp) * 15;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) my[k] = acc[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { my[9 + k] = ga[k]; my[12 + k] = wa[k]; }
+  __syncthreads();
+  // fixed-order sum over the 8 groups -> chunk partial
+  double* out = ne.partials + (long)c * kPartial;
+  for (int k = threadIdx.x; k < kPartial; k += blockDim.x) {
+    int tpos, slot;
+    if (k < 144) {
+      const int r = k / 12, cc = k % 12;
+      tpos = (r / 3) * 4 + (cc / 3);
+      slot = (r % 3) * 3 + (cc % 3);
+    } else if (k < 156) {
+      const int r = k - 144;
+      tpos = (r / 3) * 4;
+      slot = 9 + r % 3;
+    } else {
+      const int r = k - 156;
+      tpos = (r / 3) * 4;
+      slot = 12 + r % 3;
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += sAcc[(g * 16 + tpos) * 15 + slot];
+    out[k] = s;
+  }
+}
+
+__global__ void __launch_bounds__(192)
+frame_reduce_kernel(SchurStructure st, NormalEq ne, int n_frames) {
+  const int f = blockIdx.x;
+  const int k = threadIdx.x;
+  if (f >= n_frames || k >= kPartial) return;
+  double s = 0.0;
+  for (int c = st.frame_chunk_ptr[f]; c < st.frame_chunk_ptr[f + 1]; ++c) s += ne.partials[(long)c * kPartial + k];
+  if (k < 144) ne.B[(long)f * 144 + k] = s;
+  else if (k < 156) ne.gc[(long)f * 12 + (k - 144)] = s;
+  else ne.wf[(long)f * 12 + (k - 156)] = s;
+}
+
+// ---------------------------------------------------------------- Schur complement blocks
+// Half a warp per camera-pair block (a <= b).  Phase 1: each lane turns one (i, j) pair into
+// u = Jc_i^T (Jx_i Cinv_p Jx_j^T)  (12x2) and v = Jc_j (2x12) in shared memory.  Phase 2: lane
+// (tr, tc) accumulates its 3x3 tile of  sum_e u_e v_e.
+constexpr int kSchurThreads = 64;
+constexpr int kUVStride = 25;  // 24 doubles + 1 pad: conflict-free per-lane rows
+
+__global__ void __launch_bounds__(kSchurThreads)
+schur_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne,
+                    LmOptionsDev o, double* __restrict__ S, const int* __restrict__ tile_slot, int T,
+                    double* __restrict__ rhs) {
+  __shared__ double sU[(kSchurThreads / 16) * 16 * kUVStride];
+  __shared__ double sV[(kSchurThreads / 16) * 16 * kUVStride];
+  const int half = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const int blk = blockIdx.x * (kSchurThreads / 16) + half;
+  const bool live = blk < st.n_blocks;
+  const int a = live ? st.blk_a[blk] : 0, b = live ? st.blk_b[blk] : 0;
+  const long beg = live ? st.blk_ptr[blk] : 0, end = live ? st.blk_ptr[blk + 1] : 0;
+  double* U = sU + half * 16 * kUVStride;
+  double* V = sV + half * 16 * kUVStride;
+  const int tr = hl >> 2, tc = hl & 3;
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+
+  for (long base = beg; base < end; base += 16) {
+    const long e = base + hl;
+    double* u = U + hl * kUVStride;
+    double* v = V + hl * kUVStride;
+    if (e < end) {
+      const int2 ij = st.entries[e];
+      const double2* Ji = reinterpret_cast<const double2*>(jac + (long)ij.x * kJacDoubles);
+      const double2* Jj = reinterpret_cast<const double2*>(jac + (long)ij.y * kJacDoubles);
+      const int p = obs.point[ij.x];
+      const double* Ci = ne.Cinv + 6L * p;
+      const double2 xi0 = Ji[12], xi1 = Ji[13], xi2 = Ji[14];   // Jx_i rows: (xi0.x xi0.y xi1.x) (xi1.y xi2.x xi2.y)
+      const double2 xj0 = Jj[12], xj1 = Jj[13], xj2 = Jj[14];
+      const double i00 = Ci[0], i10 = Ci[1], i20 = Ci[2], i11 = Ci[3], i21 = Ci[4], i22 = Ci[5];
+      // T = Jx_i Cinv (2x3)
+      const double t00 = xi0.x * i00 + xi0.y * i10 + xi1.x * i20;
+      const double t01 = xi0.x * i10 + xi0.y * i11 + xi1.x * i21;
+      const double t02 = xi0.x * i20 + xi0.y * i21 + xi1.x * i22;
+      const double t10 = xi1.y * i00 + xi2.x * i10 + xi2.y * i20;
+      const double t11 = xi1.y * i10 + xi2.x * i11 + xi2.y * i21;
+      const double t12 = xi1.y * i20 + xi2.x * i21 + xi2.y * i22;
+      // W = T Jx_j^T (2x2)
+      const double w00 = t00 * xj0.x + t01 * xj0.y + t02 * xj1.x;
+      const double w01 = t00 * xj1.y + t01 * xj2.x + t02 * xj2.y;
+      const double w10 = t10 * xj0.x + t11 * xj0.y + t12 * xj1.x;
+      const double w11 = t10 * xj1.y + t11 * xj2.x + t12 * xj2.y;
+      // u[c][r'] = Jc_i[0][c] W[0][r'] + Jc_i[1][c] W[1][r'];  Jc_i[row][c]: record offsets
+      // c<6: row*6+c ; c>=6: 12+row*6+(c-6)  -> as double2 pairs
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {        // pose0 / pose1 halves
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {         // column pairs
+          const double2 r0 = Ji[h2 * 6 + q];        // row 0, columns 2q, 2q+1 of this half
+          const double2 r1 = Ji[h2 * 6 + 3 + q];    // row 1
+          const int cidx = h2 * 6 + 2 * q;
+          u[cidx * 2 + 0] = r0.x * w00 + r1.x * w10;
+          u[cidx * 2 + 1] = r0.x * w01 + r1.x * w11;
+          u[cidx * 2 + 2] = r0.y * w00 + r1.y * w10;
+          u[cidx * 2 + 3] = r0.y * w01 + r1.y * w11;
+          const double2 s0 = Jj[h2 * 6 + q];
+          const double2 s1 = Jj[h2 * 6 + 3 + q];
+          v[cidx] = s0.x;      v[cidx + 1] = s0.y;        // v[r'][c] at r'*12 + c
+          v[12 + cidx] = s1.x; v[12 + cidx + 1] = s1.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 24; ++k) { u[k] = 0.0; v[k] = 0.0; }
+    }
+    __syncwarp(hmask);
+    const int ne16 = (int)min(16L, end - base);
+    for (int e2 = 0; e2 < ne16; ++e2) {
+      const double* uu = U + e2 * kUVStride + (3 * tr) * 2;
+      const double* vv = V + e2 * kUVStride + 3 * tc;
+      const double a00 = uu[0], a01 = uu[1], a10 = uu[2], a11 = uu[3], a20 = uu[4], a21 = uu[5];
+      const double b00 = vv[0], b01 = vv[1], b02 = vv[2], b10 = vv[12], b11 = vv[13], b12 = vv[14];
+      acc[0] += a00 * b00 + a01 * b10; acc[1] += a00 * b01 + a01 * b11; acc[2] += a00 * b02 + a01 * b12;
+      acc[3] += a10 * b00 + a11 * b10; acc[4] += a10 * b01 + a11 * b11; acc[5] += a10 * b02 + a11 * b12;
+      acc[6] += a20 * b00 + a21 * b10; acc[7] += a20 * b01 + a21 * b11; acc[8] += a20 * b02 + a21 * b12;
+    }
+    __syncwarp(hmask);
+  }
+  if (!live) return;
+
+  // ---- scale, damp, mask constants, store
+  const unsigned ma = ne.pose_mask[a], mb = ne.pose_mask[b];
+  // tile-packed destination: row block b (>= a), column block a
+  double* tile = S + (long)tile_slot[(b / kFramesPerTile) * T + (a / kFramesPerTile)] * kTile * kTile;
+  const int ra = (a % kFramesPerTile) * kFrameParams, rb = (b % kFramesPerTile) * kFrameParams;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int r = 3 * tr + k;
+    const double sa = ne.scale_c[12L * a + r];
+    const bool rconst = (ma >> r) & 1;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+      const int c = 3 * tc + l;
+      const double sb = ne.scale_c[12L * b + c];
+      const bool cconst = (mb >> c) & 1;
+      double val = -sa * acc[k * 3 + l] * sb;
+      if (a == b) {
+        val += sa * ne.B[(long)a * 144 + r * 12 + c] * sb;
+        if (r == c) {
+          const double diag = sa * ne.B[(long)a * 144 + r * 13] * sa;
+          const double d2 = rconst ? 1.0 : fmin(fmax(diag, o.min_diag), o.max_diag) / o.radius;
+          ne.d2_c[12L * a + r] = d2;
+          val += d2;
+        }
+      }
+      if (rconst || cconst) val = (a == b && r == c) ? 1.0 : 0.0;
+      if (a == b) tile[(ra + r) * kTile + ra + c] = val;
+      else        tile[(rb + c) * kTile + ra + r] = val;       // lower triangle: row block b > col block a
+    }
+    if (a == b && tc == 0)   // rhs of  S y = rhs  (y = -scaled step)
+      rhs[12L * a + r] = rconst ? 0.0 : sa * (ne.gc[12L * a + r] - ne.wf[12L * a + r]);
+  }
+}
+
+}  // namespace
+
+void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
+                         int n_points, NormalEq ne, cudaStream_t s) {
+  if (n_points <= 0) return;
+  point_blocks_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(st.pt_ptr, st.pt_obs, jac, res, n_points, ne.C, ne.gp);
+}
+
+void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
+                         int n_frames, NormalEq ne, bool with_wf, cudaStream_t s) {
+  if (st.n_chunks > 0) frame_blocks_kernel<<<st.n_chunks, 128, 0, s>>>(st, obs, jac, res, ne, with_wf ? 1 : 0);
+  if (n_frames > 0) frame_reduce_kernel<<<n_frames, 192, 0, s>>>(st, ne, n_frames);
+}
+
+void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, cudaStream_t s) {
+  // split in two by the caller's ordering needs: points first (n_frames == 0), frames later
+  if (n_points > 0)
+    point_scale_kernel<<<(n_points + 255) / 256, 256, 0, s>>>(n_points, ne.C, ne.point_const, enabled ? 1 : 0, ne.scale_p);
+  if (n_frames > 0)
+    frame_scale_kernel<<<(n_frames * kFrameParams + 255) / 256, 256, 0, s>>>(n_frames, ne.B, ne.pose_mask,
+                                                                             enabled ? 1 : 0, ne.scale_c);
+}
+
+void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s) {
+  if (n_points <= 0) return;
+  point_invert_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(n_points, ne, o);
+}
+
+void launch_schur_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+                         LmOptionsDev o, double* S, const int* tile_slot, int n_tiles, double* rhs,
+                         cudaStream_t s) {
+  if (st.n_blocks <= 0) return;
+  const int per = kSchurThreads / 16;
+  schur_blocks_kernel<<<(st.n_blocks + per - 1) / per, kSchurThreads, 0, s>>>(st, obs, jac, ne, o, S, tile_slot, n_tiles, rhs);
+}
+
+}  // namespace rsba

@@ -1,0 +1,199 @@
+// K4 -- back-substitution of the point blocks, trial parameters and the scalars the
+// trust-region logic needs.  Supersedes SchurEliminator::BackSubstitute and the bookkeeping
+// inside TrustRegionMinimizer (Ceres 1.9.0, third-party; reached through ceres::Solve,
+// CeresHandler.h:419).
+//
+//   delta_c = -s_c * y_c
+//   delta_p = -Cinv_p ( g_p + sum_{i in p} Jx_i^T (Jc_i delta_c[frame_i]) )      (unscaled)
+//   model_cost_change = -1/2 g^T delta + 1/2 sum D^2 (delta / s)^2
+// (the last line equals Ceres' -m.(r + m/2), m = J delta, because the linear solve is direct:
+//  (J'^T J' + D^2) delta' = -g').  All reductions are two-stage with a fixed order.
+#include "lm.cuh"
+
+namespace rsba {
+namespace {
+
+constexpr int kRedThreads = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += sh[w];
+  __syncthreads();
+  return t;  // valid on thread 0
+}
+
+__device__ __forceinline__ double block_max(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t = fmax(t, sh[w]);
+  __syncthreads();
+  return t;
+}
+
+// frames: delta_c, trial poses, partial scalars -> scratch[0..2] (single CTA)
+__global__ void __launch_bounds__(kRedThreads)
+frame_step_kernel(NormalEq ne, const double* __restrict__ y, int n, const double* __restrict__ poses,
+                  double* __restrict__ delta_c, double* __restrict__ trial, double* __restrict__ scratch) {
+  __shared__ double sh[32];
+  double gd = 0.0, dd = 0.0, nn = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const double sc = ne.scale_c[t];
+    const double ys = y[t];
+    const double d = -sc * ys;
+    delta_c[t] = d;
+    trial[t] = poses[t] + d;
+    gd += ne.gc[t] * d;
+    dd += ne.d2_c[t] * ys * ys;
+    nn += d * d;
+  }
+  gd = block_sum(gd, sh);
+  dd = block_sum(dd, sh);
+  nn = block_sum(nn, sh);
+  if (threadIdx.x == 0) { scratch[0] = gd; scratch[1] = dd; scratch[2] = nn; }
+}
+
+// points: back-substitution, trial points, per-CTA partial scalars -> scratch[3 + 3*block ...]
+__global__ void __launch_bounds__(128)
+point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne,
+                  const double* __restrict__ delta_c, int n_points, const double* __restrict__ points,
+                  double* __restrict__ delta_p, double* __restrict__ trial, double* __restrict__ scratch) {
+  __shared__ double sh[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double gd = 0.0, dd = 0.0, nn = 0.0;
+  if (p < n_points) {
+    const double* g = ne.gp + 3L * p;
+    double a0 = g[0], a1 = g[1], a2 = g[2];
+    for (int e = st.pt_ptr[p]; e < st.pt_ptr[p + 1]; ++e) {
+      const long i = st.pt_obs[e];
+      const double2* J = reinterpret_cast<const double2*>(jac + i * kJacDoubles);
+      const double2* dc = reinterpret_cast<const double2*>(delta_c + 12L * obs.frame[i]);
+      double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const double2 d = dc[h * 3 + q];
+          const double2 r0 = J[h * 6 + q], r1 = J[h * 6 + 3 + q];
+          m0 += r0.x * d.x + r0.y * d.y;
+          m1 += r1.x * d.x + r1.y * d.y;
+        }
+      const double2 x0 = J[12], x1 = J[13], x2 = J[14];
+      a0 += x0.x * m0 + x1.y * m1;
+      a1 += x0.y * m0 + x2.x * m1;
+      a2 += x1.x * m0 + x2.y * m1;
+    }
+    const double* Ci = ne.Cinv + 6L * p;
+    const double d0 = -(Ci[0] * a0 + Ci[1] * a1 + Ci[2] * a2);
+    const double d1 = -(Ci[1] * a0 + Ci[3] * a1 + Ci[4] * a2);
+    const double d2 = -(Ci[2] * a0 + Ci[4] * a1 + Ci[5] * a2);
+    delta_p[3L * p] = d0; delta_p[3L * p + 1] = d1; delta_p[3L * p + 2] = d2;
+    trial[3L * p] = points[3L * p] + d0;
+    trial[3L * p + 1] = points[3L * p + 1] + d1;
+    trial[3L * p + 2] = points[3L * p + 2] + d2;
+    gd = g[0] * d0 + g[1] * d1 + g[2] * d2;
+    nn = d0 * d0 + d1 * d1 + d2 * d2;
+    const double* sp = ne.scale_p + 3L * p;
+    const double* e2 = ne.d2_p + 3L * p;
+    const double u0 = d0 / sp[0], u1 = d1 / sp[1], u2 = d2 / sp[2];
+    dd = e2[0] * u0 * u0 + e2[1] * u1 * u1 + e2[2] * u2 * u2;
+  }
+  gd = block_sum(gd, sh);
+  dd = block_sum(dd, sh);
+  nn = block_sum(nn, sh);
+  if (threadIdx.x == 0) {
+    double* o = scratch + 3 + 3L * blockIdx.x;
+    o[0] = gd; o[1] = dd; o[2] = nn;
+  }
+}
+
+// final: scalars[0..2] = frame part + sum of point partials (fixed order)
+__global__ void __launch_bounds__(kRedThreads)
+step_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __restrict__ scalars) {
+  __shared__ double sh[32];
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int k = threadIdx.x; k < n_blocks; k += blockDim.x) {
+    a += scratch[3 + 3L * k];
+    b += scratch[4 + 3L * k];
+    c += scratch[5 + 3L * k];
+  }
+  a = block_sum(a, sh);
+  b = block_sum(b, sh);
+  c = block_sum(c, sh);
+  if (threadIdx.x == 0) {
+    scalars[0] = scratch[0] + a;   // g . delta
+    scalars[1] = scratch[1] + b;   // sum D^2 delta'^2
+    scalars[2] = scratch[2] + c;   // |delta|^2
+  }
+}
+
+// |x|^2 over parameter blocks that are not entirely constant, max |g| over free parameters
+__global__ void __launch_bounds__(kRedThreads)
+state_norms_kernel(NormalEq ne, int n_frames, int n_points, const double* __restrict__ poses,
+                   const double* __restrict__ points, double* __restrict__ scratch) {
+  __shared__ double sh[32];
+  double xx = 0.0, gm = 0.0;
+  const long nc = 12L * n_frames, np = 3L * n_points;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nc + np; t += (long)gridDim.x * blockDim.x) {
+    if (t < nc) {
+      const int f = (int)(t / 12), k = (int)(t % 12);
+      const unsigned m = ne.pose_mask[f];
+      const unsigned blockbits = (k < 6) ? (m & 0x3F) : ((m >> 6) & 0x3F);
+      if (blockbits != 0x3F) xx += poses[t] * poses[t];
+      if (!((m >> k) & 1)) gm = fmax(gm, fabs(ne.gc[t]));
+    } else {
+      const long u = t - nc;
+      if (!ne.point_const[u / 3]) {
+        xx += points[u] * points[u];
+        gm = fmax(gm, fabs(ne.gp[u]));
+      }
+    }
+  }
+  xx = block_sum(xx, sh);
+  gm = block_max(gm, sh);
+  if (threadIdx.x == 0) { scratch[2L * blockIdx.x] = xx; scratch[2L * blockIdx.x + 1] = gm; }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+state_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __restrict__ scalars) {
+  __shared__ double sh[32];
+  double xx = 0.0, gm = 0.0;
+  for (int k = threadIdx.x; k < n_blocks; k += blockDim.x) {
+    xx += scratch[2L * k];
+    gm = fmax(gm, scratch[2L * k + 1]);
+  }
+  xx = block_sum(xx, sh);
+  gm = block_max(gm, sh);
+  if (threadIdx.x == 0) { scalars[3] = xx; scalars[4] = gm; }
+}
+
+constexpr int kStateBlocks = 296;
+
+}  // namespace
+
+void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+                        const double* y_c, int n_frames, int n_points, const double* poses,
+                        const double* points, double* delta_c, double* delta_p, double* trial_poses,
+                        double* trial_points, double* scalars, double* scratch, cudaStream_t s) {
+  frame_step_kernel<<<1, kRedThreads, 0, s>>>(ne, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
+  const int nb = (n_points + 127) / 128;
+  if (nb > 0)
+    point_step_kernel<<<nb, 128, 0, s>>>(st, obs, jac, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
+  step_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, nb, scalars);
+}
+
+void launch_state_norms(NormalEq ne, int n_frames, int n_points, const double* poses, const double* points,
+                        double* scalars, double* scratch, cudaStream_t s) {
+  state_norms_kernel<<<kStateBlocks, kRedThreads, 0, s>>>(ne, n_frames, n_points, poses, points, scratch);
+  state_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, kStateBlocks, scalars);
+}
+
+}  // namespace rsba

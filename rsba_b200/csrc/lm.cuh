@@ -1,0 +1,110 @@
+// Device-side state of the LM solver and the launchers of K2 (normal equations + Schur
+// complement), K3 (tile Cholesky of the reduced camera system) and K4 (back-substitution and
+// step bookkeeping).  Everything here supersedes third-party Ceres internals that the
+// reference reaches through ceres::Solve (CeresHandler.h:419): SchurEliminator,
+// SparseSchurComplementSolver/CHOLMOD, LevenbergMarquardtStrategy, TrustRegionMinimizer.
+#pragma once
+#include "common.cuh"
+
+namespace rsba {
+
+constexpr int kTile = 96;          // Cholesky tile = 8 frames x 12 parameters
+constexpr int kFramesPerTile = kTile / kFrameParams;
+
+// ---- structure (built once per scene on the host, lm_structure.cu) ----------------------
+struct SchurStructure {
+  // point-major CSR over the frame-sorted observations
+  const int* pt_ptr;      // [P+1]
+  const int* pt_obs;      // [N]
+  // frame chunks for the per-frame reductions: chunk c covers obs [chunk_beg[c], chunk_beg[c]+chunk_cnt[c]) of chunk_frame[c]
+  const int* chunk_frame; // [n_chunks]
+  const int* chunk_beg;   // [n_chunks]
+  const int* chunk_cnt;   // [n_chunks]
+  const int* frame_chunk_ptr;  // [F+1] chunks of frame f
+  int n_chunks;
+  // camera-pair blocks (a <= b) of the reduced matrix and their (i, j) observation pairs
+  const int* blk_a;       // [n_blocks]
+  const int* blk_b;       // [n_blocks]
+  const long* blk_ptr;    // [n_blocks+1]
+  const int2* entries;    // [n_entries]  (obs i in frame a, obs j in frame b, same point)
+  int n_blocks;
+  long n_entries;
+};
+
+struct NormalEq {
+  // unscaled blocks of J^T J and J^T r
+  double* B;        // [F][144] camera diagonal blocks (full 12x12, row-major)
+  double* gc;       // [F][12]
+  double* wf;       // [F][12]   sum_i Jc_i^T Jx_i t_p   (rhs correction)
+  double* C;        // [P][6]    point blocks, packed xx xy xz yy yz zz
+  double* gp;       // [P][3]
+  double* Cinv;     // [P][6]    s_p (s_p C s_p + D^2)^-1 s_p  (zero for constant points)
+  double* tp;       // [P][3]    Cinv * gp
+  double* scale_c;  // [12F] Jacobi scaling (1 for constant parameters)
+  double* scale_p;  // [3P]
+  double* d2_c;     // [12F] LM diagonal (scaled space) of the current solve
+  double* d2_p;     // [3P]
+  double* partials; // [n_chunks][104] per-chunk partial sums of the frame kernel
+  const unsigned short* pose_mask;  // [F] constant-scalar bits
+  const unsigned char* point_const; // [P]
+};
+
+struct LmOptionsDev {
+  double radius, min_diag, max_diag;
+};
+
+// ---- K2 ---------------------------------------------------------------------------------
+void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
+                         int n_points, NormalEq ne, cudaStream_t s);
+void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
+                         int n_frames, NormalEq ne, bool with_wf, cudaStream_t s);
+void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, cudaStream_t s);
+void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s);
+// S (tile-packed, see TileSchedule: lower triangle + full diagonal blocks) and rhs
+struct TileSchedule;
+void launch_schur_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+                         LmOptionsDev o, double* S, const int* tile_slot, int n_tiles, double* rhs,
+                         cudaStream_t s);
+
+// ---- K3 ---------------------------------------------------------------------------------
+struct TileSchedule {
+  int n_tiles;              // tiles per dimension (T)
+  // S is tile-packed: slot s holds tile nz_tiles[s] = (row tile i, col tile j), i >= j, all
+  // structurally non-zero lower tiles after symbolic fill; tile_slot[i*T + j] = s or -1
+  const int2* nz_tiles;     // [n_nz]
+  const int* tile_slot;     // [T*T]
+  int n_nz;
+  // per panel k: rows i > k with tile (i,k) non-zero: rows[row_ptr[k] .. row_ptr[k+1])
+  const int* row_ptr;       // [n_tiles+1]
+  const int* rows;
+  // per panel k: update pairs (i, j), i >= j, both in rows(k): upd[upd_ptr[k] .. upd_ptr[k+1])
+  const long* upd_ptr;      // [n_tiles+1]
+  const int2* upd;
+  // per tile row i: the non-zero tiles (i, j), j < i, for the triangular solves
+  const int* lrow_ptr;      // [n_tiles+1]
+  const int* lrow_cols;
+  double* Dinv;             // [n_tiles][96*96] inverses of the diagonal factors (scratch)
+  long n_real;              // 12 * frames (rows beyond it are identity padding)
+};
+
+void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s);
+// returns number of kernel launches issued; info[0] != 0 on a non-positive pivot
+int launch_tile_cholesky(double* S, const TileSchedule& ts, const int* h_row_ptr,
+                         const long* h_upd_ptr, int* info, cudaStream_t s);
+int launch_tile_solve(const double* S, const TileSchedule& ts, double* x /* in: rhs, out: solution */,
+                      cudaStream_t s);
+
+// ---- K4 ---------------------------------------------------------------------------------
+struct StepScalars {  // device doubles, filled by launch_step_update
+  double g_dot_delta, d2_delta2, step_norm2, x_norm2, gmax;
+};
+// delta_c = -scale_c * y ; delta_p by back-substitution ; trial = x + delta ; scalars
+void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+                        const double* y_c, int n_frames, int n_points, const double* poses,
+                        const double* points, double* delta_c, double* delta_p, double* trial_poses,
+                        double* trial_points, double* scalars /* [8] */, double* scratch, cudaStream_t s);
+void launch_state_norms(NormalEq ne, int n_frames, int n_points, const double* poses, const double* points,
+                        double* scalars /* [8]: writes x_norm2 (3) and gmax (4) */, double* scratch,
+                        cudaStream_t s);
+
+}  // namespace rsba

@@ -1,19 +1,525 @@
-// Levenberg-Marquardt driver (placeholder until K2-K4 land in this round).
+// Host driver of the Levenberg-Marquardt loop and the one-off structure analysis.
+//
+// Supersedes ceres::Solve(options, &problem, &summary) as CeresHandler::solve calls it
+// (CeresHandler.h:394-426; options set at VideoSfMHandler.cc:579-583): trust-region LM with
+// Jacobi scaling, Schur elimination of the point blocks, Cholesky of the reduced camera system.
+// The control flow restates Ceres 1.9.0's TrustRegionMinimizer / LevenbergMarquardtStrategy
+// (third-party, not in the reference tree; constants in rsba_cuda_default_options).  All
+// state stays in HBM; per iteration the host reads back a handful of scalars.
+#include "lm.cuh"
 #include "problem.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
 namespace rsba {
-struct LmState {};
+
+struct LmState {
+  // ---- structure (device)
+  DeviceBuffer<int> pt_ptr, pt_obs, chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr, blk_a, blk_b;
+  DeviceBuffer<long> blk_ptr;
+  DeviceBuffer<int2> entries;
+  DeviceBuffer<int2> nz_tiles, upd;
+  DeviceBuffer<int> tile_slot, row_ptr, rows, lrow_ptr, lrow_cols;
+  DeviceBuffer<long> upd_ptr;
+  DeviceBuffer<unsigned short> pose_mask;
+  DeviceBuffer<unsigned char> point_const;
+  std::vector<int> h_row_ptr;
+  std::vector<long> h_upd_ptr;
+  std::vector<int2> h_nz_tiles;
+  SchurStructure st{};
+  TileSchedule ts{};
+  bool dense = false;
+  // ---- numeric state (device)
+  DeviceBuffer<double> B, gc, wf, C, gp, Cinv, tp, scale_c, scale_p, d2_c, d2_p, partials;
+  DeviceBuffer<double> S, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
+  DeviceBuffer<int> info;
+  NormalEq ne{};
+  long n_pad = 0;
+  long num_free_params = 0;
+};
+
 void lm_state_free(LmState* s) { delete s; }
+
+namespace {
+
+int fail(int code, const std::string& msg) {
+  set_last_error(msg);
+  return code;
+}
+
+template <typename T>
+int upload(DeviceBuffer<T>& d, const std::vector<T>& h, cudaStream_t s) {
+  RSBA_CUDA_TRY(d.resize(std::max<size_t>(h.size(), 1)));
+  if (!h.empty()) RSBA_CUDA_TRY(cudaMemcpyAsync(d.ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return RSBA_OK;
+}
+
+// ------------------------------------------------------------------ structure analysis
+// The analogue of Ceres' program reordering + symbolic factorisation, done once per scene.
+int build_structure(rsba_problem* h, LmState* lm, bool dense) {
+  const long N = h->n_obs;
+  const int F = h->n_frames, P = h->n_points;
+  const std::vector<int>& fr = h->h_obs_frame;
+  const std::vector<int>& pt = h->h_obs_point;
+  cudaStream_t s = h->stream;
+  if ((long)F * F > (1L << 28)) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 16384 frames: pair index not implemented");
+
+  // point-major CSR (stable counting sort: observation order inside a point is frame order)
+  std::vector<int> pt_ptr(P + 1, 0), pt_obs(N);
+  for (long i = 0; i < N; ++i) pt_ptr[pt[i] + 1]++;
+  for (int p = 0; p < P; ++p) pt_ptr[p + 1] += pt_ptr[p];
+  {
+    std::vector<int> cur(pt_ptr.begin(), pt_ptr.end() - 1);
+    for (long i = 0; i < N; ++i) pt_obs[cur[pt[i]]++] = (int)i;
+  }
+  // frame chunks of <= 128 observations
+  std::vector<int> chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr(F + 1, 0);
+  {
+    long i = 0;
+    for (int f = 0; f < F; ++f) {
+      frame_chunk_ptr[f] = (int)chunk_frame.size();
+      long j = i;
+      while (j < N && fr[j] == f) ++j;
+      for (long b = i; b < j; b += 128) {
+        chunk_frame.push_back(f);
+        chunk_beg.push_back((int)b);
+        chunk_cnt.push_back((int)std::min<long>(128, j - b));
+      }
+      i = j;
+    }
+    frame_chunk_ptr[F] = (int)chunk_frame.size();
+  }
+  // camera-pair blocks: count, prefix, fill
+  std::vector<unsigned> cnt((size_t)F * F, 0u);
+  for (int p = 0; p < P; ++p) {
+    if (h->point_const[p]) continue;  // constant points are not eliminated: no Schur term
+    const int b = pt_ptr[p], e = pt_ptr[p + 1];
+    for (int x = b; x < e; ++x) {
+      const int fa = fr[pt_obs[x]];
+      for (int y = x; y < e; ++y) {
+        const int fb = fr[pt_obs[y]];
+        cnt[(size_t)fa * F + fb] += (fa == fb && x != y) ? 2u : 1u;
+      }
+    }
+  }
+  std::vector<int> blk_a, blk_b;
+  std::vector<long> blk_ptr(1, 0);
+  std::vector<unsigned> blk_id((size_t)F * F, 0xFFFFFFFFu);
+  for (int a = 0; a < F; ++a)
+    for (int b = a; b < F; ++b) {
+      const unsigned c = cnt[(size_t)a * F + b];
+      if (c == 0 && a != b) continue;
+      blk_id[(size_t)a * F + b] = (unsigned)blk_a.size();
+      blk_a.push_back(a);
+      blk_b.push_back(b);
+      blk_ptr.push_back(blk_ptr.back() + c);
+    }
+  const long n_entries = blk_ptr.back();
+  std::vector<int2> entries((size_t)std::max<long>(n_entries, 1));
+  {
+    std::vector<long> cur(blk_ptr.begin(), blk_ptr.end() - 1);
+    for (int p = 0; p < P; ++p) {
+      if (h->point_const[p]) continue;
+      const int b = pt_ptr[p], e = pt_ptr[p + 1];
+      for (int x = b; x < e; ++x) {
+        const int ox = pt_obs[x], fa = fr[ox];
+        for (int y = x; y < e; ++y) {
+          const int oy = pt_obs[y], fb = fr[oy];
+          const unsigned id = blk_id[(size_t)fa * F + fb];
+          entries[cur[id]++] = make_int2(ox, oy);
+          if (fa == fb && x != y) entries[cur[id]++] = make_int2(oy, ox);
+        }
+      }
+    }
+  }
+  // ---- tile graph + symbolic fill
+  const int T = (int)((12L * F + kTile - 1) / kTile);
+  std::vector<char> nz((size_t)T * T, 0);
+  for (int i = 0; i < T; ++i) nz[(size_t)i * T + i] = 1;
+  if (dense) {
+    for (int i = 0; i < T; ++i)
+      for (int j = 0; j <= i; ++j) nz[(size_t)i * T + j] = 1;
+  } else {
+    for (size_t k = 0; k < blk_a.size(); ++k)
+      nz[(size_t)(blk_b[k] / kFramesPerTile) * T + blk_a[k] / kFramesPerTile] = 1;
+  }
+  std::vector<int> row_ptr(T + 1, 0), rows;
+  std::vector<long> upd_ptr(T + 1, 0);
+  std::vector<int2> upd;
+  for (int k = 0; k < T; ++k) {
+    row_ptr[k] = (int)rows.size();
+    upd_ptr[k] = (long)upd.size();
+    const size_t r0 = rows.size();
+    for (int i = k + 1; i < T; ++i)
+      if (nz[(size_t)i * T + k]) rows.push_back(i);
+    for (size_t x = r0; x < rows.size(); ++x)
+      for (size_t y = r0; y <= x; ++y) {
+        nz[(size_t)rows[x] * T + rows[y]] = 1;  // fill
+        upd.push_back(make_int2(rows[x], rows[y]));
+      }
+  }
+  row_ptr[T] = (int)rows.size();
+  upd_ptr[T] = (long)upd.size();
+  std::vector<int2> nz_tiles;
+  std::vector<int> tile_slot((size_t)T * T, -1), lrow_ptr(T + 1, 0), lrow_cols;
+  for (int i = 0; i < T; ++i) {
+    lrow_ptr[i] = (int)lrow_cols.size();
+    for (int j = 0; j <= i; ++j)
+      if (nz[(size_t)i * T + j]) {
+        tile_slot[(size_t)i * T + j] = (int)nz_tiles.size();
+        nz_tiles.push_back(make_int2(i, j));
+        if (j < i) lrow_cols.push_back(j);
+      }
+  }
+  lrow_ptr[T] = (int)lrow_cols.size();
+
+  // ---- upload
+  int rc;
+#define UP(dev, host) if ((rc = upload(lm->dev, host, s))) return rc
+  UP(pt_ptr, pt_ptr); UP(pt_obs, pt_obs); UP(chunk_frame, chunk_frame); UP(chunk_beg, chunk_beg);
+  UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr); UP(blk_a, blk_a); UP(blk_b, blk_b);
+  UP(blk_ptr, blk_ptr); UP(entries, entries); UP(nz_tiles, nz_tiles); UP(upd, upd); UP(tile_slot, tile_slot);
+  UP(row_ptr, row_ptr); UP(rows, rows); UP(lrow_ptr, lrow_ptr); UP(lrow_cols, lrow_cols); UP(upd_ptr, upd_ptr);
+  UP(pose_mask, h->pose_mask); UP(point_const, h->point_const);
+#undef UP
+  lm->h_row_ptr = row_ptr;
+  lm->h_upd_ptr = upd_ptr;
+  lm->h_nz_tiles = nz_tiles;
+  lm->dense = dense;
+  lm->n_pad = (long)T * kTile;
+
+  SchurStructure& st = lm->st;
+  st.pt_ptr = lm->pt_ptr.ptr; st.pt_obs = lm->pt_obs.ptr;
+  st.chunk_frame = lm->chunk_frame.ptr; st.chunk_beg = lm->chunk_beg.ptr; st.chunk_cnt = lm->chunk_cnt.ptr;
+  st.frame_chunk_ptr = lm->frame_chunk_ptr.ptr; st.n_chunks = (int)chunk_frame.size();
+  st.blk_a = lm->blk_a.ptr; st.blk_b = lm->blk_b.ptr; st.blk_ptr = lm->blk_ptr.ptr; st.entries = lm->entries.ptr;
+  st.n_blocks = (int)blk_a.size(); st.n_entries = n_entries;
+
+  // ---- numeric buffers
+  const size_t Fz = std::max(F, 1), Pz = std::max(P, 1);
+  RSBA_CUDA_TRY(lm->B.resize(Fz * 144)); RSBA_CUDA_TRY(lm->gc.resize(Fz * 12)); RSBA_CUDA_TRY(lm->wf.resize(Fz * 12));
+  RSBA_CUDA_TRY(lm->C.resize(Pz * 6)); RSBA_CUDA_TRY(lm->gp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Cinv.resize(Pz * 6));
+  RSBA_CUDA_TRY(lm->tp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->scale_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->scale_p.resize(Pz * 3));
+  RSBA_CUDA_TRY(lm->d2_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->d2_p.resize(Pz * 3));
+  RSBA_CUDA_TRY(lm->partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 168));
+  RSBA_CUDA_TRY(lm->S.resize(std::max<size_t>(nz_tiles.size(), 1) * kTile * kTile));
+  RSBA_CUDA_TRY(lm->Dinv.resize((size_t)std::max(T, 1) * kTile * kTile));
+  RSBA_CUDA_TRY(lm->rhs.resize(std::max<long>(lm->n_pad, 1))); RSBA_CUDA_TRY(lm->y.resize(std::max<long>(lm->n_pad, 1)));
+  RSBA_CUDA_TRY(lm->delta_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->delta_p.resize(Pz * 3));
+  RSBA_CUDA_TRY(lm->trial_poses.resize(Fz * 12)); RSBA_CUDA_TRY(lm->trial_points.resize(Pz * 3));
+  RSBA_CUDA_TRY(lm->scalars.resize(16));
+  RSBA_CUDA_TRY(lm->scratch.resize(std::max<size_t>(3 + 3 * ((Pz + 127) / 128), 1024)));
+  RSBA_CUDA_TRY(lm->info.resize(4));
+  RSBA_CUDA_TRY(cudaMemsetAsync(lm->rhs.ptr, 0, lm->rhs.bytes(), s));
+  RSBA_CUDA_TRY(cudaMemsetAsync(lm->d2_c.ptr, 0, lm->d2_c.bytes(), s));
+
+  NormalEq& ne = lm->ne;
+  ne.B = lm->B.ptr; ne.gc = lm->gc.ptr; ne.wf = lm->wf.ptr; ne.C = lm->C.ptr; ne.gp = lm->gp.ptr;
+  ne.Cinv = lm->Cinv.ptr; ne.tp = lm->tp.ptr; ne.scale_c = lm->scale_c.ptr; ne.scale_p = lm->scale_p.ptr;
+  ne.d2_c = lm->d2_c.ptr; ne.d2_p = lm->d2_p.ptr; ne.partials = lm->partials.ptr;
+  ne.pose_mask = lm->pose_mask.ptr; ne.point_const = lm->point_const.ptr;
+
+  TileSchedule& ts = lm->ts;
+  ts.n_tiles = T; ts.nz_tiles = lm->nz_tiles.ptr; ts.tile_slot = lm->tile_slot.ptr; ts.n_nz = (int)nz_tiles.size();
+  ts.row_ptr = lm->row_ptr.ptr; ts.rows = lm->rows.ptr; ts.upd_ptr = lm->upd_ptr.ptr; ts.upd = lm->upd.ptr;
+  ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.n_real = 12L * F;
+
+  long free_params = 0;
+  for (int f = 0; f < F; ++f) free_params += 12 - __builtin_popcount(h->pose_mask[f] & 0xFFF);
+  for (int p = 0; p < P; ++p) free_params += h->point_const[p] ? 0 : 3;
+  lm->num_free_params = free_params;
+  RSBA_CUDA_TRY(cudaStreamSynchronize(s));
+  return RSBA_OK;
+}
+
+int ensure_lm(rsba_problem* h, bool dense) {
+  if (h->lm && h->lm->dense == dense) return RSBA_OK;
+  if (h->lm) { lm_state_free(h->lm); h->lm = nullptr; }
+  LmState* lm = new LmState;
+  int rc = build_structure(h, lm, dense);
+  if (rc) { delete lm; return rc; }
+  h->lm = lm;
+  return RSBA_OK;
+}
+
+// ------------------------------------------------------------------ pipeline stages
+// Normal equations + Schur complement for `radius` from the Jacobian in h->d_jac.
+void linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, double radius, bool new_jacobian,
+               bool compute_scale) {
+  cudaStream_t s = h->stream;
+  const ObsView obs = h->obs_view();
+  const LmOptionsDev o{radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
+  stage_begin(h, kStageSchur);
+  if (new_jacobian) { launch_point_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_points, lm->ne, s); h->launches += 1; }
+  if (compute_scale) { launch_jacobi_scale(0, h->n_points, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
+  launch_point_invert(h->n_points, lm->ne, o, s);
+  launch_frame_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_frames, lm->ne, true, s);
+  h->launches += 3;
+  if (compute_scale) { launch_jacobi_scale(h->n_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
+  launch_clear_tiles(lm->S.ptr, lm->ts, s);
+  launch_schur_blocks(lm->st, obs, h->d_jac.ptr, lm->ne, o, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, lm->rhs.ptr, s);
+  h->launches += 2;
+  stage_end(h, kStageSchur);
+}
+
+void factor_and_solve(rsba_problem* h, LmState* lm) {
+  cudaStream_t s = h->stream;
+  stage_begin(h, kStageCholesky);
+  cudaMemsetAsync(lm->info.ptr, 0, sizeof(int), s);
+  cudaMemcpyAsync(lm->y.ptr, lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->h_row_ptr.data(), lm->h_upd_ptr.data(), lm->info.ptr, s);
+  h->launches += launch_tile_solve(lm->S.ptr, lm->ts, lm->y.ptr, s);
+  stage_end(h, kStageCholesky);
+}
+
+void step_update(rsba_problem* h, LmState* lm) {
+  stage_begin(h, kStageUpdate);
+  launch_step_update(lm->st, h->obs_view(), h->d_jac.ptr, lm->ne, lm->y.ptr, h->n_frames, h->n_points,
+                     h->d_poses.ptr, h->d_points.ptr, lm->delta_c.ptr, lm->delta_p.ptr, lm->trial_poses.ptr,
+                     lm->trial_points.ptr, lm->scalars.ptr, lm->scratch.ptr, h->stream);
+  h->launches += 3;
+  stage_end(h, kStageUpdate);
+}
+
+struct HostScalars {
+  double s[8];
+  double cost;
+  int invalid;
+  int info;
+};
+
+int fetch(rsba_problem* h, LmState* lm, HostScalars* out) {
+  cudaStream_t s = h->stream;
+  RSBA_CUDA_TRY(cudaMemcpyAsync(out->s, lm->scalars.ptr, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  RSBA_CUDA_TRY(cudaMemcpyAsync(&out->cost, h->d_scalars.ptr, sizeof(double), cudaMemcpyDeviceToHost, s));
+  RSBA_CUDA_TRY(cudaMemcpyAsync(&out->invalid, h->d_invalid.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RSBA_CUDA_TRY(cudaMemcpyAsync(&out->info, lm->info.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RSBA_CUDA_TRY(cudaStreamSynchronize(s));
+  RSBA_CUDA_TRY(cudaGetLastError());
+  for (int k = 0; k < kNumStages; ++k) stage_collect(h, (Stage)k);
+  return RSBA_OK;
+}
+
+int prepare_solve(rsba_problem* h, const rsba_solve_options* opt) {
+  if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
+  if (!opt) return fail(RSBA_ERR_INVALID_ARGUMENT, "options are NULL");
+  if (!h->camera_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_camera has not been called");
+  if (opt->huber_loss > 0.0) return fail(RSBA_ERR_INVALID_ARGUMENT, "huber_loss: not implemented in this round");
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  if (h->ptr_mode) {
+    int rc = finalize_pointer_problem(h);
+    if (rc) return rc;
+    rc = gather_pointer_parameters(h);
+    if (rc) return rc;
+  }
+  if (!h->scene_set) return fail(RSBA_ERR_STATE, "no residual blocks");
+  if (!h->params_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_parameters has not been called");
+  int rc = ensure_eval_buffers(h, true);
+  if (rc) return rc;
+  return ensure_lm(h, opt->dense_cholesky != 0);
+}
+
+}  // namespace
 }  // namespace rsba
+
+using namespace rsba;
+
 extern "C" {
-int rsba_cuda_solve(rsba_problem*, const rsba_solve_options*, rsba_solve_summary*) {
-  rsba::set_last_error("rsba_cuda_solve: not built yet");
-  return RSBA_ERR_STATE;
+
+int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_summary* sum) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  rsba_solve_summary local;
+  if (!sum) sum = &local;
+  memset(sum, 0, sizeof(*sum));
+  sum->termination = 2;
+  int rc = prepare_solve(h, opt);
+  if (rc) { snprintf(sum->message, sizeof(sum->message), "%s", rsba_cuda_last_error()); return rc; }
+  LmState* lm = h->lm;
+  for (auto& t : h->timers) t.total_ms = 0.0;
+  sum->num_residual_blocks = h->n_obs;
+  sum->num_parameters_reduced = lm->num_free_params;
+
+  auto finish = [&](int term, const char* msg, double cost, double radius, double gmax) {
+    sum->termination = term;
+    sum->usable = term != 2;
+    sum->final_cost = cost;
+    sum->final_radius = radius;
+    sum->final_gradient_max_norm = gmax;
+    snprintf(sum->message, sizeof(sum->message), "%s", msg);
+    sum->time_jacobian_ms = h->timers[kStageJacobian].total_ms;
+    sum->time_residual_ms = h->timers[kStageResidual].total_ms;
+    sum->time_schur_ms = h->timers[kStageSchur].total_ms;
+    sum->time_cholesky_ms = h->timers[kStageCholesky].total_ms;
+    sum->time_update_ms = h->timers[kStageUpdate].total_ms;
+    sum->time_allreduce_ms = h->timers[kStageAllreduce].total_ms;
+  };
+  auto wall = [&]() {
+    sum->time_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  };
+
+  HostScalars hs{};
+  double radius = opt->initial_trust_region_radius, decrease = 2.0;
+  // ---- iteration 0: evaluate, linearise (fixes the Jacobi scaling), gradient check
+  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
+  if (rc) return rc;
+  sum->num_jacobian_evaluations = 1;
+  linearize(h, lm, *opt, radius, true, true);
+  launch_state_norms(lm->ne, h->n_frames, h->n_points, h->d_poses.ptr, h->d_points.ptr, lm->scalars.ptr,
+                     lm->scratch.ptr, h->stream);
+  h->launches += 2;
+  if ((rc = fetch(h, lm, &hs))) return rc;
+  double cost = hs.cost, x_norm = std::sqrt(hs.s[3]), gmax = hs.s[4];
+  sum->initial_cost = cost;
+  if (hs.invalid > 0) {
+    finish(2, "FAILURE: residual evaluation failed at the initial point (point behind a camera)", cost, radius, gmax);
+    wall();
+    return fail(RSBA_ERR_EVALUATION_FAILED, sum->message);
+  }
+  if (opt->verbose)
+    printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n%4d % .6e                % .2e                        % .2e\n",
+           0, cost, gmax, radius);
+  if (gmax <= opt->gradient_tolerance) {
+    finish(0, "CONVERGENCE: gradient tolerance reached", cost, radius, gmax);
+    goto done;
+  }
+  {
+    int it = 0;
+    while (true) {
+      if (it >= opt->max_num_iterations) {
+        finish(1, "NO_CONVERGENCE: maximum number of iterations reached", cost, radius, gmax);
+        break;
+      }
+      ++it;
+      sum->iterations = it;
+      factor_and_solve(h, lm);
+      step_update(h, lm);
+      cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), h->stream);
+      rc = run_evaluate(h, false, lm->trial_poses.ptr, lm->trial_points.ptr, nullptr, nullptr);
+      if (rc) return rc;
+      sum->num_residual_evaluations++;
+      if ((rc = fetch(h, lm, &hs))) return rc;
+      if (hs.info != 0) {
+        finish(2, "FAILURE: reduced camera matrix is not positive definite", cost, radius, gmax);
+        wall();
+        return fail(RSBA_ERR_LINEAR_SOLVER, sum->message);
+      }
+      const double mcc = -0.5 * hs.s[0] + 0.5 * hs.s[1];
+      const double step_norm = std::sqrt(hs.s[2]);
+      bool accepted = false;
+      double rho = 0.0, new_cost = hs.cost;
+      if (mcc > 0.0) {
+        const bool ok = hs.invalid == 0;
+        if (ok) {
+          if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
+            finish(0, "CONVERGENCE: parameter tolerance reached", cost, radius, gmax);
+            break;
+          }
+          if (std::fabs(cost - new_cost) < opt->function_tolerance * cost) {
+            finish(0, "CONVERGENCE: function tolerance reached", cost, radius, gmax);
+            break;
+          }
+          rho = (cost - new_cost) / mcc;
+          accepted = rho > opt->min_relative_decrease;
+        }
+      }
+      if (accepted) {
+        sum->num_successful_steps++;
+        cudaMemcpyAsync(h->d_poses.ptr, lm->trial_poses.ptr, h->d_poses.bytes(), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->d_points.ptr, lm->trial_points.ptr, h->d_points.bytes(), cudaMemcpyDeviceToDevice, h->stream);
+        radius = std::min(opt->max_trust_region_radius,
+                          radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+        decrease = 2.0;
+        rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
+        if (rc) return rc;
+        sum->num_jacobian_evaluations++;
+        linearize(h, lm, *opt, radius, true, false);
+        launch_state_norms(lm->ne, h->n_frames, h->n_points, h->d_poses.ptr, h->d_points.ptr, lm->scalars.ptr,
+                           lm->scratch.ptr, h->stream);
+        h->launches += 2;
+        if ((rc = fetch(h, lm, &hs))) return rc;
+        const double old = cost;
+        cost = hs.cost;
+        x_norm = std::sqrt(hs.s[3]);
+        gmax = hs.s[4];
+        if (opt->verbose)
+          printf("%4d % .6e  % .2e  % .2e  % .2e  % .2e  % .2e\n", it, cost, old - cost, gmax, step_norm, rho, radius);
+        if (gmax <= opt->gradient_tolerance) {
+          finish(0, "CONVERGENCE: gradient tolerance reached", cost, radius, gmax);
+          break;
+        }
+      } else {
+        sum->num_unsuccessful_steps++;
+        radius /= decrease;
+        decrease *= 2.0;
+        if (opt->verbose)
+          printf("%4d % .6e  % .2e  % .2e  % .2e  % .2e  % .2e (rejected)\n", it, cost, 0.0, gmax, step_norm, rho, radius);
+        if (radius < opt->min_trust_region_radius) {
+          finish(0, "CONVERGENCE: trust region radius below minimum", cost, radius, gmax);
+          break;
+        }
+        linearize(h, lm, *opt, radius, false, false);   // same Jacobian, new damping
+      }
+    }
+  }
+done:
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->ptr_mode) {
+    rc = scatter_pointer_parameters(h);
+    if (rc) return rc;
+  }
+  wall();
+  return RSBA_OK;
 }
-int rsba_cuda_linearize_and_step(rsba_problem*, const rsba_solve_options*, double, double*, double*,
-                                 double*, double*, double*) {
-  rsba::set_last_error("rsba_cuda_linearize_and_step: not built yet");
-  return RSBA_ERR_STATE;
+
+int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt, double radius, double* S_out,
+                                 double* rhs_out, double* delta_poses, double* delta_points,
+                                 double* model_cost_change) {
+  int rc = prepare_solve(h, opt);
+  if (rc) return rc;
+  if (!(radius > 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "radius must be positive");
+  LmState* lm = h->lm;
+  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
+  if (rc) return rc;
+  linearize(h, lm, *opt, radius, true, true);
+  const long n = 12L * h->n_frames;
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (S_out) {
+    std::vector<double> tile((size_t)kTile * kTile);
+    memset(S_out, 0, sizeof(double) * n * n);
+    for (size_t sidx = 0; sidx < lm->h_nz_tiles.size(); ++sidx) {
+      const int2 t = lm->h_nz_tiles[sidx];
+      RSBA_CUDA_TRY(cudaMemcpy(tile.data(), lm->S.ptr + sidx * kTile * kTile, tile.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int r = 0; r < kTile; ++r)
+        for (int c = 0; c < kTile; ++c) {
+          const long gr = (long)t.x * kTile + r, gcol = (long)t.y * kTile + c;
+          if (gr >= n || gcol >= n || gcol > gr) continue;
+          // inside a diagonal 12x12 block both triangles are stored; elsewhere mirror the lower part
+          S_out[gr * n + gcol] = tile[r * kTile + c];
+          S_out[gcol * n + gr] = tile[r * kTile + c];
+        }
+    }
+  }
+  if (rhs_out) {
+    RSBA_CUDA_TRY(cudaMemcpy(rhs_out, lm->rhs.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
+    for (long k = 0; k < n; ++k) rhs_out[k] = -rhs_out[k];   // S delta_c' = rhs
+  }
+  factor_and_solve(h, lm);
+  step_update(h, lm);
+  HostScalars hs{};
+  if ((rc = fetch(h, lm, &hs))) return rc;
+  if (hs.info != 0) return fail(RSBA_ERR_LINEAR_SOLVER, "reduced camera matrix is not positive definite");
+  if (delta_poses) RSBA_CUDA_TRY(cudaMemcpy(delta_poses, lm->delta_c.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (delta_points)
+    RSBA_CUDA_TRY(cudaMemcpy(delta_points, lm->delta_p.ptr, 3L * h->n_points * sizeof(double), cudaMemcpyDeviceToHost));
+  if (model_cost_change) *model_cost_change = -0.5 * hs.s[0] + 0.5 * hs.s[1];
+  return RSBA_OK;
 }
-int rsba_cuda_nccl_unique_id(unsigned char*) { return RSBA_ERR_NCCL; }
-int rsba_cuda_comm_init(rsba_problem*, int, int, const unsigned char*) { return RSBA_ERR_NCCL; }
-}
+
+int rsba_cuda_nccl_unique_id(unsigned char*) { set_last_error("NCCL path not built yet"); return RSBA_ERR_NCCL; }
+int rsba_cuda_comm_init(rsba_problem*, int, int, const unsigned char*) { set_last_error("NCCL path not built yet"); return RSBA_ERR_NCCL; }
+
+}  // extern "C"
