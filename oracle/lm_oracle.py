@@ -119,7 +119,7 @@ def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mas
     C[Cd.row // 3, Cd.row % 3, Cd.col % 3] = Cd.data
     C += np.einsum("pi,ij->pij", D2[nc:].reshape(P, 3), np.eye(3))
     Cinv = np.linalg.inv(C)
-    Cinv_sp = sp.block_diag([Cinv[p] for p in range(P)], format="csr") if P <= 4000 else _block_diag(Cinv)
+    Cinv_sp = _block_diag(Cinv)
     ECinv = (E @ Cinv_sp).tocsr()
     S = B - (ECinv @ E.T).toarray()
     rhs_y = g[:nc] - ECinv @ g[nc:]

@@ -148,8 +148,9 @@ def test_solve_pointer_api_writes_back_in_place(api, oracle_built):
         pb2.load_scene(sc)
         s2 = pb2.solve(api.default_options(max_num_iterations=10))
         po2, pt2 = pb2.get_parameters()
-    assert s.final_cost == s2.final_cost
-    assert np.array_equal(poses, po2) and np.array_equal(points, pt2)
+    # the pointer API numbers points by first appearance, so reductions run in another order
+    assert abs(s.final_cost - s2.final_cost) <= 1e-9 * s2.final_cost
+    assert relerr(poses, po2) <= 1e-7 and relerr(points, pt2) <= 1e-7
     assert not poses[0].any()
 
 
