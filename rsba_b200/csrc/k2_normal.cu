@@ -7,9 +7,9 @@
 // one frame with one point, so
 //   B_f  = sum_{i in f} Jc_i^T Jc_i        12x12   (frame_blocks)
 //   C_p  = sum_{i in p} Jx_i^T Jx_i         3x3    (point_blocks)
-//   S_ab = [a==b](s B s + D^2) - s_a ( sum_{p seen by a and b} Jc_i^T (Jx_i Cinv_p Jx_j^T) Jc_j ) s_b
-// with Cinv_p = s_p (s_p C_p s_p + D_p^2)^-1 s_p inverted in registers (3x3 Cholesky).  The
-// 2x2 middle factor keeps the pair term at K = 2 instead of materialising the 12x3 E blocks.
+//   S_ab = [a==b](s B s + D^2) - s_a ( sum_{p seen by a and b} Jc_i^T Jx_i Cinv_p Jx_j^T Jc_j ) s_b
+// with Cinv_p = s_p (s_p C_p s_p + D_p^2)^-1 s_p inverted in registers (3x3 Cholesky).  This file
+// holds the diagonal blocks and the point inverses; the Schur product itself is k2_schur.cu.
 // Jacobi scaling s and the LM diagonal D^2 = clamp(diag)/radius follow
 // LevenbergMarquardtStrategy::ComputeStep / TrustRegionMinimizer (Ceres 1.9.0).
 //
@@ -92,6 +92,8 @@ point_invert_kernel(int n_points, NormalEq ne, LmOptionsDev o) {
     for (int k = 0; k < 6; ++k) Ci[k] = 0.0;
     t[0] = t[1] = t[2] = 0.0;
     d2[0] = d2[1] = d2[2] = 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ne.Minv[6L * p + k] = 0.0;
     return;
   }
   const double* Cp = ne.C + 6L * p;
@@ -115,6 +117,10 @@ point_invert_kernel(int n_points, NormalEq ne, LmOptionsDev o) {
   const double m10 = -l10 * m00 * m11;
   const double m21 = -l21 * m11 * m22;
   const double m20 = -(l20 * m00 + l21 * m10) * m22;
+  {
+    double* Mi = ne.Minv + 6L * p;
+    Mi[0] = m00; Mi[1] = m10; Mi[2] = m11; Mi[3] = m20; Mi[4] = m21; Mi[5] = m22;
+  }
   // inverse (scaled space), then fold the point scaling back in: Cinv'' = s Cinv' s
   const double i00 = (m00 * m00 + m10 * m10 + m20 * m20) * s0 * s0;
   const double i10 = (m10 * m11 + m20 * m21) * s1 * s0;
@@ -228,129 +234,6 @@ frame_reduce_kernel(SchurStructure st, NormalEq ne, int n_frames) {
   else ne.wf[(long)f * 12 + (k - 156)] = s;
 }
 
-// ---------------------------------------------------------------- Schur complement blocks
-// Half a warp per camera-pair block (a <= b).  Phase 1: each lane turns one (i, j) pair into
-// u = Jc_i^T (Jx_i Cinv_p Jx_j^T)  (12x2) and v = Jc_j (2x12) in shared memory.  Phase 2: lane
-// (tr, tc) accumulates its 3x3 tile of  sum_e u_e v_e.
-constexpr int kSchurThreads = 64;
-constexpr int kUVStride = 25;  // 24 doubles + 1 pad: conflict-free per-lane rows
-
-__global__ void __launch_bounds__(kSchurThreads)
-schur_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne,
-                    LmOptionsDev o, double* __restrict__ S, const int* __restrict__ tile_slot, int T,
-                    double* __restrict__ rhs) {
-  __shared__ double sU[(kSchurThreads / 16) * 16 * kUVStride];
-  __shared__ double sV[(kSchurThreads / 16) * 16 * kUVStride];
-  const int half = threadIdx.x >> 4, hl = threadIdx.x & 15;
-  const int blk = blockIdx.x * (kSchurThreads / 16) + half;
-  const bool live = blk < st.n_blocks;
-  const int a = live ? st.blk_a[blk] : 0, b = live ? st.blk_b[blk] : 0;
-  const long beg = live ? st.blk_ptr[blk] : 0, end = live ? st.blk_ptr[blk + 1] : 0;
-  double* U = sU + half * 16 * kUVStride;
-  double* V = sV + half * 16 * kUVStride;
-  const int tr = hl >> 2, tc = hl & 3;
-  double acc[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
-
-  for (long base = beg; base < end; base += 16) {
-    const long e = base + hl;
-    double* u = U + hl * kUVStride;
-    double* v = V + hl * kUVStride;
-    if (e < end) {
-      const int2 ij = st.entries[e];
-      const double2* Ji = reinterpret_cast<const double2*>(jac + (long)ij.x * kJacDoubles);
-      const double2* Jj = reinterpret_cast<const double2*>(jac + (long)ij.y * kJacDoubles);
-      const int p = obs.point[ij.x];
-      const double* Ci = ne.Cinv + 6L * p;
-      const double2 xi0 = Ji[12], xi1 = Ji[13], xi2 = Ji[14];   // Jx_i rows: (xi0.x xi0.y xi1.x) (xi1.y xi2.x xi2.y)
-      const double2 xj0 = Jj[12], xj1 = Jj[13], xj2 = Jj[14];
-      const double i00 = Ci[0], i10 = Ci[1], i20 = Ci[2], i11 = Ci[3], i21 = Ci[4], i22 = Ci[5];
-      // T = Jx_i Cinv (2x3)
-      const double t00 = xi0.x * i00 + xi0.y * i10 + xi1.x * i20;
-      const double t01 = xi0.x * i10 + xi0.y * i11 + xi1.x * i21;
-      const double t02 = xi0.x * i20 + xi0.y * i21 + xi1.x * i22;
-      const double t10 = xi1.y * i00 + xi2.x * i10 + xi2.y * i20;
-      const double t11 = xi1.y * i10 + xi2.x * i11 + xi2.y * i21;
-      const double t12 = xi1.y * i20 + xi2.x * i21 + xi2.y * i22;
-      // W = T Jx_j^T (2x2)
-      const double w00 = t00 * xj0.x + t01 * xj0.y + t02 * xj1.x;
-      const double w01 = t00 * xj1.y + t01 * xj2.x + t02 * xj2.y;
-      const double w10 = t10 * xj0.x + t11 * xj0.y + t12 * xj1.x;
-      const double w11 = t10 * xj1.y + t11 * xj2.x + t12 * xj2.y;
-      // u[c][r'] = Jc_i[0][c] W[0][r'] + Jc_i[1][c] W[1][r'];  Jc_i[row][c]: record offsets
-      // c<6: row*6+c ; c>=6: 12+row*6+(c-6)  -> as double2 pairs
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {        // pose0 / pose1 halves
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {         // column pairs
-          const double2 r0 = Ji[h2 * 6 + q];        // row 0, columns 2q, 2q+1 of this half
-          const double2 r1 = Ji[h2 * 6 + 3 + q];    // row 1
-          const int cidx = h2 * 6 + 2 * q;
-          u[cidx * 2 + 0] = r0.x * w00 + r1.x * w10;
-          u[cidx * 2 + 1] = r0.x * w01 + r1.x * w11;
-          u[cidx * 2 + 2] = r0.y * w00 + r1.y * w10;
-          u[cidx * 2 + 3] = r0.y * w01 + r1.y * w11;
-          const double2 s0 = Jj[h2 * 6 + q];
-          const double2 s1 = Jj[h2 * 6 + 3 + q];
-          v[cidx] = s0.x;      v[cidx + 1] = s0.y;        // v[r'][c] at r'*12 + c
-          v[12 + cidx] = s1.x; v[12 + cidx + 1] = s1.y;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 24; ++k) { u[k] = 0.0; v[k] = 0.0; }
-    }
-    __syncwarp(hmask);
-    const int ne16 = (int)min(16L, end - base);
-    for (int e2 = 0; e2 < ne16; ++e2) {
-      const double* uu = U + e2 * kUVStride + (3 * tr) * 2;
-      const double* vv = V + e2 * kUVStride + 3 * tc;
-      const double a00 = uu[0], a01 = uu[1], a10 = uu[2], a11 = uu[3], a20 = uu[4], a21 = uu[5];
-      const double b00 = vv[0], b01 = vv[1], b02 = vv[2], b10 = vv[12], b11 = vv[13], b12 = vv[14];
-      acc[0] += a00 * b00 + a01 * b10; acc[1] += a00 * b01 + a01 * b11; acc[2] += a00 * b02 + a01 * b12;
-      acc[3] += a10 * b00 + a11 * b10; acc[4] += a10 * b01 + a11 * b11; acc[5] += a10 * b02 + a11 * b12;
-      acc[6] += a20 * b00 + a21 * b10; acc[7] += a20 * b01 + a21 * b11; acc[8] += a20 * b02 + a21 * b12;
-    }
-    __syncwarp(hmask);
-  }
-  if (!live) return;
-
-  // ---- scale, damp, mask constants, store
-  const unsigned ma = ne.pose_mask[a], mb = ne.pose_mask[b];
-  // tile-packed destination: row block b (>= a), column block a
-  double* tile = S + (long)tile_slot[(b / kFramesPerTile) * T + (a / kFramesPerTile)] * kTile * kTile;
-  const int ra = (a % kFramesPerTile) * kFrameParams, rb = (b % kFramesPerTile) * kFrameParams;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int r = 3 * tr + k;
-    const double sa = ne.scale_c[12L * a + r];
-    const bool rconst = (ma >> r) & 1;
-#pragma unroll
-    for (int l = 0; l < 3; ++l) {
-      const int c = 3 * tc + l;
-      const double sb = ne.scale_c[12L * b + c];
-      const bool cconst = (mb >> c) & 1;
-      double val = -sa * acc[k * 3 + l] * sb;
-      if (a == b) {
-        val += sa * ne.B[(long)a * 144 + r * 12 + c] * sb;
-        if (r == c) {
-          const double diag = sa * ne.B[(long)a * 144 + r * 13] * sa;
-          const double d2 = rconst ? 1.0 : fmin(fmax(diag, o.min_diag), o.max_diag) / o.radius;
-          ne.d2_c[12L * a + r] = d2;
-          val += d2;
-        }
-      }
-      if (rconst || cconst) val = (a == b && r == c) ? 1.0 : 0.0;
-      if (a == b) tile[(ra + r) * kTile + ra + c] = val;
-      else        tile[(rb + c) * kTile + ra + r] = val;       // lower triangle: row block b > col block a
-    }
-    if (a == b && tc == 0)   // rhs of  S y = rhs  (y = -scaled step)
-      rhs[12L * a + r] = rconst ? 0.0 : sa * (ne.gc[12L * a + r] - ne.wf[12L * a + r]);
-  }
-}
-
 }  // namespace
 
 void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
@@ -377,14 +260,6 @@ void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, 
 void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s) {
   if (n_points <= 0) return;
   point_invert_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(n_points, ne, o);
-}
-
-void launch_schur_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
-                         LmOptionsDev o, double* S, const int* tile_slot, int n_tiles, double* rhs,
-                         cudaStream_t s) {
-  if (st.n_blocks <= 0) return;
-  const int per = kSchurThreads / 16;
-  schur_blocks_kernel<<<(st.n_blocks + per - 1) / per, kSchurThreads, 0, s>>>(st, obs, jac, ne, o, S, tile_slot, n_tiles, rhs);
 }
 
 }  // namespace rsba

@@ -1,0 +1,284 @@
+// K2s -- the Schur complement of the point blocks as a tile-level SYRK on the FP64 tensor path.
+//
+// Supersedes the reduction loop of Ceres' SchurEliminator::Eliminate (third-party, reached
+// through ceres::Solve with SPARSE_SCHUR, CeresHandler.h:403,419):
+//     S = diag(s B s + D^2) - sum_p E_p C_p^-1 E_p^T .
+// With C_p'^-1 = L^-T L^-1 (3x3 Cholesky inverted in registers, k2_normal.cu) the per-observation
+// block  F_i = s_c Jc_i^T (Jx_i s_p) L^-T  (12x3) makes the point term a plain Gram product:
+//     sum_p E_p C_p^-1 E_p^T = Phi Phi^T,   Phi = [F_i] block-sparse, 12F x 3P.
+// Frames are cut into tiles of 8 (96 rows, the Cholesky tile).  For every (frame tile, point)
+// incidence phi_build writes one dense k-major panel [3][96(+4 pad)]; rows of frames that do not
+// see the point are zero.  A tile pair (A <= B) then is a dense GEMM over the points seen from
+// both tiles, K = 3 per point:
+//     S(B, A) -= sum_p Phi(B,p) Phi(A,p)^T                      96 x 96, mma.sync.m8n8k4.f64
+// Long pairs are split along K into work items of <= 512 points whose 96x96 partial products
+// are summed in a fixed order by schur_reduce (bit-reproducible, no atomics), which also adds
+// the camera diagonal blocks, the LM diagonal and the constant-parameter identity rows and
+// places the tile at its (permuted) position of the tile-packed reduced matrix.
+//
+// Data movement: panels are 2400-byte contiguous records, fetched by TMA bulk copies
+// (cp.async.bulk.shared::cluster.global.mbarrier) into a 3-stage shared-memory ring; the kernel
+// is bound by the FP64 pipe (tcgen05 has no FP64 kind: DMMA == DFMA rate, 37.1 TFLOP/s measured).
+#include "lm.cuh"
+
+namespace rsba {
+namespace {
+
+constexpr int kChunkPts = 8;                       // points per pipeline stage (24 K columns)
+constexpr int kStages = 3;
+constexpr int kOperandDoubles = kChunkPts * kPanelDoubles;       // 2400 doubles
+constexpr int kStageDoubles = 2 * kOperandDoubles;               // row side | column side
+constexpr unsigned kPanelBytes = kPanelDoubles * sizeof(double);
+constexpr size_t kSyrkSmem = (size_t)kStages * kStageDoubles * sizeof(double) + 64;
+
+// ---------------------------------------------------------------- panels
+// One thread per (incidence, frame slot): F = sum over the slot's observations (more than one only
+// when a point was observed twice in one frame) of  s_c Jc^T (Jx s_p) L^-T ; constant camera
+// parameters get zero rows, constant points have L^-1 = 0 and never appear in a pair.
+__global__ void __launch_bounds__(256)
+phi_build_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)st.n_inc * 8) return;
+  const int inc = (int)(t >> 3), fs = (int)(t & 7);
+  double F[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) F[k] = 0.0;
+  const int cnt = st.slot_cnt[t];
+  if (cnt > 0) {
+    const int p = st.inc_point[inc];
+    const int f = st.inc_tile[inc] * kFramesPerTile + fs;
+    const double* Mi = ne.Minv + 6L * p;
+    const double m00 = Mi[0], m10 = Mi[1], m11 = Mi[2], m20 = Mi[3], m21 = Mi[4], m22 = Mi[5];
+    const double sp0 = ne.scale_p[3L * p], sp1 = ne.scale_p[3L * p + 1], sp2 = ne.scale_p[3L * p + 2];
+    const unsigned mask = ne.pose_mask[f];
+    double sc[12];
+#pragma unroll
+    for (int a = 0; a < 12; ++a) sc[a] = ((mask >> a) & 1) ? 0.0 : ne.scale_c[12L * f + a];
+    const int beg = st.slot_beg[t];
+    for (int d = 0; d < cnt; ++d) {
+      const long i = st.pt_obs[beg + d];
+      const double2* J = reinterpret_cast<const double2*>(jac + i * kJacDoubles);
+      const double2 x0 = J[12], x1 = J[13], x2 = J[14];   // Jx rows: (x0.x x0.y x1.x) (x1.y x2.x x2.y)
+      // xm[row][k] = sum_c Jx[row][c] s_p[c] L^-1[k][c]
+      const double a0 = x0.x * sp0, a1 = x0.y * sp1, a2 = x1.x * sp2;
+      const double b0 = x1.y * sp0, b1 = x2.x * sp1, b2 = x2.y * sp2;
+      const double xa0 = a0 * m00, xa1 = a0 * m10 + a1 * m11, xa2 = a0 * m20 + a1 * m21 + a2 * m22;
+      const double xb0 = b0 * m00, xb1 = b0 * m10 + b1 * m11, xb2 = b0 * m20 + b1 * m21 + b2 * m22;
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const double2 r0 = J[h2 * 6 + q], r1 = J[h2 * 6 + 3 + q];   // rows 0/1, columns 2q, 2q+1 of this half
+          const int a = h2 * 6 + 2 * q;
+          const double j00 = r0.x * sc[a], j10 = r1.x * sc[a];
+          const double j01 = r0.y * sc[a + 1], j11 = r1.y * sc[a + 1];
+          F[3 * a + 0] += j00 * xa0 + j10 * xb0;
+          F[3 * a + 1] += j00 * xa1 + j10 * xb1;
+          F[3 * a + 2] += j00 * xa2 + j10 * xb2;
+          F[3 * a + 3] += j01 * xa0 + j11 * xb0;
+          F[3 * a + 4] += j01 * xa1 + j11 * xb1;
+          F[3 * a + 5] += j01 * xa2 + j11 * xb2;
+        }
+    }
+  }
+  double* dst = ne.Phi + (long)inc * kPanelDoubles + fs * kFrameParams;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double2* d2 = reinterpret_cast<double2*>(dst + k * kPanelLd);
+#pragma unroll
+    for (int a = 0; a < 12; a += 2) d2[a >> 1] = make_double2(F[3 * a + k], F[3 * (a + 1) + k]);
+  }
+}
+
+// ---------------------------------------------------------------- mbarrier / TMA helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------- tile-pair SYRK
+// One CTA per work item.  8 warps; warp w owns the 48 x 24 patch (w>>2, w&3) of the 96 x 96 tile.
+__global__ void __launch_bounds__(256, 1)
+schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entries,
+                  const int4* __restrict__ items, double* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage_base = reinterpret_cast<double*>(smem_raw);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kStages * kStageDoubles * sizeof(double));
+
+  const int4 item = items[blockIdx.x];
+  const int beg = item.y, nchunks = item.z / kChunkPts;
+  const bool diag = item.w != 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer: warp 0; lane q < 8 fetches the row-side panel of point q, lane 8+q the column side
+  auto issue = [&](int c) {
+    const int s = c % kStages;
+    const unsigned bar = smem_u32(&bars[s]);
+    if (lane == 0) mbar_expect_tx(bar, (diag ? 1u : 2u) * kChunkPts * kPanelBytes);
+    __syncwarp();
+    if (lane < (diag ? 8 : 16)) {
+      const int q = lane & 7, side = lane >> 3;
+      const int2 e = entries[beg + c * kChunkPts + q];
+      const int inc = side ? e.y : e.x;
+      double* dst = stage_base + (size_t)s * kStageDoubles + side * kOperandDoubles + q * kPanelDoubles;
+      tma_load_1d(smem_u32(dst), Phi + (long)inc * kPanelDoubles, kPanelBytes, bar);
+    }
+  };
+  if (warp == 0) {
+    for (int c = 0; c < kStages && c < nchunks; ++c) issue(c);
+  }
+
+  const int m0 = (warp >> 2) * 48, n0 = (warp & 3) * 24;
+  const int fr = lane >> 2, fc = lane & 3;
+  double acc[6][3][2];
+#pragma unroll
+  for (int mi = 0; mi < 6; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c % kStages;
+    mbar_wait(smem_u32(&bars[s]), (unsigned)((c / kStages) & 1));
+    const double* R = stage_base + (size_t)s * kStageDoubles;
+    const double* Cc = diag ? R : R + kOperandDoubles;
+#pragma unroll
+    for (int ks = 0; ks < (3 * kChunkPts) / 4; ++ks) {
+      const int krow = (4 * ks + fc) * kPanelLd + fr;
+      double a[6], b[3];
+#pragma unroll
+      for (int mi = 0; mi < 6; ++mi) a[mi] = R[krow + m0 + 8 * mi];
+#pragma unroll
+      for (int ni = 0; ni < 3; ++ni) b[ni] = Cc[krow + n0 + 8 * ni];
+#pragma unroll
+      for (int mi = 0; mi < 6; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 3; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+    __syncthreads();                         // every warp is done with stage s
+    if (warp == 0 && c + kStages < nchunks) issue(c + kStages);
+  }
+
+  double* out = partial + (long)blockIdx.x * kTile * kTile;
+#pragma unroll
+  for (int mi = 0; mi < 6; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 3; ++ni)
+      *reinterpret_cast<double2*>(out + (m0 + 8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc) =
+          make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+}
+
+// ---------------------------------------------------------------- reduce + epilogue
+// grid (n_pairs, 9): 1024 elements of the pair's tile per CTA, 4 per thread.
+__global__ void __launch_bounds__(256)
+schur_reduce_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, double* __restrict__ S,
+                    const int* __restrict__ tile_slot, int T, int n_frames) {
+  const int pr = blockIdx.x;
+  const int A = st.pair_a[pr], B = st.pair_b[pr];
+  const int ib = st.pair_item_ptr[pr], ie = st.pair_item_ptr[pr + 1];
+  const int pa = st.tile_pos[A], pb = st.tile_pos[B];
+  const bool transposed = pb < pa;           // rows must be the later position (lower triangle)
+  double* tile = S + (long)tile_slot[(transposed ? pa : pb) * T + (transposed ? pb : pa)] * kTile * kTile;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = blockIdx.y * 1024 + u * 256 + threadIdx.x;
+    const int r = e / kTile, c = e % kTile;
+    double sum = 0.0;
+    for (int it = ib; it < ie; ++it) sum += ne.partial[(long)it * kTile * kTile + e];
+    double val = -sum;
+    if (A == B && r / kFrameParams == c / kFrameParams) {
+      const int f = A * kFramesPerTile + r / kFrameParams;
+      const int rr = r % kFrameParams, cc = c % kFrameParams;
+      if (f >= n_frames) {
+        val = (rr == cc) ? 1.0 : 0.0;        // padding rows of the last tile
+      } else {
+        const unsigned m = ne.pose_mask[f];
+        if (((m >> rr) & 1) || ((m >> cc) & 1)) {
+          val = (rr == cc) ? 1.0 : 0.0;      // constant parameter: identity row
+        } else {
+          const double sr = ne.scale_c[12L * f + rr], scl = ne.scale_c[12L * f + cc];
+          const double b = sr * ne.B[(long)f * 144 + rr * 12 + cc] * scl;
+          val += b;
+          if (rr == cc) val += fmin(fmax(b, o.min_diag), o.max_diag) / o.radius;
+        }
+      }
+    }
+    if (transposed) tile[c * kTile + r] = val;
+    else            tile[r * kTile + c] = val;
+  }
+}
+
+// LM diagonal of the camera parameters and the right-hand side of  S y = rhs  (y = -scaled step),
+// both in the permuted order of the reduced system.
+__global__ void __launch_bounds__(256)
+camera_rhs_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, int n_frames, double* __restrict__ rhs) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_frames * kFrameParams) return;
+  const int f = t / kFrameParams, k = t % kFrameParams;
+  const bool cst = (ne.pose_mask[f] >> k) & 1;
+  const double s = ne.scale_c[t];
+  const double diag = s * ne.B[(long)f * 144 + k * 13] * s;
+  ne.d2_c[t] = cst ? 1.0 : fmin(fmax(diag, o.min_diag), o.max_diag) / o.radius;
+  const long pos = (long)st.tile_pos[f / kFramesPerTile] * kTile + (f % kFramesPerTile) * kFrameParams + k;
+  rhs[pos] = cst ? 0.0 : s * (ne.gc[t] - ne.wf[t]);
+}
+
+}  // namespace
+
+void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+                      cudaStream_t s) {
+  if (st.n_inc <= 0) return;
+  const long n = (long)st.n_inc * 8;
+  phi_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, obs, jac, ne);
+}
+
+void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem);
+    attr_done = true;
+  }
+  if (st.n_items <= 0) return;
+  schur_syrk_kernel<<<st.n_items, 256, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
+}
+
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,
+                         const int* tile_slot, int n_tiles, int n_frames, double* rhs, cudaStream_t s) {
+  if (st.n_pairs > 0)
+    schur_reduce_kernel<<<dim3(st.n_pairs, 9), 256, 0, s>>>(st, ne, o, S, tile_slot, n_tiles, n_frames);
+  if (n_frames > 0)
+    camera_rhs_kernel<<<(n_frames * kFrameParams + 255) / 256, 256, 0, s>>>(st, ne, o, n_frames, rhs);
+}
+
+}  // namespace rsba

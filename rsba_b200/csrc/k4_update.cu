@@ -41,13 +41,15 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
 
 // frames: delta_c, trial poses, partial scalars -> scratch[0..2] (single CTA)
 __global__ void __launch_bounds__(kRedThreads)
-frame_step_kernel(NormalEq ne, const double* __restrict__ y, int n, const double* __restrict__ poses,
-                  double* __restrict__ delta_c, double* __restrict__ trial, double* __restrict__ scratch) {
+frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* __restrict__ y, int n,
+                  const double* __restrict__ poses, double* __restrict__ delta_c, double* __restrict__ trial,
+                  double* __restrict__ scratch) {
   __shared__ double sh[32];
   double gd = 0.0, dd = 0.0, nn = 0.0;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const double sc = ne.scale_c[t];
-    const double ys = y[t];
+    // y lives in the (tile-permuted) order of the reduced system
+    const double ys = y[(long)tile_pos[t / kTile] * kTile + t % kTile];
     const double d = -sc * ys;
     delta_c[t] = d;
     trial[t] = poses[t] + d;
@@ -183,7 +185,7 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
                         double* trial_points, double* scalars, double* scratch, cudaStream_t s) {
-  frame_step_kernel<<<1, kRedThreads, 0, s>>>(ne, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
+  frame_step_kernel<<<1, kRedThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
   const int nb = (n_points + 127) / 128;
   if (nb > 0)
     point_step_kernel<<<nb, 128, 0, s>>>(st, obs, jac, ne, delta_c, n_points, points, delta_p, trial_points, scratch);

@@ -22,14 +22,31 @@ struct SchurStructure {
   const int* chunk_cnt;   // [n_chunks]
   const int* frame_chunk_ptr;  // [F+1] chunks of frame f
   int n_chunks;
-  // camera-pair blocks (a <= b) of the reduced matrix and their (i, j) observation pairs
-  const int* blk_a;       // [n_blocks]
-  const int* blk_b;       // [n_blocks]
-  const long* blk_ptr;    // [n_blocks+1]
-  const int2* entries;    // [n_entries]  (obs i in frame a, obs j in frame b, same point)
-  int n_blocks;
+  // ---- Schur complement as a tile-level SYRK  S -= Phi Phi^T  (k2_schur.cu)
+  // incidence = (frame tile A, point p) with at least one observation of p in frames 8A..8A+7;
+  // its panel Phi[inc] is [3][kPanelLd] doubles (k-major, 96 rows = 8 frame slots x 12).
+  int n_inc;
+  const int* inc_point;    // [n_inc]
+  const int* inc_tile;     // [n_inc]
+  const int* slot_beg;     // [n_inc*8] first index into pt_obs of the observations in that slot, -1 if none
+  const unsigned char* slot_cnt;  // [n_inc*8] number of observations in the slot (duplicates in one frame)
+  // tile pair (A <= B in frame-tile order): output tile rows = frames of B, columns = frames of A
+  int n_pairs;
+  const int* pair_a;       // [n_pairs]
+  const int* pair_b;       // [n_pairs]
+  const int* pair_item_ptr;  // [n_pairs+1] work items (K segments) of the pair
+  // work item = up to kSchurSegPoints common points of one pair; entries padded to a multiple of 8
+  // with the all-zero panel (index n_inc)
+  int n_items;
+  const int4* items;       // [n_items] (pair, first entry, entry count, A == B)
+  const int2* entries;     // (incidence on the row side B, incidence on the column side A)
   long n_entries;
+  const int* tile_pos;     // [T] position of frame tile A in the (permuted) reduced system
 };
+
+constexpr int kPanelLd = 100;                 // 96 rows + 4 pad: conflict-free DMMA fragment loads
+constexpr int kPanelDoubles = 3 * kPanelLd;   // one bulk copy of 2400 bytes
+constexpr int kSchurSegPoints = 512;
 
 struct NormalEq {
   // unscaled blocks of J^T J and J^T r
@@ -40,6 +57,9 @@ struct NormalEq {
   double* gp;       // [P][3]
   double* Cinv;     // [P][6]    s_p (s_p C s_p + D^2)^-1 s_p  (zero for constant points)
   double* tp;       // [P][3]    Cinv * gp
+  double* Minv;     // [P][6]    L^-1 of the damped scaled point block (m00 m10 m11 m20 m21 m22)
+  double* Phi;      // [n_inc+1][3][kPanelLd]  panels s_c Jc^T (Jx s_p) L^-T; last panel all zero
+  double* partial;  // [n_items][96*96] per-item partial products of the Schur SYRK
   double* scale_c;  // [12F] Jacobi scaling (1 for constant parameters)
   double* scale_p;  // [3P]
   double* d2_c;     // [12F] LM diagonal (scaled space) of the current solve
@@ -60,11 +80,13 @@ void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const dou
                          int n_frames, NormalEq ne, bool with_wf, cudaStream_t s);
 void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, cudaStream_t s);
 void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s);
-// S (tile-packed, see TileSchedule: lower triangle + full diagonal blocks) and rhs
-struct TileSchedule;
-void launch_schur_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
-                         LmOptionsDev o, double* S, const int* tile_slot, int n_tiles, double* rhs,
-                         cudaStream_t s);
+// Schur complement (k2_schur.cu).  S is tile-packed (see TileSchedule: structurally non-zero lower
+// tiles, diagonal tiles stored as full squares); rhs/d2_c in the permuted order given by tile_pos.
+void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+                      cudaStream_t s);
+void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s);
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,
+                         const int* tile_slot, int n_tiles, int n_frames, double* rhs, cudaStream_t s);
 
 // ---- K3 ---------------------------------------------------------------------------------
 struct TileSchedule {

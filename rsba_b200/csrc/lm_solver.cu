@@ -19,8 +19,10 @@ namespace rsba {
 
 struct LmState {
   // ---- structure (device)
-  DeviceBuffer<int> pt_ptr, pt_obs, chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr, blk_a, blk_b;
-  DeviceBuffer<long> blk_ptr;
+  DeviceBuffer<int> pt_ptr, pt_obs, chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr;
+  DeviceBuffer<int> inc_point, inc_tile, slot_beg, pair_a, pair_b, pair_item_ptr, tile_pos;
+  DeviceBuffer<unsigned char> slot_cnt;
+  DeviceBuffer<int4> items;
   DeviceBuffer<int2> entries;
   DeviceBuffer<int2> nz_tiles, upd;
   DeviceBuffer<int> tile_slot, row_ptr, rows, lrow_ptr, lrow_cols;
@@ -30,11 +32,12 @@ struct LmState {
   std::vector<int> h_row_ptr;
   std::vector<long> h_upd_ptr;
   std::vector<int2> h_nz_tiles;
+  std::vector<int> h_tile_pos, h_pos_tile;   // frame tile -> position in S, and its inverse
   SchurStructure st{};
   TileSchedule ts{};
   bool dense = false;
   // ---- numeric state (device)
-  DeviceBuffer<double> B, gc, wf, C, gp, Cinv, tp, scale_c, scale_p, d2_c, d2_p, partials;
+  DeviceBuffer<double> B, gc, wf, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
   DeviceBuffer<double> S, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
   DeviceBuffer<int> info;
   NormalEq ne{};
@@ -93,59 +96,83 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     }
     frame_chunk_ptr[F] = (int)chunk_frame.size();
   }
-  // camera-pair blocks: count, prefix, fill
-  std::vector<unsigned> cnt((size_t)F * F, 0u);
-  for (int p = 0; p < P; ++p) {
-    if (h->point_const[p]) continue;  // constant points are not eliminated: no Schur term
-    const int b = pt_ptr[p], e = pt_ptr[p + 1];
-    for (int x = b; x < e; ++x) {
-      const int fa = fr[pt_obs[x]];
-      for (int y = x; y < e; ++y) {
-        const int fb = fr[pt_obs[y]];
-        cnt[(size_t)fa * F + fb] += (fa == fb && x != y) ? 2u : 1u;
-      }
-    }
-  }
-  std::vector<int> blk_a, blk_b;
-  std::vector<long> blk_ptr(1, 0);
-  std::vector<unsigned> blk_id((size_t)F * F, 0xFFFFFFFFu);
-  for (int a = 0; a < F; ++a)
-    for (int b = a; b < F; ++b) {
-      const unsigned c = cnt[(size_t)a * F + b];
-      if (c == 0 && a != b) continue;
-      blk_id[(size_t)a * F + b] = (unsigned)blk_a.size();
-      blk_a.push_back(a);
-      blk_b.push_back(b);
-      blk_ptr.push_back(blk_ptr.back() + c);
-    }
-  const long n_entries = blk_ptr.back();
-  std::vector<int2> entries((size_t)std::max<long>(n_entries, 1));
+  // ---- Schur SYRK structure: (frame tile, point) incidences, tile pairs, work items
+  const int T = (int)((12L * F + kTile - 1) / kTile);
+  std::vector<int> tile_pos(std::max(T, 1));
+  for (int t = 0; t < T; ++t) tile_pos[t] = t;
+  std::vector<int> inc_point, inc_tile, slot_beg;
+  std::vector<unsigned char> slot_cnt;
+  struct PairEntry { long key; int inc_a, inc_b; };
+  std::vector<PairEntry> pe;
   {
-    std::vector<long> cur(blk_ptr.begin(), blk_ptr.end() - 1);
+    std::vector<int> mine;  // incidences of the current point
     for (int p = 0; p < P; ++p) {
-      if (h->point_const[p]) continue;
+      if (h->point_const[p]) continue;  // constant points are not eliminated: no Schur term
+      mine.clear();
       const int b = pt_ptr[p], e = pt_ptr[p + 1];
       for (int x = b; x < e; ++x) {
-        const int ox = pt_obs[x], fa = fr[ox];
-        for (int y = x; y < e; ++y) {
-          const int oy = pt_obs[y], fb = fr[oy];
-          const unsigned id = blk_id[(size_t)fa * F + fb];
-          entries[cur[id]++] = make_int2(ox, oy);
-          if (fa == fb && x != y) entries[cur[id]++] = make_int2(oy, ox);
+        const int f = fr[pt_obs[x]], A = f / kFramesPerTile, fs = f % kFramesPerTile;
+        if (mine.empty() || inc_tile[mine.back()] != A) {
+          mine.push_back((int)inc_point.size());
+          inc_point.push_back(p);
+          inc_tile.push_back(A);
+          slot_beg.insert(slot_beg.end(), 8, -1);
+          slot_cnt.insert(slot_cnt.end(), 8, 0);
         }
+        const size_t sl = (size_t)mine.back() * 8 + fs;
+        if (slot_cnt[sl] == 0) slot_beg[sl] = x;
+        if (slot_cnt[sl] == 255) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
+        slot_cnt[sl]++;
       }
+      for (size_t x = 0; x < mine.size(); ++x)
+        for (size_t y = x; y < mine.size(); ++y)
+          pe.push_back({(long)inc_tile[mine[x]] * T + inc_tile[mine[y]], mine[x], mine[y]});
     }
   }
+  const int n_inc = (int)inc_point.size();
+  for (int t = 0; t < T; ++t) pe.push_back({(long)t * T + t, -1, -1});   // every diagonal tile is a pair
+  std::stable_sort(pe.begin(), pe.end(), [](const PairEntry& x, const PairEntry& y) { return x.key < y.key; });
+  std::vector<int> pair_a, pair_b, pair_item_ptr;
+  std::vector<int4> items;
+  std::vector<int2> entries;
+  for (size_t i = 0; i < pe.size();) {
+    size_t j = i;
+    while (j < pe.size() && pe[j].key == pe[i].key) ++j;
+    const int A = (int)(pe[i].key / T), Bt = (int)(pe[i].key % T);
+    const int pair = (int)pair_a.size();
+    pair_a.push_back(A);
+    pair_b.push_back(Bt);
+    pair_item_ptr.push_back((int)items.size());
+    size_t k = i;
+    while (k < j) {
+      const int first = (int)entries.size();
+      int cnt = 0;
+      for (; k < j && cnt < kSchurSegPoints; ++k) {
+        if (pe[k].inc_a < 0) continue;                       // the diagonal marker
+        entries.push_back(make_int2(pe[k].inc_b, pe[k].inc_a));   // (row side B, column side A)
+        ++cnt;
+      }
+      if (cnt == 0) continue;
+      while (cnt % 8) { entries.push_back(make_int2(n_inc, n_inc)); ++cnt; }   // zero panel
+      items.push_back(make_int4(pair, first, cnt, A == Bt ? 1 : 0));
+    }
+    i = j;
+  }
+  pair_item_ptr.push_back((int)items.size());
+  if (entries.empty()) entries.push_back(make_int2(n_inc, n_inc));
+  if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
+  const int n_items = (int)pair_item_ptr.back();
   // ---- tile graph + symbolic fill
-  const int T = (int)((12L * F + kTile - 1) / kTile);
   std::vector<char> nz((size_t)T * T, 0);
   for (int i = 0; i < T; ++i) nz[(size_t)i * T + i] = 1;
   if (dense) {
     for (int i = 0; i < T; ++i)
       for (int j = 0; j <= i; ++j) nz[(size_t)i * T + j] = 1;
   } else {
-    for (size_t k = 0; k < blk_a.size(); ++k)
-      nz[(size_t)(blk_b[k] / kFramesPerTile) * T + blk_a[k] / kFramesPerTile] = 1;
+    for (size_t k = 0; k < pair_a.size(); ++k) {
+      const int pa = tile_pos[pair_a[k]], pb = tile_pos[pair_b[k]];
+      nz[(size_t)std::max(pa, pb) * T + std::min(pa, pb)] = 1;
+    }
   }
   std::vector<int> row_ptr(T + 1, 0), rows;
   std::vector<long> upd_ptr(T + 1, 0);
@@ -181,14 +208,19 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   int rc;
 #define UP(dev, host) if ((rc = upload(lm->dev, host, s))) return rc
   UP(pt_ptr, pt_ptr); UP(pt_obs, pt_obs); UP(chunk_frame, chunk_frame); UP(chunk_beg, chunk_beg);
-  UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr); UP(blk_a, blk_a); UP(blk_b, blk_b);
-  UP(blk_ptr, blk_ptr); UP(entries, entries); UP(nz_tiles, nz_tiles); UP(upd, upd); UP(tile_slot, tile_slot);
+  UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr);
+  UP(inc_point, inc_point); UP(inc_tile, inc_tile); UP(slot_beg, slot_beg); UP(slot_cnt, slot_cnt);
+  UP(pair_a, pair_a); UP(pair_b, pair_b); UP(pair_item_ptr, pair_item_ptr); UP(items, items); UP(tile_pos, tile_pos);
+  UP(entries, entries); UP(nz_tiles, nz_tiles); UP(upd, upd); UP(tile_slot, tile_slot);
   UP(row_ptr, row_ptr); UP(rows, rows); UP(lrow_ptr, lrow_ptr); UP(lrow_cols, lrow_cols); UP(upd_ptr, upd_ptr);
   UP(pose_mask, h->pose_mask); UP(point_const, h->point_const);
 #undef UP
   lm->h_row_ptr = row_ptr;
   lm->h_upd_ptr = upd_ptr;
   lm->h_nz_tiles = nz_tiles;
+  lm->h_tile_pos = tile_pos;
+  lm->h_pos_tile.assign(tile_pos.size(), 0);
+  for (int t = 0; t < T; ++t) lm->h_pos_tile[tile_pos[t]] = t;
   lm->dense = dense;
   lm->n_pad = (long)T * kTile;
 
@@ -196,14 +228,21 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.pt_ptr = lm->pt_ptr.ptr; st.pt_obs = lm->pt_obs.ptr;
   st.chunk_frame = lm->chunk_frame.ptr; st.chunk_beg = lm->chunk_beg.ptr; st.chunk_cnt = lm->chunk_cnt.ptr;
   st.frame_chunk_ptr = lm->frame_chunk_ptr.ptr; st.n_chunks = (int)chunk_frame.size();
-  st.blk_a = lm->blk_a.ptr; st.blk_b = lm->blk_b.ptr; st.blk_ptr = lm->blk_ptr.ptr; st.entries = lm->entries.ptr;
-  st.n_blocks = (int)blk_a.size(); st.n_entries = n_entries;
+  st.n_inc = n_inc; st.inc_point = lm->inc_point.ptr; st.inc_tile = lm->inc_tile.ptr;
+  st.slot_beg = lm->slot_beg.ptr; st.slot_cnt = lm->slot_cnt.ptr;
+  st.n_pairs = (int)pair_a.size(); st.pair_a = lm->pair_a.ptr; st.pair_b = lm->pair_b.ptr;
+  st.pair_item_ptr = lm->pair_item_ptr.ptr; st.n_items = n_items; st.items = lm->items.ptr;
+  st.entries = lm->entries.ptr; st.n_entries = (long)entries.size(); st.tile_pos = lm->tile_pos.ptr;
 
   // ---- numeric buffers
   const size_t Fz = std::max(F, 1), Pz = std::max(P, 1);
   RSBA_CUDA_TRY(lm->B.resize(Fz * 144)); RSBA_CUDA_TRY(lm->gc.resize(Fz * 12)); RSBA_CUDA_TRY(lm->wf.resize(Fz * 12));
   RSBA_CUDA_TRY(lm->C.resize(Pz * 6)); RSBA_CUDA_TRY(lm->gp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Cinv.resize(Pz * 6));
-  RSBA_CUDA_TRY(lm->tp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->scale_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->scale_p.resize(Pz * 3));
+  RSBA_CUDA_TRY(lm->tp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Minv.resize(Pz * 6));
+  RSBA_CUDA_TRY(lm->Phi.resize((size_t)(n_inc + 1) * kPanelDoubles));
+  RSBA_CUDA_TRY(cudaMemsetAsync(lm->Phi.ptr, 0, lm->Phi.bytes(), s));   // pad columns + the zero panel
+  RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kTile * kTile));
+  RSBA_CUDA_TRY(lm->scale_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->scale_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->d2_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->d2_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 168));
   RSBA_CUDA_TRY(lm->S.resize(std::max<size_t>(nz_tiles.size(), 1) * kTile * kTile));
@@ -219,7 +258,8 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
 
   NormalEq& ne = lm->ne;
   ne.B = lm->B.ptr; ne.gc = lm->gc.ptr; ne.wf = lm->wf.ptr; ne.C = lm->C.ptr; ne.gp = lm->gp.ptr;
-  ne.Cinv = lm->Cinv.ptr; ne.tp = lm->tp.ptr; ne.scale_c = lm->scale_c.ptr; ne.scale_p = lm->scale_p.ptr;
+  ne.Cinv = lm->Cinv.ptr; ne.tp = lm->tp.ptr; ne.Minv = lm->Minv.ptr; ne.Phi = lm->Phi.ptr; ne.partial = lm->partial.ptr;
+  ne.scale_c = lm->scale_c.ptr; ne.scale_p = lm->scale_p.ptr;
   ne.d2_c = lm->d2_c.ptr; ne.d2_p = lm->d2_p.ptr; ne.partials = lm->partials.ptr;
   ne.pose_mask = lm->pose_mask.ptr; ne.point_const = lm->point_const.ptr;
 
@@ -261,8 +301,10 @@ void linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doub
   h->launches += 3;
   if (compute_scale) { launch_jacobi_scale(h->n_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
   launch_clear_tiles(lm->S.ptr, lm->ts, s);
-  launch_schur_blocks(lm->st, obs, h->d_jac.ptr, lm->ne, o, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, lm->rhs.ptr, s);
-  h->launches += 2;
+  launch_phi_build(lm->st, obs, h->d_jac.ptr, lm->ne, s);
+  launch_schur_syrk(lm->st, lm->ne, s);
+  launch_schur_reduce(lm->st, lm->ne, o, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, h->n_frames, lm->rhs.ptr, s);
+  h->launches += 5;
   stage_end(h, kStageSchur);
 }
 
@@ -495,17 +537,20 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
       RSBA_CUDA_TRY(cudaMemcpy(tile.data(), lm->S.ptr + sidx * kTile * kTile, tile.size() * sizeof(double), cudaMemcpyDeviceToHost));
       for (int r = 0; r < kTile; ++r)
         for (int c = 0; c < kTile; ++c) {
-          const long gr = (long)t.x * kTile + r, gcol = (long)t.y * kTile + c;
-          if (gr >= n || gcol >= n || gcol > gr) continue;
-          // inside a diagonal 12x12 block both triangles are stored; elsewhere mirror the lower part
+          // tile positions -> frame tiles (the caller sees the un-permuted system)
+          const long gr = (long)lm->h_pos_tile[t.x] * kTile + r, gcol = (long)lm->h_pos_tile[t.y] * kTile + c;
+          if (gr >= n || gcol >= n) continue;
+          if (t.x == t.y && c > r) continue;   // diagonal tiles: the factorisation reads the lower triangle
           S_out[gr * n + gcol] = tile[r * kTile + c];
           S_out[gcol * n + gr] = tile[r * kTile + c];
         }
     }
   }
   if (rhs_out) {
-    RSBA_CUDA_TRY(cudaMemcpy(rhs_out, lm->rhs.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
-    for (long k = 0; k < n; ++k) rhs_out[k] = -rhs_out[k];   // S delta_c' = rhs
+    std::vector<double> tmp((size_t)lm->n_pad);
+    RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToHost));
+    for (long k = 0; k < n; ++k)   // S delta_c' = rhs, un-permuted
+      rhs_out[k] = -tmp[(size_t)lm->h_tile_pos[k / kTile] * kTile + k % kTile];
   }
   factor_and_solve(h, lm);
   step_update(h, lm);
