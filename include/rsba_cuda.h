@@ -57,6 +57,8 @@ typedef struct rsba_solve_options {
   double huber_loss;                  /* 0 = no loss (SfmOptions.h:64, CeresHandler.h:85-90) */
   int verbose;                        /* minimizer_progress_to_stdout (CeresHandler.h:404) */
   int dense_cholesky;                 /* 1: ignore the tile occupancy map, factor S fully dense */
+  int reorder_tiles;                  /* 1: nested-dissection ordering of the reduced system (default);
+                                         0: natural (frame) order */
 } rsba_solve_options;
 
 /* Solver::Summary fields the reference reads (VideoSfMHandler.cc:593-596, 627-630). */
@@ -169,6 +171,20 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
 int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt, double radius,
                                  double* S, double* rhs, double* delta_poses,
                                  double* delta_points, double* model_cost_change);
+
+/* Host-only introspection of the symbolic analysis that precedes the factorisation (what CHOLMOD's
+ * analyse phase does for Ceres' SparseSchurComplementSolver); needs no device.  The reduced
+ * system is cut into n_tiles tiles of 96 rows (8 frames); pair_a/pair_b list the structurally
+ * non-zero tile pairs in frame order.  Two-call pattern: with all output pointers NULL only
+ * counts[] is filled: {levels, non-zero tiles after fill, trsm tiles, update triples, update
+ * groups, tile-level flops}.  Outputs (tile indices are positions after reordering):
+ *   tile_pos[n_tiles] frame tile -> position; nz_tiles[2*n_nz] (i, j); panels[n_tiles] sorted by
+ *   level; panel_ptr[levels+1]; trsm[2*n_trsm] (i, k); trsm_ptr[levels+1]; upd[3*n_upd] (i, j, k);
+ *   group_ptr[groups+1] (as long); level_group_ptr[levels+1]. */
+int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, const int* pair_b,
+                                  int dense, int reorder, long counts[6], int* tile_pos, int* nz_tiles,
+                                  int* panels, int* panel_ptr, int* trsm, int* trsm_ptr, int* upd,
+                                  long* group_ptr, int* level_group_ptr);
 
 /* ------------------------------------------------------------------ multi-GPU */
 /* One process per GPU.  Rank 0 obtains an id, the host framework broadcasts the 128 bytes,

@@ -39,7 +39,7 @@ SYMBOLS = [
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
-    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_nccl_unique_id",
+    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
 
@@ -60,6 +60,7 @@ class SolveOptions(C.Structure):
         ("huber_loss", C.c_double),
         ("verbose", C.c_int),
         ("dense_cholesky", C.c_int),
+        ("reorder_tiles", C.c_int),
     ]
 
 
@@ -139,6 +140,7 @@ def load_library():
     lib.rsba_cuda_observation_order.restype = C.c_long
     lib.rsba_cuda_solve.argtypes = [vp, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
     lib.rsba_cuda_linearize_and_step.argtypes = [vp, C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp, _dp]
+    lib.rsba_cuda_plan_reduced_system.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp] + [vp] * 9
     lib.rsba_cuda_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     lib.rsba_cuda_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
     lib.rsba_cuda_launch_count.argtypes = [vp]
@@ -352,6 +354,32 @@ class Problem:
     def stage_ms(self, stage) -> float:
         idx = STAGES.index(stage) if isinstance(stage, str) else int(stage)
         return float(self.lib.rsba_cuda_stage_ms(self._h, idx))
+
+
+def plan_reduced_system(n_tiles, pair_a, pair_b, dense=False, reorder=True):
+    """Host-only symbolic analysis of the reduced camera system (no GPU needed): ordering,
+    fill, elimination levels, conflict-free update groups.  Returns a dict of numpy arrays."""
+    lib = load_library()
+    pa = np.ascontiguousarray(pair_a, dtype=np.int32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.int32)
+    counts = np.zeros(6, dtype=np.int64)
+
+    def call(*outs):
+        rc = lib.rsba_cuda_plan_reduced_system(int(n_tiles), int(pa.size), _addr(pa), _addr(pb), int(dense),
+                                               int(reorder), _addr(counts), *[_addr(o) for o in outs])
+        if rc != RSBA_OK:
+            raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
+
+    call(*([None] * 9))
+    L, nnz, ntrsm, nupd, ngroups = (int(c) for c in counts[:5])
+    out = dict(tile_pos=np.zeros(n_tiles, np.int32), nz_tiles=np.zeros((nnz, 2), np.int32),
+               panels=np.zeros(n_tiles, np.int32), panel_ptr=np.zeros(L + 1, np.int32),
+               trsm=np.zeros((ntrsm, 2), np.int32), trsm_ptr=np.zeros(L + 1, np.int32),
+               upd=np.zeros((nupd, 3), np.int32), group_ptr=np.zeros(ngroups + 1, np.int64),
+               level_group_ptr=np.zeros(L + 1, np.int32))
+    call(*out.values())
+    out.update(n_levels=L, flops=float(counts[5]))
+    return out
 
 
 def nccl_unique_id() -> bytes:

@@ -5,10 +5,11 @@
 //
 // S is cut into 96x96 tiles (8 frames) and stored TILE-PACKED in HBM: only the structurally
 // non-zero lower tiles exist, slot = tile_slot[i*T + j], each tile row-major with ld = 96.
-// The host runs a symbolic factorisation on the tile graph once per scene (lm_structure.cu);
-// the numeric right-looking factorisation below only touches structurally non-zero tiles, so a
-// video-like (banded) scene costs O(n b^2) while a fully covisible scene degenerates to the
-// classic dense blocked algorithm.  Per panel k:
+// The host runs a nested-dissection ordering and a symbolic factorisation on the tile graph once
+// per scene (tile_plan.cu).  The numeric right-looking factorisation below only touches
+// structurally non-zero tiles, so a video-like (banded) scene costs O(n b^2) while a fully
+// covisible scene degenerates to the classic dense blocked algorithm; panels of one elimination
+// level are independent and share one launch of each kernel.  Per panel k:
 //   potrf_inv : L_kk = chol(A_kk) in shared memory (8x8-blocked), plus L_kk^-1 (explicit, so
 //               that everything below is a GEMM / GEMV and not a substitution chain)
 //   trsm      : L_ik = A_ik L_kk^-T              -- tile GEMM on the FP64 tensor cores (DMMA)
@@ -25,21 +26,18 @@ constexpr int kGemmLd = kTile + 4;  // GEMM smem leading dimension (conflict-fre
 
 // ---------------------------------------------------------------- clear structurally non-zero tiles
 __global__ void __launch_bounds__(256)
-clear_tiles_kernel(double* __restrict__ S, const int2* __restrict__ tiles, int n_real) {
-  const int2 t = tiles[blockIdx.x];          // slot == blockIdx.x
-  double* base = S + (long)blockIdx.x * kTile * kTile;
-  for (int e = threadIdx.x; e < kTile * kTile; e += blockDim.x) {
-    const int r = e / kTile, c = e % kTile;
-    double v = 0.0;
-    if (t.x == t.y && r == c && t.x * kTile + r >= n_real) v = 1.0;  // padding rows: identity
-    base[e] = v;
-  }
+clear_tiles_kernel(double* __restrict__ S) {
+  // every diagonal tile is rewritten by schur_reduce (incl. the identity padding rows); fill tiles
+  // that no tile pair touches must start from zero
+  double2* base = reinterpret_cast<double2*>(S + (long)blockIdx.x * kTile * kTile);
+  for (int e = threadIdx.x; e < kTile * kTile / 2; e += blockDim.x) base[e] = make_double2(0.0, 0.0);
 }
 
 // ---------------------------------------------------------------- diagonal tile: Cholesky + inverse
 __global__ void __launch_bounds__(256)
-potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int T, int k,
-                 double* __restrict__ Dinv, int* __restrict__ info) {
+potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int T,
+                 const int* __restrict__ panels, double* __restrict__ Dinv, int* __restrict__ info) {
+  const int k = panels[blockIdx.x];
   constexpr long ld = kTile;
   extern __shared__ double smem[];
   double* A = smem;                 // [96][97]  factor
@@ -169,26 +167,28 @@ __device__ __forceinline__ void load_tile(double* dst, const double* __restrict_
   }
 }
 
-// MODE 0 (trsm):   S(i,k) = S(i,k) * Dinv[k]^T           one CTA per i in rows(k)
-// MODE 1 (update): S(i,j) -= S(i,k) * S(j,k)^T           one CTA per (i,j) in upd(k)
+// MODE 0 (trsm):   S(i,k) = S(i,k) * Dinv[k]^T           one CTA per (i,k) of the level's trsm list
+// MODE 1 (update): S(i,j) -= S(i,k) * S(j,k)^T           one CTA per (i,j,k) of the update group
 template <int MODE>
 __global__ void __launch_bounds__(256)
-tile_gemm_kernel(double* S, const int* __restrict__ tile_slot, int T, int k, const int* __restrict__ rows,
-                 const int2* __restrict__ upd, const double* __restrict__ Dinv) {
+tile_gemm_kernel(double* S, const int* __restrict__ tile_slot, int T, const int2* __restrict__ trsm,
+                 const int4* __restrict__ upd, const double* __restrict__ Dinv) {
   constexpr long ld = kTile;
   extern __shared__ double smem[];
   double* As = smem;
   double* Bs = smem + kTile * kGemmLd;
-  int ti, tj;
+  int ti, tj, k;
   const double* Bsrc;
   if (MODE == 0) {
-    ti = rows[blockIdx.x];
-    tj = k;
+    const int2 p = trsm[blockIdx.x];
+    ti = p.x;
+    tj = k = p.y;
     Bsrc = Dinv + (long)k * kTile * kTile;
   } else {
-    const int2 p = upd[blockIdx.x];
+    const int4 p = upd[blockIdx.x];
     ti = p.x;
     tj = p.y;
+    k = p.z;
     Bsrc = S + (long)tile_slot[tj * T + k] * kTile * kTile;
   }
   const double* Asrc = S + (long)tile_slot[ti * T + k] * kTile * kTile;
@@ -233,93 +233,97 @@ tile_gemm_kernel(double* S, const int* __restrict__ tile_slot, int T, int k, con
     }
 }
 
-// ---------------------------------------------------------------- triangular solves (one CTA)
+// ---------------------------------------------------------------- triangular solves, one launch per level
 // x holds the right-hand side on entry and the solution of (L L^T) x = b on exit.
-__global__ void __launch_bounds__(1024)
-tile_solve_kernel(const double* __restrict__ S, TileSchedule ts, const double* __restrict__ Dinv,
-                  double* __restrict__ x) {
+// forward:  z_k = Linv_kk (b_k - sum_{j<k} L_kj z_j)      every j sits in a lower level
+__global__ void __launch_bounds__(256)
+solve_forward_kernel(const double* __restrict__ S, TileSchedule ts, const int* __restrict__ panels,
+                     double* __restrict__ x) {
   constexpr long ld = kTile;
   __shared__ double tmp[kTile];
-  __shared__ double part[32][kTile + 1];
+  const int k = panels[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = ts.n_tiles;
-  // ---- forward: z_k = Linv_kk (b_k - sum_{j<k} L_kj z_j)
-  for (int k = 0; k < T; ++k) {
-    for (int r = warp; r < kTile; r += 32) {
-      double s = 0.0;
-      for (int q = ts.lrow_ptr[k]; q < ts.lrow_ptr[k + 1]; ++q) {
-        const int j = ts.lrow_cols[q];
-        const double* lj = S + (long)ts.tile_slot[k * T + j] * kTile * kTile + (long)r * ld;
-        const double* xj = x + (long)j * kTile;
+  for (int r = warp; r < kTile; r += 8) {
+    double s = 0.0;
+    for (int q = ts.lrow_ptr[k]; q < ts.lrow_ptr[k + 1]; ++q) {
+      const int j = ts.lrow_cols[q];
+      const double* lj = S + (long)ts.tile_slot[k * T + j] * kTile * kTile + (long)r * ld;
+      const double* xj = x + (long)j * kTile;
 #pragma unroll
-        for (int c = 0; c < kTile; c += 32) s += lj[c + lane] * xj[c + lane];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) tmp[r] = x[(long)k * kTile + r] - s;
+      for (int c = 0; c < kTile; c += 32) s += lj[c + lane] * xj[c + lane];
     }
-    __syncthreads();
-    const double* di = Dinv + (long)k * kTile * kTile;
-    for (int r = warp; r < kTile; r += 32) {
-      double s = 0.0;
 #pragma unroll
-      for (int c = 0; c < kTile; c += 32)
-        if (c + lane <= r) s += di[r * kTile + c + lane] * tmp[c + lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) x[(long)k * kTile + r] = s;
-    }
-    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tmp[r] = x[(long)k * kTile + r] - s;
   }
-  // ---- backward: y_k = Linv_kk^T (z_k - sum_{i>k} L_ik^T y_i)
-  for (int k = T - 1; k >= 0; --k) {
-    // thread (g = warp, r = lane + 32 m): partial over tile rows c = g, g+32, ... of every L_ik
-    for (int m = 0; m < 3; ++m) {
-      const int r = lane + 32 * m;
-      double s = 0.0;
-      for (int q = ts.row_ptr[k]; q < ts.row_ptr[k + 1]; ++q) {
-        const int i = ts.rows[q];
-        const double* lik = S + (long)ts.tile_slot[i * T + k] * kTile * kTile;
-        const double* yi = x + (long)i * kTile;
-        for (int c = warp; c < kTile; c += 32) s += lik[(long)c * ld + r] * yi[c];
-      }
-      part[warp][r] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < kTile) {
-      double s = 0.0;
+  __syncthreads();
+  const double* di = ts.Dinv + (long)k * kTile * kTile;
+  for (int r = warp; r < kTile; r += 8) {
+    double s = 0.0;
 #pragma unroll
-      for (int g = 0; g < 32; ++g) s += part[g][threadIdx.x];
-      tmp[threadIdx.x] = x[(long)k * kTile + threadIdx.x] - s;
-    }
-    __syncthreads();
-    const double* di = Dinv + (long)k * kTile * kTile;
-    for (int m = 0; m < 3; ++m) {
-      const int r = lane + 32 * m;
-      double s = 0.0;
-      for (int c = warp; c < kTile; c += 32)
-        if (c >= r) s += di[c * kTile + r] * tmp[c];
-      part[warp][r] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < kTile) {
-      double s = 0.0;
+    for (int c = 0; c < kTile; c += 32)
+      if (c + lane <= r) s += di[r * kTile + c + lane] * tmp[c + lane];
 #pragma unroll
-      for (int g = 0; g < 32; ++g) s += part[g][threadIdx.x];
-      x[(long)k * kTile + threadIdx.x] = s;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) x[(long)k * kTile + r] = s;
+  }
+}
+
+// backward: y_k = Linv_kk^T (z_k - sum_{i>k} L_ik^T y_i)   every i sits in a higher level
+__global__ void __launch_bounds__(256)
+solve_backward_kernel(const double* __restrict__ S, TileSchedule ts, const int* __restrict__ panels,
+                      double* __restrict__ x) {
+  constexpr long ld = kTile;
+  __shared__ double tmp[kTile];
+  __shared__ double part[8][kTile + 1];
+  const int k = panels[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = ts.n_tiles;
+  // thread (g = warp, r = lane + 32 m): partial over tile rows c = g, g+8, ... of every L_ik
+  for (int m = 0; m < 3; ++m) {
+    const int r = lane + 32 * m;
+    double s = 0.0;
+    for (int q = ts.row_ptr[k]; q < ts.row_ptr[k + 1]; ++q) {
+      const int i = ts.rows[q];
+      const double* lik = S + (long)ts.tile_slot[i * T + k] * kTile * kTile;
+      const double* yi = x + (long)i * kTile;
+      for (int c = warp; c < kTile; c += 8) s += lik[(long)c * ld + r] * yi[c];
     }
-    __syncthreads();
+    part[warp][r] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kTile) {
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
+    tmp[threadIdx.x] = x[(long)k * kTile + threadIdx.x] - s;
+  }
+  __syncthreads();
+  const double* di = ts.Dinv + (long)k * kTile * kTile;
+  for (int m = 0; m < 3; ++m) {
+    const int r = lane + 32 * m;
+    double s = 0.0;
+    for (int c = warp; c < kTile; c += 8)
+      if (c >= r) s += di[c * kTile + r] * tmp[c];
+    part[warp][r] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kTile) {
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
+    x[(long)k * kTile + threadIdx.x] = s;
   }
 }
 
 }  // namespace
 
 void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s) {
-  if (ts.n_nz > 0) clear_tiles_kernel<<<ts.n_nz, 256, 0, s>>>(S, ts.nz_tiles, (int)ts.n_real);
+  if (ts.n_nz > 0) clear_tiles_kernel<<<ts.n_nz, 256, 0, s>>>(S);
 }
 
-int launch_tile_cholesky(double* S, const TileSchedule& ts, const int* h_row_ptr,
-                         const long* h_upd_ptr, int* info, cudaStream_t s) {
+int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s) {
   static bool attr_done = false;
   const size_t potrf_smem = (size_t)(2 * kTile * kLd + 8 * kTile) * sizeof(double);
   const size_t gemm_smem = (size_t)(2 * kTile * kGemmLd) * sizeof(double);
@@ -330,26 +334,38 @@ int launch_tile_cholesky(double* S, const TileSchedule& ts, const int* h_row_ptr
     attr_done = true;
   }
   int launches = 0;
-  for (int k = 0; k < ts.n_tiles; ++k) {
-    potrf_inv_kernel<<<1, 256, potrf_smem, s>>>(S, ts.tile_slot, ts.n_tiles, k, ts.Dinv, info);
+  for (int l = 0; l < plan.n_levels; ++l) {
+    const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
+    potrf_inv_kernel<<<np, 256, potrf_smem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.panels + plan.panel_ptr[l], ts.Dinv, info);
     ++launches;
-    const int nrows = h_row_ptr[k + 1] - h_row_ptr[k];
-    if (nrows > 0) {
-      tile_gemm_kernel<0><<<nrows, 256, gemm_smem, s>>>(S, ts.tile_slot, ts.n_tiles, k, ts.rows + h_row_ptr[k], nullptr, ts.Dinv);
+    const int nt = plan.trsm_ptr[l + 1] - plan.trsm_ptr[l];
+    if (nt > 0) {
+      tile_gemm_kernel<0><<<nt, 256, gemm_smem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.trsm + plan.trsm_ptr[l], nullptr, ts.Dinv);
       ++launches;
-      const long nupd = h_upd_ptr[k + 1] - h_upd_ptr[k];
-      if (nupd > 0) {
-        tile_gemm_kernel<1><<<(unsigned)nupd, 256, gemm_smem, s>>>(S, ts.tile_slot, ts.n_tiles, k, nullptr, ts.upd + h_upd_ptr[k], nullptr);
-        ++launches;
-      }
+    }
+    for (int g = plan.level_group_ptr[l]; g < plan.level_group_ptr[l + 1]; ++g) {
+      const long nu = plan.group_ptr[g + 1] - plan.group_ptr[g];
+      if (nu <= 0) continue;
+      tile_gemm_kernel<1><<<(unsigned)nu, 256, gemm_smem, s>>>(S, ts.tile_slot, ts.n_tiles, nullptr, ts.upd + plan.group_ptr[g], nullptr);
+      ++launches;
     }
   }
   return launches;
 }
 
-int launch_tile_solve(const double* S, const TileSchedule& ts, double* x, cudaStream_t s) {
-  tile_solve_kernel<<<1, 1024, 0, s>>>(S, ts, ts.Dinv, x);
-  return 1;
+int launch_tile_solve(const double* S, const TileSchedule& ts, const TilePlan& plan, double* x, cudaStream_t s) {
+  int launches = 0;
+  for (int l = 0; l < plan.n_levels; ++l) {
+    const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
+    solve_forward_kernel<<<np, 256, 0, s>>>(S, ts, ts.panels + plan.panel_ptr[l], x);
+    ++launches;
+  }
+  for (int l = plan.n_levels - 1; l >= 0; --l) {
+    const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
+    solve_backward_kernel<<<np, 256, 0, s>>>(S, ts, ts.panels + plan.panel_ptr[l], x);
+    ++launches;
+  }
+  return launches;
 }
 
 }  // namespace rsba

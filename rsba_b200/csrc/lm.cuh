@@ -5,6 +5,7 @@
 // SparseSchurComplementSolver/CHOLMOD, LevenbergMarquardtStrategy, TrustRegionMinimizer.
 #pragma once
 #include "common.cuh"
+#include "tile_plan.cuh"
 
 namespace rsba {
 
@@ -89,19 +90,19 @@ void launch_schur_reduce(const SchurStructure& st, NormalEq ne, LmOptionsDev o, 
                          const int* tile_slot, int n_tiles, int n_frames, double* rhs, cudaStream_t s);
 
 // ---- K3 ---------------------------------------------------------------------------------
-struct TileSchedule {
+struct TileSchedule {      // device view of the TilePlan (tile_plan.cuh); tile indices are POSITIONS
   int n_tiles;              // tiles per dimension (T)
   // S is tile-packed: slot s holds tile nz_tiles[s] = (row tile i, col tile j), i >= j, all
   // structurally non-zero lower tiles after symbolic fill; tile_slot[i*T + j] = s or -1
   const int2* nz_tiles;     // [n_nz]
   const int* tile_slot;     // [T*T]
   int n_nz;
+  const int* panels;        // [T] panels sorted by elimination level
+  const int2* trsm;         // (row tile i, panel k) sorted by level of k
+  const int4* upd;          // (i, j, k, -) sorted by (level, conflict-free group)
   // per panel k: rows i > k with tile (i,k) non-zero: rows[row_ptr[k] .. row_ptr[k+1])
   const int* row_ptr;       // [n_tiles+1]
   const int* rows;
-  // per panel k: update pairs (i, j), i >= j, both in rows(k): upd[upd_ptr[k] .. upd_ptr[k+1])
-  const long* upd_ptr;      // [n_tiles+1]
-  const int2* upd;
   // per tile row i: the non-zero tiles (i, j), j < i, for the triangular solves
   const int* lrow_ptr;      // [n_tiles+1]
   const int* lrow_cols;
@@ -110,11 +111,10 @@ struct TileSchedule {
 };
 
 void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s);
-// returns number of kernel launches issued; info[0] != 0 on a non-positive pivot
-int launch_tile_cholesky(double* S, const TileSchedule& ts, const int* h_row_ptr,
-                         const long* h_upd_ptr, int* info, cudaStream_t s);
-int launch_tile_solve(const double* S, const TileSchedule& ts, double* x /* in: rhs, out: solution */,
-                      cudaStream_t s);
+// return the number of kernel launches issued; info[0] != 0 on a non-positive pivot
+int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s);
+int launch_tile_solve(const double* S, const TileSchedule& ts, const TilePlan& plan,
+                      double* x /* in: rhs, out: solution */, cudaStream_t s);
 
 // ---- K4 ---------------------------------------------------------------------------------
 struct StepScalars {  // device doubles, filled by launch_step_update

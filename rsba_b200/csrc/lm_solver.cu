@@ -24,18 +24,15 @@ struct LmState {
   DeviceBuffer<unsigned char> slot_cnt;
   DeviceBuffer<int4> items;
   DeviceBuffer<int2> entries;
-  DeviceBuffer<int2> nz_tiles, upd;
-  DeviceBuffer<int> tile_slot, row_ptr, rows, lrow_ptr, lrow_cols;
-  DeviceBuffer<long> upd_ptr;
+  DeviceBuffer<int2> nz_tiles, trsm;
+  DeviceBuffer<int4> upd;
+  DeviceBuffer<int> tile_slot, row_ptr, rows, lrow_ptr, lrow_cols, panels;
   DeviceBuffer<unsigned short> pose_mask;
   DeviceBuffer<unsigned char> point_const;
-  std::vector<int> h_row_ptr;
-  std::vector<long> h_upd_ptr;
-  std::vector<int2> h_nz_tiles;
-  std::vector<int> h_tile_pos, h_pos_tile;   // frame tile -> position in S, and its inverse
+  TilePlan plan;                              // host copy of the symbolic analysis
   SchurStructure st{};
   TileSchedule ts{};
-  bool dense = false;
+  bool dense = false, reorder = true;
   // ---- numeric state (device)
   DeviceBuffer<double> B, gc, wf, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
   DeviceBuffer<double> S, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
@@ -98,8 +95,6 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   }
   // ---- Schur SYRK structure: (frame tile, point) incidences, tile pairs, work items
   const int T = (int)((12L * F + kTile - 1) / kTile);
-  std::vector<int> tile_pos(std::max(T, 1));
-  for (int t = 0; t < T; ++t) tile_pos[t] = t;
   std::vector<int> inc_point, inc_tile, slot_beg;
   std::vector<unsigned char> slot_cnt;
   struct PairEntry { long key; int inc_a, inc_b; };
@@ -162,47 +157,16 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   if (entries.empty()) entries.push_back(make_int2(n_inc, n_inc));
   if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
   const int n_items = (int)pair_item_ptr.back();
-  // ---- tile graph + symbolic fill
-  std::vector<char> nz((size_t)T * T, 0);
-  for (int i = 0; i < T; ++i) nz[(size_t)i * T + i] = 1;
-  if (dense) {
-    for (int i = 0; i < T; ++i)
-      for (int j = 0; j <= i; ++j) nz[(size_t)i * T + j] = 1;
-  } else {
-    for (size_t k = 0; k < pair_a.size(); ++k) {
-      const int pa = tile_pos[pair_a[k]], pb = tile_pos[pair_b[k]];
-      nz[(size_t)std::max(pa, pb) * T + std::min(pa, pb)] = 1;
-    }
+  // ---- ordering, symbolic factorisation, elimination levels (tile_plan.cu)
+  TilePlan& plan = lm->plan;
+  {
+    std::vector<std::pair<int, int>> tp;
+    tp.reserve(pair_a.size());
+    for (size_t k = 0; k < pair_a.size(); ++k) tp.emplace_back(pair_a[k], pair_b[k]);
+    build_tile_plan(T, tp, dense, h->reorder_tiles, &plan);
   }
-  std::vector<int> row_ptr(T + 1, 0), rows;
-  std::vector<long> upd_ptr(T + 1, 0);
-  std::vector<int2> upd;
-  for (int k = 0; k < T; ++k) {
-    row_ptr[k] = (int)rows.size();
-    upd_ptr[k] = (long)upd.size();
-    const size_t r0 = rows.size();
-    for (int i = k + 1; i < T; ++i)
-      if (nz[(size_t)i * T + k]) rows.push_back(i);
-    for (size_t x = r0; x < rows.size(); ++x)
-      for (size_t y = r0; y <= x; ++y) {
-        nz[(size_t)rows[x] * T + rows[y]] = 1;  // fill
-        upd.push_back(make_int2(rows[x], rows[y]));
-      }
-  }
-  row_ptr[T] = (int)rows.size();
-  upd_ptr[T] = (long)upd.size();
-  std::vector<int2> nz_tiles;
-  std::vector<int> tile_slot((size_t)T * T, -1), lrow_ptr(T + 1, 0), lrow_cols;
-  for (int i = 0; i < T; ++i) {
-    lrow_ptr[i] = (int)lrow_cols.size();
-    for (int j = 0; j <= i; ++j)
-      if (nz[(size_t)i * T + j]) {
-        tile_slot[(size_t)i * T + j] = (int)nz_tiles.size();
-        nz_tiles.push_back(make_int2(i, j));
-        if (j < i) lrow_cols.push_back(j);
-      }
-  }
-  lrow_ptr[T] = (int)lrow_cols.size();
+  const std::vector<int>& tile_pos = plan.tile_pos;
+  const std::vector<int2>& nz_tiles = plan.nz_tiles;
 
   // ---- upload
   int rc;
@@ -211,17 +175,13 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr);
   UP(inc_point, inc_point); UP(inc_tile, inc_tile); UP(slot_beg, slot_beg); UP(slot_cnt, slot_cnt);
   UP(pair_a, pair_a); UP(pair_b, pair_b); UP(pair_item_ptr, pair_item_ptr); UP(items, items); UP(tile_pos, tile_pos);
-  UP(entries, entries); UP(nz_tiles, nz_tiles); UP(upd, upd); UP(tile_slot, tile_slot);
-  UP(row_ptr, row_ptr); UP(rows, rows); UP(lrow_ptr, lrow_ptr); UP(lrow_cols, lrow_cols); UP(upd_ptr, upd_ptr);
+  UP(entries, entries); UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
+  UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
+  UP(panels, plan.panels); UP(trsm, plan.trsm);
   UP(pose_mask, h->pose_mask); UP(point_const, h->point_const);
 #undef UP
-  lm->h_row_ptr = row_ptr;
-  lm->h_upd_ptr = upd_ptr;
-  lm->h_nz_tiles = nz_tiles;
-  lm->h_tile_pos = tile_pos;
-  lm->h_pos_tile.assign(tile_pos.size(), 0);
-  for (int t = 0; t < T; ++t) lm->h_pos_tile[tile_pos[t]] = t;
   lm->dense = dense;
+  lm->reorder = h->reorder_tiles;
   lm->n_pad = (long)T * kTile;
 
   SchurStructure& st = lm->st;
@@ -265,7 +225,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
 
   TileSchedule& ts = lm->ts;
   ts.n_tiles = T; ts.nz_tiles = lm->nz_tiles.ptr; ts.tile_slot = lm->tile_slot.ptr; ts.n_nz = (int)nz_tiles.size();
-  ts.row_ptr = lm->row_ptr.ptr; ts.rows = lm->rows.ptr; ts.upd_ptr = lm->upd_ptr.ptr; ts.upd = lm->upd.ptr;
+  ts.row_ptr = lm->row_ptr.ptr; ts.rows = lm->rows.ptr; ts.upd = lm->upd.ptr; ts.panels = lm->panels.ptr; ts.trsm = lm->trsm.ptr;
   ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.n_real = 12L * F;
 
   long free_params = 0;
@@ -277,7 +237,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
 }
 
 int ensure_lm(rsba_problem* h, bool dense) {
-  if (h->lm && h->lm->dense == dense) return RSBA_OK;
+  if (h->lm && h->lm->dense == dense && h->lm->reorder == h->reorder_tiles) return RSBA_OK;
   if (h->lm) { lm_state_free(h->lm); h->lm = nullptr; }
   LmState* lm = new LmState;
   int rc = build_structure(h, lm, dense);
@@ -313,8 +273,8 @@ void factor_and_solve(rsba_problem* h, LmState* lm) {
   stage_begin(h, kStageCholesky);
   cudaMemsetAsync(lm->info.ptr, 0, sizeof(int), s);
   cudaMemcpyAsync(lm->y.ptr, lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToDevice, s);
-  h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->h_row_ptr.data(), lm->h_upd_ptr.data(), lm->info.ptr, s);
-  h->launches += launch_tile_solve(lm->S.ptr, lm->ts, lm->y.ptr, s);
+  h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->info.ptr, s);
+  h->launches += launch_tile_solve(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, s);
   stage_end(h, kStageCholesky);
 }
 
@@ -362,6 +322,7 @@ int prepare_solve(rsba_problem* h, const rsba_solve_options* opt) {
   if (!h->params_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_parameters has not been called");
   int rc = ensure_eval_buffers(h, true);
   if (rc) return rc;
+  h->reorder_tiles = opt->reorder_tiles != 0;
   return ensure_lm(h, opt->dense_cholesky != 0);
 }
 
@@ -532,13 +493,13 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
   if (S_out) {
     std::vector<double> tile((size_t)kTile * kTile);
     memset(S_out, 0, sizeof(double) * n * n);
-    for (size_t sidx = 0; sidx < lm->h_nz_tiles.size(); ++sidx) {
-      const int2 t = lm->h_nz_tiles[sidx];
+    for (size_t sidx = 0; sidx < lm->plan.nz_tiles.size(); ++sidx) {
+      const int2 t = lm->plan.nz_tiles[sidx];
       RSBA_CUDA_TRY(cudaMemcpy(tile.data(), lm->S.ptr + sidx * kTile * kTile, tile.size() * sizeof(double), cudaMemcpyDeviceToHost));
       for (int r = 0; r < kTile; ++r)
         for (int c = 0; c < kTile; ++c) {
           // tile positions -> frame tiles (the caller sees the un-permuted system)
-          const long gr = (long)lm->h_pos_tile[t.x] * kTile + r, gcol = (long)lm->h_pos_tile[t.y] * kTile + c;
+          const long gr = (long)lm->plan.pos_tile[t.x] * kTile + r, gcol = (long)lm->plan.pos_tile[t.y] * kTile + c;
           if (gr >= n || gcol >= n) continue;
           if (t.x == t.y && c > r) continue;   // diagonal tiles: the factorisation reads the lower triangle
           S_out[gr * n + gcol] = tile[r * kTile + c];
@@ -550,7 +511,7 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
     std::vector<double> tmp((size_t)lm->n_pad);
     RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToHost));
     for (long k = 0; k < n; ++k)   // S delta_c' = rhs, un-permuted
-      rhs_out[k] = -tmp[(size_t)lm->h_tile_pos[k / kTile] * kTile + k % kTile];
+      rhs_out[k] = -tmp[(size_t)lm->plan.tile_pos[k / kTile] * kTile + k % kTile];
   }
   factor_and_solve(h, lm);
   step_update(h, lm);
@@ -561,6 +522,34 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
   if (delta_points)
     RSBA_CUDA_TRY(cudaMemcpy(delta_points, lm->delta_p.ptr, 3L * h->n_points * sizeof(double), cudaMemcpyDeviceToHost));
   if (model_cost_change) *model_cost_change = -0.5 * hs.s[0] + 0.5 * hs.s[1];
+  return RSBA_OK;
+}
+
+int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, const int* pair_b, int dense,
+                                  int reorder, long counts[6], int* tile_pos, int* nz_tiles, int* panels,
+                                  int* panel_ptr, int* trsm, int* trsm_ptr, int* upd, long* group_ptr,
+                                  int* level_group_ptr) {
+  if (n_tiles < 0 || n_pairs < 0 || (n_pairs > 0 && (!pair_a || !pair_b)) || !counts)
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "bad plan arguments");
+  std::vector<std::pair<int, int>> tp;
+  for (int k = 0; k < n_pairs; ++k) {
+    if (pair_a[k] < 0 || pair_b[k] < 0 || pair_a[k] >= n_tiles || pair_b[k] >= n_tiles)
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "tile index out of range");
+    tp.emplace_back(std::min(pair_a[k], pair_b[k]), std::max(pair_a[k], pair_b[k]));
+  }
+  TilePlan plan;
+  build_tile_plan(n_tiles, tp, dense != 0, reorder != 0, &plan);
+  counts[0] = plan.n_levels; counts[1] = (long)plan.nz_tiles.size(); counts[2] = (long)plan.trsm.size();
+  counts[3] = (long)plan.upd.size(); counts[4] = (long)plan.group_ptr.size() - 1; counts[5] = (long)plan.flops;
+  if (tile_pos) std::copy(plan.tile_pos.begin(), plan.tile_pos.begin() + n_tiles, tile_pos);
+  if (nz_tiles) for (size_t k = 0; k < plan.nz_tiles.size(); ++k) { nz_tiles[2 * k] = plan.nz_tiles[k].x; nz_tiles[2 * k + 1] = plan.nz_tiles[k].y; }
+  if (panels) std::copy(plan.panels.begin(), plan.panels.begin() + n_tiles, panels);
+  if (panel_ptr) std::copy(plan.panel_ptr.begin(), plan.panel_ptr.end(), panel_ptr);
+  if (trsm) for (size_t k = 0; k < plan.trsm.size(); ++k) { trsm[2 * k] = plan.trsm[k].x; trsm[2 * k + 1] = plan.trsm[k].y; }
+  if (trsm_ptr) std::copy(plan.trsm_ptr.begin(), plan.trsm_ptr.end(), trsm_ptr);
+  if (upd) for (size_t k = 0; k < plan.upd.size(); ++k) { upd[3 * k] = plan.upd[k].x; upd[3 * k + 1] = plan.upd[k].y; upd[3 * k + 2] = plan.upd[k].z; }
+  if (group_ptr) std::copy(plan.group_ptr.begin(), plan.group_ptr.end(), group_ptr);
+  if (level_group_ptr) std::copy(plan.level_group_ptr.begin(), plan.level_group_ptr.end(), level_group_ptr);
   return RSBA_OK;
 }
 

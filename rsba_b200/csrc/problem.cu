@@ -468,6 +468,7 @@ void rsba_cuda_default_options(rsba_solve_options* o) {
   o->huber_loss = 0.0;
   o->verbose = 0;
   o->dense_cholesky = 0;
+  o->reorder_tiles = 1;
 }
 
 }  // extern "C"

@@ -97,6 +97,7 @@ struct rsba_problem {
   long launches = 0;
 
   rsba::LmState* lm = nullptr;
+  bool reorder_tiles = true;   // nested-dissection ordering of the reduced system (rsba_solve_options)
 
   // multi-GPU
   void* nccl_comm = nullptr;

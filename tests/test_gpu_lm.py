@@ -78,6 +78,33 @@ def test_lm_step_multi_tile_band(api, oracle_built, lo):
     compare(gpu_step(api, sc, 1e3, dense_cholesky=1), want)
 
 
+def test_lm_step_nested_dissection_vs_natural_order(api, oracle_built, lo):
+    """160 frames = 20 Cholesky tiles: the nested-dissection ordering (elimination levels,
+    conflict-free update groups, permuted right-hand side) must give the step of the natural
+    order and of the numpy restatement."""
+    sc = make_scene(160, 4000, 10, name="nd")
+    want = oracle_step(oracle_built, lo, sc, 1e3)
+    for kw in (dict(reorder_tiles=1), dict(reorder_tiles=0), dict(reorder_tiles=1, dense_cholesky=1)):
+        compare(gpu_step(api, sc, 1e3, **kw), want)
+
+
+def test_lm_step_duplicate_observations_in_one_frame(api, oracle_built, lo):
+    """A point observed twice in the same frame (two residual blocks on the same parameter
+    blocks): the frame's Schur panel is the sum of both."""
+    sc = make_scene(12, 300, 6, name="dup")
+    n = sc.num_obs
+    extra = np.arange(0, n, 7)
+    rng = np.random.default_rng(11)
+    sc2 = Scene(**{**sc.__dict__,
+                   "obs_xy": np.concatenate([sc.obs_xy, sc.obs_xy[extra] + rng.normal(0, 0.5, (extra.size, 2))]),
+                   "obs_frame": np.concatenate([sc.obs_frame, sc.obs_frame[extra]]),
+                   "obs_point": np.concatenate([sc.obs_point, sc.obs_point[extra]])})
+    order = np.argsort(sc2.obs_frame, kind="stable")
+    sc2 = Scene(**{**sc2.__dict__, "obs_xy": sc2.obs_xy[order], "obs_frame": sc2.obs_frame[order],
+                   "obs_point": sc2.obs_point[order]})
+    compare(gpu_step(api, sc2, 1e3), oracle_step(oracle_built, lo, sc2, 1e3))
+
+
 def test_lm_step_constant_blocks_and_subsets(api, oracle_built, lo):
     """SetParameterBlockConstant on points / pose blocks and SubsetParameterization-style
     constant components (CeresHandler.h:288-300, 342-381)."""
