@@ -188,16 +188,27 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
 
 /* ------------------------------------------------------------------ multi-GPU */
 /* One process per GPU.  Rank 0 obtains an id, the host framework broadcasts the 128 bytes,
- * every rank calls comm_init.  After that rsba_cuda_solve performs exactly one NCCL
- * allreduce of [S | rhs | cost terms] per linear solve.  Single-GPU use never touches NCCL. */
+ * every rank calls comm_init and then passes the SAME whole scene to set_scene / the pointer
+ * API; the library keeps this rank's share (all observations of the points it owns) on the
+ * device.  rsba_cuda_solve then performs one NCCL all-reduce of the unscaled reduced system
+ * [S | gradient terms | diag(B) | cost, invalid count, norms] per linearisation, plus an
+ * 8-double all-reduce of the trial-step scalars per iteration and one of the points at the end;
+ * the factorisation is replicated.  Single-GPU use never loads NCCL (dlopen at comm_init). */
 int rsba_cuda_nccl_unique_id(unsigned char id[128]);
 int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigned char id[128]);
+/* Host-only (no device): the sharding rule.  owner[p] = rank that eliminates point p and therefore
+ * evaluates ALL its observations -- the rank whose contiguous range of frame tiles (8 frames)
+ * holds the point's median observation.  obs_frame must be non-decreasing. */
+int rsba_cuda_point_owners(int n_frames, int n_points, long n_obs, const int* obs_frame,
+                           const int* obs_point, int world_size, int* owner);
 
 /* ------------------------------------------------------------------ introspection */
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 long rsba_cuda_launch_count(rsba_problem* h);
 /* Device time (ms) of the last call of each stage, measured with CUDA events on the
- * launching stream: 0 jacobian, 1 residual, 2 schur, 3 cholesky, 4 update, 5 allreduce. */
+ * launching stream: 0 jacobian, 1 residual, 2 schur, 3 cholesky, 4 update, 5 allreduce; and of
+ * single kernels inside them: 6 point blocks, 7 frame blocks, 8 Schur panels, 9 Schur SYRK,
+ * 10 Schur reduce, 11 factorisation, 12 triangular solves, 13 point back-substitution. */
 double rsba_cuda_stage_ms(rsba_problem* h, int stage);
 const char* rsba_cuda_version(void);
 

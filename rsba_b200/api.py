@@ -40,7 +40,7 @@ SYMBOLS = [
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
     "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_nccl_unique_id",
-    "rsba_cuda_comm_init", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
+    "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
 
 
@@ -143,6 +143,7 @@ def load_library():
     lib.rsba_cuda_plan_reduced_system.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp] + [vp] * 9
     lib.rsba_cuda_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     lib.rsba_cuda_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
+    lib.rsba_cuda_point_owners.argtypes = [C.c_int, C.c_int, C.c_long, vp, vp, C.c_int, vp]
     lib.rsba_cuda_launch_count.argtypes = [vp]
     lib.rsba_cuda_launch_count.restype = C.c_long
     lib.rsba_cuda_stage_ms.argtypes = [vp, C.c_int]
@@ -174,7 +175,8 @@ def _addr(a):
     raise TypeError(type(a))
 
 
-STAGES = ("jacobian", "residual", "schur", "cholesky", "update", "allreduce")
+STAGES = ("jacobian", "residual", "schur", "cholesky", "update", "allreduce", "point_blocks", "frame_blocks",
+          "phi_build", "schur_syrk", "schur_reduce", "factor", "tri_solve", "point_step")
 
 
 class Problem:
@@ -328,11 +330,17 @@ class Problem:
         s.rc = rc
         return s
 
-    def linearize_and_step(self, radius, options: SolveOptions | None = None, want_S=True):
+    def linearize_and_step(self, radius, options: SolveOptions | None = None, want_S=True, fetch=True):
         """One linearisation + LM step at the current parameters (does not move them).
-        Returns dict(S, rhs, delta_poses, delta_points, model_cost_change)."""
+        Returns dict(S, rhs, delta_poses, delta_points, model_cost_change); with ``fetch=False``
+        nothing is copied back (profiling)."""
         if options is None:
             options = default_options()
+        if not fetch:
+            mcc = C.c_double(0.0)
+            self._check(self.lib.rsba_cuda_linearize_and_step(self._h, C.byref(options), float(radius), None,
+                                                              None, None, None, C.byref(mcc)))
+            return dict(model_cost_change=mcc.value)
         n = 12 * self.num_frames
         S = np.zeros((n, n)) if want_S else None
         rhs = np.zeros(n)
@@ -380,6 +388,19 @@ def plan_reduced_system(n_tiles, pair_a, pair_b, dense=False, reorder=True):
     call(*out.values())
     out.update(n_levels=L, flops=float(counts[5]))
     return out
+
+
+def point_owners(scene, world_size: int) -> np.ndarray:
+    """Host-only: owner rank of every point under the multi-GPU sharding rule."""
+    lib = load_library()
+    fr = np.ascontiguousarray(scene.obs_frame, dtype=np.int32)
+    pt = np.ascontiguousarray(scene.obs_point, dtype=np.int32)
+    owner = np.zeros(scene.num_points, dtype=np.int32)
+    rc = lib.rsba_cuda_point_owners(scene.num_frames, scene.num_points, fr.size, _addr(fr), _addr(pt),
+                                    int(world_size), _addr(owner))
+    if rc != RSBA_OK:
+        raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
+    return owner
 
 
 def nccl_unique_id() -> bytes:

@@ -69,14 +69,14 @@ __global__ void point_scale_kernel(int n_points, const double* __restrict__ C,
   for (int k = 0; k < 3; ++k) scale_p[3L * p + k] = (cst || !enabled) ? 1.0 : 1.0 / (1.0 + sqrt(d[k]));
 }
 
-__global__ void frame_scale_kernel(int n_frames, const double* __restrict__ B,
+__global__ void frame_scale_kernel(int n_frames, const double* __restrict__ diagB,
                                    const unsigned short* __restrict__ pose_mask, int enabled,
                                    double* __restrict__ scale_c) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_frames * kFrameParams) return;
   const int f = t / kFrameParams, k = t % kFrameParams;
   const bool cst = (pose_mask[f] >> k) & 1;
-  scale_c[t] = (cst || !enabled) ? 1.0 : 1.0 / (1.0 + sqrt(B[(long)f * 144 + k * 13]));
+  scale_c[t] = (cst || !enabled) ? 1.0 : 1.0 / (1.0 + sqrt(diagB[t]));
 }
 
 // ---------------------------------------------------------------- points: damped inverse
@@ -229,8 +229,10 @@ frame_reduce_kernel(SchurStructure st, NormalEq ne, int n_frames) {
   if (f >= n_frames || k >= kPartial) return;
   double s = 0.0;
   for (int c = st.frame_chunk_ptr[f]; c < st.frame_chunk_ptr[f + 1]; ++c) s += ne.partials[(long)c * kPartial + k];
-  if (k < 144) ne.B[(long)f * 144 + k] = s;
-  else if (k < 156) ne.gc[(long)f * 12 + (k - 144)] = s;
+  if (k < 144) {
+    ne.B[(long)f * 144 + k] = s;
+    if (k % 13 == 0) ne.diagB[(long)f * 12 + k / 13] = s;
+  } else if (k < 156) ne.gc[(long)f * 12 + (k - 144)] = s;
   else ne.wf[(long)f * 12 + (k - 156)] = s;
 }
 
@@ -253,7 +255,7 @@ void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, 
   if (n_points > 0)
     point_scale_kernel<<<(n_points + 255) / 256, 256, 0, s>>>(n_points, ne.C, ne.point_const, enabled ? 1 : 0, ne.scale_p);
   if (n_frames > 0)
-    frame_scale_kernel<<<(n_frames * kFrameParams + 255) / 256, 256, 0, s>>>(n_frames, ne.B, ne.pose_mask,
+    frame_scale_kernel<<<(n_frames * kFrameParams + 255) / 256, 256, 0, s>>>(n_frames, ne.diagB, ne.pose_mask,
                                                                              enabled ? 1 : 0, ne.scale_c);
 }
 

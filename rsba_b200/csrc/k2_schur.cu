@@ -4,7 +4,7 @@
 // through ceres::Solve with SPARSE_SCHUR, CeresHandler.h:403,419):
 //     S = diag(s B s + D^2) - sum_p E_p C_p^-1 E_p^T .
 // With C_p'^-1 = L^-T L^-1 (3x3 Cholesky inverted in registers, k2_normal.cu) the per-observation
-// block  F_i = s_c Jc_i^T (Jx_i s_p) L^-T  (12x3) makes the point term a plain Gram product:
+// block  F_i = Jc_i^T (Jx_i s_p) L^-T  (12x3) makes the point term a plain Gram product:
 //     sum_p E_p C_p^-1 E_p^T = Phi Phi^T,   Phi = [F_i] block-sparse, 12F x 3P.
 // Frames are cut into tiles of 8 (96 rows, the Cholesky tile).  For every (frame tile, point)
 // incidence phi_build writes one dense k-major panel [3][96(+4 pad)]; rows of frames that do not
@@ -13,8 +13,10 @@
 //     S(B, A) -= sum_p Phi(B,p) Phi(A,p)^T                      96 x 96, mma.sync.m8n8k4.f64
 // Long pairs are split along K into work items of <= 512 points whose 96x96 partial products
 // are summed in a fixed order by schur_reduce (bit-reproducible, no atomics), which also adds
-// the camera diagonal blocks, the LM diagonal and the constant-parameter identity rows and
-// places the tile at its (permuted) position of the tile-packed reduced matrix.
+// the camera diagonal blocks and places the tile at its (permuted) position of the tile-packed
+// reduced matrix.  schur_finalize then applies the camera-side Jacobi scaling, the LM diagonal
+// and the constant-parameter identity rows -- after the NCCL all-reduce when the observations
+// are sharded over several GPUs, because those depend on the global diag(B).
 //
 // Data movement: panels are 2400-byte contiguous records, fetched by TMA bulk copies
 // (cp.async.bulk.shared::cluster.global.mbarrier) into a 3-stage shared-memory ring; the kernel
@@ -33,8 +35,10 @@ constexpr size_t kSyrkSmem = (size_t)kStages * kStageDoubles * sizeof(double) + 
 
 // ---------------------------------------------------------------- panels
 // One thread per (incidence, frame slot): F = sum over the slot's observations (more than one only
-// when a point was observed twice in one frame) of  s_c Jc^T (Jx s_p) L^-T ; constant camera
-// parameters get zero rows, constant points have L^-1 = 0 and never appear in a pair.
+// when a point was observed twice in one frame) of  Jc^T (Jx s_p) L^-T ; constant camera
+// parameters get zero rows, constant points have L^-1 = 0 and never appear in a pair.  The
+// camera-side Jacobi scaling is applied to S afterwards (schur_finalize), so that partial sums of
+// different GPUs can be added before the scaling -- which depends on the global diag(B) -- is known.
 __global__ void __launch_bounds__(256)
 phi_build_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,7 +57,7 @@ phi_build_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac,
     const unsigned mask = ne.pose_mask[f];
     double sc[12];
 #pragma unroll
-    for (int a = 0; a < 12; ++a) sc[a] = ((mask >> a) & 1) ? 0.0 : ne.scale_c[12L * f + a];
+    for (int a = 0; a < 12; ++a) sc[a] = ((mask >> a) & 1) ? 0.0 : 1.0;
     const int beg = st.slot_beg[t];
     for (int d = 0; d < cnt; ++d) {
       const long i = st.pt_obs[beg + d];
@@ -199,11 +203,12 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
           make_double2(acc[mi][ni][0], acc[mi][ni][1]);
 }
 
-// ---------------------------------------------------------------- reduce + epilogue
-// grid (n_pairs, 9): 1024 elements of the pair's tile per CTA, 4 per thread.
+// ---------------------------------------------------------------- reduce
+// grid (n_pairs, 9): 1024 elements of the pair's tile per CTA, 4 per thread.  Writes the unscaled
+// tile  [A == B] B_f - sum of the pair's partial products  at its (permuted) place.
 __global__ void __launch_bounds__(256)
-schur_reduce_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, double* __restrict__ S,
-                    const int* __restrict__ tile_slot, int T, int n_frames) {
+schur_reduce_kernel(SchurStructure st, NormalEq ne, double* __restrict__ S, const int* __restrict__ tile_slot,
+                    int T) {
   const int pr = blockIdx.x;
   const int A = st.pair_a[pr], B = st.pair_b[pr];
   const int ib = st.pair_item_ptr[pr], ie = st.pair_item_ptr[pr + 1];
@@ -218,29 +223,47 @@ schur_reduce_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, double* __re
     for (int it = ib; it < ie; ++it) sum += ne.partial[(long)it * kTile * kTile + e];
     double val = -sum;
     if (A == B && r / kFrameParams == c / kFrameParams) {
-      const int f = A * kFramesPerTile + r / kFrameParams;
-      const int rr = r % kFrameParams, cc = c % kFrameParams;
-      if (f >= n_frames) {
-        val = (rr == cc) ? 1.0 : 0.0;        // padding rows of the last tile
-      } else {
-        const unsigned m = ne.pose_mask[f];
-        if (((m >> rr) & 1) || ((m >> cc) & 1)) {
-          val = (rr == cc) ? 1.0 : 0.0;      // constant parameter: identity row
-        } else {
-          const double sr = ne.scale_c[12L * f + rr], scl = ne.scale_c[12L * f + cc];
-          const double b = sr * ne.B[(long)f * 144 + rr * 12 + cc] * scl;
-          val += b;
-          if (rr == cc) val += fmin(fmax(b, o.min_diag), o.max_diag) / o.radius;
-        }
-      }
+      const long f = (long)A * kFramesPerTile + r / kFrameParams;
+      if (f * kFrameParams < st.n_cam_params) val += ne.B[f * 144 + (r % kFrameParams) * 12 + c % kFrameParams];
     }
     if (transposed) tile[c * kTile + r] = val;
     else            tile[r * kTile + c] = val;
   }
 }
 
+// ---------------------------------------------------------------- finalize (after the all-reduce)
+// grid (n_nz tiles, 9).  S' = s S s + D^2 with D^2 = clamp(s^2 diag(B)) / radius on the diagonal;
+// constant parameters and the padding rows of the last frame tile become identity rows.
+__global__ void __launch_bounds__(256)
+schur_finalize_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, double* __restrict__ S,
+                      const int2* __restrict__ nz_tiles) {
+  const int2 t = nz_tiles[blockIdx.x];
+  double* tile = S + (long)blockIdx.x * kTile * kTile;
+  const long base_r = (long)st.pos_tile[t.x] * kTile, base_c = (long)st.pos_tile[t.y] * kTile;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = blockIdx.y * 1024 + u * 256 + threadIdx.x;
+    const int r = e / kTile, c = e % kTile;
+    const long gi = base_r + r, gj = base_c + c;
+    bool fixed = gi >= st.n_cam_params || gj >= st.n_cam_params;
+    if (!fixed) {
+      const unsigned mi = ne.pose_mask[gi / kFrameParams], mj = ne.pose_mask[gj / kFrameParams];
+      fixed = ((mi >> (gi % kFrameParams)) & 1) || ((mj >> (gj % kFrameParams)) & 1);
+    }
+    double val;
+    if (fixed) {
+      val = (gi == gj) ? 1.0 : 0.0;
+    } else {
+      const double si = ne.scale_c[gi], sj = ne.scale_c[gj];
+      val = si * tile[e] * sj;
+      if (gi == gj) val += fmin(fmax(si * ne.diagB[gi] * si, o.min_diag), o.max_diag) / o.radius;
+    }
+    tile[e] = val;
+  }
+}
+
 // LM diagonal of the camera parameters and the right-hand side of  S y = rhs  (y = -scaled step),
-// both in the permuted order of the reduced system.
+// the latter in the permuted order of the reduced system.
 __global__ void __launch_bounds__(256)
 camera_rhs_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, int n_frames, double* __restrict__ rhs) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,8 +271,7 @@ camera_rhs_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, int n_frames, 
   const int f = t / kFrameParams, k = t % kFrameParams;
   const bool cst = (ne.pose_mask[f] >> k) & 1;
   const double s = ne.scale_c[t];
-  const double diag = s * ne.B[(long)f * 144 + k * 13] * s;
-  ne.d2_c[t] = cst ? 1.0 : fmin(fmax(diag, o.min_diag), o.max_diag) / o.radius;
+  ne.d2_c[t] = cst ? 1.0 : fmin(fmax(s * ne.diagB[t] * s, o.min_diag), o.max_diag) / o.radius;
   const long pos = (long)st.tile_pos[f / kFramesPerTile] * kTile + (f % kFramesPerTile) * kFrameParams + k;
   rhs[pos] = cst ? 0.0 : s * (ne.gc[t] - ne.wf[t]);
 }
@@ -273,10 +295,14 @@ void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
   schur_syrk_kernel<<<st.n_items, 256, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
 }
 
-void launch_schur_reduce(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,
-                         const int* tile_slot, int n_tiles, int n_frames, double* rhs, cudaStream_t s) {
-  if (st.n_pairs > 0)
-    schur_reduce_kernel<<<dim3(st.n_pairs, 9), 256, 0, s>>>(st, ne, o, S, tile_slot, n_tiles, n_frames);
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, double* S, const int* tile_slot, int n_tiles,
+                         cudaStream_t s) {
+  if (st.n_pairs > 0) schur_reduce_kernel<<<dim3(st.n_pairs, 9), 256, 0, s>>>(st, ne, S, tile_slot, n_tiles);
+}
+
+void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,
+                           const TileSchedule& ts, int n_frames, double* rhs, cudaStream_t s) {
+  if (ts.n_nz > 0) schur_finalize_kernel<<<dim3(ts.n_nz, 9), 256, 0, s>>>(st, ne, o, S, ts.nz_tiles);
   if (n_frames > 0)
     camera_rhs_kernel<<<(n_frames * kFrameParams + 255) / 256, 256, 0, s>>>(st, ne, o, n_frames, rhs);
 }

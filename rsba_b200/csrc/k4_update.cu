@@ -117,7 +117,7 @@ point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
   }
 }
 
-// final: scalars[0..2] = frame part + sum of point partials (fixed order)
+// final: scalars[0..2] = frame part, scalars[8..10] = sum of point partials (fixed order)
 __global__ void __launch_bounds__(kRedThreads)
 step_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __restrict__ scalars) {
   __shared__ double sh[32];
@@ -131,32 +131,25 @@ step_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __re
   b = block_sum(b, sh);
   c = block_sum(c, sh);
   if (threadIdx.x == 0) {
-    scalars[0] = scratch[0] + a;   // g . delta
-    scalars[1] = scratch[1] + b;   // sum D^2 delta'^2
-    scalars[2] = scratch[2] + c;   // |delta|^2
+    // camera part (identical on every rank) | point part (this rank's points; summed over ranks)
+    scalars[0] = scratch[0]; scalars[8] = a;    // g . delta
+    scalars[1] = scratch[1]; scalars[9] = b;    // sum D^2 delta'^2
+    scalars[2] = scratch[2]; scalars[10] = c;   // |delta|^2
   }
 }
 
-// |x|^2 over parameter blocks that are not entirely constant, max |g| over free parameters
+// |x|^2 over parameter blocks that are not entirely constant, max |g| over free parameters:
+// point part (owned points only) ...
 __global__ void __launch_bounds__(kRedThreads)
-state_norms_kernel(NormalEq ne, int n_frames, int n_points, const double* __restrict__ poses,
-                   const double* __restrict__ points, double* __restrict__ scratch) {
+point_norms_kernel(NormalEq ne, int n_points, const double* __restrict__ points, double* __restrict__ scratch) {
   __shared__ double sh[32];
   double xx = 0.0, gm = 0.0;
-  const long nc = 12L * n_frames, np = 3L * n_points;
-  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < nc + np; t += (long)gridDim.x * blockDim.x) {
-    if (t < nc) {
-      const int f = (int)(t / 12), k = (int)(t % 12);
-      const unsigned m = ne.pose_mask[f];
-      const unsigned blockbits = (k < 6) ? (m & 0x3F) : ((m >> 6) & 0x3F);
-      if (blockbits != 0x3F) xx += poses[t] * poses[t];
-      if (!((m >> k) & 1)) gm = fmax(gm, fabs(ne.gc[t]));
-    } else {
-      const long u = t - nc;
-      if (!ne.point_const[u / 3]) {
-        xx += points[u] * points[u];
-        gm = fmax(gm, fabs(ne.gp[u]));
-      }
+  const long np = 3L * n_points;
+  for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < np; u += (long)gridDim.x * blockDim.x) {
+    const long p = u / 3;
+    if (!ne.point_const[p] && ne.point_owned[p]) {
+      xx += points[u] * points[u];
+      gm = fmax(gm, fabs(ne.gp[u]));
     }
   }
   xx = block_sum(xx, sh);
@@ -165,12 +158,30 @@ state_norms_kernel(NormalEq ne, int n_frames, int n_points, const double* __rest
 }
 
 __global__ void __launch_bounds__(kRedThreads)
-state_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __restrict__ scalars) {
+point_norms_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __restrict__ out_xx,
+                         double* __restrict__ out_gmax) {
   __shared__ double sh[32];
   double xx = 0.0, gm = 0.0;
   for (int k = threadIdx.x; k < n_blocks; k += blockDim.x) {
     xx += scratch[2L * k];
     gm = fmax(gm, scratch[2L * k + 1]);
+  }
+  xx = block_sum(xx, sh);
+  gm = block_max(gm, sh);
+  if (threadIdx.x == 0) { *out_xx = xx; *out_gmax = gm; }
+}
+
+// ... and camera part (single CTA; 12 F values)
+__global__ void __launch_bounds__(kRedThreads)
+camera_norms_kernel(NormalEq ne, int n_frames, const double* __restrict__ poses, double* __restrict__ scalars) {
+  __shared__ double sh[32];
+  double xx = 0.0, gm = 0.0;
+  for (int t = threadIdx.x; t < 12 * n_frames; t += blockDim.x) {
+    const int f = t / 12, k = t % 12;
+    const unsigned m = ne.pose_mask[f];
+    const unsigned blockbits = (k < 6) ? (m & 0x3F) : ((m >> 6) & 0x3F);
+    if (blockbits != 0x3F) xx += poses[t] * poses[t];
+    if (!((m >> k) & 1)) gm = fmax(gm, fabs(ne.gc[t]));
   }
   xx = block_sum(xx, sh);
   gm = block_max(gm, sh);
@@ -192,10 +203,14 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
   step_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, nb, scalars);
 }
 
-void launch_state_norms(NormalEq ne, int n_frames, int n_points, const double* poses, const double* points,
-                        double* scalars, double* scratch, cudaStream_t s) {
-  state_norms_kernel<<<kStateBlocks, kRedThreads, 0, s>>>(ne, n_frames, n_points, poses, points, scratch);
-  state_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, kStateBlocks, scalars);
+void launch_point_norms(NormalEq ne, int n_points, const double* points, double* out_xx, double* out_gmax,
+                        double* scratch, cudaStream_t s) {
+  point_norms_kernel<<<kStateBlocks, kRedThreads, 0, s>>>(ne, n_points, points, scratch);
+  point_norms_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, kStateBlocks, out_xx, out_gmax);
+}
+
+void launch_camera_norms(NormalEq ne, int n_frames, const double* poses, double* scalars, cudaStream_t s) {
+  camera_norms_kernel<<<1, kRedThreads, 0, s>>>(ne, n_frames, poses, scalars);
 }
 
 }  // namespace rsba

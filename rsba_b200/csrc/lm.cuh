@@ -42,7 +42,9 @@ struct SchurStructure {
   const int4* items;       // [n_items] (pair, first entry, entry count, A == B)
   const int2* entries;     // (incidence on the row side B, incidence on the column side A)
   long n_entries;
+  long n_cam_params;       // 12 * frames (rows of the last tile beyond it are padding)
   const int* tile_pos;     // [T] position of frame tile A in the (permuted) reduced system
+  const int* pos_tile;     // [T] inverse
 };
 
 constexpr int kPanelLd = 100;                 // 96 rows + 4 pad: conflict-free DMMA fragment loads
@@ -52,8 +54,11 @@ constexpr int kSchurSegPoints = 512;
 struct NormalEq {
   // unscaled blocks of J^T J and J^T r
   double* B;        // [F][144] camera diagonal blocks (full 12x12, row-major)
+  // gc | wf | diagB are contiguous and sit behind S in the buffer that the multi-GPU path
+  // all-reduces (every rank holds partial sums over the observations of the points it owns)
   double* gc;       // [F][12]
   double* wf;       // [F][12]   sum_i Jc_i^T Jx_i t_p   (rhs correction)
+  double* diagB;    // [F][12]   diagonal of B (Jacobi scaling and LM diagonal of the cameras)
   double* C;        // [P][6]    point blocks, packed xx xy xz yy yz zz
   double* gp;       // [P][3]
   double* Cinv;     // [P][6]    s_p (s_p C s_p + D^2)^-1 s_p  (zero for constant points)
@@ -68,6 +73,7 @@ struct NormalEq {
   double* partials; // [n_chunks][104] per-chunk partial sums of the frame kernel
   const unsigned short* pose_mask;  // [F] constant-scalar bits
   const unsigned char* point_const; // [P]
+  const unsigned char* point_owned; // [P] 1 if this rank eliminates the point (all 1 on one GPU)
 };
 
 struct LmOptionsDev {
@@ -86,8 +92,13 @@ void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t
 void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
                       cudaStream_t s);
 void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s);
-void launch_schur_reduce(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,
-                         const int* tile_slot, int n_tiles, int n_frames, double* rhs, cudaStream_t s);
+// writes the UNSCALED tiles  B - Phi Phi^T  (partial sums on a multi-GPU rank)
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, double* S, const int* tile_slot, int n_tiles,
+                         cudaStream_t s);
+// after the (optional) all-reduce: Jacobi scaling, LM diagonal, constant rows, padding; d2_c and rhs
+struct TileSchedule;
+void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,
+                           const TileSchedule& ts, int n_frames, double* rhs, cudaStream_t s);
 
 // ---- K3 ---------------------------------------------------------------------------------
 struct TileSchedule {      // device view of the TilePlan (tile_plan.cuh); tile indices are POSITIONS
@@ -124,9 +135,13 @@ struct StepScalars {  // device doubles, filled by launch_step_update
 void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
-                        double* trial_points, double* scalars /* [8] */, double* scratch, cudaStream_t s);
-void launch_state_norms(NormalEq ne, int n_frames, int n_points, const double* poses, const double* points,
-                        double* scalars /* [8]: writes x_norm2 (3) and gmax (4) */, double* scratch,
-                        cudaStream_t s);
+                        double* trial_points, double* scalars /* [16]: [0..2] camera part, [8..10] point part */,
+                        double* scratch, cudaStream_t s);
+// |x|^2 and max|g| split into the point part (local to the rank; before the all-reduce) and the
+// camera part (replicated; after it).  out_points: [0] += |x_p|^2 over owned free points, [1] = max|g_p|
+void launch_point_norms(NormalEq ne, int n_points, const double* points, double* out_xx, double* out_gmax,
+                        double* scratch, cudaStream_t s);
+void launch_camera_norms(NormalEq ne, int n_frames, const double* poses, double* scalars /* writes [3], [4] */,
+                         cudaStream_t s);
 
 }  // namespace rsba

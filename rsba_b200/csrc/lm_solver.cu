@@ -20,8 +20,8 @@ namespace rsba {
 struct LmState {
   // ---- structure (device)
   DeviceBuffer<int> pt_ptr, pt_obs, chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr;
-  DeviceBuffer<int> inc_point, inc_tile, slot_beg, pair_a, pair_b, pair_item_ptr, tile_pos;
-  DeviceBuffer<unsigned char> slot_cnt;
+  DeviceBuffer<int> inc_point, inc_tile, slot_beg, pair_a, pair_b, pair_item_ptr, tile_pos, pos_tile;
+  DeviceBuffer<unsigned char> slot_cnt, point_owned;
   DeviceBuffer<int4> items;
   DeviceBuffer<int2> entries;
   DeviceBuffer<int2> nz_tiles, trsm;
@@ -34,8 +34,12 @@ struct LmState {
   TileSchedule ts{};
   bool dense = false, reorder = true;
   // ---- numeric state (device)
-  DeviceBuffer<double> B, gc, wf, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
-  DeviceBuffer<double> S, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
+  DeviceBuffer<double> B, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
+  // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
+  DeviceBuffer<double> S, misc_local, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
+  double* misc = nullptr;      // tail: [0] cost [1] invalid [2] |x_p|^2 ... [8 + r] max|g_p| of rank r
+  size_t comm_count = 0;       // doubles in S + tail
+  int misc_count = 0;
   DeviceBuffer<int> info;
   NormalEq ne{};
   long n_pad = 0;
@@ -158,11 +162,37 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
   const int n_items = (int)pair_item_ptr.back();
   // ---- ordering, symbolic factorisation, elimination levels (tile_plan.cu)
+  // (the plan is a function of the WHOLE scene, so every rank of a multi-GPU run derives the same one)
   TilePlan& plan = lm->plan;
   {
     std::vector<std::pair<int, int>> tp;
-    tp.reserve(pair_a.size());
-    for (size_t k = 0; k < pair_a.size(); ++k) tp.emplace_back(pair_a[k], pair_b[k]);
+    if (h->world > 1) {
+      const long NG = h->n_obs_global;
+      std::vector<long> gptr(P + 1, 0);
+      for (long i = 0; i < NG; ++i) gptr[h->g_obs_point[i] + 1]++;
+      for (int p = 0; p < P; ++p) gptr[p + 1] += gptr[p];
+      std::vector<int> gtile(NG);
+      {
+        std::vector<long> cur(gptr.begin(), gptr.end() - 1);
+        for (long i = 0; i < NG; ++i) gtile[cur[h->g_obs_point[i]]++] = h->g_obs_frame[i] / kFramesPerTile;
+      }
+      std::vector<char> seen((size_t)T * T, 0);
+      std::vector<int> tiles;
+      for (int p = 0; p < P; ++p) {
+        if (h->point_const[p]) continue;
+        tiles.clear();
+        for (long e = gptr[p]; e < gptr[p + 1]; ++e)
+          if (tiles.empty() || tiles.back() != gtile[e]) tiles.push_back(gtile[e]);
+        for (size_t x = 0; x < tiles.size(); ++x)
+          for (size_t y = x; y < tiles.size(); ++y) seen[(size_t)tiles[x] * T + tiles[y]] = 1;
+      }
+      for (int a = 0; a < T; ++a)
+        for (int b = a; b < T; ++b)
+          if (seen[(size_t)a * T + b]) tp.emplace_back(a, b);
+    } else {
+      tp.reserve(pair_a.size());
+      for (size_t k = 0; k < pair_a.size(); ++k) tp.emplace_back(pair_a[k], pair_b[k]);
+    }
     build_tile_plan(T, tp, dense, h->reorder_tiles, &plan);
   }
   const std::vector<int>& tile_pos = plan.tile_pos;
@@ -175,6 +205,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr);
   UP(inc_point, inc_point); UP(inc_tile, inc_tile); UP(slot_beg, slot_beg); UP(slot_cnt, slot_cnt);
   UP(pair_a, pair_a); UP(pair_b, pair_b); UP(pair_item_ptr, pair_item_ptr); UP(items, items); UP(tile_pos, tile_pos);
+  UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
   UP(entries, entries); UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
   UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
   UP(panels, plan.panels); UP(trsm, plan.trsm);
@@ -193,10 +224,11 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.n_pairs = (int)pair_a.size(); st.pair_a = lm->pair_a.ptr; st.pair_b = lm->pair_b.ptr;
   st.pair_item_ptr = lm->pair_item_ptr.ptr; st.n_items = n_items; st.items = lm->items.ptr;
   st.entries = lm->entries.ptr; st.n_entries = (long)entries.size(); st.tile_pos = lm->tile_pos.ptr;
+  st.pos_tile = lm->pos_tile.ptr; st.n_cam_params = 12L * F;
 
   // ---- numeric buffers
   const size_t Fz = std::max(F, 1), Pz = std::max(P, 1);
-  RSBA_CUDA_TRY(lm->B.resize(Fz * 144)); RSBA_CUDA_TRY(lm->gc.resize(Fz * 12)); RSBA_CUDA_TRY(lm->wf.resize(Fz * 12));
+  RSBA_CUDA_TRY(lm->B.resize(Fz * 144));
   RSBA_CUDA_TRY(lm->C.resize(Pz * 6)); RSBA_CUDA_TRY(lm->gp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Cinv.resize(Pz * 6));
   RSBA_CUDA_TRY(lm->tp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Minv.resize(Pz * 6));
   RSBA_CUDA_TRY(lm->Phi.resize((size_t)(n_inc + 1) * kPanelDoubles));
@@ -205,23 +237,32 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(lm->scale_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->scale_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->d2_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->d2_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 168));
-  RSBA_CUDA_TRY(lm->S.resize(std::max<size_t>(nz_tiles.size(), 1) * kTile * kTile));
+  const size_t s_count = std::max<size_t>(nz_tiles.size(), 1) * kTile * kTile;
+  lm->misc_count = 8 + h->world;
+  lm->comm_count = s_count + 3 * Fz * 12 + lm->misc_count;
+  RSBA_CUDA_TRY(lm->S.resize(lm->comm_count));
+  RSBA_CUDA_TRY(lm->misc_local.resize(lm->misc_count));
+  RSBA_CUDA_TRY(cudaMemsetAsync(lm->S.ptr, 0, lm->S.bytes(), s));
+  RSBA_CUDA_TRY(cudaMemsetAsync(lm->misc_local.ptr, 0, lm->misc_local.bytes(), s));
   RSBA_CUDA_TRY(lm->Dinv.resize((size_t)std::max(T, 1) * kTile * kTile));
   RSBA_CUDA_TRY(lm->rhs.resize(std::max<long>(lm->n_pad, 1))); RSBA_CUDA_TRY(lm->y.resize(std::max<long>(lm->n_pad, 1)));
   RSBA_CUDA_TRY(lm->delta_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->delta_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->trial_poses.resize(Fz * 12)); RSBA_CUDA_TRY(lm->trial_points.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->scalars.resize(16));
+  RSBA_CUDA_TRY(cudaMemsetAsync(lm->scalars.ptr, 0, lm->scalars.bytes(), s));
   RSBA_CUDA_TRY(lm->scratch.resize(std::max<size_t>(3 + 3 * ((Pz + 127) / 128), 1024)));
   RSBA_CUDA_TRY(lm->info.resize(4));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->rhs.ptr, 0, lm->rhs.bytes(), s));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->d2_c.ptr, 0, lm->d2_c.bytes(), s));
 
   NormalEq& ne = lm->ne;
-  ne.B = lm->B.ptr; ne.gc = lm->gc.ptr; ne.wf = lm->wf.ptr; ne.C = lm->C.ptr; ne.gp = lm->gp.ptr;
+  ne.B = lm->B.ptr; ne.C = lm->C.ptr; ne.gp = lm->gp.ptr;
+  ne.gc = lm->S.ptr + s_count; ne.wf = ne.gc + Fz * 12; ne.diagB = ne.wf + Fz * 12;
+  lm->misc = ne.diagB + Fz * 12;
   ne.Cinv = lm->Cinv.ptr; ne.tp = lm->tp.ptr; ne.Minv = lm->Minv.ptr; ne.Phi = lm->Phi.ptr; ne.partial = lm->partial.ptr;
   ne.scale_c = lm->scale_c.ptr; ne.scale_p = lm->scale_p.ptr;
   ne.d2_c = lm->d2_c.ptr; ne.d2_p = lm->d2_p.ptr; ne.partials = lm->partials.ptr;
-  ne.pose_mask = lm->pose_mask.ptr; ne.point_const = lm->point_const.ptr;
+  ne.pose_mask = lm->pose_mask.ptr; ne.point_const = lm->point_const.ptr; ne.point_owned = lm->point_owned.ptr;
 
   TileSchedule& ts = lm->ts;
   ts.n_tiles = T; ts.nz_tiles = lm->nz_tiles.ptr; ts.tile_slot = lm->tile_slot.ptr; ts.n_nz = (int)nz_tiles.size();
@@ -247,25 +288,64 @@ int ensure_lm(rsba_problem* h, bool dense) {
 }
 
 // ------------------------------------------------------------------ pipeline stages
-// Normal equations + Schur complement for `radius` from the Jacobian in h->d_jac.
-void linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, double radius, bool new_jacobian,
-               bool compute_scale) {
+__global__ void pack_cost_kernel(const double* __restrict__ cost, const int* __restrict__ invalid,
+                                 double* __restrict__ out) {
+  out[0] = cost[0];
+  out[1] = (double)invalid[0];
+}
+
+// Normal equations + Schur complement for `radius` from the Jacobian in h->d_jac (and, when
+// new_jacobian, the cost / invalid count of the evaluation that produced it, in h->d_scalars).
+int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, double radius, bool new_jacobian,
+              bool compute_scale) {
   cudaStream_t s = h->stream;
   const ObsView obs = h->obs_view();
   const LmOptionsDev o{radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
   stage_begin(h, kStageSchur);
-  if (new_jacobian) { launch_point_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_points, lm->ne, s); h->launches += 1; }
+  if (new_jacobian) {
+    stage_begin(h, kStagePointBlocks);
+    launch_point_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_points, lm->ne, s);
+    stage_end(h, kStagePointBlocks);
+    h->launches += 1;
+  }
   if (compute_scale) { launch_jacobi_scale(0, h->n_points, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
   launch_point_invert(h->n_points, lm->ne, o, s);
+  stage_begin(h, kStageFrameBlocks);
   launch_frame_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_frames, lm->ne, true, s);
+  stage_end(h, kStageFrameBlocks);
   h->launches += 3;
-  if (compute_scale) { launch_jacobi_scale(h->n_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
   launch_clear_tiles(lm->S.ptr, lm->ts, s);
+  stage_begin(h, kStagePhiBuild);
   launch_phi_build(lm->st, obs, h->d_jac.ptr, lm->ne, s);
+  stage_end(h, kStagePhiBuild);
+  stage_begin(h, kStageSchurSyrk);
   launch_schur_syrk(lm->st, lm->ne, s);
-  launch_schur_reduce(lm->st, lm->ne, o, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, h->n_frames, lm->rhs.ptr, s);
-  h->launches += 5;
+  stage_end(h, kStageSchurSyrk);
+  stage_begin(h, kStageSchurReduce);
+  launch_schur_reduce(lm->st, lm->ne, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
+  stage_end(h, kStageSchurReduce);
+  h->launches += 4;
+  if (new_jacobian) {   // scalars of the current point that ride in the same buffer
+    pack_cost_kernel<<<1, 1, 0, s>>>(h->d_scalars.ptr, h->d_invalid.ptr, lm->misc_local.ptr);
+    launch_point_norms(lm->ne, h->n_points, h->d_points.ptr, lm->misc_local.ptr + 2, lm->misc_local.ptr + 8 + h->rank,
+                       lm->scratch.ptr, s);
+    h->launches += 3;
+  }
+  cudaMemcpyAsync(lm->misc, lm->misc_local.ptr, lm->misc_count * sizeof(double), cudaMemcpyDeviceToDevice, s);
   stage_end(h, kStageSchur);
+  if (h->world > 1) {   // the one exchange step: partial S | gc | wf | diag(B) | scalars
+    stage_begin(h, kStageAllreduce);
+    int rc = allreduce_sum(h, lm->S.ptr, lm->comm_count);
+    stage_end(h, kStageAllreduce);
+    if (rc) return rc;
+  }
+  stage_begin(h, kStageFinalize);
+  if (compute_scale) { launch_jacobi_scale(h->n_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
+  launch_schur_finalize(lm->st, lm->ne, o, lm->S.ptr, lm->ts, h->n_frames, lm->rhs.ptr, s);
+  launch_camera_norms(lm->ne, h->n_frames, h->d_poses.ptr, lm->scalars.ptr, s);
+  h->launches += 3;
+  stage_end(h, kStageFinalize);
+  return RSBA_OK;
 }
 
 void factor_and_solve(rsba_problem* h, LmState* lm) {
@@ -273,8 +353,12 @@ void factor_and_solve(rsba_problem* h, LmState* lm) {
   stage_begin(h, kStageCholesky);
   cudaMemsetAsync(lm->info.ptr, 0, sizeof(int), s);
   cudaMemcpyAsync(lm->y.ptr, lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  stage_begin(h, kStageFactor);
   h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->info.ptr, s);
+  stage_end(h, kStageFactor);
+  stage_begin(h, kStageTriSolve);
   h->launches += launch_tile_solve(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, s);
+  stage_end(h, kStageTriSolve);
   stage_end(h, kStageCholesky);
 }
 
@@ -287,22 +371,67 @@ void step_update(rsba_problem* h, LmState* lm) {
   stage_end(h, kStageUpdate);
 }
 
+// cost at the trial point (K1r) + the step scalars, summed over the ranks
+int trial_cost(rsba_problem* h, LmState* lm) {
+  int rc = run_evaluate(h, false, lm->trial_poses.ptr, lm->trial_points.ptr, nullptr, nullptr);
+  if (rc) return rc;
+  pack_cost_kernel<<<1, 1, 0, h->stream>>>(h->d_scalars.ptr, h->d_invalid.ptr, lm->scalars.ptr + 11);
+  h->launches += 1;
+  return allreduce_sum(h, lm->scalars.ptr + 8, 8);
+}
+
 struct HostScalars {
-  double s[8];
-  double cost;
-  int invalid;
+  double s[16];     // lm->scalars: [0..2] camera g.d, D^2 d^2, |d|^2  [3] |x_c|^2 [4] max|g_c|
+                    //              [8..10] the same three over the points  [11] trial cost [12] trial invalid
+  double misc[8];   // tail of the reduced-system buffer: [0] cost [1] invalid [2] |x_p|^2
+  double gmax_p;    // max over the ranks' slots
   int info;
+  // derived
+  double cost, x_norm, gmax, g_dot_delta, d2_delta2, step_norm, trial_cost;
+  long invalid, trial_invalid;
 };
 
 int fetch(rsba_problem* h, LmState* lm, HostScalars* out) {
   cudaStream_t s = h->stream;
-  RSBA_CUDA_TRY(cudaMemcpyAsync(out->s, lm->scalars.ptr, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
-  RSBA_CUDA_TRY(cudaMemcpyAsync(&out->cost, h->d_scalars.ptr, sizeof(double), cudaMemcpyDeviceToHost, s));
-  RSBA_CUDA_TRY(cudaMemcpyAsync(&out->invalid, h->d_invalid.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+  std::vector<double> misc(lm->misc_count);
+  RSBA_CUDA_TRY(cudaMemcpyAsync(out->s, lm->scalars.ptr, 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  RSBA_CUDA_TRY(cudaMemcpyAsync(misc.data(), lm->misc, lm->misc_count * sizeof(double), cudaMemcpyDeviceToHost, s));
   RSBA_CUDA_TRY(cudaMemcpyAsync(&out->info, lm->info.ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
   RSBA_CUDA_TRY(cudaStreamSynchronize(s));
   RSBA_CUDA_TRY(cudaGetLastError());
+  for (int k = 0; k < 8; ++k) out->misc[k] = misc[k];
+  out->gmax_p = 0.0;
+  for (int r = 0; r < h->world; ++r) out->gmax_p = std::max(out->gmax_p, misc[8 + r]);
+  out->cost = misc[0];
+  out->invalid = (long)(misc[1] + 0.5);
+  out->x_norm = std::sqrt(out->s[3] + misc[2]);
+  out->gmax = std::max(out->s[4], out->gmax_p);
+  out->g_dot_delta = out->s[0] + out->s[8];
+  out->d2_delta2 = out->s[1] + out->s[9];
+  out->step_norm = std::sqrt(out->s[2] + out->s[10]);
+  out->trial_cost = out->s[11];
+  out->trial_invalid = (long)(out->s[12] + 0.5);
   for (int k = 0; k < kNumStages; ++k) stage_collect(h, (Stage)k);
+  return RSBA_OK;
+}
+
+__global__ void mask_unowned_kernel(const double* __restrict__ points, const unsigned char* __restrict__ owned,
+                                    long n, double* __restrict__ out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = owned[t / 3] ? points[t] : 0.0;
+}
+
+// Every rank moves only the points it owns; at the end of a solve the owners' values are summed
+// into every rank's copy (each point has exactly one owner).
+int gather_points(rsba_problem* h, LmState* lm) {
+  if (h->world <= 1 || h->n_points == 0) return RSBA_OK;
+  const long n = 3L * h->n_points;
+  mask_unowned_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_points.ptr, lm->point_owned.ptr, n,
+                                                                       lm->trial_points.ptr);
+  h->launches += 1;
+  int rc = allreduce_sum(h, lm->trial_points.ptr, (size_t)n);
+  if (rc) return rc;
+  RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_points.ptr, lm->trial_points.ptr, n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   return RSBA_OK;
 }
 
@@ -366,30 +495,26 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
 
   HostScalars hs{};
   double radius = opt->initial_trust_region_radius, decrease = 2.0;
+  double cost = 0.0, x_norm = 0.0, gmax = 0.0;
   // ---- iteration 0: evaluate, linearise (fixes the Jacobi scaling), gradient check
   rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
   if (rc) return rc;
   sum->num_jacobian_evaluations = 1;
-  linearize(h, lm, *opt, radius, true, true);
-  launch_state_norms(lm->ne, h->n_frames, h->n_points, h->d_poses.ptr, h->d_points.ptr, lm->scalars.ptr,
-                     lm->scratch.ptr, h->stream);
-  h->launches += 2;
+  if ((rc = linearize(h, lm, *opt, radius, true, true))) return rc;
   if ((rc = fetch(h, lm, &hs))) return rc;
-  double cost = hs.cost, x_norm = std::sqrt(hs.s[3]), gmax = hs.s[4];
+  cost = hs.cost; x_norm = hs.x_norm; gmax = hs.gmax;
   sum->initial_cost = cost;
   if (hs.invalid > 0) {
     finish(2, "FAILURE: residual evaluation failed at the initial point (point behind a camera)", cost, radius, gmax);
     wall();
     return fail(RSBA_ERR_EVALUATION_FAILED, sum->message);
   }
-  if (opt->verbose)
+  if (opt->verbose && h->rank == 0)
     printf("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n%4d % .6e                % .2e                        % .2e\n",
            0, cost, gmax, radius);
   if (gmax <= opt->gradient_tolerance) {
     finish(0, "CONVERGENCE: gradient tolerance reached", cost, radius, gmax);
-    goto done;
-  }
-  {
+  } else {
     int it = 0;
     while (true) {
       if (it >= opt->max_num_iterations) {
@@ -400,9 +525,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
       sum->iterations = it;
       factor_and_solve(h, lm);
       step_update(h, lm);
-      cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), h->stream);
-      rc = run_evaluate(h, false, lm->trial_poses.ptr, lm->trial_points.ptr, nullptr, nullptr);
-      if (rc) return rc;
+      if ((rc = trial_cost(h, lm))) return rc;
       sum->num_residual_evaluations++;
       if ((rc = fetch(h, lm, &hs))) return rc;
       if (hs.info != 0) {
@@ -410,24 +533,22 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         wall();
         return fail(RSBA_ERR_LINEAR_SOLVER, sum->message);
       }
-      const double mcc = -0.5 * hs.s[0] + 0.5 * hs.s[1];
-      const double step_norm = std::sqrt(hs.s[2]);
+      const double mcc = -0.5 * hs.g_dot_delta + 0.5 * hs.d2_delta2;
+      const double step_norm = hs.step_norm;
       bool accepted = false;
-      double rho = 0.0, new_cost = hs.cost;
-      if (mcc > 0.0) {
-        const bool ok = hs.invalid == 0;
-        if (ok) {
-          if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
-            finish(0, "CONVERGENCE: parameter tolerance reached", cost, radius, gmax);
-            break;
-          }
-          if (std::fabs(cost - new_cost) < opt->function_tolerance * cost) {
-            finish(0, "CONVERGENCE: function tolerance reached", cost, radius, gmax);
-            break;
-          }
-          rho = (cost - new_cost) / mcc;
-          accepted = rho > opt->min_relative_decrease;
+      double rho = 0.0;
+      const double new_cost = hs.trial_cost;
+      if (mcc > 0.0 && hs.trial_invalid == 0) {
+        if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
+          finish(0, "CONVERGENCE: parameter tolerance reached", cost, radius, gmax);
+          break;
         }
+        if (std::fabs(cost - new_cost) < opt->function_tolerance * cost) {
+          finish(0, "CONVERGENCE: function tolerance reached", cost, radius, gmax);
+          break;
+        }
+        rho = (cost - new_cost) / mcc;
+        accepted = rho > opt->min_relative_decrease;
       }
       if (accepted) {
         sum->num_successful_steps++;
@@ -439,16 +560,11 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
         if (rc) return rc;
         sum->num_jacobian_evaluations++;
-        linearize(h, lm, *opt, radius, true, false);
-        launch_state_norms(lm->ne, h->n_frames, h->n_points, h->d_poses.ptr, h->d_points.ptr, lm->scalars.ptr,
-                           lm->scratch.ptr, h->stream);
-        h->launches += 2;
+        if ((rc = linearize(h, lm, *opt, radius, true, false))) return rc;
         if ((rc = fetch(h, lm, &hs))) return rc;
         const double old = cost;
-        cost = hs.cost;
-        x_norm = std::sqrt(hs.s[3]);
-        gmax = hs.s[4];
-        if (opt->verbose)
+        cost = hs.cost; x_norm = hs.x_norm; gmax = hs.gmax;
+        if (opt->verbose && h->rank == 0)
           printf("%4d % .6e  % .2e  % .2e  % .2e  % .2e  % .2e\n", it, cost, old - cost, gmax, step_norm, rho, radius);
         if (gmax <= opt->gradient_tolerance) {
           finish(0, "CONVERGENCE: gradient tolerance reached", cost, radius, gmax);
@@ -458,18 +574,19 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         sum->num_unsuccessful_steps++;
         radius /= decrease;
         decrease *= 2.0;
-        if (opt->verbose)
+        if (opt->verbose && h->rank == 0)
           printf("%4d % .6e  % .2e  % .2e  % .2e  % .2e  % .2e (rejected)\n", it, cost, 0.0, gmax, step_norm, rho, radius);
         if (radius < opt->min_trust_region_radius) {
           finish(0, "CONVERGENCE: trust region radius below minimum", cost, radius, gmax);
           break;
         }
-        linearize(h, lm, *opt, radius, false, false);   // same Jacobian, new damping
+        if ((rc = linearize(h, lm, *opt, radius, false, false))) return rc;   // same Jacobian, new damping
       }
     }
   }
-done:
+  if ((rc = gather_points(h, lm))) return rc;
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  sum->time_schur_ms += h->timers[kStageFinalize].total_ms;
   if (h->ptr_mode) {
     rc = scatter_pointer_parameters(h);
     if (rc) return rc;
@@ -487,7 +604,7 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
   LmState* lm = h->lm;
   rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
   if (rc) return rc;
-  linearize(h, lm, *opt, radius, true, true);
+  if ((rc = linearize(h, lm, *opt, radius, true, true))) return rc;
   const long n = 12L * h->n_frames;
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (S_out) {
@@ -515,13 +632,14 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
   }
   factor_and_solve(h, lm);
   step_update(h, lm);
+  if ((rc = allreduce_sum(h, lm->scalars.ptr + 8, 8))) return rc;
   HostScalars hs{};
   if ((rc = fetch(h, lm, &hs))) return rc;
   if (hs.info != 0) return fail(RSBA_ERR_LINEAR_SOLVER, "reduced camera matrix is not positive definite");
   if (delta_poses) RSBA_CUDA_TRY(cudaMemcpy(delta_poses, lm->delta_c.ptr, n * sizeof(double), cudaMemcpyDeviceToHost));
   if (delta_points)
     RSBA_CUDA_TRY(cudaMemcpy(delta_points, lm->delta_p.ptr, 3L * h->n_points * sizeof(double), cudaMemcpyDeviceToHost));
-  if (model_cost_change) *model_cost_change = -0.5 * hs.s[0] + 0.5 * hs.s[1];
+  if (model_cost_change) *model_cost_change = -0.5 * hs.g_dot_delta + 0.5 * hs.d2_delta2;
   return RSBA_OK;
 }
 
@@ -553,7 +671,5 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
   return RSBA_OK;
 }
 
-int rsba_cuda_nccl_unique_id(unsigned char*) { set_last_error("NCCL path not built yet"); return RSBA_ERR_NCCL; }
-int rsba_cuda_comm_init(rsba_problem*, int, int, const unsigned char*) { set_last_error("NCCL path not built yet"); return RSBA_ERR_NCCL; }
 
 }  // extern "C"

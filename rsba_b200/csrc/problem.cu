@@ -1,5 +1,8 @@
 // C ABI: lifecycle, problem construction, evaluation (include/rsba_cuda.h).
 #include "problem.cuh"
+#include "nccl_dl.cuh"
+
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstring>
@@ -23,6 +26,38 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 static int fail(int code, const std::string& msg) {
   set_last_error(msg);
   return code;
+}
+
+const NcclApi* nccl_api() {
+  static NcclApi api;
+  static int state = 0;   // 0 untried, 1 ok, -1 failed
+  if (state == 0) {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      set_last_error(std::string("cannot load libnccl.so.2: ") + dlerror());
+      state = -1;
+    } else {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(lib, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(lib, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(lib, "ncclAllReduce");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(lib, "ncclGetErrorString");
+      const bool ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+      if (!ok) set_last_error("libnccl.so.2 lacks a required symbol");
+      state = ok ? 1 : -1;
+    }
+  }
+  return state == 1 ? &api : nullptr;
+}
+
+int allreduce_sum(rsba_problem* h, double* buf, size_t count) {
+  if (h->world <= 1 || count == 0) return RSBA_OK;
+  const NcclApi* api = nccl_api();
+  if (!api || !h->nccl_comm) return fail(RSBA_ERR_NCCL, "no NCCL communicator (rsba_cuda_comm_init)");
+  ncclResult_t r = api->AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream);
+  if (r != ncclSuccess) return fail(RSBA_ERR_NCCL, std::string("ncclAllReduce: ") + api->GetErrorString(r));
+  return RSBA_OK;
 }
 
 void stage_begin(rsba_problem* h, Stage s) {
@@ -89,14 +124,85 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
     RSBA_CUDA_TRY(cudaMemcpyAsync(&c, h->d_scalars.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     RSBA_CUDA_TRY(cudaMemcpyAsync(&bad, h->d_invalid.ptr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->world > 1) {   // cost and invalid count are sums over the ranks' shares
+      double pair[2] = {c, (double)bad};
+      RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_scalars.ptr + 8, pair, sizeof(pair), cudaMemcpyHostToDevice, h->stream));
+      int rc2 = allreduce_sum(h, h->d_scalars.ptr + 8, 2);
+      if (rc2) return rc2;
+      RSBA_CUDA_TRY(cudaMemcpyAsync(pair, h->d_scalars.ptr + 8, sizeof(pair), cudaMemcpyDeviceToHost, h->stream));
+      RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+      c = pair[0];
+      bad = (int)(pair[1] + 0.5);
+    }
     if (cost_out_host) *cost_out_host = c;
     if (invalid_out_host) *invalid_out_host = bad;
   }
   return RSBA_OK;
 }
 
+void compute_point_owners(int n_frames, int n_points, long n_obs, const int* obs_frame_sorted,
+                          const int* obs_point, int world, std::vector<int>* owner) {
+  owner->assign(n_points, 0);
+  const int T = std::max(1, (n_frames + 7) / 8);
+  std::vector<long> ptr(n_points + 1, 0);
+  for (long i = 0; i < n_obs; ++i) ptr[obs_point[i] + 1]++;
+  for (int p = 0; p < n_points; ++p) ptr[p + 1] += ptr[p];
+  std::vector<int> frames(n_obs);
+  {
+    std::vector<long> cur(ptr.begin(), ptr.end() - 1);
+    for (long i = 0; i < n_obs; ++i) frames[cur[obs_point[i]]++] = obs_frame_sorted[i];  // ascending per point
+  }
+  for (int p = 0; p < n_points; ++p) {
+    const long k = ptr[p + 1] - ptr[p];
+    if (k == 0) { (*owner)[p] = p % world; continue; }
+    const int home_tile = frames[ptr[p] + k / 2] / 8;
+    (*owner)[p] = std::min(world - 1, (int)((long)home_tile * world / T));
+  }
+}
+
+int materialize_local_share(rsba_problem* h) {
+  const long N = h->n_obs_global;
+  h->point_owned.assign(h->n_points, 1);
+  h->local_ids.clear();
+  if (h->world > 1) {
+    std::vector<int> owner;
+    compute_point_owners(h->n_frames, h->n_points, N, h->g_obs_frame.data(), h->g_obs_point.data(), h->world, &owner);
+    for (int p = 0; p < h->n_points; ++p) h->point_owned[p] = owner[p] == h->rank;
+    for (long i = 0; i < N; ++i)
+      if (h->point_owned[h->g_obs_point[i]]) h->local_ids.push_back(i);
+  } else {
+    h->local_ids.resize(N);
+    std::iota(h->local_ids.begin(), h->local_ids.end(), 0L);
+  }
+  const long n = (long)h->local_ids.size();
+  std::vector<double2> sxy(n);
+  h->h_obs_frame.resize(n);
+  h->h_obs_point.resize(n);
+  for (long i = 0; i < n; ++i) {
+    const long g = h->local_ids[i];
+    sxy[i] = h->g_obs_xy[g];
+    h->h_obs_frame[i] = h->g_obs_frame[g];
+    h->h_obs_point[i] = h->g_obs_point[g];
+  }
+  h->n_obs = n;
+  RSBA_CUDA_TRY(h->d_obs_xy.resize(n));
+  RSBA_CUDA_TRY(h->d_obs_frame.resize(n));
+  RSBA_CUDA_TRY(h->d_obs_point.resize(n));
+  if (n > 0) {
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_xy.ptr, sxy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame.ptr, h->h_obs_frame.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_point.ptr, h->h_obs_point.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));  // sxy is a local
+  if (h->lm) {
+    lm_state_free(h->lm);
+    h->lm = nullptr;
+  }
+  return RSBA_OK;
+}
+
 // Sort observations by frame (stable: keeps the caller's within-frame order, which is the
-// reference's insertion order, CeresHandler.h:208) and upload the SoA.
+// reference's insertion order, CeresHandler.h:208) and upload this rank's share of the SoA.
 static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr, const int* pt,
                         int n_frames, int n_points) {
   for (long i = 0; i < n; ++i) {
@@ -109,35 +215,24 @@ static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr
   for (long i = 1; i < n && sorted; ++i) sorted = fr[i - 1] <= fr[i];
   if (!sorted)
     std::stable_sort(h->order.begin(), h->order.end(), [&](long a, long b) { return fr[a] < fr[b]; });
-  std::vector<double2> sxy(n);
-  h->h_obs_frame.resize(n);
-  h->h_obs_point.resize(n);
+  h->g_obs_xy.resize(n);
+  h->g_obs_frame.resize(n);
+  h->g_obs_point.resize(n);
   for (long i = 0; i < n; ++i) {
     const long s = h->order[i];
-    sxy[i] = make_double2(xy[2 * s], xy[2 * s + 1]);
-    h->h_obs_frame[i] = fr[s];
-    h->h_obs_point[i] = pt[s];
+    h->g_obs_xy[i] = make_double2(xy[2 * s], xy[2 * s + 1]);
+    h->g_obs_frame[i] = fr[s];
+    h->g_obs_point[i] = pt[s];
   }
-  h->n_obs = n;
+  h->n_obs_global = n;
   h->n_frames = n_frames;
   h->n_points = n_points;
-  RSBA_CUDA_TRY(h->d_obs_xy.resize(n));
-  RSBA_CUDA_TRY(h->d_obs_frame.resize(n));
-  RSBA_CUDA_TRY(h->d_obs_point.resize(n));
   RSBA_CUDA_TRY(h->d_poses.resize((size_t)kFrameParams * n_frames));
   RSBA_CUDA_TRY(h->d_points.resize((size_t)kPointParams * n_points));
-  if (n > 0) {
-    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_xy.ptr, sxy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame.ptr, h->h_obs_frame.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_point.ptr, h->h_obs_point.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  }
-  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));  // sxy is a local
+  int rc = materialize_local_share(h);
+  if (rc) return rc;
   h->scene_set = true;
   h->params_set = false;
-  if (h->lm) {
-    lm_state_free(h->lm);
-    h->lm = nullptr;
-  }
   return RSBA_OK;
 }
 
@@ -226,8 +321,60 @@ void rsba_cuda_destroy(rsba_problem* h) {
     if (t.beg) cudaEventDestroy(t.beg);
     if (t.end) cudaEventDestroy(t.end);
   }
+  if (h->nccl_comm) {
+    const NcclApi* api = nccl_api();
+    if (api) api->CommDestroy((ncclComm_t)h->nccl_comm);
+  }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+int rsba_cuda_nccl_unique_id(unsigned char id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (!id) return fail(RSBA_ERR_INVALID_ARGUMENT, "id is NULL");
+  const NcclApi* api = nccl_api();
+  if (!api) return RSBA_ERR_NCCL;
+  ncclUniqueId uid;
+  ncclResult_t r = api->GetUniqueId(&uid);
+  if (r != ncclSuccess) return fail(RSBA_ERR_NCCL, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
+  memcpy(id, &uid, 128);
+  return RSBA_OK;
+}
+
+int rsba_cuda_point_owners(int n_frames, int n_points, long n_obs, const int* obs_frame, const int* obs_point,
+                           int world_size, int* owner) {
+  if (n_frames < 0 || n_points < 0 || n_obs < 0 || world_size < 1 || !owner || (n_obs > 0 && (!obs_frame || !obs_point)))
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "bad arguments");
+  for (long i = 0; i < n_obs; ++i) {
+    if (obs_frame[i] < 0 || obs_frame[i] >= n_frames || obs_point[i] < 0 || obs_point[i] >= n_points)
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "observation index out of range");
+    if (i > 0 && obs_frame[i - 1] > obs_frame[i]) return fail(RSBA_ERR_INVALID_ARGUMENT, "obs_frame must be sorted");
+  }
+  std::vector<int> o;
+  compute_point_owners(n_frames, n_points, n_obs, obs_frame, obs_point, world_size, &o);
+  std::copy(o.begin(), o.end(), owner);
+  return RSBA_OK;
+}
+
+int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigned char id[128]) {
+  if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size)
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+  if (h->nccl_comm) return fail(RSBA_ERR_STATE, "communicator already initialised");
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  if (world_size > 1) {
+    const NcclApi* api = nccl_api();
+    if (!api) return RSBA_ERR_NCCL;
+    ncclUniqueId uid;
+    memcpy(&uid, id, 128);
+    ncclComm_t comm;
+    ncclResult_t r = api->CommInitRank(&comm, world_size, uid, rank);
+    if (r != ncclSuccess) return fail(RSBA_ERR_NCCL, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
+    h->nccl_comm = comm;
+  }
+  h->rank = rank;
+  h->world = world_size;
+  if (h->scene_set) return materialize_local_share(h);   // re-shard a scene that was set first
+  return RSBA_OK;
 }
 
 int rsba_cuda_set_stream(rsba_problem* h, void* cuda_stream) {
@@ -391,17 +538,24 @@ int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double*
   rc = run_evaluate(h, jac || residuals || valid, h->d_poses.ptr, h->d_points.ptr, &c, &bad);
   if (rc) return rc;
   if (cost) *cost = c;
-  const long n = h->n_obs;
-  // outputs go back in the caller's observation order
-  bool identity = true;
+  const long n = h->n_obs, ng = h->n_obs_global;
+  // outputs go back in the caller's observation order; on a multi-GPU rank only the rows of
+  // this rank's observations are filled, the others are zero
+  bool identity = n == ng;
   for (long i = 0; i < n && identity; ++i) identity = h->order[i] == i;
+  if (!identity) {
+    if (residuals) memset(residuals, 0, 2 * ng * sizeof(double));
+    if (jacobian) memset(jacobian, 0, (size_t)kJacDoubles * ng * sizeof(double));
+    if (valid) memset(valid, 0, ng);
+  }
+  auto dst_of = [&](long i) { return h->order[h->local_ids[i]]; };
   if (residuals && n) {
     if (identity) {
       RSBA_CUDA_TRY(cudaMemcpy(residuals, h->d_res.ptr, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
     } else {
       std::vector<double> tmp(2 * n);
       RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_res.ptr, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
-      for (long i = 0; i < n; ++i) memcpy(residuals + 2 * h->order[i], &tmp[2 * i], 2 * sizeof(double));
+      for (long i = 0; i < n; ++i) memcpy(residuals + 2 * dst_of(i), &tmp[2 * i], 2 * sizeof(double));
     }
   }
   if (jacobian && n) {
@@ -411,7 +565,7 @@ int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double*
       std::vector<double> tmp((size_t)kJacDoubles * n);
       RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_jac.ptr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
       for (long i = 0; i < n; ++i)
-        memcpy(jacobian + (size_t)kJacDoubles * h->order[i], &tmp[(size_t)kJacDoubles * i], kJacDoubles * sizeof(double));
+        memcpy(jacobian + (size_t)kJacDoubles * dst_of(i), &tmp[(size_t)kJacDoubles * i], kJacDoubles * sizeof(double));
     }
   }
   if (valid && n) {
@@ -420,7 +574,7 @@ int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double*
     } else {
       std::vector<unsigned char> tmp(n);
       RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_valid.ptr, n, cudaMemcpyDeviceToHost));
-      for (long i = 0; i < n; ++i) valid[h->order[i]] = tmp[i];
+      for (long i = 0; i < n; ++i) valid[dst_of(i)] = tmp[i];
     }
   }
   if (bad > 0) return fail(RSBA_ERR_EVALUATION_FAILED, "a cost functor returned false (point behind camera)");

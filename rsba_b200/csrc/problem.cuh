@@ -52,7 +52,10 @@ struct StageTimer {
 };
 
 enum Stage { kStageJacobian = 0, kStageResidual, kStageSchur, kStageCholesky, kStageUpdate,
-             kStageAllreduce, kNumStages };
+             kStageAllreduce,
+             // single kernels inside the stages above (nested events), for the per-kernel rooflines
+             kStagePointBlocks, kStageFrameBlocks, kStagePhiBuild, kStageSchurSyrk, kStageSchurReduce,
+             kStageFactor, kStageTriSolve, kStagePointStep, kStageFinalize, kNumStages };
 
 struct LmState;  // solver-side device state (lm_solver.cu)
 
@@ -75,11 +78,17 @@ struct rsba_problem {
   bool ptr_mode = false;
   bool ptr_dirty = false;
 
-  // ---- finalised scene (sorted by frame)
-  long n_obs = 0;
+  // ---- finalised scene (sorted by frame).  g_* = the whole scene; h_* / n_obs / the device
+  // arrays = this rank's share (identical to g_* on one GPU): all observations of the points
+  // the rank owns (point-owner rule)
+  long n_obs = 0, n_obs_global = 0;
   int n_frames = 0, n_points = 0;
-  std::vector<long> order;                 // sorted position -> caller's observation index
-  std::vector<int> h_obs_frame, h_obs_point;  // sorted, host copy (structure analysis)
+  std::vector<long> order;                 // sorted global position -> caller's observation index
+  std::vector<double2> g_obs_xy;
+  std::vector<int> g_obs_frame, g_obs_point;
+  std::vector<long> local_ids;             // local observation -> sorted global position
+  std::vector<int> h_obs_frame, h_obs_point;  // local share, host copy (structure analysis)
+  std::vector<unsigned char> point_owned;  // [points] 1 if this rank eliminates the point
   std::vector<unsigned short> pose_mask;   // [frames] constant-scalar bits
   std::vector<unsigned char> point_const;  // [points]
   bool scene_set = false, params_set = false;
@@ -114,6 +123,12 @@ void stage_begin(rsba_problem* h, Stage s);
 void stage_end(rsba_problem* h, Stage s);
 double stage_collect(rsba_problem* h, Stage s);  // syncs on the end event; returns last ms
 
+int materialize_local_share(rsba_problem* h);     // g_* -> this rank's observations on the device
+// owner rank of every point: the rank whose contiguous range of frame tiles holds the point's
+// median observation (host logic, no device)
+void compute_point_owners(int n_frames, int n_points, long n_obs, const int* obs_frame_sorted,
+                          const int* obs_point, int world, std::vector<int>* owner);
+int allreduce_sum(rsba_problem* h, double* buf, size_t count);   // in place, on the handle's stream
 int finalize_pointer_problem(rsba_problem* h);   // pointer API -> sorted SoA on device
 int gather_pointer_parameters(rsba_problem* h);  // caller blocks -> device
 int scatter_pointer_parameters(rsba_problem* h); // device -> caller blocks
