@@ -361,19 +361,27 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     h2d = (poses_h.numel() + points_h.numel()) * 8 / args.steps
     d2h = (poses_h.numel() + points_h.numel()) * 8 / args.steps + 7 * 8 + 8
+    if world > 1:
+        import torch.distributed as dist
+        pb.close()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
     hbm_peak, hbm_src = load_peaks()
     bpo = k1_bytes_per_obs(scene)
     k1 = kern["jacobian"]
-    roof_k1 = {"bound": "hbm", "kernel": "k1_kernel<true> (residual + Jacobian)", "achieved": n_total * bpo / (k1 * 1e-3) / 1e9,
+    n_local = int(summ.num_residual_blocks)     # this rank's share of the observations (== n_total on one GPU)
+    share = n_local / n_total
+    roof_k1 = {"bound": "hbm", "kernel": "k1_kernel<true> (residual + Jacobian)", "achieved": n_local * bpo / (k1 * 1e-3) / 1e9,
                "peak": hbm_peak, "unit": "GB/s", "traffic": 1.364e9, "peak_source": hbm_src,
-               "algorithmic_bytes": n_total * bpo, "bytes_per_obs": bpo, "kernel_ms": k1,
-               "k1_only_M_evals_per_s": n_total / (k1 * 1e-3) / 1e6,
+               "algorithmic_bytes": n_local * bpo, "bytes_per_obs": bpo, "kernel_ms": k1,
+               "k1_only_M_evals_per_s": n_local / (k1 * 1e-3) / 1e6, "observations_on_this_rank": n_local,
                "traffic_source": "profiles/r01a_k1k2_full.txt (ncu --set full, dram read+write per launch)"}
     roof_k1["frac"] = roof_k1["achieved"] / hbm_peak
-    fl = schur_algorithmic_flops(scene)
+    if world > 1:
+        roof_k1["traffic"] = None
+    fl = schur_algorithmic_flops(scene) * share       # rank 0's share of the points
     fp64_src = "tools/fp64_peak.cu measured on this pool (profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 figure"
     roof_syrk = {"bound": "tensor", "kernel": "schur_syrk_kernel (Schur complement, FP64 mma.sync m8n8k4)",
                  "achieved": fl / (kern["schur_syrk"] * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",

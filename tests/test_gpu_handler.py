@@ -1,0 +1,78 @@
+"""The C++ host side (include/rsba_cuda_handler.hpp): a CeresHandler-shaped Add()/solve() driven
+exactly as VideoSfMHandler::BA drives the reference (VideoSfMHandler.cc:586-592), through the
+pointer-identity API, must reproduce the bulk-API solve."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from rsba_b200.scene import make_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "tools", "handler_check")
+
+
+def write_scene(path, sc):
+    with open(path, "wb") as f:
+        np.array([sc.num_frames, sc.num_points, sc.num_obs, sc.shutter], dtype=np.int64).tofile(f)
+        np.asarray(sc.cam, dtype=np.float64).tofile(f)
+        np.asarray(sc.scanlines, dtype=np.int32).tofile(f)
+        np.ascontiguousarray(sc.poses, dtype=np.float64).tofile(f)
+        np.ascontiguousarray(sc.points, dtype=np.float64).tofile(f)
+        np.ascontiguousarray(sc.obs_xy, dtype=np.float64).tofile(f)
+        np.ascontiguousarray(sc.obs_frame, dtype=np.int32).tofile(f)
+        np.ascontiguousarray(sc.obs_point, dtype=np.int32).tofile(f)
+
+
+def test_handler_binary_is_built():
+    """build() compiles the header against plain structs with g++ (no GPU needed for that)."""
+    assert os.path.exists(BIN), "run __graft_entry__.build()"
+
+
+@pytest.mark.gpu
+def test_handler_add_solve_matches_bulk_api(tmp_path):
+    import rsba_b200.api as api
+    sc = make_scene(12, 400, 8, name="handler")
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    r = subprocess.run([BIN, src, dst, "1", "6"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst)
+    usable, iters, c0, c1 = out[:4]
+    poses = out[4:4 + 12 * sc.num_frames].reshape(-1, 12)
+    points = out[4 + 12 * sc.num_frames:].reshape(-1, 3)
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        s = pb.solve(api.default_options(max_num_iterations=6))
+        po, pt = pb.get_parameters()
+    assert usable == 1 and int(iters) == s.iterations
+    assert abs(c0 - s.initial_cost) <= 1e-12 * s.initial_cost
+    assert abs(c1 - s.final_cost) <= 1e-9 * s.final_cost
+    # points that no frame observes are never handed to the handler and keep their values
+    seen = np.zeros(sc.num_points, bool)
+    seen[sc.obs_point] = True
+    assert np.linalg.norm(poses - po) <= 1e-7 * np.linalg.norm(po)
+    assert np.linalg.norm(points[seen] - pt[seen]) <= 1e-7 * np.linalg.norm(pt[seen])
+    assert not poses[0].any()                      # fixFirstNCameras = 1: frame 0 untouched
+
+
+@pytest.mark.gpu
+def test_handler_windowed_ba_freezes_old_tracks(tmp_path):
+    """startFrame > 0 (windowedBA, VideoSfMHandler.cc:185): frames before the window are not added,
+    tracks seen before it are SetParameterBlockConstant (CeresHandler.h:288-300)."""
+    sc = make_scene(12, 400, 8, name="window")
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    start = 6
+    r = subprocess.run([BIN, src, dst, "0", "5", str(start)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst)
+    assert out[0] == 1 and out[3] < out[2]
+    poses = out[4:4 + 12 * sc.num_frames].reshape(-1, 12)
+    points = out[4 + 12 * sc.num_frames:].reshape(-1, 3)
+    assert np.array_equal(poses[:start], sc.poses[:start])          # outside the window
+    old = np.zeros(sc.num_points, bool)
+    old[sc.obs_point[sc.obs_frame < start]] = True
+    assert np.array_equal(points[old], sc.points[old])               # frozen tracks
+    assert np.any(points[~old] != sc.points[~old])

@@ -1,0 +1,118 @@
+// Test driver for include/rsba_cuda_handler.hpp: a CeresHandler-shaped Add()/solve() over plain
+// structs that have the members rsba's Thrift-generated gen::Session offers on this path
+// (gen-cpp/sfm_types.h: Frame.poses, Frame.obs, Observation.{x,y,track}, Track.{pt,valid,obs},
+// Session.{cam,rs,scanlines,frames}).  Reads a flat scene file written by tests/test_gpu_handler.py,
+// runs the same calls VideoSfMHandler::BA makes (VideoSfMHandler.cc:586-592), writes the result.
+//   usage: handler_check <scene.bin> <out.bin> <fixFirstNCameras> <maxIter> [startFrame]
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <vector>
+
+#include "rsba_cuda_handler.hpp"
+
+namespace mock {
+struct IsSetObs { bool track = false; };
+struct ObservationRef { int frame = 0, obs = 0; };
+struct Observation { double x = 0, y = 0; int track = -1; IsSetObs __isset; std::vector<ObservationRef> matches; };
+struct IsSetTrack { bool pt = false; };
+struct Track { std::vector<double> pt; bool valid = true; IsSetTrack __isset; std::vector<ObservationRef> obs; };
+struct Frame { std::vector<std::vector<double>> poses; std::vector<Observation> obs; };
+struct Session {
+  std::vector<double> cam;
+  int rs = 1;
+  std::vector<int> scanlines;
+  std::vector<Frame> frames;
+  std::map<int, Track> tracks;
+  Track& getTrack(int id) { return tracks.at(id); }
+};
+struct Options {
+  struct { bool use3Dpoints = true, calibrated = true, constVelocity = false, interpolateRotation = true; } model;
+  struct {
+    double huberLoss = 0, constFrameVelocity = 0, constFrameAcceleration = 0;
+    bool const3d = false, fixScale = false, fixRotation = false, fixPosition = false, useOnlyValidMatches = false;
+    unsigned fixFirstNCameras = 1;
+  } ceres;
+};
+}  // namespace mock
+
+static void rd(FILE* f, void* p, size_t n) {
+  if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); }
+}
+
+int main(int argc, char** argv) {
+  if (argc < 5) return 2;
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) return 2;
+  long hdr[4];  // frames, points, observations, shutter
+  rd(f, hdr, sizeof(hdr));
+  const long F = hdr[0], P = hdr[1], N = hdr[2];
+  mock::Session sess;
+  sess.rs = (int)hdr[3];
+  sess.cam.resize(9);
+  rd(f, sess.cam.data(), 9 * sizeof(double));
+  sess.scanlines.resize(2);
+  rd(f, sess.scanlines.data(), 2 * sizeof(int));
+  std::vector<double> poses(12 * F), points(3 * P), xy(2 * N);
+  std::vector<int> fr(N), pt(N);
+  rd(f, poses.data(), poses.size() * sizeof(double));
+  rd(f, points.data(), points.size() * sizeof(double));
+  rd(f, xy.data(), xy.size() * sizeof(double));
+  rd(f, fr.data(), N * sizeof(int));
+  rd(f, pt.data(), N * sizeof(int));
+  fclose(f);
+  sess.frames.resize(F);
+  for (long k = 0; k < F; ++k) {
+    sess.frames[k].poses.assign(2, std::vector<double>(6));
+    for (int c = 0; c < 6; ++c) {
+      sess.frames[k].poses[0][c] = poses[12 * k + c];
+      sess.frames[k].poses[1][c] = poses[12 * k + 6 + c];
+    }
+  }
+  for (long p = 0; p < P; ++p) {
+    mock::Track t;
+    t.pt.assign(points.begin() + 3 * p, points.begin() + 3 * p + 3);
+    t.__isset.pt = true;
+    sess.tracks[(int)p] = t;
+  }
+  for (long i = 0; i < N; ++i) {
+    mock::Observation o;
+    o.x = xy[2 * i];
+    o.y = xy[2 * i + 1];
+    o.track = pt[i];
+    o.__isset.track = true;
+    mock::ObservationRef ref;
+    ref.frame = fr[i];
+    ref.obs = (int)sess.frames[fr[i]].obs.size();
+    sess.tracks[pt[i]].obs.push_back(ref);
+    sess.frames[fr[i]].obs.push_back(o);
+  }
+  mock::Options opt;
+  opt.ceres.fixFirstNCameras = (unsigned)atoi(argv[3]);
+  const size_t startFrame = argc > 5 ? (size_t)atol(argv[5]) : 0;
+
+  rsba_solve_summary s;
+  try {
+    rsba_cuda::Handler<mock::Session, mock::Options> cs(opt, startFrame);
+    for (size_t fi = startFrame; fi < (size_t)F; ++fi) cs.Add(fi, sess);    // VideoSfMHandler.cc:586-590
+    rsba_solve_options o = rsba_cuda::Problem::DefaultOptions();
+    o.max_num_iterations = atoi(argv[4]);
+    s = cs.solve(&o);                                                        // VideoSfMHandler.cc:592
+  } catch (const std::exception& e) {
+    fprintf(stderr, "handler_check: %s\n", e.what());
+    return 1;
+  }
+  printf("usable %d iterations %d initial %.17g final %.17g blocks %ld: %s\n", s.usable, s.iterations, s.initial_cost,
+         s.final_cost, s.num_residual_blocks, s.message);
+  FILE* g = fopen(argv[2], "wb");
+  if (!g) return 2;
+  double head[4] = {(double)s.usable, (double)s.iterations, s.initial_cost, s.final_cost};
+  fwrite(head, sizeof(double), 4, g);
+  for (long k = 0; k < F; ++k) {
+    fwrite(sess.frames[k].poses[0].data(), sizeof(double), 6, g);
+    fwrite(sess.frames[k].poses[1].data(), sizeof(double), 6, g);
+  }
+  for (long p = 0; p < P; ++p) fwrite(sess.tracks[(int)p].pt.data(), sizeof(double), 3, g);
+  fclose(g);
+  return 0;
+}
