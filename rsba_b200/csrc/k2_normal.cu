@@ -27,34 +27,44 @@ constexpr int kPartial = 168;      // 144 (B) + 12 (gc) + 12 (wf)
 __device__ __forceinline__ int jc_off(int t, int row) { return ((t & 2) ? 12 : 0) + row * 6 + (t & 1) * 3; }
 
 // ---------------------------------------------------------------- points: C_p, g_p
-__global__ void __launch_bounds__(128)
+// One warp per point; lanes gather the observations in parallel, fixed-order butterfly sum.
+constexpr int kPointBlockWarps = 8;
+
+__global__ void __launch_bounds__(kPointBlockWarps * 32)
 point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
                     const double* __restrict__ jac, const double* __restrict__ res, int n_points,
                     double* __restrict__ C, double* __restrict__ gp) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * kPointBlockWarps + (threadIdx.x >> 5);
   if (p >= n_points) return;
-  double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, g0 = 0, g1 = 0, g2 = 0;
+  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // c0..c5, g0..g2
   const int beg = pt_ptr[p], end = pt_ptr[p + 1];
-  for (int e = beg; e < end; ++e) {
+  for (int e = beg + lane; e < end; e += 32) {
     const long i = pt_obs[e];
     const double2* jx = reinterpret_cast<const double2*>(jac + i * kJacDoubles + 24);
     const double2 q0 = jx[0], q1 = jx[1], q2 = jx[2];   // row0: q0.x q0.y q1.x ; row1: q1.y q2.x q2.y
     const double2 r = reinterpret_cast<const double2*>(res)[i];
     const double a0 = q0.x, a1 = q0.y, a2 = q1.x, b0 = q1.y, b1 = q2.x, b2 = q2.y;
-    c0 += a0 * a0 + b0 * b0;
-    c1 += a0 * a1 + b0 * b1;
-    c2 += a0 * a2 + b0 * b2;
-    c3 += a1 * a1 + b1 * b1;
-    c4 += a1 * a2 + b1 * b2;
-    c5 += a2 * a2 + b2 * b2;
-    g0 += a0 * r.x + b0 * r.y;
-    g1 += a1 * r.x + b1 * r.y;
-    g2 += a2 * r.x + b2 * r.y;
+    v[0] += a0 * a0 + b0 * b0;
+    v[1] += a0 * a1 + b0 * b1;
+    v[2] += a0 * a2 + b0 * b2;
+    v[3] += a1 * a1 + b1 * b1;
+    v[4] += a1 * a2 + b1 * b2;
+    v[5] += a2 * a2 + b2 * b2;
+    v[6] += a0 * r.x + b0 * r.y;
+    v[7] += a1 * r.x + b1 * r.y;
+    v[8] += a2 * r.x + b2 * r.y;
   }
-  double* Cp = C + 6L * p;
-  Cp[0] = c0; Cp[1] = c1; Cp[2] = c2; Cp[3] = c3; Cp[4] = c4; Cp[5] = c5;
-  double* g = gp + 3L * p;
-  g[0] = g0; g[1] = g1; g[2] = g2;
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+#pragma unroll
+  for (int k = 0; k < 9; ++k)                        // every lane holds the full sums
+    if (lane == k) {
+      if (k < 6) C[6L * p + k] = v[k];
+      else gp[3L * p + (k - 6)] = v[k];
+    }
 }
 
 __global__ void point_scale_kernel(int n_points, const double* __restrict__ C,
@@ -241,7 +251,8 @@ frame_reduce_kernel(SchurStructure st, NormalEq ne, int n_frames) {
 void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
                          int n_points, NormalEq ne, cudaStream_t s) {
   if (n_points <= 0) return;
-  point_blocks_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(st.pt_ptr, st.pt_obs, jac, res, n_points, ne.C, ne.gp);
+  point_blocks_kernel<<<(n_points + kPointBlockWarps - 1) / kPointBlockWarps, kPointBlockWarps * 32, 0, s>>>(
+      st.pt_ptr, st.pt_obs, jac, res, n_points, ne.C, ne.gp);
 }
 
 void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,

@@ -18,11 +18,18 @@
 // sm_100a.  This is the only place in the pipeline where tensor cores apply (dense GEMM).
 #include "lm.cuh"
 
+#include <algorithm>
+
 namespace rsba {
 namespace {
 
-constexpr int kLd = kTile + 1;      // potrf smem leading dimension (conflict-free columns)
-constexpr int kGemmLd = kTile + 4;  // GEMM smem leading dimension (conflict-free DMMA fragments)
+constexpr int kLd = kTile + 4;   // smem leading dimension: conflict-free DMMA fragment loads (ld % 16 == 4)
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
 // ---------------------------------------------------------------- clear structurally non-zero tiles
 __global__ void __launch_bounds__(256)
@@ -33,232 +40,290 @@ clear_tiles_kernel(double* __restrict__ S) {
   for (int e = threadIdx.x; e < kTile * kTile / 2; e += blockDim.x) base[e] = make_double2(0.0, 0.0);
 }
 
+// ---------------------------------------------------------------- small GEMMs on shared memory
+// C[m x n] = alpha * A[m x k] * op(B) (+ C), row-major smem operands with leading dimension kLd,
+// m, n multiples of 8, k a multiple of 4.  op(B) = B (k x n) or B^T (B stored n x k).  The 8x8
+// output blocks are dealt round-robin to warps wid, wid + nw, ...
+template <bool TRANS_B, bool ACCUMULATE>
+__device__ __forceinline__ void smem_gemm(double* C, const double* A, const double* B, int m, int n, int k,
+                                          double alpha, int wid, int nw, int lane) {
+  const int fr = lane >> 2, fc = lane & 3;
+  const int nbn = n >> 3;
+  for (int blk = wid; blk < (m >> 3) * nbn; blk += nw) {
+    const int bi = blk / nbn, bj = blk % nbn;
+    double c0 = 0.0, c1 = 0.0;
+    const double* ap = A + (8 * bi + fr) * kLd + fc;
+    const double* bp = TRANS_B ? B + (8 * bj + fr) * kLd + fc : B + fc * kLd + 8 * bj + fr;
+    for (int kk = 0; kk < k; kk += 4) dmma(c0, c1, ap[kk], TRANS_B ? bp[kk] : bp[kk * kLd]);
+    double* cp = C + (8 * bi + fr) * kLd + 8 * bj + 2 * fc;
+    if (ACCUMULATE) { cp[0] += alpha * c0; cp[1] += alpha * c1; }
+    else            { cp[0] = alpha * c0;  cp[1] = alpha * c1; }
+  }
+}
+
 // ---------------------------------------------------------------- diagonal tile: Cholesky + inverse
+// One CTA (8 warps) per panel of the level.  Right-looking, 8-column blocks:
+//   (i)   the 8x8 diagonal block is factorised by warp 0 in registers (one row per lane, shuffles)
+//   (ii)  the rows below solve against it (one thread per row, reciprocal pivots)
+//   (iii) the trailing lower triangle is updated with DMMA (K = 8)
+// then L^-1 by recursive doubling (8 -> 16 -> 32 -> 96; every level is a pair of small DMMA GEMMs),
+// so that trsm and the triangular solves are GEMM / GEMV and not substitution chains.
+constexpr size_t kPotrfSmem = (size_t)(2 * kTile * kLd + 3 * 32 * kLd + kTile) * sizeof(double);
+
 __global__ void __launch_bounds__(256)
 potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int T,
                  const int* __restrict__ panels, double* __restrict__ Dinv, int* __restrict__ info) {
   const int k = panels[blockIdx.x];
-  constexpr long ld = kTile;
-  extern __shared__ double smem[];
-  double* A = smem;                 // [96][97]  factor
-  double* Li = smem + kTile * kLd;  // [96][97]  inverse
-  double* Tm = Li + kTile * kLd;    // [8][96]
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) double smem[];
+  double* A = smem;                      // [96][kLd]  factor (lower)
+  double* X = A + kTile * kLd;           // [96][kLd]  inverse (lower)
+  double* W = X + kTile * kLd;           // [3][32][kLd] products of the inverse
+  double* rdiag = W + 3 * 32 * kLd;      // [96] reciprocal pivots
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* g = S + (long)tile_slot[k * T + k] * kTile * kTile;
-  for (int e = tid; e < kTile * kTile; e += blockDim.x) {
-    const int r = e / kTile, c = e % kTile;
-    A[r * kLd + c] = (c <= r) ? g[(long)r * ld + c] : 0.0;
-    Li[r * kLd + c] = 0.0;
+  for (int e = tid; e < kTile * kTile / 2; e += blockDim.x) {
+    const int r = e / (kTile / 2), c = 2 * (e % (kTile / 2));
+    const double2 v = reinterpret_cast<const double2*>(g)[e];
+    A[r * kLd + c] = (c <= r) ? v.x : 0.0;
+    A[r * kLd + c + 1] = (c + 1 <= r) ? v.y : 0.0;
+    X[r * kLd + c] = 0.0;
+    X[r * kLd + c + 1] = 0.0;
   }
   __syncthreads();
 
   for (int I = 0; I < kTile / 8; ++I) {
     const int o = 8 * I;
-    // (i) 8x8 diagonal block, unblocked, by the first 8 lanes of warp 0
-    if (tid < 32) {
+    // ---- (i) 8x8 diagonal block in registers: lane l < 8 owns row l
+    if (warp == 0) {
+      const int l = lane & 7;
+      double a[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = A[(o + l) * kLd + o + c];
+#pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (tid == j) {
-          const double d = A[(o + j) * kLd + o + j];
-          if (!(d > 0.0)) atomicExch(info, k * kTile + o + j + 1);
-          A[(o + j) * kLd + o + j] = sqrt(d);
-        }
-        __syncwarp();
-        if (tid < 8 && tid > j) A[(o + tid) * kLd + o + j] /= A[(o + j) * kLd + o + j];
-        __syncwarp();
-        if (tid < 8 && tid > j) {
-          const double l = A[(o + tid) * kLd + o + j];
-          for (int c = j + 1; c <= tid; ++c) A[(o + tid) * kLd + o + c] -= l * A[(o + c) * kLd + o + j];
-        }
-        __syncwarp();
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (lane == 0 && !(d > 0.0)) atomicExch(info, k * kTile + o + j + 1);
+        const double rs = 1.0 / sqrt(d);
+        const double lj = (l == j) ? d * rs : a[j] * rs;   // column j of L (rows >= j are meaningful)
+        a[j] = lj;
+        if (lane == 0) rdiag[o + j] = rs;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) a[c] -= lj * __shfl_sync(0xffffffffu, lj, c);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c <= l) A[(o + l) * kLd + o + c] = a[c];
       }
     }
     __syncthreads();
-    // (ii) rows below the block: forward substitution against the 8x8 factor, one thread per row
-    {
-      const int r = o + 8 + tid;
-      if (r < kTile) {
-        double x[8];
+    // ---- (ii) rows below: x L8^T = a, one thread per row
+    const int nrem = kTile - o - 8;
+    if (tid < nrem) {
+      double* row = A + (o + 8 + tid) * kLd + o;
+      double x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          double s = A[r * kLd + o + j];
+      for (int j = 0; j < 8; ++j) {
+        double sacc = row[j];
 #pragma unroll
-          for (int m = 0; m < j; ++m) s -= x[m] * A[(o + j) * kLd + o + m];
-          x[j] = s / A[(o + j) * kLd + o + j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) A[r * kLd + o + j] = x[j];
+        for (int m = 0; m < j; ++m) sacc -= x[m] * A[(o + j) * kLd + o + m];
+        x[j] = sacc * rdiag[o + j];
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) row[j] = x[j];
     }
     __syncthreads();
-    // (iii) trailing lower triangle  A[i][c] -= sum_m P[i][m] P[c][m]
+    // ---- (iii) trailing lower block triangle: A22 -= P P^T  (K = 8), DMMA
     {
-      const int t = kTile - o - 8;
-      for (int e = tid; e < t * t; e += blockDim.x) {
-        const int i = e / t, c = e % t;
-        if (c > i) continue;
-        const double* pi = A + (o + 8 + i) * kLd + o;
-        const double* pc = A + (o + 8 + c) * kLd + o;
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) s += pi[m] * pc[m];
-        A[(o + 8 + i) * kLd + o + 8 + c] -= s;
+      const int nb = nrem >> 3, fr = lane >> 2, fc = lane & 3;
+      const double* Pm = A + (o + 8) * kLd + o;
+      double* C22 = A + (o + 8) * kLd + o + 8;
+      int bi = 0, bj = 0;
+      // warp-strided walk over the lower block triangle (bi >= bj), row-major linear order
+      for (int blk = 0, mine = warp; bi < nb; ++blk) {
+        if (blk == mine) {
+          double c0 = 0.0, c1 = 0.0;
+          const double* ap = Pm + (8 * bi + fr) * kLd + fc;
+          const double* bp = Pm + (8 * bj + fr) * kLd + fc;
+          dmma(c0, c1, ap[0], bp[0]);
+          dmma(c0, c1, ap[4], bp[4]);
+          double* cp = C22 + (8 * bi + fr) * kLd + 8 * bj + 2 * fc;
+          cp[0] -= c0;
+          cp[1] -= c1;
+          mine += 8;
+        }
+        if (++bj > bi) { bj = 0; ++bi; }
       }
     }
     __syncthreads();
   }
 
-  // ---- inverse of the lower-triangular factor, 8x8-blocked
+  // ---- inverse, level 0: the twelve 8x8 diagonal blocks (thread = (block, column))
   if (tid < kTile) {
-    const int o = (tid / 8) * 8, cc = tid % 8;
+    const int o = (tid >> 3) * 8, cc = tid & 7;
     double x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      double s = (i == cc) ? 1.0 : 0.0;
+      double sacc = (i == cc) ? 1.0 : 0.0;
 #pragma unroll
       for (int m = 0; m < i; ++m)
-        if (m >= cc) s -= A[(o + i) * kLd + o + m] * x[m];
-      x[i] = (i >= cc) ? s / A[(o + i) * kLd + o + i] : 0.0;
+        if (m >= cc) sacc -= A[(o + i) * kLd + o + m] * x[m];
+      x[i] = (i >= cc) ? sacc * rdiag[o + i] : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) Li[(o + i) * kLd + o + cc] = x[i];
+    for (int i = 0; i < 8; ++i) X[(o + i) * kLd + o + cc] = x[i];
   }
   __syncthreads();
-  for (int I = 1; I < kTile / 8; ++I) {
-    const int o = 8 * I;
-    // T = L[I][0..I) * Li[0..I)[0..I)  (8 x 8I)
-    for (int e = tid; e < 8 * o; e += blockDim.x) {
-      const int r = e / o, gc = e % o;
-      double s = 0.0;
-      for (int m = (gc / 8) * 8; m < o; ++m) s += A[(o + r) * kLd + m] * Li[m * kLd + gc];
-      Tm[r * kTile + gc] = s;
+  // ---- level 1 (8 -> 16) and level 2 (16 -> 32):  X_ba = -X_b (L_ba X_a)
+#pragma unroll 1
+  for (int h = 8; h <= 16; h *= 2) {
+    const int npair = kTile / (2 * h);              // 6 pairs of 8-blocks, then 3 pairs of 16-blocks
+    const int wpp = (h == 8) ? 1 : 2;               // warps per pair
+    if (warp < npair * wpp) {
+      const int pr = warp / wpp, o = pr * 2 * h;
+      smem_gemm<false, false>(W + pr * 16 * kLd, A + (o + h) * kLd + o, X + o * kLd + o, h, h, h, 1.0,
+                              warp % wpp, wpp, lane);
     }
     __syncthreads();
-    for (int e = tid; e < 8 * o; e += blockDim.x) {
-      const int r = e / o, gc = e % o;
-      double s = 0.0;
-      for (int q = 0; q <= r; ++q) s += Li[(o + r) * kLd + o + q] * Tm[q * kTile + gc];
-      Li[(o + r) * kLd + gc] = -s;
+    if (warp < npair * wpp) {
+      const int pr = warp / wpp, o = pr * 2 * h;
+      smem_gemm<false, false>(X + (o + h) * kLd + o, X + (o + h) * kLd + o + h, W + pr * 16 * kLd, h, h, h, -1.0,
+                              warp % wpp, wpp, lane);
     }
+    __syncthreads();
+  }
+  // ---- level 3 (32 -> 96): X21 = -X2 (L21 X1), X32 = -X3 (L32 X2), X31 = -X3 (L31 X1 + L32 X21)
+  {
+    double* T21 = W;
+    double* T32 = W + 32 * kLd;
+    double* T31 = W + 64 * kLd;
+    const int half = warp >> 2, wq = warp & 3;      // warps 0-3 / 4-7 work on different products
+    if (half == 0) smem_gemm<false, false>(T21, A + 32 * kLd, X, 32, 32, 32, 1.0, wq, 4, lane);
+    else           smem_gemm<false, false>(T32, A + 64 * kLd + 32, X + 32 * kLd + 32, 32, 32, 32, 1.0, wq, 4, lane);
+    __syncthreads();
+    if (half == 0) smem_gemm<false, false>(X + 32 * kLd, X + 32 * kLd + 32, T21, 32, 32, 32, -1.0, wq, 4, lane);
+    else           smem_gemm<false, false>(X + 64 * kLd + 32, X + 64 * kLd + 64, T32, 32, 32, 32, -1.0, wq, 4, lane);
+    __syncthreads();
+    smem_gemm<false, false>(T31, A + 64 * kLd, X, 32, 32, 32, 1.0, warp, 8, lane);
+    __syncthreads();
+    smem_gemm<false, true>(T31, A + 64 * kLd + 32, X + 32 * kLd, 32, 32, 32, 1.0, warp, 8, lane);
+    __syncthreads();
+    smem_gemm<false, false>(X + 64 * kLd, X + 64 * kLd + 64, T31, 32, 32, 32, -1.0, warp, 8, lane);
     __syncthreads();
   }
 
   double* di = Dinv + (long)k * kTile * kTile;
-  for (int e = tid; e < kTile * kTile; e += blockDim.x) {
-    const int r = e / kTile, c = e % kTile;
-    if (c <= r) g[(long)r * ld + c] = A[r * kLd + c];
-    di[e] = Li[r * kLd + c];
+  for (int e = tid; e < kTile * kTile / 2; e += blockDim.x) {
+    const int r = e / (kTile / 2), c = 2 * (e % (kTile / 2));
+    reinterpret_cast<double2*>(g)[e] = make_double2(c <= r ? A[r * kLd + c] : 0.0, c + 1 <= r ? A[r * kLd + c + 1] : 0.0);
+    reinterpret_cast<double2*>(di)[e] = make_double2(X[r * kLd + c], X[r * kLd + c + 1]);
   }
 }
 
-// ---------------------------------------------------------------- tile GEMM  C (-)= A B^T  on DMMA
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
+// ---------------------------------------------------------------- tile GEMMs  C (-)= A B^T  on DMMA
+// Both kernels split one 96x96 output tile over 4 CTAs (blockIdx.y), so that a level with few tiles
+// still spreads over many SMs; 4 warps per CTA, each a 24x24 patch (3x3 DMMA tiles), K = 96.
+//   trsm   : S(i,k) = S(i,k) * Dinv[k]^T  in place; CTA = 24 rows (it reads and writes only its own rows)
+//   update : S(i,j) -= S(i,k) * S(j,k)^T; CTA = 48x48 quadrant
+constexpr int kQ = kTile / 2;
+constexpr int kTrsmRows = kTile / 4;
+constexpr size_t kUpdateSmem = (size_t)(2 * kQ * kLd) * sizeof(double);
+constexpr size_t kTrsmSmem = (size_t)((kTrsmRows + kTile) * kLd) * sizeof(double);
 
-__device__ __forceinline__ void load_tile(double* dst, const double* __restrict__ src, long ld) {
-  // 96x96 doubles, rows of 48 double2
-  for (int e = threadIdx.x; e < kTile * (kTile / 2); e += blockDim.x) {
+__device__ __forceinline__ void load_rows(double* dst, const double* __restrict__ src, int rows) {
+  // rows x 96 doubles, rows of 48 double2
+  for (int e = threadIdx.x; e < rows * (kTile / 2); e += blockDim.x) {
     const int r = e / (kTile / 2), c2 = e % (kTile / 2);
-    const double2 v = reinterpret_cast<const double2*>(src + (long)r * ld)[c2];
-    dst[r * kGemmLd + 2 * c2] = v.x;
-    dst[r * kGemmLd + 2 * c2 + 1] = v.y;
+    const double2 v = reinterpret_cast<const double2*>(src + (long)r * kTile)[c2];
+    dst[r * kLd + 2 * c2] = v.x;
+    dst[r * kLd + 2 * c2 + 1] = v.y;
   }
 }
 
-// MODE 0 (trsm):   S(i,k) = S(i,k) * Dinv[k]^T           one CTA per (i,k) of the level's trsm list
-// MODE 1 (update): S(i,j) -= S(i,k) * S(j,k)^T           one CTA per (i,j,k) of the update group
-template <int MODE>
-__global__ void __launch_bounds__(256)
-tile_gemm_kernel(double* S, const int* __restrict__ tile_slot, int T, const int2* __restrict__ trsm,
-                 const int4* __restrict__ upd, const double* __restrict__ Dinv) {
-  constexpr long ld = kTile;
-  extern __shared__ double smem[];
-  double* As = smem;
-  double* Bs = smem + kTile * kGemmLd;
-  int ti, tj, k;
-  const double* Bsrc;
-  if (MODE == 0) {
-    const int2 p = trsm[blockIdx.x];
-    ti = p.x;
-    tj = k = p.y;
-    Bsrc = Dinv + (long)k * kTile * kTile;
-  } else {
-    const int4 p = upd[blockIdx.x];
-    ti = p.x;
-    tj = p.y;
-    k = p.z;
-    Bsrc = S + (long)tile_slot[tj * T + k] * kTile * kTile;
-  }
-  const double* Asrc = S + (long)tile_slot[ti * T + k] * kTile * kTile;
-  load_tile(As, Asrc, ld);
-  load_tile(Bs, Bsrc, ld);
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = (warp >> 2) * 48, n0 = (warp & 3) * 24;
+// acc[3][3][2] += As[m0.., :] * Bs[n0.., :]^T over K = 96
+__device__ __forceinline__ void warp_gemm_24x24(const double* As, const double* Bs, int m0, int n0, int lane,
+                                                double (&acc)[3][3][2]) {
   const int fr = lane >> 2, fc = lane & 3;
-  double acc[6][3][2];
 #pragma unroll
-  for (int mi = 0; mi < 6; ++mi)
+  for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 #pragma unroll 4
   for (int k0 = 0; k0 < kTile; k0 += 4) {
-    double a[6], b[3];
+    double a[3], b[3];
 #pragma unroll
-    for (int mi = 0; mi < 6; ++mi) a[mi] = As[(m0 + 8 * mi + fr) * kGemmLd + k0 + fc];
+    for (int mi = 0; mi < 3; ++mi) a[mi] = As[(m0 + 8 * mi + fr) * kLd + k0 + fc];
 #pragma unroll
-    for (int ni = 0; ni < 3; ++ni) b[ni] = Bs[(n0 + 8 * ni + fr) * kGemmLd + k0 + fc];
+    for (int ni = 0; ni < 3; ++ni) b[ni] = Bs[(n0 + 8 * ni + fr) * kLd + k0 + fc];
 #pragma unroll
-    for (int mi = 0; mi < 6; ++mi)
+    for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 3; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
   }
-  double* Cg = S + (long)tile_slot[ti * T + tj] * kTile * kTile;
+}
+
+__global__ void __launch_bounds__(128)
+tile_trsm_kernel(double* S, const int* __restrict__ tile_slot, int T, const int2* __restrict__ trsm,
+                 const double* __restrict__ Dinv) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;                       // [24][kLd]  this CTA's rows of S(i,k)
+  double* Bs = smem + kTrsmRows * kLd;     // [96][kLd]  Dinv[k]
+  const int2 p = trsm[blockIdx.x];
+  double* tile = S + (long)tile_slot[p.x * T + p.y] * kTile * kTile + (long)blockIdx.y * kTrsmRows * kTile;
+  load_rows(As, tile, kTrsmRows);
+  load_rows(Bs, Dinv + (long)p.y * kTile * kTile, kTile);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fr = lane >> 2, fc = lane & 3, n0 = warp * 24;
+  double acc[3][3][2];
+  warp_gemm_24x24(As, Bs, 0, n0, lane, acc);
 #pragma unroll
-  for (int mi = 0; mi < 6; ++mi)
+  for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 3; ++ni)
+      *reinterpret_cast<double2*>(tile + (long)(8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc) =
+          make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+}
+
+__global__ void __launch_bounds__(128)
+tile_update_kernel(double* S, const int* __restrict__ tile_slot, int T, const int4* __restrict__ upd) {
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + kQ * kLd;
+  const int4 p = upd[blockIdx.x];
+  const int ti = p.x, tj = p.y, k = p.z;
+  const int qi = blockIdx.y >> 1, qj = blockIdx.y & 1;
+  if (ti == tj && qj > qi) return;   // diagonal target: the factorisation reads the lower part only
+  load_rows(As, S + (long)tile_slot[ti * T + k] * kTile * kTile + (long)qi * kQ * kTile, kQ);
+  load_rows(Bs, S + (long)tile_slot[tj * T + k] * kTile * kTile + (long)qj * kQ * kTile, kQ);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (warp >> 1) * 24, n0 = (warp & 1) * 24;
+  const int fr = lane >> 2, fc = lane & 3;
+  double acc[3][3][2];
+  warp_gemm_24x24(As, Bs, m0, n0, lane, acc);
+  double* Cg = S + (long)tile_slot[ti * T + tj] * kTile * kTile + (long)qi * kQ * kTile + qj * kQ;
+#pragma unroll
+  for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 3; ++ni) {
-      double2* dst = reinterpret_cast<double2*>(Cg + (long)(m0 + 8 * mi + fr) * ld + n0 + 8 * ni + 2 * fc);
-      if (MODE == 0) {
-        *dst = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
-      } else {
-        double2 v = *dst;
-        v.x -= acc[mi][ni][0];
-        v.y -= acc[mi][ni][1];
-        *dst = v;
-      }
+      double2* dst = reinterpret_cast<double2*>(Cg + (long)(m0 + 8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc);
+      double2 v = *dst;
+      v.x -= acc[mi][ni][0];
+      v.y -= acc[mi][ni][1];
+      *dst = v;
     }
 }
 
-// ---------------------------------------------------------------- triangular solves, one launch per level
-// x holds the right-hand side on entry and the solution of (L L^T) x = b on exit.
-// forward:  z_k = Linv_kk (b_k - sum_{j<k} L_kj z_j)      every j sits in a lower level
-__global__ void __launch_bounds__(256)
-solve_forward_kernel(const double* __restrict__ S, TileSchedule ts, const int* __restrict__ panels,
-                     double* __restrict__ x) {
-  constexpr long ld = kTile;
-  __shared__ double tmp[kTile];
-  const int k = panels[blockIdx.x];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = ts.n_tiles;
-  for (int r = warp; r < kTile; r += 8) {
-    double s = 0.0;
-    for (int q = ts.lrow_ptr[k]; q < ts.lrow_ptr[k + 1]; ++q) {
-      const int j = ts.lrow_cols[q];
-      const double* lj = S + (long)ts.tile_slot[k * T + j] * kTile * kTile + (long)r * ld;
-      const double* xj = x + (long)j * kTile;
-#pragma unroll
-      for (int c = 0; c < kTile; c += 32) s += lj[c + lane] * xj[c + lane];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) tmp[r] = x[(long)k * kTile + r] - s;
-  }
-  __syncthreads();
-  const double* di = ts.Dinv + (long)k * kTile * kTile;
+// ---------------------------------------------------------------- triangular solves, level by level
+// x holds the right-hand side on entry and the solution of (L L^T) x = b on exit.  The tile row /
+// column of a separator panel can hold dozens of tiles, so the matrix-vector products of one
+// panel are split over `split` CTAs (blockIdx.y) that write partial sums; a finish kernel adds
+// them in a fixed order and applies the inverse of the diagonal factor.  split == 1 fuses both.
+constexpr int kMaxSolveSplit = 16;
+
+__device__ __forceinline__ void apply_dinv_forward(const double* __restrict__ di, const double* tmp,
+                                                   double* __restrict__ xk, int warp, int lane) {
   for (int r = warp; r < kTile; r += 8) {
     double s = 0.0;
 #pragma unroll
@@ -266,41 +331,13 @@ solve_forward_kernel(const double* __restrict__ S, TileSchedule ts, const int* _
       if (c + lane <= r) s += di[r * kTile + c + lane] * tmp[c + lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) x[(long)k * kTile + r] = s;
+    if (lane == 0) xk[r] = s;
   }
 }
 
-// backward: y_k = Linv_kk^T (z_k - sum_{i>k} L_ik^T y_i)   every i sits in a higher level
-__global__ void __launch_bounds__(256)
-solve_backward_kernel(const double* __restrict__ S, TileSchedule ts, const int* __restrict__ panels,
-                      double* __restrict__ x) {
-  constexpr long ld = kTile;
-  __shared__ double tmp[kTile];
-  __shared__ double part[8][kTile + 1];
-  const int k = panels[blockIdx.x];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = ts.n_tiles;
-  // thread (g = warp, r = lane + 32 m): partial over tile rows c = g, g+8, ... of every L_ik
-  for (int m = 0; m < 3; ++m) {
-    const int r = lane + 32 * m;
-    double s = 0.0;
-    for (int q = ts.row_ptr[k]; q < ts.row_ptr[k + 1]; ++q) {
-      const int i = ts.rows[q];
-      const double* lik = S + (long)ts.tile_slot[i * T + k] * kTile * kTile;
-      const double* yi = x + (long)i * kTile;
-      for (int c = warp; c < kTile; c += 8) s += lik[(long)c * ld + r] * yi[c];
-    }
-    part[warp][r] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x < kTile) {
-    double s = 0.0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
-    tmp[threadIdx.x] = x[(long)k * kTile + threadIdx.x] - s;
-  }
-  __syncthreads();
-  const double* di = ts.Dinv + (long)k * kTile * kTile;
+__device__ __forceinline__ void apply_dinv_backward(const double* __restrict__ di, const double* tmp,
+                                                    double (*part)[kTile + 1], double* __restrict__ xk,
+                                                    int warp, int lane) {
   for (int m = 0; m < 3; ++m) {
     const int r = lane + 32 * m;
     double s = 0.0;
@@ -313,8 +350,126 @@ solve_backward_kernel(const double* __restrict__ S, TileSchedule ts, const int* 
     double s = 0.0;
 #pragma unroll
     for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
-    x[(long)k * kTile + threadIdx.x] = s;
+    xk[threadIdx.x] = s;
   }
+}
+
+// forward:  z_k = Linv_kk (b_k - sum_{j<k} L_kj z_j)      every j sits in a lower level
+__global__ void __launch_bounds__(256)
+solve_forward_kernel(const double* __restrict__ S, TileSchedule ts, const int* __restrict__ panels,
+                     double* __restrict__ x, int split, double* __restrict__ partials) {
+  constexpr long ld = kTile;
+  __shared__ double tmp[kTile];
+  const int k = panels[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = ts.n_tiles;
+  // warp w owns rows w, w+8, ..., w+88; lane covers columns lane, lane+32, lane+64
+  double acc[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) acc[t] = 0.0;
+  for (int q = ts.lrow_ptr[k] + blockIdx.y; q < ts.lrow_ptr[k + 1]; q += split) {
+    const int j = ts.lrow_cols[q];
+    const double* lj = S + (long)ts.tile_slot[k * T + j] * kTile * kTile;
+    const double* xj = x + (long)j * kTile;
+    const double x0 = xj[lane], x1 = xj[lane + 32], x2 = xj[lane + 64];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      const double* row = lj + (long)(warp + 8 * t) * ld;
+      acc[t] += row[lane] * x0 + row[lane + 32] * x1 + row[lane + 64] * x2;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 12; ++t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+  }
+  if (split > 1) {
+    double* out = partials + ((long)k * kMaxSolveSplit + blockIdx.y) * kTile;
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) out[warp + 8 * t] = acc[t];
+    }
+    return;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) tmp[warp + 8 * t] = x[(long)k * kTile + warp + 8 * t] - acc[t];
+  }
+  __syncthreads();
+  apply_dinv_forward(ts.Dinv + (long)k * kTile * kTile, tmp, x + (long)k * kTile, warp, lane);
+}
+
+__global__ void __launch_bounds__(256)
+solve_forward_finish_kernel(TileSchedule ts, const int* __restrict__ panels, double* __restrict__ x, int split,
+                            const double* __restrict__ partials) {
+  __shared__ double tmp[kTile];
+  const int k = panels[blockIdx.x];
+  if (threadIdx.x < kTile) {
+    double s = 0.0;
+    for (int g = 0; g < split; ++g) s += partials[((long)k * kMaxSolveSplit + g) * kTile + threadIdx.x];
+    tmp[threadIdx.x] = x[(long)k * kTile + threadIdx.x] - s;
+  }
+  __syncthreads();
+  apply_dinv_forward(ts.Dinv + (long)k * kTile * kTile, tmp, x + (long)k * kTile, threadIdx.x >> 5, threadIdx.x & 31);
+}
+
+// backward: y_k = Linv_kk^T (z_k - sum_{i>k} L_ik^T y_i)   every i sits in a higher level
+__global__ void __launch_bounds__(256)
+solve_backward_kernel(const double* __restrict__ S, TileSchedule ts, const int* __restrict__ panels,
+                      double* __restrict__ x, int split, double* __restrict__ partials) {
+  constexpr long ld = kTile;
+  __shared__ double tmp[kTile];
+  __shared__ double part[8][kTile + 1];
+  const int k = panels[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = ts.n_tiles;
+  // thread (g = warp, r = lane + 32 m): partial over tile rows c = g, g+8, ... of every L_ik
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int q = ts.row_ptr[k] + blockIdx.y; q < ts.row_ptr[k + 1]; q += split) {
+    const int i = ts.rows[q];
+    const double* lik = S + (long)ts.tile_slot[i * T + k] * kTile * kTile;
+    const double* yi = x + (long)i * kTile;
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      const int c = warp + 8 * t;
+      const double y = yi[c];
+      const double* row = lik + (long)c * ld;
+      acc[0] += row[lane] * y;
+      acc[1] += row[lane + 32] * y;
+      acc[2] += row[lane + 64] * y;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 3; ++m) part[warp][lane + 32 * m] = acc[m];
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x < kTile) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
+  }
+  if (split > 1) {
+    if (threadIdx.x < kTile) partials[((long)k * kMaxSolveSplit + blockIdx.y) * kTile + threadIdx.x] = s;
+    return;
+  }
+  if (threadIdx.x < kTile) tmp[threadIdx.x] = x[(long)k * kTile + threadIdx.x] - s;
+  __syncthreads();
+  apply_dinv_backward(ts.Dinv + (long)k * kTile * kTile, tmp, part, x + (long)k * kTile, warp, lane);
+}
+
+__global__ void __launch_bounds__(256)
+solve_backward_finish_kernel(TileSchedule ts, const int* __restrict__ panels, double* __restrict__ x, int split,
+                             const double* __restrict__ partials) {
+  __shared__ double tmp[kTile];
+  __shared__ double part[8][kTile + 1];
+  const int k = panels[blockIdx.x];
+  if (threadIdx.x < kTile) {
+    double s = 0.0;
+    for (int g = 0; g < split; ++g) s += partials[((long)k * kMaxSolveSplit + g) * kTile + threadIdx.x];
+    tmp[threadIdx.x] = x[(long)k * kTile + threadIdx.x] - s;
+  }
+  __syncthreads();
+  apply_dinv_backward(ts.Dinv + (long)k * kTile * kTile, tmp, part, x + (long)k * kTile, threadIdx.x >> 5,
+                      threadIdx.x & 31);
 }
 
 }  // namespace
@@ -325,28 +480,26 @@ void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s) {
 
 int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s) {
   static bool attr_done = false;
-  const size_t potrf_smem = (size_t)(2 * kTile * kLd + 8 * kTile) * sizeof(double);
-  const size_t gemm_smem = (size_t)(2 * kTile * kGemmLd) * sizeof(double);
   if (!attr_done) {
-    cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)potrf_smem);
-    cudaFuncSetAttribute(tile_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
-    cudaFuncSetAttribute(tile_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+    cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem);
+    cudaFuncSetAttribute(tile_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem);
+    cudaFuncSetAttribute(tile_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem);
     attr_done = true;
   }
   int launches = 0;
   for (int l = 0; l < plan.n_levels; ++l) {
     const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
-    potrf_inv_kernel<<<np, 256, potrf_smem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.panels + plan.panel_ptr[l], ts.Dinv, info);
+    potrf_inv_kernel<<<np, 256, kPotrfSmem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.panels + plan.panel_ptr[l], ts.Dinv, info);
     ++launches;
     const int nt = plan.trsm_ptr[l + 1] - plan.trsm_ptr[l];
     if (nt > 0) {
-      tile_gemm_kernel<0><<<nt, 256, gemm_smem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.trsm + plan.trsm_ptr[l], nullptr, ts.Dinv);
+      tile_trsm_kernel<<<dim3(nt, 4), 128, kTrsmSmem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.trsm + plan.trsm_ptr[l], ts.Dinv);
       ++launches;
     }
     for (int g = plan.level_group_ptr[l]; g < plan.level_group_ptr[l + 1]; ++g) {
       const long nu = plan.group_ptr[g + 1] - plan.group_ptr[g];
       if (nu <= 0) continue;
-      tile_gemm_kernel<1><<<(unsigned)nu, 256, gemm_smem, s>>>(S, ts.tile_slot, ts.n_tiles, nullptr, ts.upd + plan.group_ptr[g], nullptr);
+      tile_update_kernel<<<dim3((unsigned)nu, 4), 128, kUpdateSmem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.upd + plan.group_ptr[g]);
       ++launches;
     }
   }
@@ -355,15 +508,32 @@ int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan
 
 int launch_tile_solve(const double* S, const TileSchedule& ts, const TilePlan& plan, double* x, cudaStream_t s) {
   int launches = 0;
+  auto split_of = [](int most) { return most <= 4 ? 1 : std::min(kMaxSolveSplit, (most + 2) / 3); };
   for (int l = 0; l < plan.n_levels; ++l) {
     const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
-    solve_forward_kernel<<<np, 256, 0, s>>>(S, ts, ts.panels + plan.panel_ptr[l], x);
+    int most = 0;
+    for (int q = plan.panel_ptr[l]; q < plan.panel_ptr[l + 1]; ++q)
+      most = std::max(most, plan.lrow_ptr[plan.panels[q] + 1] - plan.lrow_ptr[plan.panels[q]]);
+    const int split = split_of(most);
+    solve_forward_kernel<<<dim3(np, split), 256, 0, s>>>(S, ts, ts.panels + plan.panel_ptr[l], x, split, ts.solve_partials);
     ++launches;
+    if (split > 1) {
+      solve_forward_finish_kernel<<<np, 256, 0, s>>>(ts, ts.panels + plan.panel_ptr[l], x, split, ts.solve_partials);
+      ++launches;
+    }
   }
   for (int l = plan.n_levels - 1; l >= 0; --l) {
     const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
-    solve_backward_kernel<<<np, 256, 0, s>>>(S, ts, ts.panels + plan.panel_ptr[l], x);
+    int most = 0;
+    for (int q = plan.panel_ptr[l]; q < plan.panel_ptr[l + 1]; ++q)
+      most = std::max(most, plan.row_ptr[plan.panels[q] + 1] - plan.row_ptr[plan.panels[q]]);
+    const int split = split_of(most);
+    solve_backward_kernel<<<dim3(np, split), 256, 0, s>>>(S, ts, ts.panels + plan.panel_ptr[l], x, split, ts.solve_partials);
     ++launches;
+    if (split > 1) {
+      solve_backward_finish_kernel<<<np, 256, 0, s>>>(ts, ts.panels + plan.panel_ptr[l], x, split, ts.solve_partials);
+      ++launches;
+    }
   }
   return launches;
 }

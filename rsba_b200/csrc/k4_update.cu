@@ -64,17 +64,22 @@ frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* _
 }
 
 // points: back-substitution, trial points, per-CTA partial scalars -> scratch[3 + 3*block ...]
-__global__ void __launch_bounds__(128)
+// One WARP per point: the lanes gather the point's observations in parallel (a serial loop of
+// dependent 240-byte gathers per thread ran at 1 TB/s), then a fixed-order butterfly sums them.
+constexpr int kPointStepWarps = 8;
+
+__global__ void __launch_bounds__(kPointStepWarps * 32)
 point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne,
                   const double* __restrict__ delta_c, int n_points, const double* __restrict__ points,
                   double* __restrict__ delta_p, double* __restrict__ trial, double* __restrict__ scratch) {
   __shared__ double sh[32];
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * kPointStepWarps + warp;
   double gd = 0.0, dd = 0.0, nn = 0.0;
   if (p < n_points) {
-    const double* g = ne.gp + 3L * p;
-    double a0 = g[0], a1 = g[1], a2 = g[2];
-    for (int e = st.pt_ptr[p]; e < st.pt_ptr[p + 1]; ++e) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    const int beg = st.pt_ptr[p], end = st.pt_ptr[p + 1];
+    for (int e = beg + lane; e < end; e += 32) {
       const long i = st.pt_obs[e];
       const double2* J = reinterpret_cast<const double2*>(jac + i * kJacDoubles);
       const double2* dc = reinterpret_cast<const double2*>(delta_c + 12L * obs.frame[i]);
@@ -93,20 +98,30 @@ point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
       a1 += x0.y * m0 + x2.x * m1;
       a2 += x1.x * m0 + x2.y * m1;
     }
-    const double* Ci = ne.Cinv + 6L * p;
-    const double d0 = -(Ci[0] * a0 + Ci[1] * a1 + Ci[2] * a2);
-    const double d1 = -(Ci[1] * a0 + Ci[3] * a1 + Ci[4] * a2);
-    const double d2 = -(Ci[2] * a0 + Ci[4] * a1 + Ci[5] * a2);
-    delta_p[3L * p] = d0; delta_p[3L * p + 1] = d1; delta_p[3L * p + 2] = d2;
-    trial[3L * p] = points[3L * p] + d0;
-    trial[3L * p + 1] = points[3L * p + 1] + d1;
-    trial[3L * p + 2] = points[3L * p + 2] + d2;
-    gd = g[0] * d0 + g[1] * d1 + g[2] * d2;
-    nn = d0 * d0 + d1 * d1 + d2 * d2;
-    const double* sp = ne.scale_p + 3L * p;
-    const double* e2 = ne.d2_p + 3L * p;
-    const double u0 = d0 / sp[0], u1 = d1 / sp[1], u2 = d2 / sp[2];
-    dd = e2[0] * u0 * u0 + e2[1] * u1 * u1 + e2[2] * u2 * u2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+      const double* g = ne.gp + 3L * p;
+      a0 += g[0]; a1 += g[1]; a2 += g[2];
+      const double* Ci = ne.Cinv + 6L * p;
+      const double d0 = -(Ci[0] * a0 + Ci[1] * a1 + Ci[2] * a2);
+      const double d1 = -(Ci[1] * a0 + Ci[3] * a1 + Ci[4] * a2);
+      const double d2 = -(Ci[2] * a0 + Ci[4] * a1 + Ci[5] * a2);
+      delta_p[3L * p] = d0; delta_p[3L * p + 1] = d1; delta_p[3L * p + 2] = d2;
+      trial[3L * p] = points[3L * p] + d0;
+      trial[3L * p + 1] = points[3L * p + 1] + d1;
+      trial[3L * p + 2] = points[3L * p + 2] + d2;
+      gd = g[0] * d0 + g[1] * d1 + g[2] * d2;
+      nn = d0 * d0 + d1 * d1 + d2 * d2;
+      const double* sp = ne.scale_p + 3L * p;
+      const double* e2 = ne.d2_p + 3L * p;
+      const double u0 = d0 / sp[0], u1 = d1 / sp[1], u2 = d2 / sp[2];
+      dd = e2[0] * u0 * u0 + e2[1] * u1 * u1 + e2[2] * u2 * u2;
+    }
   }
   gd = block_sum(gd, sh);
   dd = block_sum(dd, sh);
@@ -197,9 +212,9 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
                         double* trial_points, double* scalars, double* scratch, cudaStream_t s) {
   frame_step_kernel<<<1, kRedThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
-  const int nb = (n_points + 127) / 128;
+  const int nb = (n_points + kPointStepWarps - 1) / kPointStepWarps;
   if (nb > 0)
-    point_step_kernel<<<nb, 128, 0, s>>>(st, obs, jac, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
+    point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, obs, jac, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
   step_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, nb, scalars);
 }
 

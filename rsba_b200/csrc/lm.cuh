@@ -118,6 +118,7 @@ struct TileSchedule {      // device view of the TilePlan (tile_plan.cuh); tile 
   const int* lrow_ptr;      // [n_tiles+1]
   const int* lrow_cols;
   double* Dinv;             // [n_tiles][96*96] inverses of the diagonal factors (scratch)
+  double* solve_partials;   // [n_tiles][16][96] split matrix-vector partial sums of the solves
   long n_real;              // 12 * frames (rows beyond it are identity padding)
 };
 

@@ -36,6 +36,7 @@ struct LmState {
   // ---- numeric state (device)
   DeviceBuffer<double> B, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
   // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
+  DeviceBuffer<double> solve_partials;
   DeviceBuffer<double> S, misc_local, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
   double* misc = nullptr;      // tail: [0] cost [1] invalid [2] |x_p|^2 ... [8 + r] max|g_p| of rank r
   size_t comm_count = 0;       // doubles in S + tail
@@ -245,12 +246,13 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->S.ptr, 0, lm->S.bytes(), s));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->misc_local.ptr, 0, lm->misc_local.bytes(), s));
   RSBA_CUDA_TRY(lm->Dinv.resize((size_t)std::max(T, 1) * kTile * kTile));
+  RSBA_CUDA_TRY(lm->solve_partials.resize((size_t)std::max(T, 1) * 16 * kTile));
   RSBA_CUDA_TRY(lm->rhs.resize(std::max<long>(lm->n_pad, 1))); RSBA_CUDA_TRY(lm->y.resize(std::max<long>(lm->n_pad, 1)));
   RSBA_CUDA_TRY(lm->delta_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->delta_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->trial_poses.resize(Fz * 12)); RSBA_CUDA_TRY(lm->trial_points.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->scalars.resize(16));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->scalars.ptr, 0, lm->scalars.bytes(), s));
-  RSBA_CUDA_TRY(lm->scratch.resize(std::max<size_t>(3 + 3 * ((Pz + 127) / 128), 1024)));
+  RSBA_CUDA_TRY(lm->scratch.resize(std::max<size_t>(3 + 3 * ((Pz + 7) / 8), 1024)));
   RSBA_CUDA_TRY(lm->info.resize(4));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->rhs.ptr, 0, lm->rhs.bytes(), s));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->d2_c.ptr, 0, lm->d2_c.bytes(), s));
@@ -267,7 +269,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   TileSchedule& ts = lm->ts;
   ts.n_tiles = T; ts.nz_tiles = lm->nz_tiles.ptr; ts.tile_slot = lm->tile_slot.ptr; ts.n_nz = (int)nz_tiles.size();
   ts.row_ptr = lm->row_ptr.ptr; ts.rows = lm->rows.ptr; ts.upd = lm->upd.ptr; ts.panels = lm->panels.ptr; ts.trsm = lm->trsm.ptr;
-  ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.n_real = 12L * F;
+  ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.solve_partials = lm->solve_partials.ptr; ts.n_real = 12L * F;
 
   long free_params = 0;
   for (int f = 0; f < F; ++f) free_params += 12 - __builtin_popcount(h->pose_mask[f] & 0xFFF);

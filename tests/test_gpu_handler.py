@@ -61,10 +61,10 @@ def test_handler_add_solve_matches_bulk_api(tmp_path):
 def test_handler_windowed_ba_freezes_old_tracks(tmp_path):
     """startFrame > 0 (windowedBA, VideoSfMHandler.cc:185): frames before the window are not added,
     tracks seen before it are SetParameterBlockConstant (CeresHandler.h:288-300)."""
-    sc = make_scene(12, 400, 8, name="window")
+    sc = make_scene(24, 800, 8, name="window")
     src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
     write_scene(src, sc)
-    start = 6
+    start = 12
     r = subprocess.run([BIN, src, dst, "0", "5", str(start)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     out = np.fromfile(dst)
@@ -75,4 +75,4 @@ def test_handler_windowed_ba_freezes_old_tracks(tmp_path):
     old = np.zeros(sc.num_points, bool)
     old[sc.obs_point[sc.obs_frame < start]] = True
     assert np.array_equal(points[old], sc.points[old])               # frozen tracks
-    assert np.any(points[~old] != sc.points[~old])
+    assert (~old).sum() > 20 and np.any(points[~old] != sc.points[~old])
