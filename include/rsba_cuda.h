@@ -54,7 +54,8 @@ typedef struct rsba_solve_options {
   double gradient_tolerance;          /* 1e-10 */
   double parameter_tolerance;         /* 1e-8 */
   int jacobi_scaling;                 /* 1 */
-  double huber_loss;                  /* 0 = no loss (SfmOptions.h:64, CeresHandler.h:85-90) */
+  double huber_loss;                  /* > 0: same as rsba_cuda_set_loss(h, huber_loss) before solving;
+                                         0 = keep the problem's loss (SfmOptions.h:64, CeresHandler.h:85-90) */
   int verbose;                        /* minimizer_progress_to_stdout (CeresHandler.h:404) */
   int dense_cholesky;                 /* 1: ignore the tile occupancy map, factor S fully dense */
   int reorder_tiles;                  /* 1: nested-dissection ordering of the reduced system (default);
@@ -102,6 +103,13 @@ void rsba_cuda_default_options(rsba_solve_options* o);
 int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter,
                          const int scanlines[2], int interpolate_rotation);
 
+/* Replaces: lossFunction = new ceres::HuberLoss(opt.ceres.huberLoss), handed to every
+ * AddResidualBlock (CeresHandler.h:85-90, 252).  huber_a = 0 removes the loss (the default,
+ * SfmOptions.h:64).  Applied the way Ceres' Corrector does: cost = 1/2 rho(|r|^2), residual and
+ * Jacobian rescaled by sqrt(rho') (rho'' <= 0 for Huber); rsba_cuda_evaluate returns the
+ * corrected values, as problem.Evaluate does with apply_loss_function = true. */
+int rsba_cuda_set_loss(rsba_problem* h, double huber_a);
+
 /* Replaces: RsBundleAdjustment::Create(sess,opt,obs) + problem.AddResidualBlock(cost, loss,
  * f.poses[0].data(), f.poses[1].data(), t->pt.data())  (CeresHandler.h:250-255).
  * Block identity is pointer identity, as in Ceres; the caller owns the parameter memory,
@@ -140,6 +148,16 @@ int rsba_cuda_get_parameters(rsba_problem* h, double* poses, double* points);
  * written, invalid rows zero) if any functor returned false. */
 int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double* jacobian,
                        unsigned char* valid);
+
+/* Track-validation sweep.  Replaces: validate(sess, f, opt, t.pt, obs) (struct/VideoSfM.cc:159-169) as
+ * evalTracks / createTracks run it over every observation after a BA (VideoSfMHandler.cc:377-410,
+ * 599-600): ok[i] = |c(tau_i) - X| >= min_distance_to_camera (opt.tracks.minDistanceToCamera) and the
+ * projection succeeds (z >= 1e-8) and |proj - obs|^2 < sqrd_threshold (opt.tracks.sqrdThreshold).
+ * Unlike the BA functor the pose is interpolated at the observation's own scan line: x for a
+ * HORIZONTAL, y for a VERTICAL shutter (getPose, struct/VideoSfM.cc:108-111).  HOST outputs in the
+ * caller's observation order, either may be NULL; sqrd_error[i] = -1 where the projection failed. */
+int rsba_cuda_validate(rsba_problem* h, double sqrd_threshold, double min_distance_to_camera,
+                       unsigned char* ok, double* sqrd_error);
 
 /* HBM-resident form: evaluates on the device and leaves everything there.  The returned
  * device pointers (sorted-by-frame observation order) stay valid until the next scene

@@ -49,6 +49,8 @@ class Problem {
   void SetCamera(const double cam9[9], int shutter, const int scanlines[2], bool interpolate_rotation) {
     check(rsba_cuda_set_camera(h_, cam9, shutter, scanlines, interpolate_rotation ? 1 : 0));
   }
+  // lossFunction = new ceres::HuberLoss(a), applied to every residual block (CeresHandler.h:85-90)
+  void SetHuberLoss(double a) { check(rsba_cuda_set_loss(h_, a)); }
   void AddRsResidualBlock(const double observed[2], double* pose0, double* pose1, double* point) {
     check(rsba_cuda_add_rs_residual(h_, observed, pose0, pose1, point));
     ++num_residual_blocks_;
@@ -107,7 +109,7 @@ class Handler {
   std::size_t startFrame;
 
   explicit Handler(const Options& o, std::size_t start = 0, int device = 0) : problem(device), opt(o), startFrame(start) {
-    if (opt.ceres.huberLoss > 0) throw std::runtime_error("rsba_cuda: HuberLoss is not on the device path yet");
+    if (opt.ceres.huberLoss > 0) problem.SetHuberLoss(opt.ceres.huberLoss);      // CeresHandler.h:85-90
     if (!opt.model.use3Dpoints) throw std::runtime_error("rsba_cuda: structure-less (feature ray) mode is out of scope");
     if (!opt.model.calibrated) throw std::runtime_error("rsba_cuda: uncalibrated 4-block variant is not on the device path yet");
     if (opt.ceres.constFrameVelocity != 0 || opt.ceres.constFrameAcceleration != 0)

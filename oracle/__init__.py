@@ -142,3 +142,50 @@ class RefProblem:
 
     def __del__(self):
         self.close()
+
+
+def apply_huber(res, J, a):
+    """TEST INFRASTRUCTURE.  ceres::HuberLoss(a) as Ceres 1.9.0 applies it to a residual block
+    (loss_function.cc HuberLoss::Evaluate + corrector.cc; third-party, restated): with
+    s = |r|^2, rho(s) = s (s <= a^2) else 2 a sqrt(s) - a^2; rho'' <= 0, hence residual and
+    Jacobian are rescaled by sqrt(rho') and the block's cost is 1/2 rho(s).
+    Returns (corrected residuals, corrected Jacobian or None, total cost)."""
+    s = np.sum(res * res, axis=1)
+    out = s > a * a
+    sr = np.sqrt(np.where(out, s, 1.0))
+    w = np.where(out, np.sqrt(a / sr), 1.0)
+    rho = np.where(out, 2.0 * a * sr - a * a, s)
+    return res * w[:, None], None if J is None else J * w[:, None], 0.5 * float(np.sum(rho))
+
+
+def validate_sweep(scene, poses=None, points=None, sqrd_threshold=16.0, min_distance=0.0):
+    """TEST INFRASTRUCTURE.  validate(sess, f, opt, pt, obs) (struct/VideoSfM.cc:159-169) for every
+    observation, restated on the port's primitives: getPose -> interpolate_rs with the REAL
+    observation (x or y by shutter, struct/VideoSfM.cc:108-111), norm3(c - X) >= minDistanceToCamera,
+    reprojection_error + threshold (mat/cam.h:425-457).  Python loop: small scenes only.
+    Returns (ok [N] uint8, squared error [N], -1 where w2i failed)."""
+    poses, points = _prep(scene, poses, points)
+    poses, points = poses.reshape(-1, 12), points.reshape(-1, 3)
+    lib = port_lib()
+    lib.rsba_oracle_interpolate_rs.argtypes = [_dp, _dp, C.c_int, _ip, _dp, _dp, C.c_int]
+    lib.rsba_oracle_w2i.argtypes = [_dp, _dp, _dp, _dp, C.c_int]
+    cam = np.ascontiguousarray(scene.cam, dtype=np.float64)
+    scan = np.ascontiguousarray(scene.scanlines, dtype=np.int32)
+    n = scene.num_obs
+    ok = np.zeros(n, dtype=np.uint8)
+    err = np.full(n, -1.0)
+    pose = np.zeros(6)
+    proj = np.zeros(2)
+    for i in range(n):
+        f, p = int(scene.obs_frame[i]), int(scene.obs_point[i])
+        obs = np.ascontiguousarray(scene.obs_xy[i], dtype=np.float64)
+        p0 = np.ascontiguousarray(poses[f, :6])
+        p1 = np.ascontiguousarray(poses[f, 6:])
+        X = np.ascontiguousarray(points[p])
+        lib.rsba_oracle_interpolate_rs(_ptr(p0, _dp), _ptr(p1, _dp), int(scene.shutter), _ptr(scan, _ip),
+                                       _ptr(obs, _dp), _ptr(pose, _dp), int(bool(scene.interpolate_rotation)))
+        good = lib.rsba_oracle_w2i(_ptr(cam, _dp), _ptr(pose, _dp), _ptr(X, _dp), _ptr(proj, _dp), 1)
+        if good:
+            err[i] = float(np.sum((proj - obs) ** 2))
+            ok[i] = 1 if (np.linalg.norm(pose[3:] - X) >= min_distance and err[i] < sqrd_threshold) else 0
+    return ok, err

@@ -35,10 +35,10 @@ ERR_EVALUATION_FAILED, ERR_LINEAR_SOLVER, ERR_NCCL = -5, -6, -7
 # every symbol include/rsba_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "rsba_cuda_create", "rsba_cuda_destroy", "rsba_cuda_last_error", "rsba_cuda_set_stream",
-    "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_add_rs_residual",
+    "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_loss", "rsba_cuda_add_rs_residual",
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
-    "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
+    "rsba_cuda_validate", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
     "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
@@ -126,6 +126,7 @@ def load_library():
     lib.rsba_cuda_default_options.argtypes = [C.POINTER(SolveOptions)]
     lib.rsba_cuda_default_options.restype = None
     lib.rsba_cuda_set_camera.argtypes = [vp, _dp, C.c_int, _ip, C.c_int]
+    lib.rsba_cuda_set_loss.argtypes = [vp, C.c_double]
     lib.rsba_cuda_add_rs_residual.argtypes = [vp, _dp, vp, vp, vp]
     lib.rsba_cuda_set_block_constant.argtypes = [vp, vp]
     lib.rsba_cuda_set_subset_constant.argtypes = [vp, vp, C.c_int, _ip]
@@ -134,6 +135,7 @@ def load_library():
     lib.rsba_cuda_set_parameters.argtypes = [vp, vp, vp]
     lib.rsba_cuda_get_parameters.argtypes = [vp, vp, vp]
     lib.rsba_cuda_evaluate.argtypes = [vp, _dp, vp, vp, vp]
+    lib.rsba_cuda_validate.argtypes = [vp, C.c_double, C.c_double, vp, vp]
     lib.rsba_cuda_evaluate_device.argtypes = [vp, C.c_int, _dp, C.POINTER(C.c_long)]
     lib.rsba_cuda_device_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
     lib.rsba_cuda_observation_order.argtypes = [vp, vp]
@@ -227,6 +229,10 @@ class Problem:
         self._check(self.lib.rsba_cuda_set_camera(self._h, cam.ctypes.data_as(_dp), int(shutter),
                                                   scan.ctypes.data_as(_ip), int(bool(interpolate_rotation))))
 
+    def set_loss(self, huber_a: float):
+        """``ceres::HuberLoss(huber_a)`` on every residual block (CeresHandler.h:85-90); 0 = none."""
+        self._check(self.lib.rsba_cuda_set_loss(self._h, float(huber_a)))
+
     def add_rs_residual(self, observed, pose0: np.ndarray, pose1: np.ndarray, point: np.ndarray):
         """``pose0``/``pose1``/``point`` are float64 numpy views; identity = their address."""
         obs = np.ascontiguousarray(observed, dtype=np.float64)
@@ -298,6 +304,15 @@ class Problem:
         rc = self.lib.rsba_cuda_evaluate(self._h, C.byref(cost), _addr(r), _addr(J), _addr(v))
         self._check(rc, allow=() if check else (ERR_EVALUATION_FAILED,))
         return cost.value, r, J, v
+
+    def validate(self, sqrd_threshold=16.0, min_distance_to_camera=0.0, num_obs=None):
+        """Track-validation sweep (struct/VideoSfM.cc:159-169): (ok [N] uint8, squared error [N])."""
+        n = self.num_obs if num_obs is None else num_obs
+        ok = np.zeros(n, dtype=np.uint8)
+        err = np.zeros(n)
+        self._check(self.lib.rsba_cuda_validate(self._h, float(sqrd_threshold), float(min_distance_to_camera),
+                                                _addr(ok), _addr(err)))
+        return ok, err
 
     def evaluate_device(self, with_jacobian=True, fetch=True):
         """HBM-resident evaluation; with ``fetch`` returns (cost, num_invalid) (synchronises)."""

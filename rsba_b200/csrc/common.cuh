@@ -18,6 +18,7 @@ struct CameraModel {
   double scan_span;    // scanlines[1] - scanlines[0]
   int shutter;         // 0 GLOBAL, 1 HORIZONTAL, 2 VERTICAL
   int interp_rot;      // opt.model.interpolateRotation
+  double huber;        // ceres::HuberLoss(a) on every residual block (CeresHandler.h:85-90); 0 = no loss
 };
 
 // Observation SoA, sorted by frame.
@@ -35,7 +36,11 @@ void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, c
                int* invalid_count, cudaStream_t stream);
 // K1r: cost only at trial parameters.
 void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
-                double huber, double* cost_partials, int* invalid_count, cudaStream_t stream);
+                double* cost_partials, int* invalid_count, cudaStream_t stream);
+// track validation sweep (struct/VideoSfM.cc:159-169): per-observation predicate + squared error
+void launch_validate(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
+                     double sqrd_threshold, double min_distance, unsigned char* ok, double* sqrd_error,
+                     cudaStream_t stream);
 int k1_num_partials(long n);
 // deterministic fixed-order sum of `n` partials into out[0]
 void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t stream);

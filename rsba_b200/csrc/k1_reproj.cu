@@ -10,6 +10,7 @@
 //   w2i              mat/cam.h:401-419   fails (functor returns false) when z < 1e-8
 //   c2i + distort    mat/cam.h:372-395, 49-72
 //   residual         video_bundler_free.h:45-65
+//   loss             optional ceres::HuberLoss, CeresHandler.h:85-90 (SfmOptions.h:64, default off)
 // The Jacobian is the exact chain rule of those formulas (what forward-mode autodiff yields),
 // written out by hand: because tau does not depend on the parameters,
 //   J_pose0 = (1-tau) * J_pose,  J_pose1 = tau * J_pose  (rotation columns: 1 and 0 when
@@ -87,9 +88,23 @@ k1_kernel(const CameraModel cm, const ObsView obs, const double* __restrict__ po
 #pragma unroll
       for (int k = 0; k < kFrameParams; ++k) pose[k] = __ldg(gp + k);
     }
-    const Proj pr = reproject<JAC>(cm, o.x, o.y, pose, X0, X1, X2, Jrow);
+    Proj pr = reproject<JAC>(cm, o.x, o.y, pose, X0, X1, X2, Jrow);
     cost = pr.r0 * pr.r0 + pr.r1 * pr.r1;
     bad = !pr.ok;
+    // ceres::HuberLoss(a) through Ceres' Corrector (third-party; CeresHandler.h:85-90 passes the loss to
+    // every AddResidualBlock): rho(s) = s for s <= a^2, else 2 a sqrt(s) - a^2; rho'' <= 0, so the
+    // correction is a plain rescaling of residual and Jacobian by sqrt(rho') and cost = 1/2 rho(s).
+    if (cm.huber > 0.0 && cost > cm.huber * cm.huber) {
+      const double sr = sqrt(cost);
+      const double w = sqrt(cm.huber / sr);
+      cost = 2.0 * cm.huber * sr - cm.huber * cm.huber;
+      pr.r0 *= w;
+      pr.r1 *= w;
+      if (JAC) {
+#pragma unroll
+        for (int k = 0; k < kJacDoubles; ++k) Jrow[k] *= w;
+      }
+    }
     if (residuals) reinterpret_cast<double2*>(residuals)[i] = make_double2(pr.r0, pr.r1);
     if (valid) valid[i] = pr.ok ? 1 : 0;
   }
@@ -131,6 +146,41 @@ k1_kernel(const CameraModel cm, const ObsView obs, const double* __restrict__ po
   }
 }
 
+// Track validation sweep: the predicate of validate(sess, f, opt, pt, obs) (struct/VideoSfM.cc:159-169)
+// for every observation, as evalTracks runs it after each BA (VideoSfMHandler.cc:377-410, 599-600):
+//   |c(tau) - X| >= minDistanceToCamera  and  w2i succeeds  and  |proj - obs|^2 < sqrdThreshold
+// with the pose interpolated at the observation's own scan line (x or y by shutter direction).
+__global__ void __launch_bounds__(kK1Threads)
+validate_kernel(const CameraModel cm, const ObsView obs, const double* __restrict__ poses,
+                const double* __restrict__ points, double sqrd_threshold, double min_distance,
+                unsigned char* __restrict__ ok, double* __restrict__ sqrd_error) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= obs.n) return;
+  const double2 o = obs.xy[i];
+  const double* gp = poses + (long)obs.frame[i] * kFrameParams;
+  const double* pp = points + 3L * obs.point[i];
+  double pose[kFrameParams];
+#pragma unroll
+  for (int k = 0; k < kFrameParams; ++k) pose[k] = __ldg(gp + k);
+  const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
+  CameraModel plain = cm;
+  plain.huber = 0.0;
+  const Proj pr = reproject<false, true>(plain, o.x, o.y, pose, X0, X1, X2, nullptr);
+  // camera centre at the observation's scan line (interpolate, mat/cam.h:294-311)
+  double tau = 0.0;
+  if (cm.shutter != 0) {
+    tau = ((cm.shutter == 2 ? o.y : o.x) - cm.scan0) / cm.scan_span;
+    tau = tau < 0.0 ? 0.0 : (tau > 1.0 ? 1.0 : tau);
+  }
+  const double d0 = pose[3] + (pose[9] - pose[3]) * tau - X0;
+  const double d1 = pose[4] + (pose[10] - pose[4]) * tau - X1;
+  const double d2 = pose[5] + (pose[11] - pose[5]) * tau - X2;
+  const double err = pr.r0 * pr.r0 + pr.r1 * pr.r1;
+  const bool good = pr.ok && sqrt(d0 * d0 + d1 * d1 + d2 * d2) >= min_distance && err < sqrd_threshold;
+  if (ok) ok[i] = good ? 1 : 0;
+  if (sqrd_error) sqrd_error[i] = pr.ok ? err : -1.0;
+}
+
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
   __shared__ double s[32];
@@ -161,11 +211,19 @@ void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, c
 }
 
 void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
-                double /*huber*/, double* cost_partials, int* invalid_count, cudaStream_t stream) {
+                double* cost_partials, int* invalid_count, cudaStream_t stream) {
   if (obs.n <= 0) return;
   const int grid = k1_num_partials(obs.n);
   k1_kernel<false><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, nullptr, nullptr, nullptr,
                                                     cost_partials, invalid_count);
+}
+
+void launch_validate(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
+                     double sqrd_threshold, double min_distance, unsigned char* ok, double* sqrd_error,
+                     cudaStream_t stream) {
+  if (obs.n <= 0) return;
+  validate_kernel<<<k1_num_partials(obs.n), kK1Threads, 0, stream>>>(cm, obs, poses, points, sqrd_threshold,
+                                                                      min_distance, ok, sqrd_error);
 }
 
 void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t stream) {

@@ -441,7 +441,8 @@ int prepare_solve(rsba_problem* h, const rsba_solve_options* opt) {
   if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
   if (!opt) return fail(RSBA_ERR_INVALID_ARGUMENT, "options are NULL");
   if (!h->camera_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_camera has not been called");
-  if (opt->huber_loss > 0.0) return fail(RSBA_ERR_INVALID_ARGUMENT, "huber_loss: not implemented in this round");
+  if (opt->huber_loss < 0.0) return fail(RSBA_ERR_INVALID_ARGUMENT, "huber_loss must be >= 0");
+  if (opt->huber_loss > 0.0) h->cm.huber = opt->huber_loss;   // same as rsba_cuda_set_loss
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   if (h->ptr_mode) {
     int rc = finalize_pointer_problem(h);

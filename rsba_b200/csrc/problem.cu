@@ -110,8 +110,7 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
     launch_k1(h->cm, h->obs_view(), poses, points, h->d_res.ptr, h->d_jac.ptr, h->d_valid.ptr,
               h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
   } else {
-    launch_k1r(h->cm, h->obs_view(), poses, points, 0.0, h->d_cost_partials.ptr, h->d_invalid.ptr,
-               h->stream);
+    launch_k1r(h->cm, h->obs_view(), poses, points, h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
   }
   launch_reduce_partials(h->d_cost_partials.ptr, k1_num_partials(h->n_obs), h->d_scalars.ptr,
                          h->stream);
@@ -394,8 +393,14 @@ int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter, con
   h->cm.shutter = shutter;
   h->cm.scan0 = (double)scanlines[0];
   h->cm.scan_span = (double)(scanlines[1] - scanlines[0]);
-  h->cm.interp_rot = interpolate_rotation ? 1 : 0;
+  h->cm.interp_rot = interpolate_rotation ? 1 : 0;   // (cm.huber is set by rsba_cuda_set_loss and kept)
   h->camera_set = true;
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_loss(rsba_problem* h, double huber_a) {
+  if (!h || !(huber_a >= 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "huber_a must be >= 0");
+  h->cm.huber = huber_a;
   return RSBA_OK;
 }
 
@@ -578,6 +583,35 @@ int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double*
     }
   }
   if (bad > 0) return fail(RSBA_ERR_EVALUATION_FAILED, "a cost functor returned false (point behind camera)");
+  return RSBA_OK;
+}
+
+int rsba_cuda_validate(rsba_problem* h, double sqrd_threshold, double min_distance_to_camera,
+                       unsigned char* ok, double* sqrd_error) {
+  int rc = prepare(h);
+  if (rc) return rc;
+  const long n = h->n_obs, ng = h->n_obs_global;
+  rc = ensure_eval_buffers(h, false);
+  if (rc) return rc;
+  // d_valid / d_res double as the output buffers of the sweep
+  launch_validate(h->cm, h->obs_view(), h->d_poses.ptr, h->d_points.ptr, sqrd_threshold, min_distance_to_camera,
+                  h->d_valid.ptr, h->d_res.ptr, h->stream);
+  h->launches += 1;
+  RSBA_CUDA_TRY(cudaGetLastError());
+  std::vector<unsigned char> tv(n);
+  std::vector<double> te(n);
+  if (n) {
+    RSBA_CUDA_TRY(cudaMemcpyAsync(tv.data(), h->d_valid.ptr, n, cudaMemcpyDeviceToHost, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(te.data(), h->d_res.ptr, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (ok) memset(ok, 0, ng);
+  if (sqrd_error) for (long i = 0; i < ng; ++i) sqrd_error[i] = -1.0;
+  for (long i = 0; i < n; ++i) {
+    const long dst = h->order[h->local_ids[i]];
+    if (ok) ok[dst] = tv[i];
+    if (sqrd_error) sqrd_error[dst] = te[i];
+  }
   return RSBA_OK;
 }
 

@@ -14,7 +14,10 @@ struct Proj {
 };
 
 // Everything that depends on one observation.  JAC=false skips all derivative work.
-template <bool JAC>
+// TAU_FROM_Y: the scan line of a VERTICAL shutter is read from observed_y, as interpolate_rs does
+// when it is handed the real observation (getPose / validate, struct/VideoSfM.cc:108-111,159-169).
+// The BA functor hands it {observed_x, observed_x} (VideoSfmBaRs.h:31), hence false there.
+template <bool JAC, bool TAU_FROM_Y = false>
 __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double ox, double oy,
                                           const double* __restrict__ p0,  // frame: pose0|pose1
                                           double X0, double X1, double X2,
@@ -23,7 +26,7 @@ __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double
   // ---- interpolate_rs (mat/cam.h:316-349): tau is a constant of the observation
   double tau = 0.0, wr0 = 1.0, wr1 = 0.0;
   if (cm.shutter != 0) {
-    tau = (ox - cm.scan0) / cm.scan_span;
+    tau = (((TAU_FROM_Y && cm.shutter == 2) ? oy : ox) - cm.scan0) / cm.scan_span;
     tau = tau < 0.0 ? 0.0 : tau;
     tau = tau > 1.0 ? 1.0 : tau;
     if (cm.interp_rot) { wr0 = 1.0 - tau; wr1 = tau; }

@@ -141,3 +141,50 @@ def test_k1_full_size_properties(api, oracle_built):
     r0, J0, v0 = oracle_built.evaluate(sub, impl="port")
     assert (np.abs(r[idx] - r0) / np.maximum(1.0, np.abs(r0))).max() <= TOL
     assert rel_block_err(J[idx], J0).max() <= TOL
+
+
+@pytest.mark.parametrize("a", [0.5, 2.0])
+def test_k1_huber_loss_matches_ceres_corrector(api, oracle_built, a):
+    """ceres::HuberLoss(a) on every residual block (CeresHandler.h:85-90): cost = 1/2 sum rho(|r|^2),
+    residuals and Jacobians rescaled by sqrt(rho') -- what problem.Evaluate returns."""
+    sc = small_scene()
+    xy = sc.obs_xy.copy()
+    xy[::9] += 25.0                                   # gross outliers
+    from rsba_b200.scene import Scene
+    sc = Scene(**{**sc.__dict__, "obs_xy": xy})
+    r0, J0, v0 = oracle_built.evaluate(sc, impl="port")
+    rw, Jw, cost_w = oracle_built.apply_huber(r0, J0, a)
+    assert (np.sum(r0 * r0, axis=1) > a * a).sum() > 100
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        pb.set_loss(a)
+        cost, r, J, v = pb.evaluate()
+        c_res, _ = pb.evaluate_device(with_jacobian=False)
+        pb.set_loss(0.0)
+        cost_plain, _, _, _ = pb.evaluate()
+    assert np.array_equal(v, v0)
+    assert abs(cost - cost_w) <= 1e-12 * cost_w and c_res == cost
+    assert (np.abs(r - rw) / np.maximum(1.0, np.abs(rw))).max() <= TOL
+    assert rel_block_err(J, Jw).max() <= TOL
+    assert abs(cost_plain - 0.5 * np.sum(r0 * r0)) <= 1e-12 * cost_plain and cost < cost_plain
+
+
+@pytest.mark.parametrize("shutter", [1, 2, 0])
+def test_validate_sweep_matches_reference_predicate(api, oracle_built, shutter):
+    """validate() swept over every observation (struct/VideoSfM.cc:159-169, VideoSfMHandler.cc:377-410):
+    scan line from x or y by shutter direction, distance gate, squared-error threshold."""
+    sc = edge_scene(shutter, True)
+    want_ok, want_err = oracle_built.validate_sweep(sc, sqrd_threshold=4e5, min_distance=3.5)
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        ok, err = pb.validate(sqrd_threshold=4e5, min_distance_to_camera=3.5)
+    assert np.array_equal(ok, want_ok)
+    assert 0 < ok.sum() < ok.size
+    good = want_err >= 0
+    assert np.array_equal(err < 0, ~good)
+    assert (np.abs(err[good] - want_err[good]) <= 1e-9 * np.maximum(1.0, want_err[good])).all()
+    sc2 = small_scene()                                # a clean scene validates at the default threshold
+    with api.Problem(0) as pb:
+        pb.load_scene(sc2, poses=sc2.poses_true, points=sc2.points_true)
+        ok2, err2 = pb.validate()
+    assert ok2.all() and err2.max() < 16.0

@@ -189,3 +189,38 @@ def test_solve_fails_loudly_when_a_point_is_behind_the_camera(api):
         pb.load_scene(sc, points=pts)
         s = pb.solve(api.default_options(max_num_iterations=3), check=False)
     assert s.rc == api.ERR_EVALUATION_FAILED and s.usable == 0 and s.termination == 2
+
+
+def test_lm_step_and_solve_with_huber_loss(api, oracle_built, lo):
+    """HuberLoss through Ceres' Corrector: the LM step is the step of the rescaled residuals and
+    Jacobians; the accepted cost is 1/2 sum rho."""
+    sc = small_scene()
+    xy = sc.obs_xy.copy()
+    xy[::9] += 25.0
+    sc = Scene(**{**sc.__dict__, "obs_xy": xy})
+    a = 2.0
+    r0, J0, v0 = oracle_built.evaluate(sc, impl="port")
+    rw, Jw, _ = oracle_built.apply_huber(r0, J0, a)
+    want = lo.lm_step(sc, rw, Jw, 1e3)
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        pb.set_loss(a)
+        compare(pb.linearize_and_step(1e3), want)
+        s = pb.solve(api.default_options(max_num_iterations=15))
+        po, pt = pb.get_parameters()
+    r1, _, v1 = oracle_built.evaluate(sc, po, pt, jac=False, impl="port")
+    _, _, cost1 = oracle_built.apply_huber(r1, None, a)
+    assert s.usable == 1 and s.final_cost < s.initial_cost
+    assert abs(s.final_cost - cost1) <= 1e-9 * cost1
+    with api.Problem(0) as pb:                          # options.huber_loss is the same switch
+        pb.load_scene(sc)
+        s2 = pb.solve(api.default_options(max_num_iterations=15, huber_loss=a))
+    assert s2.final_cost == s.final_cost
+    # robustified solve ends closer to the truth than the plain one on the contaminated scene
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        pb.solve(api.default_options(max_num_iterations=15))
+        _, pt_plain = pb.get_parameters()
+    e_rob = np.linalg.norm(pt - sc.points_true)
+    e_plain = np.linalg.norm(pt_plain - sc.points_true)
+    assert e_rob < e_plain
