@@ -6,19 +6,22 @@
 // With C_p'^-1 = L^-T L^-1 (3x3 Cholesky inverted in registers, k2_normal.cu) the per-observation
 // block  F_i = Jc_i^T (Jx_i s_p) L^-T  (12x3) makes the point term a plain Gram product:
 //     sum_p E_p C_p^-1 E_p^T = Phi Phi^T,   Phi = [F_i] block-sparse, 12F x 3P.
-// Frames are cut into tiles of 8 (96 rows, the Cholesky tile).  For every (frame tile, point)
-// incidence phi_build writes one dense k-major panel [3][96(+4 pad)]; rows of frames that do not
-// see the point are zero.  A tile pair (A <= B) then is a dense GEMM over the points seen from
-// both tiles, K = 3 per point:
-//     S(B, A) -= sum_p Phi(B,p) Phi(A,p)^T                      96 x 96, mma.sync.m8n8k4.f64
-// Long pairs are split along K into work items of <= 512 points whose 96x96 partial products
+// Frames are cut into sub-tiles of 4 (48 rows, a quadrant of the 96-row Cholesky tile).  For every
+// (sub-tile, point) incidence phi_build writes one dense k-major panel [3][48(+4 pad)]; rows of
+// frames that do not see the point are zero.  A sub-tile pair (a <= b) then is a dense GEMM over
+// the points seen from both, K = 3 per point:
+//     S(b, a) -= sum_p Phi(b,p) Phi(a,p)^T                      48 x 48, mma.sync.m8n8k4.f64
+// (48 rather than 96 rows: a point seen from 25 consecutive frames fills 86 % of its 4-frame
+// panels but only 78 % of 8-frame ones, and its 7 x 8 / 2 sub-tile pairs waste less of the
+// squared fill -- 0.72x the DMMAs of 96-row tiles.)
+// Long pairs are split along K into work items of <= 512 points whose 48x48 partial products
 // are summed in a fixed order by schur_reduce (bit-reproducible, no atomics), which also adds
 // the camera diagonal blocks and places the tile at its (permuted) position of the tile-packed
 // reduced matrix.  schur_finalize then applies the camera-side Jacobi scaling, the LM diagonal
 // and the constant-parameter identity rows -- after the NCCL all-reduce when the observations
 // are sharded over several GPUs, because those depend on the global diag(B).
 //
-// Data movement: panels are 2400-byte contiguous records, fetched by TMA bulk copies
+// Data movement: panels are 1248-byte contiguous records, fetched by TMA bulk copies
 // (cp.async.bulk.shared::cluster.global.mbarrier) into a 3-stage shared-memory ring; the kernel
 // is bound by the FP64 pipe (tcgen05 has no FP64 kind: DMMA == DFMA rate, 37.1 TFLOP/s measured).
 #include "lm.cuh"
@@ -28,7 +31,7 @@ namespace {
 
 constexpr int kChunkPts = 8;                       // points per pipeline stage (24 K columns)
 constexpr int kStages = 3;
-constexpr int kOperandDoubles = kChunkPts * kPanelDoubles;       // 2400 doubles
+constexpr int kOperandDoubles = kChunkPts * kPanelDoubles;       // 1248 doubles
 constexpr int kStageDoubles = 2 * kOperandDoubles;               // row side | column side
 constexpr unsigned kPanelBytes = kPanelDoubles * sizeof(double);
 constexpr size_t kSyrkSmem = (size_t)kStages * kStageDoubles * sizeof(double) + 64;
@@ -42,15 +45,15 @@ constexpr size_t kSyrkSmem = (size_t)kStages * kStageDoubles * sizeof(double) + 
 __global__ void __launch_bounds__(256)
 phi_build_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long)st.n_inc * 8) return;
-  const int inc = (int)(t >> 3), fs = (int)(t & 7);
+  if (t >= (long)st.n_inc * kSubFrames) return;
+  const int inc = (int)(t / kSubFrames), fs = (int)(t % kSubFrames);
   double F[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) F[k] = 0.0;
   const int cnt = st.slot_cnt[t];
   if (cnt > 0) {
     const int p = st.inc_point[inc];
-    const int f = st.inc_tile[inc] * kFramesPerTile + fs;
+    const int f = st.inc_tile[inc] * kSubFrames + fs;
     const double* Mi = ne.Minv + 6L * p;
     const double m00 = Mi[0], m10 = Mi[1], m11 = Mi[2], m20 = Mi[3], m21 = Mi[4], m22 = Mi[5];
     const double sp0 = ne.scale_p[3L * p], sp1 = ne.scale_p[3L * p + 1], sp2 = ne.scale_p[3L * p + 2];
@@ -125,9 +128,10 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
                : "d"(a), "d"(b));
 }
 
-// ---------------------------------------------------------------- tile-pair SYRK
-// One CTA per work item.  8 warps; warp w owns the 48 x 24 patch (w>>2, w&3) of the 96 x 96 tile.
-__global__ void __launch_bounds__(256, 1)
+// ---------------------------------------------------------------- sub-tile-pair SYRK
+// One CTA (4 warps) per work item; warp w owns the 24 x 24 patch (w>>1, w&1) of the 48 x 48 block.
+// 60 KB of shared memory per CTA: three CTAs per SM keep 12 warps on the FP64 pipe.
+__global__ void __launch_bounds__(128, 3)
 schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entries,
                   const int4* __restrict__ items, double* __restrict__ partial) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -164,11 +168,11 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
     for (int c = 0; c < kStages && c < nchunks; ++c) issue(c);
   }
 
-  const int m0 = (warp >> 2) * 48, n0 = (warp & 3) * 24;
+  const int m0 = (warp >> 1) * 24, n0 = (warp & 1) * 24;
   const int fr = lane >> 2, fc = lane & 3;
-  double acc[6][3][2];
+  double acc[3][3][2];
 #pragma unroll
-  for (int mi = 0; mi < 6; ++mi)
+  for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
@@ -180,13 +184,13 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
 #pragma unroll
     for (int ks = 0; ks < (3 * kChunkPts) / 4; ++ks) {
       const int krow = (4 * ks + fc) * kPanelLd + fr;
-      double a[6], b[3];
+      double a[3], b[3];
 #pragma unroll
-      for (int mi = 0; mi < 6; ++mi) a[mi] = R[krow + m0 + 8 * mi];
+      for (int mi = 0; mi < 3; ++mi) a[mi] = R[krow + m0 + 8 * mi];
 #pragma unroll
       for (int ni = 0; ni < 3; ++ni) b[ni] = Cc[krow + n0 + 8 * ni];
 #pragma unroll
-      for (int mi = 0; mi < 6; ++mi)
+      for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 3; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
@@ -194,40 +198,43 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
     if (warp == 0 && c + kStages < nchunks) issue(c + kStages);
   }
 
-  double* out = partial + (long)blockIdx.x * kTile * kTile;
+  double* out = partial + (long)blockIdx.x * kSub * kSub;
 #pragma unroll
-  for (int mi = 0; mi < 6; ++mi)
+  for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
     for (int ni = 0; ni < 3; ++ni)
-      *reinterpret_cast<double2*>(out + (m0 + 8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc) =
+      *reinterpret_cast<double2*>(out + (m0 + 8 * mi + fr) * kSub + n0 + 8 * ni + 2 * fc) =
           make_double2(acc[mi][ni][0], acc[mi][ni][1]);
 }
 
 // ---------------------------------------------------------------- reduce
-// grid (n_pairs, 9): 1024 elements of the pair's tile per CTA, 4 per thread.  Writes the unscaled
-// tile  [A == B] B_f - sum of the pair's partial products  at its (permuted) place.
+// grid (n_pairs, 3): 768 elements of the pair's 48 x 48 block per CTA, 3 per thread.  Writes the
+// unscaled block  [a == b] B_f - sum of the pair's partial products  into quadrant (b%2, a%2) of
+// Cholesky tile (b/2, a/2) at its (permuted) place.
 __global__ void __launch_bounds__(256)
 schur_reduce_kernel(SchurStructure st, NormalEq ne, double* __restrict__ S, const int* __restrict__ tile_slot,
                     int T) {
   const int pr = blockIdx.x;
-  const int A = st.pair_a[pr], B = st.pair_b[pr];
+  const int a = st.pair_a[pr], b = st.pair_b[pr];
   const int ib = st.pair_item_ptr[pr], ie = st.pair_item_ptr[pr + 1];
+  const int A = a >> 1, B = b >> 1;
   const int pa = st.tile_pos[A], pb = st.tile_pos[B];
   const bool transposed = pb < pa;           // rows must be the later position (lower triangle)
   double* tile = S + (long)tile_slot[(transposed ? pa : pb) * T + (transposed ? pb : pa)] * kTile * kTile;
+  const int r0 = (b & 1) * kSub, c0 = (a & 1) * kSub;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int e = blockIdx.y * 1024 + u * 256 + threadIdx.x;
-    const int r = e / kTile, c = e % kTile;
+  for (int u = 0; u < 3; ++u) {
+    const int e = blockIdx.y * 768 + u * 256 + threadIdx.x;
+    const int r = e / kSub, c = e % kSub;
     double sum = 0.0;
-    for (int it = ib; it < ie; ++it) sum += ne.partial[(long)it * kTile * kTile + e];
+    for (int it = ib; it < ie; ++it) sum += ne.partial[(long)it * kSub * kSub + e];
     double val = -sum;
-    if (A == B && r / kFrameParams == c / kFrameParams) {
-      const long f = (long)A * kFramesPerTile + r / kFrameParams;
+    if (a == b && r / kFrameParams == c / kFrameParams) {
+      const long f = (long)a * kSubFrames + r / kFrameParams;
       if (f * kFrameParams < st.n_cam_params) val += ne.B[f * 144 + (r % kFrameParams) * 12 + c % kFrameParams];
     }
-    if (transposed) tile[c * kTile + r] = val;
-    else            tile[r * kTile + c] = val;
+    if (transposed) tile[(c0 + c) * kTile + r0 + r] = val;
+    else            tile[(r0 + r) * kTile + c0 + c] = val;
   }
 }
 
@@ -281,7 +288,7 @@ camera_rhs_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, int n_frames, 
 void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
                       cudaStream_t s) {
   if (st.n_inc <= 0) return;
-  const long n = (long)st.n_inc * 8;
+  const long n = (long)st.n_inc * kSubFrames;
   phi_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, obs, jac, ne);
 }
 
@@ -292,12 +299,12 @@ void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
     attr_done = true;
   }
   if (st.n_items <= 0) return;
-  schur_syrk_kernel<<<st.n_items, 256, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
+  schur_syrk_kernel<<<st.n_items, 128, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
 }
 
 void launch_schur_reduce(const SchurStructure& st, NormalEq ne, double* S, const int* tile_slot, int n_tiles,
                          cudaStream_t s) {
-  if (st.n_pairs > 0) schur_reduce_kernel<<<dim3(st.n_pairs, 9), 256, 0, s>>>(st, ne, S, tile_slot, n_tiles);
+  if (st.n_pairs > 0) schur_reduce_kernel<<<dim3(st.n_pairs, 3), 256, 0, s>>>(st, ne, S, tile_slot, n_tiles);
 }
 
 void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,

@@ -24,14 +24,16 @@ struct SchurStructure {
   const int* frame_chunk_ptr;  // [F+1] chunks of frame f
   int n_chunks;
   // ---- Schur complement as a tile-level SYRK  S -= Phi Phi^T  (k2_schur.cu)
-  // incidence = (frame tile A, point p) with at least one observation of p in frames 8A..8A+7;
-  // its panel Phi[inc] is [3][kPanelLd] doubles (k-major, 96 rows = 8 frame slots x 12).
+  // The SYRK works on SUB-TILES of kSubFrames = 4 frames (48 rows, a quadrant of a Cholesky tile):
+  // incidence = (sub-tile h, point p) with at least one observation of p in frames 4h..4h+3;
+  // its panel Phi[inc] is [3][kPanelLd] doubles (k-major, 48 rows = 4 frame slots x 12).
   int n_inc;
   const int* inc_point;    // [n_inc]
-  const int* inc_tile;     // [n_inc]
-  const int* slot_beg;     // [n_inc*8] first index into pt_obs of the observations in that slot, -1 if none
-  const unsigned char* slot_cnt;  // [n_inc*8] number of observations in the slot (duplicates in one frame)
-  // tile pair (A <= B in frame-tile order): output tile rows = frames of B, columns = frames of A
+  const int* inc_tile;     // [n_inc] sub-tile index h
+  const int* slot_beg;     // [n_inc*4] first index into pt_obs of the observations in that slot, -1 if none
+  const unsigned char* slot_cnt;  // [n_inc*4] number of observations in the slot (duplicates in one frame)
+  // sub-tile pair (a <= b in frame order): output block rows = frames of b, columns = frames of a,
+  // i.e. quadrant (b % 2, a % 2) of Cholesky tile (b / 2, a / 2)
   int n_pairs;
   const int* pair_a;       // [n_pairs]
   const int* pair_b;       // [n_pairs]
@@ -47,8 +49,10 @@ struct SchurStructure {
   const int* pos_tile;     // [T] inverse
 };
 
-constexpr int kPanelLd = 100;                 // 96 rows + 4 pad: conflict-free DMMA fragment loads
-constexpr int kPanelDoubles = 3 * kPanelLd;   // one bulk copy of 2400 bytes
+constexpr int kSubFrames = 4;                 // frames per SYRK sub-tile
+constexpr int kSub = kSubFrames * kFrameParams;   // 48 rows
+constexpr int kPanelLd = kSub + 4;            // 48 rows + 4 pad: conflict-free DMMA fragment loads (ld % 16 == 4)
+constexpr int kPanelDoubles = 3 * kPanelLd;   // one bulk copy of 1248 bytes
 constexpr int kSchurSegPoints = 512;
 
 struct NormalEq {
@@ -65,7 +69,7 @@ struct NormalEq {
   double* tp;       // [P][3]    Cinv * gp
   double* Minv;     // [P][6]    L^-1 of the damped scaled point block (m00 m10 m11 m20 m21 m22)
   double* Phi;      // [n_inc+1][3][kPanelLd]  panels s_c Jc^T (Jx s_p) L^-T; last panel all zero
-  double* partial;  // [n_items][96*96] per-item partial products of the Schur SYRK
+  double* partial;  // [n_items][48*48] per-item partial products of the Schur SYRK
   double* scale_c;  // [12F] Jacobi scaling (1 for constant parameters)
   double* scale_p;  // [3P]
   double* d2_c;     // [12F] LM diagonal (scaled space) of the current solve

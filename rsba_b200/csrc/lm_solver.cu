@@ -100,6 +100,8 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   }
   // ---- Schur SYRK structure: (frame tile, point) incidences, tile pairs, work items
   const int T = (int)((12L * F + kTile - 1) / kTile);
+  const int H = 2 * T;                                   // sub-tiles of 4 frames
+  const int Hreal = (F + kSubFrames - 1) / kSubFrames;   // ... that hold at least one frame
   std::vector<int> inc_point, inc_tile, slot_beg;
   std::vector<unsigned char> slot_cnt;
   struct PairEntry { long key; int inc_a, inc_b; };
@@ -111,26 +113,26 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
       mine.clear();
       const int b = pt_ptr[p], e = pt_ptr[p + 1];
       for (int x = b; x < e; ++x) {
-        const int f = fr[pt_obs[x]], A = f / kFramesPerTile, fs = f % kFramesPerTile;
+        const int f = fr[pt_obs[x]], A = f / kSubFrames, fs = f % kSubFrames;
         if (mine.empty() || inc_tile[mine.back()] != A) {
           mine.push_back((int)inc_point.size());
           inc_point.push_back(p);
           inc_tile.push_back(A);
-          slot_beg.insert(slot_beg.end(), 8, -1);
-          slot_cnt.insert(slot_cnt.end(), 8, 0);
+          slot_beg.insert(slot_beg.end(), kSubFrames, -1);
+          slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
         }
-        const size_t sl = (size_t)mine.back() * 8 + fs;
+        const size_t sl = (size_t)mine.back() * kSubFrames + fs;
         if (slot_cnt[sl] == 0) slot_beg[sl] = x;
         if (slot_cnt[sl] == 255) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
         slot_cnt[sl]++;
       }
       for (size_t x = 0; x < mine.size(); ++x)
         for (size_t y = x; y < mine.size(); ++y)
-          pe.push_back({(long)inc_tile[mine[x]] * T + inc_tile[mine[y]], mine[x], mine[y]});
+          pe.push_back({(long)inc_tile[mine[x]] * H + inc_tile[mine[y]], mine[x], mine[y]});
     }
   }
   const int n_inc = (int)inc_point.size();
-  for (int t = 0; t < T; ++t) pe.push_back({(long)t * T + t, -1, -1});   // every diagonal tile is a pair
+  for (int t = 0; t < Hreal; ++t) pe.push_back({(long)t * H + t, -1, -1});   // every diagonal sub-tile is a pair
   std::stable_sort(pe.begin(), pe.end(), [](const PairEntry& x, const PairEntry& y) { return x.key < y.key; });
   std::vector<int> pair_a, pair_b, pair_item_ptr;
   std::vector<int4> items;
@@ -138,7 +140,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   for (size_t i = 0; i < pe.size();) {
     size_t j = i;
     while (j < pe.size() && pe[j].key == pe[i].key) ++j;
-    const int A = (int)(pe[i].key / T), Bt = (int)(pe[i].key % T);
+    const int A = (int)(pe[i].key / H), Bt = (int)(pe[i].key % H);
     const int pair = (int)pair_a.size();
     pair_a.push_back(A);
     pair_b.push_back(Bt);
@@ -192,7 +194,9 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
           if (seen[(size_t)a * T + b]) tp.emplace_back(a, b);
     } else {
       tp.reserve(pair_a.size());
-      for (size_t k = 0; k < pair_a.size(); ++k) tp.emplace_back(pair_a[k], pair_b[k]);
+      for (size_t k = 0; k < pair_a.size(); ++k) tp.emplace_back(pair_a[k] / 2, pair_b[k] / 2);
+      std::sort(tp.begin(), tp.end());
+      tp.erase(std::unique(tp.begin(), tp.end()), tp.end());
     }
     build_tile_plan(T, tp, dense, h->reorder_tiles, &plan);
   }
@@ -234,7 +238,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(lm->tp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Minv.resize(Pz * 6));
   RSBA_CUDA_TRY(lm->Phi.resize((size_t)(n_inc + 1) * kPanelDoubles));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->Phi.ptr, 0, lm->Phi.bytes(), s));   // pad columns + the zero panel
-  RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kTile * kTile));
+  RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kSub * kSub));
   RSBA_CUDA_TRY(lm->scale_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->scale_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->d2_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->d2_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 168));
