@@ -17,6 +17,8 @@
 // normal equations are bit-reproducible from run to run (no floating-point atomics).
 #include "lm.cuh"
 
+#include <algorithm>
+
 namespace rsba {
 namespace {
 
@@ -145,90 +147,168 @@ point_invert_kernel(int n_points, NormalEq ne, LmOptionsDev o) {
   t[2] = i20 * g[0] + i21 * g[1] + i22 * g[2];
 }
 
-// ---------------------------------------------------------------- frames: B_f, g_c, w_f
-// One CTA per chunk (<= 128 observations of one frame).  Thread (grp, tr, tc) owns the 3x3
-// tile (tr, tc) of the 12x12 block over the observations grp, grp+8, ...
-__global__ void __launch_bounds__(128)
+// ---------------------------------------------------------------- frames: B_f, g_c, w_f (+ Schur panels)
+// Persistent CTAs (two per SM) walk the chunk list (<= 128 observations of one frame each).  A
+// chunk's Jacobian records and residuals are contiguous, so each is ONE TMA bulk copy
+// (cp.async.bulk, 30 KB + 2 KB) into a double-buffered shared-memory stage: the next chunk streams
+// in while the current one is reduced.  Thread (grp, tr, tc) owns the 3x3 tile (tr, tc) of the
+// 12x12 block over the observations grp, grp+16, ...; the per-observation pass also writes the
+// observation's Schur panel rows.
+constexpr int kFrameThreads = 256;
+constexpr int kFrameGroups = kFrameThreads / 16;
+constexpr size_t kFrameSmem = (size_t)(2 * kChunk * kJacDoubles + 2 * kChunk * 2 + kChunk * 2) * sizeof(double) + 64;
+
+__device__ __forceinline__ unsigned fsmem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kFrameThreads, 2)
 frame_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac,
                     const double* __restrict__ res, NormalEq ne, int with_wf) {
-  __shared__ __align__(16) double sJ[kChunk * kJacDoubles];  // raw records
-  __shared__ double sR[kChunk * 2];
-  __shared__ double sQ[kChunk * 2];                            // Jx_i t_p
-  const int c = blockIdx.x;
-  const long beg = st.chunk_beg[c];
-  const int cnt = st.chunk_cnt[c];
-  {
-    const double2* src = reinterpret_cast<const double2*>(jac + beg * kJacDoubles);
-    double2* dst = reinterpret_cast<double2*>(sJ);
-    for (int k = threadIdx.x; k < cnt * (kJacDoubles / 2); k += blockDim.x) dst[k] = src[k];
-    for (int k = threadIdx.x; k < cnt * 2; k += blockDim.x) sR[k] = res[beg * 2 + k];
+  extern __shared__ __align__(128) unsigned char fsmem[];
+  double* sJbuf = reinterpret_cast<double*>(fsmem);                    // [2][128*30] raw records
+  double* sRbuf = sJbuf + 2 * kChunk * kJacDoubles;                    // [2][256]
+  double* sQ = sRbuf + 2 * kChunk * 2;                                 // [256] Jx_i t_p
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sQ + kChunk * 2);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fsmem_u32(&bars[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fsmem_u32(&bars[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x < cnt) {
-    double q0 = 0.0, q1 = 0.0;
-    if (with_wf) {
-      const int p = obs.point[beg + threadIdx.x];
-      const double* t = ne.tp + 3L * p;
-      const double* jx = sJ + threadIdx.x * kJacDoubles + 24;
-      q0 = jx[0] * t[0] + jx[1] * t[1] + jx[2] * t[2];
-      q1 = jx[3] * t[0] + jx[4] * t[1] + jx[5] * t[2];
+  auto issue = [&](int c, int buf) {      // one thread
+    const long beg = st.chunk_beg[c];
+    const unsigned cnt = (unsigned)st.chunk_cnt[c];
+    const unsigned bar = fsmem_u32(&bars[buf]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * 256u) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     fsmem_u32(sJbuf + buf * kChunk * kJacDoubles)),
+                 "l"(jac + beg * kJacDoubles), "r"(cnt * 240u), "r"(bar)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     fsmem_u32(sRbuf + buf * kChunk * 2)),
+                 "l"(res + beg * 2), "r"(cnt * 16u), "r"(bar)
+                 : "memory");
+  };
+  if (tid == 0 && (int)blockIdx.x < st.n_chunks) issue(blockIdx.x, 0);
+
+  const int grp = tid >> 4, tp = tid & 15, tr = tp >> 2, tc = tp & 3;
+  int it = 0;
+  for (int c = blockIdx.x; c < st.n_chunks; c += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const long beg = st.chunk_beg[c];
+    const int cnt = st.chunk_cnt[c];
+    // the other stage was fully consumed in the previous iteration (trailing __syncthreads)
+    if (tid == 0 && c + (int)gridDim.x < st.n_chunks) issue(c + gridDim.x, buf ^ 1);
+    {
+      const unsigned bar = fsmem_u32(&bars[buf]), parity = (unsigned)((it >> 1) & 1);
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "WAIT_%=:\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+          "@p bra DONE_%=;\n"
+          "bra WAIT_%=;\n"
+          "DONE_%=:\n"
+          "}\n" ::"r"(bar), "r"(parity)
+          : "memory");
     }
-    sQ[2 * threadIdx.x] = q0;
-    sQ[2 * threadIdx.x + 1] = q1;
-  }
-  __syncthreads();
-  const int grp = threadIdx.x >> 4, tp = threadIdx.x & 15, tr = tp >> 2, tc = tp & 3;
-  double acc[9], ga[3], wa[3];
+    double* sJ = sJbuf + buf * kChunk * kJacDoubles;
+    const double* sR = sRbuf + buf * kChunk * 2;
+    if (tid < cnt) {
+      double q0 = 0.0, q1 = 0.0;
+      const double* rec = sJ + tid * kJacDoubles;
+      if (with_wf) {
+        const int p = obs.point[beg + tid];
+        const double* t = ne.tp + 3L * p;
+        const double* jx = rec + 24;
+        q0 = jx[0] * t[0] + jx[1] * t[1] + jx[2] * t[2];
+        q1 = jx[3] * t[0] + jx[4] * t[1] + jx[5] * t[2];
+        // ---- Schur panel rows of this observation: F = Jc^T (Jx s_p) L^-T  (12 x 3), written straight
+        // into the point's (sub-tile, point) panel while the record is in shared memory (k2_schur.cu
+        // describes the layout; zero rows of unobserved frames were written once, at allocation)
+        const int off = st.obs_phi_off[beg + tid];
+        if (off >= 0) {
+          const double* Mi = ne.Minv + 6L * p;
+          const double m00 = Mi[0], m10 = Mi[1], m11 = Mi[2], m20 = Mi[3], m21 = Mi[4], m22 = Mi[5];
+          const double a0 = jx[0] * ne.scale_p[3L * p], a1 = jx[1] * ne.scale_p[3L * p + 1], a2 = jx[2] * ne.scale_p[3L * p + 2];
+          const double b0 = jx[3] * ne.scale_p[3L * p], b1 = jx[4] * ne.scale_p[3L * p + 1], b2 = jx[5] * ne.scale_p[3L * p + 2];
+          const double xa[3] = {a0 * m00, a0 * m10 + a1 * m11, a0 * m20 + a1 * m21 + a2 * m22};
+          const double xb[3] = {b0 * m00, b0 * m10 + b1 * m11, b0 * m20 + b1 * m21 + b2 * m22};
+          const unsigned mask = ne.pose_mask[st.chunk_frame[c]];
+          double* dst = ne.Phi + off;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-  ga[0] = ga[1] = ga[2] = wa[0] = wa[1] = wa[2] = 0.0;
-  for (int o = grp; o < cnt; o += 8) {
-    const double* rec = sJ + o * kJacDoubles;
+          for (int k = 0; k < 3; ++k) {
+            double2* d2 = reinterpret_cast<double2*>(dst + k * kPanelLd);
 #pragma unroll
-    for (int row = 0; row < 2; ++row) {
-      const double* pa = rec + jc_off(tr, row);
-      const double* pb = rec + jc_off(tc, row);
-      const double a0 = pa[0], a1 = pa[1], a2 = pa[2];
-      const double b0 = pb[0], b1 = pb[1], b2 = pb[2];
-      acc[0] += a0 * b0; acc[1] += a0 * b1; acc[2] += a0 * b2;
-      acc[3] += a1 * b0; acc[4] += a1 * b1; acc[5] += a1 * b2;
-      acc[6] += a2 * b0; acc[7] += a2 * b1; acc[8] += a2 * b2;
-      if (tc == 0) {
-        const double r = sR[2 * o + row], q = sQ[2 * o + row];
-        ga[0] += a0 * r; ga[1] += a1 * r; ga[2] += a2 * r;
-        wa[0] += a0 * q; wa[1] += a1 * q; wa[2] += a2 * q;
+            for (int a = 0; a < 12; a += 2) {
+              // camera columns a, a+1 of the record: rows 0/1 at jc offsets
+              const int o0 = (a < 6) ? a : 12 + (a - 6);
+              const double f0 = ((mask >> a) & 1) ? 0.0 : rec[o0] * xa[k] + rec[o0 + 6] * xb[k];
+              const double f1 = ((mask >> (a + 1)) & 1) ? 0.0 : rec[o0 + 1] * xa[k] + rec[o0 + 7] * xb[k];
+              d2[a >> 1] = make_double2(f0, f1);
+            }
+          }
+        }
+      }
+      sQ[2 * tid] = q0;
+      sQ[2 * tid + 1] = q1;
+    }
+    __syncthreads();
+    double acc[9], ga[3], wa[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+    ga[0] = ga[1] = ga[2] = wa[0] = wa[1] = wa[2] = 0.0;
+    for (int o = grp; o < cnt; o += kFrameGroups) {
+      const double* rec = sJ + o * kJacDoubles;
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        const double* pa = rec + jc_off(tr, row);
+        const double* pb = rec + jc_off(tc, row);
+        const double a0 = pa[0], a1 = pa[1], a2 = pa[2];
+        const double b0 = pb[0], b1 = pb[1], b2 = pb[2];
+        acc[0] += a0 * b0; acc[1] += a0 * b1; acc[2] += a0 * b2;
+        acc[3] += a1 * b0; acc[4] += a1 * b1; acc[5] += a1 * b2;
+        acc[6] += a2 * b0; acc[7] += a2 * b1; acc[8] += a2 * b2;
+        if (tc == 0) {
+          const double r = sR[2 * o + row], q = sQ[2 * o + row];
+          ga[0] += a0 * r; ga[1] += a1 * r; ga[2] += a2 * r;
+          wa[0] += a0 * q; wa[1] += a1 * q; wa[2] += a2 * q;
+        }
       }
     }
-  }
-  __syncthreads();                 // sJ is dead: reuse it for the cross-group reduction
-  double* sAcc = sJ;               // [8][16][15]
-  double* my = sAcc + (grp * 16 + tp) * 15;
+    __syncthreads();                 // sJ is dead: reuse it for the cross-group reduction
+    double* sAcc = sJ;               // [16][16][15]
+    double* my = sAcc + (grp * 16 + tp) * 15;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) my[k] = acc[k];
+    for (int k = 0; k < 9; ++k) my[k] = acc[k];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { my[9 + k] = ga[k]; my[12 + k] = wa[k]; }
-  __syncthreads();
-  // fixed-order sum over the 8 groups -> chunk partial
-  double* out = ne.partials + (long)c * kPartial;
-  for (int k = threadIdx.x; k < kPartial; k += blockDim.x) {
-    int tpos, slot;
-    if (k < 144) {
-      const int r = k / 12, cc = k % 12;
-      tpos = (r / 3) * 4 + (cc / 3);
-      slot = (r % 3) * 3 + (cc % 3);
-    } else if (k < 156) {
-      const int r = k - 144;
-      tpos = (r / 3) * 4;
-      slot = 9 + r % 3;
-    } else {
-      const int r = k - 156;
-      tpos = (r / 3) * 4;
-      slot = 12 + r % 3;
+    for (int k = 0; k < 3; ++k) { my[9 + k] = ga[k]; my[12 + k] = wa[k]; }
+    __syncthreads();
+    // fixed-order sum over the groups -> chunk partial
+    double* out = ne.partials + (long)c * kPartial;
+    for (int k = tid; k < kPartial; k += kFrameThreads) {
+      int tpos, slot;
+      if (k < 144) {
+        const int r = k / 12, cc = k % 12;
+        tpos = (r / 3) * 4 + (cc / 3);
+        slot = (r % 3) * 3 + (cc % 3);
+      } else if (k < 156) {
+        const int r = k - 144;
+        tpos = (r / 3) * 4;
+        slot = 9 + r % 3;
+      } else {
+        const int r = k - 156;
+        tpos = (r / 3) * 4;
+        slot = 12 + r % 3;
+      }
+      double sum = 0.0;
+#pragma unroll
+      for (int g = 0; g < kFrameGroups; ++g) sum += sAcc[(g * 16 + tpos) * 15 + slot];
+      out[k] = sum;
     }
-    double s = 0.0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) s += sAcc[(g * 16 + tpos) * 15 + slot];
-    out[k] = s;
+    // generic-proxy reads/writes of this stage must be ordered before the async-proxy refill
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
   }
 }
 
@@ -257,7 +337,17 @@ void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const dou
 
 void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
                          int n_frames, NormalEq ne, bool with_wf, cudaStream_t s) {
-  if (st.n_chunks > 0) frame_blocks_kernel<<<st.n_chunks, 128, 0, s>>>(st, obs, jac, res, ne, with_wf ? 1 : 0);
+  static bool attr_done = false;
+  static int n_sm = 148;
+  if (!attr_done) {
+    cudaFuncSetAttribute(frame_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    attr_done = true;
+  }
+  if (st.n_chunks > 0)
+    frame_blocks_kernel<<<std::min(st.n_chunks, 2 * n_sm), kFrameThreads, kFrameSmem, s>>>(st, obs, jac, res, ne, with_wf ? 1 : 0);
   if (n_frames > 0) frame_reduce_kernel<<<n_frames, 192, 0, s>>>(st, ne, n_frames);
 }
 

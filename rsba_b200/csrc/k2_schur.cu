@@ -37,16 +37,20 @@ constexpr unsigned kPanelBytes = kPanelDoubles * sizeof(double);
 constexpr size_t kSyrkSmem = (size_t)kStages * kStageDoubles * sizeof(double) + 64;
 
 // ---------------------------------------------------------------- panels
-// One thread per (incidence, frame slot): F = sum over the slot's observations (more than one only
-// when a point was observed twice in one frame) of  Jc^T (Jx s_p) L^-T ; constant camera
+// The panel rows of an observation are normally written by frame_blocks_kernel (k2_normal.cu), which
+// already holds the Jacobian records in shared memory.  This kernel only rebuilds the incidences in
+// which a point was observed twice in one frame (st.dup_inc), where the rows are sums:
+// one thread per (incidence, frame slot): F = sum over the slot's observations
+// of  Jc^T (Jx s_p) L^-T ; constant camera
 // parameters get zero rows, constant points have L^-1 = 0 and never appear in a pair.  The
 // camera-side Jacobi scaling is applied to S afterwards (schur_finalize), so that partial sums of
 // different GPUs can be added before the scaling -- which depends on the global diag(B) -- is known.
 __global__ void __launch_bounds__(256)
 phi_build_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne) {
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long)st.n_inc * kSubFrames) return;
-  const int inc = (int)(t / kSubFrames), fs = (int)(t % kSubFrames);
+  const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= (long)st.n_dup * kSubFrames) return;
+  const int inc = st.dup_inc[u / kSubFrames], fs = (int)(u % kSubFrames);
+  const long t = (long)inc * kSubFrames + fs;
   double F[36];
 #pragma unroll
   for (int k = 0; k < 36; ++k) F[k] = 0.0;
@@ -287,8 +291,8 @@ camera_rhs_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, int n_frames, 
 
 void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
                       cudaStream_t s) {
-  if (st.n_inc <= 0) return;
-  const long n = (long)st.n_inc * kSubFrames;
+  if (st.n_dup <= 0) return;   // the common case: frame_blocks_kernel has written every panel
+  const long n = (long)st.n_dup * kSubFrames;
   phi_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, obs, jac, ne);
 }
 

@@ -32,6 +32,13 @@ struct SchurStructure {
   const int* inc_tile;     // [n_inc] sub-tile index h
   const int* slot_beg;     // [n_inc*4] first index into pt_obs of the observations in that slot, -1 if none
   const unsigned char* slot_cnt;  // [n_inc*4] number of observations in the slot (duplicates in one frame)
+  // The panels are written by frame_blocks_kernel while it holds the Jacobian records in shared
+  // memory: obs_phi_off[i] = offset (doubles) of observation i's 12 rows inside Phi, or -1 for
+  // observations of constant points and of incidences with two observations in one frame slot;
+  // the latter (dup_inc) are rebuilt by phi_build_kernel, which sums the slot's observations.
+  const int* obs_phi_off;  // [N]
+  const int* dup_inc;      // [n_dup]
+  int n_dup;
   // sub-tile pair (a <= b in frame order): output block rows = frames of b, columns = frames of a,
   // i.e. quadrant (b % 2, a % 2) of Cholesky tile (b / 2, a / 2)
   int n_pairs;

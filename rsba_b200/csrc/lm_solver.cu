@@ -21,6 +21,7 @@ struct LmState {
   // ---- structure (device)
   DeviceBuffer<int> pt_ptr, pt_obs, chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr;
   DeviceBuffer<int> inc_point, inc_tile, slot_beg, pair_a, pair_b, pair_item_ptr, tile_pos, pos_tile;
+  DeviceBuffer<int> obs_phi_off, dup_inc;
   DeviceBuffer<unsigned char> slot_cnt, point_owned;
   DeviceBuffer<int4> items;
   DeviceBuffer<int2> entries;
@@ -132,6 +133,19 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     }
   }
   const int n_inc = (int)inc_point.size();
+  if ((long)(n_inc + 1) * kPanelDoubles > 2147483647L)
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "Schur panel buffer exceeds 2^31 doubles: shard the scene over more GPUs");
+  // where each observation's 12 panel rows live; incidences with a doubly observed frame slot are
+  // rebuilt by phi_build_kernel instead
+  std::vector<int> obs_phi_off(std::max<long>(N, 1), -1), dup_inc;
+  for (int i = 0; i < n_inc; ++i) {
+    bool dup = false;
+    for (int fs = 0; fs < kSubFrames; ++fs) dup = dup || slot_cnt[(size_t)i * kSubFrames + fs] > 1;
+    if (dup) { dup_inc.push_back(i); continue; }
+    for (int fs = 0; fs < kSubFrames; ++fs)
+      if (slot_cnt[(size_t)i * kSubFrames + fs] == 1)
+        obs_phi_off[pt_obs[slot_beg[(size_t)i * kSubFrames + fs]]] = i * kPanelDoubles + fs * kFrameParams;
+  }
   for (int t = 0; t < Hreal; ++t) pe.push_back({(long)t * H + t, -1, -1});   // every diagonal sub-tile is a pair
   std::stable_sort(pe.begin(), pe.end(), [](const PairEntry& x, const PairEntry& y) { return x.key < y.key; });
   std::vector<int> pair_a, pair_b, pair_item_ptr;
@@ -209,6 +223,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(pt_ptr, pt_ptr); UP(pt_obs, pt_obs); UP(chunk_frame, chunk_frame); UP(chunk_beg, chunk_beg);
   UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr);
   UP(inc_point, inc_point); UP(inc_tile, inc_tile); UP(slot_beg, slot_beg); UP(slot_cnt, slot_cnt);
+  UP(obs_phi_off, obs_phi_off); UP(dup_inc, dup_inc);
   UP(pair_a, pair_a); UP(pair_b, pair_b); UP(pair_item_ptr, pair_item_ptr); UP(items, items); UP(tile_pos, tile_pos);
   UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
   UP(entries, entries); UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
@@ -226,6 +241,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.frame_chunk_ptr = lm->frame_chunk_ptr.ptr; st.n_chunks = (int)chunk_frame.size();
   st.n_inc = n_inc; st.inc_point = lm->inc_point.ptr; st.inc_tile = lm->inc_tile.ptr;
   st.slot_beg = lm->slot_beg.ptr; st.slot_cnt = lm->slot_cnt.ptr;
+  st.obs_phi_off = lm->obs_phi_off.ptr; st.dup_inc = lm->dup_inc.ptr; st.n_dup = (int)dup_inc.size();
   st.n_pairs = (int)pair_a.size(); st.pair_a = lm->pair_a.ptr; st.pair_b = lm->pair_b.ptr;
   st.pair_item_ptr = lm->pair_item_ptr.ptr; st.n_items = n_items; st.items = lm->items.ptr;
   st.entries = lm->entries.ptr; st.n_entries = (long)entries.size(); st.tile_pos = lm->tile_pos.ptr;
