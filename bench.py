@@ -29,6 +29,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner,
+# library chatter) is sent to stderr; emit() writes the result to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def k1_bytes_per_obs(scene) -> float:
     return K1_BYTES_FIXED + (24.0 * scene.num_points + 96.0 * scene.num_frames) / scene.num_obs
 
@@ -129,6 +139,13 @@ class CpuLmLoop:
         from oracle import cpu_lm
         self.oracle, self.scene = oracle, scene
         self.cores = nthreads or (os.cpu_count() or 1)
+        # torchrun exports OMP_NUM_THREADS=1: the OpenMP parts get their thread count explicitly
+        # (omp_set_num_threads inside the libraries), LAPACK/OpenBLAS through threadpoolctl
+        try:
+            import threadpoolctl
+            self._blas_limit = threadpoolctl.threadpool_limits(limits=self.cores)
+        except Exception:  # noqa: BLE001
+            self._blas_limit = None
         self.n = scene.num_obs
         self.res, self.J = np.zeros((self.n, 2)), np.zeros((self.n, 30))
         self.res_t = np.zeros((self.n, 2))
@@ -221,7 +238,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": "M evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 METRIC = "M residual+Jacobian evals/sec (full LM iteration)"
@@ -417,7 +434,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_lm_baseline(scene, args.cpu_iters, 1)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():

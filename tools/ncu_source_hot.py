@@ -16,7 +16,7 @@ samp = h.index("# Samples")
 lines = []
 for r in rows[hdr + 1:]:
     if len(r) > samp and r[0].isdigit():
-        lines.append((int(r[samp] or 0), int(r[0]), r[1].strip()))
+        lines.append((int(r[samp]) if r[samp].isdigit() else 0, int(r[0]), r[1].strip()))
 tot = sum(x[0] for x in lines) or 1
 print(f"# {rows[1][1][:100]}: {tot} samples")
 for s, ln, src in sorted(lines, reverse=True)[:top]:
