@@ -116,6 +116,25 @@ int rsba_cuda_set_loss(rsba_problem* h, double huber_a);
  * which must stay put until the handle is destroyed.  Results are written back in place. */
 int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0,
                               double* pose1, double* point);
+/* Replaces: RsConstVeloPrior::Create(scale) / RsConstAccelerationPrior::Create(scale) +
+ * problem.AddResidualBlock(cost, loss, &opt.ceres.interFrameRatio, f.poses[0], f.poses[1],
+ * f_1.poses[0], f_1.poses[1])  (CeresHandler.h:148-186; functors video_bundler_rs_inter.h:55-173):
+ * the 12-residual constant-velocity (kind 1) / constant-acceleration (kind 2) prior between frame k
+ * (pose0, end0) and frame k-1 (pose1, end1), with the interFrameRatio block CONSTANT -- the reference
+ * fixes it whenever opt.ceres.interFrameRatio != 1 (CeresHandler.h:178-180).  The free, lower-bounded
+ * ratio of the reference's default (== 1) is not on the device path.  A frame may be the current
+ * frame of one prior and the previous frame of one prior.  The problem's loss (rsba_cuda_set_loss)
+ * applies to the prior blocks too, as in the reference.  Rejects ratios for which the functor
+ * returns false (velocity: ratio < 0; acceleration: ratio < DBL_EPSILON). */
+int rsba_cuda_add_motion_prior(rsba_problem* h, int kind, double scale, double inter_frame_ratio,
+                               double* pose0, double* end0, double* pose1, double* end1);
+/* Bulk form (after rsba_cuda_set_scene, which clears the list): frame[i] / prev_frame[i] index poses. */
+int rsba_cuda_set_motion_priors(rsba_problem* h, int n, const int* kind, const double* scale,
+                                const double* inter_frame_ratio, const int* frame, const int* prev_frame);
+/* Loss-corrected residuals [12 n] of the priors at the last residual+Jacobian evaluation (HOST pointer,
+ * may be NULL); returns the number of priors. */
+long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals);
+
 /* Replaces: problem.SetParameterBlockConstant(double*)  (CeresHandler.h:283,299,344-345). */
 int rsba_cuda_set_block_constant(rsba_problem* h, double* block);
 /* Replaces: problem.SetParameterization(pose, new SubsetParameterization(6, constant))
@@ -142,7 +161,8 @@ int rsba_cuda_get_parameters(rsba_problem* h, double* poses, double* points);
 /* Replaces: problem.Evaluate(EvaluateOptions(), &cost, residuals, NULL, jacobian)
  * (CeresHandler.h:386) == what ceres::ProgramEvaluator does each LM iteration with
  * AutoDiffCostFunction<RsBundleAdjustment,2,6,6,3> (VideoSfmBaRs.h:58-63).
- * Outputs are HOST pointers, any may be NULL: cost = 1/2 sum r^2; residuals[2N];
+ * Outputs are HOST pointers, any may be NULL: cost = 1/2 sum rho(r^2) over the reprojection blocks AND
+ * the motion priors; residuals[2N] / jacobian[30N] / valid[N] cover the reprojection blocks;
  * jacobian[30N]; valid[N] (the functor's bool).  Pointer-API problems read the parameter
  * values from the caller's blocks first.  Returns RSBA_ERR_EVALUATION_FAILED (outputs still
  * written, invalid rows zero) if any functor returned false. */

@@ -55,6 +55,10 @@ class Problem {
     check(rsba_cuda_add_rs_residual(h_, observed, pose0, pose1, point));
     ++num_residual_blocks_;
   }
+  // RsConstVeloPrior (1) / RsConstAccelerationPrior (2) with a constant ratio (CeresHandler.h:148-186)
+  void AddMotionPrior(int kind, double scale, double ratio, double* pose0, double* end0, double* pose1, double* end1) {
+    check(rsba_cuda_add_motion_prior(h_, kind, scale, ratio, pose0, end0, pose1, end1));
+  }
   void SetParameterBlockConstant(double* block) { check(rsba_cuda_set_block_constant(h_, block)); }
   void SetSubsetConstant(double* pose_block, const std::vector<int>& constant) {
     check(rsba_cuda_set_subset_constant(h_, pose_block, (int)constant.size(), constant.data()));
@@ -100,7 +104,8 @@ class Problem {
 // shutter frame), frames[k].obs[i].{x, y, track, __isset.track}, getTrack(id) -> {pt, valid,
 // __isset.pt, obs[j].frame}, cam, rs, scanlines.  Options: model.{use3Dpoints, calibrated,
 // constVelocity, interpolateRotation}, ceres.{huberLoss, const3d, fixFirstNCameras, fixScale,
-// fixRotation, fixPosition, useOnlyValidMatches, constFrameVelocity, constFrameAcceleration}.
+// fixRotation, fixPosition, useOnlyValidMatches, constFrameVelocity, constFrameAcceleration,
+// interFrameRatio}.
 template <typename Session, typename Options>
 class Handler {
  public:
@@ -112,8 +117,9 @@ class Handler {
     if (opt.ceres.huberLoss > 0) problem.SetHuberLoss(opt.ceres.huberLoss);      // CeresHandler.h:85-90
     if (!opt.model.use3Dpoints) throw std::runtime_error("rsba_cuda: structure-less (feature ray) mode is out of scope");
     if (!opt.model.calibrated) throw std::runtime_error("rsba_cuda: uncalibrated 4-block variant is not on the device path yet");
-    if (opt.ceres.constFrameVelocity != 0 || opt.ceres.constFrameAcceleration != 0)
-      throw std::runtime_error("rsba_cuda: motion priors are not on the device path yet");
+    if ((opt.ceres.constFrameVelocity != 0 || opt.ceres.constFrameAcceleration != 0) && opt.ceres.interFrameRatio == 1)
+      throw std::runtime_error("rsba_cuda: motion priors need a fixed interFrameRatio (!= 1, CeresHandler.h:178-180); "
+                               "the free, lower-bounded ratio is not on the device path");
   }
 
   void Add(const std::size_t frameKey, Session& sess) {
@@ -126,6 +132,20 @@ class Handler {
     if (f.poses.size() != 2) throw std::runtime_error("rsba_cuda: only rolling-shutter frames (two control poses)");
     if (opt.model.constVelocity) throw std::runtime_error("rsba_cuda: constVelocity (the reference aborts here too)");
     bool added = false;
+    // motion prior between this frame and the previous one (CeresHandler.h:147-186)
+    if (frameKey >= (std::size_t)opt.ceres.fixFirstNCameras && frameKey > 0 &&
+        (opt.ceres.constFrameVelocity != 0 || opt.ceres.constFrameAcceleration != 0)) {
+      auto& f_1 = sess.frames[frameKey - 1];
+      if (f_1.poses.size() == 2) {
+        const bool accel = opt.ceres.constFrameAcceleration != 0;
+        problem.AddMotionPrior(accel ? 2 : 1, accel ? opt.ceres.constFrameAcceleration : opt.ceres.constFrameVelocity,
+                               opt.ceres.interFrameRatio, f.poses[0].data(), f.poses[1].data(), f_1.poses[0].data(),
+                               f_1.poses[1].data());
+        added = true;
+        if (frameKey - 1 < (std::size_t)opt.ceres.fixFirstNCameras)          // :182-186
+          for (auto& pose : f_1.poses) problem.SetParameterBlockConstant(pose.data());
+      }
+    }
     for (auto& o : f.obs) {                                   // CeresHandler.h:208
       if (!o.__isset.track) continue;
       auto* t = &sess.getTrack(o.track);

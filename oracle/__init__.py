@@ -189,3 +189,89 @@ def validate_sweep(scene, poses=None, points=None, sqrd_threshold=16.0, min_dist
             err[i] = float(np.sum((proj - obs) ** 2))
             ok[i] = 1 if (np.linalg.norm(pose[3:] - X) >= min_distance and err[i] < sqrd_threshold) else 0
     return ok, err
+
+
+# --------------------------------------------------------------------------------------------
+# camera-only motion priors
+PRIOR_VELOCITY, PRIOR_ACCELERATION = 1, 2
+_EPS = np.finfo(np.float64).eps
+
+
+def motion_prior_coefficients(kind, ratio):
+    """TEST INFRASTRUCTURE.  RsConstVeloPrior / RsConstAccelerationPrior
+    (video_bundler_rs_inter.h:55-108, 113-173) with the interFrameRatio block constant are linear in
+    the four pose blocks: each 6-residual half is  sigma * (c_p0 pose0 + c_e0 end0 + c_p1 pose1 + c_e1 end1)
+    with sigma = scale * (0.01, 0.01, 0.01, 1, 1, 1).  Returns coefficient rows [2][4] in the block
+    order (pose0, end0, pose1, end1) = (frame k first, frame k last, frame k-1 first, frame k-1 last)."""
+    r = float(ratio)
+    if kind == PRIOR_VELOCITY:
+        a = [1.0, 0.0, r, -(1.0 + r)]                       # pose0 - (end1 + r (end1 - pose1))
+        if r > _EPS:
+            b = [-(1.0 + 1.0 / r), 1.0, 0.0, 1.0 / r]      # end0 - (pose0 + (pose0 - end1) / r)
+        else:
+            b = [-1.0, 1.0, 1.0, -1.0]                     # end0 - (pose0 + (end1 - pose1))
+    elif kind == PRIOR_ACCELERATION:
+        a = [0.5, 0.0, 0.5 * r, -0.5 * (1.0 + r)]
+        b = [-0.5 * (1.0 + 1.0 / r), 0.5, 0.0, 0.5 / r]
+    else:
+        raise ValueError(kind)
+    return np.array([a, b])
+
+
+def motion_prior_eval(kind, scale, ratio, frame_k, frame_km1):
+    """Residuals [12] and Jacobian [12, 24] (columns: frame k's 12 parameters, then frame k-1's) of one
+    prior from the closed form above."""
+    c = motion_prior_coefficients(kind, ratio)
+    sigma = scale * np.array([0.01, 0.01, 0.01, 1.0, 1.0, 1.0])
+    blocks = [frame_k[:6], frame_k[6:], frame_km1[:6], frame_km1[6:]]
+    res = np.zeros(12)
+    J = np.zeros((12, 24))
+    for h in range(2):
+        acc = sum(c[h, b] * blocks[b] for b in range(4))
+        res[6 * h:6 * h + 6] = sigma * acc
+        for b in range(4):
+            J[6 * h + np.arange(6), 6 * b + np.arange(6)] = sigma * c[h, b]
+    return res, J
+
+
+def motion_prior_eval_ref(kind, scale, ratio, frame_k, frame_km1):
+    """The reference's own functors under Jet autodiff (oracle/_ref).  Returns (valid, residuals [12],
+    Jacobian [12, 24] w.r.t. the pose blocks, d residual / d interFrameRatio [12])."""
+    lib = ref_lib()
+    fn = lib.rsba_ref_velo_prior if kind == PRIOR_VELOCITY else lib.rsba_ref_accel_prior
+    fn.restype = C.c_int
+    ifr = np.array([float(ratio)])
+    p0, e0 = np.ascontiguousarray(frame_k[:6]), np.ascontiguousarray(frame_k[6:])
+    p1, e1 = np.ascontiguousarray(frame_km1[:6]), np.ascontiguousarray(frame_km1[6:])
+    res = np.zeros(12)
+    jac = np.zeros((12, 25))
+    ok = fn(float(scale), _ptr(ifr, _dp), _ptr(p0, _dp), _ptr(e0, _dp), _ptr(p1, _dp), _ptr(e1, _dp),
+            _ptr(res, _dp), _ptr(jac, _dp))
+    return bool(ok), res, jac[:, 1:].copy(), jac[:, 0].copy()
+
+
+def motion_prior_rows(scene, priors, poses=None, huber=0.0):
+    """TEST INFRASTRUCTURE.  Residual rows of a list of priors (kind, scale, ratio, frame, prev_frame)
+    over the full parameter vector [12 F + 3 P]: returns (J scipy CSR [12 n, 12F+3P], r [12 n], cost).
+    With huber > 0 the 12-residual blocks are corrected like every other block (apply_huber)."""
+    import scipy.sparse as sp
+    poses = np.asarray(scene.poses if poses is None else poses, dtype=np.float64).reshape(-1, 12)
+    F, P = scene.num_frames, scene.num_points
+    rows, cols, vals, res = [], [], [], []
+    cost = 0.0
+    for i, (kind, scale, ratio, fk, fp) in enumerate(priors):
+        r, J = motion_prior_eval(kind, scale, ratio, poses[fk], poses[fp])
+        s = float(r @ r)
+        w = 1.0
+        if huber > 0 and s > huber * huber:
+            w = np.sqrt(huber / np.sqrt(s))
+            s = 2.0 * huber * np.sqrt(s) - huber * huber
+        cost += 0.5 * s
+        res.append(w * r)
+        rr, cc = np.nonzero(J)
+        rows.append(12 * i + rr)
+        cols.append(np.where(cc < 12, 12 * fk + cc, 12 * fp + (cc - 12)))
+        vals.append(w * J[rr, cc])
+    n = len(priors)
+    Jx = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(12 * n, 12 * F + 3 * P))
+    return Jx, np.concatenate(res), cost

@@ -92,7 +92,7 @@ def jacobi_scale(Js, active, enabled=True):
 
 
 def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mask=None, point_const=None,
-            want_S=True):
+            want_S=True, extra=None):
     """One linear solve of the LM subproblem.  Returns a dict with the reduced system
     ``S delta_c' = rhs`` (scaled space, constant parameters as identity rows), the unscaled
     step and model_cost_change."""
@@ -101,10 +101,15 @@ def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mas
     act_c, act_p = param_masks(scene, pose_mask, point_const)
     active = np.concatenate([act_c, act_p])
     Js = sparse_jacobian(scene, J, active)
+    rr = r.reshape(-1)
+    if extra is not None:
+        # additional residual blocks (camera-only motion priors): rows over the same parameter vector
+        Jx, rx = extra
+        Js = sp.vstack([Js, sp.csr_matrix(Jx) @ sp.diags(active.astype(np.float64))]).tocsr()
+        rr = np.concatenate([rr, np.asarray(rx).reshape(-1)])
     if scale is None:
         scale = jacobi_scale(Js, active, opts.jacobi_scaling)
     Jp = Js @ sp.diags(scale)
-    rr = r.reshape(-1)
     H = (Jp.T @ Jp).tocsr()
     g = Jp.T @ rr
     diag = H.diagonal()

@@ -36,6 +36,7 @@ ERR_EVALUATION_FAILED, ERR_LINEAR_SOLVER, ERR_NCCL = -5, -6, -7
 SYMBOLS = [
     "rsba_cuda_create", "rsba_cuda_destroy", "rsba_cuda_last_error", "rsba_cuda_set_stream",
     "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_loss", "rsba_cuda_add_rs_residual",
+    "rsba_cuda_add_motion_prior", "rsba_cuda_set_motion_priors", "rsba_cuda_get_prior_residuals",
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
@@ -128,6 +129,10 @@ def load_library():
     lib.rsba_cuda_set_camera.argtypes = [vp, _dp, C.c_int, _ip, C.c_int]
     lib.rsba_cuda_set_loss.argtypes = [vp, C.c_double]
     lib.rsba_cuda_add_rs_residual.argtypes = [vp, _dp, vp, vp, vp]
+    lib.rsba_cuda_add_motion_prior.argtypes = [vp, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp]
+    lib.rsba_cuda_set_motion_priors.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
+    lib.rsba_cuda_get_prior_residuals.argtypes = [vp, vp]
+    lib.rsba_cuda_get_prior_residuals.restype = C.c_long
     lib.rsba_cuda_set_block_constant.argtypes = [vp, vp]
     lib.rsba_cuda_set_subset_constant.argtypes = [vp, vp, C.c_int, _ip]
     lib.rsba_cuda_set_scene.argtypes = [vp, C.c_long, _dp, _ip, _ip, C.c_int, C.c_int,
@@ -241,6 +246,31 @@ class Problem:
         self._keep.extend((pose0, pose1, point))
         self._check(self.lib.rsba_cuda_add_rs_residual(self._h, obs.ctypes.data_as(_dp), _addr(pose0),
                                                        _addr(pose1), _addr(point)))
+
+    def add_motion_prior(self, kind, scale, ratio, pose0, end0, pose1, end1):
+        """RsConstVeloPrior (kind 1) / RsConstAccelerationPrior (kind 2) between frame k = (pose0, end0)
+        and frame k-1 = (pose1, end1), constant interFrameRatio (CeresHandler.h:148-186)."""
+        self._keep.extend((pose0, end0, pose1, end1))
+        self._check(self.lib.rsba_cuda_add_motion_prior(self._h, int(kind), float(scale), float(ratio), _addr(pose0),
+                                                        _addr(end0), _addr(pose1), _addr(end1)))
+
+    def set_motion_priors(self, kind, scale, ratio, frame, prev_frame):
+        """Bulk form: arrays of equal length; ``frame`` / ``prev_frame`` index the pose array."""
+        kind = np.ascontiguousarray(kind, dtype=np.int32)
+        scale = np.ascontiguousarray(scale, dtype=np.float64)
+        ratio = np.ascontiguousarray(ratio, dtype=np.float64)
+        frame = np.ascontiguousarray(frame, dtype=np.int32)
+        prev = np.ascontiguousarray(prev_frame, dtype=np.int32)
+        self._check(self.lib.rsba_cuda_set_motion_priors(self._h, int(kind.size), kind.ctypes.data_as(_ip),
+                                                         scale.ctypes.data_as(_dp), ratio.ctypes.data_as(_dp),
+                                                         frame.ctypes.data_as(_ip), prev.ctypes.data_as(_ip)))
+
+    def prior_residuals(self):
+        n = self.lib.rsba_cuda_get_prior_residuals(self._h, None)
+        r = np.zeros((max(n, 0), 12))
+        if n > 0:
+            self.lib.rsba_cuda_get_prior_residuals(self._h, _addr(r))
+        return r
 
     def set_block_constant(self, block: np.ndarray):
         self._check(self.lib.rsba_cuda_set_block_constant(self._h, _addr(block)))

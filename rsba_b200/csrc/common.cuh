@@ -29,6 +29,20 @@ struct ObsView {
   long n;
 };
 
+// Camera-only motion priors between a frame and its predecessor (k2_priors.cu), device view.
+struct PriorView {
+  int n;                 // number of priors
+  const int* frame;      // [n] current frame k
+  const int* prev;       // [n] previous frame (k-1)
+  const double* coef;    // [n][8] rows (half A, half B) x (pose0, end0, pose1, end1)
+  const double* scale;   // [n]
+  const int* cur_of;     // [F] prior whose current frame is f, or -1
+  const int* prev_of;    // [F] prior whose previous frame is f, or -1
+  double* r;             // [n][12] loss-corrected residuals at the linearisation point
+  double* w2;            // [n] squared loss-correction weight
+  double* Bx;            // [F][4][6] coupling diagonals of cur_of[f] (zero without a prior)
+};
+
 // ---- launchers (definitions in the .cu files); all asynchronous on `stream` ------------
 // K1: residual + Jacobian (+ per-CTA cost partials, invalid count).
 void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
@@ -41,6 +55,9 @@ void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, 
 void launch_validate(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
                      double sqrd_threshold, double min_distance, unsigned char* ok, double* sqrd_error,
                      cudaStream_t stream);
+// priors: cost_out[0] = sum rho(|r|^2); store: also residuals and weights for the linearisation
+void launch_prior_eval(const PriorView& pv, const double* poses, double huber, double* cost_out, bool store,
+                       cudaStream_t stream);
 int k1_num_partials(long n);
 // deterministic fixed-order sum of `n` partials into out[0]
 void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t stream);

@@ -216,8 +216,8 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
 // unscaled block  [a == b] B_f - sum of the pair's partial products  into quadrant (b%2, a%2) of
 // Cholesky tile (b/2, a/2) at its (permuted) place.
 __global__ void __launch_bounds__(256)
-schur_reduce_kernel(SchurStructure st, NormalEq ne, double* __restrict__ S, const int* __restrict__ tile_slot,
-                    int T) {
+schur_reduce_kernel(SchurStructure st, NormalEq ne, PriorView pv, double* __restrict__ S,
+                    const int* __restrict__ tile_slot, int T) {
   const int pr = blockIdx.x;
   const int a = st.pair_a[pr], b = st.pair_b[pr];
   const int ib = st.pair_item_ptr[pr], ie = st.pair_item_ptr[pr + 1];
@@ -233,9 +233,17 @@ schur_reduce_kernel(SchurStructure st, NormalEq ne, double* __restrict__ S, cons
     double sum = 0.0;
     for (int it = ib; it < ie; ++it) sum += ne.partial[(long)it * kSub * kSub + e];
     double val = -sum;
-    if (a == b && r / kFrameParams == c / kFrameParams) {
-      const long f = (long)a * kSubFrames + r / kFrameParams;
-      if (f * kFrameParams < st.n_cam_params) val += ne.B[f * 144 + (r % kFrameParams) * 12 + c % kFrameParams];
+    const int fr = b * kSubFrames + r / kFrameParams, fc = a * kSubFrames + c / kFrameParams;
+    if (fr == fc) {
+      if ((long)fr * kFrameParams < st.n_cam_params)
+        val += ne.B[(long)fr * 144 + (r % kFrameParams) * 12 + c % kFrameParams];
+    } else if (pv.n > 0 && (r % 6) == (c % 6) && (long)fr * kFrameParams < st.n_cam_params &&
+               (long)fc * kFrameParams < st.n_cam_params) {
+      // motion-prior coupling between a frame and its previous frame: 6x6 diagonal blocks
+      const int rb = (r % kFrameParams) / 6, cb = (c % kFrameParams) / 6;
+      const int pa = pv.cur_of[fr], pc = pv.cur_of[fc];
+      if (pa >= 0 && pv.prev[pa] == fc) val += pv.Bx[24L * fr + 6 * (2 * rb + cb) + r % 6];
+      else if (pc >= 0 && pv.prev[pc] == fr) val += pv.Bx[24L * fc + 6 * (2 * cb + rb) + r % 6];
     }
     if (transposed) tile[(c0 + c) * kTile + r0 + r] = val;
     else            tile[(r0 + r) * kTile + c0 + c] = val;
@@ -306,9 +314,9 @@ void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
   schur_syrk_kernel<<<st.n_items, 128, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
 }
 
-void launch_schur_reduce(const SchurStructure& st, NormalEq ne, double* S, const int* tile_slot, int n_tiles,
-                         cudaStream_t s) {
-  if (st.n_pairs > 0) schur_reduce_kernel<<<dim3(st.n_pairs, 3), 256, 0, s>>>(st, ne, S, tile_slot, n_tiles);
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, double* S,
+                         const int* tile_slot, int n_tiles, cudaStream_t s) {
+  if (st.n_pairs > 0) schur_reduce_kernel<<<dim3(st.n_pairs, 3), 256, 0, s>>>(st, ne, pv, S, tile_slot, n_tiles);
 }
 
 void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,

@@ -98,14 +98,17 @@ void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const dou
                          int n_frames, NormalEq ne, bool with_wf, cudaStream_t s);
 void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, cudaStream_t s);
 void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s);
+// adds the priors' J^T J / J^T r to B, gc, diagB and writes the frame-to-previous-frame couplings
+void launch_prior_blocks(const PriorView& pv, NormalEq ne, int n_frames, cudaStream_t s);
+
 // Schur complement (k2_schur.cu).  S is tile-packed (see TileSchedule: structurally non-zero lower
 // tiles, diagonal tiles stored as full squares); rhs/d2_c in the permuted order given by tile_pos.
 void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
                       cudaStream_t s);
 void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s);
 // writes the UNSCALED tiles  B - Phi Phi^T  (partial sums on a multi-GPU rank)
-void launch_schur_reduce(const SchurStructure& st, NormalEq ne, double* S, const int* tile_slot, int n_tiles,
-                         cudaStream_t s);
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, double* S,
+                         const int* tile_slot, int n_tiles, cudaStream_t s);
 // after the (optional) all-reduce: Jacobi scaling, LM diagonal, constant rows, padding; d2_c and rhs
 struct TileSchedule;
 void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,

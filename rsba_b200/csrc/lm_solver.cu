@@ -147,6 +147,10 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
         obs_phi_off[pt_obs[slot_beg[(size_t)i * kSubFrames + fs]]] = i * kPanelDoubles + fs * kFrameParams;
   }
   for (int t = 0; t < Hreal; ++t) pe.push_back({(long)t * H + t, -1, -1});   // every diagonal sub-tile is a pair
+  for (const auto& pr : h->priors) {                                           // ... and every prior coupling
+    const int a = std::min(pr.frame, pr.prev) / kSubFrames, b = std::max(pr.frame, pr.prev) / kSubFrames;
+    pe.push_back({(long)a * H + b, -1, -1});
+  }
   std::stable_sort(pe.begin(), pe.end(), [](const PairEntry& x, const PairEntry& y) { return x.key < y.key; });
   std::vector<int> pair_a, pair_b, pair_item_ptr;
   std::vector<int4> items;
@@ -202,6 +206,10 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
           if (tiles.empty() || tiles.back() != gtile[e]) tiles.push_back(gtile[e]);
         for (size_t x = 0; x < tiles.size(); ++x)
           for (size_t y = x; y < tiles.size(); ++y) seen[(size_t)tiles[x] * T + tiles[y]] = 1;
+      }
+      for (const auto& pr : h->priors) {
+        const int a = std::min(pr.frame, pr.prev) / kFramesPerTile, b = std::max(pr.frame, pr.prev) / kFramesPerTile;
+        seen[(size_t)a * T + b] = 1;
       }
       for (int a = 0; a < T; ++a)
         for (int b = a; b < T; ++b)
@@ -336,6 +344,11 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   launch_frame_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_frames, lm->ne, true, s);
   stage_end(h, kStageFrameBlocks);
   h->launches += 3;
+  const PriorView pv = h->prior_view();
+  if (pv.n > 0 && h->rank == 0) {   // camera-only residual blocks: added once, not sharded
+    launch_prior_blocks(pv, lm->ne, h->n_frames, s);
+    h->launches += 1;
+  }
   launch_clear_tiles(lm->S.ptr, lm->ts, s);
   stage_begin(h, kStagePhiBuild);
   launch_phi_build(lm->st, obs, h->d_jac.ptr, lm->ne, s);
@@ -344,7 +357,9 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   launch_schur_syrk(lm->st, lm->ne, s);
   stage_end(h, kStageSchurSyrk);
   stage_begin(h, kStageSchurReduce);
-  launch_schur_reduce(lm->st, lm->ne, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
+  PriorView pvr = pv;
+  if (h->rank != 0) pvr.n = 0;
+  launch_schur_reduce(lm->st, lm->ne, pvr, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
   stage_end(h, kStageSchurReduce);
   h->launches += 4;
   if (new_jacobian) {   // scalars of the current point that ride in the same buffer
@@ -472,7 +487,9 @@ int prepare_solve(rsba_problem* h, const rsba_solve_options* opt) {
   }
   if (!h->scene_set) return fail(RSBA_ERR_STATE, "no residual blocks");
   if (!h->params_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_parameters has not been called");
-  int rc = ensure_eval_buffers(h, true);
+  int rc = upload_priors(h);
+  if (rc) return rc;
+  rc = ensure_eval_buffers(h, true);
   if (rc) return rc;
   h->reorder_tiles = opt->reorder_tiles != 0;
   return ensure_lm(h, opt->dense_cholesky != 0);

@@ -112,8 +112,16 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
   } else {
     launch_k1r(h->cm, h->obs_view(), poses, points, h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
   }
-  launch_reduce_partials(h->d_cost_partials.ptr, k1_num_partials(h->n_obs), h->d_scalars.ptr,
-                         h->stream);
+  // the priors' cost rides in the extra partial slot (rank 0 only: they are not sharded)
+  const int np = k1_num_partials(h->n_obs);
+  const PriorView pv = h->prior_view();
+  if (pv.n > 0 && h->rank == 0) {
+    launch_prior_eval(pv, poses, h->cm.huber, h->d_cost_partials.ptr + np, jac, h->stream);
+    h->launches += 1;
+  } else {
+    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np, 0, sizeof(double), h->stream));
+  }
+  launch_reduce_partials(h->d_cost_partials.ptr, np + 1, h->d_scalars.ptr, h->stream);
   stage_end(h, st);
   h->launches += 2;
   RSBA_CUDA_TRY(cudaGetLastError());
@@ -235,6 +243,70 @@ static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr
   return RSBA_OK;
 }
 
+// Closed-form coefficients of the two functors with a constant interFrameRatio
+// (video_bundler_rs_inter.h:69-84 velocity, :127-148 acceleration); block order pose0, end0, pose1, end1.
+static void prior_coefficients(int kind, double r, double c[8]) {
+  if (kind == 1) {
+    c[0] = 1.0; c[1] = 0.0; c[2] = r; c[3] = -(1.0 + r);
+    if (r > 2.220446049250313e-16) { c[4] = -(1.0 + 1.0 / r); c[5] = 1.0; c[6] = 0.0; c[7] = 1.0 / r; }
+    else                           { c[4] = -1.0; c[5] = 1.0; c[6] = 1.0; c[7] = -1.0; }
+  } else {
+    c[0] = 0.5; c[1] = 0.0; c[2] = 0.5 * r; c[3] = -0.5 * (1.0 + r);
+    c[4] = -0.5 * (1.0 + 1.0 / r); c[5] = 0.5; c[6] = 0.0; c[7] = 0.5 / r;
+  }
+}
+
+int upload_priors(rsba_problem* h) {
+  if (!h->priors_dirty) return RSBA_OK;
+  const int n = (int)h->priors.size(), F = h->n_frames;
+  std::vector<int> frame(std::max(n, 1)), prev(std::max(n, 1)), cur_of(std::max(F, 1), -1), prev_of(std::max(F, 1), -1);
+  std::vector<double> coef(8 * (size_t)std::max(n, 1)), scale(std::max(n, 1));
+  for (int i = 0; i < n; ++i) {
+    const auto& p = h->priors[i];
+    if (p.frame < 0 || p.frame >= F || p.prev < 0 || p.prev >= F || p.frame == p.prev)
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "motion prior: frame index out of range");
+    if (cur_of[p.frame] >= 0) return fail(RSBA_ERR_INVALID_ARGUMENT, "motion prior: a frame has two priors");
+    if (prev_of[p.prev] >= 0) return fail(RSBA_ERR_INVALID_ARGUMENT, "motion prior: a frame precedes two priors");
+    cur_of[p.frame] = i;
+    prev_of[p.prev] = i;
+    frame[i] = p.frame;
+    prev[i] = p.prev;
+    scale[i] = p.scale;
+    prior_coefficients(p.kind, p.ratio, &coef[8 * (size_t)i]);
+  }
+  auto up = [&](auto& dev, const auto& host) -> cudaError_t {
+    cudaError_t e = dev.resize(host.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(dev.ptr, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, h->stream);
+  };
+  RSBA_CUDA_TRY(up(h->d_prior_frame, frame));
+  RSBA_CUDA_TRY(up(h->d_prior_prev, prev));
+  RSBA_CUDA_TRY(up(h->d_prior_cur_of, cur_of));
+  RSBA_CUDA_TRY(up(h->d_prior_prev_of, prev_of));
+  RSBA_CUDA_TRY(up(h->d_prior_coef, coef));
+  RSBA_CUDA_TRY(up(h->d_prior_scale, scale));
+  RSBA_CUDA_TRY(h->d_prior_r.resize(12 * (size_t)std::max(n, 1)));
+  RSBA_CUDA_TRY(h->d_prior_w2.resize(std::max(n, 1)));
+  RSBA_CUDA_TRY(h->d_prior_Bx.resize(24 * (size_t)std::max(F, 1)));
+  RSBA_CUDA_TRY(cudaMemsetAsync(h->d_prior_Bx.ptr, 0, h->d_prior_Bx.bytes(), h->stream));
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->priors_dirty = false;
+  if (h->lm) {   // the priors add structurally non-zero tile pairs
+    lm_state_free(h->lm);
+    h->lm = nullptr;
+  }
+  return RSBA_OK;
+}
+
+static int check_prior_args(int kind, double scale, double ratio) {
+  if (kind != 1 && kind != 2) return fail(RSBA_ERR_INVALID_ARGUMENT, "motion prior kind must be 1 (velocity) or 2 (acceleration)");
+  if (!(scale > 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "motion prior scale must be positive");
+  // the functors return false below these bounds (video_bundler_rs_inter.h:92, 156)
+  if (kind == 1 && !(ratio >= 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "velocity prior needs interFrameRatio >= 0");
+  if (kind == 2 && !(ratio >= 2.220446049250313e-16)) return fail(RSBA_ERR_INVALID_ARGUMENT, "acceleration prior needs interFrameRatio >= eps");
+  return RSBA_OK;
+}
+
 int finalize_pointer_problem(rsba_problem* h) {
   if (!h->ptr_mode || !h->ptr_dirty) return RSBA_OK;
   const long n = (long)h->ptr_obs.size();
@@ -254,7 +326,8 @@ int finalize_pointer_problem(rsba_problem* h) {
   h->pose_mask.resize(h->n_frames, 0);
   h->point_const.resize(h->n_points, 0);
   h->ptr_dirty = false;
-  return RSBA_OK;
+  h->priors_dirty = true;
+  return upload_priors(h);
 }
 
 int gather_pointer_parameters(rsba_problem* h) {
@@ -404,27 +477,75 @@ int rsba_cuda_set_loss(rsba_problem* h, double huber_a) {
   return RSBA_OK;
 }
 
-int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0, double* pose1,
-                              double* point) {
-  if (!h || !observed || !pose0 || !pose1 || !point) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
-  if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
-  h->ptr_mode = true;
-  int f;
+// pointer API: the frame made of the two control-pose blocks (registered on first sight); < 0 = error
+static int frame_of_blocks(rsba_problem* h, double* pose0, double* pose1) {
   auto it = h->pose0_to_frame.find(pose0);
   if (it == h->pose0_to_frame.end()) {
     if (h->pose1_to_frame.count(pose1) || h->pose0_to_frame.count(pose1) || h->pose1_to_frame.count(pose0))
       return fail(RSBA_ERR_INVALID_ARGUMENT, "pose block already paired with a different frame");
-    f = (int)h->frame_pose0.size();
+    const int f = (int)h->frame_pose0.size();
     h->pose0_to_frame[pose0] = f;
     h->pose1_to_frame[pose1] = f;
     h->frame_pose0.push_back(pose0);
     h->frame_pose1.push_back(pose1);
     h->ptr_pose_mask.push_back(0);
-  } else {
-    f = it->second;
-    if (h->frame_pose1[f] != pose1)
-      return fail(RSBA_ERR_INVALID_ARGUMENT, "pose0 block already paired with a different pose1 block");
+    return f;
   }
+  if (h->frame_pose1[it->second] != pose1)
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "pose0 block already paired with a different pose1 block");
+  return it->second;
+}
+
+int rsba_cuda_add_motion_prior(rsba_problem* h, int kind, double scale, double inter_frame_ratio, double* pose0,
+                               double* end0, double* pose1, double* end1) {
+  if (!h || !pose0 || !end0 || !pose1 || !end1) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
+  int rc = check_prior_args(kind, scale, inter_frame_ratio);
+  if (rc) return rc;
+  h->ptr_mode = true;
+  const int prev = frame_of_blocks(h, pose1, end1);
+  if (prev < 0) return prev;
+  const int cur = frame_of_blocks(h, pose0, end0);
+  if (cur < 0) return cur;
+  h->priors.push_back({kind, scale, inter_frame_ratio, cur, prev});
+  h->priors_dirty = true;
+  h->ptr_dirty = true;
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_motion_priors(rsba_problem* h, int n, const int* kind, const double* scale,
+                                const double* inter_frame_ratio, const int* frame, const int* prev_frame) {
+  if (!h || n < 0 || (n > 0 && (!kind || !scale || !inter_frame_ratio || !frame || !prev_frame)))
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "bad prior arguments");
+  if (h->ptr_mode) return fail(RSBA_ERR_STATE, "handle holds pointer-API blocks: use rsba_cuda_add_motion_prior");
+  if (!h->scene_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_scene first");
+  for (int i = 0; i < n; ++i) {
+    int rc = check_prior_args(kind[i], scale[i], inter_frame_ratio[i]);
+    if (rc) return rc;
+  }
+  h->priors.clear();
+  for (int i = 0; i < n; ++i) h->priors.push_back({kind[i], scale[i], inter_frame_ratio[i], frame[i], prev_frame[i]});
+  h->priors_dirty = true;
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  return upload_priors(h);
+}
+
+long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals) {
+  if (!h) return -1;
+  const long n = h->priors_dirty ? 0 : (long)h->priors.size();
+  if (residuals && n > 0) {
+    if (cudaMemcpy(residuals, h->d_prior_r.ptr, 12 * n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  }
+  return n;
+}
+
+int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0, double* pose1,
+                              double* point) {
+  if (!h || !observed || !pose0 || !pose1 || !point) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
+  h->ptr_mode = true;
+  const int f = frame_of_blocks(h, pose0, pose1);
+  if (f < 0) return f;
   int p;
   auto ip = h->point_to_id.find(point);
   if (ip == h->point_to_id.end()) {
@@ -481,6 +602,9 @@ int rsba_cuda_set_scene(rsba_problem* h, long n_obs, const double* obs_xy, const
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   int rc = upload_scene(h, n_obs, obs_xy, obs_frame, obs_point, n_frames, n_points);
   if (rc) return rc;
+  h->priors.clear();
+  h->priors_dirty = true;
+  if ((rc = upload_priors(h))) return rc;
   h->pose_mask.assign(n_frames, 0);
   h->point_const.assign(n_points, 0);
   if (const_pose_mask) for (int f = 0; f < n_frames; ++f) h->pose_mask[f] = const_pose_mask[f] & 0xFFF;
@@ -524,7 +648,7 @@ static int prepare(rsba_problem* h) {
   }
   if (!h->scene_set) return fail(RSBA_ERR_STATE, "no residual blocks");
   if (!h->params_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_parameters has not been called");
-  return RSBA_OK;
+  return upload_priors(h);
 }
 
 int rsba_cuda_evaluate_device(rsba_problem* h, int with_jacobian, double* cost, long* num_invalid) {

@@ -102,6 +102,21 @@ struct rsba_problem {
   rsba::DeviceBuffer<double> d_scalars;    // [0] cost, misc
   rsba::DeviceBuffer<int> d_invalid;
 
+  // ---- camera-only motion priors (k2_priors.cu)
+  struct PriorHost { int kind; double scale, ratio; int frame, prev; };
+  std::vector<PriorHost> priors;           // frame indices of the finalised scene
+  bool priors_dirty = false;
+  rsba::DeviceBuffer<int> d_prior_frame, d_prior_prev, d_prior_cur_of, d_prior_prev_of;
+  rsba::DeviceBuffer<double> d_prior_coef, d_prior_scale, d_prior_r, d_prior_w2, d_prior_Bx;
+  rsba::PriorView prior_view() const {
+    rsba::PriorView v{};
+    v.n = priors_dirty ? 0 : (int)priors.size();
+    v.frame = d_prior_frame.ptr; v.prev = d_prior_prev.ptr; v.coef = d_prior_coef.ptr; v.scale = d_prior_scale.ptr;
+    v.cur_of = d_prior_cur_of.ptr; v.prev_of = d_prior_prev_of.ptr; v.r = d_prior_r.ptr; v.w2 = d_prior_w2.ptr;
+    v.Bx = d_prior_Bx.ptr;
+    return v;
+  }
+
   rsba::StageTimer timers[rsba::kNumStages];
   long launches = 0;
 
@@ -129,6 +144,7 @@ int materialize_local_share(rsba_problem* h);     // g_* -> this rank's observat
 void compute_point_owners(int n_frames, int n_points, long n_obs, const int* obs_frame_sorted,
                           const int* obs_point, int world, std::vector<int>* owner);
 int allreduce_sum(rsba_problem* h, double* buf, size_t count);   // in place, on the handle's stream
+int upload_priors(rsba_problem* h);               // host prior list -> device (after the scene is final)
 int finalize_pointer_problem(rsba_problem* h);   // pointer API -> sorted SoA on device
 int gather_pointer_parameters(rsba_problem* h);  // caller blocks -> device
 int scatter_pointer_parameters(rsba_problem* h); // device -> caller blocks

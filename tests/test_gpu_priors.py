@@ -1,0 +1,147 @@
+"""GPU parity for the camera-only motion priors (RsConstVeloPrior /
+RsConstAccelerationPrior, video_bundler_rs_inter.h:55-173, wired at CeresHandler.h:148-186) with a
+constant interFrameRatio: cost, residuals, the LM step with the priors' J^T J in the camera blocks
+and the frame-to-previous-frame couplings of the reduced system, and full solves."""
+import numpy as np
+import pytest
+
+from rsba_b200.scene import make_scene
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def api():
+    import rsba_b200.api as api
+    api.load_library()
+    return api
+
+
+@pytest.fixture(scope="module")
+def lo(oracle_built):
+    from oracle import lm_oracle
+    return lm_oracle
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def chain_priors(sc, kind, scale, ratio, first=1):
+    return [(kind, scale, ratio, k, k - 1) for k in range(first, sc.num_frames)]
+
+
+def load_with_priors(api, pb, sc, priors, huber=0.0):
+    pb.load_scene(sc)
+    pb.set_motion_priors([p[0] for p in priors], [p[1] for p in priors], [p[2] for p in priors],
+                         [p[3] for p in priors], [p[4] for p in priors])
+    if huber:
+        pb.set_loss(huber)
+
+
+@pytest.mark.parametrize("kind,scale,ratio", [(1, 5.0, 0.9), (2, 20.0, 1.3), (1, 3.0, 0.0)])
+def test_prior_cost_and_residuals(api, oracle_built, kind, scale, ratio):
+    sc = make_scene(20, 600, 8, name="priors")
+    priors = chain_priors(sc, kind, scale, ratio)
+    r0, _, _ = oracle_built.evaluate(sc, impl="port", jac=False)
+    _, rx, cost_x = oracle_built.motion_prior_rows(sc, priors)
+    with api.Problem(0) as pb:
+        load_with_priors(api, pb, sc, priors)
+        cost, r, J, v = pb.evaluate()
+        got = pb.prior_residuals()
+        c2, _ = pb.evaluate_device(with_jacobian=False)
+    want = 0.5 * np.sum(r0 * r0) + cost_x
+    assert abs(cost - want) <= 1e-12 * want and c2 == cost
+    assert np.abs(got.reshape(-1) - rx).max() <= 1e-12 * max(1.0, np.abs(rx).max())
+    if oracle_built.ref_available():          # and against the reference functor itself
+        ok, r_ref, _, _ = oracle_built.motion_prior_eval_ref(kind, scale, ratio, sc.poses[5], sc.poses[4])
+        assert ok and np.abs(got[4] - r_ref).max() <= 1e-12 * max(1.0, np.abs(r_ref).max())
+
+
+@pytest.mark.parametrize("kind,scale,ratio", [(1, 5.0, 0.9), (2, 20.0, 1.3)])
+def test_lm_step_with_priors(api, oracle_built, lo, kind, scale, ratio):
+    sc = make_scene(40, 1500, 8, name="priors-band")      # 5 Cholesky tiles: couplings cross tile borders
+    priors = chain_priors(sc, kind, scale, ratio)
+    r, J, v = oracle_built.evaluate(sc, impl="port")
+    Jx, rx, _ = oracle_built.motion_prior_rows(sc, priors)
+    want = lo.lm_step(sc, r, J, 1e3, extra=(Jx, rx))
+    plain = lo.lm_step(sc, r, J, 1e3)
+    assert relerr(plain["delta_poses"], want["delta_poses"]) > 1e-3      # the priors matter
+    for kw in (dict(), dict(reorder_tiles=0), dict(dense_cholesky=1)):
+        with api.Problem(0) as pb:
+            load_with_priors(api, pb, sc, priors)
+            got = pb.linearize_and_step(1e3, api.default_options(**kw))
+        assert relerr(got["S"], want["S"]) <= TOL
+        assert relerr(got["rhs"], want["rhs"]) <= TOL
+        assert relerr(got["delta_poses"], want["delta_poses"]) <= TOL
+        assert relerr(got["delta_points"], want["delta_points"]) <= TOL
+        assert abs(got["model_cost_change"] - want["model_cost_change"]) <= TOL * abs(want["model_cost_change"])
+
+
+def test_lm_step_priors_with_constant_blocks_and_huber(api, oracle_built, lo):
+    sc = make_scene(20, 600, 8, name="priors-masks")
+    priors = chain_priors(sc, 1, 8.0, 0.8, first=2)        # frame 1 has no prior; frame 0 constant
+    mask = np.zeros(sc.num_frames, dtype=np.uint16)
+    mask[0] = 0xFFF
+    mask[1] = 0xFFF                                         # CeresHandler.h:182-186 fixes the predecessor too
+    mask[7] = 0b000111 | (0b000111 << 6)
+    a = 1.5
+    r, J, v = oracle_built.evaluate(sc, impl="port")
+    rw, Jw, _ = oracle_built.apply_huber(r, J, a)
+    Jx, rx, _ = oracle_built.motion_prior_rows(sc, priors, huber=a)
+    want = lo.lm_step(sc, rw, Jw, 1e2, pose_mask=mask, extra=(Jx, rx))
+    with api.Problem(0) as pb:
+        pb.set_camera(sc.cam, sc.shutter, sc.scanlines, sc.interpolate_rotation)
+        pb.set_scene(sc.obs_xy, sc.obs_frame, sc.obs_point, sc.num_frames, sc.num_points, mask)
+        pb.set_parameters(sc.poses, sc.points)
+        pb.set_motion_priors([p[0] for p in priors], [p[1] for p in priors], [p[2] for p in priors],
+                             [p[3] for p in priors], [p[4] for p in priors])
+        pb.set_loss(a)
+        got = pb.linearize_and_step(1e2)
+    for k in ("S", "rhs", "delta_poses", "delta_points"):
+        assert relerr(got[k], want[k]) <= TOL, k
+    assert not got["delta_poses"][0].any() and not got["delta_poses"][1].any()
+
+
+def test_solve_with_priors_bulk_and_pointer_api(api, oracle_built):
+    sc = make_scene(16, 400, 8, name="priors-solve")
+    priors = chain_priors(sc, 2, 10.0, 1.2)
+    with api.Problem(0) as pb:
+        load_with_priors(api, pb, sc, priors)
+        s = pb.solve(api.default_options(max_num_iterations=12))
+        po, pt = pb.get_parameters()
+    assert s.usable == 1 and s.final_cost < s.initial_cost
+    r1, _, _ = oracle_built.evaluate(sc, po, pt, jac=False, impl="port")
+    _, _, cx = oracle_built.motion_prior_rows(sc, priors, poses=po)
+    want = 0.5 * np.sum(r1 * r1) + cx
+    assert abs(s.final_cost - want) <= 1e-9 * want
+    # pointer API: AddResidualBlock order of CeresHandler::Add -- prior first, then the observations
+    poses, points = sc.poses.copy(), sc.points.copy()
+    with api.Problem(0) as pb:
+        pb.set_camera(sc.cam, sc.shutter, sc.scanlines, sc.interpolate_rotation)
+        for f in range(sc.num_frames):
+            if f > 0:
+                pb.add_motion_prior(2, 10.0, 1.2, poses[f, :6], poses[f, 6:], poses[f - 1, :6], poses[f - 1, 6:])
+            for i in np.flatnonzero(sc.obs_frame == f):
+                pb.add_rs_residual(sc.obs_xy[i], poses[f, :6], poses[f, 6:], points[int(sc.obs_point[i])])
+        pb.set_block_constant(poses[0, :6])
+        pb.set_block_constant(poses[0, 6:])
+        s2 = pb.solve(api.default_options(max_num_iterations=12))
+    assert abs(s2.final_cost - s.final_cost) <= 1e-9 * s.final_cost
+    assert relerr(poses, po) <= 1e-7
+
+
+def test_prior_argument_checks(api):
+    sc = make_scene(6, 100, 5, name="priors-args")
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        with pytest.raises(api.RsbaError):
+            pb.set_motion_priors([1], [1.0], [-0.5], [1], [0])      # functor would return false
+        with pytest.raises(api.RsbaError):
+            pb.set_motion_priors([2], [1.0], [0.0], [1], [0])
+        with pytest.raises(api.RsbaError):
+            pb.set_motion_priors([1, 1], [1.0, 1.0], [1.0, 1.0], [2, 2], [1, 0])   # two priors on one frame
+        pb.set_motion_priors([], [], [], [], [])
+        cost, _ = pb.evaluate_device(with_jacobian=False)
+        assert cost > 0

@@ -1,0 +1,35 @@
+"""Camera-only motion priors: the closed form used on the device
+(oracle.motion_prior_coefficients) against the reference's own functors compiled verbatim
+(RsConstVeloPrior / RsConstAccelerationPrior, video_bundler_rs_inter.h:55-173) under Jet autodiff."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("ratio", [1.0, 0.7, 2.5, 1e-3])
+def test_closed_form_matches_reference_functor(oracle_built, kind, ratio):
+    if not oracle_built.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(int(ratio * 1000) + kind)
+    for _ in range(5):
+        fk, fp = rng.normal(0, 0.3, 12), rng.normal(0, 0.3, 12)
+        scale = float(rng.uniform(0.1, 30.0))
+        ok, r_ref, J_ref, _ = oracle_built.motion_prior_eval_ref(kind, scale, ratio, fk, fp)
+        r, J = oracle_built.motion_prior_eval(kind, scale, ratio, fk, fp)
+        assert ok
+        assert np.abs(r - r_ref).max() <= 1e-12 * max(1.0, np.abs(r_ref).max())
+        assert np.abs(J - J_ref).max() <= 1e-12 * np.abs(J_ref).max()
+
+
+def test_velocity_prior_at_zero_ratio_uses_the_previous_velocity(oracle_built):
+    """interFrameRatio <= eps switches the second half to (end1 - pose1) (video_bundler_rs_inter.h:78-82)."""
+    if not oracle_built.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    fk, fp = rng.normal(0, 0.3, 12), rng.normal(0, 0.3, 12)
+    ok, r_ref, J_ref, _ = oracle_built.motion_prior_eval_ref(1, 2.0, 0.0, fk, fp)
+    r, J = oracle_built.motion_prior_eval(1, 2.0, 0.0, fk, fp)
+    assert ok and np.allclose(r, r_ref, rtol=0, atol=1e-13) and np.allclose(J, J_ref, rtol=0, atol=1e-13)
+    # the functors' validity: velocity needs ratio >= 0, acceleration ratio >= eps
+    assert not oracle_built.motion_prior_eval_ref(1, 2.0, -0.1, fk, fp)[0]
+    assert not oracle_built.motion_prior_eval_ref(2, 2.0, 0.0, fk, fp)[0]

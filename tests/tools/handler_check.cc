@@ -29,7 +29,7 @@ struct Session {
 struct Options {
   struct { bool use3Dpoints = true, calibrated = true, constVelocity = false, interpolateRotation = true; } model;
   struct {
-    double huberLoss = 0, constFrameVelocity = 0, constFrameAcceleration = 0;
+    double huberLoss = 0, constFrameVelocity = 0, constFrameAcceleration = 0, interFrameRatio = 1;
     bool const3d = false, fixScale = false, fixRotation = false, fixPosition = false, useOnlyValidMatches = false;
     unsigned fixFirstNCameras = 1;
   } ceres;
