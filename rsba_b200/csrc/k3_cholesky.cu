@@ -65,7 +65,8 @@ __device__ __forceinline__ void smem_gemm(double* C, const double* A, const doub
 // One CTA (8 warps) per panel of the level.  Right-looking, 8-column blocks:
 //   (i)   the 8x8 diagonal block is factorised by warp 0 in registers (one row per lane, shuffles)
 //   (ii)  the rows below solve against it (one thread per row, reciprocal pivots)
-//   (iii) the trailing lower triangle is updated with DMMA (K = 8)
+//   (iii) the trailing lower triangle is updated with DMMA (K = 8); warp 0 takes the next diagonal
+//         block first and runs its step (i) while the other warps finish the update (look-ahead)
 // then L^-1 by recursive doubling (8 -> 16 -> 32 -> 96; every level is a pair of small DMMA GEMMs),
 // so that trsm and the triangular solves are GEMM / GEMV and not substitution chains.
 constexpr size_t kPotrfSmem = (size_t)(2 * kTile * kLd + 3 * 32 * kLd + kTile) * sizeof(double);
@@ -91,32 +92,34 @@ potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int 
   }
   __syncthreads();
 
+  // (i) 8x8 diagonal block at offset o, in registers: lane l < 8 owns row l (warp 0 only)
+  auto potrf8 = [&](int o) {
+    const int l = lane & 7;
+    double a[8];   // lanes >= 8 only take part in the shuffles (sources are always lanes < 8)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = lane < 8 ? A[(o + l) * kLd + o + c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double d = __shfl_sync(0xffffffffu, a[j], j);
+      if (lane == 0 && !(d > 0.0)) atomicExch(info, k * kTile + o + j + 1);
+      const double rs = rsqrt(d);
+      const double lj = (l == j) ? d * rs : a[j] * rs;   // column j of L (rows >= j are meaningful)
+      a[j] = lj;
+      if (lane == 0) rdiag[o + j] = rs;
+#pragma unroll
+      for (int c = j + 1; c < 8; ++c) a[c] -= lj * __shfl_sync(0xffffffffu, lj, c);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c <= l) A[(o + l) * kLd + o + c] = a[c];
+    }
+  };
+  if (warp == 0) potrf8(0);
+  __syncthreads();
+
   for (int I = 0; I < kTile / 8; ++I) {
     const int o = 8 * I;
-    // ---- (i) 8x8 diagonal block in registers: lane l < 8 owns row l
-    if (warp == 0) {
-      const int l = lane & 7;
-      double a[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = A[(o + l) * kLd + o + c];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (lane == 0 && !(d > 0.0)) atomicExch(info, k * kTile + o + j + 1);
-        const double rs = 1.0 / sqrt(d);
-        const double lj = (l == j) ? d * rs : a[j] * rs;   // column j of L (rows >= j are meaningful)
-        a[j] = lj;
-        if (lane == 0) rdiag[o + j] = rs;
-#pragma unroll
-        for (int c = j + 1; c < 8; ++c) a[c] -= lj * __shfl_sync(0xffffffffu, lj, c);
-      }
-      if (lane < 8) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c <= l) A[(o + l) * kLd + o + c] = a[c];
-      }
-    }
-    __syncthreads();
     // ---- (ii) rows below: x L8^T = a, one thread per row
     const int nrem = kTile - o - 8;
     if (tid < nrem) {
@@ -133,26 +136,39 @@ potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int 
       for (int j = 0; j < 8; ++j) row[j] = x[j];
     }
     __syncthreads();
-    // ---- (iii) trailing lower block triangle: A22 -= P P^T  (K = 8), DMMA
+    // ---- (iii) trailing lower block triangle: A22 -= P P^T  (K = 8), DMMA.  Look-ahead: warp 0
+    // updates the next diagonal block and factorises it straight away while warps 1..7 update the
+    // rest, so the serial 8x8 factorisation is off the critical path.
     {
       const int nb = nrem >> 3, fr = lane >> 2, fc = lane & 3;
       const double* Pm = A + (o + 8) * kLd + o;
       double* C22 = A + (o + 8) * kLd + o + 8;
-      int bi = 0, bj = 0;
-      // warp-strided walk over the lower block triangle (bi >= bj), row-major linear order
-      for (int blk = 0, mine = warp; bi < nb; ++blk) {
-        if (blk == mine) {
-          double c0 = 0.0, c1 = 0.0;
-          const double* ap = Pm + (8 * bi + fr) * kLd + fc;
-          const double* bp = Pm + (8 * bj + fr) * kLd + fc;
-          dmma(c0, c1, ap[0], bp[0]);
-          dmma(c0, c1, ap[4], bp[4]);
-          double* cp = C22 + (8 * bi + fr) * kLd + 8 * bj + 2 * fc;
-          cp[0] -= c0;
-          cp[1] -= c1;
-          mine += 8;
+      auto update_block = [&](int bi, int bj) {
+        double c0 = 0.0, c1 = 0.0;
+        const double* ap = Pm + (8 * bi + fr) * kLd + fc;
+        const double* bp = Pm + (8 * bj + fr) * kLd + fc;
+        dmma(c0, c1, ap[0], bp[0]);
+        dmma(c0, c1, ap[4], bp[4]);
+        double* cp = C22 + (8 * bi + fr) * kLd + 8 * bj + 2 * fc;
+        cp[0] -= c0;
+        cp[1] -= c1;
+      };
+      if (warp == 0) {
+        if (nb > 0) {
+          update_block(0, 0);
+          __syncwarp();
+          potrf8(o + 8);
         }
-        if (++bj > bi) { bj = 0; ++bi; }
+      } else {
+        // warp-strided walk over the lower block triangle (bi >= bj) without block (0,0)
+        int bi = 1, bj = 0;
+        for (int blk = 0, mine = warp - 1; bi < nb; ++blk) {
+          if (blk == mine) {
+            update_block(bi, bj);
+            mine += 7;
+          }
+          if (++bj > bi) { bj = 0; ++bi; }
+        }
       }
     }
     __syncthreads();
