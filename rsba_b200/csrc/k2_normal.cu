@@ -214,46 +214,19 @@ frame_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ j
     }
     double* sJ = sJbuf + buf * kChunk * kJacDoubles;
     const double* sR = sRbuf + buf * kChunk * 2;
-    if (tid < cnt) {
-      double q0 = 0.0, q1 = 0.0;
-      const double* rec = sJ + tid * kJacDoubles;
-      if (with_wf) {
-        const int p = obs.point[beg + tid];
-        const double* t = ne.tp + 3L * p;
-        const double* jx = rec + 24;
-        q0 = jx[0] * t[0] + jx[1] * t[1] + jx[2] * t[2];
-        q1 = jx[3] * t[0] + jx[4] * t[1] + jx[5] * t[2];
-        // ---- Schur panel rows of this observation: F = Jc^T (Jx s_p) L^-T  (12 x 3), written straight
-        // into the point's (sub-tile, point) panel while the record is in shared memory (k2_schur.cu
-        // describes the layout; zero rows of unobserved frames were written once, at allocation)
-        const int off = st.obs_phi_off[beg + tid];
-        if (off >= 0) {
-          const double* Mi = ne.Minv + 6L * p;
-          const double m00 = Mi[0], m10 = Mi[1], m11 = Mi[2], m20 = Mi[3], m21 = Mi[4], m22 = Mi[5];
-          const double a0 = jx[0] * ne.scale_p[3L * p], a1 = jx[1] * ne.scale_p[3L * p + 1], a2 = jx[2] * ne.scale_p[3L * p + 2];
-          const double b0 = jx[3] * ne.scale_p[3L * p], b1 = jx[4] * ne.scale_p[3L * p + 1], b2 = jx[5] * ne.scale_p[3L * p + 2];
-          const double xa[3] = {a0 * m00, a0 * m10 + a1 * m11, a0 * m20 + a1 * m21 + a2 * m22};
-          const double xb[3] = {b0 * m00, b0 * m10 + b1 * m11, b0 * m20 + b1 * m21 + b2 * m22};
-          const unsigned mask = ne.pose_mask[st.chunk_frame[c]];
-          double* dst = ne.Phi + off;
+    // ---- phase 0: issue the per-point gathers of this chunk (point id -> t_p, L^-1, s_p, panel offset);
+    // they are consumed after the B / g_c accumulation below, which hides their latency
+    int pf_off = -1;
+    double pf_t[3] = {0.0, 0.0, 0.0}, pf_m[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, pf_s[3] = {0.0, 0.0, 0.0};
+    if (with_wf && tid < cnt) {
+      const int p = obs.point[beg + tid];
+      pf_off = st.obs_phi_off[beg + tid];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            double2* d2 = reinterpret_cast<double2*>(dst + k * kPanelLd);
+      for (int k = 0; k < 3; ++k) { pf_t[k] = ne.tp[3L * p + k]; pf_s[k] = ne.scale_p[3L * p + k]; }
 #pragma unroll
-            for (int a = 0; a < 12; a += 2) {
-              // camera columns a, a+1 of the record: rows 0/1 at jc offsets
-              const int o0 = (a < 6) ? a : 12 + (a - 6);
-              const double f0 = ((mask >> a) & 1) ? 0.0 : rec[o0] * xa[k] + rec[o0 + 6] * xb[k];
-              const double f1 = ((mask >> (a + 1)) & 1) ? 0.0 : rec[o0 + 1] * xa[k] + rec[o0 + 7] * xb[k];
-              d2[a >> 1] = make_double2(f0, f1);
-            }
-          }
-        }
-      }
-      sQ[2 * tid] = q0;
-      sQ[2 * tid + 1] = q1;
+      for (int k = 0; k < 6; ++k) pf_m[k] = ne.Minv[6L * p + k];
     }
-    __syncthreads();
+    // ---- phase 1: B_f and g_c partial sums (independent of the points)
     double acc[9], ga[3], wa[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.0;
@@ -270,9 +243,61 @@ frame_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ j
         acc[3] += a1 * b0; acc[4] += a1 * b1; acc[5] += a1 * b2;
         acc[6] += a2 * b0; acc[7] += a2 * b1; acc[8] += a2 * b2;
         if (tc == 0) {
-          const double r = sR[2 * o + row], q = sQ[2 * o + row];
+          const double r = sR[2 * o + row];
           ga[0] += a0 * r; ga[1] += a1 * r; ga[2] += a2 * r;
-          wa[0] += a0 * q; wa[1] += a1 * q; wa[2] += a2 * q;
+        }
+      }
+    }
+    // ---- phase 2: per observation  q = Jx t_p  and the Schur panel rows  F = Jc^T (Jx s_p) L^-T (12 x 3),
+    // written straight into the point's (sub-tile, point) panel while the record is in shared memory
+    // (k2_schur.cu describes the layout; zero rows of unobserved frames were written once, at allocation)
+    if (tid < cnt) {
+      double q0 = 0.0, q1 = 0.0;
+      const double* rec = sJ + tid * kJacDoubles;
+      if (with_wf) {
+        const double* jx = rec + 24;
+        q0 = jx[0] * pf_t[0] + jx[1] * pf_t[1] + jx[2] * pf_t[2];
+        q1 = jx[3] * pf_t[0] + jx[4] * pf_t[1] + jx[5] * pf_t[2];
+        if (pf_off >= 0) {
+          const double m00 = pf_m[0], m10 = pf_m[1], m11 = pf_m[2], m20 = pf_m[3], m21 = pf_m[4], m22 = pf_m[5];
+          const double a0 = jx[0] * pf_s[0], a1 = jx[1] * pf_s[1], a2 = jx[2] * pf_s[2];
+          const double b0 = jx[3] * pf_s[0], b1 = jx[4] * pf_s[1], b2 = jx[5] * pf_s[2];
+          const double xa[3] = {a0 * m00, a0 * m10 + a1 * m11, a0 * m20 + a1 * m21 + a2 * m22};
+          const double xb[3] = {b0 * m00, b0 * m10 + b1 * m11, b0 * m20 + b1 * m21 + b2 * m22};
+          const unsigned mask = ne.pose_mask[st.chunk_frame[c]];
+          double* dst = ne.Phi + pf_off;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double f[12];
+#pragma unroll
+            for (int a = 0; a < 12; ++a) {
+              // camera column a of the record: rows 0/1 at jc offsets
+              const int o0 = (a < 6) ? a : 12 + (a - 6);
+              f[a] = ((mask >> a) & 1) ? 0.0 : rec[o0] * xa[k] + rec[o0 + 6] * xb[k];
+            }
+            // the 96-byte row leaves as three full 32-byte sectors (256-bit stores, sm_100): 16-byte
+            // stores would double the number of L2 write transactions, which is what bounds this phase
+#pragma unroll
+            for (int a = 0; a < 12; a += 4)
+              asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * kPanelLd + a), "d"(f[a]),
+                           "d"(f[a + 1]), "d"(f[a + 2]), "d"(f[a + 3])
+                           : "memory");
+          }
+        }
+      }
+      sQ[2 * tid] = q0;
+      sQ[2 * tid + 1] = q1;
+    }
+    __syncthreads();
+    // ---- phase 3: w_f partial sums (need q)
+    if (tc == 0) {
+      for (int o = grp; o < cnt; o += kFrameGroups) {
+        const double* rec = sJ + o * kJacDoubles;
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+          const double* pa = rec + jc_off(tr, row);
+          const double q = sQ[2 * o + row];
+          wa[0] += pa[0] * q; wa[1] += pa[1] * q; wa[2] += pa[2] * q;
         }
       }
     }
