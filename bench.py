@@ -294,7 +294,8 @@ def run_ours(args):
     warm = max(args.warmup, 3)
 
     pb = api.Problem(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # not the legacy default stream: the library captures CUDA graphs
+    torch.cuda.set_stream(stream)
     pb.set_stream(stream.cuda_stream)
     if world > 1:
         import torch.distributed as dist

@@ -494,7 +494,7 @@ void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s) {
   if (ts.n_nz > 0) clear_tiles_kernel<<<ts.n_nz, 256, 0, s>>>(S);
 }
 
-int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s) {
+void k3_prepare() {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem);
@@ -502,6 +502,10 @@ int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan
     cudaFuncSetAttribute(tile_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem);
     attr_done = true;
   }
+}
+
+int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s) {
+  k3_prepare();
   int launches = 0;
   for (int l = 0; l < plan.n_levels; ++l) {
     const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];

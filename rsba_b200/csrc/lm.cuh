@@ -136,6 +136,7 @@ struct TileSchedule {      // device view of the TilePlan (tile_plan.cuh); tile 
   long n_real;              // 12 * frames (rows beyond it are identity padding)
 };
 
+void k3_prepare();   // one-off kernel attribute setup (call before capturing the launches in a graph)
 void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s);
 // return the number of kernel launches issued; info[0] != 0 on a non-positive pivot
 int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s);

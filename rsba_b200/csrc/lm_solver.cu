@@ -39,6 +39,16 @@ struct LmState {
   // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
   DeviceBuffer<double> solve_partials;
   DeviceBuffer<double> S, misc_local, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
+  // the launch sequences of the factorisation and of the triangular solves are static per scene:
+  // captured once into CUDA graphs, replayed every LM iteration (launch gaps matter here -- ~170
+  // short dependent kernels); nullptr = capture not available on this stream (legacy default stream)
+  cudaGraphExec_t graph_factor = nullptr, graph_solve = nullptr;
+  bool graph_tried = false;
+  int graph_factor_launches = 0, graph_solve_launches = 0;
+  ~LmState() {
+    if (graph_factor) cudaGraphExecDestroy(graph_factor);
+    if (graph_solve) cudaGraphExecDestroy(graph_solve);
+  }
   double* misc = nullptr;      // tail: [0] cost [1] invalid [2] |x_p|^2 ... [8 + r] max|g_p| of rank r
   size_t comm_count = 0;       // doubles in S + tail
   int misc_count = 0;
@@ -385,16 +395,49 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   return RSBA_OK;
 }
 
+// Capture `body` (a fixed sequence of launches on stream s) into an executable graph.
+template <typename F>
+cudaGraphExec_t capture_graph(cudaStream_t s, F body, int* launches) {
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  *launches = body();
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  if (cudaStreamEndCapture(s, &g) != cudaSuccess || !g) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) {
+    cudaGetLastError();
+    exec = nullptr;
+  }
+  cudaGraphDestroy(g);
+  return exec;
+}
+
 void factor_and_solve(rsba_problem* h, LmState* lm) {
   cudaStream_t s = h->stream;
+  if (!lm->graph_tried) {
+    lm->graph_tried = true;
+    k3_prepare();   // the kernels' one-off attribute setup stays outside the capture
+    lm->graph_factor = capture_graph(s, [&] { return launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->info.ptr, s); },
+                                     &lm->graph_factor_launches);
+    if (lm->graph_factor)
+      lm->graph_solve = capture_graph(s, [&] { return launch_tile_solve(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, s); },
+                                      &lm->graph_solve_launches);
+  }
   stage_begin(h, kStageCholesky);
   cudaMemsetAsync(lm->info.ptr, 0, sizeof(int), s);
   cudaMemcpyAsync(lm->y.ptr, lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToDevice, s);
   stage_begin(h, kStageFactor);
-  h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->info.ptr, s);
+  if (lm->graph_factor && cudaGraphLaunch(lm->graph_factor, s) == cudaSuccess) h->launches += lm->graph_factor_launches;
+  else h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->info.ptr, s);
   stage_end(h, kStageFactor);
   stage_begin(h, kStageTriSolve);
-  h->launches += launch_tile_solve(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, s);
+  if (lm->graph_solve && cudaGraphLaunch(lm->graph_solve, s) == cudaSuccess) h->launches += lm->graph_solve_launches;
+  else h->launches += launch_tile_solve(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, s);
   stage_end(h, kStageTriSolve);
   stage_end(h, kStageCholesky);
 }
