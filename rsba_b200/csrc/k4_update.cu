@@ -14,6 +14,7 @@ namespace rsba {
 namespace {
 
 constexpr int kRedThreads = 256;
+constexpr int kWideThreads = 1024;   // single-CTA reductions over 12 F / n_blocks values: latency-bound
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
 #pragma unroll
@@ -40,7 +41,7 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
 }
 
 // frames: delta_c, trial poses, partial scalars -> scratch[0..2] (single CTA)
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kWideThreads)
 frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* __restrict__ y, int n,
                   const double* __restrict__ poses, double* __restrict__ delta_c, double* __restrict__ trial,
                   double* __restrict__ scratch) {
@@ -133,7 +134,7 @@ point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
 }
 
 // final: scalars[0..2] = frame part, scalars[8..10] = sum of point partials (fixed order)
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kWideThreads)
 step_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __restrict__ scalars) {
   __shared__ double sh[32];
   double a = 0.0, b = 0.0, c = 0.0;
@@ -187,7 +188,7 @@ point_norms_final_kernel(const double* __restrict__ scratch, int n_blocks, doubl
 }
 
 // ... and camera part (single CTA; 12 F values)
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kWideThreads)
 camera_norms_kernel(NormalEq ne, int n_frames, const double* __restrict__ poses, double* __restrict__ scalars) {
   __shared__ double sh[32];
   double xx = 0.0, gm = 0.0;
@@ -211,11 +212,11 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
                         double* trial_points, double* scalars, double* scratch, cudaStream_t s) {
-  frame_step_kernel<<<1, kRedThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
+  frame_step_kernel<<<1, kWideThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
   const int nb = (n_points + kPointStepWarps - 1) / kPointStepWarps;
   if (nb > 0)
     point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, obs, jac, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
-  step_final_kernel<<<1, kRedThreads, 0, s>>>(scratch, nb, scalars);
+  step_final_kernel<<<1, kWideThreads, 0, s>>>(scratch, nb, scalars);
 }
 
 void launch_point_norms(NormalEq ne, int n_points, const double* points, double* out_xx, double* out_gmax,
@@ -225,7 +226,7 @@ void launch_point_norms(NormalEq ne, int n_points, const double* points, double*
 }
 
 void launch_camera_norms(NormalEq ne, int n_frames, const double* poses, double* scalars, cudaStream_t s) {
-  camera_norms_kernel<<<1, kRedThreads, 0, s>>>(ne, n_frames, poses, scalars);
+  camera_norms_kernel<<<1, kWideThreads, 0, s>>>(ne, n_frames, poses, scalars);
 }
 
 }  // namespace rsba

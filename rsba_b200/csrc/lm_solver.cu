@@ -82,7 +82,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   const std::vector<int>& fr = h->h_obs_frame;
   const std::vector<int>& pt = h->h_obs_point;
   cudaStream_t s = h->stream;
-  if ((long)F * F > (1L << 28)) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 16384 frames: pair index not implemented");
+  if (F > 65536) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 65536 frames: the tile index (T x T) would not fit; shard the sequence");
 
   // point-major CSR (stable counting sort: observation order inside a point is frame order)
   std::vector<int> pt_ptr(P + 1, 0), pt_obs(N);
