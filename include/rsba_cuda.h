@@ -224,6 +224,27 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
                                   int* panels, int* panel_ptr, int* trsm, int* trsm_ptr, int* upd,
                                   long* group_ptr, int* level_group_ptr);
 
+/* ------------------------------------------------------------------ batched RS-PnP */
+/* Replaces: the inner ceres::Solve of vision::solveRsPnP (solveRSpnp.cpp:100-192: RsBA<float> residual
+ * blocks <2; 6, 6> on the two control poses of one frame, 3-D points fixed, w2i without the
+ * in-front-of-camera test, max_num_iterations = 10) for ALL RANSAC hypotheses at once (pnpTask,
+ * solveRSpnp.cpp:265-335), and the inlier count each refined hypothesis is scored with
+ * (project3dPoints + |obs - proj| < reprojectionError, solveRSpnp.cpp:226-263, 318-323).
+ *   points3d[n][3], obs_xy[n][2]   the frame's 2-D/3-D correspondences (the reference passes them
+ *                                  through float; quantise before the call to reproduce that)
+ *   sample_idx[n_hyp][sample_size] the points of each hypothesis' minimal sample (sample_size <= 32)
+ *   poses[n_hyp][12]               in: initial pose0|pose1 (the reference starts every hypothesis from
+ *                                  the same guess); out: refined
+ *   options                        LM constants (max_num_iterations = 10 in the reference)
+ *   final_cost / usable / iterations / inlier_count [n_hyp]   HOST outputs, any may be NULL
+ * All arrays are HOST memory.  Larger point sets (the final refinement on all inliers, the const3d
+ * PnP-BA of VideoSfMHandler.cc:434-485) are a one-frame problem with constant points for rsba_cuda_solve. */
+int rsba_cuda_pnp_batch(rsba_problem* h, const double cam9[9], int shutter, const int scanlines[2],
+                        int n_points, const double* points3d, const double* obs_xy, int n_hyp,
+                        int sample_size, const int* sample_idx, double* poses,
+                        const rsba_solve_options* options, double inlier_threshold, double* final_cost,
+                        int* usable, int* iterations, int* inlier_count);
+
 /* ------------------------------------------------------------------ multi-GPU */
 /* One process per GPU.  Rank 0 obtains an id, the host framework broadcasts the 128 bytes,
  * every rank calls comm_init and then passes the SAME whole scene to set_scene / the pointer
@@ -246,7 +267,8 @@ long rsba_cuda_launch_count(rsba_problem* h);
 /* Device time (ms) of the last call of each stage, measured with CUDA events on the
  * launching stream: 0 jacobian, 1 residual, 2 schur, 3 cholesky, 4 update, 5 allreduce; and of
  * single kernels inside them: 6 point blocks, 7 frame blocks, 8 Schur panels, 9 Schur SYRK,
- * 10 Schur reduce, 11 factorisation, 12 triangular solves, 13 point back-substitution. */
+ * 10 Schur reduce, 11 factorisation, 12 triangular solves, 13 point back-substitution,
+ * 14 finalize, 15 batched PnP. */
 double rsba_cuda_stage_ms(rsba_problem* h, int stage);
 const char* rsba_cuda_version(void);
 

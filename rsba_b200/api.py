@@ -40,7 +40,7 @@ SYMBOLS = [
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
-    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_nccl_unique_id",
+    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
 
@@ -148,6 +148,8 @@ def load_library():
     lib.rsba_cuda_solve.argtypes = [vp, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
     lib.rsba_cuda_linearize_and_step.argtypes = [vp, C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp, _dp]
     lib.rsba_cuda_plan_reduced_system.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp] + [vp] * 9
+    lib.rsba_cuda_pnp_batch.argtypes = [vp, _dp, C.c_int, _ip, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp,
+                                        C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp]
     lib.rsba_cuda_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
     lib.rsba_cuda_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]
     lib.rsba_cuda_point_owners.argtypes = [C.c_int, C.c_int, C.c_long, vp, vp, C.c_int, vp]
@@ -183,7 +185,7 @@ def _addr(a):
 
 
 STAGES = ("jacobian", "residual", "schur", "cholesky", "update", "allreduce", "point_blocks", "frame_blocks",
-          "phi_build", "schur_syrk", "schur_reduce", "factor", "tri_solve", "point_step")
+          "phi_build", "schur_syrk", "schur_reduce", "factor", "tri_solve", "point_step", "finalize", "pnp")
 
 
 class Problem:
@@ -395,6 +397,28 @@ class Problem:
         self._check(self.lib.rsba_cuda_linearize_and_step(self._h, C.byref(options), float(radius), _addr(S),
                                                           _addr(rhs), _addr(dposes), _addr(dpoints), C.byref(mcc)))
         return dict(S=S, rhs=rhs, delta_poses=dposes, delta_points=dpoints, model_cost_change=mcc.value)
+
+    # ------------------------------------------------------------------ batched RS-PnP
+    def pnp_batch(self, cam, shutter, scanlines, points3d, obs_xy, sample_idx, poses, options=None,
+                  inlier_threshold=8.0):
+        """Batched solveRsPnP inner solve + inlier scoring (solveRSpnp.cpp:100-192, 265-335).
+        ``poses`` [H, 12] initial -> returns dict(poses, cost, usable, iterations, inliers)."""
+        if options is None:
+            options = default_options(max_num_iterations=10)
+        cam = np.ascontiguousarray(cam, dtype=np.float64)
+        scan = np.ascontiguousarray(scanlines, dtype=np.int32)
+        pts = np.ascontiguousarray(points3d, dtype=np.float64)
+        xy = np.ascontiguousarray(obs_xy, dtype=np.float64)
+        idx = np.ascontiguousarray(sample_idx, dtype=np.int32)
+        out = np.ascontiguousarray(poses, dtype=np.float64).copy()
+        H = idx.shape[0]
+        cost, usable = np.zeros(H), np.zeros(H, dtype=np.int32)
+        its, inl = np.zeros(H, dtype=np.int32), np.zeros(H, dtype=np.int32)
+        self._check(self.lib.rsba_cuda_pnp_batch(self._h, cam.ctypes.data_as(_dp), int(shutter), scan.ctypes.data_as(_ip),
+                                                 pts.shape[0], _addr(pts), _addr(xy), H, idx.shape[1], _addr(idx),
+                                                 _addr(out), C.byref(options), float(inlier_threshold), _addr(cost),
+                                                 _addr(usable), _addr(its), _addr(inl)))
+        return dict(poses=out, cost=cost, usable=usable, iterations=its, inliers=inl)
 
     # ------------------------------------------------------------------ multi-GPU / introspection
     def comm_init(self, rank: int, world_size: int, unique_id: bytes):

@@ -55,7 +55,7 @@ enum Stage { kStageJacobian = 0, kStageResidual, kStageSchur, kStageCholesky, kS
              kStageAllreduce,
              // single kernels inside the stages above (nested events), for the per-kernel rooflines
              kStagePointBlocks, kStageFrameBlocks, kStagePhiBuild, kStageSchurSyrk, kStageSchurReduce,
-             kStageFactor, kStageTriSolve, kStagePointStep, kStageFinalize, kNumStages };
+             kStageFactor, kStageTriSolve, kStagePointStep, kStageFinalize, kStagePnp, kNumStages };
 
 struct LmState;  // solver-side device state (lm_solver.cu)
 

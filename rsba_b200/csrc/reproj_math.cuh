@@ -17,7 +17,10 @@ struct Proj {
 // TAU_FROM_Y: the scan line of a VERTICAL shutter is read from observed_y, as interpolate_rs does
 // when it is handed the real observation (getPose / validate, struct/VideoSfM.cc:108-111,159-169).
 // The BA functor hands it {observed_x, observed_x} (VideoSfmBaRs.h:31), hence false there.
-template <bool JAC, bool TAU_FROM_Y = false>
+// VALIDATE = false: w2i(..., validate = false) as the RS-PnP functor and its inlier scoring call it
+// (solveRSpnp.cpp:65, 233; mat/cam.h:409-416): a point behind the camera is NOT rejected, and a depth
+// inside (-eps, eps) is replaced by eps (a constant: its derivative rows vanish).
+template <bool JAC, bool TAU_FROM_Y = false, bool VALIDATE = true>
 __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double ox, double oy,
                                           const double* __restrict__ p0,  // frame: pose0|pose1
                                           double X0, double X1, double X2,
@@ -104,7 +107,14 @@ __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double
   }
 
   // ---- w2i validity (mat/cam.h:410-412); c2i's own |z| < eps test cannot fire after it
-  out.ok = !(P2 < 1e-8);
+  out.ok = VALIDATE ? !(P2 < 1e-8) : true;
+  if (!VALIDATE && P2 < DBL_EPSILON && P2 > -DBL_EPSILON) {
+    P2 = DBL_EPSILON;
+    if (JAC) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { dPr[6 + k] = 0.0; R[6 + k] = 0.0; }
+    }
+  }
   if (!out.ok) {
     out.r0 = 0.0;
     out.r1 = 0.0;
