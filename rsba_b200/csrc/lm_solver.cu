@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -77,6 +78,16 @@ int upload(DeviceBuffer<T>& d, const std::vector<T>& h, cudaStream_t s) {
 // ------------------------------------------------------------------ structure analysis
 // The analogue of Ceres' program reordering + symbolic factorisation, done once per scene.
 int build_structure(rsba_problem* h, LmState* lm, bool dense) {
+  // RSBA_CUDA_TRACE=1: wall-clock of the one-off host analysis, to stderr
+  const bool trace = getenv("RSBA_CUDA_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[rsba_cuda] structure: %-28s %8.1f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   const long N = h->n_obs;
   const int F = h->n_frames, P = h->n_points;
   const std::vector<int>& fr = h->h_obs_frame;
@@ -109,39 +120,35 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     }
     frame_chunk_ptr[F] = (int)chunk_frame.size();
   }
+  lap("point CSR + frame chunks");
   // ---- Schur SYRK structure: (frame tile, point) incidences, tile pairs, work items
   const int T = (int)((12L * F + kTile - 1) / kTile);
   const int H = 2 * T;                                   // sub-tiles of 4 frames
   const int Hreal = (F + kSubFrames - 1) / kSubFrames;   // ... that hold at least one frame
-  std::vector<int> inc_point, inc_tile, slot_beg;
+  std::vector<int> inc_point, inc_tile, slot_beg, pt_inc_ptr(P + 1, 0);
   std::vector<unsigned char> slot_cnt;
-  struct PairEntry { long key; int inc_a, inc_b; };
-  std::vector<PairEntry> pe;
-  {
-    std::vector<int> mine;  // incidences of the current point
-    for (int p = 0; p < P; ++p) {
-      if (h->point_const[p]) continue;  // constant points are not eliminated: no Schur term
-      mine.clear();
-      const int b = pt_ptr[p], e = pt_ptr[p + 1];
-      for (int x = b; x < e; ++x) {
-        const int f = fr[pt_obs[x]], A = f / kSubFrames, fs = f % kSubFrames;
-        if (mine.empty() || inc_tile[mine.back()] != A) {
-          mine.push_back((int)inc_point.size());
-          inc_point.push_back(p);
-          inc_tile.push_back(A);
-          slot_beg.insert(slot_beg.end(), kSubFrames, -1);
-          slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
-        }
-        const size_t sl = (size_t)mine.back() * kSubFrames + fs;
-        if (slot_cnt[sl] == 0) slot_beg[sl] = x;
-        if (slot_cnt[sl] == 255) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
-        slot_cnt[sl]++;
+  for (int p = 0; p < P; ++p) {
+    pt_inc_ptr[p] = (int)inc_point.size();
+    if (h->point_const[p]) continue;  // constant points are not eliminated: no Schur term
+    const int b = pt_ptr[p], e = pt_ptr[p + 1];
+    int last = -1;
+    for (int x = b; x < e; ++x) {
+      const int f = fr[pt_obs[x]], A = f / kSubFrames, fs = f % kSubFrames;
+      if (last < 0 || inc_tile[last] != A) {
+        last = (int)inc_point.size();
+        inc_point.push_back(p);
+        inc_tile.push_back(A);
+        slot_beg.insert(slot_beg.end(), kSubFrames, -1);
+        slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
       }
-      for (size_t x = 0; x < mine.size(); ++x)
-        for (size_t y = x; y < mine.size(); ++y)
-          pe.push_back({(long)inc_tile[mine[x]] * H + inc_tile[mine[y]], mine[x], mine[y]});
+      const size_t sl = (size_t)last * kSubFrames + fs;
+      if (slot_cnt[sl] == 0) slot_beg[sl] = x;
+      if (slot_cnt[sl] == 255) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
+      slot_cnt[sl]++;
     }
   }
+  pt_inc_ptr[P] = (int)inc_point.size();
+  lap("incidences");
   const int n_inc = (int)inc_point.size();
   if ((long)(n_inc + 1) * kPanelDoubles > 2147483647L)
     return fail(RSBA_ERR_INVALID_ARGUMENT, "Schur panel buffer exceeds 2^31 doubles: shard the scene over more GPUs");
@@ -156,42 +163,80 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
       if (slot_cnt[(size_t)i * kSubFrames + fs] == 1)
         obs_phi_off[pt_obs[slot_beg[(size_t)i * kSubFrames + fs]]] = i * kPanelDoubles + fs * kFrameParams;
   }
-  for (int t = 0; t < Hreal; ++t) pe.push_back({(long)t * H + t, -1, -1});   // every diagonal sub-tile is a pair
+  // ---- sub-tile pairs and their entry lists, by a two-pass counting sort on the pair key a*H + b
+  // (entries of one pair stay in point order).  The key table is dense while H^2 is small, else the
+  // distinct keys are collected and sorted.
+  const bool dense_keys = (long)H * H <= (1L << 24) && !getenv("RSBA_CUDA_SPARSE_KEYS");   // (env: test hook)
+  std::vector<int> key_pair;          // dense: key -> pair id (or -1)
+  std::vector<long> keys;             // sparse: sorted distinct keys
+  auto for_each_pair_of_point = [&](int p, auto&& fn) {
+    for (int x = pt_inc_ptr[p]; x < pt_inc_ptr[p + 1]; ++x)
+      for (int y = x; y < pt_inc_ptr[p + 1]; ++y) fn((long)inc_tile[x] * H + inc_tile[y], x, y);
+  };
+  std::vector<long> marker_keys;
+  for (int t = 0; t < Hreal; ++t) marker_keys.push_back((long)t * H + t);     // every diagonal sub-tile is a pair
   for (const auto& pr : h->priors) {                                           // ... and every prior coupling
     const int a = std::min(pr.frame, pr.prev) / kSubFrames, b = std::max(pr.frame, pr.prev) / kSubFrames;
-    pe.push_back({(long)a * H + b, -1, -1});
+    marker_keys.push_back((long)a * H + b);
   }
-  std::stable_sort(pe.begin(), pe.end(), [](const PairEntry& x, const PairEntry& y) { return x.key < y.key; });
-  std::vector<int> pair_a, pair_b, pair_item_ptr;
-  std::vector<int4> items;
-  std::vector<int2> entries;
-  for (size_t i = 0; i < pe.size();) {
-    size_t j = i;
-    while (j < pe.size() && pe[j].key == pe[i].key) ++j;
-    const int A = (int)(pe[i].key / H), Bt = (int)(pe[i].key % H);
-    const int pair = (int)pair_a.size();
-    pair_a.push_back(A);
-    pair_b.push_back(Bt);
-    pair_item_ptr.push_back((int)items.size());
-    size_t k = i;
-    while (k < j) {
-      const int first = (int)entries.size();
-      int cnt = 0;
-      for (; k < j && cnt < kSchurSegPoints; ++k) {
-        if (pe[k].inc_a < 0) continue;                       // the diagonal marker
-        entries.push_back(make_int2(pe[k].inc_b, pe[k].inc_a));   // (row side B, column side A)
-        ++cnt;
+  std::vector<int> pair_a, pair_b;
+  std::vector<long> pair_cnt;
+  if (dense_keys) {
+    std::vector<int> cnt((size_t)H * H, 0);
+    std::vector<char> present((size_t)H * H, 0);
+    for (long k : marker_keys) present[k] = 1;
+    for (int p = 0; p < P; ++p) for_each_pair_of_point(p, [&](long key, int, int) { cnt[key]++; });
+    key_pair.assign((size_t)H * H, -1);
+    for (long key = 0; key < (long)H * H; ++key)
+      if (cnt[key] > 0 || present[key]) {
+        key_pair[key] = (int)pair_a.size();
+        pair_a.push_back((int)(key / H));
+        pair_b.push_back((int)(key % H));
+        pair_cnt.push_back(cnt[key]);
       }
-      if (cnt == 0) continue;
-      while (cnt % 8) { entries.push_back(make_int2(n_inc, n_inc)); ++cnt; }   // zero panel
-      items.push_back(make_int4(pair, first, cnt, A == Bt ? 1 : 0));
-    }
-    i = j;
+  } else {
+    keys = marker_keys;
+    for (int p = 0; p < P; ++p) for_each_pair_of_point(p, [&](long key, int, int) { keys.push_back(key); });
+    std::vector<long> all = keys;
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    pair_cnt.assign(keys.size(), 0);
+    for (size_t k = marker_keys.size(); k < all.size(); ++k)
+      pair_cnt[std::lower_bound(keys.begin(), keys.end(), all[k]) - keys.begin()]++;
+    for (long key : keys) { pair_a.push_back((int)(key / H)); pair_b.push_back((int)(key % H)); }
   }
-  pair_item_ptr.push_back((int)items.size());
-  if (entries.empty()) entries.push_back(make_int2(n_inc, n_inc));
+  auto pair_of_key = [&](long key) -> int {
+    return dense_keys ? key_pair[key] : (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
+  };
+  lap("count pairs");
+  // work items: <= kSchurSegPoints entries each; only the last item of a pair is padded (to a multiple of 8)
+  const int n_pairs_h = (int)pair_a.size();
+  std::vector<int> pair_item_ptr(n_pairs_h + 1, 0);
+  std::vector<long> pair_base(n_pairs_h + 1, 0);
+  std::vector<int4> items;
+  for (int q = 0; q < n_pairs_h; ++q) {
+    pair_item_ptr[q] = (int)items.size();
+    long left = pair_cnt[q], pos = pair_base[q];
+    while (left > 0) {
+      const int take = (int)std::min<long>(left, kSchurSegPoints);
+      const int padded = (take + 7) / 8 * 8;
+      if (pos + padded > 2147483647L) return fail(RSBA_ERR_INVALID_ARGUMENT, "Schur entry list exceeds 2^31");
+      items.push_back(make_int4(q, (int)pos, padded, pair_a[q] == pair_b[q] ? 1 : 0));
+      pos += padded;
+      left -= take;
+    }
+    pair_base[q + 1] = pos;
+  }
+  pair_item_ptr[n_pairs_h] = (int)items.size();
+  std::vector<int2> entries((size_t)std::max<long>(pair_base[n_pairs_h], 1), make_int2(n_inc, n_inc));   // zero panel
+  {
+    std::vector<long> cur(pair_base.begin(), pair_base.end() - 1);
+    for (int p = 0; p < P; ++p)
+      for_each_pair_of_point(p, [&](long key, int x, int y) { entries[cur[pair_of_key(key)]++] = make_int2(y, x); });   // (row side B, column side A)
+  }
   if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
   const int n_items = (int)pair_item_ptr.back();
+  lap("work items");
   // ---- ordering, symbolic factorisation, elimination levels (tile_plan.cu)
   // (the plan is a function of the WHOLE scene, so every rank of a multi-GPU run derives the same one)
   TilePlan& plan = lm->plan;
@@ -235,6 +280,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   const std::vector<int>& tile_pos = plan.tile_pos;
   const std::vector<int2>& nz_tiles = plan.nz_tiles;
 
+  lap("tile plan (ND + symbolic)");
   // ---- upload
   int rc;
 #define UP(dev, host) if ((rc = upload(lm->dev, host, s))) return rc
@@ -314,6 +360,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   for (int p = 0; p < P; ++p) free_params += h->point_const[p] ? 0 : 3;
   lm->num_free_params = free_params;
   RSBA_CUDA_TRY(cudaStreamSynchronize(s));
+  lap("upload + allocation + memset");
   return RSBA_OK;
 }
 
