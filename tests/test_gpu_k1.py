@@ -141,6 +141,12 @@ def test_k1_full_size_properties(api, oracle_built):
     r0, J0, v0 = oracle_built.evaluate(sub, impl="port")
     assert (np.abs(r[idx] - r0) / np.maximum(1.0, np.abs(r0))).max() <= TOL
     assert rel_block_err(J[idx], J0).max() <= TOL
+    if oracle_built.ref_available():
+        # every one of the 500 000 observations against the reference's own functor under Jet<15>
+        rr, Jr, vr = oracle_built.evaluate(sc, impl="ref")
+        assert np.array_equal(v, vr)
+        assert (np.abs(r - rr) / np.maximum(1.0, np.abs(rr))).max() <= TOL
+        assert rel_block_err(J, Jr).max() <= TOL
 
 
 @pytest.mark.parametrize("a", [0.5, 2.0])
