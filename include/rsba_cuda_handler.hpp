@@ -23,6 +23,8 @@
 #define RSBA_CUDA_HANDLER_HPP_
 
 #include <cstddef>
+#include <deque>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -129,14 +131,31 @@ class Handler {
       camera_set_ = true;
     }
     auto& f = sess.frames[frameKey];
-    if (f.poses.size() != 2) throw std::runtime_error("rsba_cuda: only rolling-shutter frames (two control poses)");
-    if (opt.model.constVelocity) throw std::runtime_error("rsba_cuda: constVelocity (the reference aborts here too)");
+    // A frame with ONE pose is the reference's global-shutter case: ReprojectionError <2; 6, 3> on
+    // getPose() = f.poses[0] (CeresHandler.h:265-286, struct/VideoSfM.cc:104-106).  The device path
+    // always has two control-pose blocks per frame; with a GLOBAL shutter the second one does not
+    // enter the projection (mat/cam.h:321-322), so a constant stand-in block completes the frame.
+    double* second_pose = nullptr;
+    if (f.poses.size() == 1) {
+      if ((int)sess.rs != 0) throw std::runtime_error("rsba_cuda: single-pose frames need a GLOBAL-shutter session");
+      auto it = gs_second_.find(frameKey);
+      if (it == gs_second_.end()) {
+        gs_store_.push_back(f.poses[0]);
+        it = gs_second_.emplace(frameKey, gs_store_.back().data()).first;
+      }
+      second_pose = it->second;
+    } else if (f.poses.size() == 2) {
+      second_pose = f.poses[1].data();
+    } else {
+      throw std::runtime_error("rsba_cuda: frames must hold one (global shutter) or two (rolling shutter) poses");
+    }
+    if (f.poses.size() == 2 && opt.model.constVelocity) throw std::runtime_error("rsba_cuda: constVelocity (the reference aborts here too)");
     bool added = false;
     // motion prior between this frame and the previous one (CeresHandler.h:147-186)
     if (frameKey >= (std::size_t)opt.ceres.fixFirstNCameras && frameKey > 0 &&
         (opt.ceres.constFrameVelocity != 0 || opt.ceres.constFrameAcceleration != 0)) {
       auto& f_1 = sess.frames[frameKey - 1];
-      if (f_1.poses.size() == 2) {
+      if (f.poses.size() == 2 && f_1.poses.size() == 2) {
         const bool accel = opt.ceres.constFrameAcceleration != 0;
         problem.AddMotionPrior(accel ? 2 : 1, accel ? opt.ceres.constFrameAcceleration : opt.ceres.constFrameVelocity,
                                opt.ceres.interFrameRatio, f.poses[0].data(), f.poses[1].data(), f_1.poses[0].data(),
@@ -151,7 +170,7 @@ class Handler {
       auto* t = &sess.getTrack(o.track);
       if (!t->__isset.pt || (opt.ceres.useOnlyValidMatches && !t->valid)) continue;
       const double obs[2] = {o.x, o.y};
-      problem.AddRsResidualBlock(obs, f.poses[0].data(), f.poses[1].data(), t->pt.data());   // :250-255
+      problem.AddRsResidualBlock(obs, f.poses[0].data(), second_pose, t->pt.data());   // :250-255 / :265-270
       added = true;
       bool fixedOldTrack = false;                             // :288-300
       if (startFrame > 0)
@@ -160,9 +179,10 @@ class Handler {
       if (fixedOldTrack || opt.ceres.const3d) problem.SetParameterBlockConstant(t->pt.data());
     }
     if (!added) return;
-    if (frameKey < (std::size_t)opt.ceres.fixFirstNCameras) {             // :342-346
+    if (f.poses.size() == 1) problem.SetParameterBlockConstant(second_pose);   // the stand-in never moves
+    if (frameKey < (std::size_t)opt.ceres.fixFirstNCameras) {             // :342-346, :280-283
       problem.SetParameterBlockConstant(f.poses[0].data());
-      problem.SetParameterBlockConstant(f.poses[1].data());
+      if (f.poses.size() == 2) problem.SetParameterBlockConstant(f.poses[1].data());
     } else if (opt.ceres.fixScale && (frameKey == 0 || frameKey == sess.frames.size() - 1)) {   // :350-361
       problem.SetSubsetConstant(frameKey == 0 ? f.poses[0].data() : f.poses.back().data(), {3, 4, 5});
     } else if (opt.ceres.fixRotation) {                                    // :362-371
@@ -185,6 +205,8 @@ class Handler {
 
  private:
   bool camera_set_ = false;
+  std::deque<std::vector<double>> gs_store_;        // stand-in second poses of single-pose frames
+  std::map<std::size_t, double*> gs_second_;
 };
 
 }  // namespace rsba_cuda

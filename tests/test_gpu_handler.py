@@ -76,3 +76,32 @@ def test_handler_windowed_ba_freezes_old_tracks(tmp_path):
     old[sc.obs_point[sc.obs_frame < start]] = True
     assert np.array_equal(points[old], sc.points[old])               # frozen tracks
     assert (~old).sum() > 20 and np.any(points[~old] != sc.points[~old])
+
+
+@pytest.mark.gpu
+def test_handler_global_shutter_single_pose_frames(tmp_path):
+    """A GLOBAL-shutter session with one pose per frame (ReprojectionError <2; 6, 3>, CeresHandler.h:265-286):
+    the handler completes each frame with a constant stand-in block; result == bulk API with the
+    second control poses masked constant."""
+    import rsba_b200.api as api
+    sc = make_scene(10, 300, 6, name="gs-handler", shutter=0)
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    r = subprocess.run([BIN, src, dst, "1", "8", "0", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst)
+    poses = out[4:4 + 12 * sc.num_frames].reshape(-1, 12)
+    points = out[4 + 12 * sc.num_frames:].reshape(-1, 3)
+    mask = np.full(sc.num_frames, 0xFC0, dtype=np.uint16)            # second control pose constant everywhere
+    mask[0] = 0xFFF
+    with api.Problem(0) as pb:
+        pb.set_camera(sc.cam, 0, sc.scanlines, True)
+        pb.set_scene(sc.obs_xy, sc.obs_frame, sc.obs_point, sc.num_frames, sc.num_points, mask)
+        pb.set_parameters(sc.poses, sc.points)
+        s = pb.solve(api.default_options(max_num_iterations=8))
+        po, pt = pb.get_parameters()
+    assert out[0] == 1 and abs(out[3] - s.final_cost) <= 1e-9 * s.final_cost
+    seen = np.zeros(sc.num_points, bool)
+    seen[sc.obs_point] = True
+    assert np.linalg.norm(poses[:, :6] - po[:, :6]) <= 1e-7 * np.linalg.norm(po[:, :6])
+    assert np.linalg.norm(points[seen] - pt[seen]) <= 1e-7 * np.linalg.norm(pt[seen])

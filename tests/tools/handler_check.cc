@@ -3,7 +3,8 @@
 // (gen-cpp/sfm_types.h: Frame.poses, Frame.obs, Observation.{x,y,track}, Track.{pt,valid,obs},
 // Session.{cam,rs,scanlines,frames}).  Reads a flat scene file written by tests/test_gpu_handler.py,
 // runs the same calls VideoSfMHandler::BA makes (VideoSfMHandler.cc:586-592), writes the result.
-//   usage: handler_check <scene.bin> <out.bin> <fixFirstNCameras> <maxIter> [startFrame]
+//   usage: handler_check <scene.bin> <out.bin> <fixFirstNCameras> <maxIter> [startFrame] [gs]
+//   (gs = 1: global-shutter session, every frame holds ONE pose -- the first control pose of the file)
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -61,12 +62,14 @@ int main(int argc, char** argv) {
   rd(f, fr.data(), N * sizeof(int));
   rd(f, pt.data(), N * sizeof(int));
   fclose(f);
+  const bool gs = argc > 6 && atoi(argv[6]) != 0;
+  if (gs) sess.rs = 0;
   sess.frames.resize(F);
   for (long k = 0; k < F; ++k) {
-    sess.frames[k].poses.assign(2, std::vector<double>(6));
+    sess.frames[k].poses.assign(gs ? 1 : 2, std::vector<double>(6));
     for (int c = 0; c < 6; ++c) {
       sess.frames[k].poses[0][c] = poses[12 * k + c];
-      sess.frames[k].poses[1][c] = poses[12 * k + 6 + c];
+      if (!gs) sess.frames[k].poses[1][c] = poses[12 * k + 6 + c];
     }
   }
   for (long p = 0; p < P; ++p) {
@@ -110,7 +113,7 @@ int main(int argc, char** argv) {
   fwrite(head, sizeof(double), 4, g);
   for (long k = 0; k < F; ++k) {
     fwrite(sess.frames[k].poses[0].data(), sizeof(double), 6, g);
-    fwrite(sess.frames[k].poses[1].data(), sizeof(double), 6, g);
+    fwrite(sess.frames[k].poses.back().data(), sizeof(double), 6, g);   // (global shutter: pose0 again)
   }
   for (long p = 0; p < P; ++p) fwrite(sess.tracks[(int)p].pt.data(), sizeof(double), 3, g);
   fclose(g);
