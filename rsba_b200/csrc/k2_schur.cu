@@ -26,6 +26,8 @@
 // is bound by the FP64 pipe (tcgen05 has no FP64 kind: DMMA == DFMA rate, 37.1 TFLOP/s measured).
 #include "lm.cuh"
 
+#include <type_traits>
+
 namespace rsba {
 namespace {
 
@@ -133,8 +135,8 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 }
 
 // ---------------------------------------------------------------- sub-tile-pair SYRK
-// One CTA (4 warps) per work item; warp w owns the 24 x 24 patch (w>>1, w&1) of the 48 x 48 block.
-// 60 KB of shared memory per CTA: three CTAs per SM keep 12 warps on the FP64 pipe.
+// One CTA (4 warps) per work item.  60 KB of shared memory per CTA: three CTAs per SM keep 12 warps on
+// the FP64 pipe.
 __global__ void __launch_bounds__(128, 3)
 schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entries,
                   const int4* __restrict__ items, double* __restrict__ partial) {
@@ -172,43 +174,62 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
     for (int c = 0; c < kStages && c < nchunks; ++c) issue(c);
   }
 
-  const int m0 = (warp >> 1) * 24, n0 = (warp & 1) * 24;
-  const int fr = lane >> 2, fc = lane & 3;
-  double acc[3][3][2];
-#pragma unroll
-  for (int mi = 0; mi < 3; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c % kStages;
-    mbar_wait(smem_u32(&bars[s]), (unsigned)((c / kStages) & 1));
-    const double* R = stage_base + (size_t)s * kStageDoubles;
-    const double* Cc = diag ? R : R + kOperandDoubles;
-#pragma unroll
-    for (int ks = 0; ks < (3 * kChunkPts) / 4; ++ks) {
-      const int krow = (4 * ks + fc) * kPanelLd + fr;
-      double a[3], b[3];
-#pragma unroll
-      for (int mi = 0; mi < 3; ++mi) a[mi] = R[krow + m0 + 8 * mi];
-#pragma unroll
-      for (int ni = 0; ni < 3; ++ni) b[ni] = Cc[krow + n0 + 8 * ni];
-#pragma unroll
-      for (int mi = 0; mi < 3; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 3; ++ni) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-    }
-    __syncthreads();                         // every warp is done with stage s
-    if (warp == 0 && c + kStages < nchunks) issue(c + kStages);
-  }
-
+  // The 48 x 48 block is a 6 x 6 grid of 8 x 8 DMMA tiles.  Off-diagonal pairs: warp w owns the 3 x 3
+  // tiles at (3 (w>>1), 3 (w&1)).  Diagonal pairs (a == b) are symmetric and only their lower tiles are
+  // ever read, so the 21 lower tiles are dealt 6 / 6 / 5 / 4 to the warps instead of 9 each: every
+  // variant is "a 3 x 3 window at (r0, c0) with a compile-time tile mask" (bit 3 i + j).
+  constexpr unsigned kAll = 0x1FF;
+  constexpr unsigned kLower = (1u << 0) | (1u << 3) | (1u << 4) | (1u << 6) | (1u << 7) | (1u << 8);
+  constexpr unsigned kRows34 = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4);       // window (3, 0)
+  constexpr unsigned kRows45 = (1u << 5) | (1u << 6) | (1u << 7) | (1u << 8);                   // window (3, 0)
   double* out = partial + (long)blockIdx.x * kSub * kSub;
+  auto run = [&](auto mask_tag, int r0, int c0) {
+    constexpr unsigned MASK = decltype(mask_tag)::value;
+    const int m0 = 8 * r0, n0 = 8 * c0;
+    const int fr = lane >> 2, fc = lane & 3;
+    double acc[3][3][2];
 #pragma unroll
-  for (int mi = 0; mi < 3; ++mi)
+    for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 3; ++ni)
-      *reinterpret_cast<double2*>(out + (m0 + 8 * mi + fr) * kSub + n0 + 8 * ni + 2 * fc) =
-          make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % kStages;
+      mbar_wait(smem_u32(&bars[s]), (unsigned)((c / kStages) & 1));
+      const double* R = stage_base + (size_t)s * kStageDoubles;
+      const double* Cc = diag ? R : R + kOperandDoubles;
+#pragma unroll
+      for (int ks = 0; ks < (3 * kChunkPts) / 4; ++ks) {
+        const int krow = (4 * ks + fc) * kPanelLd + fr;
+        double a[3], b[3];
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi)
+          if ((MASK >> (3 * mi)) & 7u) a[mi] = R[krow + m0 + 8 * mi];
+#pragma unroll
+        for (int ni = 0; ni < 3; ++ni)
+          if ((MASK >> ni) & 0x49u) b[ni] = Cc[krow + n0 + 8 * ni];
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 3; ++ni)
+            if ((MASK >> (3 * mi + ni)) & 1u) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+      }
+      // every warp is done with stage s (the warps run different instantiations of this loop, hence a
+      // PTX barrier, which is identified by its number and not by the call site)
+      asm volatile("bar.sync 0;" ::: "memory");
+      if (warp == 0 && c + kStages < nchunks) issue(c + kStages);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 3; ++ni)
+        if ((MASK >> (3 * mi + ni)) & 1u)
+          *reinterpret_cast<double2*>(out + (m0 + 8 * mi + fr) * kSub + n0 + 8 * ni + 2 * fc) =
+              make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+  };
+  if (!diag) run(std::integral_constant<unsigned, kAll>{}, 3 * (warp >> 1), 3 * (warp & 1));
+  else if (warp < 2) run(std::integral_constant<unsigned, kLower>{}, 3 * warp, 3 * warp);
+  else if (warp == 2) run(std::integral_constant<unsigned, kRows34>{}, 3, 0);
+  else run(std::integral_constant<unsigned, kRows45>{}, 3, 0);
 }
 
 // ---------------------------------------------------------------- reduce
@@ -231,7 +252,8 @@ schur_reduce_kernel(SchurStructure st, NormalEq ne, PriorView pv, double* __rest
     const int e = blockIdx.y * 768 + u * 256 + threadIdx.x;
     const int r = e / kSub, c = e % kSub;
     double sum = 0.0;
-    for (int it = ib; it < ie; ++it) sum += ne.partial[(long)it * kSub * kSub + e];
+    if (a != b || (c >> 3) <= (r >> 3))     // diagonal pairs: the SYRK leaves the strictly upper 8x8 tiles unwritten
+      for (int it = ib; it < ie; ++it) sum += ne.partial[(long)it * kSub * kSub + e];
     double val = -sum;
     const int fr = b * kSubFrames + r / kFrameParams, fc = a * kSubFrames + c / kFrameParams;
     if (fr == fc) {
