@@ -43,6 +43,17 @@ struct PriorView {
   double* Bx;            // [F][4][6] coupling diagonals of cur_of[f] (zero without a prior)
 };
 
+// Kernel attributes (opt-in shared memory) are per device: true the first time `slot` (one per call
+// site) is seen on the current device.
+inline bool first_use_on_device(bool (&seen)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (seen[dev]) return false;
+  seen[dev] = true;
+  return true;
+}
+
 // ---- launchers (definitions in the .cu files); all asynchronous on `stream` ------------
 // K1: residual + Jacobian (+ per-CTA cost partials, invalid count).
 void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,

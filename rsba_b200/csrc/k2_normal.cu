@@ -362,15 +362,15 @@ void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const dou
 
 void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
                          int n_frames, NormalEq ne, bool with_wf, cudaStream_t s) {
-  static bool attr_done = false;
-  static int n_sm = 148;
-  if (!attr_done) {
+  static bool seen[64] = {};
+  static int sm_count[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (first_use_on_device(seen)) {
     cudaFuncSetAttribute(frame_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    attr_done = true;
+    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   }
+  const int n_sm = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
   if (st.n_chunks > 0)
     frame_blocks_kernel<<<std::min(st.n_chunks, 2 * n_sm), kFrameThreads, kFrameSmem, s>>>(st, obs, jac, res, ne, with_wf ? 1 : 0);
   if (n_frames > 0) frame_reduce_kernel<<<n_frames, 192, 0, s>>>(st, ne, n_frames);

@@ -327,11 +327,9 @@ void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double
 }
 
 void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool seen[64] = {};
+  if (first_use_on_device(seen))
     cudaFuncSetAttribute(schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem);
-    attr_done = true;
-  }
   if (st.n_items <= 0) return;
   schur_syrk_kernel<<<st.n_items, 128, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
 }

@@ -495,12 +495,11 @@ void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s) {
 }
 
 void k3_prepare() {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool seen[64] = {};
+  if (first_use_on_device(seen)) {
     cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem);
     cudaFuncSetAttribute(tile_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem);
     cudaFuncSetAttribute(tile_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem);
-    attr_done = true;
   }
 }
 

@@ -262,12 +262,10 @@ extern "C" int rsba_cuda_pnp_batch(rsba_problem* h, const double cam9[9], int sh
                options->min_trust_region_radius, options->min_relative_decrease, options->min_lm_diagonal,
                options->max_lm_diagonal, options->function_tolerance, options->gradient_tolerance,
                options->parameter_tolerance, inlier_threshold};
-  static bool attr_done = false;
+  static bool seen[64] = {};
   const size_t smem = kPnpWarps * sizeof(WarpSmem);
-  if (!attr_done) {
+  if (first_use_on_device(seen))
     cudaFuncSetAttribute(pnp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
   stage_begin(h, kStagePnp);
   pnp_batch_kernel<<<(n_hyp + kPnpWarps - 1) / kPnpWarps, kPnpWarps * 32, smem, s>>>(
       cm, d_pts.ptr, d_obs.ptr, n_points, n_hyp, sample_size, d_idx.ptr, d_poses.ptr, o, d_cost.ptr, d_flags.ptr,

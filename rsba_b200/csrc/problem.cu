@@ -534,6 +534,8 @@ long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals) {
   if (!h) return -1;
   const long n = h->priors_dirty ? 0 : (long)h->priors.size();
   if (residuals && n > 0) {
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;   // written on the handle's (non-blocking) stream
     if (cudaMemcpy(residuals, h->d_prior_r.ptr, 12 * n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   }
   return n;
