@@ -103,6 +103,18 @@ void rsba_cuda_default_options(rsba_solve_options* o);
 int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter,
                          const int scanlines[2], int interpolate_rotation);
 
+/* Uncalibrated variant.  Replaces: RsBundleAdjustment::CreateWithCam(sess, opt, obs) + problem.AddResidualBlock(
+ * cost, loss, sess.cam.data(), f.poses[0], f.poses[1], t->pt)  (VideoSfmBaRs.h:38-49,68-80; CeresHandler.h:256-264,
+ * opt.model.calibrated == false): the session's nine intrinsics (fx fy k1 k2 p1 p2 k3 cx cy) become one shared
+ * 9-wide PARAMETER block of every residual block -- a dense border of the reduced camera system.  Call with 1
+ * before solving; rsba_cuda_set_camera supplies the initial values, rsba_cuda_get_camera returns the optimised
+ * ones; rsba_cuda_get_intrinsics_jacobian returns d residual / d intrinsics [N][2][9] of the last
+ * rsba_cuda_evaluate (HOST pointer, caller's observation order).  Per-frame intrinsics blocks (f.cam) are
+ * not supported. */
+int rsba_cuda_set_intrinsics_free(rsba_problem* h, int free_intrinsics);
+int rsba_cuda_get_camera(rsba_problem* h, double cam9[9]);
+int rsba_cuda_get_intrinsics_jacobian(rsba_problem* h, double* jacobian_cam);
+
 /* Replaces: lossFunction = new ceres::HuberLoss(opt.ceres.huberLoss), handed to every
  * AddResidualBlock (CeresHandler.h:85-90, 252).  huber_a = 0 removes the loss (the default,
  * SfmOptions.h:64).  Applied the way Ceres' Corrector does: cost = 1/2 rho(|r|^2), residual and

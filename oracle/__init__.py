@@ -275,3 +275,72 @@ def motion_prior_rows(scene, priors, poses=None, huber=0.0):
     n = len(priors)
     Jx = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(12 * n, 12 * F + 3 * P))
     return Jx, np.concatenate(res), cost
+
+
+def evaluate_cam_ref(scene, poses=None, points=None, cam=None, nthreads=0):
+    """TEST INFRASTRUCTURE.  Uncalibrated variant <2; 9, 6, 6, 3> (VideoSfmBaRs.h:38-49) through the
+    reference's own ReprojectionError::operator()(camera, pose, point, residuals) under Jet<24>
+    (oracle/_ref).  Returns residuals [N,2], J [N,30], Jcam [N,18] (= [2][9]), valid [N]."""
+    poses, points = _prep(scene, poses, points)
+    lib = ref_lib()
+    lib.rsba_ref_eval_cam.restype = C.c_long
+    lib.rsba_ref_eval_cam.argtypes = [C.c_long, _dp, _ip, _ip, _dp, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, _dp, _bp, C.c_int]
+    n = scene.num_obs
+    res, J, Jc = np.zeros((n, 2)), np.zeros((n, 30)), np.zeros((n, 18))
+    valid = np.zeros(n, dtype=np.uint8)
+    cam = np.ascontiguousarray(scene.cam if cam is None else cam, dtype=np.float64)
+    scan = np.ascontiguousarray(scene.scanlines, dtype=np.int32)
+    oxy = np.ascontiguousarray(scene.obs_xy, dtype=np.float64)
+    fi = np.ascontiguousarray(scene.obs_frame, dtype=np.int32)
+    pi = np.ascontiguousarray(scene.obs_point, dtype=np.int32)
+    lib.rsba_ref_eval_cam(n, _ptr(oxy, _dp), _ptr(fi, _ip), _ptr(pi, _ip), _ptr(cam, _dp), int(scene.shutter),
+                          _ptr(scan, _ip), int(bool(scene.interpolate_rotation)), _ptr(poses, _dp), _ptr(points, _dp),
+                          _ptr(res, _dp), _ptr(J, _dp), _ptr(Jc, _dp), _ptr(valid, _bp), nthreads)
+    return res, J, Jc, valid
+
+
+def intrinsics_jacobian(scene, poses=None, points=None, cam=None):
+    """TEST INFRASTRUCTURE.  Closed form of d residual / d (fx fy k1 k2 p1 p2 k3 cx cy) from c2i + distort
+    (mat/cam.h:372-395, 49-72), numpy; travels without oracle/_ref.  Returns Jcam [N,18] (zeros for invalid rows)."""
+    poses, points = _prep(scene, poses, points)
+    cam = np.asarray(scene.cam if cam is None else cam, dtype=np.float64)
+    # camera-frame point through the port (value only): recover xp, yp from the residual-free projection
+    fx, fy, k1, k2, t1, t2, k3, cx, cy = cam
+    # the normalised coordinates are obtained by numerically inverting nothing: recompute them directly
+    fr, pt = scene.obs_frame, scene.obs_point
+    ox = scene.obs_xy[:, 0]
+    poses = poses.reshape(-1, 12)
+    points = points.reshape(-1, 3)
+    if scene.shutter != 0:
+        tau = np.clip((ox - scene.scanlines[0]) / float(scene.scanlines[1] - scene.scanlines[0]), 0.0, 1.0)
+    else:
+        tau = np.zeros_like(ox)
+    p0, p1 = poses[fr, :6], poses[fr, 6:]
+    rot = p0[:, :3] + (p1[:, :3] - p0[:, :3]) * tau[:, None] if (scene.shutter != 0 and scene.interpolate_rotation) else p0[:, :3]
+    cen = p0[:, 3:] + (p1[:, 3:] - p0[:, 3:]) * tau[:, None]
+    q = points[pt] - cen
+    th = np.linalg.norm(rot, axis=1)
+    small = th * th <= np.finfo(np.float64).eps
+    w = rot / np.where(small, 1.0, th)[:, None]
+    c, s = np.cos(th)[:, None], np.sin(th)[:, None]
+    P = q * c + np.cross(w, q) * s + w * np.sum(w * q, axis=1, keepdims=True) * (1 - c)
+    P[small] = (q + np.cross(rot, q))[small]
+    ok = ~(P[:, 2] < 1e-8)
+    z = np.where(ok, P[:, 2], 1.0)
+    xp, yp = P[:, 0] / z, P[:, 1] / z
+    r2 = xp * xp + yp * yp
+    dist = 1 + r2 * (k1 + r2 * (k2 + r2 * k3))
+    xy = xp * yp
+    px = dist * xp + (2 * t1 * xy + t2 * (r2 + 2 * xp * xp))
+    py = dist * yp + (t1 * (r2 + 2 * yp * yp) + 2 * t2 * xy)
+    n = scene.num_obs
+    Jc = np.zeros((n, 18))
+    Jc[:, 0], Jc[:, 10] = px, py
+    Jc[:, 2], Jc[:, 11] = fx * xp * r2, fy * yp * r2
+    Jc[:, 3], Jc[:, 12] = fx * xp * r2 ** 2, fy * yp * r2 ** 2
+    Jc[:, 4], Jc[:, 13] = fx * 2 * xy, fy * (r2 + 2 * yp * yp)
+    Jc[:, 5], Jc[:, 14] = fx * (r2 + 2 * xp * xp), fy * 2 * xy
+    Jc[:, 6], Jc[:, 15] = fx * xp * r2 ** 3, fy * yp * r2 ** 3
+    Jc[:, 7], Jc[:, 17] = 1.0, 1.0
+    Jc[~ok] = 0.0
+    return Jc

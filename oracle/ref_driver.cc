@@ -48,6 +48,27 @@ struct RsFlagged : public vision::ReprojectionError {
   }
 };
 
+// The uncalibrated variant: RsBundleAdjustment's 4-block operator() (VideoSfmBaRs.h:38-49) = interpolate_rs
+// followed by the reference's ReprojectionError::operator()(camera, pose, point, residuals)
+// (video_bundler_free.h:45-65), the intrinsics being a parameter block <2; 9, 6, 6, 3>.
+struct RsFlaggedCam : public vision::ReprojectionError {
+  SHUTTER shutter;
+  int scan[2];
+  bool interp_rot;
+  RsFlaggedCam(const double* cam, const double* observed, SHUTTER s, const int* sc, bool ir)
+      : vision::ReprojectionError(cam, observed), shutter(s), interp_rot(ir) {
+    scan[0] = sc[0];
+    scan[1] = sc[1];
+  }
+  template <typename T>
+  bool operator()(const T* const camera, const T* const p0, const T* const p1, const T* const X, T* r) const {
+    T mid[6];
+    T xx[2] = {T(observed_x), T(observed_x)};
+    vision::interpolate_rs(p0, p1, shutter, scan, xx, mid, interp_rot);
+    return vision::ReprojectionError::operator()(camera, mid, X, r);
+  }
+};
+
 struct RefProblem {
   std::vector<ceres::CostFunction*> cost;
   vision::framePtr frame;  // carries shutter + scanlines for RsReprojectionError
@@ -118,6 +139,40 @@ long rsba_ref_problem_eval(void* h, long n, const int* frame_idx, const int* poi
       residuals[2 * i] = r[0];
       residuals[2 * i + 1] = r[1];
     }
+    if (valid) valid[i] = ok ? 1 : 0;
+  }
+  return bad;
+}
+
+// Uncalibrated evaluation: residuals[n][2], jac[n][30] (pose0 | pose1 | point), jac_cam[n][18] = [2][9]
+// w.r.t. fx fy k1 k2 p1 p2 k3 cx cy, valid[n].  Returns the number of invalid observations.
+long rsba_ref_eval_cam(long n, const double* obs_xy, const int* frame_idx, const int* point_idx, const double* cam9,
+                       int shutter, const int* scanlines, int interpolate_rotation, const double* poses,
+                       const double* points, double* residuals, double* jac, double* jac_cam, unsigned char* valid,
+                       int nthreads) {
+  long bad = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+  for (long i = 0; i < n; ++i) {
+    ceres::AutoDiffCostFunction<RsFlaggedCam, 2, 9, 6, 6, 3> cf(
+        new RsFlaggedCam(cam9, obs_xy + 2 * i, (SHUTTER)shutter, scanlines, interpolate_rotation != 0));
+    const double* params[4] = {cam9, poses + 12 * (long)frame_idx[i], poses + 12 * (long)frame_idx[i] + 6,
+                               points + 3 * (long)point_idx[i]};
+    double r[2] = {0, 0};
+    double jc[18];
+    double* J[4] = {jc, jac + 30 * i, jac + 30 * i + 12, jac + 30 * i + 24};
+    bool ok = cf.Evaluate(params, r, J);
+    if (!ok) {
+      memset(jac + 30 * i, 0, 30 * sizeof(double));
+      memset(jc, 0, sizeof(jc));
+      r[0] = r[1] = 0;
+      ++bad;
+    }
+    memcpy(jac_cam + 18 * i, jc, sizeof(jc));
+    residuals[2 * i] = r[0];
+    residuals[2 * i + 1] = r[1];
     if (valid) valid[i] = ok ? 1 : 0;
   }
   return bad;

@@ -35,7 +35,8 @@ ERR_EVALUATION_FAILED, ERR_LINEAR_SOLVER, ERR_NCCL = -5, -6, -7
 # every symbol include/rsba_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "rsba_cuda_create", "rsba_cuda_destroy", "rsba_cuda_last_error", "rsba_cuda_set_stream",
-    "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_loss", "rsba_cuda_add_rs_residual",
+    "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_intrinsics_free", "rsba_cuda_get_camera", "rsba_cuda_get_intrinsics_jacobian",
+    "rsba_cuda_set_loss", "rsba_cuda_add_rs_residual",
     "rsba_cuda_add_motion_prior", "rsba_cuda_set_motion_priors", "rsba_cuda_get_prior_residuals",
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
@@ -127,6 +128,9 @@ def load_library():
     lib.rsba_cuda_default_options.argtypes = [C.POINTER(SolveOptions)]
     lib.rsba_cuda_default_options.restype = None
     lib.rsba_cuda_set_camera.argtypes = [vp, _dp, C.c_int, _ip, C.c_int]
+    lib.rsba_cuda_set_intrinsics_free.argtypes = [vp, C.c_int]
+    lib.rsba_cuda_get_camera.argtypes = [vp, vp]
+    lib.rsba_cuda_get_intrinsics_jacobian.argtypes = [vp, vp]
     lib.rsba_cuda_set_loss.argtypes = [vp, C.c_double]
     lib.rsba_cuda_add_rs_residual.argtypes = [vp, _dp, vp, vp, vp]
     lib.rsba_cuda_add_motion_prior.argtypes = [vp, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp]
@@ -235,6 +239,21 @@ class Problem:
         assert cam.size == 9 and scan.size == 2
         self._check(self.lib.rsba_cuda_set_camera(self._h, cam.ctypes.data_as(_dp), int(shutter),
                                                   scan.ctypes.data_as(_ip), int(bool(interpolate_rotation))))
+
+    def set_intrinsics_free(self, free=True):
+        """Uncalibrated variant <2; 9, 6, 6, 3> (VideoSfmBaRs.h:38-49): the shared intrinsics are optimised."""
+        self._check(self.lib.rsba_cuda_set_intrinsics_free(self._h, int(bool(free))))
+
+    def get_camera(self):
+        cam = np.zeros(9)
+        self._check(self.lib.rsba_cuda_get_camera(self._h, _addr(cam)))
+        return cam
+
+    def intrinsics_jacobian(self, num_obs=None):
+        n = self.num_obs if num_obs is None else num_obs
+        Jc = np.zeros((n, 18))
+        self._check(self.lib.rsba_cuda_get_intrinsics_jacobian(self._h, _addr(Jc)))
+        return Jc
 
     def set_loss(self, huber_a: float):
         """``ceres::HuberLoss(huber_a)`` on every residual block (CeresHandler.h:85-90); 0 = none."""

@@ -19,6 +19,10 @@ struct CameraModel {
   int shutter;         // 0 GLOBAL, 1 HORIZONTAL, 2 VERTICAL
   int interp_rot;      // opt.model.interpolateRotation
   double huber;        // ceres::HuberLoss(a) on every residual block (CeresHandler.h:85-90); 0 = no loss
+  // Uncalibrated variant (RsBundleAdjustment::CreateWithCam <2; 9, 6, 6, 3>, VideoSfmBaRs.h:38-49,68-80): the
+  // shared intrinsics are a PARAMETER block.  It lives behind the frames in the pose array, as a
+  // pseudo-frame: poses[cam_offset .. cam_offset+8] = fx fy k1 k2 p1 p2 k3 cx cy; -1 = calibrated.
+  long cam_offset;
 };
 
 // Observation SoA, sorted by frame.
@@ -56,8 +60,9 @@ inline bool first_use_on_device(bool (&seen)[64]) {
 
 // ---- launchers (definitions in the .cu files); all asynchronous on `stream` ------------
 // K1: residual + Jacobian (+ per-CTA cost partials, invalid count).
+// jac_cam: [N][2][9] Jacobian w.r.t. the intrinsics (only with cm.cam_offset >= 0; may be NULL)
 void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
-               double* residuals, double* jac, unsigned char* valid, double* cost_partials,
+               double* residuals, double* jac, double* jac_cam, unsigned char* valid, double* cost_partials,
                int* invalid_count, cudaStream_t stream);
 // K1r: cost only at trial parameters.
 void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,

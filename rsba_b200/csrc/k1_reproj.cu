@@ -52,12 +52,19 @@ __device__ __forceinline__ int stage_poses(const ObsView& obs, const double* __r
   return f_lo;
 }
 
-template <bool JAC>
+template <bool JAC, bool CAM>
 __global__ void __launch_bounds__(kK1Threads)
-k1_kernel(const CameraModel cm, const ObsView obs, const double* __restrict__ poses,
+k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__ poses,
           const double* __restrict__ points, double* __restrict__ residuals,
-          double* __restrict__ jac, unsigned char* __restrict__ valid,
+          double* __restrict__ jac, double* __restrict__ jac_cam, unsigned char* __restrict__ valid,
           double* __restrict__ cost_partials, int* __restrict__ invalid_count) {
+  CameraModel cm_local;
+  if (CAM) {   // uncalibrated: the intrinsics are parameters, read at the point of evaluation
+    cm_local = cm_in;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) cm_local.cam[k] = __ldg(poses + cm_in.cam_offset + k);
+  }
+  const CameraModel& cm = CAM ? cm_local : cm_in;
   __shared__ double s_pose[kStageFrames * kFrameParams];
   __shared__ double s_cost[kK1Warps];
   extern __shared__ __align__(128) double s_jac[];  // [warps][32][30], JAC only
@@ -88,7 +95,9 @@ k1_kernel(const CameraModel cm, const ObsView obs, const double* __restrict__ po
 #pragma unroll
       for (int k = 0; k < kFrameParams; ++k) pose[k] = __ldg(gp + k);
     }
-    Proj pr = reproject<JAC>(cm, o.x, o.y, pose, X0, X1, X2, Jrow);
+    double Jc[CAM ? 18 : 1];
+    constexpr bool want_cam = JAC && CAM;
+    Proj pr = reproject<JAC>(cm, o.x, o.y, pose, X0, X1, X2, Jrow, want_cam ? Jc : nullptr);
     cost = pr.r0 * pr.r0 + pr.r1 * pr.r1;
     bad = !pr.ok;
     // ceres::HuberLoss(a) through Ceres' Corrector (third-party; CeresHandler.h:85-90 passes the loss to
@@ -103,7 +112,16 @@ k1_kernel(const CameraModel cm, const ObsView obs, const double* __restrict__ po
       if (JAC) {
 #pragma unroll
         for (int k = 0; k < kJacDoubles; ++k) Jrow[k] *= w;
+        if (want_cam) {
+#pragma unroll
+          for (int k = 0; k < 18; ++k) Jc[k] *= w;
+        }
       }
+    }
+    if (want_cam) {
+      double2* dst = reinterpret_cast<double2*>(jac_cam + 18 * i);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dst[k] = make_double2(Jc[2 * k], Jc[2 * k + 1]);
     }
     if (residuals) reinterpret_cast<double2*>(residuals)[i] = make_double2(pr.r0, pr.r1);
     if (valid) valid[i] = pr.ok ? 1 : 0;
@@ -165,6 +183,10 @@ validate_kernel(const CameraModel cm, const ObsView obs, const double* __restric
   const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
   CameraModel plain = cm;
   plain.huber = 0.0;
+  if (cm.cam_offset >= 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) plain.cam[k] = __ldg(poses + cm.cam_offset + k);
+  }
   const Proj pr = reproject<false, true>(plain, o.x, o.y, pose, X0, X1, X2, nullptr);
   // camera centre at the observation's scan line (interpolate, mat/cam.h:294-311)
   double tau = 0.0;
@@ -201,21 +223,29 @@ reduce_partials_kernel(const double* __restrict__ partials, int n, double* __res
 int k1_num_partials(long n) { return (int)((n + kK1Threads - 1) / kK1Threads); }
 
 void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
-               double* residuals, double* jac, unsigned char* valid, double* cost_partials,
+               double* residuals, double* jac, double* jac_cam, unsigned char* valid, double* cost_partials,
                int* invalid_count, cudaStream_t stream) {
   if (obs.n <= 0) return;
   const int grid = k1_num_partials(obs.n);
   const size_t smem = (size_t)kK1Threads * kJacDoubles * sizeof(double);
-  k1_kernel<true><<<grid, kK1Threads, smem, stream>>>(cm, obs, poses, points, residuals, jac, valid,
-                                                      cost_partials, invalid_count);
+  if (cm.cam_offset >= 0)
+    k1_kernel<true, true><<<grid, kK1Threads, smem, stream>>>(cm, obs, poses, points, residuals, jac, jac_cam, valid,
+                                                              cost_partials, invalid_count);
+  else
+    k1_kernel<true, false><<<grid, kK1Threads, smem, stream>>>(cm, obs, poses, points, residuals, jac, nullptr, valid,
+                                                               cost_partials, invalid_count);
 }
 
 void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
                 double* cost_partials, int* invalid_count, cudaStream_t stream) {
   if (obs.n <= 0) return;
   const int grid = k1_num_partials(obs.n);
-  k1_kernel<false><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, nullptr, nullptr, nullptr,
-                                                    cost_partials, invalid_count);
+  if (cm.cam_offset >= 0)
+    k1_kernel<false, true><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, nullptr, nullptr, nullptr, nullptr,
+                                                            cost_partials, invalid_count);
+  else
+    k1_kernel<false, false><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, nullptr, nullptr, nullptr, nullptr,
+                                                             cost_partials, invalid_count);
 }
 
 void launch_validate(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,

@@ -96,6 +96,7 @@ int ensure_eval_buffers(rsba_problem* h, bool jac) {
   RSBA_CUDA_TRY(h->d_scalars.resize(16));
   RSBA_CUDA_TRY(h->d_invalid.resize(4));
   if (jac) RSBA_CUDA_TRY(h->d_jac.resize((size_t)kJacDoubles * n));
+  if (jac && h->free_cam) RSBA_CUDA_TRY(h->d_jac_cam.resize((size_t)18 * n));
   return RSBA_OK;
 }
 
@@ -107,7 +108,7 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
   const Stage st = jac ? kStageJacobian : kStageResidual;
   stage_begin(h, st);
   if (jac) {
-    launch_k1(h->cm, h->obs_view(), poses, points, h->d_res.ptr, h->d_jac.ptr, h->d_valid.ptr,
+    launch_k1(h->cm, h->obs_view(), poses, points, h->d_res.ptr, h->d_jac.ptr, h->d_jac_cam.ptr, h->d_valid.ptr,
               h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
   } else {
     launch_k1r(h->cm, h->obs_view(), poses, points, h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
@@ -234,7 +235,9 @@ static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr
   h->n_obs_global = n;
   h->n_frames = n_frames;
   h->n_points = n_points;
-  RSBA_CUDA_TRY(h->d_poses.resize((size_t)kFrameParams * n_frames));
+  RSBA_CUDA_TRY(h->d_poses.resize((size_t)kFrameParams * (n_frames + 1)));   // + the intrinsics pseudo-frame
+  RSBA_CUDA_TRY(cudaMemsetAsync(h->d_poses.ptr, 0, h->d_poses.bytes(), h->stream));
+  h->cm.cam_offset = h->free_cam ? (long)kFrameParams * n_frames : -1;
   RSBA_CUDA_TRY(h->d_points.resize((size_t)kPointParams * n_points));
   int rc = materialize_local_share(h);
   if (rc) return rc;
@@ -467,7 +470,57 @@ int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter, con
   h->cm.scan0 = (double)scanlines[0];
   h->cm.scan_span = (double)(scanlines[1] - scanlines[0]);
   h->cm.interp_rot = interpolate_rotation ? 1 : 0;   // (cm.huber is set by rsba_cuda_set_loss and kept)
+  h->cm.cam_offset = (h->free_cam && h->scene_set) ? (long)kFrameParams * h->n_frames : -1;
   h->camera_set = true;
+  if (h->free_cam && h->scene_set) {   // the intrinsics are parameters: refresh their device copy
+    RSBA_CUDA_TRY(cudaSetDevice(h->device));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr + h->cm.cam_offset, h->cm.cam, 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_intrinsics_free(rsba_problem* h, int free_intrinsics) {
+  if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
+  const bool want = free_intrinsics != 0;
+  if (want == h->free_cam) return RSBA_OK;
+  h->free_cam = want;
+  h->cm.cam_offset = (want && h->scene_set) ? (long)kFrameParams * h->n_frames : -1;
+  if (h->lm) {   // one more block in the reduced system
+    lm_state_free(h->lm);
+    h->lm = nullptr;
+  }
+  if (want && h->scene_set && h->camera_set) {
+    RSBA_CUDA_TRY(cudaSetDevice(h->device));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr + h->cm.cam_offset, h->cm.cam, 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return RSBA_OK;
+}
+
+int rsba_cuda_get_camera(rsba_problem* h, double cam9[9]) {
+  if (!h || !cam9) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!h->camera_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_camera has not been called");
+  if (h->free_cam && h->scene_set && h->params_set) {
+    RSBA_CUDA_TRY(cudaSetDevice(h->device));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->cm.cam, h->d_poses.ptr + (size_t)kFrameParams * h->n_frames, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  memcpy(cam9, h->cm.cam, 9 * sizeof(double));
+  return RSBA_OK;
+}
+
+int rsba_cuda_get_intrinsics_jacobian(rsba_problem* h, double* jacobian_cam) {
+  if (!h || !jacobian_cam) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!h->free_cam || h->d_jac_cam.count == 0) return fail(RSBA_ERR_STATE, "no intrinsics Jacobian: set_intrinsics_free + evaluate first");
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  const long n = h->n_obs, ng = h->n_obs_global;
+  std::vector<double> tmp((size_t)18 * n);
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (n) RSBA_CUDA_TRY(cudaMemcpy(tmp.data(), h->d_jac_cam.ptr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  memset(jacobian_cam, 0, (size_t)18 * ng * sizeof(double));
+  for (long i = 0; i < n; ++i)
+    memcpy(jacobian_cam + 18 * h->order[h->local_ids[i]], &tmp[18 * (size_t)i], 18 * sizeof(double));
   return RSBA_OK;
 }
 
@@ -619,7 +672,11 @@ int rsba_cuda_set_parameters(rsba_problem* h, const double* poses, const double*
   if ((h->n_frames && !poses) || (h->n_points && !points)) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   if (h->n_frames)
-    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr, poses, h->d_poses.bytes(), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr, poses, (size_t)kFrameParams * h->n_frames * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (h->free_cam) {
+    if (!h->camera_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_camera before rsba_cuda_set_parameters (free intrinsics)");
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr + (size_t)kFrameParams * h->n_frames, h->cm.cam, 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
   if (h->n_points)
     RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_points.ptr, points, h->d_points.bytes(), cudaMemcpyHostToDevice, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -631,7 +688,7 @@ int rsba_cuda_get_parameters(rsba_problem* h, double* poses, double* points) {
   if (!h || !h->scene_set || !h->params_set) return fail(RSBA_ERR_STATE, "no parameters on the device");
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   if (poses && h->n_frames)
-    RSBA_CUDA_TRY(cudaMemcpyAsync(poses, h->d_poses.ptr, h->d_poses.bytes(), cudaMemcpyDeviceToHost, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(poses, h->d_poses.ptr, (size_t)kFrameParams * h->n_frames * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (points && h->n_points)
     RSBA_CUDA_TRY(cudaMemcpyAsync(points, h->d_points.ptr, h->d_points.bytes(), cudaMemcpyDeviceToHost, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));

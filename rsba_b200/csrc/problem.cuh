@@ -97,6 +97,12 @@ struct rsba_problem {
   rsba::DeviceBuffer<int> d_obs_frame, d_obs_point;
   rsba::DeviceBuffer<double> d_poses, d_points;
   rsba::DeviceBuffer<double> d_res, d_jac;
+  // uncalibrated variant: the shared intrinsics are the 9 leading parameters of a pseudo-frame stored
+  // behind the real frames in d_poses (which always has room for it); d_jac_cam = [N][2][9]
+  bool free_cam = false;
+  double* ptr_cam = nullptr;               // pointer API: the caller's intrinsics block
+  rsba::DeviceBuffer<double> d_jac_cam;
+  int n_cam_frames() const { return n_frames + (free_cam ? 1 : 0); }
   rsba::DeviceBuffer<unsigned char> d_valid;
   rsba::DeviceBuffer<double> d_cost_partials;
   rsba::DeviceBuffer<double> d_scalars;    // [0] cost, misc

@@ -24,7 +24,8 @@ template <bool JAC, bool TAU_FROM_Y = false, bool VALIDATE = true>
 __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double ox, double oy,
                                           const double* __restrict__ p0,  // frame: pose0|pose1
                                           double X0, double X1, double X2,
-                                          double* __restrict__ J /* [30], smem, JAC only */) {
+                                          double* __restrict__ J /* [30], smem, JAC only */,
+                                          double* __restrict__ Jcam = nullptr /* [18] = [2][9], JAC only */) {
   Proj out;
   // ---- interpolate_rs (mat/cam.h:316-349): tau is a constant of the observation
   double tau = 0.0, wr0 = 1.0, wr1 = 0.0;
@@ -121,6 +122,10 @@ __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double
     if (JAC) {
 #pragma unroll
       for (int k = 0; k < kJacDoubles; ++k) J[k] = 0.0;
+      if (Jcam) {
+#pragma unroll
+        for (int k = 0; k < 18; ++k) Jcam[k] = 0.0;
+      }
     }
     return out;
   }
@@ -138,6 +143,19 @@ __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double
   out.r0 = (px * fx + cm.cam[7]) - ox;
   out.r1 = (py * fy + cm.cam[8]) - oy;
 
+  if (JAC && Jcam) {
+    // d residual / d (fx fy k1 k2 p1 p2 k3 cx cy): c2i + distort (mat/cam.h:372-395, 49-72) differentiated
+    const double r4 = r2 * r2, r6 = r4 * r2;
+    Jcam[0] = px;            Jcam[9] = 0.0;
+    Jcam[1] = 0.0;           Jcam[10] = py;
+    Jcam[2] = fx * xp * r2;  Jcam[11] = fy * yp * r2;
+    Jcam[3] = fx * xp * r4;  Jcam[12] = fy * yp * r4;
+    Jcam[4] = fx * 2.0 * xy; Jcam[13] = fy * (r2 + 2.0 * yp * yp);
+    Jcam[5] = fx * (r2 + 2.0 * xp * xp); Jcam[14] = fy * 2.0 * xy;
+    Jcam[6] = fx * xp * r6;  Jcam[15] = fy * yp * r6;
+    Jcam[7] = 1.0;           Jcam[16] = 0.0;
+    Jcam[8] = 0.0;           Jcam[17] = 1.0;
+  }
   if (JAC) {
     // d(px,py)/d(xp,yp)
     const double dd = k1 + r2 * (2.0 * k2 + 3.0 * k3 * r2);

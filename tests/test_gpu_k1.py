@@ -194,3 +194,25 @@ def test_validate_sweep_matches_reference_predicate(api, oracle_built, shutter):
         pb.load_scene(sc2, poses=sc2.poses_true, points=sc2.points_true)
         ok2, err2 = pb.validate()
     assert ok2.all() and err2.max() < 16.0
+
+
+@pytest.mark.parametrize("shutter,interp", [(1, True), (2, False), (0, True)])
+def test_k1_uncalibrated_intrinsics_jacobian(api, oracle_built, shutter, interp):
+    """<2; 9, 6, 6, 3> (RsBundleAdjustment::CreateWithCam, VideoSfmBaRs.h:38-49,68-80): residual, pose/point
+    Jacobian unchanged, plus d residual / d (fx fy k1 k2 p1 p2 k3 cx cy) against the reference's own
+    ReprojectionError::operator()(camera, ...) under Jet<24> and the numpy closed form."""
+    sc = edge_scene(shutter, interp)
+    with api.Problem(0) as pb:
+        pb.set_intrinsics_free(True)
+        pb.load_scene(sc)
+        cost, r, J, v = pb.evaluate(check=False)
+        Jc = pb.intrinsics_jacobian()
+        assert np.array_equal(pb.get_camera(), sc.cam)
+    r0, J0, v0 = oracle_built.evaluate(sc, impl="port")
+    check(sc, (cost, r, J, v), (r0, J0, v0))
+    want = oracle_built.intrinsics_jacobian(sc)
+    ok = v0 == 1
+    assert rel_block_err(Jc[ok], want[ok]).max() <= TOL and not Jc[~ok].any()
+    if oracle_built.ref_available():
+        _, _, Jref, vref = oracle_built.evaluate_cam_ref(sc)
+        assert np.array_equal(v, vref) and rel_block_err(Jc[ok], Jref[ok]).max() <= TOL
