@@ -213,9 +213,11 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
 /* One linearisation at the current parameters, for parity tests and profiling: builds the
  * normal equations, applies Jacobi scaling + the LM diagonal for `radius`, eliminates the
  * points, factorises and solves.  HOST outputs, any may be NULL:
- *   S[n*n] (row-major, n = 12*frames, full symmetric), rhs[n]  -- reduced system in the
+ *   (n = 12*frames; with free intrinsics n = 12*(frames+1): the intrinsics are parameters 0..8 of a last
+ *    pseudo-frame whose parameters 9..11 are constant)
+ *   S[n*n] (row-major, full symmetric), rhs[n]  -- reduced system in the
  *     scaled space, constant parameters replaced by identity rows;
- *   delta_poses[12*frames], delta_points[3*points]            -- unscaled LM step;
+ *   delta_poses[n], delta_points[3*points]                    -- unscaled LM step;
  *   model_cost_change.
  * Does not move the parameters. */
 int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt, double radius,

@@ -91,8 +91,27 @@ def jacobi_scale(Js, active, enabled=True):
     return s
 
 
+def with_intrinsics_block(scene, J, Jcam):
+    """Uncalibrated variant <2; 9, 6, 6, 3>: the shared intrinsics as a pseudo-frame behind the real frames
+    (parameters 0..8 = fx fy k1 k2 p1 p2 k3 cx cy, 9..11 constant) -- the parameter ordering of the device
+    path.  Returns (scene', pose_mask', extra_columns) for lm_step: scene' has F+1 frames, the extra
+    columns are the dense [2N, 12] block of the pseudo-frame."""
+    import copy
+    F = scene.num_frames
+    sc = copy.copy(scene)
+    sc.poses = np.vstack([scene.poses, np.concatenate([scene.cam, np.zeros(3)])[None, :]])
+    sc.const_frames = np.concatenate([np.asarray(scene.const_frames, dtype=bool), [False]])
+    mask = np.where(sc.const_frames, 0xFFF, 0).astype(np.int64)
+    mask[F] = 0xE00
+    N = scene.num_obs
+    cols = np.zeros((2 * N, 12))
+    cols[0::2, :9] = Jcam[:, :9]
+    cols[1::2, :9] = Jcam[:, 9:]
+    return sc, mask, cols
+
+
 def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mask=None, point_const=None,
-            want_S=True, extra=None):
+            want_S=True, extra=None, cam_cols=None):
     """One linear solve of the LM subproblem.  Returns a dict with the reduced system
     ``S delta_c' = rhs`` (scaled space, constant parameters as identity rows), the unscaled
     step and model_cost_change."""
@@ -102,6 +121,12 @@ def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mas
     active = np.concatenate([act_c, act_p])
     Js = sparse_jacobian(scene, J, active)
     rr = r.reshape(-1)
+    if cam_cols is not None:
+        # dense columns of the intrinsics pseudo-frame (the LAST frame of `scene`, see with_intrinsics_block)
+        c0 = 12 * (F - 1)
+        Js = Js.tolil()
+        Js[:, c0:c0 + 12] = cam_cols * active[c0:c0 + 12][None, :]
+        Js = Js.tocsr()
     if extra is not None:
         # additional residual blocks (camera-only motion priors): rows over the same parameter vector
         Jx, rx = extra

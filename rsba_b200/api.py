@@ -243,6 +243,7 @@ class Problem:
     def set_intrinsics_free(self, free=True):
         """Uncalibrated variant <2; 9, 6, 6, 3> (VideoSfmBaRs.h:38-49): the shared intrinsics are optimised."""
         self._check(self.lib.rsba_cuda_set_intrinsics_free(self._h, int(bool(free))))
+        self.free_intrinsics = bool(free)
 
     def get_camera(self):
         cam = np.zeros(9)
@@ -407,10 +408,11 @@ class Problem:
             self._check(self.lib.rsba_cuda_linearize_and_step(self._h, C.byref(options), float(radius), None,
                                                               None, None, None, C.byref(mcc)))
             return dict(model_cost_change=mcc.value)
-        n = 12 * self.num_frames
+        nf = self.num_frames + (1 if getattr(self, "free_intrinsics", False) else 0)   # + intrinsics pseudo-frame
+        n = 12 * nf
         S = np.zeros((n, n)) if want_S else None
         rhs = np.zeros(n)
-        dposes = np.zeros((self.num_frames, 12))
+        dposes = np.zeros((nf, 12))
         dpoints = np.zeros((self.num_points, 3))
         mcc = C.c_double(0.0)
         self._check(self.lib.rsba_cuda_linearize_and_step(self._h, C.byref(options), float(radius), _addr(S),

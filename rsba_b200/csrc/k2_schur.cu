@@ -237,7 +237,7 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
 // unscaled block  [a == b] B_f - sum of the pair's partial products  into quadrant (b%2, a%2) of
 // Cholesky tile (b/2, a/2) at its (permuted) place.
 __global__ void __launch_bounds__(256)
-schur_reduce_kernel(SchurStructure st, NormalEq ne, PriorView pv, double* __restrict__ S,
+schur_reduce_kernel(SchurStructure st, NormalEq ne, PriorView pv, int cam_frame, double* __restrict__ S,
                     const int* __restrict__ tile_slot, int T) {
   const int pr = blockIdx.x;
   const int a = st.pair_a[pr], b = st.pair_b[pr];
@@ -259,6 +259,11 @@ schur_reduce_kernel(SchurStructure st, NormalEq ne, PriorView pv, double* __rest
     if (fr == fc) {
       if ((long)fr * kFrameParams < st.n_cam_params)
         val += ne.B[(long)fr * 144 + (r % kFrameParams) * 12 + c % kFrameParams];
+    } else if (fc == cam_frame || fr == cam_frame) {
+      // uncalibrated variant: coupling of a real frame with the intrinsics pseudo-frame
+      const int rp = r % kFrameParams, cp = c % kFrameParams;
+      if (fr == cam_frame) val += ne.Bcam[(long)fc * 144 + cp * 12 + rp];     // rows = intrinsics, cols = frame
+      else                 val += ne.Bcam[(long)fr * 144 + rp * 12 + cp];
     } else if (pv.n > 0 && (r % 6) == (c % 6) && (long)fr * kFrameParams < st.n_cam_params &&
                (long)fc * kFrameParams < st.n_cam_params) {
       // motion-prior coupling between a frame and its previous frame: 6x6 diagonal blocks
@@ -334,9 +339,10 @@ void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
   schur_syrk_kernel<<<st.n_items, 128, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
 }
 
-void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, double* S,
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, int cam_frame, double* S,
                          const int* tile_slot, int n_tiles, cudaStream_t s) {
-  if (st.n_pairs > 0) schur_reduce_kernel<<<dim3(st.n_pairs, 3), 256, 0, s>>>(st, ne, pv, S, tile_slot, n_tiles);
+  if (st.n_pairs > 0)
+    schur_reduce_kernel<<<dim3(st.n_pairs, 3), 256, 0, s>>>(st, ne, pv, cam_frame, S, tile_slot, n_tiles);
 }
 
 void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,

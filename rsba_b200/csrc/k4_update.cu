@@ -70,7 +70,8 @@ frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* _
 constexpr int kPointStepWarps = 8;
 
 __global__ void __launch_bounds__(kPointStepWarps * 32)
-point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne,
+point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac,
+                  const double* __restrict__ jac_cam, int cam_frame, NormalEq ne,
                   const double* __restrict__ delta_c, int n_points, const double* __restrict__ points,
                   double* __restrict__ delta_p, double* __restrict__ trial, double* __restrict__ scratch) {
   __shared__ double sh[32];
@@ -94,6 +95,15 @@ point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
           m0 += r0.x * d.x + r0.y * d.y;
           m1 += r1.x * d.x + r1.y * d.y;
         }
+      if (jac_cam) {   // uncalibrated variant: + Jcam * delta_intrinsics
+        const double* jc = jac_cam + i * 18;
+        const double* di = delta_c + 12L * cam_frame;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          m0 += jc[k] * di[k];
+          m1 += jc[9 + k] * di[k];
+        }
+      }
       const double2 x0 = J[12], x1 = J[13], x2 = J[14];
       a0 += x0.x * m0 + x1.y * m1;
       a1 += x0.y * m0 + x2.x * m1;
@@ -208,14 +218,15 @@ constexpr int kStateBlocks = 296;
 
 }  // namespace
 
-void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
+                        int cam_frame, NormalEq ne,
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
                         double* trial_points, double* scalars, double* scratch, cudaStream_t s) {
   frame_step_kernel<<<1, kWideThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
   const int nb = (n_points + kPointStepWarps - 1) / kPointStepWarps;
   if (nb > 0)
-    point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, obs, jac, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
+    point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, obs, jac, jac_cam, cam_frame, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
   step_final_kernel<<<1, kWideThreads, 0, s>>>(scratch, nb, scalars);
 }
 

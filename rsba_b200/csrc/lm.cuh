@@ -36,6 +36,7 @@ struct SchurStructure {
   // memory: obs_phi_off[i] = offset (doubles) of observation i's 12 rows inside Phi, or -1 for
   // observations of constant points and of incidences with two observations in one frame slot;
   // the latter (dup_inc) are rebuilt by phi_build_kernel, which sums the slot's observations.
+  const int* cam_inc;      // [P] uncalibrated variant: the point's incidence that holds the pseudo-frame rows, or -1
   const int* obs_phi_off;  // [N]
   const int* dup_inc;      // [n_dup]
   int n_dup;
@@ -74,6 +75,7 @@ struct NormalEq {
   double* gp;       // [P][3]
   double* Cinv;     // [P][6]    s_p (s_p C s_p + D^2)^-1 s_p  (zero for constant points)
   double* tp;       // [P][3]    Cinv * gp
+  double* Bcam;     // [F][144] uncalibrated variant: coupling of frame f (rows) with the intrinsics pseudo-frame (cols 0..8)
   double* Minv;     // [P][6]    L^-1 of the damped scaled point block (m00 m10 m11 m20 m21 m22)
   double* Phi;      // [n_inc+1][3][kPanelLd]  panels s_c Jc^T (Jx s_p) L^-T; last panel all zero
   double* partial;  // [n_items][48*48] per-item partial products of the Schur SYRK
@@ -98,6 +100,13 @@ void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const dou
                          int n_frames, NormalEq ne, bool with_wf, cudaStream_t s);
 void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, cudaStream_t s);
 void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s);
+// uncalibrated variant (k2_cam.cu): blocks of the intrinsics pseudo-frame (frame index n_frames) and its panel rows
+void launch_cam_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
+                       const double* res, NormalEq ne, int n_frames, double* partials, double* scratch,
+                       cudaStream_t s);
+void launch_phi_cam(const SchurStructure& st, const double* jac, const double* jac_cam, NormalEq ne, int n_points,
+                    int n_frames, cudaStream_t s);
+
 // adds the priors' J^T J / J^T r to B, gc, diagB and writes the frame-to-previous-frame couplings
 void launch_prior_blocks(const PriorView& pv, NormalEq ne, int n_frames, cudaStream_t s);
 
@@ -107,7 +116,8 @@ void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double
                       cudaStream_t s);
 void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s);
 // writes the UNSCALED tiles  B - Phi Phi^T  (partial sums on a multi-GPU rank)
-void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, double* S,
+// cam_frame: index of the intrinsics pseudo-frame (uncalibrated variant) or -1
+void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, int cam_frame, double* S,
                          const int* tile_slot, int n_tiles, cudaStream_t s);
 // after the (optional) all-reduce: Jacobi scaling, LM diagonal, constant rows, padding; d2_c and rhs
 struct TileSchedule;
@@ -148,7 +158,9 @@ struct StepScalars {  // device doubles, filled by launch_step_update
   double g_dot_delta, d2_delta2, step_norm2, x_norm2, gmax;
 };
 // delta_c = -scale_c * y ; delta_p by back-substitution ; trial = x + delta ; scalars
-void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+// jac_cam / cam_frame: uncalibrated variant (NULL / -1 otherwise)
+void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
+                        int cam_frame, NormalEq ne,
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
                         double* trial_points, double* scalars /* [16]: [0..2] camera part, [8..10] point part */,

@@ -22,7 +22,10 @@ struct LmState {
   // ---- structure (device)
   DeviceBuffer<int> pt_ptr, pt_obs, chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr;
   DeviceBuffer<int> inc_point, inc_tile, slot_beg, pair_a, pair_b, pair_item_ptr, tile_pos, pos_tile;
-  DeviceBuffer<int> obs_phi_off, dup_inc;
+  DeviceBuffer<int> obs_phi_off, dup_inc, cam_inc;
+  DeviceBuffer<double> Bcam, cam_partials, cam_scratch;
+  bool free_cam = false;
+  int n_cam_frames = 0;          // frames of the camera system: real frames (+ the intrinsics pseudo-frame)
   DeviceBuffer<unsigned char> slot_cnt, point_owned;
   DeviceBuffer<int4> items;
   DeviceBuffer<int2> entries;
@@ -90,6 +93,8 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   };
   const long N = h->n_obs;
   const int F = h->n_frames, P = h->n_points;
+  const bool free_cam = h->free_cam;
+  const int Fc = h->n_cam_frames();    // + the intrinsics pseudo-frame (uncalibrated variant)
   const std::vector<int>& fr = h->h_obs_frame;
   const std::vector<int>& pt = h->h_obs_point;
   cudaStream_t s = h->stream;
@@ -104,7 +109,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     for (long i = 0; i < N; ++i) pt_obs[cur[pt[i]]++] = (int)i;
   }
   // frame chunks of <= 128 observations
-  std::vector<int> chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr(F + 1, 0);
+  std::vector<int> chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr(Fc + 1, 0);
   {
     long i = 0;
     for (int f = 0; f < F; ++f) {
@@ -118,14 +123,15 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
       }
       i = j;
     }
-    frame_chunk_ptr[F] = (int)chunk_frame.size();
+    for (int f = F; f <= Fc; ++f) frame_chunk_ptr[f] = (int)chunk_frame.size();   // the pseudo-frame has no observations
   }
   lap("point CSR + frame chunks");
   // ---- Schur SYRK structure: (frame tile, point) incidences, tile pairs, work items
-  const int T = (int)((12L * F + kTile - 1) / kTile);
+  const int T = (int)((12L * Fc + kTile - 1) / kTile);
   const int H = 2 * T;                                   // sub-tiles of 4 frames
-  const int Hreal = (F + kSubFrames - 1) / kSubFrames;   // ... that hold at least one frame
-  std::vector<int> inc_point, inc_tile, slot_beg, pt_inc_ptr(P + 1, 0);
+  const int Hreal = (Fc + kSubFrames - 1) / kSubFrames;  // ... that hold at least one frame
+  const int cam_sub = F / kSubFrames, cam_slot = F % kSubFrames;   // where the pseudo-frame sits
+  std::vector<int> inc_point, inc_tile, slot_beg, pt_inc_ptr(P + 1, 0), cam_inc(std::max(P, 1), -1);
   std::vector<unsigned char> slot_cnt;
   for (int p = 0; p < P; ++p) {
     pt_inc_ptr[p] = (int)inc_point.size();
@@ -146,7 +152,20 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
       if (slot_cnt[sl] == 255) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
       slot_cnt[sl]++;
     }
+    if (free_cam && e > b) {
+      // every eliminated point also couples with the intrinsics: its panel in the pseudo-frame's sub-tile
+      // (shared with the last real frames when F is not a multiple of 4) gets the pseudo-frame rows
+      if (last < 0 || inc_tile[last] != cam_sub) {
+        last = (int)inc_point.size();
+        inc_point.push_back(p);
+        inc_tile.push_back(cam_sub);
+        slot_beg.insert(slot_beg.end(), kSubFrames, -1);
+        slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
+      }
+      cam_inc[p] = last;
+    }
   }
+  (void)cam_slot;
   pt_inc_ptr[P] = (int)inc_point.size();
   lap("incidences");
   const int n_inc = (int)inc_point.size();
@@ -275,7 +294,10 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
       std::sort(tp.begin(), tp.end());
       tp.erase(std::unique(tp.begin(), tp.end()), tp.end());
     }
-    build_tile_plan(T, tp, dense, h->reorder_tiles, &plan);
+    const int border_tile = free_cam ? F / kFramesPerTile : -1;   // couples with everything: eliminated last
+    if (free_cam && h->world > 1)
+      for (int a = 0; a < T; ++a) tp.emplace_back(std::min(a, border_tile), std::max(a, border_tile));
+    build_tile_plan(T, tp, dense, h->reorder_tiles, border_tile, &plan);
   }
   const std::vector<int>& tile_pos = plan.tile_pos;
   const std::vector<int2>& nz_tiles = plan.nz_tiles;
@@ -287,13 +309,19 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(pt_ptr, pt_ptr); UP(pt_obs, pt_obs); UP(chunk_frame, chunk_frame); UP(chunk_beg, chunk_beg);
   UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr);
   UP(inc_point, inc_point); UP(inc_tile, inc_tile); UP(slot_beg, slot_beg); UP(slot_cnt, slot_cnt);
-  UP(obs_phi_off, obs_phi_off); UP(dup_inc, dup_inc);
+  UP(obs_phi_off, obs_phi_off); UP(dup_inc, dup_inc); UP(cam_inc, cam_inc);
   UP(pair_a, pair_a); UP(pair_b, pair_b); UP(pair_item_ptr, pair_item_ptr); UP(items, items); UP(tile_pos, tile_pos);
   UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
   UP(entries, entries); UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
   UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
   UP(panels, plan.panels); UP(trsm, plan.trsm);
-  UP(pose_mask, h->pose_mask); UP(point_const, h->point_const);
+  {
+    std::vector<unsigned short> mask(h->pose_mask);
+    mask.resize(Fc, 0);
+    if (free_cam) mask[F] = 0xE00;   // parameters 9..11 of the pseudo-frame do not exist
+    UP(pose_mask, mask);
+  }
+  UP(point_const, h->point_const);
 #undef UP
   lm->dense = dense;
   lm->reorder = h->reorder_tiles;
@@ -306,13 +334,22 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.n_inc = n_inc; st.inc_point = lm->inc_point.ptr; st.inc_tile = lm->inc_tile.ptr;
   st.slot_beg = lm->slot_beg.ptr; st.slot_cnt = lm->slot_cnt.ptr;
   st.obs_phi_off = lm->obs_phi_off.ptr; st.dup_inc = lm->dup_inc.ptr; st.n_dup = (int)dup_inc.size();
+  st.cam_inc = lm->cam_inc.ptr;
   st.n_pairs = (int)pair_a.size(); st.pair_a = lm->pair_a.ptr; st.pair_b = lm->pair_b.ptr;
   st.pair_item_ptr = lm->pair_item_ptr.ptr; st.n_items = n_items; st.items = lm->items.ptr;
   st.entries = lm->entries.ptr; st.n_entries = (long)entries.size(); st.tile_pos = lm->tile_pos.ptr;
-  st.pos_tile = lm->pos_tile.ptr; st.n_cam_params = 12L * F;
+  st.pos_tile = lm->pos_tile.ptr; st.n_cam_params = 12L * Fc;
+  lm->free_cam = free_cam;
+  lm->n_cam_frames = Fc;
 
   // ---- numeric buffers
-  const size_t Fz = std::max(F, 1), Pz = std::max(P, 1);
+  const size_t Fz = std::max(Fc, 1), Pz = std::max(P, 1);
+  if (free_cam) {
+    RSBA_CUDA_TRY(lm->Bcam.resize(Fz * 144));
+    RSBA_CUDA_TRY(cudaMemsetAsync(lm->Bcam.ptr, 0, lm->Bcam.bytes(), s));
+    RSBA_CUDA_TRY(lm->cam_partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 207));
+    RSBA_CUDA_TRY(lm->cam_scratch.resize(Fz * 99));
+  }
   RSBA_CUDA_TRY(lm->B.resize(Fz * 144));
   RSBA_CUDA_TRY(lm->C.resize(Pz * 6)); RSBA_CUDA_TRY(lm->gp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Cinv.resize(Pz * 6));
   RSBA_CUDA_TRY(lm->tp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Minv.resize(Pz * 6));
@@ -342,7 +379,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->d2_c.ptr, 0, lm->d2_c.bytes(), s));
 
   NormalEq& ne = lm->ne;
-  ne.B = lm->B.ptr; ne.C = lm->C.ptr; ne.gp = lm->gp.ptr;
+  ne.B = lm->B.ptr; ne.C = lm->C.ptr; ne.gp = lm->gp.ptr; ne.Bcam = lm->Bcam.ptr;
   ne.gc = lm->S.ptr + s_count; ne.wf = ne.gc + Fz * 12; ne.diagB = ne.wf + Fz * 12;
   lm->misc = ne.diagB + Fz * 12;
   ne.Cinv = lm->Cinv.ptr; ne.tp = lm->tp.ptr; ne.Minv = lm->Minv.ptr; ne.Phi = lm->Phi.ptr; ne.partial = lm->partial.ptr;
@@ -353,10 +390,11 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   TileSchedule& ts = lm->ts;
   ts.n_tiles = T; ts.nz_tiles = lm->nz_tiles.ptr; ts.tile_slot = lm->tile_slot.ptr; ts.n_nz = (int)nz_tiles.size();
   ts.row_ptr = lm->row_ptr.ptr; ts.rows = lm->rows.ptr; ts.upd = lm->upd.ptr; ts.panels = lm->panels.ptr; ts.trsm = lm->trsm.ptr;
-  ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.solve_partials = lm->solve_partials.ptr; ts.n_real = 12L * F;
+  ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.solve_partials = lm->solve_partials.ptr; ts.n_real = 12L * Fc;
 
   long free_params = 0;
   for (int f = 0; f < F; ++f) free_params += 12 - __builtin_popcount(h->pose_mask[f] & 0xFFF);
+  if (free_cam) free_params += 9;
   for (int p = 0; p < P; ++p) free_params += h->point_const[p] ? 0 : 3;
   lm->num_free_params = free_params;
   RSBA_CUDA_TRY(cudaStreamSynchronize(s));
@@ -365,7 +403,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
 }
 
 int ensure_lm(rsba_problem* h, bool dense) {
-  if (h->lm && h->lm->dense == dense && h->lm->reorder == h->reorder_tiles) return RSBA_OK;
+  if (h->lm && h->lm->dense == dense && h->lm->reorder == h->reorder_tiles && h->lm->free_cam == h->free_cam) return RSBA_OK;
   if (h->lm) { lm_state_free(h->lm); h->lm = nullptr; }
   LmState* lm = new LmState;
   int rc = build_structure(h, lm, dense);
@@ -398,9 +436,14 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   if (compute_scale) { launch_jacobi_scale(0, h->n_points, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
   launch_point_invert(h->n_points, lm->ne, o, s);
   stage_begin(h, kStageFrameBlocks);
-  launch_frame_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_frames, lm->ne, true, s);
+  launch_frame_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, lm->n_cam_frames, lm->ne, true, s);
   stage_end(h, kStageFrameBlocks);
   h->launches += 3;
+  if (lm->free_cam) {   // blocks of the intrinsics pseudo-frame and its couplings with the frames
+    launch_cam_blocks(lm->st, obs, h->d_jac.ptr, h->d_jac_cam.ptr, h->d_res.ptr, lm->ne, h->n_frames,
+                      lm->cam_partials.ptr, lm->cam_scratch.ptr, s);
+    h->launches += 3;
+  }
   const PriorView pv = h->prior_view();
   if (pv.n > 0 && h->rank == 0) {   // camera-only residual blocks: added once, not sharded
     launch_prior_blocks(pv, lm->ne, h->n_frames, s);
@@ -410,13 +453,17 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   stage_begin(h, kStagePhiBuild);
   launch_phi_build(lm->st, obs, h->d_jac.ptr, lm->ne, s);
   stage_end(h, kStagePhiBuild);
+  if (lm->free_cam) {
+    launch_phi_cam(lm->st, h->d_jac.ptr, h->d_jac_cam.ptr, lm->ne, h->n_points, h->n_frames, s);
+    h->launches += 1;
+  }
   stage_begin(h, kStageSchurSyrk);
   launch_schur_syrk(lm->st, lm->ne, s);
   stage_end(h, kStageSchurSyrk);
   stage_begin(h, kStageSchurReduce);
   PriorView pvr = pv;
   if (h->rank != 0) pvr.n = 0;
-  launch_schur_reduce(lm->st, lm->ne, pvr, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
+  launch_schur_reduce(lm->st, lm->ne, pvr, lm->free_cam ? h->n_frames : -1, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
   stage_end(h, kStageSchurReduce);
   h->launches += 4;
   if (new_jacobian) {   // scalars of the current point that ride in the same buffer
@@ -434,9 +481,9 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     if (rc) return rc;
   }
   stage_begin(h, kStageFinalize);
-  if (compute_scale) { launch_jacobi_scale(h->n_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
-  launch_schur_finalize(lm->st, lm->ne, o, lm->S.ptr, lm->ts, h->n_frames, lm->rhs.ptr, s);
-  launch_camera_norms(lm->ne, h->n_frames, h->d_poses.ptr, lm->scalars.ptr, s);
+  if (compute_scale) { launch_jacobi_scale(lm->n_cam_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
+  launch_schur_finalize(lm->st, lm->ne, o, lm->S.ptr, lm->ts, lm->n_cam_frames, lm->rhs.ptr, s);
+  launch_camera_norms(lm->ne, lm->n_cam_frames, h->d_poses.ptr, lm->scalars.ptr, s);
   h->launches += 3;
   stage_end(h, kStageFinalize);
   return RSBA_OK;
@@ -491,7 +538,8 @@ void factor_and_solve(rsba_problem* h, LmState* lm) {
 
 void step_update(rsba_problem* h, LmState* lm) {
   stage_begin(h, kStageUpdate);
-  launch_step_update(lm->st, h->obs_view(), h->d_jac.ptr, lm->ne, lm->y.ptr, h->n_frames, h->n_points,
+  launch_step_update(lm->st, h->obs_view(), h->d_jac.ptr, lm->free_cam ? h->d_jac_cam.ptr : nullptr,
+                     lm->free_cam ? h->n_frames : -1, lm->ne, lm->y.ptr, lm->n_cam_frames, h->n_points,
                      h->d_poses.ptr, h->d_points.ptr, lm->delta_c.ptr, lm->delta_p.ptr, lm->trial_poses.ptr,
                      lm->trial_points.ptr, lm->scalars.ptr, lm->scratch.ptr, h->stream);
   h->launches += 3;
@@ -682,7 +730,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
       }
       if (accepted) {
         sum->num_successful_steps++;
-        cudaMemcpyAsync(h->d_poses.ptr, lm->trial_poses.ptr, h->d_poses.bytes(), cudaMemcpyDeviceToDevice, h->stream);
+        cudaMemcpyAsync(h->d_poses.ptr, lm->trial_poses.ptr, 12L * lm->n_cam_frames * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         cudaMemcpyAsync(h->d_points.ptr, lm->trial_points.ptr, h->d_points.bytes(), cudaMemcpyDeviceToDevice, h->stream);
         radius = std::min(opt->max_trust_region_radius,
                           radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
@@ -715,6 +763,8 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
     }
   }
   if ((rc = gather_points(h, lm))) return rc;
+  if (lm->free_cam)   // the optimised intrinsics are also the host copy used by validate / pnp and returned by get_camera
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->cm.cam, h->d_poses.ptr + 12L * h->n_frames, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   sum->time_schur_ms += h->timers[kStageFinalize].total_ms;
   if (h->ptr_mode) {
@@ -735,7 +785,7 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
   rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
   if (rc) return rc;
   if ((rc = linearize(h, lm, *opt, radius, true, true))) return rc;
-  const long n = 12L * h->n_frames;
+  const long n = 12L * lm->n_cam_frames;   // uncalibrated variant: the intrinsics pseudo-frame comes last
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (S_out) {
     std::vector<double> tile((size_t)kTile * kTile);
@@ -786,7 +836,7 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
     tp.emplace_back(std::min(pair_a[k], pair_b[k]), std::max(pair_a[k], pair_b[k]));
   }
   TilePlan plan;
-  build_tile_plan(n_tiles, tp, dense != 0, reorder != 0, &plan);
+  build_tile_plan(n_tiles, tp, dense != 0, reorder != 0, -1, &plan);
   counts[0] = plan.n_levels; counts[1] = (long)plan.nz_tiles.size(); counts[2] = (long)plan.trsm.size();
   counts[3] = (long)plan.upd.size(); counts[4] = (long)plan.group_ptr.size() - 1; counts[5] = (long)plan.flops;
   if (tile_pos) std::copy(plan.tile_pos.begin(), plan.tile_pos.begin() + n_tiles, tile_pos);

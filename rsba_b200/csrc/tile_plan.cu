@@ -96,7 +96,7 @@ struct Dissector {
 }  // namespace
 
 void build_tile_plan(int T, const std::vector<std::pair<int, int>>& tile_pairs, bool dense, bool reorder,
-                     TilePlan* plan) {
+                     int border_tile, TilePlan* plan) {
   TilePlan& P = *plan;
   P = TilePlan();
   P.T = T;
@@ -106,7 +106,7 @@ void build_tile_plan(int T, const std::vector<std::pair<int, int>>& tile_pairs, 
   if (reorder && !dense && T > kLeafTiles) {
     Adj adj(T);
     for (auto& pr : tile_pairs)
-      if (pr.first != pr.second) {
+      if (pr.first != pr.second && pr.first != border_tile && pr.second != border_tile) {
         adj[pr.first].push_back(pr.second);
         adj[pr.second].push_back(pr.first);
       }
@@ -115,9 +115,11 @@ void build_tile_plan(int T, const std::vector<std::pair<int, int>>& tile_pairs, 
       a.erase(std::unique(a.begin(), a.end()), a.end());
     }
     Dissector d(adj);
-    std::vector<int> all(T);
-    for (int t = 0; t < T; ++t) all[t] = t;
+    std::vector<int> all;
+    for (int t = 0; t < T; ++t)
+      if (t != border_tile) all.push_back(t);
     d.run(all);
+    if (border_tile >= 0 && border_tile < T) d.order.push_back(border_tile);
     for (int pos = 0; pos < T; ++pos) {
       P.pos_tile[pos] = d.order[pos];
       P.tile_pos[d.order[pos]] = pos;

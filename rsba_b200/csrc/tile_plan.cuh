@@ -35,7 +35,9 @@ struct TilePlan {
 
 // tile_pairs: structurally non-zero tile pairs (A <= B) in FRAME-tile numbering (diagonal pairs may
 // be omitted).  dense: treat every tile as non-zero.  reorder: nested dissection (else natural order).
+// border_tile >= 0: a tile that couples with every other one (the intrinsics pseudo-frame of the uncalibrated
+// variant); it is kept out of the dissection and eliminated last.
 void build_tile_plan(int T, const std::vector<std::pair<int, int>>& tile_pairs, bool dense, bool reorder,
-                     TilePlan* plan);
+                     int border_tile, TilePlan* plan);
 
 }  // namespace rsba
