@@ -112,6 +112,13 @@ int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter,
  * rsba_cuda_evaluate (HOST pointer, caller's observation order).  Per-frame intrinsics blocks (f.cam) are
  * not supported. */
 int rsba_cuda_set_intrinsics_free(rsba_problem* h, int free_intrinsics);
+/* Pointer-identity form of the same: problem.AddResidualBlock(RsBundleAdjustment::CreateWithCam(sess, opt, obs), loss,
+ * sess.cam.data(), f.poses[0].data(), f.poses[1].data(), t->pt.data())  (CeresHandler.h:256-264).  `intrinsics`
+ * (9 doubles, caller-owned, updated in place by rsba_cuda_solve) must be the same block in every call; its
+ * values at solve / evaluate time are the starting point (rsba_cuda_set_camera still supplies shutter,
+ * scan lines and interpolateRotation). */
+int rsba_cuda_add_rs_residual_with_intrinsics(rsba_problem* h, const double observed[2], double* intrinsics,
+                                              double* pose0, double* pose1, double* point);
 int rsba_cuda_get_camera(rsba_problem* h, double cam9[9]);
 int rsba_cuda_get_intrinsics_jacobian(rsba_problem* h, double* jacobian_cam);
 

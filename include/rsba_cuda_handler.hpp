@@ -53,6 +53,11 @@ class Problem {
   }
   // lossFunction = new ceres::HuberLoss(a), applied to every residual block (CeresHandler.h:85-90)
   void SetHuberLoss(double a) { check(rsba_cuda_set_loss(h_, a)); }
+  // CreateWithCam <2; 9, 6, 6, 3>: the shared intrinsics block is optimised too (CeresHandler.h:256-264)
+  void AddRsResidualBlockWithIntrinsics(const double observed[2], double* cam, double* pose0, double* pose1, double* point) {
+    check(rsba_cuda_add_rs_residual_with_intrinsics(h_, observed, cam, pose0, pose1, point));
+    ++num_residual_blocks_;
+  }
   void AddRsResidualBlock(const double observed[2], double* pose0, double* pose1, double* point) {
     check(rsba_cuda_add_rs_residual(h_, observed, pose0, pose1, point));
     ++num_residual_blocks_;
@@ -118,7 +123,6 @@ class Handler {
   explicit Handler(const Options& o, std::size_t start = 0, int device = 0) : problem(device), opt(o), startFrame(start) {
     if (opt.ceres.huberLoss > 0) problem.SetHuberLoss(opt.ceres.huberLoss);      // CeresHandler.h:85-90
     if (!opt.model.use3Dpoints) throw std::runtime_error("rsba_cuda: structure-less (feature ray) mode is out of scope");
-    if (!opt.model.calibrated) throw std::runtime_error("rsba_cuda: uncalibrated 4-block variant is not on the device path yet");
     if ((opt.ceres.constFrameVelocity != 0 || opt.ceres.constFrameAcceleration != 0) && opt.ceres.interFrameRatio == 1)
       throw std::runtime_error("rsba_cuda: motion priors need a fixed interFrameRatio (!= 1, CeresHandler.h:178-180); "
                                "the free, lower-bounded ratio is not on the device path");
@@ -170,7 +174,12 @@ class Handler {
       auto* t = &sess.getTrack(o.track);
       if (!t->__isset.pt || (opt.ceres.useOnlyValidMatches && !t->valid)) continue;
       const double obs[2] = {o.x, o.y};
-      problem.AddRsResidualBlock(obs, f.poses[0].data(), second_pose, t->pt.data());   // :250-255 / :265-270
+      if (opt.model.calibrated) {
+        problem.AddRsResidualBlock(obs, f.poses[0].data(), second_pose, t->pt.data());   // :250-255 / :265-270
+      } else {                                                                           // :256-264 / :271-277
+        if (f.__isset.cam) throw std::runtime_error("rsba_cuda: per-frame intrinsics (f.cam) are not on the device path");
+        problem.AddRsResidualBlockWithIntrinsics(obs, sess.cam.data(), f.poses[0].data(), second_pose, t->pt.data());
+      }
       added = true;
       bool fixedOldTrack = false;                             // :288-300
       if (startFrame > 0)

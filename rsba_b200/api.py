@@ -35,7 +35,7 @@ ERR_EVALUATION_FAILED, ERR_LINEAR_SOLVER, ERR_NCCL = -5, -6, -7
 # every symbol include/rsba_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "rsba_cuda_create", "rsba_cuda_destroy", "rsba_cuda_last_error", "rsba_cuda_set_stream",
-    "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_intrinsics_free", "rsba_cuda_get_camera", "rsba_cuda_get_intrinsics_jacobian",
+    "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_intrinsics_free", "rsba_cuda_add_rs_residual_with_intrinsics", "rsba_cuda_get_camera", "rsba_cuda_get_intrinsics_jacobian",
     "rsba_cuda_set_loss", "rsba_cuda_add_rs_residual",
     "rsba_cuda_add_motion_prior", "rsba_cuda_set_motion_priors", "rsba_cuda_get_prior_residuals",
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
@@ -129,6 +129,7 @@ def load_library():
     lib.rsba_cuda_default_options.restype = None
     lib.rsba_cuda_set_camera.argtypes = [vp, _dp, C.c_int, _ip, C.c_int]
     lib.rsba_cuda_set_intrinsics_free.argtypes = [vp, C.c_int]
+    lib.rsba_cuda_add_rs_residual_with_intrinsics.argtypes = [vp, _dp, vp, vp, vp, vp]
     lib.rsba_cuda_get_camera.argtypes = [vp, vp]
     lib.rsba_cuda_get_intrinsics_jacobian.argtypes = [vp, vp]
     lib.rsba_cuda_set_loss.argtypes = [vp, C.c_double]
@@ -293,6 +294,14 @@ class Problem:
         if n > 0:
             self.lib.rsba_cuda_get_prior_residuals(self._h, _addr(r))
         return r
+
+    def add_rs_residual_with_intrinsics(self, observed, cam, pose0, pose1, point):
+        """<2; 9, 6, 6, 3>: ``cam`` is the shared 9-wide intrinsics block (CeresHandler.h:256-264)."""
+        obs = np.ascontiguousarray(observed, dtype=np.float64)
+        self._keep.extend((cam, pose0, pose1, point))
+        self._check(self.lib.rsba_cuda_add_rs_residual_with_intrinsics(self._h, obs.ctypes.data_as(_dp), _addr(cam),
+                                                                       _addr(pose0), _addr(pose1), _addr(point)))
+        self.free_intrinsics = True
 
     def set_block_constant(self, block: np.ndarray):
         self._check(self.lib.rsba_cuda_set_block_constant(self._h, _addr(block)))

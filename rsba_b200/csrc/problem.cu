@@ -340,6 +340,7 @@ int gather_pointer_parameters(rsba_problem* h) {
     memcpy(&poses[(size_t)12 * f + 6], h->frame_pose1[f], 6 * sizeof(double));
   }
   for (int p = 0; p < h->n_points; ++p) memcpy(&points[(size_t)3 * p], h->point_ptr[p], 3 * sizeof(double));
+  if (h->ptr_cam) memcpy(h->cm.cam, h->ptr_cam, 9 * sizeof(double));   // the intrinsics block's current values
   return rsba_cuda_set_parameters(h, poses.data(), points.data());
 }
 
@@ -352,6 +353,12 @@ int scatter_pointer_parameters(rsba_problem* h) {
     memcpy(h->frame_pose1[f], &poses[(size_t)12 * f + 6], 6 * sizeof(double));
   }
   for (int p = 0; p < h->n_points; ++p) memcpy(h->point_ptr[p], &points[(size_t)3 * p], 3 * sizeof(double));
+  if (h->ptr_cam) {
+    double cam[9];
+    rc = rsba_cuda_get_camera(h, cam);
+    if (rc) return rc;
+    memcpy(h->ptr_cam, cam, sizeof(cam));
+  }
   return RSBA_OK;
 }
 
@@ -592,6 +599,23 @@ long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals) {
     if (cudaMemcpy(residuals, h->d_prior_r.ptr, 12 * n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   }
   return n;
+}
+
+int rsba_cuda_add_rs_residual_with_intrinsics(rsba_problem* h, const double observed[2], double* intrinsics,
+                                              double* pose0, double* pose1, double* point) {
+  if (!h || !intrinsics) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->ptr_cam && h->ptr_cam != intrinsics)
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "only ONE shared intrinsics block is supported (sess.cam); per-frame f.cam blocks are not");
+  if (!h->ptr_cam && !h->ptr_obs.empty())
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "calibrated and uncalibrated residual blocks cannot be mixed");
+  int rc = rsba_cuda_add_rs_residual(h, observed, pose0, pose1, point);
+  if (rc) return rc;
+  h->ptr_cam = intrinsics;
+  if (!h->free_cam) {
+    h->free_cam = true;
+    if (h->lm) { lm_state_free(h->lm); h->lm = nullptr; }
+  }
+  return RSBA_OK;
 }
 
 int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0, double* pose1,

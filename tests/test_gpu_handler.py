@@ -105,3 +105,29 @@ def test_handler_global_shutter_single_pose_frames(tmp_path):
     seen[sc.obs_point] = True
     assert np.linalg.norm(poses[:, :6] - po[:, :6]) <= 1e-7 * np.linalg.norm(po[:, :6])
     assert np.linalg.norm(points[seen] - pt[seen]) <= 1e-7 * np.linalg.norm(pt[seen])
+
+
+@pytest.mark.gpu
+def test_handler_uncalibrated_session(tmp_path):
+    """opt.model.calibrated = false: CeresHandler::Add uses CreateWithCam with sess.cam as a parameter block
+    (CeresHandler.h:256-264); the handler's result == bulk API with free intrinsics, sess.cam updated in place."""
+    import rsba_b200.api as api
+    sc = make_scene(12, 400, 8, name="uncal-handler")
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    r = subprocess.run([BIN, src, dst, "1", "8", "0", "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst)
+    nf, npnt = sc.num_frames, sc.num_points
+    poses = out[4:4 + 12 * nf].reshape(-1, 12)
+    cam = out[4 + 12 * nf + 3 * npnt:]
+    assert cam.size == 9
+    with api.Problem(0) as pb:
+        pb.set_intrinsics_free(True)
+        pb.load_scene(sc)
+        s = pb.solve(api.default_options(max_num_iterations=8))
+        po, _ = pb.get_parameters()
+        cam_bulk = pb.get_camera()
+    assert out[0] == 1 and abs(out[3] - s.final_cost) <= 1e-9 * s.final_cost
+    assert np.linalg.norm(poses - po) <= 1e-7 * np.linalg.norm(po)
+    assert np.linalg.norm(cam - cam_bulk) <= 1e-9 * np.linalg.norm(cam_bulk) and np.abs(cam - sc.cam).max() > 0

@@ -4,7 +4,8 @@
 // Session.{cam,rs,scanlines,frames}).  Reads a flat scene file written by tests/test_gpu_handler.py,
 // runs the same calls VideoSfMHandler::BA makes (VideoSfMHandler.cc:586-592), writes the result.
 //   usage: handler_check <scene.bin> <out.bin> <fixFirstNCameras> <maxIter> [startFrame] [gs]
-//   (gs = 1: global-shutter session, every frame holds ONE pose -- the first control pose of the file)
+//   (gs = 1: global-shutter session, every frame holds ONE pose -- the first control pose of the file;
+//    gs = 2: uncalibrated, opt.model.calibrated = false -- the optimised sess.cam is appended to the output)
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -14,11 +15,12 @@
 
 namespace mock {
 struct IsSetObs { bool track = false; };
+struct IsSetFrame { bool cam = false; };
 struct ObservationRef { int frame = 0, obs = 0; };
 struct Observation { double x = 0, y = 0; int track = -1; IsSetObs __isset; std::vector<ObservationRef> matches; };
 struct IsSetTrack { bool pt = false; };
 struct Track { std::vector<double> pt; bool valid = true; IsSetTrack __isset; std::vector<ObservationRef> obs; };
-struct Frame { std::vector<std::vector<double>> poses; std::vector<Observation> obs; };
+struct Frame { std::vector<std::vector<double>> poses; std::vector<Observation> obs; std::vector<double> cam; IsSetFrame __isset; };
 struct Session {
   std::vector<double> cam;
   int rs = 1;
@@ -62,7 +64,8 @@ int main(int argc, char** argv) {
   rd(f, fr.data(), N * sizeof(int));
   rd(f, pt.data(), N * sizeof(int));
   fclose(f);
-  const bool gs = argc > 6 && atoi(argv[6]) != 0;
+  const bool gs = argc > 6 && atoi(argv[6]) == 1;
+  const bool uncal = argc > 6 && atoi(argv[6]) == 2;
   if (gs) sess.rs = 0;
   sess.frames.resize(F);
   for (long k = 0; k < F; ++k) {
@@ -92,6 +95,7 @@ int main(int argc, char** argv) {
   }
   mock::Options opt;
   opt.ceres.fixFirstNCameras = (unsigned)atoi(argv[3]);
+  opt.model.calibrated = !uncal;
   const size_t startFrame = argc > 5 ? (size_t)atol(argv[5]) : 0;
 
   rsba_solve_summary s;
@@ -116,6 +120,7 @@ int main(int argc, char** argv) {
     fwrite(sess.frames[k].poses.back().data(), sizeof(double), 6, g);   // (global shutter: pose0 again)
   }
   for (long p = 0; p < P; ++p) fwrite(sess.tracks[(int)p].pt.data(), sizeof(double), 3, g);
+  if (uncal) fwrite(sess.cam.data(), sizeof(double), 9, g);
   fclose(g);
   return 0;
 }
