@@ -139,9 +139,10 @@ int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double*
  * problem.AddResidualBlock(cost, loss, &opt.ceres.interFrameRatio, f.poses[0], f.poses[1],
  * f_1.poses[0], f_1.poses[1])  (CeresHandler.h:148-186; functors video_bundler_rs_inter.h:55-173):
  * the 12-residual constant-velocity (kind 1) / constant-acceleration (kind 2) prior between frame k
- * (pose0, end0) and frame k-1 (pose1, end1), with the interFrameRatio block CONSTANT -- the reference
- * fixes it whenever opt.ceres.interFrameRatio != 1 (CeresHandler.h:178-180).  The free, lower-bounded
- * ratio of the reference's default (== 1) is not on the device path.  A frame may be the current
+ * (pose0, end0) and frame k-1 (pose1, end1).  inter_frame_ratio is the value of a CONSTANT ratio block --
+ * the reference fixes it whenever opt.ceres.interFrameRatio != 1 (CeresHandler.h:178-180); with the
+ * reference's default (== 1) the block is a free, lower-bounded parameter: see
+ * rsba_cuda_set_inter_frame_ratio_block / _free below (the per-prior value is then ignored).  A frame may be the current
  * frame of one prior and the previous frame of one prior.  The problem's loss (rsba_cuda_set_loss)
  * applies to the prior blocks too, as in the reference.  Rejects ratios for which the functor
  * returns false (velocity: ratio < 0; acceleration: ratio < DBL_EPSILON). */
@@ -150,6 +151,19 @@ int rsba_cuda_add_motion_prior(rsba_problem* h, int kind, double scale, double i
 /* Bulk form (after rsba_cuda_set_scene, which clears the list): frame[i] / prev_frame[i] index poses. */
 int rsba_cuda_set_motion_priors(rsba_problem* h, int n, const int* kind, const double* scale,
                                 const double* inter_frame_ratio, const int* frame, const int* prev_frame);
+/* Replaces: the parameter block `&opt.ceres.interFrameRatio` that every motion prior shares, left variable
+ * (CeresHandler.h:156,167 -- SetParameterBlockConstant only when the value != 1, :178-180) with
+ * problem.SetParameterLowerBound(&ratio, 0, _EPS) for acceleration priors / (.., 0, 0.0) for velocity priors
+ * (:161,172).  The scalar becomes one more column of the reduced camera system (parameter 9 of the pseudo-frame
+ * that also carries free intrinsics); the trial point is projected onto the bound as Ceres' Plus does.
+ * _block: pointer API -- *ratio is read at solve/evaluate entry and written back after the solve.
+ * _free : bulk API -- free_ratio = 0 returns to the constant per-prior values; read the result with _get. */
+int rsba_cuda_set_inter_frame_ratio_block(rsba_problem* h, double* ratio);
+int rsba_cuda_set_inter_frame_ratio_free(rsba_problem* h, int free_ratio, double value);
+int rsba_cuda_get_inter_frame_ratio(rsba_problem* h, double* value);
+/* d residual / d interFrameRatio [12 n] (loss-corrected) of the priors at the last residual+Jacobian
+ * evaluation, free ratio only (HOST pointer, may be NULL); returns the number of priors or -1. */
+long rsba_cuda_get_prior_ratio_jacobian(rsba_problem* h, double* d_residual_d_ratio);
 /* Loss-corrected residuals [12 n] of the priors at the last residual+Jacobian evaluation (HOST pointer,
  * may be NULL); returns the number of priors. */
 long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals);

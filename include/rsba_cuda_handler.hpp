@@ -66,6 +66,8 @@ class Problem {
   void AddMotionPrior(int kind, double scale, double ratio, double* pose0, double* end0, double* pose1, double* end1) {
     check(rsba_cuda_add_motion_prior(h_, kind, scale, ratio, pose0, end0, pose1, end1));
   }
+  // the shared `&opt.ceres.interFrameRatio` block left variable, with its lower bound (CeresHandler.h:156-180)
+  void SetInterFrameRatioBlock(double* ratio) { check(rsba_cuda_set_inter_frame_ratio_block(h_, ratio)); }
   void SetParameterBlockConstant(double* block) { check(rsba_cuda_set_block_constant(h_, block)); }
   void SetSubsetConstant(double* pose_block, const std::vector<int>& constant) {
     check(rsba_cuda_set_subset_constant(h_, pose_block, (int)constant.size(), constant.data()));
@@ -123,9 +125,6 @@ class Handler {
   explicit Handler(const Options& o, std::size_t start = 0, int device = 0) : problem(device), opt(o), startFrame(start) {
     if (opt.ceres.huberLoss > 0) problem.SetHuberLoss(opt.ceres.huberLoss);      // CeresHandler.h:85-90
     if (!opt.model.use3Dpoints) throw std::runtime_error("rsba_cuda: structure-less (feature ray) mode is out of scope");
-    if ((opt.ceres.constFrameVelocity != 0 || opt.ceres.constFrameAcceleration != 0) && opt.ceres.interFrameRatio == 1)
-      throw std::runtime_error("rsba_cuda: motion priors need a fixed interFrameRatio (!= 1, CeresHandler.h:178-180); "
-                               "the free, lower-bounded ratio is not on the device path");
   }
 
   void Add(const std::size_t frameKey, Session& sess) {
@@ -161,6 +160,12 @@ class Handler {
       auto& f_1 = sess.frames[frameKey - 1];
       if (f.poses.size() == 2 && f_1.poses.size() == 2) {
         const bool accel = opt.ceres.constFrameAcceleration != 0;
+        // the ratio block is this handler's own copy of the options, as in the reference (`opt` is copied,
+        // CeresHandler.h:79); it is constant only when it differs from 1 (:178-180)
+        if (opt.ceres.interFrameRatio == 1 && !ratio_block_set_) {
+          problem.SetInterFrameRatioBlock(&opt.ceres.interFrameRatio);
+          ratio_block_set_ = true;
+        }
         problem.AddMotionPrior(accel ? 2 : 1, accel ? opt.ceres.constFrameAcceleration : opt.ceres.constFrameVelocity,
                                opt.ceres.interFrameRatio, f.poses[0].data(), f.poses[1].data(), f_1.poses[0].data(),
                                f_1.poses[1].data());
@@ -213,7 +218,7 @@ class Handler {
   }
 
  private:
-  bool camera_set_ = false;
+  bool camera_set_ = false, ratio_block_set_ = false;
   std::deque<std::vector<double>> gs_store_;        // stand-in second poses of single-pose frames
   std::map<std::size_t, double*> gs_second_;
 };

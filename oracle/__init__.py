@@ -234,6 +234,26 @@ def motion_prior_eval(kind, scale, ratio, frame_k, frame_km1):
     return res, J
 
 
+def motion_prior_ratio_column(kind, scale, ratio, frame_k, frame_km1):
+    """TEST INFRASTRUCTURE.  d residual / d interFrameRatio [12] of one prior when the ratio block is a free
+    parameter (the reference's default, CeresHandler.h:156-180): the residuals are linear in the coefficients
+    c(ratio) of motion_prior_coefficients, so the column is the same form with dc/dratio."""
+    r = float(ratio)
+    h = 1.0 if kind == PRIOR_VELOCITY else 0.5
+    a = [0.0, 0.0, h, -h]
+    if kind == PRIOR_ACCELERATION or r > _EPS:
+        b = [h / (r * r), 0.0, 0.0, -h / (r * r)]
+    else:
+        b = [0.0, 0.0, 0.0, 0.0]
+    dc = np.array([a, b])
+    sigma = scale * np.array([0.01, 0.01, 0.01, 1.0, 1.0, 1.0])
+    blocks = [frame_k[:6], frame_k[6:], frame_km1[:6], frame_km1[6:]]
+    col = np.zeros(12)
+    for hh in range(2):
+        col[6 * hh:6 * hh + 6] = sigma * sum(dc[hh, k] * blocks[k] for k in range(4))
+    return col
+
+
 def motion_prior_eval_ref(kind, scale, ratio, frame_k, frame_km1):
     """The reference's own functors under Jet autodiff (oracle/_ref).  Returns (valid, residuals [12],
     Jacobian [12, 24] w.r.t. the pose blocks, d residual / d interFrameRatio [12])."""
@@ -250,16 +270,21 @@ def motion_prior_eval_ref(kind, scale, ratio, frame_k, frame_km1):
     return bool(ok), res, jac[:, 1:].copy(), jac[:, 0].copy()
 
 
-def motion_prior_rows(scene, priors, poses=None, huber=0.0):
+def motion_prior_rows(scene, priors, poses=None, huber=0.0, free_ratio=None):
     """TEST INFRASTRUCTURE.  Residual rows of a list of priors (kind, scale, ratio, frame, prev_frame)
     over the full parameter vector [12 F + 3 P]: returns (J scipy CSR [12 n, 12F+3P], r [12 n], cost).
-    With huber > 0 the 12-residual blocks are corrected like every other block (apply_huber)."""
+    With huber > 0 the 12-residual blocks are corrected like every other block (apply_huber).
+    free_ratio = value: the shared interFrameRatio block is a parameter -- every prior uses that value and
+    gets the column d r / d ratio at parameter 9 of a pseudo-frame behind the real frames (``scene`` must
+    then already hold the pseudo-frame as its last frame, see lm_oracle.with_pseudo_frame)."""
     import scipy.sparse as sp
     poses = np.asarray(scene.poses if poses is None else poses, dtype=np.float64).reshape(-1, 12)
     F, P = scene.num_frames, scene.num_points
     rows, cols, vals, res = [], [], [], []
     cost = 0.0
     for i, (kind, scale, ratio, fk, fp) in enumerate(priors):
+        if free_ratio is not None:
+            ratio = float(free_ratio)
         r, J = motion_prior_eval(kind, scale, ratio, poses[fk], poses[fp])
         s = float(r @ r)
         w = 1.0
@@ -272,6 +297,11 @@ def motion_prior_rows(scene, priors, poses=None, huber=0.0):
         rows.append(12 * i + rr)
         cols.append(np.where(cc < 12, 12 * fk + cc, 12 * fp + (cc - 12)))
         vals.append(w * J[rr, cc])
+        if free_ratio is not None:
+            col = motion_prior_ratio_column(kind, scale, ratio, poses[fk], poses[fp])
+            rows.append(12 * i + np.arange(12))
+            cols.append(np.full(12, 12 * (F - 1) + 9))
+            vals.append(w * col)
     n = len(priors)
     Jx = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(12 * n, 12 * F + 3 * P))
     return Jx, np.concatenate(res), cost

@@ -110,6 +110,25 @@ def with_intrinsics_block(scene, J, Jcam):
     return sc, mask, cols
 
 
+def with_pseudo_frame(scene, ratio=None, free_cam=False):
+    """The pseudo-frame of the device path behind the real frames: parameters 0..8 = the shared intrinsics when
+    they are free (uncalibrated variant), parameter 9 = the motion priors' interFrameRatio when it is free
+    (CeresHandler.h:156-180), everything else constant.  Returns (scene', pose_mask')."""
+    import copy
+    F = scene.num_frames
+    sc = copy.copy(scene)
+    row = np.zeros(12)
+    if free_cam:
+        row[:9] = scene.cam
+    if ratio is not None:
+        row[9] = ratio
+    sc.poses = np.vstack([scene.poses, row[None, :]])
+    sc.const_frames = np.concatenate([np.asarray(scene.const_frames, dtype=bool), [False]])
+    mask = np.where(sc.const_frames, 0xFFF, 0).astype(np.int64)
+    mask[F] = 0xFFF & ~(0x1FF if free_cam else 0) & ~(0x200 if ratio is not None else 0)
+    return sc, mask
+
+
 def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mask=None, point_const=None,
             want_S=True, extra=None, cam_cols=None):
     """One linear solve of the LM subproblem.  Returns a dict with the reduced system

@@ -38,6 +38,8 @@ SYMBOLS = [
     "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_intrinsics_free", "rsba_cuda_add_rs_residual_with_intrinsics", "rsba_cuda_get_camera", "rsba_cuda_get_intrinsics_jacobian",
     "rsba_cuda_set_loss", "rsba_cuda_add_rs_residual",
     "rsba_cuda_add_motion_prior", "rsba_cuda_set_motion_priors", "rsba_cuda_get_prior_residuals",
+    "rsba_cuda_set_inter_frame_ratio_block", "rsba_cuda_set_inter_frame_ratio_free", "rsba_cuda_get_inter_frame_ratio",
+    "rsba_cuda_get_prior_ratio_jacobian",
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
@@ -138,6 +140,11 @@ def load_library():
     lib.rsba_cuda_set_motion_priors.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
     lib.rsba_cuda_get_prior_residuals.argtypes = [vp, vp]
     lib.rsba_cuda_get_prior_residuals.restype = C.c_long
+    lib.rsba_cuda_set_inter_frame_ratio_block.argtypes = [vp, vp]
+    lib.rsba_cuda_set_inter_frame_ratio_free.argtypes = [vp, C.c_int, C.c_double]
+    lib.rsba_cuda_get_inter_frame_ratio.argtypes = [vp, vp]
+    lib.rsba_cuda_get_prior_ratio_jacobian.argtypes = [vp, vp]
+    lib.rsba_cuda_get_prior_ratio_jacobian.restype = C.c_long
     lib.rsba_cuda_set_block_constant.argtypes = [vp, vp]
     lib.rsba_cuda_set_subset_constant.argtypes = [vp, vp, C.c_int, _ip]
     lib.rsba_cuda_set_scene.argtypes = [vp, C.c_long, _dp, _ip, _ip, C.c_int, C.c_int,
@@ -288,6 +295,33 @@ class Problem:
                                                          scale.ctypes.data_as(_dp), ratio.ctypes.data_as(_dp),
                                                          frame.ctypes.data_as(_ip), prev.ctypes.data_as(_ip)))
 
+    def set_inter_frame_ratio_free(self, free=True, value=1.0):
+        """The interFrameRatio block of the motion priors as a free, lower-bounded parameter (the reference's
+        default, CeresHandler.h:156-180); bulk form."""
+        self._check(self.lib.rsba_cuda_set_inter_frame_ratio_free(self._h, int(bool(free)), float(value)))
+        self.free_ratio = bool(free)
+
+    def set_inter_frame_ratio_block(self, ratio):
+        """Pointer form: ``ratio`` is a float64 numpy array of one element (&opt.ceres.interFrameRatio)."""
+        assert ratio.dtype == np.float64 and ratio.size == 1
+        self._keep.append(ratio)
+        self._check(self.lib.rsba_cuda_set_inter_frame_ratio_block(self._h, _addr(ratio)))
+        self.free_ratio = True
+
+    def inter_frame_ratio(self):
+        v = C.c_double(0.0)
+        self._check(self.lib.rsba_cuda_get_inter_frame_ratio(self._h, C.byref(v)))
+        return v.value
+
+    def prior_ratio_jacobian(self):
+        n = self.lib.rsba_cuda_get_prior_ratio_jacobian(self._h, None)
+        if n < 0:
+            raise RsbaError(ERR_STATE, self.lib.rsba_cuda_last_error().decode())
+        j = np.zeros((n, 12))
+        if n > 0:
+            self.lib.rsba_cuda_get_prior_ratio_jacobian(self._h, _addr(j))
+        return j
+
     def prior_residuals(self):
         n = self.lib.rsba_cuda_get_prior_residuals(self._h, None)
         r = np.zeros((max(n, 0), 12))
@@ -417,7 +451,8 @@ class Problem:
             self._check(self.lib.rsba_cuda_linearize_and_step(self._h, C.byref(options), float(radius), None,
                                                               None, None, None, C.byref(mcc)))
             return dict(model_cost_change=mcc.value)
-        nf = self.num_frames + (1 if getattr(self, "free_intrinsics", False) else 0)   # + intrinsics pseudo-frame
+        # + the pseudo-frame (free intrinsics = parameters 0..8, free interFrameRatio = parameter 9)
+        nf = self.num_frames + (1 if getattr(self, "free_intrinsics", False) or getattr(self, "free_ratio", False) else 0)
         n = 12 * nf
         S = np.zeros((n, n)) if want_S else None
         rhs = np.zeros(n)

@@ -45,6 +45,13 @@ struct PriorView {
   double* r;             // [n][12] loss-corrected residuals at the linearisation point
   double* w2;            // [n] squared loss-correction weight
   double* Bx;            // [F][4][6] coupling diagonals of cur_of[f] (zero without a prior)
+  // Free interFrameRatio (the reference's default, interFrameRatio == 1: CeresHandler.h:156-180 leaves the
+  // scalar block `&opt.ceres.interFrameRatio` variable, with a lower bound).  The ratio is parameter 9 of
+  // the pseudo-frame behind the real frames: poses[ratio_off]; -1 = constant (coef fixed at upload).
+  long ratio_off;
+  const int* kind;       // [n] 1 velocity, 2 acceleration
+  double* coef_dev;      // == coef, writable: refreshed from the current ratio at every linearisation
+  double* jr;            // [n][12] loss-corrected d residual / d ratio at the linearisation point
 };
 
 // Kernel attributes (opt-in shared memory) are per device: true the first time `slot` (one per call
@@ -72,8 +79,9 @@ void launch_validate(const CameraModel& cm, const ObsView& obs, const double* po
                      double sqrd_threshold, double min_distance, unsigned char* ok, double* sqrd_error,
                      cudaStream_t stream);
 // priors: cost_out[0] = sum rho(|r|^2); store: also residuals and weights for the linearisation
+// invalid_count += priors whose functor returns false (ratio below the functor's bound; free ratio only)
 void launch_prior_eval(const PriorView& pv, const double* poses, double huber, double* cost_out, bool store,
-                       cudaStream_t stream);
+                       int* invalid_count, cudaStream_t stream);
 int k1_num_partials(long n);
 // deterministic fixed-order sum of `n` partials into out[0]
 void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t stream);

@@ -44,7 +44,7 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
 __global__ void __launch_bounds__(kWideThreads)
 frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* __restrict__ y, int n,
                   const double* __restrict__ poses, double* __restrict__ delta_c, double* __restrict__ trial,
-                  double* __restrict__ scratch) {
+                  double* __restrict__ scratch, int bounded, double lower_bound) {
   __shared__ double sh[32];
   double gd = 0.0, dd = 0.0, nn = 0.0;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
@@ -53,7 +53,9 @@ frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* _
     const double ys = y[(long)tile_pos[t / kTile] * kTile + t % kTile];
     const double d = -sc * ys;
     delta_c[t] = d;
-    trial[t] = poses[t] + d;
+    // the one bounded parameter (free interFrameRatio, SetParameterLowerBound at CeresHandler.h:161,172):
+    // Ceres' Plus projects the trial point onto the feasible set
+    trial[t] = (t == bounded) ? fmax(lower_bound, poses[t] + d) : poses[t] + d;
     gd += ne.gc[t] * d;
     dd += ne.d2_c[t] * ys * ys;
     nn += d * d;
@@ -222,8 +224,10 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
                         int cam_frame, NormalEq ne,
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
-                        double* trial_points, double* scalars, double* scratch, cudaStream_t s) {
-  frame_step_kernel<<<1, kWideThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch);
+                        double* trial_points, double* scalars, double* scratch, int bounded_param,
+                        double lower_bound, cudaStream_t s) {
+  frame_step_kernel<<<1, kWideThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch,
+                                               bounded_param, lower_bound);
   const int nb = (n_points + kPointStepWarps - 1) / kPointStepWarps;
   if (nb > 0)
     point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, obs, jac, jac_cam, cam_frame, ne, delta_c, n_points, points, delta_p, trial_points, scratch);

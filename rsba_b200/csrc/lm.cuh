@@ -164,7 +164,9 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
                         double* trial_points, double* scalars /* [16]: [0..2] camera part, [8..10] point part */,
-                        double* scratch, cudaStream_t s);
+                        double* scratch,
+                        int bounded_param /* index into the camera parameters with a lower bound, or -1 */,
+                        double lower_bound, cudaStream_t s);
 // |x|^2 and max|g| split into the point part (local to the rank; before the all-reduce) and the
 // camera part (replicated; after it).  out_points: [0] += |x_p|^2 over owned free points, [1] = max|g_p|
 void launch_point_norms(NormalEq ne, int n_points, const double* points, double* out_xx, double* out_gmax,

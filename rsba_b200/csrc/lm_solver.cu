@@ -24,7 +24,7 @@ struct LmState {
   DeviceBuffer<int> inc_point, inc_tile, slot_beg, pair_a, pair_b, pair_item_ptr, tile_pos, pos_tile;
   DeviceBuffer<int> obs_phi_off, dup_inc, cam_inc;
   DeviceBuffer<double> Bcam, cam_partials, cam_scratch;
-  bool free_cam = false;
+  bool free_cam = false, free_ratio = false;
   int n_cam_frames = 0;          // frames of the camera system: real frames (+ the intrinsics pseudo-frame)
   DeviceBuffer<unsigned char> slot_cnt, point_owned;
   DeviceBuffer<int4> items;
@@ -93,8 +93,9 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   };
   const long N = h->n_obs;
   const int F = h->n_frames, P = h->n_points;
-  const bool free_cam = h->free_cam;
-  const int Fc = h->n_cam_frames();    // + the intrinsics pseudo-frame (uncalibrated variant)
+  const bool free_cam = h->free_cam, free_ratio = h->free_ratio && !h->priors.empty();
+  const bool pseudo = h->has_pseudo_frame();
+  const int Fc = h->n_cam_frames();    // + the pseudo-frame (free intrinsics / free interFrameRatio)
   const std::vector<int>& fr = h->h_obs_frame;
   const std::vector<int>& pt = h->h_obs_point;
   cudaStream_t s = h->stream;
@@ -197,6 +198,10 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   for (const auto& pr : h->priors) {                                           // ... and every prior coupling
     const int a = std::min(pr.frame, pr.prev) / kSubFrames, b = std::max(pr.frame, pr.prev) / kSubFrames;
     marker_keys.push_back((long)a * H + b);
+    if (free_ratio) {   // the ratio (pseudo-frame) couples with both frames of every prior
+      marker_keys.push_back((long)a * H + cam_sub);
+      marker_keys.push_back((long)b * H + cam_sub);
+    }
   }
   std::vector<int> pair_a, pair_b;
   std::vector<long> pair_cnt;
@@ -284,6 +289,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
       for (const auto& pr : h->priors) {
         const int a = std::min(pr.frame, pr.prev) / kFramesPerTile, b = std::max(pr.frame, pr.prev) / kFramesPerTile;
         seen[(size_t)a * T + b] = 1;
+        if (free_ratio) seen[(size_t)a * T + F / kFramesPerTile] = seen[(size_t)b * T + F / kFramesPerTile] = 1;
       }
       for (int a = 0; a < T; ++a)
         for (int b = a; b < T; ++b)
@@ -294,7 +300,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
       std::sort(tp.begin(), tp.end());
       tp.erase(std::unique(tp.begin(), tp.end()), tp.end());
     }
-    const int border_tile = free_cam ? F / kFramesPerTile : -1;   // couples with everything: eliminated last
+    const int border_tile = pseudo ? F / kFramesPerTile : -1;   // couples with everything: eliminated last
     if (free_cam && h->world > 1)
       for (int a = 0; a < T; ++a) tp.emplace_back(std::min(a, border_tile), std::max(a, border_tile));
     build_tile_plan(T, tp, dense, h->reorder_tiles, border_tile, &plan);
@@ -318,7 +324,8 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   {
     std::vector<unsigned short> mask(h->pose_mask);
     mask.resize(Fc, 0);
-    if (free_cam) mask[F] = 0xE00;   // parameters 9..11 of the pseudo-frame do not exist
+    if (pseudo)   // parameters 0..8 = intrinsics, 9 = interFrameRatio; what is not a parameter is constant
+      mask[F] = (unsigned short)(0xFFF & ~(free_cam ? 0x1FF : 0) & ~(free_ratio ? 0x200 : 0));
     UP(pose_mask, mask);
   }
   UP(point_const, h->point_const);
@@ -340,13 +347,16 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.entries = lm->entries.ptr; st.n_entries = (long)entries.size(); st.tile_pos = lm->tile_pos.ptr;
   st.pos_tile = lm->pos_tile.ptr; st.n_cam_params = 12L * Fc;
   lm->free_cam = free_cam;
+  lm->free_ratio = h->free_ratio;
   lm->n_cam_frames = Fc;
 
   // ---- numeric buffers
   const size_t Fz = std::max(Fc, 1), Pz = std::max(P, 1);
-  if (free_cam) {
+  if (pseudo) {
     RSBA_CUDA_TRY(lm->Bcam.resize(Fz * 144));
     RSBA_CUDA_TRY(cudaMemsetAsync(lm->Bcam.ptr, 0, lm->Bcam.bytes(), s));
+  }
+  if (free_cam) {
     RSBA_CUDA_TRY(lm->cam_partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 207));
     RSBA_CUDA_TRY(lm->cam_scratch.resize(Fz * 99));
   }
@@ -395,6 +405,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   long free_params = 0;
   for (int f = 0; f < F; ++f) free_params += 12 - __builtin_popcount(h->pose_mask[f] & 0xFFF);
   if (free_cam) free_params += 9;
+  if (free_ratio) free_params += 1;
   for (int p = 0; p < P; ++p) free_params += h->point_const[p] ? 0 : 3;
   lm->num_free_params = free_params;
   RSBA_CUDA_TRY(cudaStreamSynchronize(s));
@@ -403,7 +414,8 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
 }
 
 int ensure_lm(rsba_problem* h, bool dense) {
-  if (h->lm && h->lm->dense == dense && h->lm->reorder == h->reorder_tiles && h->lm->free_cam == h->free_cam) return RSBA_OK;
+  if (h->lm && h->lm->dense == dense && h->lm->reorder == h->reorder_tiles && h->lm->free_cam == h->free_cam &&
+      h->lm->free_ratio == h->free_ratio) return RSBA_OK;
   if (h->lm) { lm_state_free(h->lm); h->lm = nullptr; }
   LmState* lm = new LmState;
   int rc = build_structure(h, lm, dense);
@@ -463,7 +475,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   stage_begin(h, kStageSchurReduce);
   PriorView pvr = pv;
   if (h->rank != 0) pvr.n = 0;
-  launch_schur_reduce(lm->st, lm->ne, pvr, lm->free_cam ? h->n_frames : -1, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
+  launch_schur_reduce(lm->st, lm->ne, pvr, lm->n_cam_frames > h->n_frames ? h->n_frames : -1, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
   stage_end(h, kStageSchurReduce);
   h->launches += 4;
   if (new_jacobian) {   // scalars of the current point that ride in the same buffer
@@ -541,7 +553,8 @@ void step_update(rsba_problem* h, LmState* lm) {
   launch_step_update(lm->st, h->obs_view(), h->d_jac.ptr, lm->free_cam ? h->d_jac_cam.ptr : nullptr,
                      lm->free_cam ? h->n_frames : -1, lm->ne, lm->y.ptr, lm->n_cam_frames, h->n_points,
                      h->d_poses.ptr, h->d_points.ptr, lm->delta_c.ptr, lm->delta_p.ptr, lm->trial_poses.ptr,
-                     lm->trial_points.ptr, lm->scalars.ptr, lm->scratch.ptr, h->stream);
+                     lm->trial_points.ptr, lm->scalars.ptr, lm->scratch.ptr,
+                     lm->free_ratio ? 12 * h->n_frames + 9 : -1, h->ratio_lower_bound(), h->stream);
   h->launches += 3;
   stage_end(h, kStageUpdate);
 }
@@ -765,6 +778,8 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   if ((rc = gather_points(h, lm))) return rc;
   if (lm->free_cam)   // the optimised intrinsics are also the host copy used by validate / pnp and returned by get_camera
     RSBA_CUDA_TRY(cudaMemcpyAsync(h->cm.cam, h->d_poses.ptr + 12L * h->n_frames, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (lm->free_ratio)
+    RSBA_CUDA_TRY(cudaMemcpyAsync(&h->ratio_value, h->d_poses.ptr + 12L * h->n_frames + 9, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   sum->time_schur_ms += h->timers[kStageFinalize].total_ms;
   if (h->ptr_mode) {

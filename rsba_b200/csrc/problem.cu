@@ -117,7 +117,7 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
   const int np = k1_num_partials(h->n_obs);
   const PriorView pv = h->prior_view();
   if (pv.n > 0 && h->rank == 0) {
-    launch_prior_eval(pv, poses, h->cm.huber, h->d_cost_partials.ptr + np, jac, h->stream);
+    launch_prior_eval(pv, poses, h->cm.huber, h->d_cost_partials.ptr + np, jac, h->d_invalid.ptr, h->stream);
     h->launches += 1;
   } else {
     RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np, 0, sizeof(double), h->stream));
@@ -264,6 +264,7 @@ int upload_priors(rsba_problem* h) {
   const int n = (int)h->priors.size(), F = h->n_frames;
   std::vector<int> frame(std::max(n, 1)), prev(std::max(n, 1)), cur_of(std::max(F, 1), -1), prev_of(std::max(F, 1), -1);
   std::vector<double> coef(8 * (size_t)std::max(n, 1)), scale(std::max(n, 1));
+  std::vector<int> kind(std::max(n, 1), 1);
   for (int i = 0; i < n; ++i) {
     const auto& p = h->priors[i];
     if (p.frame < 0 || p.frame >= F || p.prev < 0 || p.prev >= F || p.frame == p.prev)
@@ -275,7 +276,9 @@ int upload_priors(rsba_problem* h) {
     frame[i] = p.frame;
     prev[i] = p.prev;
     scale[i] = p.scale;
-    prior_coefficients(p.kind, p.ratio, &coef[8 * (size_t)i]);
+    kind[i] = p.kind;
+    // (with a free ratio the device refreshes the coefficients from the ratio parameter at every evaluation)
+    prior_coefficients(p.kind, h->free_ratio ? h->ratio_value : p.ratio, &coef[8 * (size_t)i]);
   }
   auto up = [&](auto& dev, const auto& host) -> cudaError_t {
     cudaError_t e = dev.resize(host.size());
@@ -288,6 +291,8 @@ int upload_priors(rsba_problem* h) {
   RSBA_CUDA_TRY(up(h->d_prior_prev_of, prev_of));
   RSBA_CUDA_TRY(up(h->d_prior_coef, coef));
   RSBA_CUDA_TRY(up(h->d_prior_scale, scale));
+  RSBA_CUDA_TRY(up(h->d_prior_kind, kind));
+  RSBA_CUDA_TRY(h->d_prior_jr.resize(12 * (size_t)std::max(n, 1)));
   RSBA_CUDA_TRY(h->d_prior_r.resize(12 * (size_t)std::max(n, 1)));
   RSBA_CUDA_TRY(h->d_prior_w2.resize(std::max(n, 1)));
   RSBA_CUDA_TRY(h->d_prior_Bx.resize(24 * (size_t)std::max(F, 1)));
@@ -341,6 +346,7 @@ int gather_pointer_parameters(rsba_problem* h) {
   }
   for (int p = 0; p < h->n_points; ++p) memcpy(&points[(size_t)3 * p], h->point_ptr[p], 3 * sizeof(double));
   if (h->ptr_cam) memcpy(h->cm.cam, h->ptr_cam, 9 * sizeof(double));   // the intrinsics block's current values
+  if (h->ptr_ratio) h->ratio_value = *h->ptr_ratio;
   return rsba_cuda_set_parameters(h, poses.data(), points.data());
 }
 
@@ -358,6 +364,10 @@ int scatter_pointer_parameters(rsba_problem* h) {
     rc = rsba_cuda_get_camera(h, cam);
     if (rc) return rc;
     memcpy(h->ptr_cam, cam, sizeof(cam));
+  }
+  if (h->ptr_ratio) {
+    rc = rsba_cuda_get_inter_frame_ratio(h, h->ptr_ratio);
+    if (rc) return rc;
   }
   return RSBA_OK;
 }
@@ -601,6 +611,62 @@ long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals) {
   return n;
 }
 
+static int set_ratio_free(rsba_problem* h, bool want, double value) {
+  if (want) {
+    // the functors return false below these bounds (video_bundler_rs_inter.h:92, 157)
+    if (!(value >= h->ratio_lower_bound())) return fail(RSBA_ERR_INVALID_ARGUMENT, "interFrameRatio below its lower bound");
+    h->ratio_value = value;
+  }
+  if (want != h->free_ratio) {
+    h->free_ratio = want;
+    h->priors_dirty = true;   // coefficients + structure (the ratio couples with every prior frame)
+    if (h->lm) { lm_state_free(h->lm); h->lm = nullptr; }
+  }
+  if (h->scene_set) {
+    RSBA_CUDA_TRY(cudaSetDevice(h->device));
+    const double v = want ? value : 0.0;
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr + (size_t)kFrameParams * h->n_frames + 9, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return upload_priors(h);
+  }
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_inter_frame_ratio_free(rsba_problem* h, int free_ratio, double value) {
+  if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
+  if (h->ptr_ratio && !free_ratio) h->ptr_ratio = nullptr;
+  return set_ratio_free(h, free_ratio != 0, value);
+}
+
+int rsba_cuda_set_inter_frame_ratio_block(rsba_problem* h, double* ratio) {
+  if (!h || !ratio) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  h->ptr_ratio = ratio;
+  return set_ratio_free(h, true, *ratio);
+}
+
+long rsba_cuda_get_prior_ratio_jacobian(rsba_problem* h, double* d_residual_d_ratio) {
+  if (!h) return -1;
+  if (!h->free_ratio) { fail(RSBA_ERR_STATE, "the interFrameRatio is not a free parameter"); return -1; }
+  const long n = h->priors_dirty ? 0 : (long)h->priors.size();
+  if (d_residual_d_ratio && n > 0) {
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(d_residual_d_ratio, h->d_prior_jr.ptr, 12 * n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  }
+  return n;
+}
+
+int rsba_cuda_get_inter_frame_ratio(rsba_problem* h, double* value) {
+  if (!h || !value) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->free_ratio && h->scene_set && h->params_set) {
+    RSBA_CUDA_TRY(cudaSetDevice(h->device));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(&h->ratio_value, h->d_poses.ptr + (size_t)kFrameParams * h->n_frames + 9, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  *value = h->ratio_value;
+  return RSBA_OK;
+}
+
 int rsba_cuda_add_rs_residual_with_intrinsics(rsba_problem* h, const double observed[2], double* intrinsics,
                                               double* pose0, double* pose1, double* point) {
   if (!h || !intrinsics) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -697,10 +763,14 @@ int rsba_cuda_set_parameters(rsba_problem* h, const double* poses, const double*
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   if (h->n_frames)
     RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr, poses, (size_t)kFrameParams * h->n_frames * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  // the pseudo-frame behind the real frames: intrinsics (0..8) and interFrameRatio (9) when they are parameters
+  RSBA_CUDA_TRY(cudaMemsetAsync(h->d_poses.ptr + (size_t)kFrameParams * h->n_frames, 0, kFrameParams * sizeof(double), h->stream));
   if (h->free_cam) {
     if (!h->camera_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_camera before rsba_cuda_set_parameters (free intrinsics)");
     RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr + (size_t)kFrameParams * h->n_frames, h->cm.cam, 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
+  if (h->free_ratio)
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_poses.ptr + (size_t)kFrameParams * h->n_frames + 9, &h->ratio_value, sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (h->n_points)
     RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_points.ptr, points, h->d_points.bytes(), cudaMemcpyHostToDevice, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));

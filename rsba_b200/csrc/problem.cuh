@@ -102,7 +102,18 @@ struct rsba_problem {
   bool free_cam = false;
   double* ptr_cam = nullptr;               // pointer API: the caller's intrinsics block
   rsba::DeviceBuffer<double> d_jac_cam;
-  int n_cam_frames() const { return n_frames + (free_cam ? 1 : 0); }
+  // free interFrameRatio of the motion priors (CeresHandler.h:156-180): parameter 9 of the same pseudo-frame
+  bool free_ratio = false;
+  double ratio_value = 1.0;                // host copy: initial value / value after the last solve
+  double* ptr_ratio = nullptr;             // pointer API: the caller's scalar block (&opt.ceres.interFrameRatio)
+  bool has_pseudo_frame() const { return free_cam || free_ratio; }
+  int n_cam_frames() const { return n_frames + (has_pseudo_frame() ? 1 : 0); }
+  // lower bound of the ratio block: SetParameterLowerBound(.., 0, _EPS) with acceleration priors, 0.0 with
+  // velocity priors (CeresHandler.h:161, 172)
+  double ratio_lower_bound() const {
+    for (const auto& p : priors) if (p.kind == 2) return 2.220446049250313e-16;
+    return 0.0;
+  }
   rsba::DeviceBuffer<unsigned char> d_valid;
   rsba::DeviceBuffer<double> d_cost_partials;
   rsba::DeviceBuffer<double> d_scalars;    // [0] cost, misc
@@ -112,14 +123,16 @@ struct rsba_problem {
   struct PriorHost { int kind; double scale, ratio; int frame, prev; };
   std::vector<PriorHost> priors;           // frame indices of the finalised scene
   bool priors_dirty = false;
-  rsba::DeviceBuffer<int> d_prior_frame, d_prior_prev, d_prior_cur_of, d_prior_prev_of;
-  rsba::DeviceBuffer<double> d_prior_coef, d_prior_scale, d_prior_r, d_prior_w2, d_prior_Bx;
+  rsba::DeviceBuffer<int> d_prior_frame, d_prior_prev, d_prior_cur_of, d_prior_prev_of, d_prior_kind;
+  rsba::DeviceBuffer<double> d_prior_coef, d_prior_scale, d_prior_r, d_prior_w2, d_prior_Bx, d_prior_jr;
   rsba::PriorView prior_view() const {
     rsba::PriorView v{};
     v.n = priors_dirty ? 0 : (int)priors.size();
     v.frame = d_prior_frame.ptr; v.prev = d_prior_prev.ptr; v.coef = d_prior_coef.ptr; v.scale = d_prior_scale.ptr;
     v.cur_of = d_prior_cur_of.ptr; v.prev_of = d_prior_prev_of.ptr; v.r = d_prior_r.ptr; v.w2 = d_prior_w2.ptr;
     v.Bx = d_prior_Bx.ptr;
+    v.ratio_off = free_ratio ? (long)rsba::kFrameParams * n_frames + 9 : -1;
+    v.kind = d_prior_kind.ptr; v.coef_dev = d_prior_coef.ptr; v.jr = d_prior_jr.ptr;
     return v;
   }
 

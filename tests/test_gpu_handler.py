@@ -131,3 +131,35 @@ def test_handler_uncalibrated_session(tmp_path):
     assert out[0] == 1 and abs(out[3] - s.final_cost) <= 1e-9 * s.final_cost
     assert np.linalg.norm(poses - po) <= 1e-7 * np.linalg.norm(po)
     assert np.linalg.norm(cam - cam_bulk) <= 1e-9 * np.linalg.norm(cam_bulk) and np.abs(cam - sc.cam).max() > 0
+
+
+@pytest.mark.gpu
+def test_handler_velocity_priors_with_the_default_free_ratio(tmp_path):
+    """opt.ceres.constFrameVelocity != 0 with the default interFrameRatio == 1: the handler's own copy of the
+    ratio is a variable, lower-bounded block shared by every prior (CeresHandler.h:156-180) and is updated in
+    place; result == bulk API with rsba_cuda_set_inter_frame_ratio_free."""
+    import rsba_b200.api as api
+    sc = make_scene(12, 400, 8, name="velo-handler")
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    r = subprocess.run([BIN, src, dst, "1", "8", "0", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst)
+    nf, npnt = sc.num_frames, sc.num_points
+    poses = out[4:4 + 12 * nf].reshape(-1, 12)
+    ratio = out[4 + 12 * nf + 3 * npnt:]
+    assert ratio.size == 1
+    mask = np.zeros(nf, dtype=np.uint16)
+    mask[0] = 0xFFF                                          # fixFirstNCameras = 1; frame 1's prior fixes frame 0 too
+    with api.Problem(0) as pb:
+        pb.set_camera(sc.cam, sc.shutter, sc.scanlines, sc.interpolate_rotation)
+        pb.set_scene(sc.obs_xy, sc.obs_frame, sc.obs_point, nf, npnt, mask)
+        pb.set_parameters(sc.poses, sc.points)
+        pb.set_motion_priors([1] * (nf - 1), [10.0] * (nf - 1), [1.0] * (nf - 1), list(range(1, nf)), list(range(nf - 1)))
+        pb.set_inter_frame_ratio_free(True, 1.0)
+        s = pb.solve(api.default_options(max_num_iterations=8))
+        po, _ = pb.get_parameters()
+        ratio_bulk = pb.inter_frame_ratio()
+    assert out[0] == 1 and abs(out[3] - s.final_cost) <= 1e-9 * s.final_cost
+    assert np.linalg.norm(poses - po) <= 1e-7 * np.linalg.norm(po)
+    assert abs(ratio[0] - ratio_bulk) <= 1e-9 and ratio[0] != 1.0

@@ -33,3 +33,23 @@ def test_velocity_prior_at_zero_ratio_uses_the_previous_velocity(oracle_built):
     # the functors' validity: velocity needs ratio >= 0, acceleration ratio >= eps
     assert not oracle_built.motion_prior_eval_ref(1, 2.0, -0.1, fk, fp)[0]
     assert not oracle_built.motion_prior_eval_ref(2, 2.0, 0.0, fk, fp)[0]
+
+
+@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("ratio", [1.0, 0.7, 2.5, 1e-3])
+def test_ratio_column_matches_reference_functor(oracle_built, kind, ratio):
+    """Free interFrameRatio (the reference's default, CeresHandler.h:156-180): d residual / d ratio of the
+    closed form against the reference functor's own Jet column for the <1> block."""
+    if not oracle_built.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(int(ratio * 1000) + 7 * kind)
+    for _ in range(5):
+        fk, fp = rng.normal(0, 0.3, 12), rng.normal(0, 0.3, 12)
+        scale = float(rng.uniform(0.1, 30.0))
+        ok, _, _, col_ref = oracle_built.motion_prior_eval_ref(kind, scale, ratio, fk, fp)
+        col = oracle_built.motion_prior_ratio_column(kind, scale, ratio, fk, fp)
+        assert ok and np.abs(col - col_ref).max() <= 1e-12 * max(1.0, np.abs(col_ref).max())
+    # velocity prior at ratio <= eps: the second half no longer depends on the ratio
+    ok, _, _, col_ref = oracle_built.motion_prior_eval_ref(1, 2.0, 0.0, fk, fp)
+    col = oracle_built.motion_prior_ratio_column(1, 2.0, 0.0, fk, fp)
+    assert ok and np.allclose(col, col_ref, rtol=0, atol=1e-13) and not col[6:].any()

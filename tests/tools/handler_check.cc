@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
   fclose(f);
   const bool gs = argc > 6 && atoi(argv[6]) == 1;
   const bool uncal = argc > 6 && atoi(argv[6]) == 2;
+  const bool velo = argc > 6 && atoi(argv[6]) == 3;   // constant-velocity priors, default (free) interFrameRatio
   if (gs) sess.rs = 0;
   sess.frames.resize(F);
   for (long k = 0; k < F; ++k) {
@@ -96,6 +97,8 @@ int main(int argc, char** argv) {
   mock::Options opt;
   opt.ceres.fixFirstNCameras = (unsigned)atoi(argv[3]);
   opt.model.calibrated = !uncal;
+  if (velo) opt.ceres.constFrameVelocity = 10.0;
+  double ratio_out = 1.0;
   const size_t startFrame = argc > 5 ? (size_t)atol(argv[5]) : 0;
 
   rsba_solve_summary s;
@@ -105,6 +108,7 @@ int main(int argc, char** argv) {
     rsba_solve_options o = rsba_cuda::Problem::DefaultOptions();
     o.max_num_iterations = atoi(argv[4]);
     s = cs.solve(&o);                                                        // VideoSfMHandler.cc:592
+    ratio_out = cs.opt.ceres.interFrameRatio;
   } catch (const std::exception& e) {
     fprintf(stderr, "handler_check: %s\n", e.what());
     return 1;
@@ -121,6 +125,7 @@ int main(int argc, char** argv) {
   }
   for (long p = 0; p < P; ++p) fwrite(sess.tracks[(int)p].pt.data(), sizeof(double), 3, g);
   if (uncal) fwrite(sess.cam.data(), sizeof(double), 9, g);
+  if (velo) fwrite(&ratio_out, sizeof(double), 1, g);
   fclose(g);
   return 0;
 }
