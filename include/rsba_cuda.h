@@ -168,6 +168,24 @@ long rsba_cuda_get_prior_ratio_jacobian(rsba_problem* h, double* d_residual_d_ra
  * may be NULL); returns the number of priors. */
 long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals);
 
+/* Replaces: GoodPosePrior::Create(opt.ceres.trustPriorCamRotation, opt.ceres.trustPriorCamPosition) +
+ * problem.AddResidualBlock(cost, nullptr, f.priorPoses[i].data(), f.poses[i].data())  (CeresHandler.h:55-73,
+ * 188-204): 6 residuals  diag(rotation x3, position x3) (prior - pose), no loss; the functor returns false
+ * when the first residual is >= 1.  BOTH blocks are parameter blocks -- the reference never fixes the prior
+ * block, so it moves too (it is eliminated in closed form on the device and written back after the solve);
+ * rsba_cuda_set_block_constant(prior_block) fixes it.  pose_block must be one of the control-pose blocks of
+ * a frame that also appears in a reprojection residual block.  One prior per control pose. */
+int rsba_cuda_add_pose_prior(rsba_problem* h, double rotation, double position, double* prior_block,
+                             double* pose_block);
+/* Bulk form (after rsba_cuda_set_scene, which clears the list): prior i ties prior_values[6 i .. 6 i + 5] to
+ * control pose which_pose[i] (0 | 1) of frame[i]; prior_constant may be NULL (all free, as in the reference). */
+int rsba_cuda_set_pose_priors(rsba_problem* h, int n, const int* frame, const int* which_pose,
+                              const double* rotation, const double* position, const double* prior_values,
+                              const unsigned char* prior_constant);
+/* Current values [6 n] of the prior blocks and the trial values of the last LM step (HOST pointers, either
+ * may be NULL); returns the number of pose priors or -1. */
+long rsba_cuda_get_pose_priors(rsba_problem* h, double* prior_values, double* trial_values);
+
 /* Replaces: problem.SetParameterBlockConstant(double*)  (CeresHandler.h:283,299,344-345). */
 int rsba_cuda_set_block_constant(rsba_problem* h, double* block);
 /* Replaces: problem.SetParameterization(pose, new SubsetParameterization(6, constant))

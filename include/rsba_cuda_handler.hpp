@@ -66,6 +66,10 @@ class Problem {
   void AddMotionPrior(int kind, double scale, double ratio, double* pose0, double* end0, double* pose1, double* end1) {
     check(rsba_cuda_add_motion_prior(h_, kind, scale, ratio, pose0, end0, pose1, end1));
   }
+  // GoodPosePrior between a prior block and a control pose; both are parameter blocks (CeresHandler.h:188-204)
+  void AddPosePrior(double rotation, double position, double* prior_block, double* pose_block) {
+    check(rsba_cuda_add_pose_prior(h_, rotation, position, prior_block, pose_block));
+  }
   // the shared `&opt.ceres.interFrameRatio` block left variable, with its lower bound (CeresHandler.h:156-180)
   void SetInterFrameRatioBlock(double* ratio) { check(rsba_cuda_set_inter_frame_ratio_block(h_, ratio)); }
   void SetParameterBlockConstant(double* block) { check(rsba_cuda_set_block_constant(h_, block)); }
@@ -114,7 +118,7 @@ class Problem {
 // __isset.pt, obs[j].frame}, cam, rs, scanlines.  Options: model.{use3Dpoints, calibrated,
 // constVelocity, interpolateRotation}, ceres.{huberLoss, const3d, fixFirstNCameras, fixScale,
 // fixRotation, fixPosition, useOnlyValidMatches, constFrameVelocity, constFrameAcceleration,
-// interFrameRatio}.
+// interFrameRatio, trustPriorCamRotation, trustPriorCamPosition}; frames[k].priorPoses + __isset.priorPoses.
 template <typename Session, typename Options>
 class Handler {
  public:
@@ -134,6 +138,11 @@ class Handler {
       camera_set_ = true;
     }
     auto& f = sess.frames[frameKey];
+    // "good initial guess" priors (CeresHandler.h:188-204); a size mismatch re-seeds the poses from the priors
+    const bool pose_priors = frameKey >= (std::size_t)opt.ceres.fixFirstNCameras &&
+                             (opt.ceres.trustPriorCamRotation != 0 || opt.ceres.trustPriorCamPosition != 0) &&
+                             f.__isset.priorPoses && f.priorPoses.size() > 0;
+    if (pose_priors && f.poses.size() != f.priorPoses.size()) f.poses = f.priorPoses;
     // A frame with ONE pose is the reference's global-shutter case: ReprojectionError <2; 6, 3> on
     // getPose() = f.poses[0] (CeresHandler.h:265-286, struct/VideoSfM.cc:104-106).  The device path
     // always has two control-pose blocks per frame; with a GLOBAL shutter the second one does not
@@ -174,6 +183,10 @@ class Handler {
           for (auto& pose : f_1.poses) problem.SetParameterBlockConstant(pose.data());
       }
     }
+    if (pose_priors)
+      for (std::size_t i = 0; i < f.poses.size(); ++i)
+        problem.AddPosePrior(opt.ceres.trustPriorCamRotation, opt.ceres.trustPriorCamPosition,
+                             f.priorPoses[i].data(), f.poses[i].data());
     for (auto& o : f.obs) {                                   // CeresHandler.h:208
       if (!o.__isset.track) continue;
       auto* t = &sess.getTrack(o.track);

@@ -307,6 +307,42 @@ def motion_prior_rows(scene, priors, poses=None, huber=0.0, free_ratio=None):
     return Jx, np.concatenate(res), cost
 
 
+def pose_prior_rows(scene, priors, poses=None):
+    """TEST INFRASTRUCTURE.  GoodPosePrior <6; 6, 6> (CeresHandler.h:55-73, wired at :188-204):
+    r = diag(rot x3, pos x3) (prior - pose); the functor is valid iff r[0] < 1.  ``priors`` is a list of
+    (frame, which_pose, rotation, position, prior_values[6], constant).  The prior blocks are parameter
+    blocks of their own (the reference never fixes them); for the dense restatement they are appended as
+    pseudo-frames F, F+1, ... (parameters 0..5 = the prior block, 6..11 constant).  Returns
+    (scene' with those frames, pose_mask', J scipy CSR [6 n, 12 (F + n) + 3 P], r [6 n], cost, valid)."""
+    import copy
+    import scipy.sparse as sp
+    F, P, n = scene.num_frames, scene.num_points, len(priors)
+    poses = np.asarray(scene.poses if poses is None else poses, dtype=np.float64).reshape(-1, 12)
+    sc = copy.copy(scene)
+    extra = np.zeros((n, 12))
+    mask = np.where(np.asarray(scene.const_frames, dtype=bool), 0xFFF, 0).astype(np.int64)
+    mask = np.concatenate([mask, np.full(n, 0xFC0, dtype=np.int64)])
+    rows, cols, vals, res = [], [], [], []
+    valid = True
+    for i, (f, which, rot, pos, val, constant) in enumerate(priors):
+        extra[i, :6] = val
+        if constant:
+            mask[F + i] = 0xFFF
+        w = np.array([rot] * 3 + [pos] * 3, dtype=np.float64)
+        r = w * (np.asarray(val, dtype=np.float64) - poses[f, 6 * which:6 * which + 6])
+        valid = valid and bool(r[0] < 1.0)
+        res.append(r)
+        rows += [6 * i + np.arange(6)] * 2
+        cols += [12 * (F + i) + np.arange(6), 12 * f + 6 * which + np.arange(6)]
+        vals += [w, -w]
+    sc.poses = np.vstack([poses, extra])
+    sc.const_frames = np.concatenate([np.asarray(scene.const_frames, dtype=bool), np.zeros(n, dtype=bool)])
+    Jx = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                       shape=(6 * n, 12 * (F + n) + 3 * P))
+    rr = np.concatenate(res)
+    return sc, mask, Jx, rr, 0.5 * float(rr @ rr), valid
+
+
 def evaluate_cam_ref(scene, poses=None, points=None, cam=None, nthreads=0):
     """TEST INFRASTRUCTURE.  Uncalibrated variant <2; 9, 6, 6, 3> (VideoSfmBaRs.h:38-49) through the
     reference's own ReprojectionError::operator()(camera, pose, point, residuals) under Jet<24>

@@ -40,6 +40,7 @@ SYMBOLS = [
     "rsba_cuda_add_motion_prior", "rsba_cuda_set_motion_priors", "rsba_cuda_get_prior_residuals",
     "rsba_cuda_set_inter_frame_ratio_block", "rsba_cuda_set_inter_frame_ratio_free", "rsba_cuda_get_inter_frame_ratio",
     "rsba_cuda_get_prior_ratio_jacobian",
+    "rsba_cuda_add_pose_prior", "rsba_cuda_set_pose_priors", "rsba_cuda_get_pose_priors",
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
@@ -145,6 +146,10 @@ def load_library():
     lib.rsba_cuda_get_inter_frame_ratio.argtypes = [vp, vp]
     lib.rsba_cuda_get_prior_ratio_jacobian.argtypes = [vp, vp]
     lib.rsba_cuda_get_prior_ratio_jacobian.restype = C.c_long
+    lib.rsba_cuda_add_pose_prior.argtypes = [vp, C.c_double, C.c_double, vp, vp]
+    lib.rsba_cuda_set_pose_priors.argtypes = [vp, C.c_int, _ip, _ip, _dp, _dp, _dp, vp]
+    lib.rsba_cuda_get_pose_priors.argtypes = [vp, vp, vp]
+    lib.rsba_cuda_get_pose_priors.restype = C.c_long
     lib.rsba_cuda_set_block_constant.argtypes = [vp, vp]
     lib.rsba_cuda_set_subset_constant.argtypes = [vp, vp, C.c_int, _ip]
     lib.rsba_cuda_set_scene.argtypes = [vp, C.c_long, _dp, _ip, _ip, C.c_int, C.c_int,
@@ -321,6 +326,34 @@ class Problem:
         if n > 0:
             self.lib.rsba_cuda_get_prior_ratio_jacobian(self._h, _addr(j))
         return j
+
+    def add_pose_prior(self, rotation, position, prior_block, pose_block):
+        """GoodPosePrior between a 6-wide prior block and a control-pose block (CeresHandler.h:188-204)."""
+        assert prior_block.dtype == np.float64 and prior_block.size == 6 and prior_block.flags.c_contiguous
+        self._keep.extend((prior_block, pose_block))
+        self._check(self.lib.rsba_cuda_add_pose_prior(self._h, float(rotation), float(position), _addr(prior_block),
+                                                      _addr(pose_block)))
+
+    def set_pose_priors(self, frame, which_pose, rotation, position, prior_values, prior_constant=None):
+        frame = np.ascontiguousarray(frame, dtype=np.int32)
+        which = np.ascontiguousarray(which_pose, dtype=np.int32)
+        rot = np.ascontiguousarray(rotation, dtype=np.float64)
+        pos = np.ascontiguousarray(position, dtype=np.float64)
+        val = np.ascontiguousarray(prior_values, dtype=np.float64).reshape(-1)
+        assert val.size == 6 * frame.size
+        cst = None if prior_constant is None else np.ascontiguousarray(prior_constant, dtype=np.uint8)
+        self._check(self.lib.rsba_cuda_set_pose_priors(self._h, int(frame.size), frame.ctypes.data_as(_ip),
+                                                       which.ctypes.data_as(_ip), rot.ctypes.data_as(_dp),
+                                                       pos.ctypes.data_as(_dp), val.ctypes.data_as(_dp),
+                                                       None if cst is None else _addr(cst)))
+
+    def pose_priors(self):
+        """(current values [n, 6], trial values of the last LM step [n, 6]) of the prior blocks."""
+        n = self.lib.rsba_cuda_get_pose_priors(self._h, None, None)
+        val, trial = np.zeros((max(n, 0), 6)), np.zeros((max(n, 0), 6))
+        if n > 0:
+            self.lib.rsba_cuda_get_pose_priors(self._h, _addr(val), _addr(trial))
+        return val, trial
 
     def prior_residuals(self):
         n = self.lib.rsba_cuda_get_prior_residuals(self._h, None)

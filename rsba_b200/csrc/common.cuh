@@ -54,6 +54,22 @@ struct PriorView {
   double* jr;            // [n][12] loss-corrected d residual / d ratio at the linearisation point
 };
 
+// "Good initial guess" priors (GoodPosePrior, CeresHandler.h:55-73, wired at :188-204): residual
+// diag(rotation x3, position x3) (prior - pose) between a 6-wide PRIOR block and one control pose.  The
+// reference never fixes the prior block, so by default it is a free parameter block that occurs in this one
+// residual only: it is eliminated in closed form like a 3-D point seen once (k2_pose_priors.cu).
+struct PosePriorView {
+  int n;
+  const int* slot;               // [n] control pose = 2 * frame + (0 | 1): parameters 6*slot .. 6*slot+5
+  const double* w;               // [n][2] rotation, position weights
+  const unsigned char* constant; // [n] prior block held constant (set_block_constant)
+  double* val;                   // [n][6] current prior block values
+  double* trial;                 // [n][6] trial values
+  double* r;                     // [n][6] residuals at the linearisation point
+  double* cinv;                  // [n][6] s^2 / (s^2 w^2 + D^2): inverse of the damped block (unscaled space)
+  double* d2;                    // [n][6] LM diagonal of the block over s^2 (so that D^2 (delta/s)^2 = d2 delta^2)
+};
+
 // Kernel attributes (opt-in shared memory) are per device: true the first time `slot` (one per call
 // site) is seen on the current device.
 inline bool first_use_on_device(bool (&seen)[64]) {
@@ -82,6 +98,10 @@ void launch_validate(const CameraModel& cm, const ObsView& obs, const double* po
 // invalid_count += priors whose functor returns false (ratio below the functor's bound; free ratio only)
 void launch_prior_eval(const PriorView& pv, const double* poses, double huber, double* cost_out, bool store,
                        int* invalid_count, cudaStream_t stream);
+// pose priors: cost_out[0] = sum |r|^2 at (poses, vals); store: residuals for the linearisation;
+// invalid_count += blocks whose functor returns false (rotation residual >= 1, CeresHandler.h:66)
+void launch_pose_prior_eval(const PosePriorView& pv, const double* poses, const double* vals, double* cost_out,
+                            bool store, int* invalid_count, cudaStream_t stream);
 int k1_num_partials(long n);
 // deterministic fixed-order sum of `n` partials into out[0]
 void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t stream);

@@ -110,6 +110,15 @@ void launch_phi_cam(const SchurStructure& st, const double* jac, const double* j
 // adds the priors' J^T J / J^T r to B, gc, diagB and writes the frame-to-previous-frame couplings
 void launch_prior_blocks(const PriorView& pv, NormalEq ne, int n_frames, cudaStream_t s);
 
+// pose priors (k2_pose_priors.cu): inverse of every damped prior block; with `add` also the block's
+// contribution to B, diag(B), gc, wf of its control pose, Schur term included (B += w^2 - w^4 cinv)
+void launch_pose_prior_blocks(const PosePriorView& pv, NormalEq ne, LmOptionsDev o, bool jacobi, bool add,
+                              cudaStream_t s);
+// back-substitution of the prior blocks, trial values; adds their part to scalars[0..2]
+void launch_pose_prior_step(const PosePriorView& pv, const double* delta_c, double* scalars, cudaStream_t s);
+// adds |x|^2 of the free prior blocks to scalars[3], max|g| to scalars[4]
+void launch_pose_prior_norms(const PosePriorView& pv, double* scalars, cudaStream_t s);
+
 // Schur complement (k2_schur.cu).  S is tile-packed (see TileSchedule: structurally non-zero lower
 // tiles, diagonal tiles stored as full squares); rhs/d2_c in the permuted order given by tile_pos.
 void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,

@@ -461,6 +461,11 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     launch_prior_blocks(pv, lm->ne, h->n_frames, s);
     h->launches += 1;
   }
+  const PosePriorView ppv = h->pose_prior_view();
+  if (ppv.n > 0) {   // GoodPosePrior blocks: eliminated in closed form; their terms are added once (rank 0)
+    launch_pose_prior_blocks(ppv, lm->ne, o, opt.jacobi_scaling != 0, h->rank == 0, s);
+    h->launches += 1;
+  }
   launch_clear_tiles(lm->S.ptr, lm->ts, s);
   stage_begin(h, kStagePhiBuild);
   launch_phi_build(lm->st, obs, h->d_jac.ptr, lm->ne, s);
@@ -496,6 +501,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   if (compute_scale) { launch_jacobi_scale(lm->n_cam_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
   launch_schur_finalize(lm->st, lm->ne, o, lm->S.ptr, lm->ts, lm->n_cam_frames, lm->rhs.ptr, s);
   launch_camera_norms(lm->ne, lm->n_cam_frames, h->d_poses.ptr, lm->scalars.ptr, s);
+  if (ppv.n > 0) { launch_pose_prior_norms(ppv, lm->scalars.ptr, s); h->launches += 1; }
   h->launches += 3;
   stage_end(h, kStageFinalize);
   return RSBA_OK;
@@ -556,6 +562,8 @@ void step_update(rsba_problem* h, LmState* lm) {
                      lm->trial_points.ptr, lm->scalars.ptr, lm->scratch.ptr,
                      lm->free_ratio ? 12 * h->n_frames + 9 : -1, h->ratio_lower_bound(), h->stream);
   h->launches += 3;
+  const PosePriorView ppv = h->pose_prior_view();
+  if (ppv.n > 0) { launch_pose_prior_step(ppv, lm->delta_c.ptr, lm->scalars.ptr, h->stream); h->launches += 1; }
   stage_end(h, kStageUpdate);
 }
 
@@ -640,6 +648,8 @@ int prepare_solve(rsba_problem* h, const rsba_solve_options* opt) {
   if (!h->params_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_parameters has not been called");
   int rc = upload_priors(h);
   if (rc) return rc;
+  rc = upload_pose_priors(h);
+  if (rc) return rc;
   rc = ensure_eval_buffers(h, true);
   if (rc) return rc;
   h->reorder_tiles = opt->reorder_tiles != 0;
@@ -664,7 +674,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   LmState* lm = h->lm;
   for (auto& t : h->timers) t.total_ms = 0.0;
   sum->num_residual_blocks = h->n_obs;
-  sum->num_parameters_reduced = lm->num_free_params;
+  sum->num_parameters_reduced = lm->num_free_params + h->free_pose_prior_params();
 
   auto finish = [&](int term, const char* msg, double cost, double radius, double gmax) {
     sum->termination = term;
@@ -745,6 +755,8 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         sum->num_successful_steps++;
         cudaMemcpyAsync(h->d_poses.ptr, lm->trial_poses.ptr, 12L * lm->n_cam_frames * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         cudaMemcpyAsync(h->d_points.ptr, lm->trial_points.ptr, h->d_points.bytes(), cudaMemcpyDeviceToDevice, h->stream);
+        if (!h->pose_priors.empty())
+          cudaMemcpyAsync(h->d_pp_val.ptr, h->d_pp_trial.ptr, h->d_pp_val.bytes(), cudaMemcpyDeviceToDevice, h->stream);
         radius = std::min(opt->max_trust_region_radius,
                           radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
         decrease = 2.0;

@@ -92,7 +92,7 @@ int ensure_eval_buffers(rsba_problem* h, bool jac) {
   const size_t n = (size_t)h->n_obs;
   RSBA_CUDA_TRY(h->d_res.resize(2 * n));
   RSBA_CUDA_TRY(h->d_valid.resize(n));
-  RSBA_CUDA_TRY(h->d_cost_partials.resize((size_t)k1_num_partials(h->n_obs) + 1));
+  RSBA_CUDA_TRY(h->d_cost_partials.resize((size_t)k1_num_partials(h->n_obs) + 2));
   RSBA_CUDA_TRY(h->d_scalars.resize(16));
   RSBA_CUDA_TRY(h->d_invalid.resize(4));
   if (jac) RSBA_CUDA_TRY(h->d_jac.resize((size_t)kJacDoubles * n));
@@ -122,7 +122,16 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
   } else {
     RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np, 0, sizeof(double), h->stream));
   }
-  launch_reduce_partials(h->d_cost_partials.ptr, np + 1, h->d_scalars.ptr, h->stream);
+  // ... and the pose priors' (GoodPosePrior) in the next one; they go with the point the poses belong to
+  const PosePriorView ppv = h->pose_prior_view();
+  if (ppv.n > 0 && h->rank == 0) {
+    launch_pose_prior_eval(ppv, poses, poses == h->d_poses.ptr ? ppv.val : ppv.trial, h->d_cost_partials.ptr + np + 1,
+                           jac, h->d_invalid.ptr, h->stream);
+    h->launches += 1;
+  } else {
+    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np + 1, 0, sizeof(double), h->stream));
+  }
+  launch_reduce_partials(h->d_cost_partials.ptr, np + 2, h->d_scalars.ptr, h->stream);
   stage_end(h, st);
   h->launches += 2;
   RSBA_CUDA_TRY(cudaGetLastError());
@@ -306,6 +315,50 @@ int upload_priors(rsba_problem* h) {
   return RSBA_OK;
 }
 
+int upload_pose_priors(rsba_problem* h) {
+  if (!h->pose_priors_dirty) return RSBA_OK;
+  const int n = (int)h->pose_priors.size(), F = h->n_frames;
+  const size_t nz = (size_t)std::max(n, 1);
+  std::vector<int> slot(nz, 0);
+  std::vector<unsigned char> cst(nz, 0), used((size_t)2 * std::max(F, 1), 0);
+  std::vector<double> w(2 * nz, 0.0), val(6 * nz, 0.0);
+  for (int i = 0; i < n; ++i) {
+    auto& p = h->pose_priors[i];
+    if (h->ptr_mode) {   // the control pose is known by its block address only
+      auto a = h->pose0_to_frame.find(p.pose);
+      if (a != h->pose0_to_frame.end()) p.slot = 2 * a->second;
+      else {
+        auto b = h->pose1_to_frame.find(p.pose);
+        if (b == h->pose1_to_frame.end()) return fail(RSBA_ERR_INVALID_ARGUMENT, "pose prior on a pose block that no residual block uses");
+        p.slot = 2 * b->second + 1;
+      }
+      memcpy(p.val, p.prior, sizeof(p.val));
+    }
+    if (p.slot < 0 || p.slot >= 2 * F) return fail(RSBA_ERR_INVALID_ARGUMENT, "pose prior: control pose out of range");
+    if (used[p.slot]) return fail(RSBA_ERR_INVALID_ARGUMENT, "pose prior: a control pose has two priors");
+    used[p.slot] = 1;
+    slot[i] = p.slot; cst[i] = p.constant; w[2 * i] = p.rot; w[2 * i + 1] = p.pos;
+    memcpy(&val[6 * (size_t)i], p.val, sizeof(p.val));
+  }
+  auto up = [&](auto& dev, const auto& host) -> cudaError_t {
+    cudaError_t e = dev.resize(host.size());
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(dev.ptr, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, h->stream);
+  };
+  RSBA_CUDA_TRY(up(h->d_pp_slot, slot));
+  RSBA_CUDA_TRY(up(h->d_pp_const, cst));
+  RSBA_CUDA_TRY(up(h->d_pp_w, w));
+  RSBA_CUDA_TRY(up(h->d_pp_val, val));
+  RSBA_CUDA_TRY(up(h->d_pp_trial, val));
+  RSBA_CUDA_TRY(h->d_pp_r.resize(6 * nz));
+  RSBA_CUDA_TRY(h->d_pp_cinv.resize(6 * nz));
+  RSBA_CUDA_TRY(h->d_pp_d2.resize(6 * nz));
+  RSBA_CUDA_TRY(cudaMemsetAsync(h->d_pp_r.ptr, 0, h->d_pp_r.bytes(), h->stream));
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->pose_priors_dirty = false;
+  return RSBA_OK;
+}
+
 static int check_prior_args(int kind, double scale, double ratio) {
   if (kind != 1 && kind != 2) return fail(RSBA_ERR_INVALID_ARGUMENT, "motion prior kind must be 1 (velocity) or 2 (acceleration)");
   if (!(scale > 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "motion prior scale must be positive");
@@ -335,6 +388,7 @@ int finalize_pointer_problem(rsba_problem* h) {
   h->point_const.resize(h->n_points, 0);
   h->ptr_dirty = false;
   h->priors_dirty = true;
+  h->pose_priors_dirty = true;
   return upload_priors(h);
 }
 
@@ -347,6 +401,7 @@ int gather_pointer_parameters(rsba_problem* h) {
   for (int p = 0; p < h->n_points; ++p) memcpy(&points[(size_t)3 * p], h->point_ptr[p], 3 * sizeof(double));
   if (h->ptr_cam) memcpy(h->cm.cam, h->ptr_cam, 9 * sizeof(double));   // the intrinsics block's current values
   if (h->ptr_ratio) h->ratio_value = *h->ptr_ratio;
+  if (!h->pose_priors.empty()) h->pose_priors_dirty = true;   // re-read the caller's prior blocks
   return rsba_cuda_set_parameters(h, poses.data(), points.data());
 }
 
@@ -368,6 +423,12 @@ int scatter_pointer_parameters(rsba_problem* h) {
   if (h->ptr_ratio) {
     rc = rsba_cuda_get_inter_frame_ratio(h, h->ptr_ratio);
     if (rc) return rc;
+  }
+  if (!h->pose_priors.empty()) {
+    std::vector<double> vals(6 * h->pose_priors.size());
+    if (rsba_cuda_get_pose_priors(h, vals.data(), nullptr) < 0) return RSBA_ERR_CUDA;
+    for (size_t i = 0; i < h->pose_priors.size(); ++i)
+      if (h->pose_priors[i].prior) memcpy(h->pose_priors[i].prior, &vals[6 * i], 6 * sizeof(double));
   }
   return RSBA_OK;
 }
@@ -611,6 +672,55 @@ long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals) {
   return n;
 }
 
+int rsba_cuda_add_pose_prior(rsba_problem* h, double rotation, double position, double* prior_block,
+                             double* pose_block) {
+  if (!h || !prior_block || !pose_block) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
+  if (h->pose_prior_of_block.count(prior_block)) return fail(RSBA_ERR_INVALID_ARGUMENT, "prior block already used");
+  h->ptr_mode = true;
+  rsba_problem::PosePriorHost p{};
+  p.slot = -1; p.rot = rotation; p.pos = position; p.constant = 0; p.prior = prior_block; p.pose = pose_block;
+  h->pose_prior_of_block[prior_block] = (int)h->pose_priors.size();
+  h->pose_priors.push_back(p);
+  h->pose_priors_dirty = true;
+  h->ptr_dirty = true;
+  return RSBA_OK;
+}
+
+int rsba_cuda_set_pose_priors(rsba_problem* h, int n, const int* frame, const int* which_pose, const double* rotation,
+                              const double* position, const double* prior_values, const unsigned char* prior_constant) {
+  if (!h || n < 0 || (n > 0 && (!frame || !which_pose || !rotation || !position || !prior_values)))
+    return fail(RSBA_ERR_INVALID_ARGUMENT, "bad pose prior arguments");
+  if (h->ptr_mode) return fail(RSBA_ERR_STATE, "handle holds pointer-API blocks: use rsba_cuda_add_pose_prior");
+  if (!h->scene_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_scene first");
+  std::vector<rsba_problem::PosePriorHost> list;
+  for (int i = 0; i < n; ++i) {
+    if (which_pose[i] != 0 && which_pose[i] != 1) return fail(RSBA_ERR_INVALID_ARGUMENT, "which_pose must be 0 or 1");
+    if (frame[i] < 0 || frame[i] >= h->n_frames) return fail(RSBA_ERR_INVALID_ARGUMENT, "pose prior: frame out of range");
+    rsba_problem::PosePriorHost p{};
+    p.slot = 2 * frame[i] + which_pose[i]; p.rot = rotation[i]; p.pos = position[i];
+    p.constant = prior_constant && prior_constant[i] ? 1 : 0;
+    memcpy(p.val, prior_values + 6 * (size_t)i, sizeof(p.val));
+    list.push_back(p);
+  }
+  h->pose_priors.swap(list);
+  h->pose_priors_dirty = true;
+  RSBA_CUDA_TRY(cudaSetDevice(h->device));
+  return upload_pose_priors(h);
+}
+
+long rsba_cuda_get_pose_priors(rsba_problem* h, double* prior_values, double* trial_values) {
+  if (!h) return -1;
+  const long n = h->pose_priors_dirty ? 0 : (long)h->pose_priors.size();
+  if (n > 0 && (prior_values || trial_values)) {
+    cudaSetDevice(h->device);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    if (prior_values && cudaMemcpy(prior_values, h->d_pp_val.ptr, 6 * n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (trial_values && cudaMemcpy(trial_values, h->d_pp_trial.ptr, 6 * n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  }
+  return n;
+}
+
 static int set_ratio_free(rsba_problem* h, bool want, double value) {
   if (want) {
     // the functors return false below these bounds (video_bundler_rs_inter.h:92, 157)
@@ -714,6 +824,8 @@ int rsba_cuda_set_block_constant(rsba_problem* h, double* block) {
   if (b != h->pose1_to_frame.end()) { h->ptr_pose_mask[b->second] |= 0xFC0; h->ptr_dirty = true; return RSBA_OK; }
   auto c = h->point_to_id.find(block);
   if (c != h->point_to_id.end()) { h->ptr_point_const[c->second] = 1; h->ptr_dirty = true; return RSBA_OK; }
+  auto d = h->pose_prior_of_block.find(block);
+  if (d != h->pose_prior_of_block.end()) { h->pose_priors[d->second].constant = 1; h->pose_priors_dirty = true; return RSBA_OK; }
   return fail(RSBA_ERR_INVALID_ARGUMENT, "unknown parameter block (Ceres would abort here too)");
 }
 
@@ -750,6 +862,9 @@ int rsba_cuda_set_scene(rsba_problem* h, long n_obs, const double* obs_xy, const
   h->priors.clear();
   h->priors_dirty = true;
   if ((rc = upload_priors(h))) return rc;
+  h->pose_priors.clear();
+  h->pose_priors_dirty = true;
+  if ((rc = upload_pose_priors(h))) return rc;
   h->pose_mask.assign(n_frames, 0);
   h->point_const.assign(n_points, 0);
   if (const_pose_mask) for (int f = 0; f < n_frames; ++f) h->pose_mask[f] = const_pose_mask[f] & 0xFFF;
@@ -801,7 +916,9 @@ static int prepare(rsba_problem* h) {
   }
   if (!h->scene_set) return fail(RSBA_ERR_STATE, "no residual blocks");
   if (!h->params_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_parameters has not been called");
-  return upload_priors(h);
+  int rc = upload_priors(h);
+  if (rc) return rc;
+  return upload_pose_priors(h);
 }
 
 int rsba_cuda_evaluate_device(rsba_problem* h, int with_jacobian, double* cost, long* num_invalid) {

@@ -136,6 +136,34 @@ struct rsba_problem {
     return v;
   }
 
+  // ---- GoodPosePrior blocks (k2_pose_priors.cu)
+  struct PosePriorHost {
+    int slot;                // control pose = 2 * frame + (0 | 1); pointer API: resolved when the problem is finalised
+    double rot, pos;         // opt.ceres.trustPriorCamRotation / trustPriorCamPosition
+    double val[6];           // prior block values (bulk API; pointer API: read from `prior` at solve entry)
+    unsigned char constant;  // prior block fixed by the caller
+    double* prior;           // pointer API: the caller's prior block (f.priorPoses[i].data())
+    double* pose;            // pointer API: the control-pose block (f.poses[i].data())
+  };
+  std::vector<PosePriorHost> pose_priors;
+  std::unordered_map<const double*, int> pose_prior_of_block;   // pointer API: prior block -> index
+  bool pose_priors_dirty = false;
+  rsba::DeviceBuffer<int> d_pp_slot;
+  rsba::DeviceBuffer<unsigned char> d_pp_const;
+  rsba::DeviceBuffer<double> d_pp_w, d_pp_val, d_pp_trial, d_pp_r, d_pp_cinv, d_pp_d2;
+  rsba::PosePriorView pose_prior_view() const {
+    rsba::PosePriorView v{};
+    v.n = pose_priors_dirty ? 0 : (int)pose_priors.size();
+    v.slot = d_pp_slot.ptr; v.w = d_pp_w.ptr; v.constant = d_pp_const.ptr; v.val = d_pp_val.ptr;
+    v.trial = d_pp_trial.ptr; v.r = d_pp_r.ptr; v.cinv = d_pp_cinv.ptr; v.d2 = d_pp_d2.ptr;
+    return v;
+  }
+  long free_pose_prior_params() const {
+    long n = 0;
+    for (const auto& p : pose_priors) n += p.constant ? 0 : 6;
+    return n;
+  }
+
   rsba::StageTimer timers[rsba::kNumStages];
   long launches = 0;
 
@@ -164,6 +192,7 @@ void compute_point_owners(int n_frames, int n_points, long n_obs, const int* obs
                           const int* obs_point, int world, std::vector<int>* owner);
 int allreduce_sum(rsba_problem* h, double* buf, size_t count);   // in place, on the handle's stream
 int upload_priors(rsba_problem* h);               // host prior list -> device (after the scene is final)
+int upload_pose_priors(rsba_problem* h);          // GoodPosePrior list (+ the prior blocks' current values) -> device
 int finalize_pointer_problem(rsba_problem* h);   // pointer API -> sorted SoA on device
 int gather_pointer_parameters(rsba_problem* h);  // caller blocks -> device
 int scatter_pointer_parameters(rsba_problem* h); // device -> caller blocks

@@ -163,3 +163,39 @@ def test_handler_velocity_priors_with_the_default_free_ratio(tmp_path):
     assert out[0] == 1 and abs(out[3] - s.final_cost) <= 1e-9 * s.final_cost
     assert np.linalg.norm(poses - po) <= 1e-7 * np.linalg.norm(po)
     assert abs(ratio[0] - ratio_bulk) <= 1e-9 and ratio[0] != 1.0
+
+
+@pytest.mark.gpu
+def test_handler_good_pose_priors(tmp_path):
+    """opt.ceres.trustPriorCamRotation / trustPriorCamPosition with f.priorPoses (CeresHandler.h:188-204): one
+    GoodPosePrior per control pose of every frame >= fixFirstNCameras; the prior blocks are free parameter
+    blocks (the reference never fixes them) and are written back in place; result == bulk API."""
+    import rsba_b200.api as api
+    sc = make_scene(10, 300, 8, name="good-handler")
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    r = subprocess.run([BIN, src, dst, "1", "8", "0", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst)
+    nf, npnt = sc.num_frames, sc.num_points
+    poses = out[4:4 + 12 * nf].reshape(-1, 12)
+    blocks = out[4 + 12 * nf + 3 * npnt:].reshape(nf, 2, 6)
+    k, c = np.arange(nf)[:, None, None], np.arange(6)[None, None, :]
+    prior0 = sc.poses.reshape(nf, 2, 6) + np.where(c < 3, 1e-3, 2e-2) * ((k + c) % 3 - 1)
+    frames = [f for f in range(1, nf) for _ in (0, 1)]
+    which = [w for _ in range(1, nf) for w in (0, 1)]
+    mask = np.zeros(nf, dtype=np.uint16)
+    mask[0] = 0xFFF
+    with api.Problem(0) as pb:
+        pb.set_camera(sc.cam, sc.shutter, sc.scanlines, sc.interpolate_rotation)
+        pb.set_scene(sc.obs_xy, sc.obs_frame, sc.obs_point, nf, npnt, mask)
+        pb.set_parameters(sc.poses, sc.points)
+        pb.set_pose_priors(frames, which, [20.0] * len(frames), [6.0] * len(frames), prior0[1:].reshape(-1, 6))
+        s = pb.solve(api.default_options(max_num_iterations=8))
+        po, _ = pb.get_parameters()
+        val, _ = pb.pose_priors()
+    assert out[0] == 1 and abs(out[3] - s.final_cost) <= 1e-9 * s.final_cost
+    assert np.linalg.norm(poses - po) <= 1e-7 * np.linalg.norm(po)
+    assert np.array_equal(blocks[0], prior0[0])                      # frame 0 < fixFirstNCameras: no prior, untouched
+    assert np.linalg.norm(blocks[1:].reshape(-1, 6) - val) <= 1e-7 * np.linalg.norm(val)
+    assert np.abs(blocks[1:] - prior0[1:]).max() > 1e-6              # the free prior blocks moved

@@ -5,7 +5,10 @@
 // runs the same calls VideoSfMHandler::BA makes (VideoSfMHandler.cc:586-592), writes the result.
 //   usage: handler_check <scene.bin> <out.bin> <fixFirstNCameras> <maxIter> [startFrame] [gs]
 //   (gs = 1: global-shutter session, every frame holds ONE pose -- the first control pose of the file;
-//    gs = 2: uncalibrated, opt.model.calibrated = false -- the optimised sess.cam is appended to the output)
+//    gs = 2: uncalibrated, opt.model.calibrated = false -- the optimised sess.cam is appended to the output;
+//    gs = 3: constant-velocity priors with the default, free interFrameRatio -- the ratio is appended;
+//    gs = 4: GoodPosePrior on every frame past the first, priorPoses = the initial poses + a fixed offset --
+//            the (free, hence moved) prior blocks are appended)
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -15,12 +18,12 @@
 
 namespace mock {
 struct IsSetObs { bool track = false; };
-struct IsSetFrame { bool cam = false; };
+struct IsSetFrame { bool cam = false, priorPoses = false; };
 struct ObservationRef { int frame = 0, obs = 0; };
 struct Observation { double x = 0, y = 0; int track = -1; IsSetObs __isset; std::vector<ObservationRef> matches; };
 struct IsSetTrack { bool pt = false; };
 struct Track { std::vector<double> pt; bool valid = true; IsSetTrack __isset; std::vector<ObservationRef> obs; };
-struct Frame { std::vector<std::vector<double>> poses; std::vector<Observation> obs; std::vector<double> cam; IsSetFrame __isset; };
+struct Frame { std::vector<std::vector<double>> poses, priorPoses; std::vector<Observation> obs; std::vector<double> cam; IsSetFrame __isset; };
 struct Session {
   std::vector<double> cam;
   int rs = 1;
@@ -33,6 +36,7 @@ struct Options {
   struct { bool use3Dpoints = true, calibrated = true, constVelocity = false, interpolateRotation = true; } model;
   struct {
     double huberLoss = 0, constFrameVelocity = 0, constFrameAcceleration = 0, interFrameRatio = 1;
+    double trustPriorCamRotation = 0, trustPriorCamPosition = 0;
     bool const3d = false, fixScale = false, fixRotation = false, fixPosition = false, useOnlyValidMatches = false;
     unsigned fixFirstNCameras = 1;
   } ceres;
@@ -67,6 +71,7 @@ int main(int argc, char** argv) {
   const bool gs = argc > 6 && atoi(argv[6]) == 1;
   const bool uncal = argc > 6 && atoi(argv[6]) == 2;
   const bool velo = argc > 6 && atoi(argv[6]) == 3;   // constant-velocity priors, default (free) interFrameRatio
+  const bool good = argc > 6 && atoi(argv[6]) == 4;   // GoodPosePrior blocks
   if (gs) sess.rs = 0;
   sess.frames.resize(F);
   for (long k = 0; k < F; ++k) {
@@ -98,6 +103,16 @@ int main(int argc, char** argv) {
   opt.ceres.fixFirstNCameras = (unsigned)atoi(argv[3]);
   opt.model.calibrated = !uncal;
   if (velo) opt.ceres.constFrameVelocity = 10.0;
+  if (good) {
+    opt.ceres.trustPriorCamRotation = 20.0;
+    opt.ceres.trustPriorCamPosition = 6.0;
+    for (long k = 0; k < F; ++k) {
+      sess.frames[k].priorPoses = sess.frames[k].poses;
+      for (auto& pose : sess.frames[k].priorPoses)
+        for (int c = 0; c < 6; ++c) pose[c] += (c < 3 ? 1e-3 : 2e-2) * ((k + c) % 3 - 1);
+      sess.frames[k].__isset.priorPoses = true;
+    }
+  }
   double ratio_out = 1.0;
   const size_t startFrame = argc > 5 ? (size_t)atol(argv[5]) : 0;
 
@@ -126,6 +141,9 @@ int main(int argc, char** argv) {
   for (long p = 0; p < P; ++p) fwrite(sess.tracks[(int)p].pt.data(), sizeof(double), 3, g);
   if (uncal) fwrite(sess.cam.data(), sizeof(double), 9, g);
   if (velo) fwrite(&ratio_out, sizeof(double), 1, g);
+  if (good)
+    for (long k = 0; k < F; ++k)
+      for (auto& pose : sess.frames[k].priorPoses) fwrite(pose.data(), sizeof(double), 6, g);
   fclose(g);
   return 0;
 }
