@@ -31,6 +31,17 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): a whole operand tile is put in flight at once.
+// These kernels are short and latency-bound; a load -> store loop through registers serialised one L2
+// round trip per iteration (18-36 of them per CTA) and was most of their run time.
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- clear structurally non-zero tiles
 __global__ void __launch_bounds__(256)
 clear_tiles_kernel(double* __restrict__ S) {
@@ -84,11 +95,15 @@ potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int 
   double* g = S + (long)tile_slot[k * T + k] * kTile * kTile;
   for (int e = tid; e < kTile * kTile / 2; e += blockDim.x) {
     const int r = e / (kTile / 2), c = 2 * (e % (kTile / 2));
-    const double2 v = reinterpret_cast<const double2*>(g)[e];
-    A[r * kLd + c] = (c <= r) ? v.x : 0.0;
-    A[r * kLd + c + 1] = (c + 1 <= r) ? v.y : 0.0;
+    cp_async16(A + r * kLd + c, g + 2 * e);
     X[r * kLd + c] = 0.0;
     X[r * kLd + c + 1] = 0.0;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  for (int e = tid; e < kTile * kTile; e += blockDim.x) {   // the factorisation works on the lower triangle
+    const int r = e / kTile, c = e % kTile;
+    if (c > r) A[r * kLd + c] = 0.0;
   }
   __syncthreads();
 
@@ -248,11 +263,10 @@ constexpr size_t kTrsmSmem = (size_t)((kTrsmRows + kTile) * kLd) * sizeof(double
 
 __device__ __forceinline__ void load_rows(double* dst, const double* __restrict__ src, int rows) {
   // rows x 96 doubles, rows of 48 double2
+  // (asynchronous: the caller runs cp_async_wait_all() + __syncthreads() before reading dst)
   for (int e = threadIdx.x; e < rows * (kTile / 2); e += blockDim.x) {
     const int r = e / (kTile / 2), c2 = e % (kTile / 2);
-    const double2 v = reinterpret_cast<const double2*>(src + (long)r * kTile)[c2];
-    dst[r * kLd + 2 * c2] = v.x;
-    dst[r * kLd + 2 * c2 + 1] = v.y;
+    cp_async16(dst + r * kLd + 2 * c2, src + (long)r * kTile + 2 * c2);
   }
 }
 
@@ -288,6 +302,7 @@ tile_trsm_kernel(double* S, const int* __restrict__ tile_slot, int T, const int2
   double* tile = S + (long)tile_slot[p.x * T + p.y] * kTile * kTile + (long)blockIdx.y * kTrsmRows * kTile;
   load_rows(As, tile, kTrsmRows);
   load_rows(Bs, Dinv + (long)p.y * kTile * kTile, kTile);
+  cp_async_wait_all();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int fr = lane >> 2, fc = lane & 3, n0 = warp * 24;
@@ -312,23 +327,26 @@ tile_update_kernel(double* S, const int* __restrict__ tile_slot, int T, const in
   if (ti == tj && qj > qi) return;   // diagonal target: the factorisation reads the lower part only
   load_rows(As, S + (long)tile_slot[ti * T + k] * kTile * kTile + (long)qi * kQ * kTile, kQ);
   load_rows(Bs, S + (long)tile_slot[tj * T + k] * kTile * kTile + (long)qj * kQ * kTile, kQ);
+  cp_async_wait_all();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (warp >> 1) * 24, n0 = (warp & 1) * 24;
   const int fr = lane >> 2, fc = lane & 3;
   double acc[3][3][2];
-  warp_gemm_24x24(As, Bs, m0, n0, lane, acc);
   double* Cg = S + (long)tile_slot[ti * T + tj] * kTile * kTile + (long)qi * kQ * kTile + qj * kQ;
+  double2 cv[3][3];   // the target's old values: requested before the GEMM, consumed after it
 #pragma unroll
   for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
-    for (int ni = 0; ni < 3; ++ni) {
-      double2* dst = reinterpret_cast<double2*>(Cg + (long)(m0 + 8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc);
-      double2 v = *dst;
-      v.x -= acc[mi][ni][0];
-      v.y -= acc[mi][ni][1];
-      *dst = v;
-    }
+    for (int ni = 0; ni < 3; ++ni)
+      cv[mi][ni] = *reinterpret_cast<const double2*>(Cg + (long)(m0 + 8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc);
+  warp_gemm_24x24(As, Bs, m0, n0, lane, acc);
+#pragma unroll
+  for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 3; ++ni)
+      *reinterpret_cast<double2*>(Cg + (long)(m0 + 8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc) =
+          make_double2(cv[mi][ni].x - acc[mi][ni][0], cv[mi][ni].y - acc[mi][ni][1]);
 }
 
 // ---------------------------------------------------------------- triangular solves, level by level
@@ -340,25 +358,40 @@ constexpr int kMaxSolveSplit = 16;
 
 __device__ __forceinline__ void apply_dinv_forward(const double* __restrict__ di, const double* tmp,
                                                    double* __restrict__ xk, int warp, int lane) {
-  for (int r = warp; r < kTile; r += 8) {
-    double s = 0.0;
+  // all 36 loads of the inverse are issued before the first use (fully unrolled: independent rows)
+  double s[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) {
+    const int r = warp + 8 * t;
+    double v = 0.0;
 #pragma unroll
     for (int c = 0; c < kTile; c += 32)
-      if (c + lane <= r) s += di[r * kTile + c + lane] * tmp[c + lane];
+      if (c + lane <= r) v += __ldg(di + r * kTile + c + lane) * tmp[c + lane];
+    s[t] = v;
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) xk[r] = s;
+  for (int t = 0; t < 12; ++t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) xk[warp + 8 * t] = s[t];
   }
 }
 
 __device__ __forceinline__ void apply_dinv_backward(const double* __restrict__ di, const double* tmp,
                                                     double (*part)[kTile + 1], double* __restrict__ xk,
                                                     int warp, int lane) {
+#pragma unroll
   for (int m = 0; m < 3; ++m) {
     const int r = lane + 32 * m;
     double s = 0.0;
-    for (int c = warp; c < kTile; c += 8)
-      if (c >= r) s += di[c * kTile + r] * tmp[c];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {     // fully unrolled: the 36 loads of the inverse go out together
+      const int c = warp + 8 * t;
+      if (c >= r) s += __ldg(di + c * kTile + r) * tmp[c];
+    }
     part[warp][r] = s;
   }
   __syncthreads();
