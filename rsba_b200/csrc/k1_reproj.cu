@@ -31,6 +31,12 @@ namespace {
 constexpr int kK1Threads = 128;
 constexpr int kK1Warps = kK1Threads / 32;
 constexpr int kStageFrames = 8;  // control poses staged per CTA (frames spanned by 128 obs)
+constexpr bool kStagePoses = false;       // experiment: stage the CTA's control poses in shared memory
+constexpr int kPrefetchTiles = 148 * 5;   // CTAs resident at once on a B200 (148 SMs x 5 per SM by registers)
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -71,30 +77,63 @@ k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__
 
   const long base = (long)blockIdx.x * kK1Threads;
   const int cnt = (int)min((long)kK1Threads, obs.n - base);
-  const int staged = stage_poses(obs, poses, base, cnt, s_pose);
-  __syncthreads();
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long i = base + threadIdx.x;
+  // The observation and its point are requested BEFORE the pose staging and its barrier: the two dependent
+  // round trips (index -> point, frame -> poses) then overlap instead of queueing behind each other.
+  double2 o = make_double2(0.0, 0.0);
+  int f = 0;
+  double X0 = 0.0, X1 = 0.0, X2 = 0.0;
+  if (i < obs.n) {
+    o = obs.xy[i];
+    f = obs.frame[i];
+    const double* pp = points + 3L * obs.point[i];
+    X0 = pp[0]; X1 = pp[1]; X2 = pp[2];
+  }
+  // Half of this kernel's stall samples sat on those input round trips (profiles/r01_notes.md).  CTAs run in
+  // blockIdx order, about one resident wave (kPrefetchTiles) at a time, so each CTA pulls the inputs of the
+  // CTAs two and one wave ahead into L2: the observation lines of tile + 2 waves, and -- through the point
+  // indices of tile + 1 wave, themselves prefetched a wave ago -- the 3-D points of tile + 1 wave.
+  int p_ahead = -1;
+  {
+    const long j2 = i + 2L * kPrefetchTiles * kK1Threads, j1 = i + 1L * kPrefetchTiles * kK1Threads;
+    if (j2 < obs.n) {
+      if ((lane & 7) == 0) prefetch_l2(obs.xy + j2);        // 8 x 16 B = one 128-byte line
+      if (lane == 0) { prefetch_l2(obs.frame + j2); prefetch_l2(obs.point + j2); }
+    }
+    if (j1 < obs.n) p_ahead = obs.point[j1];                // consumed after the arithmetic below
+  }
+  double pose[kFrameParams];
+  if (kStagePoses) {
+    const int staged = stage_poses(obs, poses, base, cnt, s_pose);
+    __syncthreads();
+    if (i < obs.n) {
+      if (staged >= 0) {
+        const double* sp = s_pose + (f - staged) * kFrameParams;
+#pragma unroll
+        for (int k = 0; k < kFrameParams; ++k) pose[k] = sp[k];
+      } else {
+        const double* gp = poses + (long)f * kFrameParams;
+#pragma unroll
+        for (int k = 0; k < kFrameParams; ++k) pose[k] = __ldg(gp + k);
+      }
+    }
+  } else if (i < obs.n) {
+    // no staging, no barrier: the frame's 96 bytes come through L1 (the threads of a warp share a frame, so
+    // these are broadcast hits) as six 128-bit loads that queue right behind the point gather
+    const double2* gp = reinterpret_cast<const double2*>(poses + (long)f * kFrameParams);
+#pragma unroll
+    for (int k = 0; k < kFrameParams / 2; ++k) {
+      const double2 v = __ldg(gp + k);
+      pose[2 * k] = v.x;
+      pose[2 * k + 1] = v.y;
+    }
+  }
+
   double cost = 0.0;
   bool bad = false;
   double* Jrow = JAC ? s_jac + (warp * 32 + lane) * kJacDoubles : nullptr;
   if (i < obs.n) {
-    const double2 o = obs.xy[i];
-    const int f = obs.frame[i];
-    const int p = obs.point[i];
-    const double* pp = points + 3L * p;
-    const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
-    double pose[kFrameParams];
-    if (staged >= 0) {
-      const double* sp = s_pose + (f - staged) * kFrameParams;
-#pragma unroll
-      for (int k = 0; k < kFrameParams; ++k) pose[k] = sp[k];
-    } else {
-      const double* gp = poses + (long)f * kFrameParams;
-#pragma unroll
-      for (int k = 0; k < kFrameParams; ++k) pose[k] = __ldg(gp + k);
-    }
     double Jc[CAM ? 18 : 1];
     constexpr bool want_cam = JAC && CAM;
     Proj pr = reproject<JAC>(cm, o.x, o.y, pose, X0, X1, X2, Jrow, want_cam ? Jc : nullptr);
@@ -143,6 +182,8 @@ k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
+
+  if (p_ahead >= 0) prefetch_l2(points + 3L * p_ahead);
 
   // cost partial of this CTA (fixed reduction order -> deterministic cost)
   cost = warp_sum(cost);
