@@ -230,6 +230,15 @@ int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double*
 int rsba_cuda_validate(rsba_problem* h, double sqrd_threshold, double min_distance_to_camera,
                        unsigned char* ok, double* sqrd_error);
 
+/* Iterative re-projection.  Replaces: reproject(sess, f, opt, t.pt, obs) (struct/VideoSfM.cc:139-155) for a batch
+ * of (frame, point) pairs at the CURRENT parameters: the rolling-shutter scan line of a projection is unknown, so
+ * the reference starts at the principal point and repeats  pose = getPose(proj), proj = w2i(cam, pose, pt)  until
+ * the projection moves by less than 1e-3 px, at most 49 times.  ok[i] = 0 when w2i fails (z < 1e-8), the limit is
+ * hit or sqrd_threshold <= 0 (the final validate() compares the projection with itself); proj_xy[i] is the last
+ * iterate either way.  HOST arrays: frame[n], point[n] in, proj_xy[2 n], ok[n] out. */
+int rsba_cuda_reproject(rsba_problem* h, long n, const int* frame, const int* point, double sqrd_threshold,
+                        double* proj_xy, unsigned char* ok);
+
 /* HBM-resident form: evaluates on the device and leaves everything there.  The returned
  * device pointers (sorted-by-frame observation order) stay valid until the next scene
  * change.  with_jacobian = 0 runs the cost-only kernel. */

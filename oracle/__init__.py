@@ -191,6 +191,46 @@ def validate_sweep(scene, poses=None, points=None, sqrd_threshold=16.0, min_dist
     return ok, err
 
 
+def reproject_sweep(scene, frame, point, poses=None, points=None, sqrd_threshold=16.0):
+    """TEST INFRASTRUCTURE.  reproject(sess, f, opt, pt, obs) (struct/VideoSfM.cc:139-155) for a list of
+    (frame, point) pairs, restated on the port's primitives: start at the principal point, repeat
+    getPose(proj) -> w2i until the projection moves by <= 1e-3 px (limit 50, pre-decremented), then
+    ::vision::validate of the projection against itself.  Python loop: small batches only.
+    Returns (proj [n, 2], ok [n] uint8)."""
+    poses, points = _prep(scene, poses, points)
+    poses, points = poses.reshape(-1, 12), points.reshape(-1, 3)
+    lib = port_lib()
+    lib.rsba_oracle_interpolate_rs.argtypes = [_dp, _dp, C.c_int, _ip, _dp, _dp, C.c_int]
+    lib.rsba_oracle_w2i.argtypes = [_dp, _dp, _dp, _dp, C.c_int]
+    cam = np.ascontiguousarray(scene.cam, dtype=np.float64)
+    scan = np.ascontiguousarray(scene.scanlines, dtype=np.int32)
+    n = len(frame)
+    out, ok = np.zeros((n, 2)), np.zeros(n, dtype=np.uint8)
+    pose = np.zeros(6)
+    for i in range(n):
+        p0 = np.ascontiguousarray(poses[int(frame[i]), :6])
+        p1 = np.ascontiguousarray(poses[int(frame[i]), 6:])
+        X = np.ascontiguousarray(points[int(point[i])])
+        proj = np.array([cam[7], cam[8]])
+        limit, good = 50, False
+        while True:
+            limit -= 1
+            if limit < 1:
+                break
+            proj0 = proj.copy()
+            lib.rsba_oracle_interpolate_rs(_ptr(p0, _dp), _ptr(p1, _dp), int(scene.shutter), _ptr(scan, _ip),
+                                           _ptr(proj0, _dp), _ptr(pose, _dp), int(bool(scene.interpolate_rotation)))
+            if not lib.rsba_oracle_w2i(_ptr(cam, _dp), _ptr(pose, _dp), _ptr(X, _dp), _ptr(proj, _dp), 1):
+                break
+            d = proj0 - proj
+            if not (d @ d > 1e-6):
+                good = True
+                break
+        out[i] = proj
+        ok[i] = 1 if (good and 0.0 < sqrd_threshold) else 0
+    return out, ok
+
+
 # --------------------------------------------------------------------------------------------
 # camera-only motion priors (SURVEY 8f rank 1)
 PRIOR_VELOCITY, PRIOR_ACCELERATION = 1, 2

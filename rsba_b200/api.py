@@ -43,7 +43,7 @@ SYMBOLS = [
     "rsba_cuda_add_pose_prior", "rsba_cuda_set_pose_priors", "rsba_cuda_get_pose_priors",
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
-    "rsba_cuda_validate", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
+    "rsba_cuda_validate", "rsba_cuda_reproject", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
     "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
@@ -158,6 +158,7 @@ def load_library():
     lib.rsba_cuda_get_parameters.argtypes = [vp, vp, vp]
     lib.rsba_cuda_evaluate.argtypes = [vp, _dp, vp, vp, vp]
     lib.rsba_cuda_validate.argtypes = [vp, C.c_double, C.c_double, vp, vp]
+    lib.rsba_cuda_reproject.argtypes = [vp, C.c_long, _ip, _ip, C.c_double, vp, vp]
     lib.rsba_cuda_evaluate_device.argtypes = [vp, C.c_int, _dp, C.POINTER(C.c_long)]
     lib.rsba_cuda_device_buffers.argtypes = [vp] + [C.POINTER(vp)] * 5
     lib.rsba_cuda_observation_order.argtypes = [vp, vp]
@@ -354,6 +355,17 @@ class Problem:
         if n > 0:
             self.lib.rsba_cuda_get_pose_priors(self._h, _addr(val), _addr(trial))
         return val, trial
+
+    def reproject(self, frame, point, sqrd_threshold=16.0):
+        """Iterative rolling-shutter re-projection of (frame, point) pairs (struct/VideoSfM.cc:139-155).
+        Returns (proj_xy [n, 2], ok [n])."""
+        frame = np.ascontiguousarray(frame, dtype=np.int32)
+        point = np.ascontiguousarray(point, dtype=np.int32)
+        n = int(frame.size)
+        xy, ok = np.zeros((n, 2)), np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.rsba_cuda_reproject(self._h, C.c_long(n), frame.ctypes.data_as(_ip), point.ctypes.data_as(_ip),
+                                                 C.c_double(sqrd_threshold), _addr(xy), _addr(ok)))
+        return xy, ok
 
     def prior_residuals(self):
         n = self.lib.rsba_cuda_get_prior_residuals(self._h, None)

@@ -94,6 +94,10 @@ void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, 
 void launch_validate(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
                      double sqrd_threshold, double min_distance, unsigned char* ok, double* sqrd_error,
                      cudaStream_t stream);
+// iterative rolling-shutter re-projection of (frame, point) pairs (struct/VideoSfM.cc:139-155); device arrays
+void launch_reproject(const CameraModel& cm, long n, const int* frame, const int* point, const double* poses,
+                      const double* points, double sqrd_threshold, double* proj_xy, unsigned char* ok,
+                      cudaStream_t stream);
 // priors: cost_out[0] = sum rho(|r|^2); store: also residuals and weights for the linearisation
 // invalid_count += priors whose functor returns false (ratio below the functor's bound; free ratio only)
 void launch_prior_eval(const PriorView& pv, const double* poses, double huber, double* cost_out, bool store,

@@ -244,11 +244,58 @@ validate_kernel(const CameraModel cm, const ObsView obs, const double* __restric
   if (sqrd_error) sqrd_error[i] = pr.ok ? err : -1.0;
 }
 
+// Iterative re-projection: reproject(sess, f, opt, pt, obs) (struct/VideoSfM.cc:139-155).  The scan line --
+// hence the interpolated pose -- of a rolling-shutter projection is unknown, so the reference starts at the
+// principal point and repeats  pose = getPose(proj); proj = w2i(cam, pose, pt)  until the projection moves by
+// less than 1e-3 px (squared 1e-6), at most 49 times (limit = 50, pre-decremented); fails when w2i fails
+// (z < 1e-8) or the limit is hit; the final ::vision::validate compares the projection with itself, i.e.
+// passes iff sqrdThreshold > 0.  One thread per (frame, point) pair.
+__global__ void __launch_bounds__(kK1Threads)
+reproject_kernel(const CameraModel cm, long n, const int* __restrict__ frame, const int* __restrict__ point,
+                 const double* __restrict__ poses, const double* __restrict__ points, double sqrd_threshold,
+                 double2* __restrict__ proj_xy, unsigned char* __restrict__ ok) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* gp = poses + (long)frame[i] * kFrameParams;
+  const double* pp = points + 3L * point[i];
+  double pose[kFrameParams];
+#pragma unroll
+  for (int k = 0; k < kFrameParams; ++k) pose[k] = __ldg(gp + k);
+  const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
+  CameraModel plain = cm;
+  plain.huber = 0.0;
+  if (cm.cam_offset >= 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) plain.cam[k] = __ldg(poses + cm.cam_offset + k);
+  }
+  double px = plain.cam[7], py = plain.cam[8];
+  bool good = false;
+  for (int limit = 49; limit >= 1; --limit) {
+    // residual of the current guess against itself as "observation": r = w2i(pose(guess)) - guess
+    const Proj pr = reproject<false, true>(plain, px, py, pose, X0, X1, X2, nullptr);
+    if (!pr.ok) break;
+    px += pr.r0;
+    py += pr.r1;
+    if (!(pr.r0 * pr.r0 + pr.r1 * pr.r1 > 1e-6)) { good = true; break; }
+  }
+  proj_xy[i] = make_double2(px, py);
+  ok[i] = (good && 0.0 < sqrd_threshold) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(1024)
 reduce_partials_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
   __shared__ double s[32];
   double t = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) t += partials[i];
+  // eight loads in flight per thread (a rolled loop paid one L2 round trip per partial: ~20 us per call)
+  int i = threadIdx.x;
+  for (; i + 7 * (int)blockDim.x < n; i += 8 * blockDim.x) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = partials[i + u * blockDim.x];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t += v[u];
+  }
+  for (; i < n; i += blockDim.x) t += partials[i];
   t = warp_sum(t);
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
   __syncthreads();
@@ -295,6 +342,14 @@ void launch_validate(const CameraModel& cm, const ObsView& obs, const double* po
   if (obs.n <= 0) return;
   validate_kernel<<<k1_num_partials(obs.n), kK1Threads, 0, stream>>>(cm, obs, poses, points, sqrd_threshold,
                                                                       min_distance, ok, sqrd_error);
+}
+
+void launch_reproject(const CameraModel& cm, long n, const int* frame, const int* point, const double* poses,
+                      const double* points, double sqrd_threshold, double* proj_xy, unsigned char* ok,
+                      cudaStream_t stream) {
+  if (n <= 0) return;
+  reproject_kernel<<<k1_num_partials(n), kK1Threads, 0, stream>>>(cm, n, frame, point, poses, points, sqrd_threshold,
+                                                                 reinterpret_cast<double2*>(proj_xy), ok);
 }
 
 void launch_reduce_partials(const double* partials, int n, double* out, cudaStream_t stream) {

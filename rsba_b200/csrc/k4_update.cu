@@ -47,6 +47,7 @@ frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* _
                   double* __restrict__ scratch, int bounded, double lower_bound) {
   __shared__ double sh[32];
   double gd = 0.0, dd = 0.0, nn = 0.0;
+#pragma unroll 4   // single CTA, latency-bound: keep several iterations' loads in flight
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const double sc = ne.scale_c[t];
     // y lives in the (tile-permuted) order of the reduced system
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(kWideThreads)
 step_final_kernel(const double* __restrict__ scratch, int n_blocks, double* __restrict__ scalars) {
   __shared__ double sh[32];
   double a = 0.0, b = 0.0, c = 0.0;
+#pragma unroll 8
   for (int k = threadIdx.x; k < n_blocks; k += blockDim.x) {
     a += scratch[3 + 3L * k];
     b += scratch[4 + 3L * k];
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(kWideThreads)
 camera_norms_kernel(NormalEq ne, int n_frames, const double* __restrict__ poses, double* __restrict__ scalars) {
   __shared__ double sh[32];
   double xx = 0.0, gm = 0.0;
+#pragma unroll 4
   for (int t = threadIdx.x; t < 12 * n_frames; t += blockDim.x) {
     const int f = t / 12, k = t % 12;
     const unsigned m = ne.pose_mask[f];

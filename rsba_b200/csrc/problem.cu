@@ -1009,6 +1009,30 @@ int rsba_cuda_validate(rsba_problem* h, double sqrd_threshold, double min_distan
   return RSBA_OK;
 }
 
+int rsba_cuda_reproject(rsba_problem* h, long n, const int* frame, const int* point, double sqrd_threshold,
+                        double* proj_xy, unsigned char* ok) {
+  int rc = prepare(h);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!frame || !point || !proj_xy || !ok))) return fail(RSBA_ERR_INVALID_ARGUMENT, "bad reproject arguments");
+  for (long i = 0; i < n; ++i)
+    if (frame[i] < 0 || frame[i] >= h->n_frames || point[i] < 0 || point[i] >= h->n_points)
+      return fail(RSBA_ERR_INVALID_ARGUMENT, "reproject: frame / point index out of range");
+  if (n == 0) return RSBA_OK;
+  DeviceBuffer<int> d_f, d_p;
+  DeviceBuffer<double> d_xy;
+  DeviceBuffer<unsigned char> d_ok;
+  RSBA_CUDA_TRY(d_f.resize(n)); RSBA_CUDA_TRY(d_p.resize(n)); RSBA_CUDA_TRY(d_xy.resize(2 * n)); RSBA_CUDA_TRY(d_ok.resize(n));
+  RSBA_CUDA_TRY(cudaMemcpyAsync(d_f.ptr, frame, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  RSBA_CUDA_TRY(cudaMemcpyAsync(d_p.ptr, point, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  launch_reproject(h->cm, n, d_f.ptr, d_p.ptr, h->d_poses.ptr, h->d_points.ptr, sqrd_threshold, d_xy.ptr, d_ok.ptr, h->stream);
+  h->launches += 1;
+  RSBA_CUDA_TRY(cudaGetLastError());
+  RSBA_CUDA_TRY(cudaMemcpyAsync(proj_xy, d_xy.ptr, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  RSBA_CUDA_TRY(cudaMemcpyAsync(ok, d_ok.ptr, n, cudaMemcpyDeviceToHost, h->stream));
+  RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return RSBA_OK;
+}
+
 int rsba_cuda_device_buffers(rsba_problem* h, void** residuals, void** jacobian, void** valid,
                              void** poses, void** points) {
   if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");

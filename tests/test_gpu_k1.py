@@ -196,6 +196,33 @@ def test_validate_sweep_matches_reference_predicate(api, oracle_built, shutter):
     assert ok2.all() and err2.max() < 16.0
 
 
+@pytest.mark.parametrize("shutter", [1, 2, 0])
+def test_iterative_reprojection_matches_reference_loop(api, oracle_built, shutter):
+    """reproject() (struct/VideoSfM.cc:139-155): fixed point on the scan line from the principal point, limit
+    and failure rules of the reference, for every (frame, point) pair of the scene plus pairs the frame never
+    observed (some of which lie behind the camera)."""
+    sc = edge_scene(shutter, True)
+    rng = np.random.default_rng(11)
+    frame = np.concatenate([sc.obs_frame, rng.integers(0, sc.num_frames, 200)]).astype(np.int32)
+    point = np.concatenate([sc.obs_point, rng.integers(0, sc.num_points, 200)]).astype(np.int32)
+    want_xy, want_ok = oracle_built.reproject_sweep(sc, frame, point)
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        xy, ok = pb.reproject(frame, point)
+        _, ok0 = pb.reproject(frame, point, sqrd_threshold=0.0)
+    assert np.array_equal(ok, want_ok) and not ok0.any()
+    good = want_ok == 1
+    assert good.sum() > 100
+    assert (np.abs(xy[good] - want_xy[good]) <= 1e-9 * np.maximum(1280.0, np.abs(want_xy[good]))).all()
+    # at the true parameters a re-projection lands on the (noisy, sigma = 0.5 px) observation it came from
+    sc2 = small_scene()
+    with api.Problem(0) as pb:
+        pb.load_scene(sc2, poses=sc2.poses_true, points=sc2.points_true)
+        xy2, ok2 = pb.reproject(sc2.obs_frame, sc2.obs_point)
+    d = np.linalg.norm(xy2 - sc2.obs_xy, axis=1)
+    assert ok2.all() and np.median(d) < 1.0 and d.max() < 4.0
+
+
 @pytest.mark.parametrize("shutter,interp", [(1, True), (2, False), (0, True)])
 def test_k1_uncalibrated_intrinsics_jacobian(api, oracle_built, shutter, interp):
     """<2; 9, 6, 6, 3> (RsBundleAdjustment::CreateWithCam, VideoSfmBaRs.h:38-49,68-80): residual, pose/point
