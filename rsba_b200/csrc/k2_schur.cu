@@ -146,7 +146,9 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
 
   const int4 item = items[blockIdx.x];
   const int beg = item.y, nchunks = item.z / kChunkPts;
-  const bool diag = item.w != 0;
+  const bool diag = (item.w & 1) != 0;
+  // off-diagonal items: which 2-frame halves of the column (A) / row (B) side are populated for EVERY entry
+  const unsigned half_a = ((unsigned)item.w >> 4) & 3u, half_b = ((unsigned)item.w >> 8) & 3u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -226,7 +228,26 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
           *reinterpret_cast<double2*>(out + (m0 + 8 * mi + fr) * kSub + n0 + 8 * ni + 2 * fc) =
               make_double2(acc[mi][ni][0], acc[mi][ni][1]);
   };
-  if (!diag) run(std::integral_constant<unsigned, kAll>{}, 3 * (warp >> 1), 3 * (warp & 1));
+  // A warp whose 24 x 24 patch is structurally zero for this item (a track that starts or ends inside the
+  // sub-tile leaves a 2-frame half empty) only keeps the chunk barriers -- and, for warp 0, the TMA refills --
+  // going and writes zeros: its DMMA slots go to the other CTAs of the SM.
+  auto idle = [&](int r0, int c0) {
+    for (int c = 0; c < nchunks; ++c) {
+      asm volatile("bar.sync 0;" ::: "memory");
+      if (warp == 0 && c + kStages < nchunks) issue(c + kStages);
+    }
+    const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
+    for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 3; ++ni)
+        *reinterpret_cast<double2*>(out + (8 * r0 + 8 * mi + fr) * kSub + 8 * c0 + 8 * ni + 2 * fc) = make_double2(0.0, 0.0);
+  };
+  if (!diag) {
+    const bool live = ((half_b >> (warp >> 1)) & 1u) && ((half_a >> (warp & 1)) & 1u);
+    if (live) run(std::integral_constant<unsigned, kAll>{}, 3 * (warp >> 1), 3 * (warp & 1));
+    else idle(3 * (warp >> 1), 3 * (warp & 1));
+  }
   else if (warp < 2) run(std::integral_constant<unsigned, kLower>{}, 3 * warp, 3 * warp);
   else if (warp == 2) run(std::integral_constant<unsigned, kRows34>{}, 3, 0);
   else run(std::integral_constant<unsigned, kRows45>{}, 3, 0);

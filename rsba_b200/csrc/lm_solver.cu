@@ -233,30 +233,62 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     return dense_keys ? key_pair[key] : (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
   };
   lap("count pairs");
-  // work items: <= kSchurSegPoints entries each; only the last item of a pair is padded (to a multiple of 8)
+  // Which 2-frame halves of an incidence's 4 frame slots are populated (bit 0: slots 0-1, bit 1: slots 2-3).
+  // A track that starts or ends inside a sub-tile leaves a half empty; the entries of an off-diagonal pair are
+  // grouped by the (column side, row side) half masks so that the SYRK skips the 24 x 24 patches that are
+  // structurally zero for a whole work item (k2_schur.cu).
+  std::vector<unsigned char> inc_half(std::max(n_inc, 1), 0);
+  for (int i = 0; i < n_inc; ++i) {
+    unsigned m = 0;
+    for (int fs = 0; fs < kSubFrames; ++fs)
+      if (slot_cnt[(size_t)i * kSubFrames + fs]) m |= 1u << (fs / 2);
+    inc_half[i] = (unsigned char)m;
+  }
+  if (free_cam)   // the pseudo-frame rows of a point's panel are written by phi_cam, not through a slot
+    for (int p = 0; p < P; ++p)
+      if (cam_inc[p] >= 0) inc_half[cam_inc[p]] |= (unsigned char)(1u << (cam_slot / 2));
+  constexpr int kClasses = 9;   // (mask_a - 1) * 3 + (mask_b - 1); diagonal pairs use class 0 only
+  auto class_of = [&](int x, int y) -> int {
+    if (x == y) return 0;
+    const int ma = inc_half[x] ? inc_half[x] : 3, mb = inc_half[y] ? inc_half[y] : 3;
+    return (ma - 1) * 3 + (mb - 1);
+  };
+  // work items: <= kSchurSegPoints entries of one (pair, class) each, padded to a multiple of 8
   const int n_pairs_h = (int)pair_a.size();
+  std::vector<long> class_cnt((size_t)n_pairs_h * kClasses + 1, 0);
+  for (int p = 0; p < P; ++p)
+    for_each_pair_of_point(p, [&](long key, int x, int y) { class_cnt[(size_t)pair_of_key(key) * kClasses + class_of(x, y)]++; });
   std::vector<int> pair_item_ptr(n_pairs_h + 1, 0);
-  std::vector<long> pair_base(n_pairs_h + 1, 0);
+  std::vector<long> class_base((size_t)n_pairs_h * kClasses + 1, 0);
   std::vector<int4> items;
+  long pos = 0;
   for (int q = 0; q < n_pairs_h; ++q) {
     pair_item_ptr[q] = (int)items.size();
-    long left = pair_cnt[q], pos = pair_base[q];
-    while (left > 0) {
-      const int take = (int)std::min<long>(left, kSchurSegPoints);
-      const int padded = (take + 7) / 8 * 8;
-      if (pos + padded > 2147483647L) return fail(RSBA_ERR_INVALID_ARGUMENT, "Schur entry list exceeds 2^31");
-      items.push_back(make_int4(q, (int)pos, padded, pair_a[q] == pair_b[q] ? 1 : 0));
-      pos += padded;
-      left -= take;
+    const bool dg = pair_a[q] == pair_b[q];
+    for (int cl = 0; cl < kClasses; ++cl) {
+      class_base[(size_t)q * kClasses + cl] = pos;
+      long left = class_cnt[(size_t)q * kClasses + cl];
+      const int ma = cl / 3 + 1, mb = cl % 3 + 1;
+      while (left > 0) {
+        const int take = (int)std::min<long>(left, kSchurSegPoints);
+        const int padded = (take + 7) / 8 * 8;
+        if (pos + padded > 2147483647L) return fail(RSBA_ERR_INVALID_ARGUMENT, "Schur entry list exceeds 2^31");
+        // w: bit 0 = diagonal pair; bits 4-5 / 8-9 = populated halves of the column (A) / row (B) side
+        items.push_back(make_int4(q, (int)pos, padded, dg ? 1 : ((ma << 4) | (mb << 8))));
+        pos += padded;
+        left -= take;
+      }
     }
-    pair_base[q + 1] = pos;
   }
   pair_item_ptr[n_pairs_h] = (int)items.size();
-  std::vector<int2> entries((size_t)std::max<long>(pair_base[n_pairs_h], 1), make_int2(n_inc, n_inc));   // zero panel
+  std::vector<int2> entries((size_t)std::max<long>(pos, 1), make_int2(n_inc, n_inc));   // zero panel
   {
-    std::vector<long> cur(pair_base.begin(), pair_base.end() - 1);
+    // (kSchurSegPoints is a multiple of 8: only the last segment of a class is padded, so a class is contiguous)
+    std::vector<long> cur(class_base.begin(), class_base.end() - 1);
     for (int p = 0; p < P; ++p)
-      for_each_pair_of_point(p, [&](long key, int x, int y) { entries[cur[pair_of_key(key)]++] = make_int2(y, x); });   // (row side B, column side A)
+      for_each_pair_of_point(p, [&](long key, int x, int y) {
+        entries[cur[(size_t)pair_of_key(key) * kClasses + class_of(x, y)]++] = make_int2(y, x);   // (row side B, column side A)
+      });
   }
   if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
   const int n_items = (int)pair_item_ptr.back();
