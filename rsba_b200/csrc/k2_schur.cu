@@ -153,28 +153,53 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);              // "full": the stage's TMA bytes have landed
+      mbar_init(smem_u32(&bars[kStages + s]), 4);    // "empty": all four warps are done reading the stage
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // producer: warp 0; lane q < 8 fetches the row-side panel of point q, lane 8+q the column side
+  // producer: warp 0; lane q < 8 fetches the row-side panel of point q, lane 8+q the column side.  The entry
+  // (panel indices) of the chunk after the one being issued is already in a register, so the refill does not
+  // wait on a global load.
+  int2 e_next = make_int2(0, 0);
+  auto load_entry = [&](int c) {
+    if (lane < (diag ? 8 : 16) && c < nchunks) e_next = entries[beg + c * kChunkPts + (lane & 7)];
+  };
   auto issue = [&](int c) {
     const int s = c % kStages;
     const unsigned bar = smem_u32(&bars[s]);
     if (lane == 0) mbar_expect_tx(bar, (diag ? 1u : 2u) * kChunkPts * kPanelBytes);
     __syncwarp();
+    const int2 e = e_next;
+    load_entry(c + 1);
     if (lane < (diag ? 8 : 16)) {
       const int q = lane & 7, side = lane >> 3;
-      const int2 e = entries[beg + c * kChunkPts + q];
       const int inc = side ? e.y : e.x;
       double* dst = stage_base + (size_t)s * kStageDoubles + side * kOperandDoubles + q * kPanelDoubles;
       tma_load_1d(smem_u32(dst), Phi + (long)inc * kPanelDoubles, kPanelBytes, bar);
     }
   };
   if (warp == 0) {
+    load_entry(0);
     for (int c = 0; c < kStages && c < nchunks; ++c) issue(c);
   }
+  // The warps are NOT kept in lockstep: a warp that has read stage s arrives on the stage's "empty" barrier
+  // and moves on; warp 0 refills the stage of chunk c - 1 when it reaches chunk c, by which time the others
+  // have normally passed it.  (A CTA-wide barrier per 8-point chunk was 30 % of this kernel's stall samples.)
+  auto refill = [&](int c) {          // warp 0, at the top of chunk c
+    const int prev = c - 1;
+    if (prev >= 0 && prev + kStages < nchunks) {
+      mbar_wait(smem_u32(&bars[kStages + prev % kStages]), (unsigned)((prev / kStages) & 1));
+      issue(prev + kStages);
+    }
+  };
+  auto release = [&](int s) {         // every warp, after its last read of stage s
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[kStages + s])) : "memory");
+  };
 
   // The 48 x 48 block is a 6 x 6 grid of 8 x 8 DMMA tiles.  Off-diagonal pairs: warp w owns the 3 x 3
   // tiles at (3 (w>>1), 3 (w&1)).  Diagonal pairs (a == b) are symmetric and only their lower tiles are
@@ -196,6 +221,7 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
       for (int ni = 0; ni < 3; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % kStages;
+      if (warp == 0) refill(c);
       mbar_wait(smem_u32(&bars[s]), (unsigned)((c / kStages) & 1));
       const double* R = stage_base + (size_t)s * kStageDoubles;
       const double* Cc = diag ? R : R + kOperandDoubles;
@@ -215,10 +241,7 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
           for (int ni = 0; ni < 3; ++ni)
             if ((MASK >> (3 * mi + ni)) & 1u) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
-      // every warp is done with stage s (the warps run different instantiations of this loop, hence a
-      // PTX barrier, which is identified by its number and not by the call site)
-      asm volatile("bar.sync 0;" ::: "memory");
-      if (warp == 0 && c + kStages < nchunks) issue(c + kStages);
+      release(s);
     }
 #pragma unroll
     for (int mi = 0; mi < 3; ++mi)
@@ -229,12 +252,14 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
               make_double2(acc[mi][ni][0], acc[mi][ni][1]);
   };
   // A warp whose 24 x 24 patch is structurally zero for this item (a track that starts or ends inside the
-  // sub-tile leaves a 2-frame half empty) only keeps the chunk barriers -- and, for warp 0, the TMA refills --
+  // sub-tile leaves a 2-frame half empty) only keeps the pipeline's barriers -- and, for warp 0, the TMA refills --
   // going and writes zeros: its DMMA slots go to the other CTAs of the SM.
   auto idle = [&](int r0, int c0) {
-    for (int c = 0; c < nchunks; ++c) {
-      asm volatile("bar.sync 0;" ::: "memory");
-      if (warp == 0 && c + kStages < nchunks) issue(c + kStages);
+    for (int c = 0; c < nchunks; ++c) {      // paced by the TMA like everyone else (one arrival per phase)
+      const int s = c % kStages;
+      if (warp == 0) refill(c);
+      mbar_wait(smem_u32(&bars[s]), (unsigned)((c / kStages) & 1));
+      release(s);
     }
     const int fr = lane >> 2, fc = lane & 3;
 #pragma unroll
