@@ -406,10 +406,11 @@ def run_ours(args):
     n_local = int(summ.num_residual_blocks)     # this rank's share of the observations (== n_total on one GPU)
     share = n_local / n_total
     roof_k1 = {"bound": "hbm", "kernel": "k1_kernel<true> (residual + Jacobian)", "achieved": n_local * bpo / (k1 * 1e-3) / 1e9,
-               "peak": hbm_peak, "unit": "GB/s", "traffic": 1.364e9, "peak_source": hbm_src,
+               "peak": hbm_peak, "unit": "GB/s", "traffic": 1.370e9, "peak_source": hbm_src,
                "algorithmic_bytes": n_local * bpo, "bytes_per_obs": bpo, "kernel_ms": k1,
                "k1_only_M_evals_per_s": n_local / (k1 * 1e-3) / 1e6, "observations_on_this_rank": n_local,
-               "traffic_source": "profiles/r01l_k1_k2_full.txt (ncu --set full, dram read+write per launch, C3 on one GPU)"}
+               "traffic_source": "profiles/r01n_k1_k2_full.txt (ncu --set full, dram read+write per launch, C3 on one GPU)",
+               "write_stream_note": "K1 is a write stream (1.23 GB written, 0.14 GB read); a pure write stream measures 7.5 TB/s on this pool, the read+write copy 6.66 TB/s (profiles/r01m_hbm_write_peak.txt)"}
     roof_k1["frac"] = roof_k1["achieved"] / hbm_peak
     if world > 1 or args.config != "C3":
         roof_k1["traffic"] = None
@@ -417,10 +418,10 @@ def run_ours(args):
     fp64_src = "tools/fp64_peak.cu measured on this pool (profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 figure"
     roof_syrk = {"bound": "tensor", "kernel": "schur_syrk_kernel (Schur complement, FP64 mma.sync m8n8k4)",
                  "achieved": fl / (kern["schur_syrk"] * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                 "traffic": 3.331e9 if (world == 1 and args.config == "C3") else None,
-                 "traffic_source": "profiles/r01l_k1_k2_full.txt (dram read+write of one launch, C3 on one GPU; the panels are 1.8 GB)",
+                 "traffic": 3.358e9 if (world == 1 and args.config == "C3") else None,
+                 "traffic_source": "profiles/r01n_k1_k2_full.txt (dram read+write of one launch, C3 on one GPU; the panels are 1.8 GB)",
                  "peak_source": fp64_src, "algorithmic_flops": fl, "kernel_ms": kern["schur_syrk"],
-                 "executed_flops_note": "8.4e10 executed at C3 (zero rows of partially seen sub-tiles, full diagonal blocks)"}
+                 "executed_flops_note": "6.3e10 executed at C3 (zero rows of partially seen 2-frame halves, 21 of 36 tiles on diagonal pairs); the kernel also moves 14.5 GB of panels L2 -> shared memory per launch (6.5 TB/s), its second ceiling (profiles/r01_notes.md)"}
     roof_syrk["frac"] = roof_syrk["achieved"] / FP64_PEAK_TFLOPS
     cf = band_cholesky_flops(scene)
     roof_chol = {"bound": "tensor", "kernel": "tile Cholesky (potrf_inv + tile_gemm kernels, all levels)",
