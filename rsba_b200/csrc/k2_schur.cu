@@ -308,8 +308,9 @@ schur_reduce_kernel(SchurStructure st, NormalEq ne, PriorView pv, int cam_frame,
     } else if (fc == cam_frame || fr == cam_frame) {
       // uncalibrated variant: coupling of a real frame with the intrinsics pseudo-frame
       const int rp = r % kFrameParams, cp = c % kFrameParams;
-      if (fr == cam_frame) val += ne.Bcam[(long)fc * 144 + cp * 12 + rp];     // rows = intrinsics, cols = frame
-      else                 val += ne.Bcam[(long)fr * 144 + rp * 12 + cp];
+      // (the pseudo-frame's sub-tile can hold padding slots behind it: no frame, no coupling)
+      if (fr == cam_frame) { if (fc < cam_frame) val += ne.Bcam[(long)fc * 144 + cp * 12 + rp]; }   // rows = intrinsics, cols = frame
+      else if (fr < cam_frame) val += ne.Bcam[(long)fr * 144 + rp * 12 + cp];
     } else if (pv.n > 0 && (r % 6) == (c % 6) && (long)fr * kFrameParams < st.n_cam_params &&
                (long)fc * kFrameParams < st.n_cam_params) {
       // motion-prior coupling between a frame and its previous frame: 6x6 diagonal blocks
