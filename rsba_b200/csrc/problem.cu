@@ -124,13 +124,15 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
   }
   // ... and the pose priors' (GoodPosePrior) in the next one; they go with the point the poses belong to
   const PosePriorView ppv = h->pose_prior_view();
-  if (ppv.n > 0 && h->rank == 0) {
+  if (ppv.n > 0) {
+    // every rank needs the residuals (the prior blocks are back-substituted everywhere, identically); the cost
+    // is counted once, by rank 0
     launch_pose_prior_eval(ppv, poses, poses == h->d_poses.ptr ? ppv.val : ppv.trial, h->d_cost_partials.ptr + np + 1,
                            jac, h->d_invalid.ptr, h->stream);
     h->launches += 1;
-  } else {
-    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np + 1, 0, sizeof(double), h->stream));
   }
+  if (ppv.n == 0 || h->rank != 0)
+    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np + 1, 0, sizeof(double), h->stream));
   launch_reduce_partials(h->d_cost_partials.ptr, np + 2, h->d_scalars.ptr, h->stream);
   stage_end(h, st);
   h->launches += 2;
