@@ -31,6 +31,26 @@ def dump(name, scene, keep=None):
     print(name, "obs", res[sel].shape[0], "invalid", int((valid[sel] == 0).sum()))
 
 
+def dump_prior_functors():
+    """RsConstVeloPrior / RsConstAccelerationPrior (video_bundler_rs_inter.h:55-173) under Jet autodiff: residuals,
+    Jacobian w.r.t. the four pose blocks and the d residual / d interFrameRatio column, on fixed inputs."""
+    rng = np.random.default_rng(20240917)
+    rows = []
+    for kind in (1, 2):
+        for ratio in (1.0, 0.7, 2.5, 1e-3, 0.0):
+            if kind == 2 and ratio == 0.0:
+                continue                       # the acceleration functor divides by the ratio
+            for _ in range(4):
+                fk, fp = rng.normal(0, 0.3, 12), rng.normal(0, 0.3, 12)
+                scale = float(rng.uniform(0.1, 30.0))
+                ok, r, J, col = oracle.motion_prior_eval_ref(kind, scale, ratio, fk, fp)
+                rows.append(dict(kind=kind, ratio=ratio, scale=scale, fk=fk, fp=fp, ok=ok, r=r, J=J, col=col))
+    os.makedirs(os.path.join(HERE, "priors"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "priors", "prior_functors.npz"),
+                        **{k: np.array([row[k] for row in rows]) for k in rows[0]})
+    print("prior_functors", len(rows), "cases")
+
+
 if __name__ == "__main__":
     oracle.build()
     assert oracle.ref_available(), "needs /root/reference to build oracle/_ref"
@@ -39,3 +59,4 @@ if __name__ == "__main__":
     for sh in (0, 1, 2):
         for ir in (0, 1):
             dump(f"edge_s{sh}_r{ir}", edge_scene(shutter=sh, interpolate_rotation=bool(ir)))
+    dump_prior_functors()

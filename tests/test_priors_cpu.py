@@ -53,3 +53,19 @@ def test_ratio_column_matches_reference_functor(oracle_built, kind, ratio):
     ok, _, _, col_ref = oracle_built.motion_prior_eval_ref(1, 2.0, 0.0, fk, fp)
     col = oracle_built.motion_prior_ratio_column(1, 2.0, 0.0, fk, fp)
     assert ok and np.allclose(col, col_ref, rtol=0, atol=1e-13) and not col[6:].any()
+
+
+def test_closed_form_matches_committed_reference_vectors(oracle_built):
+    """The same pin without oracle/_ref: tests/golden/priors/prior_functors.npz holds the reference functors'
+    own outputs (tests/golden/make_golden.py, generated where /root/reference exists)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "priors", "prior_functors.npz"))
+    assert g["kind"].size >= 30
+    for i in range(g["kind"].size):
+        kind, ratio, scale = int(g["kind"][i]), float(g["ratio"][i]), float(g["scale"][i])
+        r, J = oracle_built.motion_prior_eval(kind, scale, ratio, g["fk"][i], g["fp"][i])
+        col = oracle_built.motion_prior_ratio_column(kind, scale, ratio, g["fk"][i], g["fp"][i])
+        assert bool(g["ok"][i])
+        assert np.abs(r - g["r"][i]).max() <= 1e-12 * max(1.0, np.abs(g["r"][i]).max())
+        assert np.abs(J - g["J"][i]).max() <= 1e-12 * np.abs(g["J"][i]).max()
+        assert np.abs(col - g["col"][i]).max() <= 1e-12 * max(1.0, np.abs(g["col"][i]).max())
