@@ -84,7 +84,8 @@ constexpr size_t kPotrfSmem = (size_t)(2 * kTile * kLd + 3 * 32 * kLd + kTile) *
 
 __global__ void __launch_bounds__(256)
 potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int T,
-                 const int* __restrict__ panels, double* __restrict__ Dinv, int* __restrict__ info) {
+                 const int* __restrict__ panels, double* __restrict__ Dinv, int* __restrict__ info,
+                 double* __restrict__ x, const int* __restrict__ lrow_ptr, const double* __restrict__ fwd_partials) {
   const int k = panels[blockIdx.x];
   extern __shared__ __align__(16) double smem[];
   double* A = smem;                      // [96][kLd]  factor (lower)
@@ -249,6 +250,37 @@ potrf_inv_kernel(double* __restrict__ S, const int* __restrict__ tile_slot, int 
     reinterpret_cast<double2*>(g)[e] = make_double2(c <= r ? A[r * kLd + c] : 0.0, c + 1 <= r ? A[r * kLd + c + 1] : 0.0);
     reinterpret_cast<double2*>(di)[e] = make_double2(X[r * kLd + c], X[r * kLd + c + 1]);
   }
+  // ---- forward substitution of this panel, while its inverse is in shared memory:
+  //   z_k = L_kk^-1 (b_k - sum_{j<k} L_kj z_j);  the terms L_kj z_j were left by tile_trsm_kernel at the levels
+  //   of the panels j (all lower than this one), one slot per tile, and are summed in list order
+  double* tvec = rdiag;   // the reciprocal pivots are dead
+  if (tid < kTile) {
+    double sum = 0.0;
+    for (int q = lrow_ptr[k]; q < lrow_ptr[k + 1]; ++q) sum += fwd_partials[(long)q * kTile + tid];
+    tvec[tid] = x[(long)k * kTile + tid] - sum;
+  }
+  __syncthreads();
+  {
+    double zs[12];
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      const int r = warp + 8 * t;
+      double v = 0.0;
+#pragma unroll
+      for (int c = 0; c < kTile; c += 32)
+        if (c + lane <= r) v += X[r * kLd + c + lane] * tvec[c + lane];
+      zs[t] = v;
+    }
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) zs[t] += __shfl_xor_sync(0xffffffffu, zs[t], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < 12; ++t) x[(long)k * kTile + warp + 8 * t] = zs[t];
+    }
+  }
 }
 
 // ---------------------------------------------------------------- tile GEMMs  C (-)= A B^T  on DMMA
@@ -294,11 +326,15 @@ __device__ __forceinline__ void warp_gemm_24x24(const double* As, const double* 
 
 __global__ void __launch_bounds__(128)
 tile_trsm_kernel(double* S, const int* __restrict__ tile_slot, int T, const int2* __restrict__ trsm,
-                 const double* __restrict__ Dinv) {
+                 const double* __restrict__ Dinv, const double* __restrict__ x, const int* __restrict__ fwd_slot,
+                 double* __restrict__ fwd_partials) {
   extern __shared__ __align__(16) double smem[];
+  __shared__ double zs[kTile];             // z_k of the panel (written by this level's potrf_inv launch)
+  __shared__ double red[4][kTrsmRows];
   double* As = smem;                       // [24][kLd]  this CTA's rows of S(i,k)
   double* Bs = smem + kTrsmRows * kLd;     // [96][kLd]  Dinv[k]
   const int2 p = trsm[blockIdx.x];
+  if (threadIdx.x < kTile) zs[threadIdx.x] = x[(long)p.y * kTile + threadIdx.x];
   double* tile = S + (long)tile_slot[p.x * T + p.y] * kTile * kTile + (long)blockIdx.y * kTrsmRows * kTile;
   load_rows(As, tile, kTrsmRows);
   load_rows(Bs, Dinv + (long)p.y * kTile * kTile, kTile);
@@ -314,6 +350,22 @@ tile_trsm_kernel(double* S, const int* __restrict__ tile_slot, int T, const int2
     for (int ni = 0; ni < 3; ++ni)
       *reinterpret_cast<double2*>(tile + (long)(8 * mi + fr) * kTile + n0 + 8 * ni + 2 * fc) =
           make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+  // forward-substitution term of this tile: (L_ik z_k)[rows of this CTA], fixed summation order
+  // (zs was written before the __syncthreads above)
+#pragma unroll
+  for (int mi = 0; mi < 3; ++mi) {
+    double v = 0.0;
+#pragma unroll
+    for (int ni = 0; ni < 3; ++ni)
+      v += acc[mi][ni][0] * zs[n0 + 8 * ni + 2 * fc] + acc[mi][ni][1] * zs[n0 + 8 * ni + 2 * fc + 1];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (fc == 0) red[warp][8 * mi + fr] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kTrsmRows)
+    fwd_partials[(long)fwd_slot[blockIdx.x] * kTile + blockIdx.y * kTrsmRows + threadIdx.x] =
+        (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(128)
@@ -350,35 +402,14 @@ tile_update_kernel(double* S, const int* __restrict__ tile_slot, int T, const in
 }
 
 // ---------------------------------------------------------------- triangular solves, level by level
-// x holds the right-hand side on entry and the solution of (L L^T) x = b on exit.  The tile row /
+// The FORWARD substitution z = L^-1 b rides in the factorisation's own launches (potrf_inv_kernel's epilogue
+// forms z_k while the panel's inverse is in shared memory, tile_trsm_kernel's epilogue leaves L_ik z_k in the
+// tile's slot): the 19 + 12 extra launches of a separate forward sweep were a quarter of the solve time.
+// Below: the backward substitution.  x holds z on entry and the solution of (L L^T) x = b on exit.  The tile row /
 // column of a separator panel can hold dozens of tiles, so the matrix-vector products of one
 // panel are split over `split` CTAs (blockIdx.y) that write partial sums; a finish kernel adds
 // them in a fixed order and applies the inverse of the diagonal factor.  split == 1 fuses both.
 constexpr int kMaxSolveSplit = 16;
-
-__device__ __forceinline__ void apply_dinv_forward(const double* __restrict__ di, const double* tmp,
-                                                   double* __restrict__ xk, int warp, int lane) {
-  // all 36 loads of the inverse are issued before the first use (fully unrolled: independent rows)
-  double s[12];
-#pragma unroll
-  for (int t = 0; t < 12; ++t) {
-    const int r = warp + 8 * t;
-    double v = 0.0;
-#pragma unroll
-    for (int c = 0; c < kTile; c += 32)
-      if (c + lane <= r) v += __ldg(di + r * kTile + c + lane) * tmp[c + lane];
-    s[t] = v;
-  }
-#pragma unroll
-  for (int t = 0; t < 12; ++t) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int t = 0; t < 12; ++t) xk[warp + 8 * t] = s[t];
-  }
-}
 
 __device__ __forceinline__ void apply_dinv_backward(const double* __restrict__ di, const double* tmp,
                                                     double (*part)[kTile + 1], double* __restrict__ xk,
@@ -401,65 +432,6 @@ __device__ __forceinline__ void apply_dinv_backward(const double* __restrict__ d
     for (int g = 0; g < 8; ++g) s += part[g][threadIdx.x];
     xk[threadIdx.x] = s;
   }
-}
-
-// forward:  z_k = Linv_kk (b_k - sum_{j<k} L_kj z_j)      every j sits in a lower level
-__global__ void __launch_bounds__(256)
-solve_forward_kernel(const double* __restrict__ S, TileSchedule ts, const int* __restrict__ panels,
-                     double* __restrict__ x, int split, double* __restrict__ partials) {
-  constexpr long ld = kTile;
-  __shared__ double tmp[kTile];
-  const int k = panels[blockIdx.x];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int T = ts.n_tiles;
-  // warp w owns rows w, w+8, ..., w+88; lane covers columns lane, lane+32, lane+64
-  double acc[12];
-#pragma unroll
-  for (int t = 0; t < 12; ++t) acc[t] = 0.0;
-  for (int q = ts.lrow_ptr[k] + blockIdx.y; q < ts.lrow_ptr[k + 1]; q += split) {
-    const int j = ts.lrow_cols[q];
-    const double* lj = S + (long)ts.tile_slot[k * T + j] * kTile * kTile;
-    const double* xj = x + (long)j * kTile;
-    const double x0 = xj[lane], x1 = xj[lane + 32], x2 = xj[lane + 64];
-#pragma unroll
-    for (int t = 0; t < 12; ++t) {
-      const double* row = lj + (long)(warp + 8 * t) * ld;
-      acc[t] += row[lane] * x0 + row[lane + 32] * x1 + row[lane + 64] * x2;
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < 12; ++t) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
-  }
-  if (split > 1) {
-    double* out = partials + ((long)k * kMaxSolveSplit + blockIdx.y) * kTile;
-    if (lane == 0) {
-#pragma unroll
-      for (int t = 0; t < 12; ++t) out[warp + 8 * t] = acc[t];
-    }
-    return;
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int t = 0; t < 12; ++t) tmp[warp + 8 * t] = x[(long)k * kTile + warp + 8 * t] - acc[t];
-  }
-  __syncthreads();
-  apply_dinv_forward(ts.Dinv + (long)k * kTile * kTile, tmp, x + (long)k * kTile, warp, lane);
-}
-
-__global__ void __launch_bounds__(256)
-solve_forward_finish_kernel(TileSchedule ts, const int* __restrict__ panels, double* __restrict__ x, int split,
-                            const double* __restrict__ partials) {
-  __shared__ double tmp[kTile];
-  const int k = panels[blockIdx.x];
-  if (threadIdx.x < kTile) {
-    double s = 0.0;
-    for (int g = 0; g < split; ++g) s += partials[((long)k * kMaxSolveSplit + g) * kTile + threadIdx.x];
-    tmp[threadIdx.x] = x[(long)k * kTile + threadIdx.x] - s;
-  }
-  __syncthreads();
-  apply_dinv_forward(ts.Dinv + (long)k * kTile * kTile, tmp, x + (long)k * kTile, threadIdx.x >> 5, threadIdx.x & 31);
 }
 
 // backward: y_k = Linv_kk^T (z_k - sum_{i>k} L_ik^T y_i)   every i sits in a higher level
@@ -536,16 +508,18 @@ void k3_prepare() {
   }
 }
 
-int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s) {
+int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, double* x, int* info, cudaStream_t s) {
   k3_prepare();
   int launches = 0;
   for (int l = 0; l < plan.n_levels; ++l) {
     const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
-    potrf_inv_kernel<<<np, 256, kPotrfSmem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.panels + plan.panel_ptr[l], ts.Dinv, info);
+    potrf_inv_kernel<<<np, 256, kPotrfSmem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.panels + plan.panel_ptr[l], ts.Dinv, info,
+                                                 x, ts.lrow_ptr, ts.fwd_partials);
     ++launches;
     const int nt = plan.trsm_ptr[l + 1] - plan.trsm_ptr[l];
     if (nt > 0) {
-      tile_trsm_kernel<<<dim3(nt, 4), 128, kTrsmSmem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.trsm + plan.trsm_ptr[l], ts.Dinv);
+      tile_trsm_kernel<<<dim3(nt, 4), 128, kTrsmSmem, s>>>(S, ts.tile_slot, ts.n_tiles, ts.trsm + plan.trsm_ptr[l], ts.Dinv,
+                                                           x, ts.fwd_slot + plan.trsm_ptr[l], ts.fwd_partials);
       ++launches;
     }
     for (int g = plan.level_group_ptr[l]; g < plan.level_group_ptr[l + 1]; ++g) {
@@ -561,19 +535,7 @@ int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan
 int launch_tile_solve(const double* S, const TileSchedule& ts, const TilePlan& plan, double* x, cudaStream_t s) {
   int launches = 0;
   auto split_of = [](int most) { return most <= 4 ? 1 : std::min(kMaxSolveSplit, (most + 2) / 3); };
-  for (int l = 0; l < plan.n_levels; ++l) {
-    const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
-    int most = 0;
-    for (int q = plan.panel_ptr[l]; q < plan.panel_ptr[l + 1]; ++q)
-      most = std::max(most, plan.lrow_ptr[plan.panels[q] + 1] - plan.lrow_ptr[plan.panels[q]]);
-    const int split = split_of(most);
-    solve_forward_kernel<<<dim3(np, split), 256, 0, s>>>(S, ts, ts.panels + plan.panel_ptr[l], x, split, ts.solve_partials);
-    ++launches;
-    if (split > 1) {
-      solve_forward_finish_kernel<<<np, 256, 0, s>>>(ts, ts.panels + plan.panel_ptr[l], x, split, ts.solve_partials);
-      ++launches;
-    }
-  }
+  // (the forward substitution z = L^-1 b was done inside launch_tile_cholesky)
   for (int l = plan.n_levels - 1; l >= 0; --l) {
     const int np = plan.panel_ptr[l + 1] - plan.panel_ptr[l];
     int most = 0;

@@ -152,15 +152,20 @@ struct TileSchedule {      // device view of the TilePlan (tile_plan.cuh); tile 
   const int* lrow_cols;
   double* Dinv;             // [n_tiles][96*96] inverses of the diagonal factors (scratch)
   double* solve_partials;   // [n_tiles][16][96] split matrix-vector partial sums of the solves
+  // forward substitution folded into the factorisation: tile (i, k) leaves  L_ik z_k  in slot
+  // fwd_slot[its trsm entry] = its index in the lrow lists; panel i sums its slots in list order
+  const int* fwd_slot;      // [n_trsm]
+  double* fwd_partials;     // [n off-diagonal tiles][96]
   long n_real;              // 12 * frames (rows beyond it are identity padding)
 };
 
 void k3_prepare();   // one-off kernel attribute setup (call before capturing the launches in a graph)
 void launch_clear_tiles(double* S, const TileSchedule& ts, cudaStream_t s);
 // return the number of kernel launches issued; info[0] != 0 on a non-positive pivot
-int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, int* info, cudaStream_t s);
+// x (rhs on entry) leaves as z = L^-1 rhs: the forward substitution rides in the factorisation's launches
+int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan, double* x, int* info, cudaStream_t s);
 int launch_tile_solve(const double* S, const TileSchedule& ts, const TilePlan& plan,
-                      double* x /* in: rhs, out: solution */, cudaStream_t s);
+                      double* x /* in: z = L^-1 rhs (from launch_tile_cholesky), out: solution */, cudaStream_t s);
 
 // ---- K4 ---------------------------------------------------------------------------------
 struct StepScalars {  // device doubles, filled by launch_step_update

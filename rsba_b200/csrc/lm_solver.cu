@@ -41,7 +41,8 @@ struct LmState {
   // ---- numeric state (device)
   DeviceBuffer<double> B, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
   // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
-  DeviceBuffer<double> solve_partials;
+  DeviceBuffer<double> solve_partials, fwd_partials;
+  DeviceBuffer<int> fwd_slot;
   DeviceBuffer<double> S, misc_local, Dinv, rhs, y, delta_c, delta_p, trial_poses, trial_points, scalars, scratch;
   // the launch sequences of the factorisation and of the triangular solves are static per scene:
   // captured once into CUDA graphs, replayed every LM iteration (launch gaps matter here -- ~170
@@ -354,6 +355,18 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
   UP(panels, plan.panels); UP(trsm, plan.trsm);
   {
+    // where each off-diagonal tile (i, k) leaves its forward-substitution term: its index in row i's list
+    std::vector<int> fwd_slot(std::max<size_t>(plan.trsm.size(), 1), 0);
+    for (size_t t = 0; t < plan.trsm.size(); ++t) {
+      const int i = plan.trsm[t].x, k = plan.trsm[t].y;
+      int q = plan.lrow_ptr[i];
+      while (q < plan.lrow_ptr[i + 1] && plan.lrow_cols[q] != k) ++q;
+      if (q == plan.lrow_ptr[i + 1]) return fail(RSBA_ERR_STATE, "tile plan: trsm tile missing from the row list");
+      fwd_slot[t] = q;
+    }
+    UP(fwd_slot, fwd_slot);
+  }
+  {
     std::vector<unsigned short> mask(h->pose_mask);
     mask.resize(Fc, 0);
     if (pseudo)   // parameters 0..8 = intrinsics, 9 = interFrameRatio; what is not a parameter is constant
@@ -410,6 +423,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->misc_local.ptr, 0, lm->misc_local.bytes(), s));
   RSBA_CUDA_TRY(lm->Dinv.resize((size_t)std::max(T, 1) * kTile * kTile));
   RSBA_CUDA_TRY(lm->solve_partials.resize((size_t)std::max(T, 1) * 16 * kTile));
+  RSBA_CUDA_TRY(lm->fwd_partials.resize(std::max<size_t>(plan.lrow_cols.size(), 1) * kTile));
   RSBA_CUDA_TRY(lm->rhs.resize(std::max<long>(lm->n_pad, 1))); RSBA_CUDA_TRY(lm->y.resize(std::max<long>(lm->n_pad, 1)));
   RSBA_CUDA_TRY(lm->delta_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->delta_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->trial_poses.resize(Fz * 12)); RSBA_CUDA_TRY(lm->trial_points.resize(Pz * 3));
@@ -433,6 +447,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   ts.n_tiles = T; ts.nz_tiles = lm->nz_tiles.ptr; ts.tile_slot = lm->tile_slot.ptr; ts.n_nz = (int)nz_tiles.size();
   ts.row_ptr = lm->row_ptr.ptr; ts.rows = lm->rows.ptr; ts.upd = lm->upd.ptr; ts.panels = lm->panels.ptr; ts.trsm = lm->trsm.ptr;
   ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.solve_partials = lm->solve_partials.ptr; ts.n_real = 12L * Fc;
+  ts.fwd_slot = lm->fwd_slot.ptr; ts.fwd_partials = lm->fwd_partials.ptr;
 
   long free_params = 0;
   for (int f = 0; f < F; ++f) free_params += 12 - __builtin_popcount(h->pose_mask[f] & 0xFFF);
@@ -566,7 +581,7 @@ void factor_and_solve(rsba_problem* h, LmState* lm) {
   if (!lm->graph_tried) {
     lm->graph_tried = true;
     k3_prepare();   // the kernels' one-off attribute setup stays outside the capture
-    lm->graph_factor = capture_graph(s, [&] { return launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->info.ptr, s); },
+    lm->graph_factor = capture_graph(s, [&] { return launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, lm->info.ptr, s); },
                                      &lm->graph_factor_launches);
     if (lm->graph_factor)
       lm->graph_solve = capture_graph(s, [&] { return launch_tile_solve(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, s); },
@@ -577,7 +592,7 @@ void factor_and_solve(rsba_problem* h, LmState* lm) {
   cudaMemcpyAsync(lm->y.ptr, lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToDevice, s);
   stage_begin(h, kStageFactor);
   if (lm->graph_factor && cudaGraphLaunch(lm->graph_factor, s) == cudaSuccess) h->launches += lm->graph_factor_launches;
-  else h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->info.ptr, s);
+  else h->launches += launch_tile_cholesky(lm->S.ptr, lm->ts, lm->plan, lm->y.ptr, lm->info.ptr, s);
   stage_end(h, kStageFactor);
   stage_begin(h, kStageTriSolve);
   if (lm->graph_solve && cudaGraphLaunch(lm->graph_solve, s) == cudaSuccess) h->launches += lm->graph_solve_launches;
