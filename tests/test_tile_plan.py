@@ -34,8 +34,11 @@ def spd_with_pattern(T, pairs, seed=0):
     return A
 
 
-def run_plan(plan, A, T):
-    """Tile right-looking Cholesky in plan order; returns L in permuted position order plus checks."""
+def run_plan(plan, A, T, rhs=None):
+    """Tile right-looking Cholesky in plan order; returns L in permuted position order plus checks.
+    With ``rhs`` (in position order) also runs the forward substitution the way the device does, inside the
+    factorisation's own launches: the potrf launch forms z_k = L_kk^-1 (b_k - sum of the slots of row k), the trsm
+    launch leaves L_ik z_k in the slot of tile (i, k); returns (L, perm, z)."""
     pos = plan["tile_pos"]
     perm = np.empty(T * B, dtype=int)
     for t in range(T):
@@ -49,14 +52,24 @@ def run_plan(plan, A, T):
             if np.any(M[blk(i, j)] != 0):
                 assert (i, j) in nz
     done = set()
+    z = None if rhs is None else np.array(rhs, dtype=np.float64)
+    slots = {}                                                             # (i, k) -> L_ik z_k
     for l in range(plan["n_levels"]):
         pan = plan["panels"][plan["panel_ptr"][l]:plan["panel_ptr"][l + 1]]
         for k in pan:                                                      # potrf (one launch)
             M[blk(k, k)] = np.linalg.cholesky(M[blk(k, k)])
+            if z is not None:                                              # ... and its forward-substitution epilogue
+                row = sorted(j for (i, j) in nz if i == k and j < k)
+                assert all((k, j) in slots for j in row), "a term of row k is not there yet"
+                t = z[k * B:(k + 1) * B] - sum((slots[(k, j)] for j in row), np.zeros(B))
+                z[k * B:(k + 1) * B] = np.linalg.solve(M[blk(k, k)], t)
         tr = plan["trsm"][plan["trsm_ptr"][l]:plan["trsm_ptr"][l + 1]]
         for i, k in tr:                                                    # trsm (one launch)
             assert k in pan and (i, k) in nz and i > k
             M[blk(i, k)] = np.linalg.solve(M[blk(k, k)], M[blk(i, k)].T).T
+            if z is not None:
+                assert (i, k) not in slots
+                slots[(int(i), int(k))] = M[blk(i, k)] @ z[k * B:(k + 1) * B]
         for g in range(plan["level_group_ptr"][l], plan["level_group_ptr"][l + 1]):
             ups = plan["upd"][plan["group_ptr"][g]:plan["group_ptr"][g + 1]]
             targets = [(i, j) for i, j, k in ups]
@@ -72,6 +85,9 @@ def run_plan(plan, A, T):
         for j in range(i):
             if (i, j) not in nz:
                 L[blk(i, j)] = 0.0
+    if z is not None:
+        assert set(slots) == {(i, j) for (i, j) in nz if i > j}, "every off-diagonal tile leaves exactly one term"
+        return L, perm, z
     return L, perm
 
 
@@ -119,3 +135,21 @@ def test_disconnected_components_are_independent():
     want = np.linalg.cholesky(A[np.ix_(perm, perm)])
     assert np.abs(L - want).max() <= 1e-10 * np.abs(want).max()
     assert plan["n_levels"] <= 15
+
+
+@pytest.mark.parametrize("T,pairs,reorder", [
+    (7, band_pairs(7, 2), True),
+    (40, band_pairs(40, 3), False),
+    (125, band_pairs(125, 3), True),
+    (33, random_pairs(33, 40, 1), True),
+])
+def test_forward_substitution_rides_in_the_factorisation(T, pairs, reorder):
+    """K3 folds z = L^-1 b into the potrf / trsm launches (k3_cholesky.cu): every term L_kj z_j that panel k needs
+    was produced at the level of panel j, which the elimination order puts strictly before panel k's."""
+    pa, pb = np.array([p[0] for p in pairs]), np.array([p[1] for p in pairs])
+    plan = api.plan_reduced_system(T, pa, pb, dense=False, reorder=reorder)
+    A = spd_with_pattern(T, pairs, seed=5)
+    b = np.random.default_rng(9).normal(size=T * B)
+    L, perm, z = run_plan(plan, A, T, rhs=b)
+    want = np.linalg.solve(np.linalg.cholesky(A[np.ix_(perm, perm)]), b)
+    assert np.abs(z - want).max() <= 1e-10 * np.abs(want).max()
