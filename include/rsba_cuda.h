@@ -286,6 +286,28 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
                                   int* panels, int* panel_ptr, int* trsm, int* trsm_ptr, int* upd,
                                   long* group_ptr, int* level_group_ptr);
 
+/* Host-only introspection of the WHOLE one-off structure analysis that rsba_cuda_solve runs before its first
+ * linearisation -- what Ceres does in Program reordering + SchurEliminator block-structure detection + CHOLMOD's
+ * analyse phase (third-party; reached through ceres::Solve, CeresHandler.h:403,419).  Needs no device: the CPU
+ * tests execute the returned work lists in numpy against a direct Schur complement.
+ *   obs_frame / obs_point [n_obs]  observations sorted by frame (the order rsba_cuda_observation_order reports)
+ *   const_point [n_points] or NULL; free_intrinsics / free_ratio: the pseudo-frame behind the real frames
+ *   prior_frame / prior_prev [n_priors]: the (frame, previous frame) couplings of the motion priors
+ *   dense / reorder: as rsba_solve_options.dense_cholesky / reorder_tiles; sparse_keys: force the sorted-key path
+ * The result is an opaque object; rsba_cuda_structure_array returns the element count of the named array (or -1)
+ * and, through data / elem_bytes, a pointer into the object (valid until rsba_cuda_structure_free).  Names:
+ *   pt_ptr pt_obs chunk_frame chunk_beg chunk_cnt frame_chunk_ptr inc_point inc_tile slot_beg slot_cnt pt_inc_ptr
+ *   cam_inc inc_half obs_phi_off dup_inc pair_a pair_b pair_item_ptr items(int4) entries(int2) fwd_slot
+ *   plan.tile_pos plan.pos_tile plan.nz_tiles(int2) plan.tile_slot plan.panels plan.panel_ptr plan.trsm(int2)
+ *   plan.trsm_ptr plan.upd(int4) plan.lrow_ptr plan.lrow_cols; the scalars T, n_inc, n_items come back as the count. */
+typedef struct rsba_structure rsba_structure;
+int rsba_cuda_analyze_structure(long n_obs, const int* obs_frame, const int* obs_point, int n_frames, int n_points,
+                                const unsigned char* const_point, int free_intrinsics, int free_ratio, int n_priors,
+                                const int* prior_frame, const int* prior_prev, int dense, int reorder,
+                                int sparse_keys, rsba_structure** out);
+long rsba_cuda_structure_array(const rsba_structure* s, const char* name, const void** data, int* elem_bytes);
+void rsba_cuda_structure_free(rsba_structure* s);
+
 /* ------------------------------------------------------------------ batched RS-PnP */
 /* Replaces: the inner ceres::Solve of vision::solveRsPnP (solveRSpnp.cpp:100-192: RsBA<float> residual
  * blocks <2; 6, 6> on the two control poses of one frame, 3-D points fixed, w2i without the

@@ -44,7 +44,8 @@ SYMBOLS = [
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_reproject", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
-    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
+    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_analyze_structure", "rsba_cuda_structure_array",
+    "rsba_cuda_structure_free", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
 
@@ -166,6 +167,12 @@ def load_library():
     lib.rsba_cuda_solve.argtypes = [vp, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
     lib.rsba_cuda_linearize_and_step.argtypes = [vp, C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp, _dp]
     lib.rsba_cuda_plan_reduced_system.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp] + [vp] * 9
+    lib.rsba_cuda_analyze_structure.argtypes = [C.c_long, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp,
+                                                C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.rsba_cuda_structure_array.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    lib.rsba_cuda_structure_array.restype = C.c_long
+    lib.rsba_cuda_structure_free.argtypes = [vp]
+    lib.rsba_cuda_structure_free.restype = None
     lib.rsba_cuda_pnp_batch.argtypes = [vp, _dp, C.c_int, _ip, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp,
                                         C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp]
     lib.rsba_cuda_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
@@ -567,6 +574,61 @@ def plan_reduced_system(n_tiles, pair_a, pair_b, dense=False, reorder=True):
     call(*out.values())
     out.update(n_levels=L, flops=float(counts[5]))
     return out
+
+
+_STRUCTURE_ARRAYS = {
+    "pt_ptr": (np.int32, 1), "pt_obs": (np.int32, 1), "chunk_frame": (np.int32, 1), "chunk_beg": (np.int32, 1),
+    "chunk_cnt": (np.int32, 1), "frame_chunk_ptr": (np.int32, 1), "inc_point": (np.int32, 1), "inc_tile": (np.int32, 1),
+    "slot_beg": (np.int32, 4), "slot_cnt": (np.uint8, 4), "pt_inc_ptr": (np.int32, 1), "cam_inc": (np.int32, 1),
+    "inc_half": (np.uint8, 1), "obs_phi_off": (np.int32, 1), "dup_inc": (np.int32, 1), "pair_a": (np.int32, 1),
+    "pair_b": (np.int32, 1), "pair_item_ptr": (np.int32, 1), "items": (np.int32, 4), "entries": (np.int32, 2),
+    "fwd_slot": (np.int32, 1), "plan.tile_pos": (np.int32, 1), "plan.pos_tile": (np.int32, 1),
+    "plan.nz_tiles": (np.int32, 2), "plan.tile_slot": (np.int32, 1), "plan.panels": (np.int32, 1),
+    "plan.panel_ptr": (np.int32, 1), "plan.trsm": (np.int32, 2), "plan.trsm_ptr": (np.int32, 1),
+    "plan.upd": (np.int32, 4), "plan.lrow_ptr": (np.int32, 1), "plan.lrow_cols": (np.int32, 1),
+}
+
+
+def analyze_structure(obs_frame, obs_point, n_frames, n_points, const_point=None, free_intrinsics=False,
+                      free_ratio=False, prior_frame=(), prior_prev=(), dense=False, reorder=True, sparse_keys=False):
+    """Host-only: the one-off structure analysis of rsba_cuda_solve (point CSR, frame chunks, Schur incidences,
+    sub-tile pairs, work items and entry lists, tile plan) as a dict of numpy arrays.  No GPU needed.
+    Observations must be sorted by frame."""
+    lib = load_library()
+    fr = np.ascontiguousarray(obs_frame, dtype=np.int32)
+    pt = np.ascontiguousarray(obs_point, dtype=np.int32)
+    cp = None if const_point is None else np.ascontiguousarray(const_point, dtype=np.uint8)
+    pf = np.ascontiguousarray(prior_frame, dtype=np.int32)
+    pp = np.ascontiguousarray(prior_prev, dtype=np.int32)
+    handle = C.c_void_p()
+    rc = lib.rsba_cuda_analyze_structure(fr.size, _addr(fr), _addr(pt), int(n_frames), int(n_points), _addr(cp),
+                                         int(free_intrinsics), int(free_ratio), int(pf.size), _addr(pf), _addr(pp),
+                                         int(dense), int(reorder), int(sparse_keys), C.byref(handle))
+    if rc != RSBA_OK:
+        raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
+    try:
+        out = {}
+        for name, (dtype, width) in _STRUCTURE_ARRAYS.items():
+            data, eb = C.c_void_p(), C.c_int()
+            n = lib.rsba_cuda_structure_array(handle, name.encode(), C.byref(data), C.byref(eb))
+            if n < 0:
+                raise RsbaError(ERR_INVALID_ARGUMENT, name)
+            itemsize = np.dtype(dtype).itemsize
+            per = eb.value // itemsize if eb.value else 1
+            if n == 0 or not data.value:
+                arr = np.zeros((0, max(per, width)) if max(per, width) > 1 else 0, dtype)
+            else:
+                arr = np.ctypeslib.as_array(C.cast(data, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), (n * per,)).copy()
+                if per > 1:
+                    arr = arr.reshape(n, per)
+                elif width > 1:
+                    arr = arr.reshape(-1, width)
+            out[name] = arr
+        for name in ("T", "n_inc", "n_items"):
+            out[name] = int(lib.rsba_cuda_structure_array(handle, name.encode(), None, None))
+        return out
+    finally:
+        lib.rsba_cuda_structure_free(handle)
 
 
 def point_owners(scene, world_size: int) -> np.ndarray:

@@ -8,6 +8,7 @@
 // state stays in HBM; per iteration the host reads back a handful of scalars.
 #include "lm.cuh"
 #include "problem.cuh"
+#include "structure.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -97,275 +98,45 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   const bool free_cam = h->free_cam, free_ratio = h->free_ratio && !h->priors.empty();
   const bool pseudo = h->has_pseudo_frame();
   const int Fc = h->n_cam_frames();    // + the pseudo-frame (free intrinsics / free interFrameRatio)
-  const std::vector<int>& fr = h->h_obs_frame;
-  const std::vector<int>& pt = h->h_obs_point;
   cudaStream_t s = h->stream;
-  if (F > 65536) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 65536 frames: the tile index (T x T) would not fit; shard the sequence");
 
-  // point-major CSR (stable counting sort: observation order inside a point is frame order)
-  std::vector<int> pt_ptr(P + 1, 0), pt_obs(N);
-  for (long i = 0; i < N; ++i) pt_ptr[pt[i] + 1]++;
-  for (int p = 0; p < P; ++p) pt_ptr[p + 1] += pt_ptr[p];
+  // ---- host analysis (structure.cu; no device involved)
+  SceneTopology topo;
+  topo.n_obs = N; topo.n_frames = F; topo.n_points = P;
+  topo.obs_frame = h->h_obs_frame.data(); topo.obs_point = h->h_obs_point.data();
+  topo.point_const = h->point_const.data();
+  topo.free_cam = free_cam; topo.free_ratio = h->free_ratio;
+  for (const auto& pr : h->priors) topo.prior_pairs.emplace_back(pr.frame, pr.prev);
+  topo.world = h->world; topo.n_obs_global = h->n_obs_global;
+  topo.g_obs_frame = h->g_obs_frame.data(); topo.g_obs_point = h->g_obs_point.data();
+  topo.dense = dense; topo.reorder = h->reorder_tiles;
+  topo.sparse_keys = getenv("RSBA_CUDA_SPARSE_KEYS") != nullptr;   // (env: test hook)
+  HostStructure hs;
   {
-    std::vector<int> cur(pt_ptr.begin(), pt_ptr.end() - 1);
-    for (long i = 0; i < N; ++i) pt_obs[cur[pt[i]]++] = (int)i;
+    std::string err;
+    auto lap_cb = [](const char* what, void* ctx) { (*static_cast<decltype(lap)*>(ctx))(what); };
+    const int arc = analyze_structure(topo, &hs, &err, lap_cb, &lap);
+    if (arc) return fail(arc, err);
   }
-  // frame chunks of <= 128 observations
-  std::vector<int> chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr(Fc + 1, 0);
-  {
-    long i = 0;
-    for (int f = 0; f < F; ++f) {
-      frame_chunk_ptr[f] = (int)chunk_frame.size();
-      long j = i;
-      while (j < N && fr[j] == f) ++j;
-      for (long b = i; b < j; b += 128) {
-        chunk_frame.push_back(f);
-        chunk_beg.push_back((int)b);
-        chunk_cnt.push_back((int)std::min<long>(128, j - b));
-      }
-      i = j;
-    }
-    for (int f = F; f <= Fc; ++f) frame_chunk_ptr[f] = (int)chunk_frame.size();   // the pseudo-frame has no observations
-  }
-  lap("point CSR + frame chunks");
-  // ---- Schur SYRK structure: (frame tile, point) incidences, tile pairs, work items
-  const int T = (int)((12L * Fc + kTile - 1) / kTile);
-  const int H = 2 * T;                                   // sub-tiles of 4 frames
-  const int Hreal = (Fc + kSubFrames - 1) / kSubFrames;  // ... that hold at least one frame
-  const int cam_sub = F / kSubFrames, cam_slot = F % kSubFrames;   // where the pseudo-frame sits
-  std::vector<int> inc_point, inc_tile, slot_beg, pt_inc_ptr(P + 1, 0), cam_inc(std::max(P, 1), -1);
-  std::vector<unsigned char> slot_cnt;
-  for (int p = 0; p < P; ++p) {
-    pt_inc_ptr[p] = (int)inc_point.size();
-    if (h->point_const[p]) continue;  // constant points are not eliminated: no Schur term
-    const int b = pt_ptr[p], e = pt_ptr[p + 1];
-    int last = -1;
-    for (int x = b; x < e; ++x) {
-      const int f = fr[pt_obs[x]], A = f / kSubFrames, fs = f % kSubFrames;
-      if (last < 0 || inc_tile[last] != A) {
-        last = (int)inc_point.size();
-        inc_point.push_back(p);
-        inc_tile.push_back(A);
-        slot_beg.insert(slot_beg.end(), kSubFrames, -1);
-        slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
-      }
-      const size_t sl = (size_t)last * kSubFrames + fs;
-      if (slot_cnt[sl] == 0) slot_beg[sl] = x;
-      if (slot_cnt[sl] == 255) return fail(RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
-      slot_cnt[sl]++;
-    }
-    if (free_cam && e > b) {
-      // every eliminated point also couples with the intrinsics: its panel in the pseudo-frame's sub-tile
-      // (shared with the last real frames when F is not a multiple of 4) gets the pseudo-frame rows
-      if (last < 0 || inc_tile[last] != cam_sub) {
-        last = (int)inc_point.size();
-        inc_point.push_back(p);
-        inc_tile.push_back(cam_sub);
-        slot_beg.insert(slot_beg.end(), kSubFrames, -1);
-        slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
-      }
-      cam_inc[p] = last;
-    }
-  }
-  (void)cam_slot;
-  pt_inc_ptr[P] = (int)inc_point.size();
-  lap("incidences");
-  const int n_inc = (int)inc_point.size();
-  if ((long)(n_inc + 1) * kPanelDoubles > 2147483647L)
-    return fail(RSBA_ERR_INVALID_ARGUMENT, "Schur panel buffer exceeds 2^31 doubles: shard the scene over more GPUs");
-  // where each observation's 12 panel rows live; incidences with a doubly observed frame slot are
-  // rebuilt by phi_build_kernel instead
-  std::vector<int> obs_phi_off(std::max<long>(N, 1), -1), dup_inc;
-  for (int i = 0; i < n_inc; ++i) {
-    bool dup = false;
-    for (int fs = 0; fs < kSubFrames; ++fs) dup = dup || slot_cnt[(size_t)i * kSubFrames + fs] > 1;
-    if (dup) { dup_inc.push_back(i); continue; }
-    for (int fs = 0; fs < kSubFrames; ++fs)
-      if (slot_cnt[(size_t)i * kSubFrames + fs] == 1)
-        obs_phi_off[pt_obs[slot_beg[(size_t)i * kSubFrames + fs]]] = i * kPanelDoubles + fs * kFrameParams;
-  }
-  // ---- sub-tile pairs and their entry lists, by a two-pass counting sort on the pair key a*H + b
-  // (entries of one pair stay in point order).  The key table is dense while H^2 is small, else the
-  // distinct keys are collected and sorted.
-  const bool dense_keys = (long)H * H <= (1L << 24) && !getenv("RSBA_CUDA_SPARSE_KEYS");   // (env: test hook)
-  std::vector<int> key_pair;          // dense: key -> pair id (or -1)
-  std::vector<long> keys;             // sparse: sorted distinct keys
-  auto for_each_pair_of_point = [&](int p, auto&& fn) {
-    for (int x = pt_inc_ptr[p]; x < pt_inc_ptr[p + 1]; ++x)
-      for (int y = x; y < pt_inc_ptr[p + 1]; ++y) fn((long)inc_tile[x] * H + inc_tile[y], x, y);
-  };
-  std::vector<long> marker_keys;
-  for (int t = 0; t < Hreal; ++t) marker_keys.push_back((long)t * H + t);     // every diagonal sub-tile is a pair
-  for (const auto& pr : h->priors) {                                           // ... and every prior coupling
-    const int a = std::min(pr.frame, pr.prev) / kSubFrames, b = std::max(pr.frame, pr.prev) / kSubFrames;
-    marker_keys.push_back((long)a * H + b);
-    if (free_ratio) {   // the ratio (pseudo-frame) couples with both frames of every prior
-      marker_keys.push_back((long)a * H + cam_sub);
-      marker_keys.push_back((long)b * H + cam_sub);
-    }
-  }
-  std::vector<int> pair_a, pair_b;
-  std::vector<long> pair_cnt;
-  if (dense_keys) {
-    std::vector<int> cnt((size_t)H * H, 0);
-    std::vector<char> present((size_t)H * H, 0);
-    for (long k : marker_keys) present[k] = 1;
-    for (int p = 0; p < P; ++p) for_each_pair_of_point(p, [&](long key, int, int) { cnt[key]++; });
-    key_pair.assign((size_t)H * H, -1);
-    for (long key = 0; key < (long)H * H; ++key)
-      if (cnt[key] > 0 || present[key]) {
-        key_pair[key] = (int)pair_a.size();
-        pair_a.push_back((int)(key / H));
-        pair_b.push_back((int)(key % H));
-        pair_cnt.push_back(cnt[key]);
-      }
-  } else {
-    keys = marker_keys;
-    for (int p = 0; p < P; ++p) for_each_pair_of_point(p, [&](long key, int, int) { keys.push_back(key); });
-    std::vector<long> all = keys;
-    std::sort(keys.begin(), keys.end());
-    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-    pair_cnt.assign(keys.size(), 0);
-    for (size_t k = marker_keys.size(); k < all.size(); ++k)
-      pair_cnt[std::lower_bound(keys.begin(), keys.end(), all[k]) - keys.begin()]++;
-    for (long key : keys) { pair_a.push_back((int)(key / H)); pair_b.push_back((int)(key % H)); }
-  }
-  auto pair_of_key = [&](long key) -> int {
-    return dense_keys ? key_pair[key] : (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
-  };
-  lap("count pairs");
-  // Which 2-frame halves of an incidence's 4 frame slots are populated (bit 0: slots 0-1, bit 1: slots 2-3).
-  // A track that starts or ends inside a sub-tile leaves a half empty; the entries of an off-diagonal pair are
-  // grouped by the (column side, row side) half masks so that the SYRK skips the 24 x 24 patches that are
-  // structurally zero for a whole work item (k2_schur.cu).
-  std::vector<unsigned char> inc_half(std::max(n_inc, 1), 0);
-  for (int i = 0; i < n_inc; ++i) {
-    unsigned m = 0;
-    for (int fs = 0; fs < kSubFrames; ++fs)
-      if (slot_cnt[(size_t)i * kSubFrames + fs]) m |= 1u << (fs / 2);
-    inc_half[i] = (unsigned char)m;
-  }
-  if (free_cam)   // the pseudo-frame rows of a point's panel are written by phi_cam, not through a slot
-    for (int p = 0; p < P; ++p)
-      if (cam_inc[p] >= 0) inc_half[cam_inc[p]] |= (unsigned char)(1u << (cam_slot / 2));
-  constexpr int kClasses = 9;   // (mask_a - 1) * 3 + (mask_b - 1); diagonal pairs use class 0 only
-  auto class_of = [&](int x, int y) -> int {
-    if (x == y) return 0;
-    const int ma = inc_half[x] ? inc_half[x] : 3, mb = inc_half[y] ? inc_half[y] : 3;
-    return (ma - 1) * 3 + (mb - 1);
-  };
-  // work items: <= kSchurSegPoints entries of one (pair, class) each, padded to a multiple of 8
-  const int n_pairs_h = (int)pair_a.size();
-  std::vector<long> class_cnt((size_t)n_pairs_h * kClasses + 1, 0);
-  for (int p = 0; p < P; ++p)
-    for_each_pair_of_point(p, [&](long key, int x, int y) { class_cnt[(size_t)pair_of_key(key) * kClasses + class_of(x, y)]++; });
-  std::vector<int> pair_item_ptr(n_pairs_h + 1, 0);
-  std::vector<long> class_base((size_t)n_pairs_h * kClasses + 1, 0);
-  std::vector<int4> items;
-  long pos = 0;
-  for (int q = 0; q < n_pairs_h; ++q) {
-    pair_item_ptr[q] = (int)items.size();
-    const bool dg = pair_a[q] == pair_b[q];
-    for (int cl = 0; cl < kClasses; ++cl) {
-      class_base[(size_t)q * kClasses + cl] = pos;
-      long left = class_cnt[(size_t)q * kClasses + cl];
-      const int ma = cl / 3 + 1, mb = cl % 3 + 1;
-      while (left > 0) {
-        const int take = (int)std::min<long>(left, kSchurSegPoints);
-        const int padded = (take + 7) / 8 * 8;
-        if (pos + padded > 2147483647L) return fail(RSBA_ERR_INVALID_ARGUMENT, "Schur entry list exceeds 2^31");
-        // w: bit 0 = diagonal pair; bits 4-5 / 8-9 = populated halves of the column (A) / row (B) side
-        items.push_back(make_int4(q, (int)pos, padded, dg ? 1 : ((ma << 4) | (mb << 8))));
-        pos += padded;
-        left -= take;
-      }
-    }
-  }
-  pair_item_ptr[n_pairs_h] = (int)items.size();
-  std::vector<int2> entries((size_t)std::max<long>(pos, 1), make_int2(n_inc, n_inc));   // zero panel
-  {
-    // (kSchurSegPoints is a multiple of 8: only the last segment of a class is padded, so a class is contiguous)
-    std::vector<long> cur(class_base.begin(), class_base.end() - 1);
-    for (int p = 0; p < P; ++p)
-      for_each_pair_of_point(p, [&](long key, int x, int y) {
-        entries[cur[(size_t)pair_of_key(key) * kClasses + class_of(x, y)]++] = make_int2(y, x);   // (row side B, column side A)
-      });
-  }
-  if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
-  const int n_items = (int)pair_item_ptr.back();
-  lap("work items");
-  // ---- ordering, symbolic factorisation, elimination levels (tile_plan.cu)
-  // (the plan is a function of the WHOLE scene, so every rank of a multi-GPU run derives the same one)
-  TilePlan& plan = lm->plan;
-  {
-    std::vector<std::pair<int, int>> tp;
-    if (h->world > 1) {
-      const long NG = h->n_obs_global;
-      std::vector<long> gptr(P + 1, 0);
-      for (long i = 0; i < NG; ++i) gptr[h->g_obs_point[i] + 1]++;
-      for (int p = 0; p < P; ++p) gptr[p + 1] += gptr[p];
-      std::vector<int> gtile(NG);
-      {
-        std::vector<long> cur(gptr.begin(), gptr.end() - 1);
-        for (long i = 0; i < NG; ++i) gtile[cur[h->g_obs_point[i]]++] = h->g_obs_frame[i] / kFramesPerTile;
-      }
-      std::vector<char> seen((size_t)T * T, 0);
-      std::vector<int> tiles;
-      for (int p = 0; p < P; ++p) {
-        if (h->point_const[p]) continue;
-        tiles.clear();
-        for (long e = gptr[p]; e < gptr[p + 1]; ++e)
-          if (tiles.empty() || tiles.back() != gtile[e]) tiles.push_back(gtile[e]);
-        for (size_t x = 0; x < tiles.size(); ++x)
-          for (size_t y = x; y < tiles.size(); ++y) seen[(size_t)tiles[x] * T + tiles[y]] = 1;
-      }
-      for (const auto& pr : h->priors) {
-        const int a = std::min(pr.frame, pr.prev) / kFramesPerTile, b = std::max(pr.frame, pr.prev) / kFramesPerTile;
-        seen[(size_t)a * T + b] = 1;
-        if (free_ratio) seen[(size_t)a * T + F / kFramesPerTile] = seen[(size_t)b * T + F / kFramesPerTile] = 1;
-      }
-      for (int a = 0; a < T; ++a)
-        for (int b = a; b < T; ++b)
-          if (seen[(size_t)a * T + b]) tp.emplace_back(a, b);
-    } else {
-      tp.reserve(pair_a.size());
-      for (size_t k = 0; k < pair_a.size(); ++k) tp.emplace_back(pair_a[k] / 2, pair_b[k] / 2);
-      std::sort(tp.begin(), tp.end());
-      tp.erase(std::unique(tp.begin(), tp.end()), tp.end());
-    }
-    const int border_tile = pseudo ? F / kFramesPerTile : -1;   // couples with everything: eliminated last
-    if (free_cam && h->world > 1)
-      for (int a = 0; a < T; ++a) tp.emplace_back(std::min(a, border_tile), std::max(a, border_tile));
-    build_tile_plan(T, tp, dense, h->reorder_tiles, border_tile, &plan);
-  }
-  const std::vector<int>& tile_pos = plan.tile_pos;
+  lm->plan = std::move(hs.plan);
+  const TilePlan& plan = lm->plan;
+  const int T = hs.T, n_inc = hs.n_inc, n_items = hs.n_items;
+  const std::vector<int>& chunk_frame = hs.chunk_frame;
+  const std::vector<int>& pair_a = hs.pair_a;
   const std::vector<int2>& nz_tiles = plan.nz_tiles;
 
-  lap("tile plan (ND + symbolic)");
   // ---- upload
   int rc;
 #define UP(dev, host) if ((rc = upload(lm->dev, host, s))) return rc
-  UP(pt_ptr, pt_ptr); UP(pt_obs, pt_obs); UP(chunk_frame, chunk_frame); UP(chunk_beg, chunk_beg);
-  UP(chunk_cnt, chunk_cnt); UP(frame_chunk_ptr, frame_chunk_ptr);
-  UP(inc_point, inc_point); UP(inc_tile, inc_tile); UP(slot_beg, slot_beg); UP(slot_cnt, slot_cnt);
-  UP(obs_phi_off, obs_phi_off); UP(dup_inc, dup_inc); UP(cam_inc, cam_inc);
-  UP(pair_a, pair_a); UP(pair_b, pair_b); UP(pair_item_ptr, pair_item_ptr); UP(items, items); UP(tile_pos, tile_pos);
-  UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
-  UP(entries, entries); UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
+  UP(pt_ptr, hs.pt_ptr); UP(pt_obs, hs.pt_obs); UP(chunk_frame, hs.chunk_frame); UP(chunk_beg, hs.chunk_beg);
+  UP(chunk_cnt, hs.chunk_cnt); UP(frame_chunk_ptr, hs.frame_chunk_ptr);
+  UP(inc_point, hs.inc_point); UP(inc_tile, hs.inc_tile); UP(slot_beg, hs.slot_beg); UP(slot_cnt, hs.slot_cnt);
+  UP(obs_phi_off, hs.obs_phi_off); UP(dup_inc, hs.dup_inc); UP(cam_inc, hs.cam_inc);
+  UP(pair_a, hs.pair_a); UP(pair_b, hs.pair_b); UP(pair_item_ptr, hs.pair_item_ptr); UP(items, hs.items);
+  UP(tile_pos, plan.tile_pos); UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
+  UP(entries, hs.entries); UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
   UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
-  UP(panels, plan.panels); UP(trsm, plan.trsm);
-  {
-    // where each off-diagonal tile (i, k) leaves its forward-substitution term: its index in row i's list
-    std::vector<int> fwd_slot(std::max<size_t>(plan.trsm.size(), 1), 0);
-    for (size_t t = 0; t < plan.trsm.size(); ++t) {
-      const int i = plan.trsm[t].x, k = plan.trsm[t].y;
-      int q = plan.lrow_ptr[i];
-      while (q < plan.lrow_ptr[i + 1] && plan.lrow_cols[q] != k) ++q;
-      if (q == plan.lrow_ptr[i + 1]) return fail(RSBA_ERR_STATE, "tile plan: trsm tile missing from the row list");
-      fwd_slot[t] = q;
-    }
-    UP(fwd_slot, fwd_slot);
-  }
+  UP(panels, plan.panels); UP(trsm, plan.trsm); UP(fwd_slot, hs.fwd_slot);
   {
     std::vector<unsigned short> mask(h->pose_mask);
     mask.resize(Fc, 0);
@@ -385,11 +156,11 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.frame_chunk_ptr = lm->frame_chunk_ptr.ptr; st.n_chunks = (int)chunk_frame.size();
   st.n_inc = n_inc; st.inc_point = lm->inc_point.ptr; st.inc_tile = lm->inc_tile.ptr;
   st.slot_beg = lm->slot_beg.ptr; st.slot_cnt = lm->slot_cnt.ptr;
-  st.obs_phi_off = lm->obs_phi_off.ptr; st.dup_inc = lm->dup_inc.ptr; st.n_dup = (int)dup_inc.size();
+  st.obs_phi_off = lm->obs_phi_off.ptr; st.dup_inc = lm->dup_inc.ptr; st.n_dup = (int)hs.dup_inc.size();
   st.cam_inc = lm->cam_inc.ptr;
   st.n_pairs = (int)pair_a.size(); st.pair_a = lm->pair_a.ptr; st.pair_b = lm->pair_b.ptr;
   st.pair_item_ptr = lm->pair_item_ptr.ptr; st.n_items = n_items; st.items = lm->items.ptr;
-  st.entries = lm->entries.ptr; st.n_entries = (long)entries.size(); st.tile_pos = lm->tile_pos.ptr;
+  st.entries = lm->entries.ptr; st.n_entries = (long)hs.entries.size(); st.tile_pos = lm->tile_pos.ptr;
   st.pos_tile = lm->pos_tile.ptr; st.n_cam_params = 12L * Fc;
   lm->free_cam = free_cam;
   lm->free_ratio = h->free_ratio;

@@ -1,0 +1,241 @@
+"""CPU suite: the one-off host structure analysis of rsba_cuda_solve (rsba_b200/csrc/structure.cu), run through the
+device-free C ABI `rsba_cuda_analyze_structure`.  It is the analogue of what Ceres does before its first iteration
+(Program reordering, SchurEliminator block-structure detection, CHOLMOD analyse; reached through ceres::Solve,
+CeresHandler.h:403,419).  The work lists the Schur SYRK kernel consumes are EXECUTED here in numpy and compared with
+a direct per-point Schur complement, so a wrong pair, a dropped entry or a wrong half mask shows up without a GPU."""
+import numpy as np
+import pytest
+
+import rsba_b200.api as api
+from helpers import small_scene
+
+SUB, FP, SEG = 4, 12, 512          # frames per sub-tile, parameters per frame, max entries per work item
+PANEL_DOUBLES = 3 * (SUB * FP + 4)
+
+
+def ragged_topology(seed, F, P, const_frac=0.1, dup_frac=0.05, max_track=9):
+    """Frame-sorted (frame, point) lists with ragged tracks, unobserved points, constant points and a few
+    points seen twice in one frame."""
+    rng = np.random.default_rng(seed)
+    fr, pt = [], []
+    for p in range(P):
+        if rng.random() < 0.05:
+            continue                                  # never observed
+        k = int(rng.integers(1, max_track + 1))
+        start = int(rng.integers(0, F))
+        frames = sorted(set(int(f) for f in rng.integers(start, min(F, start + 2 * max_track), size=k)))
+        for f in frames:
+            fr.append(f); pt.append(p)
+            if rng.random() < dup_frac:
+                fr.append(f); pt.append(p)            # duplicate observation in the same frame
+    fr, pt = np.array(fr, np.int32), np.array(pt, np.int32)
+    order = np.argsort(fr, kind="stable")
+    const_point = (rng.random(P) < const_frac).astype(np.uint8)
+    return fr[order], pt[order], const_point
+
+
+def check_structure(fr, pt, F, P, const_point=None, free_cam=False, free_ratio=False, priors=(), seed=0, **kw):
+    const_point = np.zeros(P, np.uint8) if const_point is None else const_point
+    pf = [a for a, _ in priors]
+    pp = [b for _, b in priors]
+    st = api.analyze_structure(fr, pt, F, P, const_point, free_cam, free_ratio, pf, pp, **kw)
+    N = fr.size
+    pseudo = free_cam or free_ratio
+    Fc = F + (1 if pseudo else 0)
+    T = (12 * Fc + 95) // 96
+    assert st["T"] == T
+
+    # ---- point-major CSR = stable sort of the observations by point
+    want_obs = np.argsort(pt, kind="stable").astype(np.int32)
+    assert np.array_equal(st["pt_obs"], want_obs)
+    assert np.array_equal(st["pt_ptr"], np.concatenate([[0], np.cumsum(np.bincount(pt, minlength=P))]))
+
+    # ---- frame chunks: each frame's run of observations cut into pieces of <= 128, in order
+    cf, cb, cc, fcp = st["chunk_frame"], st["chunk_beg"], st["chunk_cnt"], st["frame_chunk_ptr"]
+    assert fcp.size == Fc + 1 and fcp[-1] == cf.size
+    assert np.all(cc >= 1) and np.all(cc <= 128)
+    covered = np.concatenate([np.arange(b, b + c) for b, c in zip(cb, cc)]) if cf.size else np.zeros(0, int)
+    assert np.array_equal(covered, np.arange(N))
+    assert np.array_equal(np.repeat(cf, cc), fr)
+    for f in range(F):
+        assert np.all(cf[fcp[f]:fcp[f + 1]] == f)
+
+    # ---- incidences: one per (sub-tile, eliminated point) with an observation (+ the pseudo-frame's sub-tile)
+    n_inc = st["n_inc"]
+    ip, it, sb, sc_ = st["inc_point"], st["inc_tile"], st["slot_beg"], st["slot_cnt"]
+    pip, cam_inc = st["pt_inc_ptr"], st["cam_inc"]
+    assert ip.size == n_inc == it.size and sb.shape == (n_inc, SUB) and sc_.shape == (n_inc, SUB)
+    cam_sub, cam_slot = F // SUB, F % SUB
+    for p in range(P):
+        obs = want_obs[st["pt_ptr"][p]:st["pt_ptr"][p + 1]]
+        subs = sorted(set(int(fr[o]) // SUB for o in obs)) if not const_point[p] else []
+        if free_cam and subs and subs[-1] != cam_sub:
+            subs.append(cam_sub)
+        got = it[pip[p]:pip[p + 1]]
+        assert list(got) == subs, (p, got, subs)
+        assert np.all(ip[pip[p]:pip[p + 1]] == p)
+        if free_cam and subs:
+            assert it[cam_inc[p]] == cam_sub and ip[cam_inc[p]] == p
+        else:
+            assert cam_inc[p] == -1
+        for i in range(pip[p], pip[p + 1]):
+            for fs in range(SUB):
+                mine = [x for x in range(st["pt_ptr"][p], st["pt_ptr"][p + 1]) if fr[want_obs[x]] == it[i] * SUB + fs]
+                assert sc_[i, fs] == len(mine)
+                assert sb[i, fs] == (mine[0] if mine else -1)
+
+    # ---- where frame_blocks writes each observation's 12 panel rows
+    dup = set(int(i) for i in st["dup_inc"])
+    assert dup == set(int(i) for i in np.nonzero((sc_ > 1).any(axis=1))[0])
+    off = st["obs_phi_off"]
+    want_off = np.full(max(N, 1), -1, np.int64)
+    for i in range(n_inc):
+        if i in dup:
+            continue
+        for fs in range(SUB):
+            if sc_[i, fs] == 1:
+                want_off[want_obs[sb[i, fs]]] = i * PANEL_DOUBLES + fs * FP
+    assert np.array_equal(off, want_off)
+
+    # ---- half masks
+    half = st["inc_half"]
+    for i in range(n_inc):
+        m = (1 if sc_[i, 0] or sc_[i, 1] else 0) | (2 if sc_[i, 2] or sc_[i, 3] else 0)
+        if free_cam and cam_inc[ip[i]] == i:
+            m |= 1 << (cam_slot // 2)
+        assert half[i] == m
+
+    # ---- random panels with the structural zero rows the kernels leave
+    rng = np.random.default_rng(seed)
+    Phi = np.zeros((n_inc + 1, SUB * FP, 3))
+    for i in range(n_inc):
+        for fs in range(SUB):
+            if sc_[i, fs] or (free_cam and cam_inc[ip[i]] == i and fs == cam_slot):
+                Phi[i, fs * FP:(fs + 1) * FP] = rng.standard_normal((FP, 3))
+    H = 2 * T
+    direct = {}
+    for p in range(P):
+        for x in range(pip[p], pip[p + 1]):
+            for y in range(x, pip[p + 1]):
+                key = (int(it[x]), int(it[y]))
+                direct[key] = direct.get(key, 0) + Phi[y] @ Phi[x].T
+
+    # ---- execute the work lists the way schur_syrk_kernel + schur_reduce do
+    pa, pb, pitem, items, entries = st["pair_a"], st["pair_b"], st["pair_item_ptr"], st["items"], st["entries"]
+    assert np.all(pa <= pb) and np.all(pb < H)
+    keys = pa.astype(np.int64) * H + pb
+    assert np.all(np.diff(keys) > 0), "pairs sorted by (a, b), no repeats"
+    assert pitem.size == pa.size + 1 and pitem[-1] == st["n_items"]
+    n_real_entries = 0
+    pos = 0
+    for q in range(pa.size):
+        acc = np.zeros((SUB * FP, SUB * FP))
+        diag = pa[q] == pb[q]
+        for j in range(pitem[q], pitem[q + 1]):
+            iq, beg, cnt, w = (int(v) for v in items[j])
+            assert iq == q and beg == pos and cnt % 8 == 0 and 0 < cnt <= SEG
+            pos += cnt
+            assert (w & 1) == int(diag)
+            ma, mb = ((w >> 4) & 3, (w >> 8) & 3) if not diag else (3, 3)
+            rows_b = np.concatenate([np.arange(24) + 24 * hb for hb in range(2) if mb >> hb & 1])
+            rows_a = np.concatenate([np.arange(24) + 24 * ha for ha in range(2) if ma >> ha & 1])
+            for e in range(beg, beg + cnt):
+                y, x = (int(v) for v in entries[e])
+                if y == n_inc:
+                    assert x == n_inc                  # padding: the all-zero panel
+                    continue
+                n_real_entries += 1
+                assert it[x] == pa[q] and it[y] == pb[q] and ip[x] == ip[y]
+                # the kernel only computes the patches of populated halves: what it skips must be zero
+                part = np.zeros_like(acc)
+                part[np.ix_(rows_b, rows_a)] = Phi[y][rows_b] @ Phi[x][rows_a].T
+                acc += part
+        want = direct.pop((int(pa[q]), int(pb[q])), np.zeros_like(acc))
+        if diag:   # the kernel produces the lower triangle of a diagonal pair only
+            acc, want = np.tril(acc), np.tril(want)
+        assert np.allclose(acc, want, rtol=1e-12, atol=1e-12), (q, pa[q], pb[q])
+    assert not direct, f"pairs with Schur terms but no work items: {list(direct)[:5]}"
+    assert n_real_entries == sum((pip[p + 1] - pip[p]) * (pip[p + 1] - pip[p] + 1) // 2 for p in range(P))
+    assert entries.shape[0] == max(pos, 1)
+
+    # ---- every diagonal sub-tile with a frame, and every prior coupling, is a pair (even without a Schur term)
+    have = set(zip(pa.tolist(), pb.tolist()))
+    for t in range((Fc + SUB - 1) // SUB):
+        assert (t, t) in have
+    for a, b in priors:
+        lo, hi = min(a, b) // SUB, max(a, b) // SUB
+        assert (lo, hi) in have
+        if free_ratio:
+            assert (lo, cam_sub) in have and (hi, cam_sub) in have
+
+    # ---- the tile plan covers every pair's Cholesky tile; forward-substitution slots point at the right tile
+    tile_pos, slot = st["plan.tile_pos"], st["plan.tile_slot"]
+    for a, b in have:
+        i, j = sorted((int(tile_pos[a // 2]), int(tile_pos[b // 2])))
+        assert slot[j * T + i] >= 0, (a, b)
+    trsm, lptr, lcols, fwd = st["plan.trsm"], st["plan.lrow_ptr"], st["plan.lrow_cols"], st["fwd_slot"]
+    for t in range(trsm.shape[0]):
+        i, k = (int(v) for v in trsm[t])
+        assert lptr[i] <= fwd[t] < lptr[i + 1] and lcols[fwd[t]] == k
+    return st
+
+
+def test_structure_of_c1():
+    sc = small_scene()
+    check_structure(sc.obs_frame, sc.obs_point, sc.num_frames, sc.num_points)
+
+
+@pytest.mark.parametrize("F", [1, 3, 4, 5, 8, 9, 17, 37])
+def test_structure_ragged_tracks_around_tile_borders(F):
+    fr, pt, cp = ragged_topology(100 + F, F, 60)
+    check_structure(fr, pt, F, 60, cp, seed=F)
+
+
+@pytest.mark.parametrize("F", [7, 8, 12, 21])
+def test_structure_with_intrinsics_pseudo_frame(F):
+    fr, pt, cp = ragged_topology(200 + F, F, 50)
+    check_structure(fr, pt, F, 50, cp, free_cam=True, seed=F)
+
+
+@pytest.mark.parametrize("free_cam", [False, True])
+def test_structure_with_motion_priors_and_free_ratio(free_cam):
+    F = 19
+    fr, pt, cp = ragged_topology(300, F, 40, max_track=4)
+    priors = [(f, f - 1) for f in range(1, F)]
+    check_structure(fr, pt, F, 40, cp, free_cam=free_cam, free_ratio=True, priors=priors)
+    check_structure(fr, pt, F, 40, cp, free_cam=free_cam, free_ratio=False, priors=priors)
+
+
+def test_structure_long_tracks_split_into_segments_of_512_entries():
+    # 700 points all seen by the same two sub-tiles: (0, 1) needs two work items per half-mask class
+    F, P = 8, 700
+    fr = np.repeat(np.arange(F, dtype=np.int32), P)
+    pt = np.tile(np.arange(P, dtype=np.int32), F)
+    st = check_structure(fr, pt, F, P)
+    assert st["n_items"] == 3 * 2 and np.array_equal(st["items"][:, 2], [512, 192] * 3)
+
+
+def test_structure_sparse_key_path_is_identical():
+    fr, pt, cp = ragged_topology(7, 41, 80)
+    a = api.analyze_structure(fr, pt, 41, 80, cp)
+    b = api.analyze_structure(fr, pt, 41, 80, cp, sparse_keys=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_structure_empty_and_all_constant():
+    st = api.analyze_structure(np.zeros(0, np.int32), np.zeros(0, np.int32), 5, 3)
+    assert st["n_inc"] == 0 and st["n_items"] == 0 and st["pair_a"].size == 2      # the diagonal sub-tiles
+    fr, pt, _ = ragged_topology(9, 10, 20)
+    st = check_structure(fr, pt, 10, 20, np.ones(20, np.uint8))
+    assert st["n_inc"] == 0 and st["n_items"] == 0
+
+
+def test_structure_argument_checks():
+    fr = np.array([1, 0], np.int32)
+    with pytest.raises(api.RsbaError):
+        api.analyze_structure(fr, np.zeros(2, np.int32), 2, 1)             # not sorted by frame
+    with pytest.raises(api.RsbaError):
+        api.analyze_structure(np.array([0, 5], np.int32), np.zeros(2, np.int32), 2, 1)   # frame out of range
+    with pytest.raises(api.RsbaError):
+        api.analyze_structure(np.zeros(300, np.int32), np.zeros(300, np.int32), 1, 1)    # > 255 in one frame
