@@ -73,8 +73,8 @@ int fail(int code, const std::string& msg) {
   return code;
 }
 
-template <typename T>
-int upload(DeviceBuffer<T>& d, const std::vector<T>& h, cudaStream_t s) {
+template <typename T, typename A>
+int upload(DeviceBuffer<T>& d, const std::vector<T, A>& h, cudaStream_t s) {
   RSBA_CUDA_TRY(d.resize(std::max<size_t>(h.size(), 1)));
   if (!h.empty()) RSBA_CUDA_TRY(cudaMemcpyAsync(d.ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   return RSBA_OK;

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "../../include/rsba_cuda.h"
 
@@ -14,6 +15,36 @@ namespace rsba {
 void set_last_error(const std::string& msg);   // problem.cu
 
 namespace {
+
+// A handful of host threads for the one-off analysis (std::thread per phase: the phases take milliseconds each).
+// RSBA_CUDA_HOST_THREADS overrides the count; small scenes run on the calling thread alone.
+struct HostThreads {
+  int n = 1;
+  explicit HostThreads(long work) {
+    int want = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("RSBA_CUDA_HOST_THREADS")) want = std::max(1, std::min(64, atoi(e)));
+    else if (work < 100000) want = 1;
+    n = want;
+  }
+  template <typename Fn>
+  void run(Fn&& fn) const {
+    if (n == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(n - 1);
+    for (int t = 1; t < n; ++t) th.emplace_back([&fn, t] { fn(t); });
+    fn(0);
+    for (auto& x : th) x.join();
+  }
+  // v.resize(n) without a serial fill, then every thread writes `value` over its share
+  template <typename Vec, typename T>
+  void resize_fill(Vec& v, size_t count, T value) const {
+    v.resize(count);
+    auto* d = v.data();
+    const int nt = n;
+    run([&](int t) { std::fill(d + count * t / nt, d + count * (t + 1) / nt, value); });
+  }
+};
+
 int fail(std::string* error, int code, const char* msg) {
   if (error) *error = msg;
   return code;
@@ -33,16 +64,42 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
   if (F > 65536) return fail(error, RSBA_ERR_INVALID_ARGUMENT, "more than 65536 frames: the tile index (T x T) would not fit; shard the sequence");
   if (N > 2147483647L) return fail(error, RSBA_ERR_INVALID_ARGUMENT, "more than 2^31 observations on one GPU: shard the scene over more GPUs");
 
-  // point-major CSR (stable counting sort: observation order inside a point is frame order)
+  HostThreads pool(N);
+
+  // point-major CSR by a stable parallel counting sort (observation order inside a point stays frame order):
+  // every thread histograms a contiguous range of observations, the per-(thread, point) start offsets follow from a
+  // prefix over points and threads, and each thread scatters its own range.  The frame of each entry travels with
+  // it, so that the incidence passes below read sequentially instead of gathering fr[pt_obs[x]].
   std::vector<int>& pt_ptr = out->pt_ptr;
-  std::vector<int>& pt_obs = out->pt_obs;
+  HostVec<int>& pt_obs = out->pt_obs;
   pt_ptr.assign(P + 1, 0);
   pt_obs.resize(N);
-  for (long i = 0; i < N; ++i) pt_ptr[pt[i] + 1]++;
-  for (int p = 0; p < P; ++p) pt_ptr[p + 1] += pt_ptr[p];
+  HostVec<int2> pt_both(N);   // (observation, frame): scattered as ONE 8-byte store
   {
-    std::vector<int> cur(pt_ptr.begin(), pt_ptr.end() - 1);
-    for (long i = 0; i < N; ++i) pt_obs[cur[pt[i]]++] = (int)i;
+    const int nt = pool.n;
+    std::vector<std::vector<int>> hist(nt);
+    pool.run([&](int t) {
+      hist[t].assign(P, 0);
+      const long b = N * t / nt, e = N * (t + 1) / nt;
+      int* h = hist[t].data();
+      for (long i = b; i < e; ++i) h[pt[i]]++;
+    });
+    // (a single pass over P x threads counters: 1.6 M at C3 with 8 threads)
+    int run = 0;
+    for (int p = 0; p < P; ++p) {
+      pt_ptr[p] = run;
+      for (int t = 0; t < nt; ++t) { const int c = hist[t][p]; hist[t][p] = run; run += c; }
+    }
+    pt_ptr[P] = run;
+    pool.run([&](int t) {
+      const long b = N * t / nt, e = N * (t + 1) / nt;
+      int* cur = hist[t].data();
+      for (long i = b; i < e; ++i) pt_both[cur[pt[i]]++] = make_int2((int)i, fr[i]);
+    });
+    pool.run([&](int t) {
+      const long b = N * t / nt, e = N * (t + 1) / nt;
+      for (long i = b; i < e; ++i) pt_obs[i] = pt_both[i].x;
+    });
   }
   // frame chunks of <= 128 observations
   std::vector<int>& chunk_frame = out->chunk_frame;
@@ -55,8 +112,7 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
     long i = 0;
     for (int f = 0; f < F; ++f) {
       frame_chunk_ptr[f] = (int)chunk_frame.size();
-      long j = i;
-      while (j < N && fr[j] == f) ++j;
+      const long j = std::upper_bound(fr + i, fr + N, f) - fr;   // (sorted by frame)
       for (long b = i; b < j; b += 128) {
         chunk_frame.push_back(f);
         chunk_beg.push_back((int)b);
@@ -73,66 +129,117 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
   const int H = 2 * T;                                   // sub-tiles of 4 frames
   const int Hreal = (Fc + kSubFrames - 1) / kSubFrames;  // ... that hold at least one frame
   const int cam_sub = F / kSubFrames, cam_slot = F % kSubFrames;   // where the pseudo-frame sits
-  std::vector<int>& inc_point = out->inc_point;
-  std::vector<int>& inc_tile = out->inc_tile;
-  std::vector<int>& slot_beg = out->slot_beg;
+  HostVec<int>& inc_point = out->inc_point;
+  HostVec<int>& inc_tile = out->inc_tile;
+  HostVec<int>& slot_beg = out->slot_beg;
   std::vector<int>& pt_inc_ptr = out->pt_inc_ptr;
   std::vector<int>& cam_inc = out->cam_inc;
-  std::vector<unsigned char>& slot_cnt = out->slot_cnt;
-  inc_point.clear(); inc_tile.clear(); slot_beg.clear(); slot_cnt.clear();
+  HostVec<unsigned char>& slot_cnt = out->slot_cnt;
   pt_inc_ptr.assign(P + 1, 0);
   cam_inc.assign(std::max(P, 1), -1);
-  for (int p = 0; p < P; ++p) {
-    pt_inc_ptr[p] = (int)inc_point.size();
-    if (sc.point_const[p]) continue;  // constant points are not eliminated: no Schur term
-    const int b = pt_ptr[p], e = pt_ptr[p + 1];
-    int last = -1;
-    for (int x = b; x < e; ++x) {
-      const int f = fr[pt_obs[x]], A = f / kSubFrames, fs = f % kSubFrames;
-      if (last < 0 || inc_tile[last] != A) {
-        last = (int)inc_point.size();
-        inc_point.push_back(p);
-        inc_tile.push_back(A);
-        slot_beg.insert(slot_beg.end(), kSubFrames, -1);
-        slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
+  // threads own contiguous point ranges holding about the same number of observations each
+  std::vector<int> pt_cut(pool.n + 1, P);
+  pt_cut[0] = 0;
+  for (int t = 1; t < pool.n; ++t)
+    pt_cut[t] = (int)(std::lower_bound(pt_ptr.begin(), pt_ptr.end(), (int)(N * t / pool.n)) - pt_ptr.begin());
+  for (int t = 1; t <= pool.n; ++t) pt_cut[t] = std::min(P, std::max(pt_cut[t], pt_cut[t - 1]));
+  // pass 1: incidences per point (distinct sub-tiles among its frames; + the pseudo-frame's sub-tile when the
+  // intrinsics are free: every eliminated point couples with them, and its panel in that sub-tile -- shared with
+  // the last real frames when F is not a multiple of 4 -- gets the pseudo-frame rows)
+  pool.run([&](int t) {
+    for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p) {
+      if (sc.point_const[p]) continue;  // constant points are not eliminated: no Schur term
+      const int b = pt_ptr[p], e = pt_ptr[p + 1];
+      int n = 0, last_tile = -1;
+      for (int x = b; x < e; ++x) {
+        const int A = pt_both[x].y / kSubFrames;
+        if (A != last_tile) { ++n; last_tile = A; }
       }
-      const size_t sl = (size_t)last * kSubFrames + fs;
-      if (slot_cnt[sl] == 0) slot_beg[sl] = x;
-      if (slot_cnt[sl] == 255) return fail(error, RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
-      slot_cnt[sl]++;
+      if (free_cam && e > b && last_tile != cam_sub) ++n;
+      pt_inc_ptr[p + 1] = n;
     }
-    if (free_cam && e > b) {
-      // every eliminated point also couples with the intrinsics: its panel in the pseudo-frame's sub-tile
-      // (shared with the last real frames when F is not a multiple of 4) gets the pseudo-frame rows
-      if (last < 0 || inc_tile[last] != cam_sub) {
-        last = (int)inc_point.size();
-        inc_point.push_back(p);
-        inc_tile.push_back(cam_sub);
-        slot_beg.insert(slot_beg.end(), kSubFrames, -1);
-        slot_cnt.insert(slot_cnt.end(), kSubFrames, 0);
-      }
-      cam_inc[p] = last;
-    }
+  });
+  {
+    long run = 0;
+    for (int p = 0; p < P; ++p) { run += pt_inc_ptr[p + 1]; pt_inc_ptr[p + 1] = (int)std::min<long>(run, 2147483647L); }
+    if (run * kPanelDoubles + kPanelDoubles > 2147483647L)
+      return fail(error, RSBA_ERR_INVALID_ARGUMENT, "Schur panel buffer exceeds 2^31 doubles: shard the scene over more GPUs");
   }
-  pt_inc_ptr[P] = (int)inc_point.size();
-  lap("incidences");
-  const int n_inc = (int)inc_point.size();
+  const int n_inc = pt_inc_ptr[P];
   out->n_inc = n_inc;
-  if ((long)(n_inc + 1) * kPanelDoubles > 2147483647L)
-    return fail(error, RSBA_ERR_INVALID_ARGUMENT, "Schur panel buffer exceeds 2^31 doubles: shard the scene over more GPUs");
+  inc_point.resize(n_inc);
+  inc_tile.resize(n_inc);
+  pool.resize_fill(slot_beg, (size_t)n_inc * kSubFrames, -1);
+  pool.resize_fill(slot_cnt, (size_t)n_inc * kSubFrames, (unsigned char)0);
+  // pass 2: fill them
+  std::vector<char> slot_overflow(pool.n, 0);
+  pool.run([&](int t) {
+    for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p) {
+      if (pt_inc_ptr[p] == pt_inc_ptr[p + 1]) continue;
+      const int b = pt_ptr[p], e = pt_ptr[p + 1];
+      int last = pt_inc_ptr[p] - 1, last_tile = -1;
+      for (int x = b; x < e; ++x) {
+        const int f = pt_both[x].y, A = f / kSubFrames, fs = f % kSubFrames;
+        if (A != last_tile) {
+          ++last;
+          last_tile = A;
+          inc_point[last] = p;
+          inc_tile[last] = A;
+        }
+        const size_t sl = (size_t)last * kSubFrames + fs;
+        if (slot_cnt[sl] == 0) slot_beg[sl] = x;
+        if (slot_cnt[sl] == 255) { slot_overflow[t] = 1; continue; }
+        slot_cnt[sl]++;
+      }
+      if (free_cam && e > b) {
+        if (last_tile != cam_sub) {
+          ++last;
+          inc_point[last] = p;
+          inc_tile[last] = cam_sub;
+        }
+        cam_inc[p] = last;
+      }
+    }
+  });
+  for (char o : slot_overflow)
+    if (o) return fail(error, RSBA_ERR_INVALID_ARGUMENT, "more than 255 observations of one point in one frame");
+  lap("incidences");
+  // threads own contiguous incidence ranges (cut at point borders: the pair passes below go point by point)
+  std::vector<int> inc_cut(pool.n + 1, n_inc);
+  for (int t = 0; t <= pool.n; ++t) inc_cut[t] = pt_inc_ptr[pt_cut[t]];
   // where each observation's 12 panel rows live; incidences with a doubly observed frame slot are
-  // rebuilt by phi_build_kernel instead
-  std::vector<int>& obs_phi_off = out->obs_phi_off;
+  // rebuilt by phi_build_kernel instead.  Which 2-frame halves of an incidence's 4 frame slots are populated
+  // (bit 0: slots 0-1, bit 1: slots 2-3): a track that starts or ends inside a sub-tile leaves a half empty; the
+  // entries of an off-diagonal pair are grouped by the (column side, row side) half masks so that the SYRK skips
+  // the 24 x 24 patches that are structurally zero for a whole work item (k2_schur.cu).
+  HostVec<int>& obs_phi_off = out->obs_phi_off;
   std::vector<int>& dup_inc = out->dup_inc;
-  obs_phi_off.assign(std::max<long>(N, 1), -1);
+  std::vector<unsigned char>& inc_half = out->inc_half;
+  pool.resize_fill(obs_phi_off, (size_t)std::max<long>(N, 1), -1);
+  inc_half.assign(std::max(n_inc, 1), 0);
   dup_inc.clear();
-  for (int i = 0; i < n_inc; ++i) {
-    bool dup = false;
-    for (int fs = 0; fs < kSubFrames; ++fs) dup = dup || slot_cnt[(size_t)i * kSubFrames + fs] > 1;
-    if (dup) { dup_inc.push_back(i); continue; }
-    for (int fs = 0; fs < kSubFrames; ++fs)
-      if (slot_cnt[(size_t)i * kSubFrames + fs] == 1)
-        obs_phi_off[pt_obs[slot_beg[(size_t)i * kSubFrames + fs]]] = i * kPanelDoubles + fs * kFrameParams;
+  {
+    std::vector<std::vector<int>> dup_of(pool.n);
+    pool.run([&](int t) {
+      for (int i = inc_cut[t]; i < inc_cut[t + 1]; ++i) {
+        const unsigned char* c = &slot_cnt[(size_t)i * kSubFrames];
+        const int* sb = &slot_beg[(size_t)i * kSubFrames];
+        unsigned m = 0;
+        bool dup = false;
+        for (int fs = 0; fs < kSubFrames; ++fs) {
+          if (c[fs]) m |= 1u << (fs / 2);
+          dup = dup || c[fs] > 1;
+        }
+        inc_half[i] = (unsigned char)m;
+        if (dup) { dup_of[t].push_back(i); continue; }
+        for (int fs = 0; fs < kSubFrames; ++fs)
+          if (c[fs] == 1) obs_phi_off[pt_obs[sb[fs]]] = i * kPanelDoubles + fs * kFrameParams;
+      }
+      if (free_cam)   // the pseudo-frame rows of a point's panel are written by phi_cam, not through a slot
+        for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p)
+          if (cam_inc[p] >= 0) inc_half[cam_inc[p]] |= (unsigned char)(1u << (cam_slot / 2));
+    });
+    for (const auto& d : dup_of) dup_inc.insert(dup_inc.end(), d.begin(), d.end());   // ascending
   }
   // ---- sub-tile pairs and their entry lists, by a two-pass counting sort on the pair key a*H + b
   // (entries of one pair stay in point order).  The key table is dense while H^2 is small, else the
@@ -157,64 +264,57 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
   std::vector<int>& pair_a = out->pair_a;
   std::vector<int>& pair_b = out->pair_b;
   pair_a.clear(); pair_b.clear();
-  std::vector<long> pair_cnt;
   if (dense_keys) {
-    std::vector<int> cnt((size_t)H * H, 0);
-    std::vector<char> present((size_t)H * H, 0);
+    // which keys occur: one byte per key and thread, OR-ed together
+    std::vector<std::vector<char>> seen(pool.n);
+    pool.run([&](int t) {
+      seen[t].assign((size_t)H * H, 0);
+      char* s = seen[t].data();
+      for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p) for_each_pair_of_point(p, [&](long key, int, int) { s[key] = 1; });
+    });
+    std::vector<char>& present = seen[0];
+    for (int t = 1; t < pool.n; ++t)
+      for (size_t k = 0; k < (size_t)H * H; ++k) present[k] |= seen[t][k];
     for (long k : marker_keys) present[k] = 1;
-    for (int p = 0; p < P; ++p) for_each_pair_of_point(p, [&](long key, int, int) { cnt[key]++; });
     key_pair.assign((size_t)H * H, -1);
     for (long key = 0; key < (long)H * H; ++key)
-      if (cnt[key] > 0 || present[key]) {
+      if (present[key]) {
         key_pair[key] = (int)pair_a.size();
         pair_a.push_back((int)(key / H));
         pair_b.push_back((int)(key % H));
-        pair_cnt.push_back(cnt[key]);
       }
   } else {
     keys = marker_keys;
     for (int p = 0; p < P; ++p) for_each_pair_of_point(p, [&](long key, int, int) { keys.push_back(key); });
-    std::vector<long> all = keys;
     std::sort(keys.begin(), keys.end());
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-    pair_cnt.assign(keys.size(), 0);
-    for (size_t k = marker_keys.size(); k < all.size(); ++k)
-      pair_cnt[std::lower_bound(keys.begin(), keys.end(), all[k]) - keys.begin()]++;
     for (long key : keys) { pair_a.push_back((int)(key / H)); pair_b.push_back((int)(key % H)); }
   }
   auto pair_of_key = [&](long key) -> int {
     return dense_keys ? key_pair[key] : (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
   };
-  lap("count pairs");
-  // Which 2-frame halves of an incidence's 4 frame slots are populated (bit 0: slots 0-1, bit 1: slots 2-3).
-  // A track that starts or ends inside a sub-tile leaves a half empty; the entries of an off-diagonal pair are
-  // grouped by the (column side, row side) half masks so that the SYRK skips the 24 x 24 patches that are
-  // structurally zero for a whole work item (k2_schur.cu).
-  std::vector<unsigned char>& inc_half = out->inc_half;
-  inc_half.assign(std::max(n_inc, 1), 0);
-  for (int i = 0; i < n_inc; ++i) {
-    unsigned m = 0;
-    for (int fs = 0; fs < kSubFrames; ++fs)
-      if (slot_cnt[(size_t)i * kSubFrames + fs]) m |= 1u << (fs / 2);
-    inc_half[i] = (unsigned char)m;
-  }
-  if (free_cam)   // the pseudo-frame rows of a point's panel are written by phi_cam, not through a slot
-    for (int p = 0; p < P; ++p)
-      if (cam_inc[p] >= 0) inc_half[cam_inc[p]] |= (unsigned char)(1u << (cam_slot / 2));
+  lap("pairs");
   constexpr int kClasses = 9;   // (mask_a - 1) * 3 + (mask_b - 1); diagonal pairs use class 0 only
   auto class_of = [&](int x, int y) -> int {
     if (x == y) return 0;
     const int ma = inc_half[x] ? inc_half[x] : 3, mb = inc_half[y] ? inc_half[y] : 3;
     return (ma - 1) * 3 + (mb - 1);
   };
-  // work items: <= kSchurSegPoints entries of one (pair, class) each, padded to a multiple of 8
+  // work items: <= kSchurSegPoints entries of one (pair, class) each, padded to a multiple of 8.
+  // Entries per (pair, class) and thread first; a thread's entries of a class go behind those of the threads
+  // before it, which keeps every class in point order whatever the thread count.
   const int n_pairs_h = (int)pair_a.size();
-  std::vector<long> class_cnt((size_t)n_pairs_h * kClasses + 1, 0);
-  for (int p = 0; p < P; ++p)
-    for_each_pair_of_point(p, [&](long key, int x, int y) { class_cnt[(size_t)pair_of_key(key) * kClasses + class_of(x, y)]++; });
+  const size_t n_cls = (size_t)n_pairs_h * kClasses;
+  std::vector<std::vector<long>> cnt_of(pool.n);
+  pool.run([&](int t) {
+    cnt_of[t].assign(n_cls + 1, 0);
+    long* c = cnt_of[t].data();
+    for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p)
+      for_each_pair_of_point(p, [&](long key, int x, int y) { c[(size_t)pair_of_key(key) * kClasses + class_of(x, y)]++; });
+  });
+  lap("entry counts");
   std::vector<int>& pair_item_ptr = out->pair_item_ptr;
   pair_item_ptr.assign(n_pairs_h + 1, 0);
-  std::vector<long> class_base((size_t)n_pairs_h * kClasses + 1, 0);
   std::vector<int4>& items = out->items;
   items.clear();
   long pos = 0;
@@ -222,8 +322,9 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
     pair_item_ptr[q] = (int)items.size();
     const bool dg = pair_a[q] == pair_b[q];
     for (int cl = 0; cl < kClasses; ++cl) {
-      class_base[(size_t)q * kClasses + cl] = pos;
-      long left = class_cnt[(size_t)q * kClasses + cl];
+      const size_t k = (size_t)q * kClasses + cl;
+      long left = 0;
+      for (int t = 0; t < pool.n; ++t) { const long c = cnt_of[t][k]; cnt_of[t][k] = pos + left; left += c; }   // -> write cursors
       const int ma = cl / 3 + 1, mb = cl % 3 + 1;
       while (left > 0) {
         const int take = (int)std::min<long>(left, kSchurSegPoints);
@@ -237,19 +338,20 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
     }
   }
   pair_item_ptr[n_pairs_h] = (int)items.size();
-  std::vector<int2>& entries = out->entries;
-  entries.assign((size_t)std::max<long>(pos, 1), make_int2(n_inc, n_inc));   // zero panel
-  {
-    // (kSchurSegPoints is a multiple of 8: only the last segment of a class is padded, so a class is contiguous)
-    std::vector<long> cur(class_base.begin(), class_base.end() - 1);
-    for (int p = 0; p < P; ++p)
+  HostVec<int2>& entries = out->entries;
+  lap("work items");
+  pool.resize_fill(entries, (size_t)std::max<long>(pos, 1), make_int2(n_inc, n_inc));   // zero panel
+  // (kSchurSegPoints is a multiple of 8: only the last segment of a class is padded, so a class is contiguous)
+  pool.run([&](int t) {
+    long* cur = cnt_of[t].data();
+    for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p)
       for_each_pair_of_point(p, [&](long key, int x, int y) {
         entries[cur[(size_t)pair_of_key(key) * kClasses + class_of(x, y)]++] = make_int2(y, x);   // (row side B, column side A)
       });
-  }
+  });
   out->n_items = (int)pair_item_ptr.back();
   if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
-  lap("work items");
+  lap("entry lists");
   // ---- ordering, symbolic factorisation, elimination levels (tile_plan.cu)
   // (the plan is a function of the WHOLE scene, so every rank of a multi-GPU run derives the same one)
   TilePlan& plan = out->plan;

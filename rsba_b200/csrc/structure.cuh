@@ -6,7 +6,9 @@
 // device state, so `rsba_cuda_analyze_structure` (include/rsba_cuda.h) and the CPU tests can run it
 // without a GPU.
 #pragma once
+#include <memory>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -33,17 +35,34 @@ struct SceneTopology {
   int n_cam_frames() const { return n_frames + ((free_cam || free_ratio) ? 1 : 0); }
 };
 
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the big arrays below are
+// written exactly once by the analysis' threads, and a serial zero fill of 20-45 MB each would cost as much as
+// the phase that fills them.
+template <typename T>
+struct DefaultInitAllocator : std::allocator<T> {
+  template <typename U> struct rebind { using other = DefaultInitAllocator<U>; };
+  using std::allocator<T>::allocator;
+  template <typename U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+  template <typename U, typename... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+template <typename T>
+using HostVec = std::vector<T, DefaultInitAllocator<T>>;
+
 struct HostStructure {
-  std::vector<int> pt_ptr, pt_obs;                                   // point-major CSR
+  std::vector<int> pt_ptr;                                           // point-major CSR
+  HostVec<int> pt_obs;
   std::vector<int> chunk_frame, chunk_beg, chunk_cnt, frame_chunk_ptr;   // frame chunks of <= 128 observations
   int T = 0;                                                         // Cholesky tiles per dimension
   int n_inc = 0;
-  std::vector<int> inc_point, inc_tile, slot_beg, pt_inc_ptr, cam_inc;
-  std::vector<unsigned char> slot_cnt, inc_half;
-  std::vector<int> obs_phi_off, dup_inc;
+  HostVec<int> inc_point, inc_tile, slot_beg;
+  std::vector<int> pt_inc_ptr, cam_inc;
+  HostVec<unsigned char> slot_cnt;
+  std::vector<unsigned char> inc_half;
+  HostVec<int> obs_phi_off;
+  std::vector<int> dup_inc;
   std::vector<int> pair_a, pair_b, pair_item_ptr;
   std::vector<int4> items;
-  std::vector<int2> entries;
+  HostVec<int2> entries;
   int n_items = 0;
   TilePlan plan;
   std::vector<int> fwd_slot;   // where each trsm tile (i, k) leaves its forward-substitution term in row i's list

@@ -223,6 +223,26 @@ def test_structure_sparse_key_path_is_identical():
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("free_cam", [False, True])
+def test_structure_is_independent_of_the_host_thread_count(free_cam, monkeypatch):
+    # the analysis runs on a few host threads (contiguous point ranges); entries of a (pair, class) must stay in
+    # point order whatever the count -- the GPU summation order, hence bit reproducibility, depends on it
+    F, P = 57, 900
+    fr, pt, cp = ragged_topology(11, F, P, max_track=12)
+    priors = [(f, f - 1) for f in range(1, F)]
+    monkeypatch.setenv("RSBA_CUDA_HOST_THREADS", "1")
+    ref = check_structure(fr, pt, F, P, cp, free_cam=free_cam, free_ratio=True, priors=priors)
+    for n in (2, 3, 8, 13):
+        monkeypatch.setenv("RSBA_CUDA_HOST_THREADS", str(n))
+        got = api.analyze_structure(fr, pt, F, P, cp, free_cam, True, [a for a, _ in priors], [b for _, b in priors])
+        for k in ref:
+            assert np.array_equal(ref[k], got[k]), (n, k)
+    # more threads than points, and threads whose point range is empty
+    monkeypatch.setenv("RSBA_CUDA_HOST_THREADS", "16")
+    fr2, pt2, cp2 = ragged_topology(12, 9, 5)
+    check_structure(fr2, pt2, 9, 5, cp2, free_cam=free_cam)
+
+
 def test_structure_empty_and_all_constant():
     st = api.analyze_structure(np.zeros(0, np.int32), np.zeros(0, np.int32), 5, 3)
     assert st["n_inc"] == 0 and st["n_items"] == 0 and st["pair_a"].size == 2      # the diagonal sub-tiles
