@@ -250,6 +250,12 @@ int rsba_cuda_device_buffers(rsba_problem* h, void** residuals, void** jacobian,
  * query the count). */
 long rsba_cuda_observation_order(rsba_problem* h, long* order);
 
+/* Host only, needs no device: the order above for a given observation list -- a STABLE sort by frame, which
+ * keeps the caller's within-frame order (the reference's insertion order, CeresHandler.h:208-255).  Returns
+ * n_obs, or -1 (index out of range; message in rsba_cuda_last_error).  order may be NULL (validation only). */
+long rsba_cuda_sort_observations(long n_obs, const int* obs_frame, const int* obs_point, int n_frames, int n_points,
+                                 long* order);
+
 /* ------------------------------------------------------------------ solve */
 /* Replaces: ceres::Solve(options, &problem, &summary) with linear_solver_type = SPARSE_SCHUR
  * (CeresHandler.h:403,419): Levenberg-Marquardt trust region; point blocks eliminated by a

@@ -45,7 +45,7 @@ SYMBOLS = [
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_reproject", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
     "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_analyze_structure", "rsba_cuda_structure_array",
-    "rsba_cuda_structure_free", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
+    "rsba_cuda_structure_free", "rsba_cuda_sort_observations", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
 
@@ -173,6 +173,8 @@ def load_library():
     lib.rsba_cuda_structure_array.restype = C.c_long
     lib.rsba_cuda_structure_free.argtypes = [vp]
     lib.rsba_cuda_structure_free.restype = None
+    lib.rsba_cuda_sort_observations.argtypes = [C.c_long, vp, vp, C.c_int, C.c_int, vp]
+    lib.rsba_cuda_sort_observations.restype = C.c_long
     lib.rsba_cuda_pnp_batch.argtypes = [vp, _dp, C.c_int, _ip, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp,
                                         C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp]
     lib.rsba_cuda_nccl_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
@@ -629,6 +631,18 @@ def analyze_structure(obs_frame, obs_point, n_frames, n_points, const_point=None
         return out
     finally:
         lib.rsba_cuda_structure_free(handle)
+
+
+def sort_observations(obs_frame, obs_point, n_frames, n_points) -> np.ndarray:
+    """Host-only: sorted position -> caller's observation index (stable sort by frame), as the library
+    orders a scene internally."""
+    lib = load_library()
+    fr = np.ascontiguousarray(obs_frame, dtype=np.int32)
+    pt = np.ascontiguousarray(obs_point, dtype=np.int32)
+    order = np.zeros(fr.size, dtype=np.int64)
+    if lib.rsba_cuda_sort_observations(fr.size, _addr(fr), _addr(pt), int(n_frames), int(n_points), _addr(order)) < 0:
+        raise RsbaError(ERR_INVALID_ARGUMENT, lib.rsba_cuda_last_error().decode(errors="replace"))
+    return order
 
 
 def point_owners(scene, world_size: int) -> np.ndarray:

@@ -181,34 +181,47 @@ void compute_point_owners(int n_frames, int n_points, long n_obs, const int* obs
 
 int materialize_local_share(rsba_problem* h) {
   const long N = h->n_obs_global;
+  const HostThreads pool(N);
   h->point_owned.assign(h->n_points, 1);
-  h->local_ids.clear();
+  const double2* src_xy = h->g_obs_xy.data();   // what goes to the device: the whole scene on one GPU ...
+  HostVec<double2> sxy;                         // ... this rank's share otherwise
   if (h->world > 1) {
     std::vector<int> owner;
     compute_point_owners(h->n_frames, h->n_points, N, h->g_obs_frame.data(), h->g_obs_point.data(), h->world, &owner);
     for (int p = 0; p < h->n_points; ++p) h->point_owned[p] = owner[p] == h->rank;
+    h->local_ids.clear();
     for (long i = 0; i < N; ++i)
       if (h->point_owned[h->g_obs_point[i]]) h->local_ids.push_back(i);
+    const long n = (long)h->local_ids.size();
+    sxy.resize(n);
+    h->h_obs_frame.resize(n);
+    h->h_obs_point.resize(n);
+    pool.split(n, [&](int, long b, long e) {
+      for (long i = b; i < e; ++i) {
+        const long g = h->local_ids[i];
+        sxy[i] = h->g_obs_xy[g];
+        h->h_obs_frame[i] = h->g_obs_frame[g];
+        h->h_obs_point[i] = h->g_obs_point[g];
+      }
+    });
+    src_xy = sxy.data();
   } else {
     h->local_ids.resize(N);
-    std::iota(h->local_ids.begin(), h->local_ids.end(), 0L);
+    h->h_obs_frame.resize(N);
+    h->h_obs_point.resize(N);
+    pool.split(N, [&](int, long b, long e) {
+      for (long i = b; i < e; ++i) h->local_ids[i] = i;
+      std::copy(h->g_obs_frame.begin() + b, h->g_obs_frame.begin() + e, h->h_obs_frame.begin() + b);
+      std::copy(h->g_obs_point.begin() + b, h->g_obs_point.begin() + e, h->h_obs_point.begin() + b);
+    });
   }
   const long n = (long)h->local_ids.size();
-  std::vector<double2> sxy(n);
-  h->h_obs_frame.resize(n);
-  h->h_obs_point.resize(n);
-  for (long i = 0; i < n; ++i) {
-    const long g = h->local_ids[i];
-    sxy[i] = h->g_obs_xy[g];
-    h->h_obs_frame[i] = h->g_obs_frame[g];
-    h->h_obs_point[i] = h->g_obs_point[g];
-  }
   h->n_obs = n;
   RSBA_CUDA_TRY(h->d_obs_xy.resize(n));
   RSBA_CUDA_TRY(h->d_obs_frame.resize(n));
   RSBA_CUDA_TRY(h->d_obs_point.resize(n));
   if (n > 0) {
-    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_xy.ptr, sxy.data(), n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_xy.ptr, src_xy, n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_frame.ptr, h->h_obs_frame.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     RSBA_CUDA_TRY(cudaMemcpyAsync(h->d_obs_point.ptr, h->h_obs_point.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   }
@@ -220,29 +233,47 @@ int materialize_local_share(rsba_problem* h) {
   return RSBA_OK;
 }
 
-// Sort observations by frame (stable: keeps the caller's within-frame order, which is the
-// reference's insertion order, CeresHandler.h:208) and upload this rank's share of the SoA.
+// order[i] = the caller's index of the i-th observation after a STABLE sort by frame (keeps the caller's
+// within-frame order, which is the reference's insertion order, CeresHandler.h:208).  Host only.
+static int sort_by_frame(const HostThreads& pool, long n, const int* fr, const int* pt, int n_frames, int n_points,
+                         HostVec<long>* order) {
+  // range check and "already sorted by frame" in one parallel pass (bit 0: index out of range, bit 1: unsorted)
+  std::vector<int> flags(pool.n, 0);
+  pool.split(n, [&](int t, long b, long e) {
+    int f = 0;
+    for (long i = b; i < e; ++i) {
+      if (fr[i] < 0 || fr[i] >= n_frames || pt[i] < 0 || pt[i] >= n_points) f |= 1;
+      if (i > 0 && fr[i - 1] > fr[i]) f |= 2;
+    }
+    flags[t] = f;
+  });
+  int flag = 0;
+  for (int f : flags) flag |= f;
+  if (flag & 1) return fail(RSBA_ERR_INVALID_ARGUMENT, "observation index out of range");
+  order->resize(n);
+  long* o = order->data();
+  pool.split(n, [&](int, long b, long e) { for (long i = b; i < e; ++i) o[i] = i; });
+  if (flag & 2) std::stable_sort(order->begin(), order->end(), [&](long a, long b) { return fr[a] < fr[b]; });
+  return RSBA_OK;
+}
+
+// Sort observations by frame and upload this rank's share of the SoA.
 static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr, const int* pt,
                         int n_frames, int n_points) {
-  for (long i = 0; i < n; ++i) {
-    if (fr[i] < 0 || fr[i] >= n_frames || pt[i] < 0 || pt[i] >= n_points)
-      return fail(RSBA_ERR_INVALID_ARGUMENT, "observation index out of range");
-  }
-  h->order.resize(n);
-  std::iota(h->order.begin(), h->order.end(), 0L);
-  bool sorted = true;
-  for (long i = 1; i < n && sorted; ++i) sorted = fr[i - 1] <= fr[i];
-  if (!sorted)
-    std::stable_sort(h->order.begin(), h->order.end(), [&](long a, long b) { return fr[a] < fr[b]; });
+  const HostThreads pool(n);
+  int rc0 = sort_by_frame(pool, n, fr, pt, n_frames, n_points, &h->order);
+  if (rc0) return rc0;
   h->g_obs_xy.resize(n);
   h->g_obs_frame.resize(n);
   h->g_obs_point.resize(n);
-  for (long i = 0; i < n; ++i) {
-    const long s = h->order[i];
-    h->g_obs_xy[i] = make_double2(xy[2 * s], xy[2 * s + 1]);
-    h->g_obs_frame[i] = fr[s];
-    h->g_obs_point[i] = pt[s];
-  }
+  pool.split(n, [&](int, long b, long e) {
+    for (long i = b; i < e; ++i) {
+      const long s = h->order[i];
+      h->g_obs_xy[i] = make_double2(xy[2 * s], xy[2 * s + 1]);
+      h->g_obs_frame[i] = fr[s];
+      h->g_obs_point[i] = pt[s];
+    }
+  });
   h->n_obs_global = n;
   h->n_frames = n_frames;
   h->n_points = n_points;
@@ -509,6 +540,18 @@ int rsba_cuda_point_owners(int n_frames, int n_points, long n_obs, const int* ob
   compute_point_owners(n_frames, n_points, n_obs, obs_frame, obs_point, world_size, &o);
   std::copy(o.begin(), o.end(), owner);
   return RSBA_OK;
+}
+
+long rsba_cuda_sort_observations(long n_obs, const int* obs_frame, const int* obs_point, int n_frames, int n_points,
+                                 long* order) {
+  if (n_obs < 0 || n_frames < 0 || n_points < 0 || (n_obs > 0 && (!obs_frame || !obs_point))) {
+    fail(RSBA_ERR_INVALID_ARGUMENT, "bad arguments");
+    return -1;
+  }
+  HostVec<long> o;
+  if (sort_by_frame(HostThreads(n_obs), n_obs, obs_frame, obs_point, n_frames, n_points, &o)) return -1;
+  if (order) std::copy(o.begin(), o.end(), order);
+  return n_obs;
 }
 
 int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigned char id[128]) {

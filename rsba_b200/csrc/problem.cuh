@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "host_threads.h"
 #include "../../include/rsba_cuda.h"
 
 namespace rsba {
@@ -83,11 +84,11 @@ struct rsba_problem {
   // the rank owns (point-owner rule)
   long n_obs = 0, n_obs_global = 0;
   int n_frames = 0, n_points = 0;
-  std::vector<long> order;                 // sorted global position -> caller's observation index
-  std::vector<double2> g_obs_xy;
-  std::vector<int> g_obs_frame, g_obs_point;
-  std::vector<long> local_ids;             // local observation -> sorted global position
-  std::vector<int> h_obs_frame, h_obs_point;  // local share, host copy (structure analysis)
+  rsba::HostVec<long> order;               // sorted global position -> caller's observation index
+  rsba::HostVec<double2> g_obs_xy;
+  rsba::HostVec<int> g_obs_frame, g_obs_point;
+  rsba::HostVec<long> local_ids;           // local observation -> sorted global position
+  rsba::HostVec<int> h_obs_frame, h_obs_point;  // local share, host copy (structure analysis)
   std::vector<unsigned char> point_owned;  // [points] 1 if this rank eliminates the point
   std::vector<unsigned short> pose_mask;   // [frames] constant-scalar bits
   std::vector<unsigned char> point_const;  // [points]

@@ -6,7 +6,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <thread>
 
 #include "../../include/rsba_cuda.h"
 
@@ -15,35 +14,6 @@ namespace rsba {
 void set_last_error(const std::string& msg);   // problem.cu
 
 namespace {
-
-// A handful of host threads for the one-off analysis (std::thread per phase: the phases take milliseconds each).
-// RSBA_CUDA_HOST_THREADS overrides the count; small scenes run on the calling thread alone.
-struct HostThreads {
-  int n = 1;
-  explicit HostThreads(long work) {
-    int want = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-    if (const char* e = getenv("RSBA_CUDA_HOST_THREADS")) want = std::max(1, std::min(64, atoi(e)));
-    else if (work < 100000) want = 1;
-    n = want;
-  }
-  template <typename Fn>
-  void run(Fn&& fn) const {
-    if (n == 1) { fn(0); return; }
-    std::vector<std::thread> th;
-    th.reserve(n - 1);
-    for (int t = 1; t < n; ++t) th.emplace_back([&fn, t] { fn(t); });
-    fn(0);
-    for (auto& x : th) x.join();
-  }
-  // v.resize(n) without a serial fill, then every thread writes `value` over its share
-  template <typename Vec, typename T>
-  void resize_fill(Vec& v, size_t count, T value) const {
-    v.resize(count);
-    auto* d = v.data();
-    const int nt = n;
-    run([&](int t) { std::fill(d + count * t / nt, d + count * (t + 1) / nt, value); });
-  }
-};
 
 int fail(std::string* error, int code, const char* msg) {
   if (error) *error = msg;

@@ -6,12 +6,11 @@
 // device state, so `rsba_cuda_analyze_structure` (include/rsba_cuda.h) and the CPU tests can run it
 // without a GPU.
 #pragma once
-#include <memory>
 #include <string>
-#include <type_traits>
 #include <utility>
 #include <vector>
 
+#include "host_threads.h"
 #include "lm.cuh"
 
 namespace rsba {
@@ -34,19 +33,6 @@ struct SceneTopology {
   bool dense = false, reorder = true, sparse_keys = false;
   int n_cam_frames() const { return n_frames + ((free_cam || free_ratio) ? 1 : 0); }
 };
-
-// std::vector whose resize() leaves trivially constructible elements uninitialised: the big arrays below are
-// written exactly once by the analysis' threads, and a serial zero fill of 20-45 MB each would cost as much as
-// the phase that fills them.
-template <typename T>
-struct DefaultInitAllocator : std::allocator<T> {
-  template <typename U> struct rebind { using other = DefaultInitAllocator<U>; };
-  using std::allocator<T>::allocator;
-  template <typename U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
-  template <typename U, typename... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
-};
-template <typename T>
-using HostVec = std::vector<T, DefaultInitAllocator<T>>;
 
 struct HostStructure {
   std::vector<int> pt_ptr;                                           // point-major CSR

@@ -259,3 +259,28 @@ def test_structure_argument_checks():
         api.analyze_structure(np.array([0, 5], np.int32), np.zeros(2, np.int32), 2, 1)   # frame out of range
     with pytest.raises(api.RsbaError):
         api.analyze_structure(np.zeros(300, np.int32), np.zeros(300, np.int32), 1, 1)    # > 255 in one frame
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_scene_intake_is_a_stable_sort_by_frame(threads, monkeypatch):
+    # CeresHandler::Add inserts frame-major (CeresHandler.h:208-255); whatever order the caller uses, the library
+    # keeps the caller's order inside a frame
+    monkeypatch.setenv("RSBA_CUDA_HOST_THREADS", threads)
+    rng = np.random.default_rng(5)
+    fr = rng.integers(0, 13, size=4000).astype(np.int32)
+    pt = rng.integers(0, 50, size=4000).astype(np.int32)
+    order = api.sort_observations(fr, pt, 13, 50)
+    assert np.array_equal(order, np.argsort(fr, kind="stable"))
+    srt = np.sort(fr)
+    assert np.array_equal(api.sort_observations(srt, pt, 13, 50), np.arange(4000))      # sorted input: identity
+    # a single inversion, at a thread border or anywhere else, is seen
+    for at in (1, 799, 800, 801, 3999):
+        f2 = srt.copy()
+        f2[at - 1], f2[at] = 12, 0
+        assert np.array_equal(api.sort_observations(f2, pt, 13, 50), np.argsort(f2, kind="stable")), at
+    assert api.sort_observations(np.zeros(0, np.int32), np.zeros(0, np.int32), 3, 3).size == 0
+    for bad_fr, bad_pt in ((13, 0), (-1, 0), (0, 50), (0, -1)):
+        f2, p2 = fr.copy(), pt.copy()
+        f2[3999], p2[3999] = bad_fr, bad_pt
+        with pytest.raises(api.RsbaError):
+            api.sort_observations(f2, p2, 13, 50)
