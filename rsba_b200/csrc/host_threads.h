@@ -16,8 +16,9 @@ namespace rsba {
 
 struct HostThreads {
   int n = 1;
-  explicit HostThreads(long work) {
-    int want = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  // sharers: processes that do the same work at the same time on this host (the ranks of a multi-GPU run)
+  explicit HostThreads(long work, int sharers = 1) {
+    int want = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)std::max(1, sharers)));
     if (const char* e = getenv("RSBA_CUDA_HOST_THREADS")) want = std::max(1, std::min(64, atoi(e)));
     else if (work < 100000) want = 1;
     n = want;

@@ -181,7 +181,7 @@ void compute_point_owners(int n_frames, int n_points, long n_obs, const int* obs
 
 int materialize_local_share(rsba_problem* h) {
   const long N = h->n_obs_global;
-  const HostThreads pool(N);
+  const HostThreads pool(N, h->world);
   h->point_owned.assign(h->n_points, 1);
   const double2* src_xy = h->g_obs_xy.data();   // what goes to the device: the whole scene on one GPU ...
   HostVec<double2> sxy;                         // ... this rank's share otherwise
@@ -260,7 +260,7 @@ static int sort_by_frame(const HostThreads& pool, long n, const int* fr, const i
 // Sort observations by frame and upload this rank's share of the SoA.
 static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr, const int* pt,
                         int n_frames, int n_points) {
-  const HostThreads pool(n);
+  const HostThreads pool(n, h->world);
   int rc0 = sort_by_frame(pool, n, fr, pt, n_frames, n_points, &h->order);
   if (rc0) return rc0;
   h->g_obs_xy.resize(n);

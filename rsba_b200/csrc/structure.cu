@@ -34,7 +34,7 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
   if (F > 65536) return fail(error, RSBA_ERR_INVALID_ARGUMENT, "more than 65536 frames: the tile index (T x T) would not fit; shard the sequence");
   if (N > 2147483647L) return fail(error, RSBA_ERR_INVALID_ARGUMENT, "more than 2^31 observations on one GPU: shard the scene over more GPUs");
 
-  HostThreads pool(N);
+  HostThreads pool(N, sc.world);
 
   // point-major CSR by a stable parallel counting sort (observation order inside a point stays frame order):
   // every thread histograms a contiguous range of observations, the per-(thread, point) start offsets follow from a
