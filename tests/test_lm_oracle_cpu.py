@@ -13,7 +13,7 @@ import scipy.sparse as sp
 
 import oracle
 from oracle import lm_oracle
-from helpers import small_scene
+from helpers import damped_normal_equation_residual, small_scene
 from rsba_b200.scene import make_scene
 
 
@@ -100,3 +100,23 @@ def test_lm_loop_reaches_the_minimum_third_party_solvers_find():
     # the reference's options (function tolerance 1e-6, CeresHandler.h:394-419) stop within 1e-5 of that minimum
     _, _, dflt = lm_oracle.solve(sc, lambda po, pt, jac: oracle.evaluate(sc, po, pt, jac=jac), lm_oracle.Options())
     assert "CONVERGENCE" in dflt.termination and 0.0 <= dflt.final_cost - summ.final_cost <= 1e-5 * summ.final_cost
+
+
+def test_matrix_free_normal_equation_check_used_at_full_size():
+    # the property the GPU test at C3 relies on (tests/test_gpu_zz_full_size.py), here at C2 with the C++ restatement
+    # as the solver: it holds to rounding for a correct step and sees a single point's step off by 0.1 %
+    from oracle import cpu_lm
+    from rsba_b200.scene import make_config
+    sc = make_config("C2")
+    r, J, valid = oracle.evaluate(sc)
+    assert valid.all()
+    st = cpu_lm.CpuLm(sc).step(J, r, 1e4, compute_scale=True)
+    rel, mcc, comp = damped_normal_equation_residual(sc, r, J, st["delta_poses"], st["delta_points"], 1e4)
+    assert rel <= 1e-12 and comp <= 1e-12 and abs(mcc - st["model_cost_change"]) <= 1e-12 * mcc
+    bad = st["delta_points"].copy()
+    bad[12345] *= 1.001
+    rel, _, comp = damped_normal_equation_residual(sc, r, J, st["delta_poses"], bad, 1e4)
+    assert rel >= 2e-6 and comp >= 1e-4
+    bad = st["delta_poses"].copy()
+    bad[57, 4] *= 1.001
+    assert damped_normal_equation_residual(sc, r, J, bad, st["delta_points"], 1e4)[2] >= 2e-6
