@@ -300,6 +300,9 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
  *   const_point [n_points] or NULL; free_intrinsics / free_ratio: the pseudo-frame behind the real frames
  *   prior_frame / prior_prev [n_priors]: the (frame, previous frame) couplings of the motion priors
  *   dense / reorder: as rsba_solve_options.dense_cholesky / reorder_tiles; sparse_keys: force the sorted-key path
+ *   rank / world_size: world_size > 1 analyses the share that rank keeps of the scene (all observations of the
+ *     points it owns, rsba_cuda_point_owners); the tile plan is derived from the whole scene on every rank.  Extra
+ *     arrays then: local_ids (long: the rank's observations as positions in the given list), point_owned (bytes)
  * The result is an opaque object; rsba_cuda_structure_array returns the element count of the named array (or -1)
  * and, through data / elem_bytes, a pointer into the object (valid until rsba_cuda_structure_free).  Names:
  *   pt_ptr pt_obs chunk_frame chunk_beg chunk_cnt frame_chunk_ptr inc_point inc_tile slot_beg slot_cnt pt_inc_ptr
@@ -310,7 +313,7 @@ typedef struct rsba_structure rsba_structure;
 int rsba_cuda_analyze_structure(long n_obs, const int* obs_frame, const int* obs_point, int n_frames, int n_points,
                                 const unsigned char* const_point, int free_intrinsics, int free_ratio, int n_priors,
                                 const int* prior_frame, const int* prior_prev, int dense, int reorder,
-                                int sparse_keys, rsba_structure** out);
+                                int sparse_keys, int rank, int world_size, rsba_structure** out);
 long rsba_cuda_structure_array(const rsba_structure* s, const char* name, const void** data, int* elem_bytes);
 void rsba_cuda_structure_free(rsba_structure* s);
 

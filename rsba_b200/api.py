@@ -168,7 +168,7 @@ def load_library():
     lib.rsba_cuda_linearize_and_step.argtypes = [vp, C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp, _dp]
     lib.rsba_cuda_plan_reduced_system.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp] + [vp] * 9
     lib.rsba_cuda_analyze_structure.argtypes = [C.c_long, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp,
-                                                C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+                                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.rsba_cuda_structure_array.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     lib.rsba_cuda_structure_array.restype = C.c_long
     lib.rsba_cuda_structure_free.argtypes = [vp]
@@ -588,14 +588,16 @@ _STRUCTURE_ARRAYS = {
     "plan.nz_tiles": (np.int32, 2), "plan.tile_slot": (np.int32, 1), "plan.panels": (np.int32, 1),
     "plan.panel_ptr": (np.int32, 1), "plan.trsm": (np.int32, 2), "plan.trsm_ptr": (np.int32, 1),
     "plan.upd": (np.int32, 4), "plan.lrow_ptr": (np.int32, 1), "plan.lrow_cols": (np.int32, 1),
+    "local_ids": (np.int64, 1), "point_owned": (np.uint8, 1),
 }
 
 
 def analyze_structure(obs_frame, obs_point, n_frames, n_points, const_point=None, free_intrinsics=False,
-                      free_ratio=False, prior_frame=(), prior_prev=(), dense=False, reorder=True, sparse_keys=False):
+                      free_ratio=False, prior_frame=(), prior_prev=(), dense=False, reorder=True, sparse_keys=False,
+                      rank=0, world_size=1):
     """Host-only: the one-off structure analysis of rsba_cuda_solve (point CSR, frame chunks, Schur incidences,
     sub-tile pairs, work items and entry lists, tile plan) as a dict of numpy arrays.  No GPU needed.
-    Observations must be sorted by frame."""
+    Observations must be sorted by frame.  ``world_size`` > 1: the share of ``rank`` (multi-GPU sharding)."""
     lib = load_library()
     fr = np.ascontiguousarray(obs_frame, dtype=np.int32)
     pt = np.ascontiguousarray(obs_point, dtype=np.int32)
@@ -605,7 +607,8 @@ def analyze_structure(obs_frame, obs_point, n_frames, n_points, const_point=None
     handle = C.c_void_p()
     rc = lib.rsba_cuda_analyze_structure(fr.size, _addr(fr), _addr(pt), int(n_frames), int(n_points), _addr(cp),
                                          int(free_intrinsics), int(free_ratio), int(pf.size), _addr(pf), _addr(pp),
-                                         int(dense), int(reorder), int(sparse_keys), C.byref(handle))
+                                         int(dense), int(reorder), int(sparse_keys), int(rank), int(world_size),
+                                         C.byref(handle))
     if rc != RSBA_OK:
         raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
     try:

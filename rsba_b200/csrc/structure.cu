@@ -12,6 +12,8 @@
 namespace rsba {
 
 void set_last_error(const std::string& msg);   // problem.cu
+void compute_point_owners(int n_frames, int n_points, long n_obs, const int* obs_frame_sorted, const int* obs_point,
+                          int world, std::vector<int>* owner);   // problem.cu
 
 namespace {
 
@@ -384,6 +386,10 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
 // ------------------------------------------------------------------ device-free C ABI (include/rsba_cuda.h)
 struct rsba_structure {
   rsba::HostStructure hs;
+  // multi-GPU shard (world_size > 1): the rank's observations (positions in the caller's sorted list)
+  std::vector<long> local_ids;
+  std::vector<int> local_frame, local_point;
+  std::vector<unsigned char> point_owned;
 };
 
 extern "C" {
@@ -391,13 +397,13 @@ extern "C" {
 int rsba_cuda_analyze_structure(long n_obs, const int* obs_frame, const int* obs_point, int n_frames, int n_points,
                                 const unsigned char* const_point, int free_intrinsics, int free_ratio, int n_priors,
                                 const int* prior_frame, const int* prior_prev, int dense, int reorder,
-                                int sparse_keys, rsba_structure** out) {
+                                int sparse_keys, int rank, int world_size, rsba_structure** out) {
   using namespace rsba;
   auto bad = [](const char* msg) { set_last_error(msg); return (int)RSBA_ERR_INVALID_ARGUMENT; };
   if (!out) return bad("out is NULL");
   *out = nullptr;
   if (n_obs < 0 || n_frames < 0 || n_points < 0 || n_priors < 0 || (n_obs > 0 && (!obs_frame || !obs_point)) ||
-      (n_priors > 0 && (!prior_frame || !prior_prev)))
+      (n_priors > 0 && (!prior_frame || !prior_prev)) || world_size < 1 || rank < 0 || rank >= world_size)
     return bad("bad arguments");
   for (long i = 0; i < n_obs; ++i) {
     if (obs_frame[i] < 0 || obs_frame[i] >= n_frames || obs_point[i] < 0 || obs_point[i] >= n_points)
@@ -419,6 +425,25 @@ int rsba_cuda_analyze_structure(long n_obs, const int* obs_frame, const int* obs
   sc.n_obs_global = n_obs; sc.g_obs_frame = obs_frame; sc.g_obs_point = obs_point;
   sc.dense = dense != 0; sc.reorder = reorder != 0; sc.sparse_keys = sparse_keys != 0;
   rsba_structure* s = new rsba_structure;
+  if (world_size > 1) {
+    // this rank's share as materialize_local_share (problem.cu) forms it: all observations of the points it owns
+    std::vector<int> owner;
+    compute_point_owners(n_frames, n_points, n_obs, obs_frame, obs_point, world_size, &owner);
+    s->point_owned.resize(n_points);
+    for (int p = 0; p < n_points; ++p) s->point_owned[p] = owner[p] == rank;
+    for (long i = 0; i < n_obs; ++i)
+      if (s->point_owned[obs_point[i]]) {
+        s->local_ids.push_back(i);
+        s->local_frame.push_back(obs_frame[i]);
+        s->local_point.push_back(obs_point[i]);
+      }
+    sc.world = world_size;
+    sc.n_obs = (long)s->local_ids.size();
+    sc.obs_frame = s->local_frame.data();
+    sc.obs_point = s->local_point.data();
+  } else {
+    s->point_owned.assign(n_points, 1);
+  }
   std::string err;
   // RSBA_CUDA_TRACE=1: wall-clock of each phase, to stderr (as rsba_cuda_solve prints it)
   auto t_prev = std::chrono::steady_clock::now();
@@ -458,6 +483,8 @@ long rsba_cuda_structure_array(const rsba_structure* s, const char* name, const 
   RSBA_PLAN(tile_pos); RSBA_PLAN(pos_tile); RSBA_PLAN(nz_tiles); RSBA_PLAN(tile_slot); RSBA_PLAN(panels);
   RSBA_PLAN(panel_ptr); RSBA_PLAN(trsm); RSBA_PLAN(trsm_ptr); RSBA_PLAN(upd); RSBA_PLAN(lrow_ptr); RSBA_PLAN(lrow_cols);
 #undef RSBA_PLAN
+  if (n == "local_ids") return give(s->local_ids);
+  if (n == "point_owned") return give(s->point_owned);
   if (n == "T" || n == "n_inc" || n == "n_items") {   // scalars come back as the count
     if (data) *data = nullptr;
     if (elem_bytes) *elem_bytes = 0;

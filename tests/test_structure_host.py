@@ -34,6 +34,47 @@ def ragged_topology(seed, F, P, const_frac=0.1, dup_frac=0.05, max_track=9):
     return fr[order], pt[order], const_point
 
 
+def execute_work_lists(st, Phi):
+    """The Schur work lists executed the way schur_syrk_kernel + schur_reduce do: {(a, b): 48 x 48 block}, summing
+    the items of each pair; patches the kernel skips (half masks) are skipped here too.  Also checks the lists' own
+    invariants.  Returns (blocks, number of non-padding entries, total entries)."""
+    n_inc = st["n_inc"]
+    ip, it = st["inc_point"], st["inc_tile"]
+    pa, pb, pitem, items, entries = st["pair_a"], st["pair_b"], st["pair_item_ptr"], st["items"], st["entries"]
+    H = 2 * st["T"]
+    assert np.all(pa <= pb) and np.all(pb < H)
+    keys = pa.astype(np.int64) * H + pb
+    assert np.all(np.diff(keys) > 0), "pairs sorted by (a, b), no repeats"
+    assert pitem.size == pa.size + 1 and pitem[-1] == st["n_items"]
+    blocks = {}
+    n_real_entries = 0
+    pos = 0
+    for q in range(pa.size):
+        acc = np.zeros((SUB * FP, SUB * FP))
+        diag = pa[q] == pb[q]
+        for j in range(pitem[q], pitem[q + 1]):
+            iq, beg, cnt, w = (int(v) for v in items[j])
+            assert iq == q and beg == pos and cnt % 8 == 0 and 0 < cnt <= SEG
+            pos += cnt
+            assert (w & 1) == int(diag)
+            ma, mb = ((w >> 4) & 3, (w >> 8) & 3) if not diag else (3, 3)
+            rows_b = np.concatenate([np.arange(24) + 24 * hb for hb in range(2) if mb >> hb & 1])
+            rows_a = np.concatenate([np.arange(24) + 24 * ha for ha in range(2) if ma >> ha & 1])
+            for e in range(beg, beg + cnt):
+                y, x = (int(v) for v in entries[e])
+                if y == n_inc:
+                    assert x == n_inc                  # padding: the all-zero panel
+                    continue
+                n_real_entries += 1
+                assert it[x] == pa[q] and it[y] == pb[q] and ip[x] == ip[y]
+                # the kernel only computes the patches of populated halves: what it skips must be zero
+                part = np.zeros_like(acc)
+                part[np.ix_(rows_b, rows_a)] = Phi[y][rows_b] @ Phi[x][rows_a].T
+                acc += part
+        blocks[(int(pa[q]), int(pb[q]))] = acc
+    return blocks, n_real_entries, pos
+
+
 def check_structure(fr, pt, F, P, const_point=None, free_cam=False, free_ratio=False, priors=(), seed=0, **kw):
     const_point = np.zeros(P, np.uint8) if const_point is None else const_point
     pf = [a for a, _ in priors]
@@ -121,39 +162,13 @@ def check_structure(fr, pt, F, P, const_point=None, free_cam=False, free_ratio=F
                 direct[key] = direct.get(key, 0) + Phi[y] @ Phi[x].T
 
     # ---- execute the work lists the way schur_syrk_kernel + schur_reduce do
-    pa, pb, pitem, items, entries = st["pair_a"], st["pair_b"], st["pair_item_ptr"], st["items"], st["entries"]
-    assert np.all(pa <= pb) and np.all(pb < H)
-    keys = pa.astype(np.int64) * H + pb
-    assert np.all(np.diff(keys) > 0), "pairs sorted by (a, b), no repeats"
-    assert pitem.size == pa.size + 1 and pitem[-1] == st["n_items"]
-    n_real_entries = 0
-    pos = 0
-    for q in range(pa.size):
-        acc = np.zeros((SUB * FP, SUB * FP))
-        diag = pa[q] == pb[q]
-        for j in range(pitem[q], pitem[q + 1]):
-            iq, beg, cnt, w = (int(v) for v in items[j])
-            assert iq == q and beg == pos and cnt % 8 == 0 and 0 < cnt <= SEG
-            pos += cnt
-            assert (w & 1) == int(diag)
-            ma, mb = ((w >> 4) & 3, (w >> 8) & 3) if not diag else (3, 3)
-            rows_b = np.concatenate([np.arange(24) + 24 * hb for hb in range(2) if mb >> hb & 1])
-            rows_a = np.concatenate([np.arange(24) + 24 * ha for ha in range(2) if ma >> ha & 1])
-            for e in range(beg, beg + cnt):
-                y, x = (int(v) for v in entries[e])
-                if y == n_inc:
-                    assert x == n_inc                  # padding: the all-zero panel
-                    continue
-                n_real_entries += 1
-                assert it[x] == pa[q] and it[y] == pb[q] and ip[x] == ip[y]
-                # the kernel only computes the patches of populated halves: what it skips must be zero
-                part = np.zeros_like(acc)
-                part[np.ix_(rows_b, rows_a)] = Phi[y][rows_b] @ Phi[x][rows_a].T
-                acc += part
-        want = direct.pop((int(pa[q]), int(pb[q])), np.zeros_like(acc))
-        if diag:   # the kernel produces the lower triangle of a diagonal pair only
+    pa, pb, entries = st["pair_a"], st["pair_b"], st["entries"]
+    blocks, n_real_entries, pos = execute_work_lists(st, Phi)
+    for (a, b), acc in blocks.items():
+        want = direct.pop((a, b), np.zeros_like(acc))
+        if a == b:   # the kernel produces the lower triangle of a diagonal pair only
             acc, want = np.tril(acc), np.tril(want)
-        assert np.allclose(acc, want, rtol=1e-12, atol=1e-12), (q, pa[q], pb[q])
+        assert np.allclose(acc, want, rtol=1e-12, atol=1e-12), (a, b)
     assert not direct, f"pairs with Schur terms but no work items: {list(direct)[:5]}"
     assert n_real_entries == sum((pip[p + 1] - pip[p]) * (pip[p + 1] - pip[p] + 1) // 2 for p in range(P))
     assert entries.shape[0] == max(pos, 1)
@@ -241,6 +256,58 @@ def test_structure_is_independent_of_the_host_thread_count(free_cam, monkeypatch
     monkeypatch.setenv("RSBA_CUDA_HOST_THREADS", "16")
     fr2, pt2, cp2 = ragged_topology(12, 9, 5)
     check_structure(fr2, pt2, 9, 5, cp2, free_cam=free_cam)
+
+
+@pytest.mark.parametrize("world,free_cam", [(2, False), (3, True)])
+def test_structure_of_a_multi_gpu_shard(world, free_cam):
+    # every rank keeps all observations of the points it owns: the ranks' work lists together must give the
+    # single-GPU Schur complement, and every rank must derive the SAME tile plan (it comes from the whole scene)
+    F, P = 45, 500
+    fr, pt, cp = ragged_topology(21, F, P, max_track=10)
+    priors = [(f, f - 1) for f in range(1, F)]
+    pf, pp = [a for a, _ in priors], [b for _, b in priors]
+    one = api.analyze_structure(fr, pt, F, P, cp, free_cam, False, pf, pp)
+    rng = np.random.default_rng(3)
+    panel = {}                                     # one random panel per (sub-tile, point), shared by all ranks
+
+    def panels_of(st):
+        Phi = np.zeros((st["n_inc"] + 1, SUB * FP, 3))
+        cam_slot = F % SUB
+        for i in range(st["n_inc"]):
+            key = (int(st["inc_tile"][i]), int(st["inc_point"][i]))
+            if key not in panel:
+                panel[key] = rng.standard_normal((SUB * FP, 3))
+            for fs in range(SUB):
+                if st["slot_cnt"][i, fs] or (free_cam and st["cam_inc"][st["inc_point"][i]] == i and fs == cam_slot):
+                    Phi[i, fs * FP:(fs + 1) * FP] = panel[key][fs * FP:(fs + 1) * FP]
+        return Phi
+
+    want, n_one, _ = execute_work_lists(one, panels_of(one))
+    total, n_sum, owned, seen_obs = {}, 0, np.zeros(P, int), np.zeros(fr.size, int)
+    owners = api.point_owners(type("S", (), dict(obs_frame=fr, obs_point=pt, num_frames=F, num_points=P))(), world)
+    for rank in range(world):
+        st = api.analyze_structure(fr, pt, F, P, cp, free_cam, False, pf, pp, rank=rank, world_size=world)
+        assert np.array_equal(st["point_owned"], owners == rank)
+        ids = st["local_ids"]
+        assert np.array_equal(ids, np.nonzero(owners[pt] == rank)[0])     # all observations of the rank's points
+        owned += st["point_owned"]
+        seen_obs[ids] += 1
+        for k in st:
+            if k.startswith("plan.") or k in ("T", "fwd_slot"):
+                assert np.array_equal(st[k], one[k]), (rank, k)
+        # the rank's lists refer to ITS observations: point CSR over the local list
+        assert np.array_equal(st["pt_obs"], np.argsort(pt[ids], kind="stable"))
+        blocks, n_real, _ = execute_work_lists(st, panels_of(st))
+        n_sum += n_real
+        for key, blk in blocks.items():
+            total[key] = total.get(key, 0) + blk
+    assert np.all(owned == 1) and np.all(seen_obs == 1) and n_sum == n_one
+    assert set(k for k, v in total.items() if np.any(v)) == set(k for k, v in want.items() if np.any(v))
+    for key, blk in want.items():
+        got = total.get(key, np.zeros_like(blk))
+        if key[0] == key[1]:
+            got, blk = np.tril(got), np.tril(blk)
+        assert np.allclose(got, blk, rtol=1e-12, atol=1e-12), key
 
 
 def test_structure_empty_and_all_constant():
