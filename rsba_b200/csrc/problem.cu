@@ -5,6 +5,9 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -27,6 +30,18 @@ static int fail(int code, const std::string& msg) {
   set_last_error(msg);
   return code;
 }
+
+// RSBA_CUDA_TRACE=1: wall-clock of the one-off host phases, to stderr (as lm_solver.cu prints the structure analysis)
+struct TraceLap {
+  const bool on = getenv("RSBA_CUDA_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point prev = std::chrono::steady_clock::now();
+  void operator()(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[rsba_cuda] scene:     %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - prev).count());
+    prev = now;
+  }
+};
 
 const NcclApi* nccl_api() {
   static NcclApi api;
@@ -261,8 +276,10 @@ static int sort_by_frame(const HostThreads& pool, long n, const int* fr, const i
 static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr, const int* pt,
                         int n_frames, int n_points) {
   const HostThreads pool(n, h->world);
+  TraceLap lap;
   int rc0 = sort_by_frame(pool, n, fr, pt, n_frames, n_points, &h->order);
   if (rc0) return rc0;
+  lap("check + sort by frame");
   h->g_obs_xy.resize(n);
   h->g_obs_frame.resize(n);
   h->g_obs_point.resize(n);
@@ -274,6 +291,7 @@ static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr
       h->g_obs_point[i] = pt[s];
     }
   });
+  lap("SoA copy");
   h->n_obs_global = n;
   h->n_frames = n_frames;
   h->n_points = n_points;
@@ -283,6 +301,7 @@ static int upload_scene(rsba_problem* h, long n, const double* xy, const int* fr
   RSBA_CUDA_TRY(h->d_points.resize((size_t)kPointParams * n_points));
   int rc = materialize_local_share(h);
   if (rc) return rc;
+  lap("local share + H2D");
   h->scene_set = true;
   h->params_set = false;
   return RSBA_OK;
