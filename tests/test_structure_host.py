@@ -351,3 +351,64 @@ def test_scene_intake_is_a_stable_sort_by_frame(threads, monkeypatch):
         f2[3999], p2[3999] = bad_fr, bad_pt
         with pytest.raises(api.RsbaError):
             api.sort_observations(f2, p2, 13, 50)
+
+
+def test_k2_algorithm_over_the_real_work_lists_gives_the_restated_reduced_system():
+    """K2 end to end on the CPU: the panels  F_i = Jc_i^T (Jx_i s_p) L^-T  (k2_normal.cu / k2_schur.cu header), summed
+    over the REAL work lists of the structure analysis, reduced as schur_reduce does and finalised as schur_finalize
+    does (camera Jacobi scaling + LM diagonal after the sum, identity rows for constant parameters), must be the reduced
+    camera system of the Ceres-style LM step restated in oracle/lm_oracle.py."""
+    import oracle
+    from oracle import lm_oracle
+    sc = small_scene()
+    F, P, radius = sc.num_frames, sc.num_points, 1e3
+    r, J, valid = oracle.evaluate(sc)
+    assert valid.all()
+    want = lm_oracle.lm_step(sc, r, J, radius)
+    fr, pt = sc.obs_frame, sc.obs_point
+    Jc = np.concatenate([J[:, :12].reshape(-1, 2, 6), J[:, 12:24].reshape(-1, 2, 6)], axis=2)       # [N, 2, 12]
+    Jx = J[:, 24:].reshape(-1, 2, 3)
+    free_c = np.repeat(~np.asarray(sc.const_frames, dtype=bool), 12).reshape(F, 12)
+    Jc = Jc * free_c[fr][:, None, :]                                   # constant camera parameters: zero columns
+    # unscaled blocks
+    B = np.zeros((F, 12, 12)); np.add.at(B, fr, np.einsum("nri,nrj->nij", Jc, Jc))
+    C = np.zeros((P, 3, 3)); np.add.at(C, pt, np.einsum("nri,nrj->nij", Jx, Jx))
+    gc = np.zeros((F, 12)); np.add.at(gc, fr, np.einsum("nri,nr->ni", Jc, r))
+    gp = np.zeros((P, 3)); np.add.at(gp, pt, np.einsum("nri,nr->ni", Jx, r))
+    diagB = np.einsum("fii->fi", B)
+    s_c = np.where(free_c, 1.0 / (1.0 + np.sqrt(diagB)), 1.0)
+    s_p = 1.0 / (1.0 + np.sqrt(np.einsum("pii->pi", C)))
+    # point side (point_invert): damped scaled block, its Cholesky factor, t_p = Cinv g_p
+    Cs = C * s_p[:, :, None] * s_p[:, None, :]
+    Cs = Cs + np.einsum("pi,ij->pij", np.clip(np.einsum("pii->pi", Cs), 1e-6, 1e32) / radius, np.eye(3))
+    Linv = np.linalg.inv(np.linalg.cholesky(Cs))                       # Minv
+    tp = np.einsum("pi,pij,pj->pi", s_p, np.linalg.inv(Cs), s_p * gp)  # s_p C'^-1 s_p g_p
+    # per-observation panel rows and the rhs correction w_f
+    Fi = np.einsum("nri,nrk,nk,nlk->nil", Jc, Jx, s_p[pt], Linv[pt])   # Jc^T (Jx s_p) L^-T   [N, 12, 3]
+    wf = np.zeros((F, 12)); np.add.at(wf, fr, np.einsum("nri,nrk,nk->ni", Jc, Jx, tp[pt]))
+    st = api.analyze_structure(fr, pt, F, P)
+    Phi = np.zeros((st["n_inc"] + 1, SUB * FP, 3))
+    for i in range(st["n_inc"]):
+        for fs in range(SUB):
+            b, c = st["slot_beg"][i, fs], st["slot_cnt"][i, fs]
+            for x in range(b, b + c):
+                Phi[i, fs * FP:(fs + 1) * FP] += Fi[st["pt_obs"][x]]
+    blocks, _, _ = execute_work_lists(st, Phi)
+    n = 12 * F
+    S = np.zeros((n + 48, n + 48))                                     # (room for the padding frames of the last sub-tile)
+    for (a, b), blk in blocks.items():
+        S[48 * b:48 * b + 48, 48 * a:48 * a + 48] = -blk if a != b else -np.tril(blk)
+    S = S[:n, :n]
+    S = np.tril(S) + np.tril(S, -1).T
+    for f in range(F):
+        S[12 * f:12 * f + 12, 12 * f:12 * f + 12] += B[f]
+    # finalize (after the all-reduce on several GPUs): camera scaling, LM diagonal, identity rows
+    sv, act = s_c.reshape(-1), free_c.reshape(-1)
+    S = S * sv[:, None] * sv[None, :]
+    S[np.diag_indices(n)] += np.clip(sv * diagB.reshape(-1) * sv, 1e-6, 1e32) / radius
+    S[~act, :] = 0.0
+    S[:, ~act] = 0.0
+    S[~act, ~act] = 1.0
+    rhs = np.where(act, sv * (gc - wf).reshape(-1), 0.0)
+    assert np.linalg.norm(S - want["S"]) <= 1e-11 * np.linalg.norm(want["S"])
+    assert np.linalg.norm(-rhs - want["rhs"]) <= 1e-11 * np.linalg.norm(want["rhs"])
