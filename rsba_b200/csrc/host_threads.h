@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <memory>
+#include <system_error>
 #include <thread>
 #include <type_traits>
 #include <utility>
@@ -29,8 +30,14 @@ struct HostThreads {
     if (n == 1) { fn(0); return; }
     std::vector<std::thread> th;
     th.reserve(n - 1);
-    for (int t = 1; t < n; ++t) th.emplace_back([&fn, t] { fn(t); });
+    int started = 1;
+    try {
+      for (int t = 1; t < n; ++t) { th.emplace_back([&fn, t] { fn(t); }); ++started; }
+    } catch (const std::system_error&) {
+      // no more threads to be had (pid / resource limit): the caller takes the remaining shares itself
+    }
     fn(0);
+    for (int t = started; t < n; ++t) fn(t);
     for (auto& x : th) x.join();
   }
   // fn(t, begin, end) over an even split of [0, count)
