@@ -36,7 +36,8 @@ enum {
   RSBA_ERR_STATE = -4,
   RSBA_ERR_EVALUATION_FAILED = -5, /* a functor returned false (mat/cam.h:410-412) */
   RSBA_ERR_LINEAR_SOLVER = -6,     /* reduced camera matrix not positive definite */
-  RSBA_ERR_NCCL = -7
+  RSBA_ERR_NCCL = -7,
+  RSBA_ERR_INTERNAL = -8           /* a C++ exception of the host code (e.g. out of host memory), caught at the boundary */
 };
 
 /* Solver::Options as used by CeresHandler::solve (CeresHandler.h:394-419) and

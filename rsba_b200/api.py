@@ -30,7 +30,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "librsba_cuda.so")
 
 RSBA_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = -1, -2, -3, -4
-ERR_EVALUATION_FAILED, ERR_LINEAR_SOLVER, ERR_NCCL = -5, -6, -7
+ERR_EVALUATION_FAILED, ERR_LINEAR_SOLVER, ERR_NCCL, ERR_INTERNAL = -5, -6, -7, -8
 
 # every symbol include/rsba_cuda.h declares (tests check the library exports all of them)
 SYMBOLS = [

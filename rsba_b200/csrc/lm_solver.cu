@@ -482,6 +482,7 @@ using namespace rsba;
 extern "C" {
 
 int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_summary* sum) {
+  return rsba::api_guard([&]() -> int {
   const auto t_begin = std::chrono::steady_clock::now();
   rsba_solve_summary local;
   if (!sum) sum = &local;
@@ -618,11 +619,13 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   }
   wall();
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt, double radius, double* S_out,
                                  double* rhs_out, double* delta_poses, double* delta_points,
                                  double* model_cost_change) {
+  return rsba::api_guard([&]() -> int {
   int rc = prepare_solve(h, opt);
   if (rc) return rc;
   if (!(radius > 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "radius must be positive");
@@ -666,12 +669,14 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
     RSBA_CUDA_TRY(cudaMemcpy(delta_points, lm->delta_p.ptr, 3L * h->n_points * sizeof(double), cudaMemcpyDeviceToHost));
   if (model_cost_change) *model_cost_change = -0.5 * hs.g_dot_delta + 0.5 * hs.d2_delta2;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, const int* pair_b, int dense,
                                   int reorder, long counts[6], int* tile_pos, int* nz_tiles, int* panels,
                                   int* panel_ptr, int* trsm, int* trsm_ptr, int* upd, long* group_ptr,
                                   int* level_group_ptr) {
+  return rsba::api_guard([&]() -> int {
   if (n_tiles < 0 || n_pairs < 0 || (n_pairs > 0 && (!pair_a || !pair_b)) || !counts)
     return fail(RSBA_ERR_INVALID_ARGUMENT, "bad plan arguments");
   std::vector<std::pair<int, int>> tp;
@@ -694,6 +699,7 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
   if (group_ptr) std::copy(plan.group_ptr.begin(), plan.group_ptr.end(), group_ptr);
   if (level_group_ptr) std::copy(plan.level_group_ptr.begin(), plan.level_group_ptr.end(), level_group_ptr);
   return RSBA_OK;
+  });
 }
 
 

@@ -495,6 +495,7 @@ const char* rsba_cuda_last_error(void) { return g_last_error.c_str(); }
 const char* rsba_cuda_version(void) { return "rsba_b200 0.1 (sm_100a)"; }
 
 int rsba_cuda_create(rsba_problem** out, int device) {
+  return rsba::api_guard([&]() -> int {
   if (!out) return fail(RSBA_ERR_INVALID_ARGUMENT, "out is NULL");
   *out = nullptr;
   int count = 0;
@@ -515,6 +516,7 @@ int rsba_cuda_create(rsba_problem** out, int device) {
   h->own_stream = true;
   *out = h;
   return RSBA_OK;
+  });
 }
 
 void rsba_cuda_destroy(rsba_problem* h) {
@@ -535,6 +537,7 @@ void rsba_cuda_destroy(rsba_problem* h) {
 }
 
 int rsba_cuda_nccl_unique_id(unsigned char id[128]) {
+  return rsba::api_guard([&]() -> int {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
   if (!id) return fail(RSBA_ERR_INVALID_ARGUMENT, "id is NULL");
   const NcclApi* api = nccl_api();
@@ -544,10 +547,12 @@ int rsba_cuda_nccl_unique_id(unsigned char id[128]) {
   if (r != ncclSuccess) return fail(RSBA_ERR_NCCL, std::string("ncclGetUniqueId: ") + api->GetErrorString(r));
   memcpy(id, &uid, 128);
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_point_owners(int n_frames, int n_points, long n_obs, const int* obs_frame, const int* obs_point,
                            int world_size, int* owner) {
+  return rsba::api_guard([&]() -> int {
   if (n_frames < 0 || n_points < 0 || n_obs < 0 || world_size < 1 || !owner || (n_obs > 0 && (!obs_frame || !obs_point)))
     return fail(RSBA_ERR_INVALID_ARGUMENT, "bad arguments");
   for (long i = 0; i < n_obs; ++i) {
@@ -559,6 +564,7 @@ int rsba_cuda_point_owners(int n_frames, int n_points, long n_obs, const int* ob
   compute_point_owners(n_frames, n_points, n_obs, obs_frame, obs_point, world_size, &o);
   std::copy(o.begin(), o.end(), owner);
   return RSBA_OK;
+  });
 }
 
 long rsba_cuda_sort_observations(long n_obs, const int* obs_frame, const int* obs_point, int n_frames, int n_points,
@@ -574,6 +580,7 @@ long rsba_cuda_sort_observations(long n_obs, const int* obs_frame, const int* ob
 }
 
 int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigned char id[128]) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size)
     return fail(RSBA_ERR_INVALID_ARGUMENT, "bad communicator arguments");
   if (h->nccl_comm) return fail(RSBA_ERR_STATE, "communicator already initialised");
@@ -592,19 +599,23 @@ int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigne
   h->world = world_size;
   if (h->scene_set) return materialize_local_share(h);   // re-shard a scene that was set first
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_stream(rsba_problem* h, void* cuda_stream) {
+  return rsba::api_guard([&]() -> int {
   if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
   cudaStreamSynchronize(h->stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   h->stream = (cudaStream_t)cuda_stream;
   h->own_stream = false;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter, const int scanlines[2],
                          int interpolate_rotation) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !cam9 || !scanlines) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (shutter < 0 || shutter > 2) return fail(RSBA_ERR_INVALID_ARGUMENT, "shutter must be 0, 1 or 2");
   memcpy(h->cm.cam, cam9, sizeof(h->cm.cam));
@@ -620,9 +631,11 @@ int rsba_cuda_set_camera(rsba_problem* h, const double cam9[9], int shutter, con
     RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_intrinsics_free(rsba_problem* h, int free_intrinsics) {
+  return rsba::api_guard([&]() -> int {
   if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
   const bool want = free_intrinsics != 0;
   if (want == h->free_cam) return RSBA_OK;
@@ -638,9 +651,11 @@ int rsba_cuda_set_intrinsics_free(rsba_problem* h, int free_intrinsics) {
     RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_get_camera(rsba_problem* h, double cam9[9]) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !cam9) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (!h->camera_set) return fail(RSBA_ERR_STATE, "rsba_cuda_set_camera has not been called");
   if (h->free_cam && h->scene_set && h->params_set) {
@@ -650,9 +665,11 @@ int rsba_cuda_get_camera(rsba_problem* h, double cam9[9]) {
   }
   memcpy(cam9, h->cm.cam, 9 * sizeof(double));
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_get_intrinsics_jacobian(rsba_problem* h, double* jacobian_cam) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !jacobian_cam) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (!h->free_cam || h->d_jac_cam.count == 0) return fail(RSBA_ERR_STATE, "no intrinsics Jacobian: set_intrinsics_free + evaluate first");
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
@@ -664,12 +681,15 @@ int rsba_cuda_get_intrinsics_jacobian(rsba_problem* h, double* jacobian_cam) {
   for (long i = 0; i < n; ++i)
     memcpy(jacobian_cam + 18 * h->order[h->local_ids[i]], &tmp[18 * (size_t)i], 18 * sizeof(double));
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_loss(rsba_problem* h, double huber_a) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !(huber_a >= 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "huber_a must be >= 0");
   h->cm.huber = huber_a;
   return RSBA_OK;
+  });
 }
 
 // pointer API: the frame made of the two control-pose blocks (registered on first sight); < 0 = error
@@ -693,6 +713,7 @@ static int frame_of_blocks(rsba_problem* h, double* pose0, double* pose1) {
 
 int rsba_cuda_add_motion_prior(rsba_problem* h, int kind, double scale, double inter_frame_ratio, double* pose0,
                                double* end0, double* pose1, double* end1) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !pose0 || !end0 || !pose1 || !end1) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
   int rc = check_prior_args(kind, scale, inter_frame_ratio);
@@ -706,10 +727,12 @@ int rsba_cuda_add_motion_prior(rsba_problem* h, int kind, double scale, double i
   h->priors_dirty = true;
   h->ptr_dirty = true;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_motion_priors(rsba_problem* h, int n, const int* kind, const double* scale,
                                 const double* inter_frame_ratio, const int* frame, const int* prev_frame) {
+  return rsba::api_guard([&]() -> int {
   if (!h || n < 0 || (n > 0 && (!kind || !scale || !inter_frame_ratio || !frame || !prev_frame)))
     return fail(RSBA_ERR_INVALID_ARGUMENT, "bad prior arguments");
   if (h->ptr_mode) return fail(RSBA_ERR_STATE, "handle holds pointer-API blocks: use rsba_cuda_add_motion_prior");
@@ -723,6 +746,7 @@ int rsba_cuda_set_motion_priors(rsba_problem* h, int n, const int* kind, const d
   h->priors_dirty = true;
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   return upload_priors(h);
+  });
 }
 
 long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals) {
@@ -738,6 +762,7 @@ long rsba_cuda_get_prior_residuals(rsba_problem* h, double* residuals) {
 
 int rsba_cuda_add_pose_prior(rsba_problem* h, double rotation, double position, double* prior_block,
                              double* pose_block) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !prior_block || !pose_block) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
   if (h->pose_prior_of_block.count(prior_block)) return fail(RSBA_ERR_INVALID_ARGUMENT, "prior block already used");
@@ -749,10 +774,12 @@ int rsba_cuda_add_pose_prior(rsba_problem* h, double rotation, double position, 
   h->pose_priors_dirty = true;
   h->ptr_dirty = true;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_pose_priors(rsba_problem* h, int n, const int* frame, const int* which_pose, const double* rotation,
                               const double* position, const double* prior_values, const unsigned char* prior_constant) {
+  return rsba::api_guard([&]() -> int {
   if (!h || n < 0 || (n > 0 && (!frame || !which_pose || !rotation || !position || !prior_values)))
     return fail(RSBA_ERR_INVALID_ARGUMENT, "bad pose prior arguments");
   if (h->ptr_mode) return fail(RSBA_ERR_STATE, "handle holds pointer-API blocks: use rsba_cuda_add_pose_prior");
@@ -771,6 +798,7 @@ int rsba_cuda_set_pose_priors(rsba_problem* h, int n, const int* frame, const in
   h->pose_priors_dirty = true;
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   return upload_pose_priors(h);
+  });
 }
 
 long rsba_cuda_get_pose_priors(rsba_problem* h, double* prior_values, double* trial_values) {
@@ -807,15 +835,19 @@ static int set_ratio_free(rsba_problem* h, bool want, double value) {
 }
 
 int rsba_cuda_set_inter_frame_ratio_free(rsba_problem* h, int free_ratio, double value) {
+  return rsba::api_guard([&]() -> int {
   if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
   if (h->ptr_ratio && !free_ratio) h->ptr_ratio = nullptr;
   return set_ratio_free(h, free_ratio != 0, value);
+  });
 }
 
 int rsba_cuda_set_inter_frame_ratio_block(rsba_problem* h, double* ratio) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !ratio) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   h->ptr_ratio = ratio;
   return set_ratio_free(h, true, *ratio);
+  });
 }
 
 long rsba_cuda_get_prior_ratio_jacobian(rsba_problem* h, double* d_residual_d_ratio) {
@@ -831,6 +863,7 @@ long rsba_cuda_get_prior_ratio_jacobian(rsba_problem* h, double* d_residual_d_ra
 }
 
 int rsba_cuda_get_inter_frame_ratio(rsba_problem* h, double* value) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !value) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (h->free_ratio && h->scene_set && h->params_set) {
     RSBA_CUDA_TRY(cudaSetDevice(h->device));
@@ -839,10 +872,12 @@ int rsba_cuda_get_inter_frame_ratio(rsba_problem* h, double* value) {
   }
   *value = h->ratio_value;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_add_rs_residual_with_intrinsics(rsba_problem* h, const double observed[2], double* intrinsics,
                                               double* pose0, double* pose1, double* point) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !intrinsics) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (h->ptr_cam && h->ptr_cam != intrinsics)
     return fail(RSBA_ERR_INVALID_ARGUMENT, "only ONE shared intrinsics block is supported (sess.cam); per-frame f.cam blocks are not");
@@ -856,10 +891,12 @@ int rsba_cuda_add_rs_residual_with_intrinsics(rsba_problem* h, const double obse
     if (h->lm) { lm_state_free(h->lm); h->lm = nullptr; }
   }
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0, double* pose1,
                               double* point) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !observed || !pose0 || !pose1 || !point) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
   h->ptr_mode = true;
@@ -878,9 +915,11 @@ int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double*
   h->ptr_obs.push_back({observed[0], observed[1], f, p});
   h->ptr_dirty = true;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_block_constant(rsba_problem* h, double* block) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !block) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   auto a = h->pose0_to_frame.find(block);
   if (a != h->pose0_to_frame.end()) { h->ptr_pose_mask[a->second] |= 0x03F; h->ptr_dirty = true; return RSBA_OK; }
@@ -891,10 +930,12 @@ int rsba_cuda_set_block_constant(rsba_problem* h, double* block) {
   auto d = h->pose_prior_of_block.find(block);
   if (d != h->pose_prior_of_block.end()) { h->pose_priors[d->second].constant = 1; h->pose_priors_dirty = true; return RSBA_OK; }
   return fail(RSBA_ERR_INVALID_ARGUMENT, "unknown parameter block (Ceres would abort here too)");
+  });
 }
 
 int rsba_cuda_set_subset_constant(rsba_problem* h, double* pose_block, int n_constant,
                                   const int* constant_components) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !pose_block || (n_constant > 0 && !constant_components))
     return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   int shift, f;
@@ -912,11 +953,13 @@ int rsba_cuda_set_subset_constant(rsba_problem* h, double* pose_block, int n_con
   }
   h->ptr_dirty = true;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_scene(rsba_problem* h, long n_obs, const double* obs_xy, const int* obs_frame,
                         const int* obs_point, int n_frames, int n_points,
                         const unsigned short* const_pose_mask, const unsigned char* const_point) {
+  return rsba::api_guard([&]() -> int {
   if (!h || n_obs < 0 || n_frames < 0 || n_points < 0 || (n_obs > 0 && (!obs_xy || !obs_frame || !obs_point)))
     return fail(RSBA_ERR_INVALID_ARGUMENT, "bad scene arguments");
   if (h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds pointer-API residual blocks");
@@ -934,9 +977,11 @@ int rsba_cuda_set_scene(rsba_problem* h, long n_obs, const double* obs_xy, const
   if (const_pose_mask) for (int f = 0; f < n_frames; ++f) h->pose_mask[f] = const_pose_mask[f] & 0xFFF;
   if (const_point) for (int p = 0; p < n_points; ++p) h->point_const[p] = const_point[p] ? 1 : 0;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_set_parameters(rsba_problem* h, const double* poses, const double* points) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !h->scene_set) return fail(RSBA_ERR_STATE, "no scene");
   if ((h->n_frames && !poses) || (h->n_points && !points)) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
@@ -955,9 +1000,11 @@ int rsba_cuda_set_parameters(rsba_problem* h, const double* poses, const double*
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->params_set = true;
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_get_parameters(rsba_problem* h, double* poses, double* points) {
+  return rsba::api_guard([&]() -> int {
   if (!h || !h->scene_set || !h->params_set) return fail(RSBA_ERR_STATE, "no parameters on the device");
   RSBA_CUDA_TRY(cudaSetDevice(h->device));
   if (poses && h->n_frames)
@@ -966,6 +1013,7 @@ int rsba_cuda_get_parameters(rsba_problem* h, double* poses, double* points) {
     RSBA_CUDA_TRY(cudaMemcpyAsync(points, h->d_points.ptr, h->d_points.bytes(), cudaMemcpyDeviceToHost, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return RSBA_OK;
+  });
 }
 
 static int prepare(rsba_problem* h) {
@@ -986,13 +1034,16 @@ static int prepare(rsba_problem* h) {
 }
 
 int rsba_cuda_evaluate_device(rsba_problem* h, int with_jacobian, double* cost, long* num_invalid) {
+  return rsba::api_guard([&]() -> int {
   int rc = prepare(h);
   if (rc) return rc;
   return run_evaluate(h, with_jacobian != 0, h->d_poses.ptr, h->d_points.ptr, cost, num_invalid);
+  });
 }
 
 int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double* jacobian,
                        unsigned char* valid) {
+  return rsba::api_guard([&]() -> int {
   int rc = prepare(h);
   if (rc) return rc;
   const bool jac = jacobian != nullptr;
@@ -1042,10 +1093,12 @@ int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double*
   }
   if (bad > 0) return fail(RSBA_ERR_EVALUATION_FAILED, "a cost functor returned false (point behind camera)");
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_validate(rsba_problem* h, double sqrd_threshold, double min_distance_to_camera,
                        unsigned char* ok, double* sqrd_error) {
+  return rsba::api_guard([&]() -> int {
   int rc = prepare(h);
   if (rc) return rc;
   const long n = h->n_obs, ng = h->n_obs_global;
@@ -1071,10 +1124,12 @@ int rsba_cuda_validate(rsba_problem* h, double sqrd_threshold, double min_distan
     if (sqrd_error) sqrd_error[dst] = te[i];
   }
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_reproject(rsba_problem* h, long n, const int* frame, const int* point, double sqrd_threshold,
                         double* proj_xy, unsigned char* ok) {
+  return rsba::api_guard([&]() -> int {
   int rc = prepare(h);
   if (rc) return rc;
   if (n < 0 || (n > 0 && (!frame || !point || !proj_xy || !ok))) return fail(RSBA_ERR_INVALID_ARGUMENT, "bad reproject arguments");
@@ -1095,10 +1150,12 @@ int rsba_cuda_reproject(rsba_problem* h, long n, const int* frame, const int* po
   RSBA_CUDA_TRY(cudaMemcpyAsync(ok, d_ok.ptr, n, cudaMemcpyDeviceToHost, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   return RSBA_OK;
+  });
 }
 
 int rsba_cuda_device_buffers(rsba_problem* h, void** residuals, void** jacobian, void** valid,
                              void** poses, void** points) {
+  return rsba::api_guard([&]() -> int {
   if (!h) return fail(RSBA_ERR_INVALID_ARGUMENT, "handle is NULL");
   if (residuals) *residuals = h->d_res.ptr;
   if (jacobian) *jacobian = h->d_jac.ptr;
@@ -1106,6 +1163,7 @@ int rsba_cuda_device_buffers(rsba_problem* h, void** residuals, void** jacobian,
   if (poses) *poses = h->d_poses.ptr;
   if (points) *points = h->d_points.ptr;
   return RSBA_OK;
+  });
 }
 
 long rsba_cuda_observation_order(rsba_problem* h, long* order) {

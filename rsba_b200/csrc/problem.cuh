@@ -6,6 +6,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "api_guard.h"
 #include "common.cuh"
 #include "host_threads.h"
 #include "../../include/rsba_cuda.h"

@@ -1,6 +1,8 @@
 // Host analysis of a scene's structure (structure.cuh).  No device calls in this file.
 #include "structure.cuh"
 
+#include "api_guard.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -398,6 +400,7 @@ int rsba_cuda_analyze_structure(long n_obs, const int* obs_frame, const int* obs
                                 const unsigned char* const_point, int free_intrinsics, int free_ratio, int n_priors,
                                 const int* prior_frame, const int* prior_prev, int dense, int reorder,
                                 int sparse_keys, int rank, int world_size, rsba_structure** out) {
+  return rsba::api_guard([&]() -> int {
   using namespace rsba;
   auto bad = [](const char* msg) { set_last_error(msg); return (int)RSBA_ERR_INVALID_ARGUMENT; };
   if (!out) return bad("out is NULL");
@@ -462,6 +465,7 @@ int rsba_cuda_analyze_structure(long n_obs, const int* obs_frame, const int* obs
   }
   *out = s;
   return RSBA_OK;
+  });
 }
 
 long rsba_cuda_structure_array(const rsba_structure* s, const char* name, const void** data, int* elem_bytes) {
