@@ -51,6 +51,74 @@ def dump_prior_functors():
     print("prior_functors", len(rows), "cases")
 
 
+def mat_test_fixtures():
+    """The INPUT tables of the reference's own tests (src/rsba/test/mat_test.cc): TEST(SfM, reprojection) poses /
+    points / cameras (:170-229) and TEST(SfM, Distortion) cameras / image points (:145-167).  Values only."""
+    eps, pi2 = np.finfo(np.float64).eps, np.pi / 2          # _EPS = __DBL_EPSILON__ (mat/core.h:12), M_PI_2
+    pose = np.array([[0, 0, 0, 0, 0, 0], [0, 0, 0, 1, 1, 1], [0, 0, pi2, 20, 20, 20], [0, pi2, pi2, -2, 20, 20],
+                     [pi2, pi2, pi2, -2, -2, 20], [-1, -1, -1, -2, -2, -2], [-pi2, -1, -1, -20, -2, -2],
+                     [0.5, -pi2, -1, -2, -20, -2], [0.5, 0.5, -pi2, 0.2, -2, -20], [eps] * 6, [-eps] * 6], dtype=np.float64)
+    pt = np.array([[10, 10, 10], [100, 0, 1], [0, 100, 1], [0, 0, 100], [-100, 0, 1], [0, -100, 1], [0, 0, -100],
+                   [0, 0, -1], [0, 0, 0], [1, 1, 1], [-1, -1, -1], [0.1, 0.1, 0.1], [100, 100, 100],
+                   [-100, -100, -100], [-0.39, 1.25, 2014], [eps, eps, eps], [eps, eps, -eps], [-eps, -eps, -eps]],
+                  dtype=np.float64)
+    cam = np.array([[0.1, 0.1, 0, 0, 0, 0, 0, 0, 0], [100, 100, 0, 0, 0, 0, 0, 0, 0], [500, 500, 0, 0, 0, 0, 0, 640, 480],
+                    [100, 100, eps, 0, 0, 0, 0, 0, 0], [500, 500, -eps, -eps, 0, 0, 0, 0, 0],
+                    [860, 860, 0.001, 0, 0, 0, 0, 100, 200]], dtype=np.float64)
+    dcam = np.array([[0.1, 0.1, 0, 0, 0, 0, 0, 0, 0], [100, 100, 0.01, 0, 0, 0, 0, 0, 0],
+                     [500, 500, -0.03, 0, 0, 0, 0, 0, 0], [500, 500, -0.1, 0.02, 0, 0, 0, 0, 0]], dtype=np.float64)
+    dimg = np.array([[0.10, 0.10], [0.21, 0.19], [1.10, 0.50]], dtype=np.float64)
+    return pose, pt, cam, dcam, dimg
+
+
+def dump_mat_test_grid():
+    """What the REFERENCE's own w2c / w2i / distort (mat/cam.h:355-419, 49-72; compiled verbatim in oracle/_ref) return
+    on the exact input grid of its own tests: 11 poses x 18 points (x 6 cameras), 4 cameras x 3 image points."""
+    import ctypes as C
+    lib = oracle.ref_lib()
+    dp = C.POINTER(C.c_double)
+    p = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    pose, pt, cam, dcam, dimg = mat_test_fixtures()
+    w2c = np.zeros((11, 18, 3))
+    proj = np.zeros((11, 18, 6, 2))
+    ok = np.zeros((11, 18, 6), dtype=np.int32)
+    proj_nv = np.zeros((11, 18, 6, 2))            # w2i(validate = false), as solveRSpnp.cpp:65 calls it
+    for i in range(11):
+        for j in range(18):
+            out = np.zeros(3)
+            lib.rsba_ref_w2c(p(pose[i]), p(pt[j]), p(out))
+            w2c[i, j] = out
+            for k in range(6):
+                o2 = np.zeros(2)
+                ok[i, j, k] = lib.rsba_ref_w2i(p(cam[k]), p(pose[i]), p(pt[j]), p(o2), 1)
+                proj[i, j, k] = o2
+                if abs(out[2]) > 0.0:             # (z == 0 divides by zero: not a value to pin)
+                    o3 = np.zeros(2)
+                    lib.rsba_ref_w2i(p(cam[k]), p(pose[i]), p(pt[j]), p(o3), 0)
+                    proj_nv[i, j, k] = o3
+    dist = np.zeros((4, 3, 2))
+    for k in range(4):
+        for j in range(3):
+            o2 = np.zeros(2)
+            lib.rsba_ref_distort(p(dcam[k]), p(dimg[j]), p(o2))
+            dist[k, j] = o2
+    os.makedirs(os.path.join(HERE, "mat_test"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "mat_test", "grid.npz"), pose=pose, pt=pt, cam=cam, dcam=dcam, dimg=dimg,
+                        w2c=w2c, proj=proj, ok=ok, proj_nv=proj_nv, distort=dist)
+    print("mat_test/grid: w2i valid on", int(ok.sum()), "of", ok.size)
+    # ... and the same grid through the reference's FUNCTOR under Jet autodiff, as ordinary golden scenes (one per
+    # camera; global shutter: one pose per frame, stored twice; observation = origin, so residual = projection): the
+    # port, the product's host-compiled K1 arithmetic and the GPU kernel are all compared with these
+    from rsba_b200.scene import Scene
+    fr, pi = np.meshgrid(np.arange(11), np.arange(18), indexing="ij")
+    for k in range(6):
+        sc = Scene(cam=cam[k], shutter=0, scanlines=np.array([0, 1280], dtype=np.int32), interpolate_rotation=True,
+                   poses=np.concatenate([pose, pose], axis=1), points=pt, obs_xy=np.zeros((198, 2)),
+                   obs_frame=fr.reshape(-1).astype(np.int32), obs_point=pi.reshape(-1).astype(np.int32),
+                   const_frames=np.zeros(11, dtype=bool), name=f"mat_test_cam{k}")
+        dump(f"mat_test_cam{k}", sc)
+
+
 if __name__ == "__main__":
     oracle.build()
     assert oracle.ref_available(), "needs /root/reference to build oracle/_ref"
@@ -60,3 +128,4 @@ if __name__ == "__main__":
         for ir in (0, 1):
             dump(f"edge_s{sh}_r{ir}", edge_scene(shutter=sh, interpolate_rotation=bool(ir)))
     dump_prior_functors()
+    dump_mat_test_grid()

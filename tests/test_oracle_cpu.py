@@ -226,3 +226,56 @@ def test_distortion_known_answer(oracle_built):
         ex = d * u[0] + 2 * cam[4] * u[0] * u[1] + cam[5] * (r2 + 2 * u[0] ** 2)
         ey = d * u[1] + cam[4] * (r2 + 2 * u[1] ** 2) + 2 * cam[5] * u[0] * u[1]
         assert np.allclose(out, [ex, ey], rtol=1e-13, atol=1e-15)
+
+
+def test_port_on_the_reference_tests_own_grid(oracle_built):
+    """The exact input tables of TEST(SfM, reprojection) (mat_test.cc:170-229: 11 poses x 18 points x 6 cameras) and
+    TEST(SfM, Distortion) (:145-167): the port's w2c / w2i / distort against what the REFERENCE's own functions return
+    on them (tests/golden/mat_test/grid.npz, written by make_golden.py from oracle/_ref), plus the properties the
+    reference test asserts that involve only hot-path functions."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mat_test", "grid.npz"))
+    lib, _ = _prim(oracle_built)
+    dp = C.POINTER(C.c_double)
+    p = lambda a: np.ascontiguousarray(a).ctypes.data_as(dp)  # noqa: E731
+    pose, pt, cam = g["pose"], g["pt"], g["cam"]
+    assert pose.shape == (11, 6) and pt.shape == (18, 3) and cam.shape == (6, 9)
+    n_valid = 0
+    for i in range(11):
+        R = _rodrigues_matrix(pose[i, :3])
+        for j in range(18):
+            pc = np.zeros(3)
+            lib.rsba_oracle_w2c(p(pose[i]), p(pt[j]), p(pc))
+            assert np.allclose(pc, g["w2c"][i, j], rtol=1e-14, atol=1e-300)
+            # CHECK_LE(dist3(pt[j], w3), 1e-6) with w3 = c2w(pose, w2c(pose, pt))  (mat_test.cc:207-212)
+            assert np.linalg.norm(R.T @ pc + pose[i, 3:] - pt[j]) <= 1e-6 * max(1.0, np.linalg.norm(pt[j]))
+            for k in range(6):
+                proj = np.zeros(2)
+                ok = lib.rsba_oracle_w2i(p(cam[k]), p(pose[i]), p(pt[j]), p(proj), 1)
+                assert ok == g["ok"][i, j, k]
+                assert bool(ok) == (pc[2] >= 1e-8)                    # mat/cam.h:410-412
+                if ok:
+                    n_valid += 1
+                    assert np.allclose(proj, g["proj"][i, j, k], rtol=1e-13, atol=1e-300)
+                if pc[2] != 0.0:                                      # validate = false (solveRSpnp.cpp:65)
+                    lib.rsba_oracle_w2i(p(cam[k]), p(pose[i]), p(pt[j]), p(proj), 0)
+                    assert np.allclose(proj, g["proj_nv"][i, j, k], rtol=1e-13, atol=1e-300)
+    assert n_valid == int(g["ok"].sum()) == 672
+    for k in range(4):
+        for j in range(3):
+            out = np.zeros(2)
+            lib.rsba_oracle_distort(p(g["dcam"][k]), p(g["dimg"][j]), p(out))
+            assert np.allclose(out, g["distort"][k, j], rtol=1e-14, atol=0)
+            # CHECK_LE(dist2(img, undistort(distort(img))), 1e-6): the distortion is invertible there (fixed point)
+            u = out.copy()
+            k1, k2 = g["dcam"][k, 2], g["dcam"][k, 3]
+            for _ in range(200):
+                r2 = u @ u
+                u = out / (1.0 + k1 * r2 + k2 * r2 * r2)
+            assert np.linalg.norm(u - g["dimg"][j]) <= 1e-6
+    if oracle_built.ref_available():                                  # the fixture IS what the reference computes here
+        ref = oracle_built.ref_lib()
+        for i in (0, 4, 9):
+            for j in (0, 14, 16):
+                pc = np.zeros(3)
+                ref.rsba_ref_w2c(p(pose[i]), p(pt[j]), p(pc))
+                assert np.array_equal(pc, g["w2c"][i, j])
