@@ -119,6 +119,30 @@ def dump_mat_test_grid():
         dump(f"mat_test_cam{k}", sc)
 
 
+def dump_mat_test_slerp():
+    """The 16-rotation table of the reference's TEST(SfM, SLERP) (mat_test.cc:76-94) as the two control poses of
+    rolling-shutter frames -- every pair (i, j) the test visits is one frame -- seen through the reference functor under
+    Jet autodiff at scan-line times spread over [0, 1] (and clamped outside)."""
+    from rsba_b200.scene import Scene
+    pi2, eps = np.pi / 2, np.finfo(np.float64).eps
+    r = np.array([[0, 0.5, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [0, 1, 1], [1, 1, 1], [0, -1, 0], [-1, 0, 0],
+                  [-1, 0, -1], [0, pi2, 0], [pi2, 0, 0], [0, 1 - pi2, 0], [0, -1, pi2], [0, -1, 1 - pi2], [0, 0, eps],
+                  [1, -1, eps]], dtype=np.float64)
+    pairs = [(i, j) for i in range(16) for j in range(1, 16)]
+    poses = np.array([np.concatenate([r[i], [0.0, 0.0, 0.0], r[j], [0.1, -0.05, 0.02]]) for i, j in pairs])
+    pts = np.array([[10, 10, 10], [0, 0, 100], [1, 1, 1], [-0.39, 1.25, 2014], [100, 100, 100], [0.1, 0.1, 0.1],
+                    [-10, 3, 8], [2, -30, -40]], dtype=np.float64)
+    xs = np.array([-50.0, 0.0, 1.0, 320.0, 640.0, 1000.0, 1279.0, 1280.0, 1400.0])
+    fr, pi = np.meshgrid(np.arange(len(pairs)), np.arange(len(pts)), indexing="ij")
+    fr, pi = fr.reshape(-1), pi.reshape(-1)
+    xy = np.stack([xs[(fr * 7 + pi * 3) % len(xs)], 100.0 + 37.0 * (pi % 5)], axis=1)
+    sc = Scene(cam=np.array([860.0, 860.0, 1e-3, 0, 0, 0, 0, 640.0, 360.0]), shutter=1,
+               scanlines=np.array([0, 1280], dtype=np.int32), interpolate_rotation=True, poses=poses, points=pts,
+               obs_xy=xy, obs_frame=fr.astype(np.int32), obs_point=pi.astype(np.int32),
+               const_frames=np.zeros(len(pairs), dtype=bool), name="mat_test_slerp")
+    dump("mat_test_slerp", sc)
+
+
 if __name__ == "__main__":
     oracle.build()
     assert oracle.ref_available(), "needs /root/reference to build oracle/_ref"
@@ -129,3 +153,4 @@ if __name__ == "__main__":
             dump(f"edge_s{sh}_r{ir}", edge_scene(shutter=sh, interpolate_rotation=bool(ir)))
     dump_prior_functors()
     dump_mat_test_grid()
+    dump_mat_test_slerp()

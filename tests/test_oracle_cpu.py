@@ -279,3 +279,51 @@ def test_port_on_the_reference_tests_own_grid(oracle_built):
                 pc = np.zeros(3)
                 ref.rsba_ref_w2c(p(pose[i]), p(pt[j]), p(pc))
                 assert np.array_equal(pc, g["w2c"][i, j])
+
+
+def test_rotation_and_slerp_on_the_reference_tests_own_tables(oracle_built):
+    """The exact vectors of TEST(SfM, Rotation) (mat_test.cc:34-72) and the 16-rotation table of TEST(SfM, SLERP)
+    (:75-142) with the assertions the reference makes on them."""
+    lib, _ = _prim(oracle_built)
+    dp = C.POINTER(C.c_double)
+    lib.rsba_oracle_slerp.argtypes = [dp, dp, C.c_double, dp]
+    pi, pi2, eps = np.pi, np.pi / 2, np.finfo(np.float64).eps
+
+    def rot(aa, pt, inplace=False):
+        aa, pt = np.array(aa, dtype=np.float64), np.array(pt, dtype=np.float64)
+        out = pt if inplace else np.zeros(3)
+        lib.rsba_oracle_rotate(aa.ctypes.data_as(dp), pt.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        return out
+
+    p, p2, p3, p4 = [0, 0, -10], [0, 0, 10], [10, 0, 0], [0, 10, 0]
+    test = rot([0, pi, 0], p)
+    assert np.linalg.norm(test - p2) <= 1e-9                                       # pi
+    assert np.linalg.norm(rot([0, -pi, 0], test, inplace=True) - p) <= 1e-9        # invert3(r), in place (:51-53)
+    assert np.linalg.norm(rot([0, -pi, 0], p) - p2) <= 1e-9                        # -pi
+    assert np.linalg.norm(rot([0, -pi2, 0], p) - p3) <= 1e-9                       # -pi/2
+    assert np.linalg.norm(rot([pi2, 0, 0], p) - p4) <= 1e-9                        # pi/2
+
+    def slerp(a, b, t):
+        a, b, out = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64), np.zeros(3)
+        lib.rsba_oracle_slerp(a.ctypes.data_as(dp), b.ctypes.data_as(dp), float(t), out.ctypes.data_as(dp))
+        return out
+
+    r = np.array([[0, 0.5, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [0, 1, 1], [1, 1, 1], [0, -1, 0], [-1, 0, 0],
+                  [-1, 0, -1], [0, pi2, 0], [pi2, 0, 0], [0, 1 - pi2, 0], [0, -1, pi2], [0, -1, 1 - pi2], [0, 0, eps],
+                  [1, -1, eps]], dtype=np.float64)
+    for i in range(16):
+        for j in range(1, 16):
+            assert np.linalg.norm(slerp(r[i], r[j], 1.0) - r[j]) <= 1e-6
+            assert np.linalg.norm(slerp(r[i], r[j], 0.0) - r[i]) <= 1e-6
+            r05, r15, r20 = slerp(r[i], r[j], 0.5), slerp(r[i], r[j], 1.5), slerp(r[i], r[j], 2.0)
+            assert np.linalg.norm(slerp(r[i], r20, 0.5) - r[j]) <= 1e-6
+            assert np.linalg.norm(slerp(r05, r15, 0.5) - r[j]) <= 1e-6
+            if i != j:   # the loose agreement with a true quaternion slerp (:124-139, CHECK_LE(..., 0.2))
+                qi, qj = _quat(r[i]), _quat(r[j])
+                frac = 2
+                while frac < 500:
+                    for n in range(1, frac):
+                        tau = n / frac
+                        true = _quat_to_aa(_quat_slerp(qi, qj, tau))
+                        assert np.linalg.norm(slerp(r[i], r[j], tau) - true) <= 0.2, (i, j, tau)
+                    frac = frac * 2 - 1
