@@ -23,6 +23,10 @@ restated from Ceres 1.9.0's published implementation
 * Constant parameter blocks / components are removed from the program (their columns do not
   exist); here their columns are zeroed, their diagonal set to one and their step is zero.
 
+What is checked without Ceres (tests/test_lm_oracle_cpu.py): one step equals the least-squares solution of the
+augmented system [J'; D] y = [-r; 0] by dense LAPACK, and the loop reaches the minimum MINPACK's Levenberg-Marquardt
+and scipy's trust-region reflective find on the same residuals.  The iterate-by-iterate trajectory stays a restatement.
+
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
 """
 from __future__ import annotations
