@@ -293,6 +293,26 @@ int rsba_cuda_plan_reduced_system(int n_tiles, int n_pairs, const int* pair_a, c
                                   int* panels, int* panel_ptr, int* trsm, int* trsm_ptr, int* upd,
                                   long* group_ptr, int* level_group_ptr);
 
+/* Host-only: the numeric phase of the reduced-system solve (Cholesky factorisation, forward and backward
+ * substitution) as the static task graph that the persistent kernel of rsba_b200/csrc/k3_dag.cu executes --
+ * the stand-in for CHOLMOD's numeric factorisation + solve behind Ceres' SPARSE_SCHUR (CeresHandler.h:403).
+ * Same plan inputs as rsba_cuda_plan_reduced_system; merge_levels >= 1 = elimination levels per merged update
+ * group.  Two-call pattern: counts[] = {tasks, update sources, non-zero tiles, factorisation tasks}; then
+ *   tasks[8*n_tasks]   records {type, a..g} in topological (execution) order, see tile_plan.cuh
+ *   sources[2*n_src]   (slot(i,k), slot(j,k)) of the updates;  need[4*n_nz] update groups per tile quadrant. */
+int rsba_cuda_plan_task_graph(int n_tiles, int n_pairs, const int* pair_a, const int* pair_b, int dense,
+                              int reorder, int merge_levels, long counts[4], int* tasks, int* sources,
+                              int* need);
+
+/* K3 on its own (test and measurement hook; no counterpart in the reference, where CHOLMOD sits behind
+ * ceres::Solve): solves A x = rhs on `device` for a symmetric positive definite A (n x n row-major,
+ * n = 96 n_tiles) whose block pattern is given by the tile pairs (or dense).  mode 0 = task-graph kernel,
+ * 1 = level-batched launches.  Optional outputs: L (n x n, in the PERMUTED tile order tile_pos_out[n_tiles]
+ * describes), info (0, or 1 + index of the first non-positive pivot), device time of the numeric phase. */
+int rsba_cuda_reduced_solve(int device, int n_tiles, int n_pairs, const int* pair_a, const int* pair_b, int dense,
+                            int reorder, int mode, int merge_levels, const double* A, const double* rhs,
+                            double* x_out, double* L_out, int* tile_pos_out, int* info_out, float* ms_out);
+
 /* Host-only introspection of the WHOLE one-off structure analysis that rsba_cuda_solve runs before its first
  * linearisation -- what Ceres does in Program reordering + SchurEliminator block-structure detection + CHOLMOD's
  * analyse phase (third-party; reached through ceres::Solve, CeresHandler.h:403,419).  Needs no device: the CPU

@@ -167,6 +167,9 @@ def load_library():
     lib.rsba_cuda_solve.argtypes = [vp, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
     lib.rsba_cuda_linearize_and_step.argtypes = [vp, C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp, _dp]
     lib.rsba_cuda_plan_reduced_system.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp] + [vp] * 9
+    lib.rsba_cuda_plan_task_graph.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.rsba_cuda_reduced_solve.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_float)]
     lib.rsba_cuda_analyze_structure.argtypes = [C.c_long, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp,
                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.rsba_cuda_structure_array.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
@@ -575,6 +578,59 @@ def plan_reduced_system(n_tiles, pair_a, pair_b, dense=False, reorder=True):
                level_group_ptr=np.zeros(L + 1, np.int32))
     call(*out.values())
     out.update(n_levels=L, flops=float(counts[5]))
+    return out
+
+
+TASK_FACTOR, TASK_TRSM, TASK_UPDATE, TASK_BACK_FIN, TASK_BACK_TILE = range(5)
+
+
+def plan_task_graph(n_tiles, pair_a, pair_b, dense=False, reorder=True, merge_levels=4):
+    """Host-only: the numeric phase of the reduced-system solve as the static task list of the persistent
+    kernel (rsba_b200/csrc/k3_dag.cu).  Returns dict(tasks[n, 8], sources[m, 2], need[n_nz, 4],
+    n_factor_tasks)."""
+    lib = load_library()
+    pa = np.ascontiguousarray(pair_a, dtype=np.int32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.int32)
+    counts = np.zeros(4, dtype=np.int64)
+
+    def call(*outs):
+        rc = lib.rsba_cuda_plan_task_graph(int(n_tiles), int(pa.size), _addr(pa), _addr(pb), int(dense), int(reorder),
+                                           int(merge_levels), _addr(counts), *[_addr(o) for o in outs])
+        if rc != RSBA_OK:
+            raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
+
+    call(None, None, None)
+    tasks = np.zeros((int(counts[0]), 8), np.int32)
+    sources = np.zeros((max(int(counts[1]), 1), 2), np.int32)
+    need = np.zeros((max(int(counts[2]), 1), 4), np.int32)
+    call(tasks, sources, need)
+    return dict(tasks=tasks, sources=sources[:int(counts[1])], need=need[:int(counts[2])],
+                n_factor_tasks=int(counts[3]))
+
+
+def reduced_solve(A, rhs, n_tiles, pair_a=(), pair_b=(), dense=False, reorder=True, mode="dag", merge_levels=4,
+                  want_L=False, device=0):
+    """K3 on its own, on the GPU: solves A x = rhs for an SPD matrix with the given tile pattern (tile = 96 rows).
+    Returns dict(x, info, ms[, L, tile_pos]); L is in the permuted tile order that tile_pos describes."""
+    lib = load_library()
+    n = 96 * int(n_tiles)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+    assert A.shape == (n, n) and rhs.shape == (n,)
+    pa = np.ascontiguousarray(pair_a, dtype=np.int32)
+    pb = np.ascontiguousarray(pair_b, dtype=np.int32)
+    x = np.zeros(n)
+    L = np.zeros((n, n)) if want_L else None
+    pos = np.zeros(int(n_tiles), dtype=np.int32)
+    info, ms = C.c_int(0), C.c_float(0)
+    rc = lib.rsba_cuda_reduced_solve(int(device), int(n_tiles), int(pa.size), _addr(pa), _addr(pb), int(dense),
+                                     int(reorder), {"dag": 0, "levels": 1}[mode], int(merge_levels), _addr(A),
+                                     _addr(rhs), _addr(x), _addr(L), _addr(pos), C.byref(info), C.byref(ms))
+    if rc != RSBA_OK:
+        raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
+    out = dict(x=x, info=info.value, ms=ms.value, tile_pos=pos)
+    if want_L:
+        out["L"] = L
     return out
 
 

@@ -167,6 +167,20 @@ int launch_tile_cholesky(double* S, const TileSchedule& ts, const TilePlan& plan
 int launch_tile_solve(const double* S, const TileSchedule& ts, const TilePlan& plan,
                       double* x /* in: z = L^-1 rhs (from launch_tile_cholesky), out: solution */, cudaStream_t s);
 
+// task-graph form of the same factorisation + both substitutions (k3_dag.cu): one persistent kernel
+struct DagDevice {
+  const DagTask* tasks;     // [n_tasks] topological order (tile_plan.cuh); the first n_factor_tasks factorise
+  int n_tasks, n_factor_tasks;
+  const int2* sources;
+  const int* need;          // [n_nz * 4]
+  int* counters;            // [dag_counter_ints] device-side dependency counters (cleared by the launcher)
+  double* bwd_partials;     // [off-diagonal tiles][96]
+};
+size_t dag_counter_ints(const TileSchedule& ts);
+// factor: L, inverses of the diagonal factors, z = L^-1 x;  solve: x = L^-T z.  Returns the launches issued.
+int launch_tile_dag(double* S, const TileSchedule& ts, const DagDevice& dd, double* x, int* info, bool factor,
+                    bool solve, cudaStream_t s);
+
 // ---- K4 ---------------------------------------------------------------------------------
 struct StepScalars {  // device doubles, filled by launch_step_update
   double g_dot_delta, d2_delta2, step_norm2, x_norm2, gmax;

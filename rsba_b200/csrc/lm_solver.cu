@@ -36,6 +36,15 @@ struct LmState {
   DeviceBuffer<unsigned short> pose_mask;
   DeviceBuffer<unsigned char> point_const;
   TilePlan plan;                              // host copy of the symbolic analysis
+  // the numeric phase of K3 as one persistent task-graph kernel (k3_dag.cu); RSBA_CUDA_K3=levels selects the
+  // level-batched launch sequence instead
+  bool use_dag = true, dag_split = false;
+  int n_dag_tasks = 0, n_dag_factor_tasks = 0;
+  DeviceBuffer<DagTask> dag_tasks;
+  DeviceBuffer<int2> dag_sources;
+  DeviceBuffer<int> dag_need, dag_counters;
+  DeviceBuffer<double> bwd_partials;
+  DagDevice dd{};
   SchurStructure st{};
   TileSchedule ts{};
   bool dense = false, reorder = true;
@@ -138,6 +147,18 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
   UP(panels, plan.panels); UP(trsm, plan.trsm); UP(fwd_slot, hs.fwd_slot);
   {
+    const char* mode = getenv("RSBA_CUDA_K3");
+    lm->use_dag = !(mode && strcmp(mode, "levels") == 0);
+    lm->dag_split = getenv("RSBA_CUDA_K3_SPLIT") != nullptr;
+    const char* merge = getenv("RSBA_CUDA_K3_MERGE");   // (env: experiment hook) levels per merged update group
+    DagPlan dag;
+    build_dag_plan(plan, merge ? atoi(merge) : 4, &dag);
+    lap("task graph");
+    lm->n_dag_tasks = (int)dag.tasks.size();
+    lm->n_dag_factor_tasks = dag.n_factor_tasks;
+    UP(dag_tasks, dag.tasks); UP(dag_sources, dag.sources); UP(dag_need, dag.need);
+  }
+  {
     std::vector<unsigned short> mask(h->pose_mask);
     mask.resize(Fc, 0);
     if (pseudo)   // parameters 0..8 = intrinsics, 9 = interFrameRatio; what is not a parameter is constant
@@ -219,6 +240,10 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   ts.row_ptr = lm->row_ptr.ptr; ts.rows = lm->rows.ptr; ts.upd = lm->upd.ptr; ts.panels = lm->panels.ptr; ts.trsm = lm->trsm.ptr;
   ts.lrow_ptr = lm->lrow_ptr.ptr; ts.lrow_cols = lm->lrow_cols.ptr; ts.Dinv = lm->Dinv.ptr; ts.solve_partials = lm->solve_partials.ptr; ts.n_real = 12L * Fc;
   ts.fwd_slot = lm->fwd_slot.ptr; ts.fwd_partials = lm->fwd_partials.ptr;
+  RSBA_CUDA_TRY(lm->dag_counters.resize(dag_counter_ints(ts)));
+  RSBA_CUDA_TRY(lm->bwd_partials.resize(std::max<size_t>(plan.rows.size(), 1) * kTile));
+  lm->dd = DagDevice{lm->dag_tasks.ptr, lm->n_dag_tasks, lm->n_dag_factor_tasks, lm->dag_sources.ptr, lm->dag_need.ptr,
+                     lm->dag_counters.ptr, lm->bwd_partials.ptr};
 
   long free_params = 0;
   for (int f = 0; f < F; ++f) free_params += 12 - __builtin_popcount(h->pose_mask[f] & 0xFFF);
@@ -349,6 +374,23 @@ cudaGraphExec_t capture_graph(cudaStream_t s, F body, int* launches) {
 
 void factor_and_solve(rsba_problem* h, LmState* lm) {
   cudaStream_t s = h->stream;
+  if (lm->use_dag) {   // one persistent kernel: factorisation, forward and backward substitution
+    stage_begin(h, kStageCholesky);
+    cudaMemsetAsync(lm->info.ptr, 0, sizeof(int), s);
+    cudaMemcpyAsync(lm->y.ptr, lm->rhs.ptr, lm->n_pad * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (lm->dag_split) {   // RSBA_CUDA_K3_SPLIT=1: two launches, so that the stage timers can tell the parts apart
+      stage_begin(h, kStageFactor);
+      h->launches += launch_tile_dag(lm->S.ptr, lm->ts, lm->dd, lm->y.ptr, lm->info.ptr, true, false, s);
+      stage_end(h, kStageFactor);
+      stage_begin(h, kStageTriSolve);
+      h->launches += launch_tile_dag(lm->S.ptr, lm->ts, lm->dd, lm->y.ptr, lm->info.ptr, false, true, s);
+      stage_end(h, kStageTriSolve);
+    } else {
+      h->launches += launch_tile_dag(lm->S.ptr, lm->ts, lm->dd, lm->y.ptr, lm->info.ptr, true, true, s);
+    }
+    stage_end(h, kStageCholesky);
+    return;
+  }
   if (!lm->graph_tried) {
     lm->graph_tried = true;
     k3_prepare();   // the kernels' one-off attribute setup stays outside the capture

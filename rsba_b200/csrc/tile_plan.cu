@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <initializer_list>
 #include <queue>
 
 namespace rsba {
@@ -225,6 +226,96 @@ void build_tile_plan(int T, const std::vector<std::pair<int, int>>& tile_pairs, 
   }
   P.trsm_ptr[P.n_levels] = (int)P.trsm.size();
   P.level_group_ptr[P.n_levels] = (int)P.group_ptr.size() - 1;
+}
+
+// ---------------------------------------------------------------- task graph of the numeric phase
+void build_dag_plan(const TilePlan& P, int merge_levels, DagPlan* dag) {
+  DagPlan& D = *dag;
+  D = DagPlan();
+  const int T = P.T;
+  const int L = P.n_levels;
+  if (merge_levels < 1) merge_levels = 1;
+  std::vector<int> level(std::max(T, 1), 0);
+  for (int l = 0; l < L; ++l)
+    for (int q = P.panel_ptr[l]; q < P.panel_ptr[l + 1]; ++q) level[P.panels[q]] = l;
+  auto slot = [&](int i, int j) { return P.tile_slot[(size_t)i * T + j]; };
+  D.need.assign(std::max<size_t>(P.nz_tiles.size(), 1) * 4, 0);
+
+  struct Keyed { long key[7]; DagTask t; };
+  std::vector<Keyed> all;
+  auto push = [&](std::initializer_list<long> key, DagTask t) {
+    Keyed k{};
+    int n = 0;
+    for (long v : key) k.key[n++] = v;
+    k.t = t;
+    all.push_back(k);
+  };
+  // ---- factorisation: one FACTOR per panel, kTrsmParts TRSM slabs per tile below it
+  for (int k = 0; k < T; ++k) {
+    push({level[k], 0, k}, DagTask{kTaskFactor, k, slot(k, k), 0, 0, 0, 0, 0});
+    for (int x = P.row_ptr[k]; x < P.row_ptr[k + 1]; ++x) {
+      const int i = P.rows[x];
+      int fwd = -1;
+      for (int q = P.lrow_ptr[i]; q < P.lrow_ptr[i + 1]; ++q)
+        if (P.lrow_cols[q] == k) fwd = q;
+      for (int part = 0; part < kTrsmParts; ++part)
+        push({level[k], 2, level[i], i, k, part}, DagTask{kTaskTrsm, i, k, part, slot(i, k), slot(k, k), fwd, 0});
+    }
+  }
+  // ---- trailing updates, gathered per target tile; sources in (level, panel) order
+  {
+    std::vector<std::vector<int>> by_target(P.nz_tiles.size());   // source panels k of each target slot
+    for (const int4& u : P.upd) by_target[slot(u.x, u.y)].push_back(u.z);
+    for (size_t s = 0; s < by_target.size(); ++s) {
+      std::vector<int>& ks = by_target[s];
+      if (ks.empty()) continue;
+      const int i = P.nz_tiles[s].x, j = P.nz_tiles[s].y;
+      std::sort(ks.begin(), ks.end(), [&](int a, int b) { return level[a] != level[b] ? level[a] < level[b] : a < b; });
+      const int lj = level[j];
+      // group id: the sources right below the target's column stay on their own (they are on the critical
+      // path); older ones are taken merge_levels levels at a time
+      auto group_of = [&](int k) { return level[k] >= lj - 1 ? (long)1 << 30 : (long)(level[k] / merge_levels); };
+      int order = 0;
+      for (size_t b = 0; b < ks.size();) {
+        size_t e = b;
+        while (e < ks.size() && group_of(ks[e]) == group_of(ks[b])) ++e;
+        const int first = (int)D.sources.size();
+        int lmax = 0;
+        for (size_t x = b; x < e; ++x) {
+          D.sources.push_back(make_int2(slot(i, ks[x]), slot(j, ks[x])));
+          lmax = std::max(lmax, level[ks[x]]);
+        }
+        for (int q = 0; q < 4; ++q) {
+          if (i == j && q == 1) continue;          // diagonal targets: the upper-right quadrant is never read
+          const DagTask t{kTaskUpdate, (int)s, q, order, first, (int)(e - b), 0, 0};
+          if (lmax == lj - 1) push({lmax, 3, i != j, level[i], i, j, q}, t);
+          else push({lmax + 1, 1, lj, i != j, i, j, q}, t);
+          D.need[s * 4 + q] = order + 1;
+        }
+        ++order;
+        b = e;
+      }
+    }
+  }
+  // ---- backward substitution: y_k = L_kk^-T (z_k - sum_{i > k} L_ik^T y_i), highest level first
+  for (int k = 0; k < T; ++k) {
+    push({L + (L - 1 - level[k]), 0, k},
+         DagTask{kTaskBackFin, k, slot(k, k), P.row_ptr[k], P.row_ptr[k + 1] - P.row_ptr[k], 0, 0, 0});
+    for (int x = P.row_ptr[k]; x < P.row_ptr[k + 1]; ++x) {
+      const int i = P.rows[x];
+      push({L + (L - 1 - level[i]), 1, -level[k], i, k}, DagTask{kTaskBackTile, i, k, slot(i, k), x, 0, 0, 0});
+    }
+  }
+  std::stable_sort(all.begin(), all.end(), [](const Keyed& a, const Keyed& b) {
+    for (int n = 0; n < 7; ++n)
+      if (a.key[n] != b.key[n]) return a.key[n] < b.key[n];
+    return false;
+  });
+  D.tasks.reserve(all.size());
+  for (const Keyed& k : all) {
+    D.tasks.push_back(k.t);
+    if (k.t.type <= kTaskUpdate) D.n_factor_tasks = (int)D.tasks.size();
+  }
 }
 
 }  // namespace rsba

@@ -41,3 +41,39 @@ void build_tile_plan(int T, const std::vector<std::pair<int, int>>& tile_pairs, 
                      int border_tile, TilePlan* plan);
 
 }  // namespace rsba
+
+namespace rsba {
+
+// ---- the numeric factorisation and the triangular solves as ONE static task graph (k3_dag.cu) ----
+// The level-batched launch sequence above costs one launch boundary and one straggler wait per kernel
+// and level (~70 launches for the factorisation and ~30 for the solves of a video scene) and keeps
+// every update of level l in front of the panels of level l+1, needed or not.  The same work as a task
+// list for ONE persistent kernel: CTAs fetch tasks in list order and wait on device-side counters for
+// what a task depends on.  The list is a topological order of the dependency graph (every task only
+// waits for tasks in front of it), so in-order fetching cannot deadlock whatever the number of CTAs.
+enum DagTaskType : int {
+  kTaskFactor = 0,   // a = panel k, b = slot(k,k)
+  kTaskTrsm = 1,     // a = row tile i, b = panel k, c = part (rows 32c..32c+31), d = slot(i,k), e = slot(k,k),
+                     // f = forward-substitution slot (position of k in row i's list)
+  kTaskUpdate = 2,   // a = target slot(i,j), b = quadrant 2 qi + qj (48 x 48), c = how many groups of this
+                     // target run before this one, d = first source in `sources`, e = number of sources
+  kTaskBackFin = 3,  // a = panel k, b = slot(k,k), c = first backward slot of column k, d = tiles below k
+  kTaskBackTile = 4, // a = row tile i, b = panel k, c = slot(i,k), d = backward slot
+};
+struct DagTask { int type, a, b, c, d, e, f, g; };
+
+constexpr int kTrsmParts = 3;       // a tile's triangular solve is cut into 3 slabs of 32 rows
+
+struct DagPlan {
+  std::vector<DagTask> tasks;       // topological order; the factorisation first, then the backward substitution
+  std::vector<int2> sources;        // per update task: (slot(i,k), slot(j,k)) of S(i,j) -= L(i,k) L(j,k)^T
+  std::vector<int> need;            // [n_nz * 4] update groups that must have run on quadrant q of a tile
+  int n_factor_tasks = 0;           // tasks[0 .. n_factor_tasks) factorise (and substitute forward)
+};
+
+// merge_levels: sources of one target whose elimination levels lie more than one level below the
+// target's column are applied `merge_levels` levels at a time (one read-modify-write of the target for
+// all of them); the sources of the level right below the target's column always run on their own.
+void build_dag_plan(const TilePlan& plan, int merge_levels, DagPlan* dag);
+
+}  // namespace rsba
