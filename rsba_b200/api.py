@@ -44,7 +44,7 @@ SYMBOLS = [
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_reproject", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
-    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_analyze_structure", "rsba_cuda_structure_array",
+    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_plan_task_graph", "rsba_cuda_reduced_solve", "rsba_cuda_analyze_structure", "rsba_cuda_structure_array",
     "rsba_cuda_structure_free", "rsba_cuda_sort_observations", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
