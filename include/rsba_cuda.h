@@ -19,6 +19,8 @@
 #ifndef RSBA_CUDA_H_
 #define RSBA_CUDA_H_
 
+#include "rsba_ceres_constants.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -61,6 +63,11 @@ typedef struct rsba_solve_options {
   int dense_cholesky;                 /* 1: ignore the tile occupancy map, factor S fully dense */
   int reorder_tiles;                  /* 1: nested-dissection ordering of the reduced system (default);
                                          0: natural (frame) order */
+  int max_num_consecutive_invalid_steps; /* 5: a failed linear solve (reduced camera matrix not positive
+                                         definite, non-finite step) or a step with model_cost_change <= 0
+                                         is an INVALID step -- the radius shrinks and the loop goes on;
+                                         the solve fails only after this many in a row (Ceres 1.9
+                                         trust_region_minimizer.cc; values <= 0 mean 5) */
 } rsba_solve_options;
 
 /* Solver::Summary fields the reference reads (VideoSfMHandler.cc:593-596, 627-630). */
@@ -308,10 +315,13 @@ int rsba_cuda_plan_task_graph(int n_tiles, int n_pairs, const int* pair_a, const
  * ceres::Solve): solves A x = rhs on `device` for a symmetric positive definite A (n x n row-major,
  * n = 96 n_tiles) whose block pattern is given by the tile pairs (or dense).  mode 0 = task-graph kernel,
  * 1 = level-batched launches.  Optional outputs: L (n x n, in the PERMUTED tile order tile_pos_out[n_tiles]
- * describes), info (0, or 1 + index of the first non-positive pivot), device time of the numeric phase. */
+ * describes), info (0, or 1 + index of the first non-positive pivot), device time of the numeric phase
+ * (the fastest of `repeats` runs on the same data), and -- mode 0, trace_out[8 * tasks] -- per task of the
+ * last run {globaltimer ns at fetch, inputs ready, end; clock64 at the same three points; SM id; type}. */
 int rsba_cuda_reduced_solve(int device, int n_tiles, int n_pairs, const int* pair_a, const int* pair_b, int dense,
-                            int reorder, int mode, int merge_levels, const double* A, const double* rhs,
-                            double* x_out, double* L_out, int* tile_pos_out, int* info_out, float* ms_out);
+                            int reorder, int mode, int merge_levels, int repeats, const double* A,
+                            const double* rhs, double* x_out, double* L_out, int* tile_pos_out, int* info_out,
+                            float* ms_out, long long* trace_out);
 
 /* Host-only introspection of the WHOLE one-off structure analysis that rsba_cuda_solve runs before its first
  * linearisation -- what Ceres does in Program reordering + SchurEliminator block-structure detection + CHOLMOD's

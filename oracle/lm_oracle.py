@@ -18,6 +18,9 @@ restated from Ceres 1.9.0's published implementation
 * ``rho = (cost - new_cost) / model_cost_change``; accept iff ``rho > min_relative_decrease``;
   accept: ``radius /= max(1/3, 1 - (2 rho - 1)^3)`` (capped at max radius), ``decrease_factor = 2``;
   reject: ``radius /= decrease_factor; decrease_factor *= 2``.
+* Invalid steps: a failed factorisation of the reduced camera matrix (not positive definite), a non-finite
+  step or ``model_cost_change <= 0`` shrink the radius like a rejected step; ``max_num_consecutive_invalid_steps``
+  (5) of them in a row end the solve with FAILURE.
 * Termination: parameter tolerance ``|delta| <= 1e-8 (|x| + 1e-8)``, function tolerance
   ``|cost change| < 1e-6 cost``, gradient tolerance ``max|g| <= 1e-10``, max iterations.
 * Constant parameter blocks / components are removed from the program (their columns do not
@@ -34,6 +37,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 
 import numpy as np
+import scipy.linalg
 import scipy.sparse as sp
 
 
@@ -50,6 +54,7 @@ class Options:
     gradient_tolerance: float = 1e-10
     parameter_tolerance: float = 1e-8
     jacobi_scaling: bool = True
+    max_num_consecutive_invalid_steps: int = 5
 
 
 def param_masks(scene, pose_mask=None, point_const=None):
@@ -176,7 +181,12 @@ def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mas
     ECinv = (E @ Cinv_sp).tocsr()
     S = B - (ECinv @ E.T).toarray()
     rhs_y = g[:nc] - ECinv @ g[nc:]
-    y_c = np.linalg.solve(S, rhs_y)
+    solver_ok = True
+    try:    # Cholesky, like SparseSchurComplementSolver: a matrix that is not positive definite is a solver FAILURE
+        y_c = scipy.linalg.cho_solve(scipy.linalg.cho_factor(S, lower=True), rhs_y)
+    except (np.linalg.LinAlgError, ValueError):
+        solver_ok = False
+        y_c = np.full(nc, np.nan)
     y_p = np.einsum("pij,pj->pi", Cinv, (g[nc:] - E.T @ y_c).reshape(P, 3)).reshape(-1)
     step_s = -np.concatenate([y_c, y_p])
     step_s[~active] = 0.0
@@ -185,7 +195,7 @@ def lm_step(scene, r, J, radius, opts: Options = Options(), scale=None, pose_mas
     delta = step_s * scale
     return dict(S=S if want_S else None, rhs=-rhs_y, delta_poses=delta[:nc].reshape(F, 12),
                 delta_points=delta[nc:].reshape(P, 3), model_cost_change=mcc, scale=scale,
-                gradient=(Js.T @ rr), D2=D2, step_scaled=step_s)
+                gradient=(Js.T @ rr), D2=D2, step_scaled=step_s, solver_ok=solver_ok)
 
 
 def _block_diag(blocks):
@@ -241,6 +251,7 @@ def solve(scene, evaluate, opts: Options = Options(), pose_mask=None, point_cons
     D2_kept = None
     reuse = False
     it = 0
+    invalid_in_a_row = 0
     while True:
         if it >= opts.max_num_iterations:
             s.termination = "NO_CONVERGENCE: max iterations"
@@ -250,16 +261,22 @@ def solve(scene, evaluate, opts: Options = Options(), pose_mask=None, point_cons
             else _lm_step_reuse(scene, r, J, radius, opts, scale, pose_mask, point_const, D2_kept)
         D2_kept = st["D2_unit"] if "D2_unit" in st else st["D2"] * radius
         mcc = st["model_cost_change"]
-        if not (mcc > 0.0):
+        if not st["solver_ok"] or not np.isfinite(mcc) or not (mcc > 0.0):       # invalid step
+            invalid_in_a_row += 1
             s.num_unsuccessful_steps += 1
+            if invalid_in_a_row >= opts.max_num_consecutive_invalid_steps:
+                s.usable, s.termination = False, "FAILURE: successive invalid steps"
+                break
             radius /= decrease
             decrease *= 2.0
             reuse = True
-            s.trace.append(dict(it=it, cost=cost, accepted=False, radius=radius, reason="model"))
+            s.trace.append(dict(it=it, cost=cost, accepted=False, radius=radius,
+                                reason="model" if st["solver_ok"] else "linear solver"))
             if radius < opts.min_trust_region_radius:
                 s.termination = "CONVERGENCE: radius too small"
                 break
             continue
+        invalid_in_a_row = 0
         new_poses, new_points = poses + st["delta_poses"], points + st["delta_points"]
         r_new, _, v_new = evaluate(new_poses, new_points, False)
         step_norm = float(np.sqrt(np.sum(st["delta_poses"] ** 2) + np.sum(st["delta_points"] ** 2)))

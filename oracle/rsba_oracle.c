@@ -11,6 +11,7 @@
  */
 #include <math.h>
 #include <float.h>
+#include "../include/rsba_ceres_constants.h"
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>

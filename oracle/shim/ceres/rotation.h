@@ -12,6 +12,7 @@
 #include <cmath>
 #include <limits>
 #include "ceres/jet.h"
+#include "../../../include/rsba_ceres_constants.h"
 
 namespace ceres {
 
@@ -38,14 +39,14 @@ struct MatrixAdapter {
 // result = R(angle_axis) * pt.   Safe when result aliases pt: every input
 // component is consumed into temporaries before the first store.
 //
-// Threshold of the small-angle branch: see oracle/../rsba_b200/csrc/lm_constants.h
-// (RSBA_ANGLE_AXIS_EPS).  Ceres releases differ between `> 0.0` and
+// Threshold of the small-angle branch: RSBA_ANGLE_AXIS_EPS in include/rsba_ceres_constants.h, the one
+// header of recalled Ceres constants.  Ceres releases differ between `> 0.0` and
 // `> epsilon`; for theta2 in (0, eps] the two branches agree to < 1e-16 in value.
 template <typename T>
 inline void AngleAxisRotatePoint(const T angle_axis[3], const T pt[3], T result[3]) {
   using std::sqrt; using std::cos; using std::sin;
   const T theta2 = DotProduct(angle_axis, angle_axis);
-  if (theta2 > T(std::numeric_limits<double>::epsilon())) {
+  if (theta2 > T(RSBA_ANGLE_AXIS_EPS)) {
     const T theta = sqrt(theta2);
     const T costheta = cos(theta);
     const T sintheta = sin(theta);

@@ -67,6 +67,7 @@ class SolveOptions(C.Structure):
         ("verbose", C.c_int),
         ("dense_cholesky", C.c_int),
         ("reorder_tiles", C.c_int),
+        ("max_num_consecutive_invalid_steps", C.c_int),
     ]
 
 
@@ -168,8 +169,8 @@ def load_library():
     lib.rsba_cuda_linearize_and_step.argtypes = [vp, C.POINTER(SolveOptions), C.c_double, vp, vp, vp, vp, _dp]
     lib.rsba_cuda_plan_reduced_system.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp] + [vp] * 9
     lib.rsba_cuda_plan_task_graph.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
-    lib.rsba_cuda_reduced_solve.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
-                                            vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    lib.rsba_cuda_reduced_solve.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_float), vp]
     lib.rsba_cuda_analyze_structure.argtypes = [C.c_long, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp,
                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.rsba_cuda_structure_array.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
@@ -609,7 +610,7 @@ def plan_task_graph(n_tiles, pair_a, pair_b, dense=False, reorder=True, merge_le
 
 
 def reduced_solve(A, rhs, n_tiles, pair_a=(), pair_b=(), dense=False, reorder=True, mode="dag", merge_levels=4,
-                  want_L=False, device=0):
+                  want_L=False, device=0, repeats=1, want_trace=False):
     """K3 on its own, on the GPU: solves A x = rhs for an SPD matrix with the given tile pattern (tile = 96 rows).
     Returns dict(x, info, ms[, L, tile_pos]); L is in the permuted tile order that tile_pos describes."""
     lib = load_library()
@@ -623,14 +624,21 @@ def reduced_solve(A, rhs, n_tiles, pair_a=(), pair_b=(), dense=False, reorder=Tr
     L = np.zeros((n, n)) if want_L else None
     pos = np.zeros(int(n_tiles), dtype=np.int32)
     info, ms = C.c_int(0), C.c_float(0)
+    trace = None
+    if want_trace:
+        n_tasks = len(plan_task_graph(n_tiles, pa, pb, dense, reorder, merge_levels)["tasks"])
+        trace = np.zeros((n_tasks, 8), dtype=np.int64)
     rc = lib.rsba_cuda_reduced_solve(int(device), int(n_tiles), int(pa.size), _addr(pa), _addr(pb), int(dense),
-                                     int(reorder), {"dag": 0, "levels": 1}[mode], int(merge_levels), _addr(A),
-                                     _addr(rhs), _addr(x), _addr(L), _addr(pos), C.byref(info), C.byref(ms))
+                                     int(reorder), {"dag": 0, "levels": 1}[mode], int(merge_levels), int(repeats),
+                                     _addr(A), _addr(rhs), _addr(x), _addr(L), _addr(pos), C.byref(info), C.byref(ms),
+                                     _addr(trace))
     if rc != RSBA_OK:
         raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
     out = dict(x=x, info=info.value, ms=ms.value, tile_pos=pos)
     if want_L:
         out["L"] = L
+    if want_trace:
+        out["trace"] = trace
     return out
 
 

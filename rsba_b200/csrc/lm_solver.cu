@@ -556,8 +556,11 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   };
 
   HostScalars hs{};
-  double radius = opt->initial_trust_region_radius, decrease = 2.0;
+  double radius = opt->initial_trust_region_radius, decrease = RSBA_CERES_LM_INITIAL_DECREASE_FACTOR;
   double cost = 0.0, x_norm = 0.0, gmax = 0.0;
+  int invalid_in_a_row = 0, fail_rc = RSBA_OK;
+  const int max_invalid = opt->max_num_consecutive_invalid_steps > 0 ? opt->max_num_consecutive_invalid_steps
+                                                                      : RSBA_CERES_MAX_NUM_CONSECUTIVE_INVALID_STEPS;
   // ---- iteration 0: evaluate, linearise (fixes the Jacobi scaling), gradient check
   rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
   if (rc) return rc;
@@ -590,17 +593,39 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
       if ((rc = trial_cost(h, lm))) return rc;
       sum->num_residual_evaluations++;
       if ((rc = fetch(h, lm, &hs))) return rc;
-      if (hs.info != 0) {
-        finish(2, "FAILURE: reduced camera matrix is not positive definite", cost, radius, gmax);
-        wall();
-        return fail(RSBA_ERR_LINEAR_SOLVER, sum->message);
-      }
       const double mcc = -0.5 * hs.g_dot_delta + 0.5 * hs.d2_delta2;
       const double step_norm = hs.step_norm;
+      // Ceres 1.9 (trust_region_minimizer.cc): a failed linear solve, a non-finite step or a step that does not
+      // decrease the model is an INVALID step -- radius shrinks like after a rejected step and the loop goes
+      // on; only max_num_consecutive_invalid_steps of them in a row end the solve
+      const bool invalid = hs.info != 0 || !std::isfinite(step_norm) || !std::isfinite(mcc) || !(mcc > 0.0);
+      if (invalid) {
+        ++invalid_in_a_row;
+        sum->num_unsuccessful_steps++;
+        if (opt->verbose && h->rank == 0)
+          printf("%4d % .6e  invalid step (%s), radius % .2e\n", it, cost,
+                 hs.info != 0 ? "reduced camera matrix not positive definite" : "model cost does not decrease", radius);
+        if (invalid_in_a_row >= max_invalid) {
+          finish(2, hs.info != 0 ? "FAILURE: reduced camera matrix is not positive definite (successive invalid steps)"
+                                 : "FAILURE: number of successive invalid steps exceeds max_num_consecutive_invalid_steps",
+                 cost, radius, gmax);
+          fail_rc = fail(RSBA_ERR_LINEAR_SOLVER, sum->message);
+          break;
+        }
+        radius /= decrease;
+        decrease *= 2.0;
+        if (radius < opt->min_trust_region_radius) {
+          finish(0, "CONVERGENCE: trust region radius below minimum", cost, radius, gmax);
+          break;
+        }
+        if ((rc = linearize(h, lm, *opt, radius, false, false))) return rc;   // same Jacobian, new damping
+        continue;
+      }
+      invalid_in_a_row = 0;
       bool accepted = false;
       double rho = 0.0;
       const double new_cost = hs.trial_cost;
-      if (mcc > 0.0 && hs.trial_invalid == 0) {
+      if (hs.trial_invalid == 0) {
         if (step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
           finish(0, "CONVERGENCE: parameter tolerance reached", cost, radius, gmax);
           break;
@@ -619,8 +644,8 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         if (!h->pose_priors.empty())
           cudaMemcpyAsync(h->d_pp_val.ptr, h->d_pp_trial.ptr, h->d_pp_val.bytes(), cudaMemcpyDeviceToDevice, h->stream);
         radius = std::min(opt->max_trust_region_radius,
-                          radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
-        decrease = 2.0;
+                          radius / std::max(RSBA_CERES_LM_MIN_RADIUS_SHRINK, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+        decrease = RSBA_CERES_LM_INITIAL_DECREASE_FACTOR;
         rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
         if (rc) return rc;
         sum->num_jacobian_evaluations++;
@@ -660,7 +685,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
     if (rc) return rc;
   }
   wall();
-  return RSBA_OK;
+  return fail_rc;   // a failed solve still leaves the last accepted iterate in the caller's blocks
   });
 }
 

@@ -1182,21 +1182,23 @@ double rsba_cuda_stage_ms(rsba_problem* h, int stage) {
 void rsba_cuda_default_options(rsba_solve_options* o) {
   if (!o) return;
   memset(o, 0, sizeof(*o));
-  o->max_num_iterations = 50;
-  o->initial_trust_region_radius = 1e4;
-  o->max_trust_region_radius = 1e16;
-  o->min_trust_region_radius = 1e-32;
-  o->min_relative_decrease = 1e-3;
-  o->min_lm_diagonal = 1e-6;
-  o->max_lm_diagonal = 1e32;
-  o->function_tolerance = 1e-6;
-  o->gradient_tolerance = 1e-10;
-  o->parameter_tolerance = 1e-8;
-  o->jacobi_scaling = 1;
+  // recalled Ceres 1.9.0 defaults: include/rsba_ceres_constants.h
+  o->max_num_iterations = RSBA_CERES_MAX_NUM_ITERATIONS;
+  o->initial_trust_region_radius = RSBA_CERES_INITIAL_TRUST_REGION_RADIUS;
+  o->max_trust_region_radius = RSBA_CERES_MAX_TRUST_REGION_RADIUS;
+  o->min_trust_region_radius = RSBA_CERES_MIN_TRUST_REGION_RADIUS;
+  o->min_relative_decrease = RSBA_CERES_MIN_RELATIVE_DECREASE;
+  o->min_lm_diagonal = RSBA_CERES_MIN_LM_DIAGONAL;
+  o->max_lm_diagonal = RSBA_CERES_MAX_LM_DIAGONAL;
+  o->function_tolerance = RSBA_CERES_FUNCTION_TOLERANCE;
+  o->gradient_tolerance = RSBA_CERES_GRADIENT_TOLERANCE;
+  o->parameter_tolerance = RSBA_CERES_PARAMETER_TOLERANCE;
+  o->jacobi_scaling = RSBA_CERES_JACOBI_SCALING;
   o->huber_loss = 0.0;
   o->verbose = 0;
   o->dense_cholesky = 0;
   o->reorder_tiles = 1;
+  o->max_num_consecutive_invalid_steps = RSBA_CERES_MAX_NUM_CONSECUTIVE_INVALID_STEPS;
 }
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 // __host__ __device__ so that tests/tools can run the very same code on the CPU as a
 // debugging aid; the product library only ever calls it from device code.
 #pragma once
+#include "../../include/rsba_ceres_constants.h"
 #include "common.cuh"
 #include <cfloat>
 #include <cmath>
@@ -53,7 +54,7 @@ __host__ __device__ __forceinline__ Proj reproject(const CameraModel& cm, double
   double P0, P1, P2;
   double R[9];       // rotation matrix, row-major            (JAC)
   double dPr[9];     // dP/dr, row-major [component][k]       (JAC)
-  if (theta2 > DBL_EPSILON) {
+  if (theta2 > RSBA_ANGLE_AXIS_EPS) {   // (recalled Ceres constant: include/rsba_ceres_constants.h)
     const double theta = sqrt(theta2);
     double s, co;
     sincos(theta, &s, &co);

@@ -224,3 +224,47 @@ def test_lm_step_and_solve_with_huber_loss(api, oracle_built, lo):
     e_rob = np.linalg.norm(pt - sc.points_true)
     e_plain = np.linalg.norm(pt_plain - sc.points_true)
     assert e_rob < e_plain
+
+
+def gauge_free_problem(api, sc):
+    pb = api.Problem(0)
+    pb.set_camera(sc.cam, sc.shutter, sc.scanlines, sc.interpolate_rotation)
+    pb.set_scene(sc.obs_xy, sc.obs_frame, sc.obs_point, sc.num_frames, sc.num_points,
+                 const_pose_mask=np.zeros(sc.num_frames, dtype=np.uint16))
+    pb.set_parameters(sc.poses, sc.points)
+    return pb
+
+
+def test_failed_linear_solve_is_an_invalid_step_not_the_end(api, oracle_built, lo):
+    """Ceres 1.9 (trust_region_minimizer.cc; reached through CeresHandler.h:419): a reduced camera matrix that
+    is not positive definite is an INVALID step -- radius /= decrease_factor, try again -- and only
+    max_num_consecutive_invalid_steps of them in a row end the solve.  Scene: no constant frame (the 7-dof
+    gauge freedom makes S singular) and a trust region so large that the damping is below rounding."""
+    sc = small_scene()
+    pm = np.zeros(sc.num_frames, dtype=np.int64)
+    ev = lambda po, pt, jac: oracle_built.evaluate(sc, po, pt, jac=jac, impl="port")  # noqa: E731
+    kw = dict(max_num_iterations=30, initial_trust_region_radius=1e20, max_trust_region_radius=1e32)
+    _, _, want = lo.solve(sc, ev, lo.Options(max_num_consecutive_invalid_steps=40, **kw), pose_mask=pm)
+    assert want.usable and any(t.get("reason") == "linear solver" for t in want.trace)
+    with gauge_free_problem(api, sc) as pb:
+        s = pb.solve(api.default_options(max_num_consecutive_invalid_steps=40, **kw))
+        assert s.usable == 1 and s.termination in (0, 1)
+        assert s.num_unsuccessful_steps >= 1
+        assert s.iterations == s.num_successful_steps + s.num_unsuccessful_steps
+        # same rule, same neighbourhood: where the factorisation first succeeds depends on rounding, so the two
+        # trajectories are not identical -- both must have done most of the descent
+        assert s.final_cost <= 1.5 * want.final_cost and want.final_cost <= 1.5 * s.final_cost
+        assert s.final_cost < 0.05 * s.initial_cost
+
+
+def test_successive_invalid_steps_fail_and_leave_the_last_accepted_iterate(api):
+    sc = small_scene()
+    with gauge_free_problem(api, sc) as pb:
+        opt = api.default_options(max_num_iterations=30, initial_trust_region_radius=1e20, max_trust_region_radius=1e32,
+                                  max_num_consecutive_invalid_steps=2)
+        s = pb.solve(opt, check=False)
+        assert s.usable == 0 and s.termination == 2
+        assert s.num_successful_steps == 0 and s.iterations == 2
+        assert b"invalid steps" in s.message or b"positive definite" in s.message
+        po, pt = pb.get_parameters()
+        assert np.array_equal(po, sc.poses) and np.array_equal(pt, sc.points)

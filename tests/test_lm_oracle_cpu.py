@@ -120,3 +120,23 @@ def test_matrix_free_normal_equation_check_used_at_full_size():
     bad = st["delta_poses"].copy()
     bad[57, 4] *= 1.001
     assert damped_normal_equation_residual(sc, r, J, bad, st["delta_points"], 1e4)[2] >= 2e-6
+
+
+def test_invalid_steps_shrink_the_radius_and_only_a_run_of_them_fails():
+    """Ceres 1.9's rule for a failed linear solve / a step with model_cost_change <= 0 (trust_region_minimizer.cc,
+    restated; constants in include/rsba_ceres_constants.h): the GPU loop follows the same rule
+    (tests/test_gpu_lm.py::test_failed_linear_solve_is_an_invalid_step_not_the_end)."""
+    from helpers import small_scene
+    sc = small_scene()
+    pm = np.zeros(sc.num_frames, dtype=np.int64)          # no constant frame: gauge freedom, S singular undamped
+    ev = lambda po, pt, jac: oracle.evaluate(sc, po, pt, jac=jac, impl="port")  # noqa: E731
+    kw = dict(max_num_iterations=30, initial_trust_region_radius=1e20, max_trust_region_radius=1e32)
+    _, _, ok = lm_oracle.solve(sc, ev, lm_oracle.Options(max_num_consecutive_invalid_steps=40, **kw), pose_mask=pm)
+    fails = [t for t in ok.trace if t.get("reason") == "linear solver"]
+    assert ok.usable and len(fails) >= 2 and ok.final_cost < 0.05 * ok.initial_cost
+    # the radius halves, quarters, ... exactly like after rejected steps
+    radii = [t["radius"] for t in fails]
+    assert np.allclose(radii[:2], [1e20 / 2, 1e20 / 8])
+    po, pt, bad = lm_oracle.solve(sc, ev, lm_oracle.Options(max_num_consecutive_invalid_steps=2, **kw), pose_mask=pm)
+    assert not bad.usable and "invalid" in bad.termination and bad.iterations == 2
+    assert np.array_equal(po, sc.poses) and np.array_equal(pt, sc.points)
