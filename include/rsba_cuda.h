@@ -143,6 +143,12 @@ int rsba_cuda_set_loss(rsba_problem* h, double huber_a);
  * which must stay put until the handle is destroyed.  Results are written back in place. */
 int rsba_cuda_add_rs_residual(rsba_problem* h, const double observed[2], double* pose0,
                               double* pose1, double* point);
+/* ceres::Problem::AddParameterBlock for one frame: registers the two control-pose blocks of a frame that no
+ * rolling-shutter residual block or motion prior has introduced yet -- a frame that (so far) only carries
+ * GoodPosePrior blocks (CeresHandler.h:188-204), which name ONE pose block each and cannot tell the library
+ * which blocks form a frame.  Ceres accepts such a problem; so does rsba_cuda_solve.  Idempotent. */
+int rsba_cuda_add_frame_blocks(rsba_problem* h, double* pose0, double* pose1);
+
 /* Replaces: RsConstVeloPrior::Create(scale) / RsConstAccelerationPrior::Create(scale) +
  * problem.AddResidualBlock(cost, loss, &opt.ceres.interFrameRatio, f.poses[0], f.poses[1],
  * f_1.poses[0], f_1.poses[1])  (CeresHandler.h:148-186; functors video_bundler_rs_inter.h:55-173):
@@ -316,8 +322,9 @@ int rsba_cuda_plan_task_graph(int n_tiles, int n_pairs, const int* pair_a, const
  * n = 96 n_tiles) whose block pattern is given by the tile pairs (or dense).  mode 0 = task-graph kernel,
  * 1 = level-batched launches.  Optional outputs: L (n x n, in the PERMUTED tile order tile_pos_out[n_tiles]
  * describes), info (0, or 1 + index of the first non-positive pivot), device time of the numeric phase
- * (the fastest of `repeats` runs on the same data), and -- mode 0, trace_out[8 * tasks] -- per task of the
- * last run {globaltimer ns at fetch, inputs ready, end; clock64 at the same three points; SM id; type}. */
+ * (the fastest of `repeats` runs on the same data), and -- mode 0, trace_out[16 * tasks] -- per task of the
+ * last run {globaltimer ns at fetch, inputs ready, end; clock64 at the same three points; SM id; type;
+ * FACTOR tasks also clock64 after load / factorisation / inversion / stores and two phase sums}. */
 int rsba_cuda_reduced_solve(int device, int n_tiles, int n_pairs, const int* pair_a, const int* pair_b, int dense,
                             int reorder, int mode, int merge_levels, int repeats, const double* A,
                             const double* rhs, double* x_out, double* L_out, int* tile_pos_out, int* info_out,

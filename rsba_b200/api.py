@@ -37,7 +37,7 @@ SYMBOLS = [
     "rsba_cuda_create", "rsba_cuda_destroy", "rsba_cuda_last_error", "rsba_cuda_set_stream",
     "rsba_cuda_default_options", "rsba_cuda_set_camera", "rsba_cuda_set_intrinsics_free", "rsba_cuda_add_rs_residual_with_intrinsics", "rsba_cuda_get_camera", "rsba_cuda_get_intrinsics_jacobian",
     "rsba_cuda_set_loss", "rsba_cuda_add_rs_residual",
-    "rsba_cuda_add_motion_prior", "rsba_cuda_set_motion_priors", "rsba_cuda_get_prior_residuals",
+    "rsba_cuda_add_frame_blocks", "rsba_cuda_add_motion_prior", "rsba_cuda_set_motion_priors", "rsba_cuda_get_prior_residuals",
     "rsba_cuda_set_inter_frame_ratio_block", "rsba_cuda_set_inter_frame_ratio_free", "rsba_cuda_get_inter_frame_ratio",
     "rsba_cuda_get_prior_ratio_jacobian",
     "rsba_cuda_add_pose_prior", "rsba_cuda_set_pose_priors", "rsba_cuda_get_pose_priors",
@@ -139,6 +139,7 @@ def load_library():
     lib.rsba_cuda_get_intrinsics_jacobian.argtypes = [vp, vp]
     lib.rsba_cuda_set_loss.argtypes = [vp, C.c_double]
     lib.rsba_cuda_add_rs_residual.argtypes = [vp, _dp, vp, vp, vp]
+    lib.rsba_cuda_add_frame_blocks.argtypes = [vp, vp, vp]
     lib.rsba_cuda_add_motion_prior.argtypes = [vp, C.c_int, C.c_double, C.c_double, vp, vp, vp, vp]
     lib.rsba_cuda_set_motion_priors.argtypes = [vp, C.c_int, _ip, _dp, _dp, _ip, _ip]
     lib.rsba_cuda_get_prior_residuals.argtypes = [vp, vp]
@@ -295,6 +296,11 @@ class Problem:
         self._keep.extend((pose0, pose1, point))
         self._check(self.lib.rsba_cuda_add_rs_residual(self._h, obs.ctypes.data_as(_dp), _addr(pose0),
                                                        _addr(pose1), _addr(point)))
+
+    def add_frame_blocks(self, pose0: np.ndarray, pose1: np.ndarray):
+        """ceres::Problem::AddParameterBlock for a frame's two control poses (a frame with pose priors only)."""
+        self._keep += [pose0, pose1]
+        self._check(self.lib.rsba_cuda_add_frame_blocks(self._h, _addr(pose0), _addr(pose1)))
 
     def add_motion_prior(self, kind, scale, ratio, pose0, end0, pose1, end1):
         """RsConstVeloPrior (kind 1) / RsConstAccelerationPrior (kind 2) between frame k = (pose0, end0)
@@ -627,7 +633,7 @@ def reduced_solve(A, rhs, n_tiles, pair_a=(), pair_b=(), dense=False, reorder=Tr
     trace = None
     if want_trace:
         n_tasks = len(plan_task_graph(n_tiles, pa, pb, dense, reorder, merge_levels)["tasks"])
-        trace = np.zeros((n_tasks, 8), dtype=np.int64)
+        trace = np.zeros((n_tasks, 16), dtype=np.int64)
     rc = lib.rsba_cuda_reduced_solve(int(device), int(n_tiles), int(pa.size), _addr(pa), _addr(pb), int(dense),
                                      int(reorder), {"dag": 0, "levels": 1}[mode], int(merge_levels), int(repeats),
                                      _addr(A), _addr(rhs), _addr(x), _addr(L), _addr(pos), C.byref(info), C.byref(ms),

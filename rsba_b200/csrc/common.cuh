@@ -1,29 +1,15 @@
 // Internal declarations shared by the kernels and the host driver (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include "../../include/rsba_reproj_math.h"
 #include <cstdint>
 #include <cstdio>
 
 namespace rsba {
 
-constexpr int kPoseParams = 6;    // NUM_POSE_PARAMS  (mat/cam.h:20)
-constexpr int kPointParams = 3;   // NUM_POINT_PARAMS (mat/cam.h:19)
-constexpr int kFrameParams = 12;  // pose0 | pose1
-constexpr int kJacDoubles = 30;   // 2x6 | 2x6 | 2x3
 
-// Per-session constants captured by every cost functor (VideoSfmBaRs.h:16-22).
-struct CameraModel {
-  double cam[9];       // fx fy k1 k2 p1 p2 k3 cx cy
-  double scan0;        // scanlines[0]
-  double scan_span;    // scanlines[1] - scanlines[0]
-  int shutter;         // 0 GLOBAL, 1 HORIZONTAL, 2 VERTICAL
-  int interp_rot;      // opt.model.interpolateRotation
-  double huber;        // ceres::HuberLoss(a) on every residual block (CeresHandler.h:85-90); 0 = no loss
-  // Uncalibrated variant (RsBundleAdjustment::CreateWithCam <2; 9, 6, 6, 3>, VideoSfmBaRs.h:38-49,68-80): the
-  // shared intrinsics are a PARAMETER block.  It lives behind the frames in the pose array, as a
-  // pseudo-frame: poses[cam_offset .. cam_offset+8] = fx fy k1 k2 p1 p2 k3 cx cy; -1 = calibrated.
-  long cam_offset;
-};
+// CameraModel (the per-session constants every cost functor captures) lives in the public header
+// include/rsba_reproj_math.h together with the per-observation arithmetic.
 
 // Observation SoA, sorted by frame.
 struct ObsView {

@@ -126,7 +126,7 @@ int rsba_cuda_reduced_solve(int device, int n_tiles, int n_pairs, const int* pai
                  bwd_partials.ptr};
     DeviceBuffer<long long> trace;
     if (trace_out && mode == 0) {
-      RSBA_CUDA_TRY(trace.resize(std::max<size_t>(dag.tasks.size(), 1) * 8));
+      RSBA_CUDA_TRY(trace.resize(std::max<size_t>(dag.tasks.size(), 1) * 16));
       RSBA_CUDA_TRY(cudaMemset(trace.ptr, 0, trace.bytes()));
       dd.trace = trace.ptr;
     }
@@ -164,7 +164,7 @@ int rsba_cuda_reduced_solve(int device, int n_tiles, int n_pairs, const int* pai
     RSBA_CUDA_TRY(cudaGetLastError());
     if (ms_out) *ms_out = ms;
     if (dd.trace)   // time stamps of the LAST run
-      RSBA_CUDA_TRY(cudaMemcpy(trace_out, trace.ptr, dag.tasks.size() * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+      RSBA_CUDA_TRY(cudaMemcpy(trace_out, trace.ptr, dag.tasks.size() * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
     int h_info = 0;
     RSBA_CUDA_TRY(cudaMemcpy(&h_info, info.ptr, sizeof(int), cudaMemcpyDeviceToHost));
     if (info_out) *info_out = h_info;

@@ -175,7 +175,7 @@ struct DagDevice {
   const int* need;          // [n_nz * 4]
   int* counters;            // [dag_counter_ints] device-side dependency counters (cleared by the launcher)
   double* bwd_partials;     // [off-diagonal tiles][96]
-  long long* trace = nullptr;  // optional [n_tasks][8] per-task time stamps (rsba_cuda_reduced_solve's trace_out)
+  long long* trace = nullptr;  // optional [n_tasks][16] per-task time stamps (rsba_cuda_reduced_solve's trace_out)
 };
 size_t dag_counter_ints(const TileSchedule& ts);
 // factor: L, inverses of the diagonal factors, z = L^-1 x;  solve: x = L^-T z.  Returns the launches issued.

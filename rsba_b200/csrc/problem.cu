@@ -711,6 +711,18 @@ static int frame_of_blocks(rsba_problem* h, double* pose0, double* pose1) {
   return it->second;
 }
 
+int rsba_cuda_add_frame_blocks(rsba_problem* h, double* pose0, double* pose1) {
+  return rsba::api_guard([&]() -> int {
+  if (!h || !pose0 || !pose1) return fail(RSBA_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (h->scene_set && !h->ptr_mode) return fail(RSBA_ERR_STATE, "handle already holds a bulk scene");
+  h->ptr_mode = true;
+  const int f = frame_of_blocks(h, pose0, pose1);
+  if (f < 0) return f;
+  h->ptr_dirty = true;
+  return RSBA_OK;
+  });
+}
+
 int rsba_cuda_add_motion_prior(rsba_problem* h, int kind, double scale, double inter_frame_ratio, double* pose0,
                                double* end0, double* pose1, double* end1) {
   return rsba::api_guard([&]() -> int {

@@ -199,3 +199,25 @@ def test_handler_good_pose_priors(tmp_path):
     assert np.array_equal(blocks[0], prior0[0])                      # frame 0 < fixFirstNCameras: no prior, untouched
     assert np.linalg.norm(blocks[1:].reshape(-1, 6) - val) <= 1e-7 * np.linalg.norm(val)
     assert np.abs(blocks[1:] - prior0[1:]).max() > 1e-6              # the free prior blocks moved
+
+
+@pytest.mark.gpu
+def test_handler_frame_with_pose_priors_only(tmp_path):
+    """A frame that carries GoodPosePrior blocks and NO observation (nor a motion prior) is a legal Ceres problem
+    (CeresHandler.h:188-204 adds the priors before the residual loop): its control poses are registered through
+    rsba_cuda_add_frame_blocks and the solve moves them half-way to the (free) prior blocks -- both ends of a
+    GoodPosePrior are parameter blocks, so pose and prior meet in the middle of the weighted residual."""
+    sc = make_scene(10, 300, 8, name="good-handler")
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    r = subprocess.run([BIN, src, dst, "1", "8", "0", "5"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(dst)
+    nf, npnt = sc.num_frames, sc.num_points
+    assert out[0] == 1 and out[3] < out[2]
+    poses = out[4:4 + 12 * nf].reshape(nf, 2, 6)
+    blocks = out[4 + 12 * nf + 3 * npnt:].reshape(nf, 2, 6)
+    # last frame: no observation -> the only residual on its poses is the prior, which the solve drives to zero
+    assert np.abs(poses[-1] - blocks[-1]).max() <= 1e-6
+    assert np.abs(poses[-1] - sc.poses[-1].reshape(2, 6)).max() > 1e-5      # ... by moving both ends
+    assert not poses[0].any()

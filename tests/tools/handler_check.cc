@@ -8,7 +8,9 @@
 //    gs = 2: uncalibrated, opt.model.calibrated = false -- the optimised sess.cam is appended to the output;
 //    gs = 3: constant-velocity priors with the default, free interFrameRatio -- the ratio is appended;
 //    gs = 4: GoodPosePrior on every frame past the first, priorPoses = the initial poses + a fixed offset --
-//            the (free, hence moved) prior blocks are appended)
+//            the (free, hence moved) prior blocks are appended;
+//    gs = 5: as 4, and the LAST frame loses its observations: a frame that carries pose priors only, which Ceres
+//            accepts (its poses move to where the priors pull them))
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -18,7 +20,7 @@
 
 namespace mock {
 struct IsSetObs { bool track = false; };
-struct IsSetFrame { bool cam = false, priorPoses = false; };
+struct IsSetFrame { bool cam = false, priorPoses = false, poses = false; };
 struct ObservationRef { int frame = 0, obs = 0; };
 struct Observation { double x = 0, y = 0; int track = -1; IsSetObs __isset; std::vector<ObservationRef> matches; };
 struct IsSetTrack { bool pt = false; };
@@ -33,11 +35,13 @@ struct Session {
   Track& getTrack(int id) { return tracks.at(id); }
 };
 struct Options {
-  struct { bool use3Dpoints = true, calibrated = true, constVelocity = false, interpolateRotation = true; } model;
+  struct { bool use3Dpoints = true, calibrated = true, constVelocity = false, interpolateRotation = true, rolling_shutter = true; } model;
+  struct { double sqrdThreshold = 16.0; unsigned minDistanceToCamera = 0; } tracks;
   struct {
     double huberLoss = 0, constFrameVelocity = 0, constFrameAcceleration = 0, interFrameRatio = 1;
     double trustPriorCamRotation = 0, trustPriorCamPosition = 0;
     bool const3d = false, fixScale = false, fixRotation = false, fixPosition = false, useOnlyValidMatches = false;
+    bool revalidateReprojections = false;
     unsigned fixFirstNCameras = 1;
   } ceres;
 };
@@ -71,11 +75,13 @@ int main(int argc, char** argv) {
   const bool gs = argc > 6 && atoi(argv[6]) == 1;
   const bool uncal = argc > 6 && atoi(argv[6]) == 2;
   const bool velo = argc > 6 && atoi(argv[6]) == 3;   // constant-velocity priors, default (free) interFrameRatio
-  const bool good = argc > 6 && atoi(argv[6]) == 4;   // GoodPosePrior blocks
+  const bool prior_only = argc > 6 && atoi(argv[6]) == 5;
+  const bool good = (argc > 6 && atoi(argv[6]) == 4) || prior_only;   // GoodPosePrior blocks
   if (gs) sess.rs = 0;
   sess.frames.resize(F);
   for (long k = 0; k < F; ++k) {
     sess.frames[k].poses.assign(gs ? 1 : 2, std::vector<double>(6));
+    sess.frames[k].__isset.poses = true;
     for (int c = 0; c < 6; ++c) {
       sess.frames[k].poses[0][c] = poses[12 * k + c];
       if (!gs) sess.frames[k].poses[1][c] = poses[12 * k + 6 + c];
@@ -113,6 +119,7 @@ int main(int argc, char** argv) {
       sess.frames[k].__isset.priorPoses = true;
     }
   }
+  if (prior_only) sess.frames[F - 1].obs.clear();
   double ratio_out = 1.0;
   const size_t startFrame = argc > 5 ? (size_t)atol(argv[5]) : 0;
 

@@ -28,6 +28,11 @@ def summarize(trace, tasks):
                    "run_cycles_median": float(np.median(run_ck)), "wait_us_median": float(np.median(wait)),
                    "wait_us_max": float(wait.max())}
     fac = np.flatnonzero(tasks[:, 0] == 0)
+    f = trace[fac]
+    out["factor_phase_cycles_median"] = {
+        "load": float(np.median(f[:, 8] - f[:, 4])), "factorise": float(np.median(f[:, 9] - f[:, 8])),
+        "invert": float(np.median(f[:, 10] - f[:, 9])), "store_and_forward": float(np.median(f[:, 11] - f[:, 10])),
+        "panels_sum_warp0": float(np.median(f[:, 12])), "phase1_sum": float(np.median(f[:, 13]))}
     ends = np.sort(trace[fac, 2] - t0) / 1e3
     out["factor_end_us_sorted_tail"] = [float(v) for v in ends[-24:]]
     nf = (tasks[:, 0] <= 2)
