@@ -232,7 +232,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "M evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_iteration"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "step": STEP_DESC, "sample": base["sample"]},
+        "config": bench_config(args.config), "sample": base["sample"],
         "lm_iters_per_sec": 1e3 / base["ms_per_iteration"],
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "M evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -247,6 +247,8 @@ WORKLOADS = {
     "C2": "C2: 100 frames / 20k points / 500k observations synthetic RS scene",
     "C3": "C3: 1000 frames / 200k points / 5M observations synthetic RS scene",
     "C5": "C5: 4000 frames / 1M points / 20M observations synthetic RS scene",
+    "C2dense": "C2dense: 100 frames / 20k points / 500k observations, every frame pair covisible (orbit): dense reduced system",
+    "C3dense": "C3dense: 1000 frames / 200k points / 5M observations, every frame pair covisible (orbit): dense reduced system",
 }
 STEP_DESC = ("one Levenberg-Marquardt iteration of rsba_cuda_solve: residual+Jacobian (K1), block normal "
              "equations + Schur complement (K2), tile Cholesky + solves (K3), back-substitution/step (K4), "
@@ -259,7 +261,34 @@ def bench_options(api, iters):
                                parameter_tolerance=0.0)
 
 
-FP64_PEAK_TFLOPS = 37.1   # tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.txt): DMMA == DFMA rate
+FP64_PEAK_FALLBACK_TFLOPS = 37.1   # profiles/r01_fp64_peak.txt; only used if the in-run measurement fails
+
+
+def fp64_peak(api, device):
+    """FP64 peak of THIS device, measured in this run by the library itself (rsba_cuda_measure_fp64_peak:
+    register-resident DFMA chains and mma.sync.m8n8k4.f64 chains; MEASURED_PEAKS.json has no FP64 figure)."""
+    try:
+        dfma, dmma = api.measure_fp64_peak(device)
+        peak = max(dfma, dmma)
+        if peak > 1.0:
+            return peak, (f"measured in this run: DFMA {dfma:.2f}, DMMA {dmma:.2f} TFLOP/s "
+                          "(rsba_cuda_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure")
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] FP64 peak measurement failed: {e}")
+    return FP64_PEAK_FALLBACK_TFLOPS, "fallback: profiles/r01_fp64_peak.txt (in-run measurement failed)"
+
+
+def dram_traffic(kernel, config, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest committed
+    `ncu --set full` summary (profiles/traffic.json: {kernel: {config, bytes, source, commit}}); None when there is
+    no capture of this kernel on this workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+    except (OSError, KeyError, ValueError):
+        return None, None
+    if t.get("config") != config or world != 1:
+        return None, None
+    return float(t["bytes"]), f'{t["source"]} @ {t.get("commit", "?")}'
 
 
 def schur_algorithmic_flops(scene) -> float:
@@ -392,6 +421,25 @@ def run_ours(args):
         barrier()
         cold_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
+    # ---------------- parity of the sharded solve with the single-GPU one (outside every timed region): rank 0
+    # re-solves the same K iterations from the same initial estimate on its own GPU alone and compares
+    parity = None
+    if world > 1:
+        pb.set_parameters(poses_h, points_h)
+        s_multi = pb.solve(bench_options(api, args.steps))
+        pb.get_parameters(out_poses, out_points)
+        if rank == 0:
+            po_m, pt_m = out_poses.numpy().copy(), out_points.numpy().copy()
+            with api.Problem(local) as p1:
+                p1.set_stream(stream.cuda_stream)
+                p1.load_scene(scene)
+                s_one = p1.solve(bench_options(api, args.steps))
+                po_1, pt_1 = p1.get_parameters()
+            rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))  # noqa: E731
+            parity = {"final_cost_rel": abs(s_multi.final_cost - s_one.final_cost) / s_one.final_cost,
+                      "poses_rel": rel(po_m, po_1), "points_rel": rel(pt_m, pt_1),
+                      "successful_steps": [int(s_multi.num_successful_steps), int(s_one.num_successful_steps)]}
+        barrier()
     h2d = (poses_h.numel() + points_h.numel()) * 8 / args.steps
     d2h = (poses_h.numel() + points_h.numel()) * 8 / args.steps + 7 * 8 + 8
     if world > 1:
@@ -402,50 +450,55 @@ def run_ours(args):
         return
 
     hbm_peak, hbm_src = load_peaks()
+    fp64_tf, fp64_src = fp64_peak(api, local)
     bpo = k1_bytes_per_obs(scene)
     k1 = kern["jacobian"]
     n_local = int(summ.num_residual_blocks)     # this rank's share of the observations (== n_total on one GPU)
     share = n_local / n_total
+    tr_k1, tr_k1_src = dram_traffic("k1_kernel", args.config, world)
     roof_k1 = {"bound": "hbm", "kernel": "k1_kernel<true> (residual + Jacobian)", "achieved": n_local * bpo / (k1 * 1e-3) / 1e9,
-               "peak": hbm_peak, "unit": "GB/s", "traffic": 1.370e9, "peak_source": hbm_src,
+               "peak": hbm_peak, "unit": "GB/s", "traffic": tr_k1, "traffic_source": tr_k1_src, "peak_source": hbm_src,
                "algorithmic_bytes": n_local * bpo, "bytes_per_obs": bpo, "kernel_ms": k1,
-               "k1_only_M_evals_per_s": n_local / (k1 * 1e-3) / 1e6, "observations_on_this_rank": n_local,
-               "traffic_source": "profiles/r01n_k1_k2_full.txt (ncu --set full, dram read+write per launch, C3 on one GPU)",
-               "write_stream_note": "K1 is a write stream (1.23 GB written, 0.14 GB read); a pure write stream measures 7.5 TB/s on this pool, the read+write copy 6.66 TB/s (profiles/r01m_hbm_write_peak.txt)"}
+               "k1_only_M_evals_per_s": n_local / (k1 * 1e-3) / 1e6, "observations_on_this_rank": n_local}
     roof_k1["frac"] = roof_k1["achieved"] / hbm_peak
-    if world > 1 or args.config != "C3":
-        roof_k1["traffic"] = None
     fl = schur_algorithmic_flops(scene) * share       # rank 0's share of the points
-    fp64_src = "tools/fp64_peak.cu measured on this pool (profiles/r01_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 figure"
+    tr_sy, tr_sy_src = dram_traffic("schur_syrk_kernel", args.config, world)
     roof_syrk = {"bound": "tensor", "kernel": "schur_syrk_kernel (Schur complement, FP64 mma.sync m8n8k4)",
-                 "achieved": fl / (kern["schur_syrk"] * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                 "traffic": 3.358e9 if (world == 1 and args.config == "C3") else None,
-                 "traffic_source": "profiles/r01n_k1_k2_full.txt (dram read+write of one launch, C3 on one GPU; the panels are 1.8 GB)",
-                 "peak_source": fp64_src, "algorithmic_flops": fl, "kernel_ms": kern["schur_syrk"],
-                 "executed_flops_note": "6.3e10 executed at C3 (zero rows of partially seen 2-frame halves, 21 of 36 tiles on diagonal pairs); the kernel also moves 14.5 GB of panels L2 -> shared memory per launch (6.5 TB/s), its second ceiling (profiles/r01_notes.md)"}
-    roof_syrk["frac"] = roof_syrk["achieved"] / FP64_PEAK_TFLOPS
-    cf = band_cholesky_flops(scene)
-    k3_ms = kern["cholesky"]     # factorisation + both substitutions: one persistent task-graph kernel (k3_dag.cu)
+                 "achieved": fl / (kern["schur_syrk"] * 1e-3) / 1e12, "peak": fp64_tf, "unit": "TFLOP/s",
+                 "traffic": tr_sy, "traffic_source": tr_sy_src, "peak_source": fp64_src, "algorithmic_flops": fl,
+                 "kernel_ms": kern["schur_syrk"]}
+    roof_syrk["frac"] = roof_syrk["achieved"] / fp64_tf
+    # K3: factorisation + both substitutions are ONE persistent task-graph kernel (k3_dag.cu).  Algorithmic flops =
+    # what the tile plan of this scene executes (sum over non-zero tiles after fill: potrf n^3/3, trsm n^3, update 2 n^3),
+    # which is n b^2 for a banded (video) scene and n^3 / 3 for a fully covisible one.
+    k3_ms = kern["cholesky"]
+    cf = float(summ.tile_flops) if getattr(summ, "tile_flops", 0) else band_cholesky_flops(scene)
+    tr_k3, tr_k3_src = dram_traffic("k3_dag_kernel", args.config, world)
     roof_chol = {"bound": "tensor", "kernel": "k3_dag_kernel (tile Cholesky + forward/backward substitution, one persistent kernel)",
-                 "achieved": cf / (k3_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                 "traffic": None, "peak_source": fp64_src, "algorithmic_flops": cf, "kernel_ms": k3_ms,
-                 "note": "latency-bound: a chain of dependent 96x96 panel factorisations"}
-    roof_chol["frac"] = roof_chol["achieved"] / FP64_PEAK_TFLOPS
+                 "achieved": cf / (k3_ms * 1e-3) / 1e12, "peak": fp64_tf, "unit": "TFLOP/s", "traffic": tr_k3,
+                 "traffic_source": tr_k3_src, "peak_source": fp64_src, "algorithmic_flops": cf, "kernel_ms": k3_ms,
+                 "note": "a banded (video) system is a latency chain of dependent 96x96 panels, not a throughput problem; "
+                         "a fully covisible one (--config C3dense) is the dense blocked algorithm"}
+    roof_chol["frac"] = roof_chol["achieved"] / fp64_tf
     roofs = {"k1": roof_k1, "schur_syrk": roof_syrk, "cholesky": roof_chol}
     dominant = max(roofs, key=lambda k: roofs[k]["kernel_ms"])
     out = {
         "metric": METRIC, "value": value, "unit": "M evals/s", "n_gpus": world, "steps": args.steps,
-        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "warmup": warm, "ms_per_step": ms_per_step,
+        # (kept early in the line: the driver's record of a scaling run is a truncated tail)
+        "stage_ms_per_step": {k: round(v, 4) for k, v in stages.items()},
+        "parity_vs_1gpu": parity,
+        "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.config], "step": STEP_DESC,
-                   "l2": "no flush needed: every iteration streams > 4 GB through HBM (J alone is 1.2 GB > 126 MB L2)",
-                   "parallelism": "single GPU" if world == 1 else f"observations sharded by point owner x{world}, one NCCL allreduce of the reduced system per linear solve",
-                   "setup_ms": {"scene_upload": upload_ms, "warmup_solve_incl_structure": warm_ms}},
+        "config": bench_config(args.config),
+        "l2": "no flush needed: every iteration streams > 4 GB through HBM (J alone is 1.2 GB > 126 MB L2)",
+        "parallelism": "single GPU" if world == 1 else f"observations sharded by point owner x{world}, one NCCL allreduce of the reduced system per linear solve",
+        "setup_ms": {"scene_upload": upload_ms, "warmup_solve_incl_structure": warm_ms},
         "lm_iters_per_sec": 1e3 / ms_per_step,
         "lm": {"iterations": summ.iterations, "successful_steps": summ.num_successful_steps,
                "jacobian_evals": summ.num_jacobian_evaluations, "residual_evals": summ.num_residual_evaluations,
                "initial_cost": summ.initial_cost, "final_cost": summ.final_cost},
-        "stage_ms_per_step": stages, "kernel_ms": kern,
+        "kernel_ms": kern,
         "roofline": dict(roofs[dominant], dominant=dominant),
         "roofline_k1": roof_k1, "roofline_schur": roof_syrk, "roofline_cholesky": roof_chol,
         "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": "M evals/s", "h2d_bytes_per_step": h2d,
@@ -455,10 +508,18 @@ def run_ours(args):
                 "cold_call": "fresh handle: rsba_cuda_create + set_camera + set_scene (observations H2D) + set_parameters + "
                              "solve(K iterations, incl. structure analysis) + get_parameters + destroy"},
         "gpu_launches": launches, "clocks": clocks,
+        "denominator_note": "the reference arm / cpu_baseline is the reference's own functor under Jet<15> (oracle/_ref) PLUS "
+                            "our CPU restatement of Ceres' Schur elimination / LM loop (oracle/cpu_lm.cc, LAPACK dpbsv); "
+                            "it is not Ceres itself, which cannot be built here",
     }
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_lm_baseline(scene, args.cpu_iters, 1)
     emit(out)
+
+
+def bench_config(name):
+    """The `config` object: identical in both arms (ours / --impl reference)."""
+    return {"workload": WORKLOADS[name], "step": STEP_DESC}
 
 
 def main():

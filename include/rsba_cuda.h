@@ -93,6 +93,10 @@ typedef struct rsba_solve_summary {
   double time_update_ms;       /* device time: back-substitution, step, bookkeeping */
   double time_allreduce_ms;    /* device time: NCCL allreduce of the reduced system */
   char message[128];
+  double tile_flops;           /* FP64 work of one reduced-system factorisation at tile granularity (what the
+                                  symbolic analysis of this scene executes: potrf n^3/3, trsm n^3, update 2 n^3 per tile) */
+  int reduced_levels;          /* elimination levels (length of the dependent panel chain) */
+  int reduced_tiles;           /* non-zero 96 x 96 tiles of the factor after fill */
 } rsba_solve_summary;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -329,6 +333,11 @@ int rsba_cuda_reduced_solve(int device, int n_tiles, int n_pairs, const int* pai
                             int reorder, int mode, int merge_levels, int repeats, const double* A,
                             const double* rhs, double* x_out, double* L_out, int* tile_pos_out, int* info_out,
                             float* ms_out, long long* trace_out);
+
+/* Measurement hook: the FP64 peak of `device` in TFLOP/s, by register-resident DFMA chains and by
+ * mma.sync.m8n8k4.f64 chains (the two FP64 paths of sm_100a; tcgen05 has no FP64 kind).  ~30 ms.  bench.py quotes
+ * the K2 / K3 rooflines against the larger of the two, measured in the same run. */
+int rsba_cuda_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops);
 
 /* Host-only introspection of the WHOLE one-off structure analysis that rsba_cuda_solve runs before its first
  * linearisation -- what Ceres does in Program reordering + SchurEliminator block-structure detection + CHOLMOD's

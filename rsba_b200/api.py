@@ -44,7 +44,7 @@ SYMBOLS = [
     "rsba_cuda_set_block_constant", "rsba_cuda_set_subset_constant", "rsba_cuda_set_scene",
     "rsba_cuda_set_parameters", "rsba_cuda_get_parameters", "rsba_cuda_evaluate",
     "rsba_cuda_validate", "rsba_cuda_reproject", "rsba_cuda_evaluate_device", "rsba_cuda_device_buffers", "rsba_cuda_observation_order",
-    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_plan_task_graph", "rsba_cuda_reduced_solve", "rsba_cuda_analyze_structure", "rsba_cuda_structure_array",
+    "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_plan_task_graph", "rsba_cuda_reduced_solve", "rsba_cuda_measure_fp64_peak", "rsba_cuda_analyze_structure", "rsba_cuda_structure_array",
     "rsba_cuda_structure_free", "rsba_cuda_sort_observations", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
 ]
@@ -94,6 +94,9 @@ class SolveSummary(C.Structure):
         ("time_update_ms", C.c_double),
         ("time_allreduce_ms", C.c_double),
         ("message", C.c_char * 128),
+        ("tile_flops", C.c_double),
+        ("reduced_levels", C.c_int),
+        ("reduced_tiles", C.c_int),
     ]
 
     def as_dict(self):
@@ -172,6 +175,7 @@ def load_library():
     lib.rsba_cuda_plan_task_graph.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.rsba_cuda_reduced_solve.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                             vp, vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_float), vp]
+    lib.rsba_cuda_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.rsba_cuda_analyze_structure.argtypes = [C.c_long, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp,
                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.rsba_cuda_structure_array.argtypes = [vp, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
@@ -646,6 +650,16 @@ def reduced_solve(A, rhs, n_tiles, pair_a=(), pair_b=(), dense=False, reorder=Tr
     if want_trace:
         out["trace"] = trace
     return out
+
+
+def measure_fp64_peak(device=0):
+    """(DFMA, DMMA) TFLOP/s of the device, measured now (rsba_cuda_measure_fp64_peak)."""
+    lib = load_library()
+    a, b = C.c_double(0), C.c_double(0)
+    rc = lib.rsba_cuda_measure_fp64_peak(int(device), C.byref(a), C.byref(b))
+    if rc != RSBA_OK:
+        raise RsbaError(rc, lib.rsba_cuda_last_error().decode(errors="replace"))
+    return a.value, b.value
 
 
 _STRUCTURE_ARRAYS = {

@@ -34,11 +34,12 @@ constexpr int kPointBlockWarps = 8;
 
 __global__ void __launch_bounds__(kPointBlockWarps * 32)
 point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
-                    const double* __restrict__ jac, const double* __restrict__ res, int n_points,
+                    const double* __restrict__ jac, const double* __restrict__ res, NormalEq ne,
                     double* __restrict__ C, double* __restrict__ gp) {
   const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * kPointBlockWarps + (threadIdx.x >> 5);
-  if (p >= n_points) return;
+  const int k = blockIdx.x * kPointBlockWarps + (threadIdx.x >> 5);
+  if (k >= ne.n_owned) return;
+  const int p = owned_point(ne, k);
   double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // c0..c5, g0..g2
   const int beg = pt_ptr[p], end = pt_ptr[p + 1];
   for (int e = beg + lane; e < end; e += 32) {
@@ -69,11 +70,12 @@ point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_o
     }
 }
 
-__global__ void point_scale_kernel(int n_points, const double* __restrict__ C,
+__global__ void point_scale_kernel(NormalEq ne, const double* __restrict__ C,
                                    const unsigned char* __restrict__ point_const, int enabled,
                                    double* __restrict__ scale_p) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_points) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ne.n_owned) return;
+  const int p = owned_point(ne, t);
   const bool cst = point_const[p] != 0;
   const double* Cp = C + 6L * p;
   const double d[3] = {Cp[0], Cp[3], Cp[5]};
@@ -93,9 +95,10 @@ __global__ void frame_scale_kernel(int n_frames, const double* __restrict__ diag
 
 // ---------------------------------------------------------------- points: damped inverse
 __global__ void __launch_bounds__(128)
-point_invert_kernel(int n_points, NormalEq ne, LmOptionsDev o) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_points) return;
+point_invert_kernel(NormalEq ne, LmOptionsDev o) {
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 >= ne.n_owned) return;
+  const int p = owned_point(ne, t0);
   double* Ci = ne.Cinv + 6L * p;
   double* t = ne.tp + 3L * p;
   double* d2 = ne.d2_p + 3L * p;
@@ -354,10 +357,10 @@ frame_reduce_kernel(SchurStructure st, NormalEq ne, int n_frames) {
 }  // namespace
 
 void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
-                         int n_points, NormalEq ne, cudaStream_t s) {
-  if (n_points <= 0) return;
-  point_blocks_kernel<<<(n_points + kPointBlockWarps - 1) / kPointBlockWarps, kPointBlockWarps * 32, 0, s>>>(
-      st.pt_ptr, st.pt_obs, jac, res, n_points, ne.C, ne.gp);
+                         NormalEq ne, cudaStream_t s) {
+  if (ne.n_owned <= 0) return;
+  point_blocks_kernel<<<(ne.n_owned + kPointBlockWarps - 1) / kPointBlockWarps, kPointBlockWarps * 32, 0, s>>>(
+      st.pt_ptr, st.pt_obs, jac, res, ne, ne.C, ne.gp);
 }
 
 void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
@@ -376,18 +379,18 @@ void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const dou
   if (n_frames > 0) frame_reduce_kernel<<<n_frames, 192, 0, s>>>(st, ne, n_frames);
 }
 
-void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, cudaStream_t s) {
+void launch_jacobi_scale(int n_frames, bool points, NormalEq ne, bool enabled, cudaStream_t s) {
   // split in two by the caller's ordering needs: points first (n_frames == 0), frames later
-  if (n_points > 0)
-    point_scale_kernel<<<(n_points + 255) / 256, 256, 0, s>>>(n_points, ne.C, ne.point_const, enabled ? 1 : 0, ne.scale_p);
+  if (points && ne.n_owned > 0)
+    point_scale_kernel<<<(ne.n_owned + 255) / 256, 256, 0, s>>>(ne, ne.C, ne.point_const, enabled ? 1 : 0, ne.scale_p);
   if (n_frames > 0)
     frame_scale_kernel<<<(n_frames * kFrameParams + 255) / 256, 256, 0, s>>>(n_frames, ne.diagB, ne.pose_mask,
                                                                              enabled ? 1 : 0, ne.scale_c);
 }
 
-void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s) {
-  if (n_points <= 0) return;
-  point_invert_kernel<<<(n_points + 127) / 128, 128, 0, s>>>(n_points, ne, o);
+void launch_point_invert(NormalEq ne, LmOptionsDev o, cudaStream_t s) {
+  if (ne.n_owned <= 0) return;
+  point_invert_kernel<<<(ne.n_owned + 127) / 128, 128, 0, s>>>(ne, o);
 }
 
 }  // namespace rsba

@@ -13,6 +13,34 @@ using namespace rsba;
 
 namespace {
 
+// ---- FP64 peak of the device this process runs on (the denominator of the K2/K3 rooflines): chains of
+// register-resident DFMAs and of mma.sync.m8n8k4.f64, the two FP64 paths of sm_100a (tcgen05 has no FP64 kind)
+template <int ILP>
+__global__ void peak_dfma_kernel(double* out, int iters) {
+  double a[ILP], b = 1.0000001, c = 1e-9;
+  for (int k = 0; k < ILP; ++k) a[k] = threadIdx.x + k;
+  for (int i = 0; i < iters; ++i)
+#pragma unroll
+    for (int k = 0; k < ILP; ++k) a[k] = fma(a[k], b, c);
+  double s = 0;
+  for (int k = 0; k < ILP; ++k) s += a[k];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int ILP>
+__global__ void peak_dmma_kernel(double* out, int iters) {
+  double c0[ILP], c1[ILP];
+  const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+  for (int k = 0; k < ILP; ++k) c0[k] = c1[k] = 0.0;
+  for (int i = 0; i < iters; ++i)
+#pragma unroll
+    for (int k = 0; k < ILP; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[k]), "+d"(c1[k]) : "d"(a), "d"(b));
+  double s = 0;
+  for (int k = 0; k < ILP; ++k) s += c0[k] + c1[k];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int fail(int code, const std::string& msg) {
   set_last_error(msg);
   return code;
@@ -183,6 +211,45 @@ int rsba_cuda_reduced_solve(int device, int n_tiles, int n_pairs, const int* pai
           }
       }
     }
+    return RSBA_OK;
+  });
+}
+
+int rsba_cuda_measure_fp64_peak(int device, double* dfma_tflops, double* dmma_tflops) {
+  return rsba::api_guard([&]() -> int {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+      cudaGetLastError();
+      return fail(RSBA_ERR_NO_DEVICE, "no such CUDA device");
+    }
+    RSBA_CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    RSBA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int threads = 1024, grid = 2 * sms, iters = 4000;
+    DeviceBuffer<double> out;
+    RSBA_CUDA_TRY(out.resize((size_t)grid * threads));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best[2] = {0.0, 0.0};
+    for (int rep = 0; rep < 4; ++rep)          // first round = warm-up (clocks), best of the rest
+      for (int which = 0; which < 2; ++which) {
+        cudaEventRecord(e0);
+        if (which == 0) peak_dfma_kernel<8><<<grid, threads>>>(out.ptr, iters);
+        else peak_dmma_kernel<8><<<grid, threads>>>(out.ptr, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = which == 0 ? 2.0 * 8 * iters * (double)threads * grid
+                                       : 2.0 * 8 * 8 * 4 * 8 * iters * (double)(threads / 32) * grid;
+        if (rep > 0 && ms > 0.f) best[which] = std::max(best[which], flop / ms / 1e9);
+      }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    RSBA_CUDA_TRY(cudaGetLastError());
+    if (dfma_tflops) *dfma_tflops = best[0];
+    if (dmma_tflops) *dmma_tflops = best[1];
     return RSBA_OK;
   });
 }

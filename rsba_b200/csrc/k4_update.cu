@@ -79,9 +79,10 @@ point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
                   double* __restrict__ delta_p, double* __restrict__ trial, double* __restrict__ scratch) {
   __shared__ double sh[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * kPointStepWarps + warp;
+  const int k = blockIdx.x * kPointStepWarps + warp;
   double gd = 0.0, dd = 0.0, nn = 0.0;
-  if (p < n_points) {
+  if (k < ne.n_owned) {
+    const int p = owned_point(ne, k);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     const int beg = st.pt_ptr[p], end = st.pt_ptr[p + 1];
     for (int e = beg + lane; e < end; e += 32) {
@@ -174,10 +175,11 @@ __global__ void __launch_bounds__(kRedThreads)
 point_norms_kernel(NormalEq ne, int n_points, const double* __restrict__ points, double* __restrict__ scratch) {
   __shared__ double sh[32];
   double xx = 0.0, gm = 0.0;
-  const long np = 3L * n_points;
-  for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < np; u += (long)gridDim.x * blockDim.x) {
-    const long p = u / 3;
-    if (!ne.point_const[p] && ne.point_owned[p]) {
+  const long np = 3L * ne.n_owned;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < np; t += (long)gridDim.x * blockDim.x) {
+    const long p = owned_point(ne, (int)(t / 3));
+    const long u = 3 * p + t % 3;
+    if (!ne.point_const[p]) {
       xx += points[u] * points[u];
       gm = fmax(gm, fabs(ne.gp[u]));
     }
@@ -231,7 +233,7 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
                         double lower_bound, cudaStream_t s) {
   frame_step_kernel<<<1, kWideThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch,
                                                bounded_param, lower_bound);
-  const int nb = (n_points + kPointStepWarps - 1) / kPointStepWarps;
+  const int nb = (ne.n_owned + kPointStepWarps - 1) / kPointStepWarps;
   if (nb > 0)
     point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, obs, jac, jac_cam, cam_frame, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
   step_final_kernel<<<1, kWideThreads, 0, s>>>(scratch, nb, scalars);

@@ -87,7 +87,13 @@ struct NormalEq {
   const unsigned short* pose_mask;  // [F] constant-scalar bits
   const unsigned char* point_const; // [P]
   const unsigned char* point_owned; // [P] 1 if this rank eliminates the point (all 1 on one GPU)
+  // the point kernels (blocks, scaling, inverse, back-substitution, norms) walk the points this rank OWNS:
+  // point id = owned_ids[k], k < n_owned; owned_ids == NULL means the identity (one GPU: n_owned == P)
+  const int* owned_ids;
+  int n_owned;
 };
+
+__device__ __forceinline__ int owned_point(const NormalEq& ne, int k) { return ne.owned_ids ? ne.owned_ids[k] : k; }
 
 struct LmOptionsDev {
   double radius, min_diag, max_diag;
@@ -95,11 +101,13 @@ struct LmOptionsDev {
 
 // ---- K2 ---------------------------------------------------------------------------------
 void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
-                         int n_points, NormalEq ne, cudaStream_t s);
+                         NormalEq ne, cudaStream_t s);
 void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
                          int n_frames, NormalEq ne, bool with_wf, cudaStream_t s);
-void launch_jacobi_scale(int n_frames, int n_points, NormalEq ne, bool enabled, cudaStream_t s);
-void launch_point_invert(int n_points, NormalEq ne, LmOptionsDev o, cudaStream_t s);
+// n_frames > 0: the camera parameters; points: the owned points (two calls: the point part runs before the
+// all-reduce, the camera part after it)
+void launch_jacobi_scale(int n_frames, bool points, NormalEq ne, bool enabled, cudaStream_t s);
+void launch_point_invert(NormalEq ne, LmOptionsDev o, cudaStream_t s);
 // uncalibrated variant (k2_cam.cu): blocks of the intrinsics pseudo-frame (frame index n_frames) and its panel rows
 void launch_cam_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
                        const double* res, NormalEq ne, int n_frames, double* partials, double* scratch,

@@ -28,6 +28,7 @@ struct LmState {
   bool free_cam = false, free_ratio = false;
   int n_cam_frames = 0;          // frames of the camera system: real frames (+ the intrinsics pseudo-frame)
   DeviceBuffer<unsigned char> slot_cnt, point_owned;
+  DeviceBuffer<int> owned_ids;
   DeviceBuffer<int4> items;
   DeviceBuffer<int2> entries;
   DeviceBuffer<int2> nz_tiles, trsm;
@@ -234,6 +235,22 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   ne.scale_c = lm->scale_c.ptr; ne.scale_p = lm->scale_p.ptr;
   ne.d2_c = lm->d2_c.ptr; ne.d2_p = lm->d2_p.ptr; ne.partials = lm->partials.ptr;
   ne.pose_mask = lm->pose_mask.ptr; ne.point_const = lm->point_const.ptr; ne.point_owned = lm->point_owned.ptr;
+  ne.owned_ids = nullptr;
+  ne.n_owned = P;
+  if (h->world > 1) {   // the point kernels only walk the points this rank eliminates
+    std::vector<int> ids;
+    for (int p = 0; p < P; ++p)
+      if (h->point_owned[p]) ids.push_back(p);
+    ne.n_owned = (int)ids.size();
+    if ((rc = upload(lm->owned_ids, ids, s))) return rc;
+    ne.owned_ids = lm->owned_ids.ptr;
+    // what this rank never computes (blocks, steps, trial values of other ranks' points) must still be defined
+    RSBA_CUDA_TRY(cudaMemsetAsync(lm->C.ptr, 0, lm->C.bytes(), s)); RSBA_CUDA_TRY(cudaMemsetAsync(lm->gp.ptr, 0, lm->gp.bytes(), s));
+    RSBA_CUDA_TRY(cudaMemsetAsync(lm->Cinv.ptr, 0, lm->Cinv.bytes(), s)); RSBA_CUDA_TRY(cudaMemsetAsync(lm->tp.ptr, 0, lm->tp.bytes(), s));
+    RSBA_CUDA_TRY(cudaMemsetAsync(lm->Minv.ptr, 0, lm->Minv.bytes(), s)); RSBA_CUDA_TRY(cudaMemsetAsync(lm->delta_p.ptr, 0, lm->delta_p.bytes(), s));
+    RSBA_CUDA_TRY(cudaMemsetAsync(lm->scale_p.ptr, 0, lm->scale_p.bytes(), s)); RSBA_CUDA_TRY(cudaMemsetAsync(lm->d2_p.ptr, 0, lm->d2_p.bytes(), s));
+    RSBA_CUDA_TRY(cudaMemcpyAsync(lm->trial_points.ptr, h->d_points.ptr, 3L * P * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
 
   TileSchedule& ts = lm->ts;
   ts.n_tiles = T; ts.nz_tiles = lm->nz_tiles.ptr; ts.tile_slot = lm->tile_slot.ptr; ts.n_nz = (int)nz_tiles.size();
@@ -284,12 +301,12 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   stage_begin(h, kStageSchur);
   if (new_jacobian) {
     stage_begin(h, kStagePointBlocks);
-    launch_point_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, h->n_points, lm->ne, s);
+    launch_point_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, lm->ne, s);
     stage_end(h, kStagePointBlocks);
     h->launches += 1;
   }
-  if (compute_scale) { launch_jacobi_scale(0, h->n_points, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
-  launch_point_invert(h->n_points, lm->ne, o, s);
+  if (compute_scale) { launch_jacobi_scale(0, true, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
+  launch_point_invert(lm->ne, o, s);
   stage_begin(h, kStageFrameBlocks);
   launch_frame_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, lm->n_cam_frames, lm->ne, true, s);
   stage_end(h, kStageFrameBlocks);
@@ -341,7 +358,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     if (rc) return rc;
   }
   stage_begin(h, kStageFinalize);
-  if (compute_scale) { launch_jacobi_scale(lm->n_cam_frames, 0, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
+  if (compute_scale) { launch_jacobi_scale(lm->n_cam_frames, false, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
   launch_schur_finalize(lm->st, lm->ne, o, lm->S.ptr, lm->ts, lm->n_cam_frames, lm->rhs.ptr, s);
   launch_camera_norms(lm->ne, lm->n_cam_frames, h->d_poses.ptr, lm->scalars.ptr, s);
   if (ppv.n > 0) { launch_pose_prior_norms(ppv, lm->scalars.ptr, s); h->launches += 1; }
@@ -536,6 +553,9 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   for (auto& t : h->timers) t.total_ms = 0.0;
   sum->num_residual_blocks = h->n_obs;
   sum->num_parameters_reduced = lm->num_free_params + h->free_pose_prior_params();
+  sum->tile_flops = lm->plan.flops;
+  sum->reduced_levels = lm->plan.n_levels;
+  sum->reduced_tiles = (int)lm->plan.nz_tiles.size();
 
   auto finish = [&](int term, const char* msg, double cost, double radius, double gmax) {
     sum->termination = term;

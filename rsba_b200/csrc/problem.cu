@@ -594,6 +594,17 @@ int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigne
     ncclResult_t r = api->CommInitRank(&comm, world_size, uid, rank);
     if (r != ncclSuccess) return fail(RSBA_ERR_NCCL, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
     h->nccl_comm = comm;
+    h->rank = rank;
+    h->world = world_size;
+    // NCCL connects its channels lazily, at the first collective of each protocol: pay that here (one small
+    // and one multi-megabyte all-reduce) and not inside the first solve, where it was ~1 s at 8 ranks
+    DeviceBuffer<double> warm;
+    RSBA_CUDA_TRY(warm.resize((size_t)1 << 20));
+    RSBA_CUDA_TRY(cudaMemsetAsync(warm.ptr, 0, warm.bytes(), h->stream));
+    int rc = allreduce_sum(h, warm.ptr, 8);
+    if (!rc) rc = allreduce_sum(h, warm.ptr, warm.count);
+    if (rc) return rc;
+    RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   }
   h->rank = rank;
   h->world = world_size;

@@ -28,7 +28,12 @@ CONFIGS = {
     "C2": (100, 20_000, 25),
     "C3": (1_000, 200_000, 25),
     "C5": (4_000, 1_000_000, 20),
+    # not in BASELINE.json: the sizes of C3 with FULL covisibility (every frame pair shares points) -- an orbit
+    # around one object, the loop-closure / turntable case in which the reduced camera matrix is dense
+    "C3dense": (1_000, 200_000, 25),
+    "C2dense": (100, 20_000, 25),
 }
+ORBIT = {"C3dense", "C2dense"}
 
 
 @dataclass
@@ -219,13 +224,66 @@ def make_scene(num_frames: int, num_points: int, obs_per_point: int, seed: int =
                        "noise_px": noise_px, "image": [IMAGE_W, IMAGE_H]})
 
 
+def make_orbit_scene(num_frames: int, num_points: int, obs_per_point: int, seed: int = SEED, name: str = "",
+                     noise_px: float = 0.5) -> Scene:
+    """Fully covisible scene: the camera orbits an object of radius 1.2 m at 6 m distance, every point is seen
+    from ``obs_per_point`` frames drawn at random over the WHOLE sequence, so any two frames share points
+    (expected P (K/F)^2 of them) and the reduced camera matrix is dense.  Same camera model, noise and
+    frame-0 gauge as make_scene."""
+    F, P, K = int(num_frames), int(num_points), int(obs_per_point)
+    rng = np.random.Generator(np.random.Philox(seed + 1))
+    cam = DEFAULT_CAM.copy()
+    scan = np.array([0, IMAGE_W], dtype=np.int32)
+    shutter, interp = SHUTTER_HORIZONTAL, True
+    R = 6.0
+    theta = 2.0 * np.pi * np.arange(F + 1, dtype=np.float64) / F        # unwrapped: pose1 blends towards the next frame
+    centre = np.stack([R * np.sin(theta), 0.02 * np.sin(7 * theta), R - R * np.cos(theta)], axis=1)   # frame 0 at the origin
+    rot = np.stack([np.zeros(F + 1), theta, np.zeros(F + 1)], axis=1)   # looks at the object centre (0, 0, R)
+    pose0 = np.concatenate([rot, centre], axis=1)
+    pose1 = pose0[:-1] + 0.5 * (pose0[1:] - pose0[:-1])
+    poses_true = np.concatenate([pose0[:-1], pose1], axis=1)
+    poses_true[0] = 0.0
+    # points: uniform in a ball around the object centre
+    d = rng.normal(size=(P, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    points_true = np.array([0.0, 0.0, R]) + 1.2 * d * rng.uniform(0, 1, size=(P, 1)) ** (1 / 3)
+    # K distinct frames per point, anywhere in the sequence (argpartition of random keys = sampling w/o replacement)
+    obs_frame = np.empty((P, K), dtype=np.int64)
+    for b in range(0, P, 20000):
+        e = min(P, b + 20000)
+        obs_frame[b:e] = np.argpartition(rng.random((e - b, F)), K - 1, axis=1)[:, :K]
+    obs_point = np.repeat(np.arange(P, dtype=np.int64), K)
+    obs_frame = obs_frame.reshape(-1)
+    order = np.lexsort((obs_point, obs_frame))
+    obs_point, obs_frame = obs_point[order], obs_frame[order]
+    proj, z = rs_project(cam, poses_true[obs_frame], points_true[obs_point], shutter, scan, interp)
+    assert np.all(z > 0.25) and np.all((proj[:, 0] > 0) & (proj[:, 0] < IMAGE_W) & (proj[:, 1] > 0) & (proj[:, 1] < IMAGE_H))
+    obs_xy = proj + rng.normal(0.0, noise_px, size=proj.shape)
+    poses = poses_true.copy()
+    for blk in (0, 6):
+        poses[:, blk:blk + 3] += rng.normal(0, 1e-3, size=(F, 3))
+        poses[:, blk + 3:blk + 6] += rng.normal(0, 1e-2, size=(F, 3))
+    poses[0] = 0.0
+    points = points_true + rng.normal(0, 2e-2, size=(P, 3))
+    const_frames = np.zeros(F, dtype=bool)
+    const_frames[0] = True
+    return Scene(cam=cam, shutter=shutter, scanlines=scan, interpolate_rotation=interp,
+                 poses=np.ascontiguousarray(poses), points=np.ascontiguousarray(points),
+                 obs_xy=np.ascontiguousarray(obs_xy), obs_frame=obs_frame.astype(np.int32),
+                 obs_point=obs_point.astype(np.int32), const_frames=const_frames,
+                 poses_true=poses_true, points_true=points_true, name=name,
+                 meta={"seed": seed, "frames": F, "points": P, "obs_per_point": K, "noise_px": noise_px,
+                       "image": [IMAGE_W, IMAGE_H], "pattern": "orbit"})
+
+
 def make_config(name: str, cache: bool = True, **kw) -> Scene:
     """BASELINE.json config by name.  Large scenes are cached as .npz under
     $RSBA_SCENE_CACHE (default /tmp/rsba_scene_cache): generation is deterministic."""
     import os
     F, P, K = CONFIGS[name]
+    gen = make_orbit_scene if name in ORBIT else make_scene
     if kw or not cache or F * P < 1_000_000:
-        return make_scene(F, P, K, name=name, **kw)
+        return gen(F, P, K, name=name, **kw)
     d = os.environ.get("RSBA_SCENE_CACHE", "/tmp/rsba_scene_cache")
     path = os.path.join(d, f"{name}_seed{SEED}.npz")
     if os.path.exists(path):
@@ -239,7 +297,7 @@ def make_config(name: str, cache: bool = True, **kw) -> Scene:
                          meta={"seed": SEED, "frames": F, "points": P, "obs_per_point": K})
         except Exception:
             pass
-    sc = make_scene(F, P, K, name=name)
+    sc = gen(F, P, K, name=name)
     try:
         os.makedirs(d, exist_ok=True)
         tmp = path + f".{os.getpid()}.tmp.npz"
