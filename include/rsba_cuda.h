@@ -395,6 +395,23 @@ int rsba_cuda_pnp_batch(rsba_problem* h, const double cam9[9], int shutter, cons
  * the factorisation is replicated.  Single-GPU use never loads NCCL (dlopen at comm_init). */
 int rsba_cuda_nccl_unique_id(unsigned char id[128]);
 int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigned char id[128]);
+/* One HOST THREAD, N GPUs of one node -- for a driver that is single-threaded like the reference's
+ * (VideoSfMHandler::BA builds one CeresHandler and calls ceres::Solve from the request thread,
+ * VideoSfMHandler.cc:574-631, CeresHandler.h:408-419).  rsba_cuda_create_multi creates one problem handle per
+ * device and connects them (ncclCommInitRank from worker threads of this process; n_devices == 1 never loads
+ * NCCL).  The caller forwards every builder call (set_camera, set_scene / add_*, set_parameters, priors ...) to
+ * each rsba_cuda_multi_handle(m, r) with the SAME arguments -- every rank keeps its share -- and then calls
+ * rsba_cuda_multi_solve once: the ranks' LM loops run on worker threads and are joined before it returns;
+ * `summary` is rank 0's (costs and counts are global).  Results are read from handle 0 (get_parameters); with
+ * the pointer API rank 0 writes the caller's blocks back.  include/rsba_cuda_handler.hpp does the forwarding when
+ * it is constructed with a device list. */
+typedef struct rsba_multi rsba_multi;
+int rsba_cuda_create_multi(rsba_multi** out, const int* devices, int n_devices);
+int rsba_cuda_multi_size(const rsba_multi* m);
+rsba_problem* rsba_cuda_multi_handle(rsba_multi* m, int rank);
+int rsba_cuda_multi_solve(rsba_multi* m, const rsba_solve_options* options, rsba_solve_summary* summary);
+void rsba_cuda_destroy_multi(rsba_multi* m);
+
 /* Host-only (no device): the sharding rule.  owner[p] = rank that eliminates point p and therefore
  * evaluates ALL its observations -- the rank whose contiguous range of frame tiles (8 frames)
  * holds the point's median observation.  obs_frame must be non-decreasing. */

@@ -29,6 +29,12 @@ constexpr int kPoseParams = 6;    // NUM_POSE_PARAMS  (mat/cam.h:20)
 constexpr int kPointParams = 3;   // NUM_POINT_PARAMS (mat/cam.h:19)
 constexpr int kFrameParams = 12;  // pose0 | pose1
 constexpr int kJacDoubles = 30;   // 2x6 | 2x6 | 2x3
+// Compact record of the same Jacobian (what the solver's kernels read; rsba_cuda_evaluate hands out the full
+// one): tau is a constant of the observation, so J_pose0 = [wr0 jr | -(1-tau) jx], J_pose1 = [wr1 jr | -tau jx],
+// J_point = jx with jr = d res / d rotation and jx = d res / d X of the INTERPOLATED pose (2x3 each), and
+// (wr0, wr1) = (1-tau, tau) when the rotation is interpolated, (1, 0) otherwise.  12 doubles = three 32-byte
+// sectors instead of 240 bytes:  jx row 0 | jx row 1 | jr row 0 | jr row 1.
+constexpr int kJacCompact = 12;
 
 // Per-session constants captured by every cost functor (VideoSfmBaRs.h:16-22).
 struct CameraModel {
@@ -48,6 +54,7 @@ struct CameraModel {
 struct Proj {
   double r0, r1;   // residual
   bool ok;
+  double tau;      // interpolation parameter of the observation, clamped to [0, 1] (0 for a global shutter)
 };
 
 // Everything that depends on one observation.  JAC=false skips all derivative work.
@@ -57,7 +64,8 @@ struct Proj {
 // VALIDATE = false: w2i(..., validate = false) as the RS-PnP functor and its inlier scoring call it
 // (solveRSpnp.cpp:65, 233; mat/cam.h:409-416): a point behind the camera is NOT rejected, and a depth
 // inside (-eps, eps) is replaced by eps (a constant: its derivative rows vanish).
-template <bool JAC, bool TAU_FROM_Y = false, bool VALIDATE = true>
+// COMPACT: J receives the kJacCompact-double record above instead of the 30-double Ceres layout.
+template <bool JAC, bool TAU_FROM_Y = false, bool VALIDATE = true, bool COMPACT = false>
 RSBA_HD Proj reproject(const CameraModel& cm, double ox, double oy,
                                           const double* __restrict__ p0,  // frame: pose0|pose1
                                           double X0, double X1, double X2,
@@ -72,6 +80,7 @@ RSBA_HD Proj reproject(const CameraModel& cm, double ox, double oy,
     tau = tau > 1.0 ? 1.0 : tau;
     if (cm.interp_rot) { wr0 = 1.0 - tau; wr1 = tau; }
   }
+  out.tau = tau;
   const double* p1 = p0 + 6;
   double r[3], c[3];
   if (cm.shutter != 0 && cm.interp_rot) {
@@ -158,7 +167,7 @@ RSBA_UNROLL
     out.r1 = 0.0;
     if (JAC) {
 RSBA_UNROLL
-      for (int k = 0; k < kJacDoubles; ++k) J[k] = 0.0;
+      for (int k = 0; k < (COMPACT ? kJacCompact : kJacDoubles); ++k) J[k] = 0.0;
       if (Jcam) {
 RSBA_UNROLL
         for (int k = 0; k < 18; ++k) Jcam[k] = 0.0;
@@ -211,14 +220,34 @@ RSBA_UNROLL
       const double jr1 = A10 * dPr[k] + A11 * dPr[3 + k] + A12 * dPr[6 + k];
       const double jx0 = A00 * R[k] + A01 * R[3 + k] + A02 * R[6 + k];        // d res / d X
       const double jx1 = A10 * R[k] + A11 * R[3 + k] + A12 * R[6 + k];
-      J[k] = wr0 * jr0;        J[6 + k] = wr0 * jr1;         // J_pose0 rows 0,1: rotation
-      J[3 + k] = -w0c * jx0;   J[9 + k] = -w0c * jx1;        //                   centre
-      J[12 + k] = wr1 * jr0;   J[18 + k] = wr1 * jr1;        // J_pose1
-      J[15 + k] = -w1c * jx0;  J[21 + k] = -w1c * jx1;
-      J[24 + k] = jx0;         J[27 + k] = jx1;              // J_point
+      if (COMPACT) {
+        J[k] = jx0;  J[3 + k] = jx1;  J[6 + k] = jr0;  J[9 + k] = jr1;
+      } else {
+        J[k] = wr0 * jr0;        J[6 + k] = wr0 * jr1;         // J_pose0 rows 0,1: rotation
+        J[3 + k] = -w0c * jx0;   J[9 + k] = -w0c * jx1;        //                   centre
+        J[12 + k] = wr1 * jr0;   J[18 + k] = wr1 * jr1;        // J_pose1
+        J[15 + k] = -w1c * jx0;  J[21 + k] = -w1c * jx1;
+        J[24 + k] = jx0;         J[27 + k] = jx1;              // J_point
+      }
     }
   }
   return out;
+}
+
+// The 30-double Ceres layout back from a compact record (the kernels that are not on the hot path index
+// the full record; the hot ones use the structure directly).  rot_interp = shutter != GLOBAL && interpolateRotation.
+RSBA_HD void expand_jacobian(const double* __restrict__ rec, double tau, bool rot_interp, double* __restrict__ J) {
+  const double wr0 = rot_interp ? 1.0 - tau : 1.0, wr1 = rot_interp ? tau : 0.0;
+  const double w0c = 1.0 - tau, w1c = tau;
+RSBA_UNROLL
+  for (int k = 0; k < 3; ++k) {
+    const double jx0 = rec[k], jx1 = rec[3 + k], jr0 = rec[6 + k], jr1 = rec[9 + k];
+    J[k] = wr0 * jr0;        J[6 + k] = wr0 * jr1;
+    J[3 + k] = -w0c * jx0;   J[9 + k] = -w0c * jx1;
+    J[12 + k] = wr1 * jr0;   J[18 + k] = wr1 * jr1;
+    J[15 + k] = -w1c * jx0;  J[21 + k] = -w1c * jx1;
+    J[24 + k] = jx0;         J[27 + k] = jx1;
+  }
 }
 
 }  // namespace rsba

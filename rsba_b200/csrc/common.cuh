@@ -73,9 +73,15 @@ inline bool first_use_on_device(bool (&seen)[64]) {
 void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
                double* residuals, double* jac, double* jac_cam, unsigned char* valid, double* cost_partials,
                int* invalid_count, cudaStream_t stream);
+// K1 for the solver: compact 12-double Jacobian records + tau per observation (rsba_reproj_math.h)
+void launch_k1_compact(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
+                       double* residuals, double* jac_compact, double* tau, double* jac_cam, double* cost_partials,
+                       int* invalid_count, cudaStream_t stream);
 // K1r: cost only at trial parameters.
+// residuals / valid: optional per-observation outputs (rsba_cuda_evaluate without a Jacobian)
 void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
-                double* cost_partials, int* invalid_count, cudaStream_t stream);
+                double* cost_partials, int* invalid_count, cudaStream_t stream, double* residuals = nullptr,
+                unsigned char* valid = nullptr);
 // track validation sweep (struct/VideoSfM.cc:159-169): per-observation predicate + squared error
 void launch_validate(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
                      double sqrd_threshold, double min_distance, unsigned char* ok, double* sqrd_error,

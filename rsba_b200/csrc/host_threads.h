@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdlib>
+#include <exception>
 #include <memory>
 #include <system_error>
 #include <thread>
@@ -25,20 +26,28 @@ struct HostThreads {
     n = want;
   }
   // fn(t) on threads t = 0 .. n-1 (t = 0 is the caller); returns when all are done
+  // An exception of any share (std::bad_alloc in a worker, ...) is rethrown on the caller AFTER every thread
+  // has been joined: it reaches api_guard as RSBA_ERR_INTERNAL instead of std::terminate.
   template <typename Fn>
   void run(Fn&& fn) const {
     if (n == 1) { fn(0); return; }
     std::vector<std::thread> th;
-    th.reserve(n - 1);
+    std::vector<std::exception_ptr> err(n);
+    auto guarded = [&fn, &err](int t) {
+      try { fn(t); } catch (...) { err[t] = std::current_exception(); }
+    };
     int started = 1;
     try {
-      for (int t = 1; t < n; ++t) { th.emplace_back([&fn, t] { fn(t); }); ++started; }
-    } catch (const std::system_error&) {
-      // no more threads to be had (pid / resource limit): the caller takes the remaining shares itself
+      th.reserve(n - 1);
+      for (int t = 1; t < n; ++t) { th.emplace_back(guarded, t); ++started; }
+    } catch (...) {
+      // no more threads to be had (pid / resource limit, memory): the caller takes the remaining shares itself
     }
-    fn(0);
-    for (int t = started; t < n; ++t) fn(t);
+    guarded(0);
+    for (int t = started; t < n; ++t) guarded(t);
     for (auto& x : th) x.join();
+    for (auto& e : err)
+      if (e) std::rethrow_exception(e);
   }
   // fn(t, begin, end) over an even split of [0, count)
   template <typename Fn>

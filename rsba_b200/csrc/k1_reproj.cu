@@ -58,12 +58,15 @@ __device__ __forceinline__ int stage_poses(const ObsView& obs, const double* __r
   return f_lo;
 }
 
-template <bool JAC, bool CAM>
+// COMPACT (the solver's own linearisation): `jac` receives the 12-double record of rsba_reproj_math.h and
+// `tau_out` the observation's interpolation parameter -- 120 instead of 256 bytes written per observation.
+template <bool JAC, bool CAM, bool COMPACT = false>
 __global__ void __launch_bounds__(kK1Threads)
 k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__ poses,
           const double* __restrict__ points, double* __restrict__ residuals,
           double* __restrict__ jac, double* __restrict__ jac_cam, unsigned char* __restrict__ valid,
-          double* __restrict__ cost_partials, int* __restrict__ invalid_count) {
+          double* __restrict__ cost_partials, int* __restrict__ invalid_count, double* __restrict__ tau_out = nullptr) {
+  constexpr int kRec = COMPACT ? kJacCompact : kJacDoubles;
   CameraModel cm_local;
   if (CAM) {   // uncalibrated: the intrinsics are parameters, read at the point of evaluation
     cm_local = cm_in;
@@ -73,7 +76,7 @@ k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__
   const CameraModel& cm = CAM ? cm_local : cm_in;
   __shared__ double s_pose[kStageFrames * kFrameParams];
   __shared__ double s_cost[kK1Warps];
-  extern __shared__ __align__(128) double s_jac[];  // [warps][32][30], JAC only
+  extern __shared__ __align__(128) double s_jac[];  // [warps][32][kRec], JAC only
 
   const long base = (long)blockIdx.x * kK1Threads;
   const int cnt = (int)min((long)kK1Threads, obs.n - base);
@@ -132,11 +135,12 @@ k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__
 
   double cost = 0.0;
   bool bad = false;
-  double* Jrow = JAC ? s_jac + (warp * 32 + lane) * kJacDoubles : nullptr;
+  double* Jrow = JAC ? s_jac + (warp * 32 + lane) * kRec : nullptr;
   if (i < obs.n) {
     double Jc[CAM ? 18 : 1];
     constexpr bool want_cam = JAC && CAM;
-    Proj pr = reproject<JAC>(cm, o.x, o.y, pose, X0, X1, X2, Jrow, want_cam ? Jc : nullptr);
+    Proj pr = reproject<JAC, false, true, COMPACT>(cm, o.x, o.y, pose, X0, X1, X2, Jrow, want_cam ? Jc : nullptr);
+    if (COMPACT && tau_out) tau_out[i] = pr.tau;
     cost = pr.r0 * pr.r0 + pr.r1 * pr.r1;
     bad = !pr.ok;
     // ceres::HuberLoss(a) through Ceres' Corrector (third-party; CeresHandler.h:85-90 passes the loss to
@@ -150,7 +154,7 @@ k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__
       pr.r1 *= w;
       if (JAC) {
 #pragma unroll
-        for (int k = 0; k < kJacDoubles; ++k) Jrow[k] *= w;
+        for (int k = 0; k < kRec; ++k) Jrow[k] *= w;
         if (want_cam) {
 #pragma unroll
           for (int k = 0; k < 18; ++k) Jc[k] *= w;
@@ -173,9 +177,9 @@ k1_kernel(const CameraModel cm_in, const ObsView obs, const double* __restrict__
     const long wbase = base + warp * 32;
     if (lane == 0 && wbase < obs.n) {
       const int wcnt = (int)min(32L, obs.n - wbase);
-      const unsigned bytes = (unsigned)(wcnt * kJacDoubles * sizeof(double));  // multiple of 16
-      const unsigned src = (unsigned)__cvta_generic_to_shared(s_jac + warp * 32 * kJacDoubles);
-      double* dst = jac + wbase * kJacDoubles;
+      const unsigned bytes = (unsigned)(wcnt * kRec * sizeof(double));  // multiple of 16
+      const unsigned src = (unsigned)__cvta_generic_to_shared(s_jac + warp * 32 * kRec);
+      double* dst = jac + wbase * kRec;
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src),
                    "r"(bytes)
                    : "memory");
@@ -324,15 +328,30 @@ void launch_k1(const CameraModel& cm, const ObsView& obs, const double* poses, c
                                                                cost_partials, invalid_count);
 }
 
+void launch_k1_compact(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
+                       double* residuals, double* jac_compact, double* tau, double* jac_cam, double* cost_partials,
+                       int* invalid_count, cudaStream_t stream) {
+  if (obs.n <= 0) return;
+  const int grid = k1_num_partials(obs.n);
+  const size_t smem = (size_t)kK1Threads * kJacCompact * sizeof(double);
+  if (cm.cam_offset >= 0)
+    k1_kernel<true, true, true><<<grid, kK1Threads, smem, stream>>>(cm, obs, poses, points, residuals, jac_compact, jac_cam,
+                                                                    nullptr, cost_partials, invalid_count, tau);
+  else
+    k1_kernel<true, false, true><<<grid, kK1Threads, smem, stream>>>(cm, obs, poses, points, residuals, jac_compact, nullptr,
+                                                                     nullptr, cost_partials, invalid_count, tau);
+}
+
 void launch_k1r(const CameraModel& cm, const ObsView& obs, const double* poses, const double* points,
-                double* cost_partials, int* invalid_count, cudaStream_t stream) {
+                double* cost_partials, int* invalid_count, cudaStream_t stream, double* residuals,
+                unsigned char* valid) {
   if (obs.n <= 0) return;
   const int grid = k1_num_partials(obs.n);
   if (cm.cam_offset >= 0)
-    k1_kernel<false, true><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, nullptr, nullptr, nullptr, nullptr,
+    k1_kernel<false, true><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, residuals, nullptr, nullptr, valid,
                                                             cost_partials, invalid_count);
   else
-    k1_kernel<false, false><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, nullptr, nullptr, nullptr, nullptr,
+    k1_kernel<false, false><<<grid, kK1Threads, 0, stream>>>(cm, obs, poses, points, residuals, nullptr, nullptr, valid,
                                                              cost_partials, invalid_count);
 }
 

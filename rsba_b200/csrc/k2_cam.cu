@@ -20,7 +20,7 @@ constexpr int kCamPartial = 108 + 81 + 9 + 9;   // B_fI | B_II | g_I | w_I
 // One CTA per frame chunk.  The chunk's rows are staged in shared memory, then thread k < 207 owns one
 // output and runs over the observations in a fixed order.
 __global__ void __launch_bounds__(256)
-cam_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, const double* __restrict__ jac_cam,
+cam_blocks_kernel(SchurStructure st, ObsView obs, JacView jv, const double* __restrict__ jac_cam,
                   const double* __restrict__ res, NormalEq ne, double* __restrict__ partials) {
   __shared__ double sC[kCamChunk * 2 * 12];   // camera rows of J
   __shared__ double sI[kCamChunk * 2 * 9];    // intrinsics rows
@@ -28,16 +28,21 @@ cam_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
   const int c = blockIdx.x;
   const long beg = st.chunk_beg[c];
   const int cnt = st.chunk_cnt[c];
-  for (int t = threadIdx.x; t < cnt * 24; t += blockDim.x) {
-    const int o = t / 24, k = t % 24, row = k / 12, col = k % 12;
-    sC[t] = jac[(beg + o) * kJacDoubles + (col < 6 ? row * 6 + col : 12 + row * 6 + (col - 6))];
+  for (int o = threadIdx.x; o < cnt; o += blockDim.x) {
+    double Jf[kJacDoubles];
+    load_full_jacobian(jv, beg + o, Jf);
+#pragma unroll
+    for (int k = 0; k < 24; ++k) {
+      const int row = k / 12, col = k % 12;
+      sC[o * 24 + k] = Jf[col < 6 ? row * 6 + col : 12 + row * 6 + (col - 6)];
+    }
   }
   for (int t = threadIdx.x; t < cnt * 18; t += blockDim.x) sI[t] = jac_cam[beg * 18 + t];
   for (int t = threadIdx.x; t < cnt * 2; t += blockDim.x) {
     const int o = t >> 1, row = t & 1;
     sR[t] = res[beg * 2 + t];
     const int p = obs.point[beg + o];
-    const double* jx = jac + (beg + o) * kJacDoubles + 24 + 3 * row;
+    const double* jx = jv.rec + (beg + o) * kJacCompact + 3 * row;   // point part: first six doubles of the record
     sQ[t] = jx[0] * ne.tp[3L * p] + jx[1] * ne.tp[3L * p + 1] + jx[2] * ne.tp[3L * p + 2];
   }
   __syncthreads();
@@ -93,7 +98,7 @@ cam_reduce_final_kernel(NormalEq ne, const double* __restrict__ scratch, int n_f
 
 // One warp per point: pseudo-frame rows of the point's Schur panel.
 __global__ void __launch_bounds__(256)
-phi_cam_kernel(SchurStructure st, const double* __restrict__ jac, const double* __restrict__ jac_cam, NormalEq ne,
+phi_cam_kernel(SchurStructure st, JacView jv, const double* __restrict__ jac_cam, NormalEq ne,
                int n_points, int slot) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -108,7 +113,7 @@ phi_cam_kernel(SchurStructure st, const double* __restrict__ jac, const double* 
   for (int k = 0; k < 27; ++k) F[k] = 0.0;
   for (int e = st.pt_ptr[p] + lane; e < st.pt_ptr[p + 1]; e += 32) {
     const long i = st.pt_obs[e];
-    const double* jx = jac + i * kJacDoubles + 24;
+    const double* jx = jv.rec + i * kJacCompact;
     const double a0 = jx[0] * sp0, a1 = jx[1] * sp1, a2 = jx[2] * sp2;
     const double b0 = jx[3] * sp0, b1 = jx[4] * sp1, b2 = jx[5] * sp2;
     const double xa[3] = {a0 * m00, a0 * m10 + a1 * m11, a0 * m20 + a1 * m21 + a2 * m22};
@@ -132,18 +137,18 @@ phi_cam_kernel(SchurStructure st, const double* __restrict__ jac, const double* 
 
 }  // namespace
 
-void launch_cam_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
+void launch_cam_blocks(const SchurStructure& st, const ObsView& obs, const JacView& jv, const double* jac_cam,
                        const double* res, NormalEq ne, int n_frames, double* partials, double* scratch,
                        cudaStream_t s) {
-  if (st.n_chunks > 0) cam_blocks_kernel<<<st.n_chunks, 256, 0, s>>>(st, obs, jac, jac_cam, res, ne, partials);
+  if (st.n_chunks > 0) cam_blocks_kernel<<<st.n_chunks, 256, 0, s>>>(st, obs, jv, jac_cam, res, ne, partials);
   if (n_frames > 0) cam_reduce_frames_kernel<<<n_frames, 256, 0, s>>>(st, ne, partials, scratch);
   cam_reduce_final_kernel<<<1, 128, 0, s>>>(ne, scratch, n_frames);
 }
 
-void launch_phi_cam(const SchurStructure& st, const double* jac, const double* jac_cam, NormalEq ne, int n_points,
+void launch_phi_cam(const SchurStructure& st, const JacView& jv, const double* jac_cam, NormalEq ne, int n_points,
                     int n_frames, cudaStream_t s) {
   if (n_points > 0)
-    phi_cam_kernel<<<(n_points + 7) / 8, 256, 0, s>>>(st, jac, jac_cam, ne, n_points, n_frames % kSubFrames);
+    phi_cam_kernel<<<(n_points + 7) / 8, 256, 0, s>>>(st, jv, jac_cam, ne, n_points, n_frames % kSubFrames);
 }
 
 }  // namespace rsba

@@ -25,16 +25,14 @@ namespace {
 constexpr int kChunk = 128;        // observations per frame chunk (host builds the chunk table)
 constexpr int kPartial = 168;      // 144 (B) + 12 (gc) + 12 (wf)
 
-// offset of columns 3*t .. 3*t+2 (t = 0..3) of camera row `row` inside a 30-double record
-__device__ __forceinline__ int jc_off(int t, int row) { return ((t & 2) ? 12 : 0) + row * 6 + (t & 1) * 3; }
-
 // ---------------------------------------------------------------- points: C_p, g_p
-// One warp per point; lanes gather the observations in parallel, fixed-order butterfly sum.
+// One warp per point; lanes gather the observations in parallel, fixed-order butterfly sum.  The point part of
+// the Jacobian is the first 48 bytes (two sectors) of the observation's compact record.
 constexpr int kPointBlockWarps = 8;
 
 __global__ void __launch_bounds__(kPointBlockWarps * 32)
 point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_obs,
-                    const double* __restrict__ jac, const double* __restrict__ res, NormalEq ne,
+                    const double* __restrict__ rec, const double* __restrict__ res, NormalEq ne,
                     double* __restrict__ C, double* __restrict__ gp) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * kPointBlockWarps + (threadIdx.x >> 5);
@@ -44,7 +42,7 @@ point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_o
   const int beg = pt_ptr[p], end = pt_ptr[p + 1];
   for (int e = beg + lane; e < end; e += 32) {
     const long i = pt_obs[e];
-    const double2* jx = reinterpret_cast<const double2*>(jac + i * kJacDoubles + 24);
+    const double2* jx = reinterpret_cast<const double2*>(rec + i * kJacCompact);
     const double2 q0 = jx[0], q1 = jx[1], q2 = jx[2];   // row0: q0.x q0.y q1.x ; row1: q1.y q2.x q2.y
     const double2 r = reinterpret_cast<const double2*>(res)[i];
     const double a0 = q0.x, a1 = q0.y, a2 = q1.x, b0 = q1.y, b1 = q2.x, b2 = q2.y;
@@ -68,6 +66,17 @@ point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_o
       if (k < 6) C[6L * p + k] = v[k];
       else gp[3L * p + (k - 6)] = v[k];
     }
+}
+
+// tau and frame of every observation in point-major order (coalesced for the warp-per-point kernels)
+__global__ void point_major_obs_kernel(const int* __restrict__ pt_obs, const int* __restrict__ frame,
+                                       const double* __restrict__ tau, long n, double* __restrict__ pt_tau,
+                                       int* __restrict__ pt_frame) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const long i = pt_obs[e];
+  pt_tau[e] = tau[i];
+  pt_frame[e] = frame[i];
 }
 
 __global__ void point_scale_kernel(NormalEq ne, const double* __restrict__ C,
@@ -109,6 +118,8 @@ point_invert_kernel(NormalEq ne, LmOptionsDev o) {
     d2[0] = d2[1] = d2[2] = 1.0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) ne.Minv[6L * p + k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPointRec; ++k) ne.prec[(long)kPointRec * p + k] = 0.0;
     return;
   }
   const double* Cp = ne.C + 6L * p;
@@ -148,195 +159,147 @@ point_invert_kernel(NormalEq ne, LmOptionsDev o) {
   t[0] = i00 * g[0] + i10 * g[1] + i20 * g[2];
   t[1] = i10 * g[0] + i11 * g[1] + i21 * g[2];
   t[2] = i20 * g[0] + i21 * g[1] + i22 * g[2];
+  // what frame_blocks gathers per observation, as one 96-byte record
+  double2* pr = reinterpret_cast<double2*>(ne.prec + (long)kPointRec * p);
+  pr[0] = make_double2(s0 * m00, s0 * m10);
+  pr[1] = make_double2(s1 * m11, s0 * m20);
+  pr[2] = make_double2(s1 * m21, s2 * m22);
+  pr[3] = make_double2(t[0], t[1]);
+  pr[4] = make_double2(t[2], 0.0);
+  pr[5] = make_double2(0.0, 0.0);
 }
 
 // ---------------------------------------------------------------- frames: B_f, g_c, w_f (+ Schur panels)
-// Persistent CTAs (two per SM) walk the chunk list (<= 128 observations of one frame each).  A
-// chunk's Jacobian records and residuals are contiguous, so each is ONE TMA bulk copy
-// (cp.async.bulk, 30 KB + 2 KB) into a double-buffered shared-memory stage: the next chunk streams
-// in while the current one is reduced.  Thread (grp, tr, tc) owns the 3x3 tile (tr, tc) of the
-// 12x12 block over the observations grp, grp+16, ...; the per-observation pass also writes the
-// observation's Schur panel rows.
-constexpr int kFrameThreads = 256;
-constexpr int kFrameGroups = kFrameThreads / 16;
-constexpr size_t kFrameSmem = (size_t)(2 * kChunk * kJacDoubles + 2 * kChunk * 2 + kChunk * 2) * sizeof(double) + 64;
+// One CTA per frame chunk (<= 128 observations of one frame), one thread per observation.  The thread reads its
+// compact Jacobian record, tau, the residual and the 72 bytes its point contributes (W = s_p L^-T and t_p, one
+// gathered 96-byte record), and
+//   * writes the observation's Schur panel rows  F = Jc^T (Jx W)  (12 x 3) straight into the point's
+//     (sub-tile, point) panel (k2_schur.cu describes the layout; zero rows of unobserved frames were written once,
+//     at allocation).  With Jc = [wr0 jr | -(1-tau) jx | wr1 jr | -tau jx] the twelve rows are two 3x3 products
+//     G_rot = jr^T Xm, G_c = jx^T Xm scaled by the four weights;
+//   * stores its two rows of  Z = [Jc | r | q]  (q = Jx t_p) transposed in shared memory.
+// The chunk's sums  B_f = Jc^T Jc, g_c = Jc^T r, w_f = Jc^T q  are then the lower tiles of the Gram matrix
+// Z^T Z (16 x 16, K = 256): three DMMA.8x8x4 per four rows, 16 k-steps per warp, summed over the four warps in
+// a fixed order -- no per-thread accumulators, no shared-memory operand traffic beyond two fragment loads per
+// k-step (the scalar version was bound by its barriers and 34 M bank conflicts per launch).
+constexpr int kFrameThreads = kChunk;              // 128
+constexpr int kZld = 2 * kChunk + 4;               // row stride of Z^T: == 4 (mod 16) -> conflict-free DMMA fragment loads
+constexpr size_t kFrameSmem = (size_t)(16 * kZld + 4 * 3 * 64) * sizeof(double);
 
-__device__ __forceinline__ unsigned fsmem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dmma_gram(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
-__global__ void __launch_bounds__(kFrameThreads, 2)
-frame_blocks_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac,
-                    const double* __restrict__ res, NormalEq ne, int with_wf) {
-  extern __shared__ __align__(128) unsigned char fsmem[];
-  double* sJbuf = reinterpret_cast<double*>(fsmem);                    // [2][128*30] raw records
-  double* sRbuf = sJbuf + 2 * kChunk * kJacDoubles;                    // [2][256]
-  double* sQ = sRbuf + 2 * kChunk * 2;                                 // [256] Jx_i t_p
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sQ + kChunk * 2);
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fsmem_u32(&bars[0])) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fsmem_u32(&bars[1])) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+__global__ void __launch_bounds__(kFrameThreads, 4)
+frame_blocks_kernel(SchurStructure st, ObsView obs, JacView jv, const double* __restrict__ res, NormalEq ne) {
+  extern __shared__ __align__(16) double fsm[];
+  double* Zt = fsm;                        // [16][kZld]: column-major Z, row index = (residual row) * 128 + observation
+  double* red = fsm + 16 * kZld;           // [4 warps][3 tiles][64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = blockIdx.x;
+  const long beg = st.chunk_beg[c];
+  const int cnt = st.chunk_cnt[c];
+  double z0[14], z1[14];
+#pragma unroll
+  for (int k = 0; k < 14; ++k) z0[k] = z1[k] = 0.0;
+  if (tid < cnt) {
+    const long i = beg + tid;
+    const double2* rp = reinterpret_cast<const double2*>(jv.rec + i * kJacCompact);
+    const double2 a01 = __ldg(rp), a2b0 = __ldg(rp + 1), b12 = __ldg(rp + 2);      // jx rows
+    const double2 c01 = __ldg(rp + 3), c2d0 = __ldg(rp + 4), d12 = __ldg(rp + 5);  // jr rows
+    const double tau = jv.tau[i];
+    const double2 r = reinterpret_cast<const double2*>(res)[i];
+    const int p = obs.point[i];
+    const int off = st.obs_phi_off[i];
+    const double2* pp = reinterpret_cast<const double2*>(ne.prec + (long)kPointRec * p);
+    const double2 w0 = __ldg(pp), w1 = __ldg(pp + 1), w2 = __ldg(pp + 2), t01 = __ldg(pp + 3), t2_ = __ldg(pp + 4);
+    const double jx0[3] = {a01.x, a01.y, a2b0.x}, jx1[3] = {a2b0.y, b12.x, b12.y};
+    const double jr0[3] = {c01.x, c01.y, c2d0.x}, jr1[3] = {c2d0.y, d12.x, d12.y};
+    const double th0 = 1.0 - tau, th1 = tau;
+    const double wr0 = jv.rot_interp ? th0 : 1.0, wr1 = jv.rot_interp ? th1 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      z0[k] = wr0 * jr0[k];      z1[k] = wr0 * jr1[k];
+      z0[3 + k] = -th0 * jx0[k]; z1[3 + k] = -th0 * jx1[k];
+      z0[6 + k] = wr1 * jr0[k];  z1[6 + k] = wr1 * jr1[k];
+      z0[9 + k] = -th1 * jx0[k]; z1[9 + k] = -th1 * jx1[k];
+    }
+    z0[12] = r.x; z1[12] = r.y;
+    z0[13] = jx0[0] * t01.x + jx0[1] * t01.y + jx0[2] * t2_.x;     // q = Jx t_p
+    z1[13] = jx1[0] * t01.x + jx1[1] * t01.y + jx1[2] * t2_.x;
+    if (off >= 0) {
+      // Xm = Jx W:  xa[k] = sum_{c <= k} jx0[c] W[k][c]
+      const double xa[3] = {jx0[0] * w0.x, jx0[0] * w0.y + jx0[1] * w1.x, jx0[0] * w1.y + jx0[1] * w2.x + jx0[2] * w2.y};
+      const double xb[3] = {jx1[0] * w0.x, jx1[0] * w0.y + jx1[1] * w1.x, jx1[0] * w1.y + jx1[1] * w2.x + jx1[2] * w2.y};
+      const unsigned mask = ne.pose_mask[st.chunk_frame[c]];
+      const double wgt[4] = {wr0, -th0, wr1, -th1};
+      double* dst = ne.Phi + off;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double gr[3], gc3[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          gr[j] = jr0[j] * xa[k] + jr1[j] * xb[k];
+          gc3[j] = jx0[j] * xa[k] + jx1[j] * xb[k];
+        }
+        double f[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+          const double g = ((a / 3) & 1) ? gc3[a % 3] : gr[a % 3];
+          f[a] = ((mask >> a) & 1) ? 0.0 : wgt[a / 3] * g;
+        }
+        // the 96-byte row leaves as three full 32-byte sectors (256-bit stores, sm_100): 16-byte stores would
+        // double the number of L2 write transactions
+#pragma unroll
+        for (int a = 0; a < 12; a += 4)
+          asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * kPanelLd + a), "d"(f[a]),
+                       "d"(f[a + 1]), "d"(f[a + 2]), "d"(f[a + 3])
+                       : "memory");
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 14; ++k) {
+    Zt[k * kZld + tid] = z0[k];
+    Zt[k * kZld + kChunk + tid] = z1[k];
+  }
+  Zt[14 * kZld + tid] = 0.0; Zt[14 * kZld + kChunk + tid] = 0.0;
+  Zt[15 * kZld + tid] = 0.0; Zt[15 * kZld + kChunk + tid] = 0.0;
+  __syncthreads();
+  // Gram tiles: D00 = rows/cols 0..7, D10 = rows 8..15 x cols 0..7, D11 = rows/cols 8..15
+  {
+    const int fr = lane >> 2, fc = lane & 3;
+    double d00[2] = {0.0, 0.0}, d10[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
+    const double* zlo = Zt + fr * kZld + warp * 64 + fc;
+    const double* zhi = zlo + 8 * kZld;
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) {
+      const double lo = zlo[4 * ks], hi = zhi[4 * ks];
+      dmma_gram(d00[0], d00[1], lo, lo);
+      dmma_gram(d10[0], d10[1], hi, lo);
+      dmma_gram(d11[0], d11[1], hi, hi);
+    }
+    double2* rw = reinterpret_cast<double2*>(red + warp * 192);
+    rw[lane] = make_double2(d00[0], d00[1]);            // element (fr, 2 fc + {0, 1}) of the tile
+    rw[32 + lane] = make_double2(d10[0], d10[1]);
+    rw[64 + lane] = make_double2(d11[0], d11[1]);
   }
   __syncthreads();
-  auto issue = [&](int c, int buf) {      // one thread
-    const long beg = st.chunk_beg[c];
-    const unsigned cnt = (unsigned)st.chunk_cnt[c];
-    const unsigned bar = fsmem_u32(&bars[buf]);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cnt * 256u) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     fsmem_u32(sJbuf + buf * kChunk * kJacDoubles)),
-                 "l"(jac + beg * kJacDoubles), "r"(cnt * 240u), "r"(bar)
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     fsmem_u32(sRbuf + buf * kChunk * 2)),
-                 "l"(res + beg * 2), "r"(cnt * 16u), "r"(bar)
-                 : "memory");
-  };
-  if (tid == 0 && (int)blockIdx.x < st.n_chunks) issue(blockIdx.x, 0);
-
-  const int grp = tid >> 4, tp = tid & 15, tr = tp >> 2, tc = tp & 3;
-  int it = 0;
-  for (int c = blockIdx.x; c < st.n_chunks; c += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const long beg = st.chunk_beg[c];
-    const int cnt = st.chunk_cnt[c];
-    // the other stage was fully consumed in the previous iteration (trailing __syncthreads)
-    if (tid == 0 && c + (int)gridDim.x < st.n_chunks) issue(c + gridDim.x, buf ^ 1);
-    {
-      const unsigned bar = fsmem_u32(&bars[buf]), parity = (unsigned)((it >> 1) & 1);
-      asm volatile(
-          "{\n"
-          ".reg .pred p;\n"
-          "WAIT_%=:\n"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-          "@p bra DONE_%=;\n"
-          "bra WAIT_%=;\n"
-          "DONE_%=:\n"
-          "}\n" ::"r"(bar), "r"(parity)
-          : "memory");
-    }
-    double* sJ = sJbuf + buf * kChunk * kJacDoubles;
-    const double* sR = sRbuf + buf * kChunk * 2;
-    // ---- phase 0: issue the per-point gathers of this chunk (point id -> t_p, L^-1, s_p, panel offset);
-    // they are consumed after the B / g_c accumulation below, which hides their latency
-    int pf_off = -1;
-    double pf_t[3] = {0.0, 0.0, 0.0}, pf_m[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, pf_s[3] = {0.0, 0.0, 0.0};
-    if (with_wf && tid < cnt) {
-      const int p = obs.point[beg + tid];
-      pf_off = st.obs_phi_off[beg + tid];
+  // fixed-order sum over the warps -> chunk partial  B (144, row-major, both triangles) | g_c (12) | w_f (12)
+  double* out = ne.partials + (long)c * kPartial;
+  for (int k = tid; k < kPartial; k += kFrameThreads) {
+    int r, cc;
+    if (k < 144) { r = k / 12; cc = k % 12; if (cc > r) { const int t = r; r = cc; cc = t; } }
+    else if (k < 156) { r = 12; cc = k - 144; }
+    else { r = 13; cc = k - 156; }
+    const int tile = (r < 8) ? 0 : ((cc < 8) ? 1 : 2);
+    const int e = tile * 64 + (r & 7) * 8 + (cc & 7);
+    double sum = 0.0;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) { pf_t[k] = ne.tp[3L * p + k]; pf_s[k] = ne.scale_p[3L * p + k]; }
-#pragma unroll
-      for (int k = 0; k < 6; ++k) pf_m[k] = ne.Minv[6L * p + k];
-    }
-    // ---- phase 1: B_f and g_c partial sums (independent of the points)
-    double acc[9], ga[3], wa[3];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-    ga[0] = ga[1] = ga[2] = wa[0] = wa[1] = wa[2] = 0.0;
-    for (int o = grp; o < cnt; o += kFrameGroups) {
-      const double* rec = sJ + o * kJacDoubles;
-#pragma unroll
-      for (int row = 0; row < 2; ++row) {
-        const double* pa = rec + jc_off(tr, row);
-        const double* pb = rec + jc_off(tc, row);
-        const double a0 = pa[0], a1 = pa[1], a2 = pa[2];
-        const double b0 = pb[0], b1 = pb[1], b2 = pb[2];
-        acc[0] += a0 * b0; acc[1] += a0 * b1; acc[2] += a0 * b2;
-        acc[3] += a1 * b0; acc[4] += a1 * b1; acc[5] += a1 * b2;
-        acc[6] += a2 * b0; acc[7] += a2 * b1; acc[8] += a2 * b2;
-        if (tc == 0) {
-          const double r = sR[2 * o + row];
-          ga[0] += a0 * r; ga[1] += a1 * r; ga[2] += a2 * r;
-        }
-      }
-    }
-    // ---- phase 2: per observation  q = Jx t_p  and the Schur panel rows  F = Jc^T (Jx s_p) L^-T (12 x 3),
-    // written straight into the point's (sub-tile, point) panel while the record is in shared memory
-    // (k2_schur.cu describes the layout; zero rows of unobserved frames were written once, at allocation)
-    if (tid < cnt) {
-      double q0 = 0.0, q1 = 0.0;
-      const double* rec = sJ + tid * kJacDoubles;
-      if (with_wf) {
-        const double* jx = rec + 24;
-        q0 = jx[0] * pf_t[0] + jx[1] * pf_t[1] + jx[2] * pf_t[2];
-        q1 = jx[3] * pf_t[0] + jx[4] * pf_t[1] + jx[5] * pf_t[2];
-        if (pf_off >= 0) {
-          const double m00 = pf_m[0], m10 = pf_m[1], m11 = pf_m[2], m20 = pf_m[3], m21 = pf_m[4], m22 = pf_m[5];
-          const double a0 = jx[0] * pf_s[0], a1 = jx[1] * pf_s[1], a2 = jx[2] * pf_s[2];
-          const double b0 = jx[3] * pf_s[0], b1 = jx[4] * pf_s[1], b2 = jx[5] * pf_s[2];
-          const double xa[3] = {a0 * m00, a0 * m10 + a1 * m11, a0 * m20 + a1 * m21 + a2 * m22};
-          const double xb[3] = {b0 * m00, b0 * m10 + b1 * m11, b0 * m20 + b1 * m21 + b2 * m22};
-          const unsigned mask = ne.pose_mask[st.chunk_frame[c]];
-          double* dst = ne.Phi + pf_off;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            double f[12];
-#pragma unroll
-            for (int a = 0; a < 12; ++a) {
-              // camera column a of the record: rows 0/1 at jc offsets
-              const int o0 = (a < 6) ? a : 12 + (a - 6);
-              f[a] = ((mask >> a) & 1) ? 0.0 : rec[o0] * xa[k] + rec[o0 + 6] * xb[k];
-            }
-            // the 96-byte row leaves as three full 32-byte sectors (256-bit stores, sm_100): 16-byte
-            // stores would double the number of L2 write transactions, which is what bounds this phase
-#pragma unroll
-            for (int a = 0; a < 12; a += 4)
-              asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * kPanelLd + a), "d"(f[a]),
-                           "d"(f[a + 1]), "d"(f[a + 2]), "d"(f[a + 3])
-                           : "memory");
-          }
-        }
-      }
-      sQ[2 * tid] = q0;
-      sQ[2 * tid + 1] = q1;
-    }
-    __syncthreads();
-    // ---- phase 3: w_f partial sums (need q)
-    if (tc == 0) {
-      for (int o = grp; o < cnt; o += kFrameGroups) {
-        const double* rec = sJ + o * kJacDoubles;
-#pragma unroll
-        for (int row = 0; row < 2; ++row) {
-          const double* pa = rec + jc_off(tr, row);
-          const double q = sQ[2 * o + row];
-          wa[0] += pa[0] * q; wa[1] += pa[1] * q; wa[2] += pa[2] * q;
-        }
-      }
-    }
-    __syncthreads();                 // sJ is dead: reuse it for the cross-group reduction
-    double* sAcc = sJ;               // [16][16][15]
-    double* my = sAcc + (grp * 16 + tp) * 15;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) my[k] = acc[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { my[9 + k] = ga[k]; my[12 + k] = wa[k]; }
-    __syncthreads();
-    // fixed-order sum over the groups -> chunk partial
-    double* out = ne.partials + (long)c * kPartial;
-    for (int k = tid; k < kPartial; k += kFrameThreads) {
-      int tpos, slot;
-      if (k < 144) {
-        const int r = k / 12, cc = k % 12;
-        tpos = (r / 3) * 4 + (cc / 3);
-        slot = (r % 3) * 3 + (cc % 3);
-      } else if (k < 156) {
-        const int r = k - 144;
-        tpos = (r / 3) * 4;
-        slot = 9 + r % 3;
-      } else {
-        const int r = k - 156;
-        tpos = (r / 3) * 4;
-        slot = 12 + r % 3;
-      }
-      double sum = 0.0;
-#pragma unroll
-      for (int g = 0; g < kFrameGroups; ++g) sum += sAcc[(g * 16 + tpos) * 15 + slot];
-      out[k] = sum;
-    }
-    // generic-proxy reads/writes of this stage must be ordered before the async-proxy refill
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    for (int w = 0; w < 4; ++w) sum += red[w * 192 + e];
+    out[k] = sum;
   }
 }
 
@@ -356,26 +319,23 @@ frame_reduce_kernel(SchurStructure st, NormalEq ne, int n_frames) {
 
 }  // namespace
 
-void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
-                         NormalEq ne, cudaStream_t s) {
+void launch_point_blocks(const SchurStructure& st, const JacView& jv, const double* res, NormalEq ne, cudaStream_t s) {
   if (ne.n_owned <= 0) return;
   point_blocks_kernel<<<(ne.n_owned + kPointBlockWarps - 1) / kPointBlockWarps, kPointBlockWarps * 32, 0, s>>>(
-      st.pt_ptr, st.pt_obs, jac, res, ne, ne.C, ne.gp);
+      st.pt_ptr, st.pt_obs, jv.rec, res, ne, ne.C, ne.gp);
 }
 
-void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
-                         int n_frames, NormalEq ne, bool with_wf, cudaStream_t s) {
+void launch_point_major_obs(const SchurStructure& st, const ObsView& obs, const double* tau, long n, double* pt_tau,
+                            int* pt_frame, cudaStream_t s) {
+  if (n > 0) point_major_obs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st.pt_obs, obs.frame, tau, n, pt_tau, pt_frame);
+}
+
+void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const JacView& jv, const double* res,
+                         int n_frames, NormalEq ne, cudaStream_t s) {
   static bool seen[64] = {};
-  static int sm_count[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (first_use_on_device(seen)) {
+  if (first_use_on_device(seen))
     cudaFuncSetAttribute(frame_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem);
-    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-  }
-  const int n_sm = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
-  if (st.n_chunks > 0)
-    frame_blocks_kernel<<<std::min(st.n_chunks, 2 * n_sm), kFrameThreads, kFrameSmem, s>>>(st, obs, jac, res, ne, with_wf ? 1 : 0);
+  if (st.n_chunks > 0) frame_blocks_kernel<<<st.n_chunks, kFrameThreads, kFrameSmem, s>>>(st, obs, jv, res, ne);
   if (n_frames > 0) frame_reduce_kernel<<<n_frames, 192, 0, s>>>(st, ne, n_frames);
 }
 

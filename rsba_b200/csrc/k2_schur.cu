@@ -48,7 +48,7 @@ constexpr size_t kSyrkSmem = (size_t)kStages * kStageDoubles * sizeof(double) + 
 // camera-side Jacobi scaling is applied to S afterwards (schur_finalize), so that partial sums of
 // different GPUs can be added before the scaling -- which depends on the global diag(B) -- is known.
 __global__ void __launch_bounds__(256)
-phi_build_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac, NormalEq ne) {
+phi_build_kernel(SchurStructure st, ObsView obs, JacView jv, NormalEq ne) {
   const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= (long)st.n_dup * kSubFrames) return;
   const int inc = st.dup_inc[u / kSubFrames], fs = (int)(u % kSubFrames);
@@ -70,7 +70,9 @@ phi_build_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac,
     const int beg = st.slot_beg[t];
     for (int d = 0; d < cnt; ++d) {
       const long i = st.pt_obs[beg + d];
-      const double2* J = reinterpret_cast<const double2*>(jac + i * kJacDoubles);
+      double Jf[kJacDoubles];
+      load_full_jacobian(jv, i, Jf);
+      const double2* J = reinterpret_cast<const double2*>(Jf);
       const double2 x0 = J[12], x1 = J[13], x2 = J[14];   // Jx rows: (x0.x x0.y x1.x) (x1.y x2.x x2.y)
       // xm[row][k] = sum_c Jx[row][c] s_p[c] L^-1[k][c]
       const double a0 = x0.x * sp0, a1 = x0.y * sp1, a2 = x1.x * sp2;
@@ -371,11 +373,11 @@ camera_rhs_kernel(SchurStructure st, NormalEq ne, LmOptionsDev o, int n_frames, 
 
 }  // namespace
 
-void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+void launch_phi_build(const SchurStructure& st, const ObsView& obs, const JacView& jv, NormalEq ne,
                       cudaStream_t s) {
   if (st.n_dup <= 0) return;   // the common case: frame_blocks_kernel has written every panel
   const long n = (long)st.n_dup * kSubFrames;
-  phi_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, obs, jac, ne);
+  phi_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, obs, jv, ne);
 }
 
 void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {

@@ -73,7 +73,7 @@ frame_step_kernel(NormalEq ne, const int* __restrict__ tile_pos, const double* _
 constexpr int kPointStepWarps = 8;
 
 __global__ void __launch_bounds__(kPointStepWarps * 32)
-point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac,
+point_step_kernel(SchurStructure st, JacView jv,
                   const double* __restrict__ jac_cam, int cam_frame, NormalEq ne,
                   const double* __restrict__ delta_c, int n_points, const double* __restrict__ points,
                   double* __restrict__ delta_p, double* __restrict__ trial, double* __restrict__ scratch) {
@@ -87,18 +87,18 @@ point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
     const int beg = st.pt_ptr[p], end = st.pt_ptr[p + 1];
     for (int e = beg + lane; e < end; e += 32) {
       const long i = st.pt_obs[e];
-      const double2* J = reinterpret_cast<const double2*>(jac + i * kJacDoubles);
-      const double2* dc = reinterpret_cast<const double2*>(delta_c + 12L * obs.frame[i]);
-      double m0 = 0.0, m1 = 0.0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const double2 d = dc[h * 3 + q];
-          const double2 r0 = J[h * 6 + q], r1 = J[h * 6 + 3 + q];
-          m0 += r0.x * d.x + r0.y * d.y;
-          m1 += r1.x * d.x + r1.y * d.y;
-        }
+      // compact record: Jc delta_c = jr . (wr0 d_rot0 + wr1 d_rot1) - jx . ((1-tau) d_c0 + tau d_c1), i.e. the
+      // Jacobian of the INTERPOLATED pose applied to the interpolated camera step -- 96 bytes per observation
+      const double2* rp = reinterpret_cast<const double2*>(jv.rec + i * kJacCompact);
+      const double2 a01 = rp[0], a2b0 = rp[1], b12 = rp[2], c01 = rp[3], c2d0 = rp[4], d12 = rp[5];
+      const double tau = st.pt_tau[e];
+      const double2* dc = reinterpret_cast<const double2*>(delta_c + 12L * st.pt_frame[e]);
+      const double2 u0 = dc[0], u1 = dc[1], u2 = dc[2], u3 = dc[3], u4 = dc[4], u5 = dc[5];
+      const double th0 = 1.0 - tau, wr0 = jv.rot_interp ? th0 : 1.0, wr1 = jv.rot_interp ? tau : 0.0;
+      const double dr0 = wr0 * u0.x + wr1 * u3.x, dr1 = wr0 * u0.y + wr1 * u3.y, dr2 = wr0 * u1.x + wr1 * u4.x;
+      const double dq0 = th0 * u1.y + tau * u4.y, dq1 = th0 * u2.x + tau * u5.x, dq2 = th0 * u2.y + tau * u5.y;
+      double m0 = c01.x * dr0 + c01.y * dr1 + c2d0.x * dr2 - (a01.x * dq0 + a01.y * dq1 + a2b0.x * dq2);
+      double m1 = c2d0.y * dr0 + d12.x * dr1 + d12.y * dr2 - (a2b0.y * dq0 + b12.x * dq1 + b12.y * dq2);
       if (jac_cam) {   // uncalibrated variant: + Jcam * delta_intrinsics
         const double* jc = jac_cam + i * 18;
         const double* di = delta_c + 12L * cam_frame;
@@ -108,10 +108,9 @@ point_step_kernel(SchurStructure st, ObsView obs, const double* __restrict__ jac
           m1 += jc[9 + k] * di[k];
         }
       }
-      const double2 x0 = J[12], x1 = J[13], x2 = J[14];
-      a0 += x0.x * m0 + x1.y * m1;
-      a1 += x0.y * m0 + x2.x * m1;
-      a2 += x1.x * m0 + x2.y * m1;
+      a0 += a01.x * m0 + a2b0.y * m1;
+      a1 += a01.y * m0 + b12.x * m1;
+      a2 += a2b0.x * m0 + b12.y * m1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -225,7 +224,7 @@ constexpr int kStateBlocks = 296;
 
 }  // namespace
 
-void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
+void launch_step_update(const SchurStructure& st, const ObsView& obs, const JacView& jv, const double* jac_cam,
                         int cam_frame, NormalEq ne,
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
@@ -235,7 +234,7 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const doub
                                                bounded_param, lower_bound);
   const int nb = (ne.n_owned + kPointStepWarps - 1) / kPointStepWarps;
   if (nb > 0)
-    point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, obs, jac, jac_cam, cam_frame, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
+    point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, jv, jac_cam, cam_frame, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
   step_final_kernel<<<1, kWideThreads, 0, s>>>(scratch, nb, scalars);
 }
 

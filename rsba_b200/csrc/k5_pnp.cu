@@ -229,6 +229,7 @@ extern "C" int rsba_cuda_pnp_batch(rsba_problem* h, const double cam9[9], int sh
                                    int sample_size, const int* sample_idx, double* poses,
                                    const rsba_solve_options* options, double inlier_threshold, double* final_cost,
                                    int* usable, int* iterations, int* inlier_count) {
+  return rsba::api_guard([&]() -> int {
   auto bad = [](const char* m) { set_last_error(m); return (int)RSBA_ERR_INVALID_ARGUMENT; };
   if (!h || !cam9 || !scanlines || !points3d || !obs_xy || !sample_idx || !poses || !options) return bad("NULL argument");
   if (n_points <= 0 || n_hyp < 0 || sample_size <= 0 || sample_size > kPnpMaxSample)
@@ -281,4 +282,5 @@ extern "C" int rsba_cuda_pnp_batch(rsba_problem* h, const double cam9[9], int sh
   RSBA_CUDA_TRY(cudaStreamSynchronize(s));
   stage_collect(h, kStagePnp);
   return RSBA_OK;
+  });
 }

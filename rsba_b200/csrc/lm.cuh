@@ -9,6 +9,21 @@
 
 namespace rsba {
 
+// The Jacobian as K1 leaves it for the solver: compact records (rsba_reproj_math.h) in observation order.
+struct JacView {
+  const double* rec;     // [N][kJacCompact]  jx row 0 | jx row 1 | jr row 0 | jr row 1
+  const double* tau;     // [N]
+  int rot_interp;        // shutter != GLOBAL && interpolateRotation: rotation columns weigh (1-tau, tau), else (1, 0)
+};
+// the full 30-double record of observation i (kernels off the hot path)
+__device__ __forceinline__ void load_full_jacobian(const JacView& jv, long i, double* __restrict__ J) {
+  double rec[kJacCompact];
+  const double2* src = reinterpret_cast<const double2*>(jv.rec + i * kJacCompact);
+#pragma unroll
+  for (int k = 0; k < kJacCompact / 2; ++k) { const double2 v = src[k]; rec[2 * k] = v.x; rec[2 * k + 1] = v.y; }
+  expand_jacobian(rec, jv.tau[i], jv.rot_interp != 0, J);
+}
+
 constexpr int kTile = 96;          // Cholesky tile = 8 frames x 12 parameters
 constexpr int kFramesPerTile = kTile / kFrameParams;
 
@@ -17,6 +32,8 @@ struct SchurStructure {
   // point-major CSR over the frame-sorted observations
   const int* pt_ptr;      // [P+1]
   const int* pt_obs;      // [N]
+  const double* pt_tau;   // [N] tau of observation pt_obs[e] (point-major copy: coalesced for the point kernels)
+  const int* pt_frame;    // [N] its frame
   // frame chunks for the per-frame reductions: chunk c covers obs [chunk_beg[c], chunk_beg[c]+chunk_cnt[c]) of chunk_frame[c]
   const int* chunk_frame; // [n_chunks]
   const int* chunk_beg;   // [n_chunks]
@@ -62,6 +79,7 @@ constexpr int kSub = kSubFrames * kFrameParams;   // 48 rows
 constexpr int kPanelLd = kSub + 4;            // 48 rows + 4 pad: conflict-free DMMA fragment loads (ld % 16 == 4)
 constexpr int kPanelDoubles = 3 * kPanelLd;   // one bulk copy of 1248 bytes
 constexpr int kSchurSegPoints = 512;
+constexpr int kPointRec = 12;
 
 struct NormalEq {
   // unscaled blocks of J^T J and J^T r
@@ -77,6 +95,8 @@ struct NormalEq {
   double* tp;       // [P][3]    Cinv * gp
   double* Bcam;     // [F][144] uncalibrated variant: coupling of frame f (rows) with the intrinsics pseudo-frame (cols 0..8)
   double* Minv;     // [P][6]    L^-1 of the damped scaled point block (m00 m10 m11 m20 m21 m22)
+  double* prec;     // [P][kPointRec] what frame_blocks gathers per observation: W = s_p L^-T as (s0 m00, s0 m10, s1 m11,
+                    //           s0 m20, s1 m21, s2 m22) | t_p (3) | pad -- three full 32-byte sectors
   double* Phi;      // [n_inc+1][3][kPanelLd]  panels s_c Jc^T (Jx s_p) L^-T; last panel all zero
   double* partial;  // [n_items][48*48] per-item partial products of the Schur SYRK
   double* scale_c;  // [12F] Jacobi scaling (1 for constant parameters)
@@ -100,19 +120,21 @@ struct LmOptionsDev {
 };
 
 // ---- K2 ---------------------------------------------------------------------------------
-void launch_point_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
-                         NormalEq ne, cudaStream_t s);
-void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* res,
-                         int n_frames, NormalEq ne, bool with_wf, cudaStream_t s);
+void launch_point_blocks(const SchurStructure& st, const JacView& jv, const double* res, NormalEq ne, cudaStream_t s);
+void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const JacView& jv, const double* res,
+                         int n_frames, NormalEq ne, cudaStream_t s);
+// point-major copies of tau / frame (once per solve, after the first K1)
+void launch_point_major_obs(const SchurStructure& st, const ObsView& obs, const double* tau, long n, double* pt_tau,
+                            int* pt_frame, cudaStream_t s);
 // n_frames > 0: the camera parameters; points: the owned points (two calls: the point part runs before the
 // all-reduce, the camera part after it)
 void launch_jacobi_scale(int n_frames, bool points, NormalEq ne, bool enabled, cudaStream_t s);
 void launch_point_invert(NormalEq ne, LmOptionsDev o, cudaStream_t s);
 // uncalibrated variant (k2_cam.cu): blocks of the intrinsics pseudo-frame (frame index n_frames) and its panel rows
-void launch_cam_blocks(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
+void launch_cam_blocks(const SchurStructure& st, const ObsView& obs, const JacView& jv, const double* jac_cam,
                        const double* res, NormalEq ne, int n_frames, double* partials, double* scratch,
                        cudaStream_t s);
-void launch_phi_cam(const SchurStructure& st, const double* jac, const double* jac_cam, NormalEq ne, int n_points,
+void launch_phi_cam(const SchurStructure& st, const JacView& jv, const double* jac_cam, NormalEq ne, int n_points,
                     int n_frames, cudaStream_t s);
 
 // adds the priors' J^T J / J^T r to B, gc, diagB and writes the frame-to-previous-frame couplings
@@ -129,7 +151,7 @@ void launch_pose_prior_norms(const PosePriorView& pv, double* scalars, cudaStrea
 
 // Schur complement (k2_schur.cu).  S is tile-packed (see TileSchedule: structurally non-zero lower
 // tiles, diagonal tiles stored as full squares); rhs/d2_c in the permuted order given by tile_pos.
-void launch_phi_build(const SchurStructure& st, const ObsView& obs, const double* jac, NormalEq ne,
+void launch_phi_build(const SchurStructure& st, const ObsView& obs, const JacView& jv, NormalEq ne,
                       cudaStream_t s);
 void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s);
 // writes the UNSCALED tiles  B - Phi Phi^T  (partial sums on a multi-GPU rank)
@@ -196,7 +218,7 @@ struct StepScalars {  // device doubles, filled by launch_step_update
 };
 // delta_c = -scale_c * y ; delta_p by back-substitution ; trial = x + delta ; scalars
 // jac_cam / cam_frame: uncalibrated variant (NULL / -1 otherwise)
-void launch_step_update(const SchurStructure& st, const ObsView& obs, const double* jac, const double* jac_cam,
+void launch_step_update(const SchurStructure& st, const ObsView& obs, const JacView& jv, const double* jac_cam,
                         int cam_frame, NormalEq ne,
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,

@@ -51,6 +51,9 @@ struct LmState {
   bool dense = false, reorder = true;
   // ---- numeric state (device)
   DeviceBuffer<double> B, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
+  DeviceBuffer<double> prec, pt_tau;      // per-point gather record; point-major tau (refreshed once per solve)
+  DeviceBuffer<int> pt_frame;
+  bool pt_major_valid = false;
   // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
   DeviceBuffer<double> solve_partials, fwd_partials;
   DeviceBuffer<int> fwd_slot;
@@ -201,6 +204,11 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(lm->B.resize(Fz * 144));
   RSBA_CUDA_TRY(lm->C.resize(Pz * 6)); RSBA_CUDA_TRY(lm->gp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Cinv.resize(Pz * 6));
   RSBA_CUDA_TRY(lm->tp.resize(Pz * 3)); RSBA_CUDA_TRY(lm->Minv.resize(Pz * 6));
+  RSBA_CUDA_TRY(lm->prec.resize(Pz * kPointRec));
+  RSBA_CUDA_TRY(cudaMemsetAsync(lm->prec.ptr, 0, lm->prec.bytes(), s));
+  RSBA_CUDA_TRY(lm->pt_tau.resize(std::max<size_t>((size_t)h->n_obs, 1)));
+  RSBA_CUDA_TRY(lm->pt_frame.resize(std::max<size_t>((size_t)h->n_obs, 1)));
+  lm->st.pt_tau = lm->pt_tau.ptr; lm->st.pt_frame = lm->pt_frame.ptr;
   RSBA_CUDA_TRY(lm->Phi.resize((size_t)(n_inc + 1) * kPanelDoubles));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->Phi.ptr, 0, lm->Phi.bytes(), s));   // pad columns + the zero panel
   RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kSub * kSub));
@@ -232,6 +240,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   ne.gc = lm->S.ptr + s_count; ne.wf = ne.gc + Fz * 12; ne.diagB = ne.wf + Fz * 12;
   lm->misc = ne.diagB + Fz * 12;
   ne.Cinv = lm->Cinv.ptr; ne.tp = lm->tp.ptr; ne.Minv = lm->Minv.ptr; ne.Phi = lm->Phi.ptr; ne.partial = lm->partial.ptr;
+  ne.prec = lm->prec.ptr;
   ne.scale_c = lm->scale_c.ptr; ne.scale_p = lm->scale_p.ptr;
   ne.d2_c = lm->d2_c.ptr; ne.d2_p = lm->d2_p.ptr; ne.partials = lm->partials.ptr;
   ne.pose_mask = lm->pose_mask.ptr; ne.point_const = lm->point_const.ptr; ne.point_owned = lm->point_owned.ptr;
@@ -291,28 +300,38 @@ __global__ void pack_cost_kernel(const double* __restrict__ cost, const int* __r
   out[1] = (double)invalid[0];
 }
 
-// Normal equations + Schur complement for `radius` from the Jacobian in h->d_jac (and, when
+JacView jac_view(const rsba_problem* h) {
+  return JacView{h->d_jacc.ptr, h->d_tau.ptr, (h->cm.shutter != 0 && h->cm.interp_rot) ? 1 : 0};
+}
+
+// Normal equations + Schur complement for `radius` from the compact Jacobian in h->d_jacc (and, when
 // new_jacobian, the cost / invalid count of the evaluation that produced it, in h->d_scalars).
 int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, double radius, bool new_jacobian,
               bool compute_scale) {
   cudaStream_t s = h->stream;
   const ObsView obs = h->obs_view();
   const LmOptionsDev o{radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
+  const JacView jv = jac_view(h);
   stage_begin(h, kStageSchur);
+  if (new_jacobian && !lm->pt_major_valid) {   // tau is a constant of the observation: once per solve
+    launch_point_major_obs(lm->st, obs, h->d_tau.ptr, h->n_obs, lm->pt_tau.ptr, lm->pt_frame.ptr, s);
+    lm->pt_major_valid = true;
+    h->launches += 1;
+  }
   if (new_jacobian) {
     stage_begin(h, kStagePointBlocks);
-    launch_point_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, lm->ne, s);
+    launch_point_blocks(lm->st, jv, h->d_res.ptr, lm->ne, s);
     stage_end(h, kStagePointBlocks);
     h->launches += 1;
   }
   if (compute_scale) { launch_jacobi_scale(0, true, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
   launch_point_invert(lm->ne, o, s);
   stage_begin(h, kStageFrameBlocks);
-  launch_frame_blocks(lm->st, obs, h->d_jac.ptr, h->d_res.ptr, lm->n_cam_frames, lm->ne, true, s);
+  launch_frame_blocks(lm->st, obs, jv, h->d_res.ptr, lm->n_cam_frames, lm->ne, s);
   stage_end(h, kStageFrameBlocks);
   h->launches += 3;
   if (lm->free_cam) {   // blocks of the intrinsics pseudo-frame and its couplings with the frames
-    launch_cam_blocks(lm->st, obs, h->d_jac.ptr, h->d_jac_cam.ptr, h->d_res.ptr, lm->ne, h->n_frames,
+    launch_cam_blocks(lm->st, obs, jv, h->d_jac_cam.ptr, h->d_res.ptr, lm->ne, h->n_frames,
                       lm->cam_partials.ptr, lm->cam_scratch.ptr, s);
     h->launches += 3;
   }
@@ -328,10 +347,10 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   }
   launch_clear_tiles(lm->S.ptr, lm->ts, s);
   stage_begin(h, kStagePhiBuild);
-  launch_phi_build(lm->st, obs, h->d_jac.ptr, lm->ne, s);
+  launch_phi_build(lm->st, obs, jv, lm->ne, s);
   stage_end(h, kStagePhiBuild);
   if (lm->free_cam) {
-    launch_phi_cam(lm->st, h->d_jac.ptr, h->d_jac_cam.ptr, lm->ne, h->n_points, h->n_frames, s);
+    launch_phi_cam(lm->st, jv, h->d_jac_cam.ptr, lm->ne, h->n_points, h->n_frames, s);
     h->launches += 1;
   }
   stage_begin(h, kStageSchurSyrk);
@@ -433,7 +452,7 @@ void factor_and_solve(rsba_problem* h, LmState* lm) {
 
 void step_update(rsba_problem* h, LmState* lm) {
   stage_begin(h, kStageUpdate);
-  launch_step_update(lm->st, h->obs_view(), h->d_jac.ptr, lm->free_cam ? h->d_jac_cam.ptr : nullptr,
+  launch_step_update(lm->st, h->obs_view(), jac_view(h), lm->free_cam ? h->d_jac_cam.ptr : nullptr,
                      lm->free_cam ? h->n_frames : -1, lm->ne, lm->y.ptr, lm->n_cam_frames, h->n_points,
                      h->d_poses.ptr, h->d_points.ptr, lm->delta_c.ptr, lm->delta_p.ptr, lm->trial_poses.ptr,
                      lm->trial_points.ptr, lm->scalars.ptr, lm->scratch.ptr,
@@ -527,10 +546,12 @@ int prepare_solve(rsba_problem* h, const rsba_solve_options* opt) {
   if (rc) return rc;
   rc = upload_pose_priors(h);
   if (rc) return rc;
-  rc = ensure_eval_buffers(h, true);
+  rc = ensure_eval_buffers(h, true, true);
   if (rc) return rc;
   h->reorder_tiles = opt->reorder_tiles != 0;
-  return ensure_lm(h, opt->dense_cholesky != 0);
+  rc = ensure_lm(h, opt->dense_cholesky != 0);
+  if (!rc) h->lm->pt_major_valid = false;   // the camera model (hence tau) may have changed since the last solve
+  return rc;
 }
 
 }  // namespace
@@ -550,6 +571,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   int rc = prepare_solve(h, opt);
   if (rc) { snprintf(sum->message, sizeof(sum->message), "%s", rsba_cuda_last_error()); return rc; }
   LmState* lm = h->lm;
+  h->fine_timers = getenv("RSBA_CUDA_TRACE") != nullptr;
   for (auto& t : h->timers) t.total_ms = 0.0;
   sum->num_residual_blocks = h->n_obs;
   sum->num_parameters_reduced = lm->num_free_params + h->free_pose_prior_params();
@@ -582,7 +604,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   const int max_invalid = opt->max_num_consecutive_invalid_steps > 0 ? opt->max_num_consecutive_invalid_steps
                                                                       : RSBA_CERES_MAX_NUM_CONSECUTIVE_INVALID_STEPS;
   // ---- iteration 0: evaluate, linearise (fixes the Jacobi scaling), gradient check
-  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
+  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
   if (rc) return rc;
   sum->num_jacobian_evaluations = 1;
   if ((rc = linearize(h, lm, *opt, radius, true, true))) return rc;
@@ -666,7 +688,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         radius = std::min(opt->max_trust_region_radius,
                           radius / std::max(RSBA_CERES_LM_MIN_RADIUS_SHRINK, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
         decrease = RSBA_CERES_LM_INITIAL_DECREASE_FACTOR;
-        rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
+        rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
         if (rc) return rc;
         sum->num_jacobian_evaluations++;
         if ((rc = linearize(h, lm, *opt, radius, true, false))) return rc;
@@ -700,7 +722,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
     RSBA_CUDA_TRY(cudaMemcpyAsync(&h->ratio_value, h->d_poses.ptr + 12L * h->n_frames + 9, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));
   sum->time_schur_ms += h->timers[kStageFinalize].total_ms;
-  if (h->ptr_mode) {
+  if (h->ptr_mode && h->scatter_owner) {
     rc = scatter_pointer_parameters(h);
     if (rc) return rc;
   }
@@ -717,7 +739,8 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
   if (rc) return rc;
   if (!(radius > 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "radius must be positive");
   LmState* lm = h->lm;
-  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr);
+  h->fine_timers = true;
+  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
   if (rc) return rc;
   if ((rc = linearize(h, lm, *opt, radius, true, true))) return rc;
   const long n = 12L * lm->n_cam_frames;   // uncalibrated variant: the intrinsics pseudo-frame comes last

@@ -75,7 +75,10 @@ int allreduce_sum(rsba_problem* h, double* buf, size_t count) {
   return RSBA_OK;
 }
 
+static bool stage_on(const rsba_problem* h, Stage s) { return s < kStagePointBlocks || s == kStagePnp || s == kStageFinalize || h->fine_timers; }
+
 void stage_begin(rsba_problem* h, Stage s) {
+  if (!stage_on(h, s)) return;
   StageTimer& t = h->timers[s];
   if (!t.beg) {
     cudaEventCreate(&t.beg);
@@ -85,6 +88,7 @@ void stage_begin(rsba_problem* h, Stage s) {
 }
 
 void stage_end(rsba_problem* h, Stage s) {
+  if (!stage_on(h, s)) return;
   StageTimer& t = h->timers[s];
   cudaEventRecord(t.end, h->stream);
   t.pending = true;
@@ -103,30 +107,38 @@ double stage_collect(rsba_problem* h, Stage s) {
   return t.last_ms;
 }
 
-int ensure_eval_buffers(rsba_problem* h, bool jac) {
+int ensure_eval_buffers(rsba_problem* h, bool jac, bool compact) {
   const size_t n = (size_t)h->n_obs;
   RSBA_CUDA_TRY(h->d_res.resize(2 * n));
   RSBA_CUDA_TRY(h->d_valid.resize(n));
   RSBA_CUDA_TRY(h->d_cost_partials.resize((size_t)k1_num_partials(h->n_obs) + 2));
   RSBA_CUDA_TRY(h->d_scalars.resize(16));
   RSBA_CUDA_TRY(h->d_invalid.resize(4));
-  if (jac) RSBA_CUDA_TRY(h->d_jac.resize((size_t)kJacDoubles * n));
+  if (jac && !compact) RSBA_CUDA_TRY(h->d_jac.resize((size_t)kJacDoubles * n));
+  if (jac && compact) {
+    RSBA_CUDA_TRY(h->d_jacc.resize((size_t)kJacCompact * n));
+    RSBA_CUDA_TRY(h->d_tau.resize(n));
+  }
   if (jac && h->free_cam) RSBA_CUDA_TRY(h->d_jac_cam.resize((size_t)18 * n));
   return RSBA_OK;
 }
 
 int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* points,
-                 double* cost_out_host, long* invalid_out_host) {
-  int rc = ensure_eval_buffers(h, jac);
+                 double* cost_out_host, long* invalid_out_host, bool compact, bool store_residuals) {
+  int rc = ensure_eval_buffers(h, jac, compact);
   if (rc) return rc;
   RSBA_CUDA_TRY(cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), h->stream));
   const Stage st = jac ? kStageJacobian : kStageResidual;
   stage_begin(h, st);
-  if (jac) {
+  if (jac && compact) {
+    launch_k1_compact(h->cm, h->obs_view(), poses, points, h->d_res.ptr, h->d_jacc.ptr, h->d_tau.ptr, h->d_jac_cam.ptr,
+                      h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
+  } else if (jac) {
     launch_k1(h->cm, h->obs_view(), poses, points, h->d_res.ptr, h->d_jac.ptr, h->d_jac_cam.ptr, h->d_valid.ptr,
               h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
   } else {
-    launch_k1r(h->cm, h->obs_view(), poses, points, h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream);
+    launch_k1r(h->cm, h->obs_view(), poses, points, h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream,
+               store_residuals ? h->d_res.ptr : nullptr, store_residuals ? h->d_valid.ptr : nullptr);
   }
   // the priors' cost rides in the extra partial slot (rank 0 only: they are not sharded)
   const int np = k1_num_partials(h->n_obs);
@@ -1072,7 +1084,8 @@ int rsba_cuda_evaluate(rsba_problem* h, double* cost, double* residuals, double*
   const bool jac = jacobian != nullptr;
   long bad = 0;
   double c = 0.0;
-  rc = run_evaluate(h, jac || residuals || valid, h->d_poses.ptr, h->d_points.ptr, &c, &bad);
+  // only a requested Jacobian runs the Jacobian kernel (and allocates its 240 bytes per observation)
+  rc = run_evaluate(h, jac, h->d_poses.ptr, h->d_points.ptr, &c, &bad, false, residuals || valid);
   if (rc) return rc;
   if (cost) *cost = c;
   const long n = h->n_obs, ng = h->n_obs_global;

@@ -99,6 +99,9 @@ struct rsba_problem {
   rsba::DeviceBuffer<int> d_obs_frame, d_obs_point;
   rsba::DeviceBuffer<double> d_poses, d_points;
   rsba::DeviceBuffer<double> d_res, d_jac;
+  // the solver's own linearisation: compact Jacobian records [N][12] and tau [N] (rsba_reproj_math.h);
+  // d_jac ([N][30], the Ceres layout) is only allocated for rsba_cuda_evaluate
+  rsba::DeviceBuffer<double> d_jacc, d_tau;
   // uncalibrated variant: the shared intrinsics are the 9 leading parameters of a pseudo-frame stored
   // behind the real frames in d_poses (which always has room for it); d_jac_cam = [N][2][9]
   bool free_cam = false;
@@ -167,6 +170,10 @@ struct rsba_problem {
   }
 
   rsba::StageTimer timers[rsba::kNumStages];
+  // events around single kernels (kStagePointBlocks ...) are only recorded when this is set: rsba_cuda_solve
+  // leaves them out (every record is a stream operation between two kernels), rsba_cuda_linearize_and_step --
+  // what bench.py's per-kernel pass calls -- and RSBA_CUDA_TRACE switch them on
+  bool fine_timers = false;
   long launches = 0;
 
   rsba::LmState* lm = nullptr;
@@ -175,6 +182,7 @@ struct rsba_problem {
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  bool scatter_owner = true;   // pointer API under rsba_multi: only one rank writes the caller's blocks back
 
   rsba::ObsView obs_view() const {
     return rsba::ObsView{d_obs_xy.ptr, d_obs_frame.ptr, d_obs_point.ptr, n_obs};
@@ -198,10 +206,12 @@ int upload_pose_priors(rsba_problem* h);          // GoodPosePrior list (+ the p
 int finalize_pointer_problem(rsba_problem* h);   // pointer API -> sorted SoA on device
 int gather_pointer_parameters(rsba_problem* h);  // caller blocks -> device
 int scatter_pointer_parameters(rsba_problem* h); // device -> caller blocks
-int ensure_eval_buffers(rsba_problem* h, bool jac);
+int ensure_eval_buffers(rsba_problem* h, bool jac, bool compact = false);
 // residual(+Jacobian) evaluation at (poses, points) on the device; cost lands in d_scalars[0]
+// compact (with jac): the Jacobian goes to d_jacc / d_tau as 12-double records instead of d_jac
 int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* points,
-                 double* cost_out_host, long* invalid_out_host);
+                 double* cost_out_host, long* invalid_out_host, bool compact = false,
+                 bool store_residuals = false /* without jac: also write d_res / d_valid */);
 
 void lm_state_free(LmState* s);
 }  // namespace rsba
