@@ -22,10 +22,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# K1 inside the LM loop writes the COMPACT Jacobian record (12 doubles: jr, jx of the interpolated pose, from which
-# J_pose0 / J_pose1 / J_point follow with tau) + tau: xy, indices, residual, record, tau.  The 240-byte Ceres layout
-# of SURVEY 8d is what rsba_cuda_evaluate writes (K1_FULL_BYTES_FIXED; timed separately as roofline_k1_full).
-K1_BYTES_FIXED = 16 + 8 + 16 + 96 + 8
+# Inside the LM loop the residual + Jacobian evaluation is the fused point pass (k2_fused.cu): per observation it reads
+# xy (16) and three point-major indices (12) and writes the compact Jacobian record (96: jr, jx of the interpolated
+# pose, from which J_pose0 / J_pose1 / J_point follow with tau), tau (8) and the observation's 12 x 3 Schur panel
+# rows (288); per point it reads X (24) + the CSR pointer (4) and writes C, g, Cinv, L^-1, t, D^2, (X | t) (288).
+# The 240-byte Ceres layout of SURVEY 8d is what rsba_cuda_evaluate writes (K1_FULL_BYTES_FIXED; roofline_k1_full).
+K1_BYTES_FIXED = 16 + 12 + 96 + 8 + 288
+K1_BYTES_PER_POINT = 24 + 4 + 288
 K1_FULL_BYTES_FIXED = 16 + 8 + 16 + 240 + 1
 
 
@@ -44,7 +47,9 @@ def emit(obj):
 
 
 def k1_bytes_per_obs(scene, full=False) -> float:
-    return (K1_FULL_BYTES_FIXED if full else K1_BYTES_FIXED) + (24.0 * scene.num_points + 96.0 * scene.num_frames) / scene.num_obs
+    if full:
+        return K1_FULL_BYTES_FIXED + (24.0 * scene.num_points + 96.0 * scene.num_frames) / scene.num_obs
+    return K1_BYTES_FIXED + (K1_BYTES_PER_POINT * scene.num_points + 96.0 * scene.num_frames) / scene.num_obs
 
 
 def load_peaks():
@@ -386,6 +391,8 @@ def run_ours(args):
     value = n_total / (ms_per_step * 1e-3) / 1e6
     stages = {k: getattr(summ, f"time_{k}_ms") / args.steps
               for k in ("jacobian", "residual", "schur", "cholesky", "update", "allreduce")}
+    # RSBA_CUDA_FINE_TIMERS=1 (diagnostic): the per-kernel events are also recorded inside rsba_cuda_solve
+    inloop = {k: round(pb.stage_ms(k), 4) for k in api.STAGES} if os.environ.get("RSBA_CUDA_FINE_TIMERS") else None
 
     # ---------------- per-kernel times: CUDA events inside the library on the launching stream
     pb.set_parameters(poses_h, points_h)
@@ -465,8 +472,9 @@ def run_ours(args):
     k1 = kern["jacobian"]
     n_local = int(summ.num_residual_blocks)     # this rank's share of the observations (== n_total on one GPU)
     share = n_local / n_total
-    tr_k1, tr_k1_src = dram_traffic("k1_kernel<1, 0, 1>", args.config, world)
-    roof_k1 = {"bound": "hbm", "kernel": "k1_kernel<true, compact> (residual + compact Jacobian record, the solver's linearisation)",
+    tr_k1, tr_k1_src = dram_traffic("point_pass_kernel", args.config, world)
+    roof_k1 = {"bound": "hbm", "kernel": "point_pass_kernel (residual + Jacobian of every observation, point blocks + inverse, "
+                                          "Schur panel rows, point-major compact Jacobian records: the solver's linearisation)",
                "achieved": n_local * bpo / (k1 * 1e-3) / 1e9,
                "peak": hbm_peak, "unit": "GB/s", "traffic": tr_k1, "traffic_source": tr_k1_src, "peak_source": hbm_src,
                "algorithmic_bytes": n_local * bpo, "bytes_per_obs": bpo, "kernel_ms": k1,
@@ -515,7 +523,7 @@ def run_ours(args):
         "lm": {"iterations": summ.iterations, "successful_steps": summ.num_successful_steps,
                "jacobian_evals": summ.num_jacobian_evaluations, "residual_evals": summ.num_residual_evaluations,
                "initial_cost": summ.initial_cost, "final_cost": summ.final_cost},
-        "kernel_ms": kern,
+        "kernel_ms": kern, "inloop_stage_ms_last_iteration": inloop,
         "roofline": dict(roofs[dominant], dominant=dominant),
         "roofline_k1": roof_k1, "roofline_k1_full": roof_k1_full, "roofline_schur": roof_syrk, "roofline_cholesky": roof_chol,
         "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": "M evals/s", "h2d_bytes_per_step": h2d,

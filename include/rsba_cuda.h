@@ -406,6 +406,7 @@ int rsba_cuda_comm_init(rsba_problem* h, int rank, int world_size, const unsigne
  * the pointer API rank 0 writes the caller's blocks back.  include/rsba_cuda_handler.hpp does the forwarding when
  * it is constructed with a device list. */
 typedef struct rsba_multi rsba_multi;
+int rsba_cuda_device_count(void);   /* CUDA devices visible to this process (0 without a driver / device) */
 int rsba_cuda_create_multi(rsba_multi** out, const int* devices, int n_devices);
 int rsba_cuda_multi_size(const rsba_multi* m);
 rsba_problem* rsba_cuda_multi_handle(rsba_multi* m, int rank);

@@ -132,6 +132,88 @@ class Problem {
   std::set<const double*> blocks_;      // block identity = pointer identity, as in ceres::Problem
 };
 
+// The same surface over rsba_cuda_create_multi: ONE host thread, several GPUs of the node.  Every builder call is
+// forwarded to the handle of every device (each keeps the share of the points it owns), Solve() runs the ranks'
+// LM loops on worker threads inside the library and returns rank 0's summary; results are written back into the
+// caller's blocks by rank 0.  `Handler<Session, Options, MultiGpuProblem> cs(opt, startFrame, n_gpus)` is what lets
+// the reference's single-threaded VideoSfMHandler::BA (VideoSfMHandler.cc:574-631) use the whole box.
+class MultiGpuProblem {
+ public:
+  // n_devices GPUs: devices 0 .. n_devices - 1
+  explicit MultiGpuProblem(int n_devices = 1) {
+    if (n_devices < 1) throw Error(RSBA_ERR_INVALID_ARGUMENT, "MultiGpuProblem: at least one device");
+    std::vector<int> dev(n_devices);
+    for (int k = 0; k < n_devices; ++k) dev[k] = k;
+    check(rsba_cuda_create_multi(&m_, dev.data(), n_devices));
+  }
+  ~MultiGpuProblem() { rsba_cuda_destroy_multi(m_); }
+  MultiGpuProblem(const MultiGpuProblem&) = delete;
+  MultiGpuProblem& operator=(const MultiGpuProblem&) = delete;
+
+  void SetCamera(const double cam9[9], int shutter, const int scanlines[2], bool interpolate_rotation) {
+    each([&](rsba_problem* h) { return rsba_cuda_set_camera(h, cam9, shutter, scanlines, interpolate_rotation ? 1 : 0); });
+  }
+  void SetHuberLoss(double a) { each([&](rsba_problem* h) { return rsba_cuda_set_loss(h, a); }); }
+  void AddRsResidualBlockWithIntrinsics(const double observed[2], double* cam, double* pose0, double* pose1, double* point) {
+    each([&](rsba_problem* h) { return rsba_cuda_add_rs_residual_with_intrinsics(h, observed, cam, pose0, pose1, point); });
+    ++num_residual_blocks_;
+    note(cam); note(pose0); note(pose1); note(point);
+  }
+  void AddRsResidualBlock(const double observed[2], double* pose0, double* pose1, double* point) {
+    each([&](rsba_problem* h) { return rsba_cuda_add_rs_residual(h, observed, pose0, pose1, point); });
+    ++num_residual_blocks_;
+    note(pose0); note(pose1); note(point);
+  }
+  void AddFrameBlocks(double* pose0, double* pose1) {
+    each([&](rsba_problem* h) { return rsba_cuda_add_frame_blocks(h, pose0, pose1); });
+    note(pose0); note(pose1);
+  }
+  void AddMotionPrior(int kind, double scale, double ratio, double* pose0, double* end0, double* pose1, double* end1) {
+    each([&](rsba_problem* h) { return rsba_cuda_add_motion_prior(h, kind, scale, ratio, pose0, end0, pose1, end1); });
+    note(pose0); note(end0); note(pose1); note(end1);
+  }
+  void AddPosePrior(double rotation, double position, double* prior_block, double* pose_block) {
+    each([&](rsba_problem* h) { return rsba_cuda_add_pose_prior(h, rotation, position, prior_block, pose_block); });
+    note(prior_block); note(pose_block);
+  }
+  void SetInterFrameRatioBlock(double* ratio) {
+    each([&](rsba_problem* h) { return rsba_cuda_set_inter_frame_ratio_block(h, ratio); });
+    note(ratio);
+  }
+  void SetParameterBlockConstant(double* block) { each([&](rsba_problem* h) { return rsba_cuda_set_block_constant(h, block); }); }
+  void SetSubsetConstant(double* pose_block, const std::vector<int>& constant) {
+    each([&](rsba_problem* h) { return rsba_cuda_set_subset_constant(h, pose_block, (int)constant.size(), constant.data()); });
+  }
+  long NumResidualBlocks() const { return num_residual_blocks_; }
+  long NumParameterBlocks() const { return (long)blocks_.size(); }
+  rsba_solve_summary Solve(const rsba_solve_options& options) {
+    rsba_solve_summary s;
+    const int rc = rsba_cuda_multi_solve(m_, &options, &s);
+    if (rc != RSBA_OK && rc != RSBA_ERR_EVALUATION_FAILED && rc != RSBA_ERR_LINEAR_SOLVER) check(rc);
+    return s;
+  }
+  static rsba_solve_options DefaultOptions() {
+    rsba_solve_options o;
+    rsba_cuda_default_options(&o);
+    return o;
+  }
+  int size() const { return rsba_cuda_multi_size(m_); }
+  rsba_problem* handle(int rank = 0) { return rsba_cuda_multi_handle(m_, rank); }
+
+ private:
+  static void check(int rc) {
+    if (rc != RSBA_OK) throw Error(rc, rsba_cuda_last_error());
+  }
+  template <typename Fn>
+  void each(Fn fn) {
+    for (int r = 0; r < rsba_cuda_multi_size(m_); ++r) check(fn(rsba_cuda_multi_handle(m_, r)));
+  }
+  void note(const double* block) { blocks_.insert(block); }
+  rsba_multi* m_ = nullptr;
+  long num_residual_blocks_ = 0;
+  std::set<const double*> blocks_;
+};
+
 // validate(sess, f, opt, pt, obs) of the reference (struct/VideoSfM.cc:159-169) on the host: the pose at the
 // observation's own scan line (getPose, :102-131; x or y by shutter direction), the point at least
 // minDistanceToCamera away from the camera centre, in front of the camera, and re-projected within

@@ -47,6 +47,7 @@ SYMBOLS = [
     "rsba_cuda_solve", "rsba_cuda_linearize_and_step", "rsba_cuda_plan_reduced_system", "rsba_cuda_plan_task_graph", "rsba_cuda_reduced_solve", "rsba_cuda_measure_fp64_peak", "rsba_cuda_analyze_structure", "rsba_cuda_structure_array",
     "rsba_cuda_structure_free", "rsba_cuda_sort_observations", "rsba_cuda_pnp_batch", "rsba_cuda_nccl_unique_id",
     "rsba_cuda_comm_init", "rsba_cuda_point_owners", "rsba_cuda_launch_count", "rsba_cuda_stage_ms", "rsba_cuda_version",
+    "rsba_cuda_device_count", "rsba_cuda_create_multi", "rsba_cuda_multi_size", "rsba_cuda_multi_handle", "rsba_cuda_multi_solve", "rsba_cuda_destroy_multi",
 ]
 
 
@@ -193,6 +194,14 @@ def load_library():
     lib.rsba_cuda_launch_count.restype = C.c_long
     lib.rsba_cuda_stage_ms.argtypes = [vp, C.c_int]
     lib.rsba_cuda_stage_ms.restype = C.c_double
+    lib.rsba_cuda_device_count.argtypes = []
+    lib.rsba_cuda_create_multi.argtypes = [C.POINTER(C.c_void_p), _ip, C.c_int]
+    lib.rsba_cuda_multi_size.argtypes = [vp]
+    lib.rsba_cuda_multi_handle.argtypes = [vp, C.c_int]
+    lib.rsba_cuda_multi_handle.restype = C.c_void_p
+    lib.rsba_cuda_multi_solve.argtypes = [vp, C.POINTER(SolveOptions), C.POINTER(SolveSummary)]
+    lib.rsba_cuda_destroy_multi.argtypes = [vp]
+    lib.rsba_cuda_destroy_multi.restype = None
     _lib = lib
     return lib
 
@@ -227,11 +236,15 @@ STAGES = ("jacobian", "residual", "schur", "cholesky", "update", "allreduce", "p
 class Problem:
     """One BA problem on one GPU (the analogue of ``ceres::Problem`` + ``ceres::Solve``)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self.lib = load_library()
         h = C.c_void_p()
         self._h = None
-        self._check(self.lib.rsba_cuda_create(C.byref(h), int(device)))
+        self._owned = _borrowed is None
+        if self._owned:
+            self._check(self.lib.rsba_cuda_create(C.byref(h), int(device)))
+        else:
+            h = C.c_void_p(_borrowed)     # a rank of a MultiProblem: destroyed with it
         self._h = h
         self._keep = []          # arrays whose memory the pointer API refers to
         self.num_obs = 0
@@ -246,7 +259,8 @@ class Problem:
 
     def close(self):
         if self._h is not None:
-            self.lib.rsba_cuda_destroy(self._h)
+            if self._owned:
+                self.lib.rsba_cuda_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -566,6 +580,61 @@ class Problem:
         return float(self.lib.rsba_cuda_stage_ms(self._h, idx))
 
 
+class MultiProblem:
+    """One host thread, N GPUs of one node (``rsba_cuda_create_multi``): ``ranks[r]`` are :class:`Problem` views of
+    the per-device handles -- builder calls go to every one of them (``each``) -- and ``solve`` runs the ranks' LM
+    loops on worker threads inside the library.  Results are read from ``ranks[0]``."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        m = C.c_void_p()
+        self._m = None
+        rc = self.lib.rsba_cuda_create_multi(C.byref(m), dev.ctypes.data_as(_ip), int(dev.size))
+        if rc != RSBA_OK:
+            raise RsbaError(rc, self.lib.rsba_cuda_last_error().decode(errors="replace"))
+        self._m = m
+        self.ranks = [Problem(_borrowed=self.lib.rsba_cuda_multi_handle(m, r)) for r in range(self.lib.rsba_cuda_multi_size(m))]
+
+    def each(self, fn):
+        return [fn(pb) for pb in self.ranks]
+
+    def load_scene(self, scene, poses=None, points=None):
+        self.each(lambda pb: pb.load_scene(scene, poses, points))
+
+    def solve(self, options: SolveOptions | None = None, check=True) -> SolveSummary:
+        if options is None:
+            options = default_options()
+        s = SolveSummary()
+        rc = self.lib.rsba_cuda_multi_solve(self._m, C.byref(options), C.byref(s))
+        if check and rc != RSBA_OK:
+            raise RsbaError(rc, self.lib.rsba_cuda_last_error().decode(errors="replace"))
+        s.rc = rc
+        return s
+
+    def get_parameters(self):
+        return self.ranks[0].get_parameters()
+
+    def close(self):
+        if self._m is not None:
+            for pb in self.ranks:
+                pb.close()
+            self.lib.rsba_cuda_destroy_multi(self._m)
+            self._m = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def plan_reduced_system(n_tiles, pair_a, pair_b, dense=False, reorder=True):
     """Host-only symbolic analysis of the reduced camera system (no GPU needed): ordering,
     fill, elimination levels, conflict-free update groups.  Returns a dict of numpy arrays."""
@@ -673,6 +742,8 @@ _STRUCTURE_ARRAYS = {
     "plan.panel_ptr": (np.int32, 1), "plan.trsm": (np.int32, 2), "plan.trsm_ptr": (np.int32, 1),
     "plan.upd": (np.int32, 4), "plan.lrow_ptr": (np.int32, 1), "plan.lrow_cols": (np.int32, 1),
     "local_ids": (np.int64, 1), "point_owned": (np.uint8, 1),
+    "tp_a": (np.int32, 1), "tp_b": (np.int32, 1), "tp_item_ptr": (np.int32, 1), "pair_tp": (np.int32, 1),
+    "items2": (np.int32, 4), "entries2": (np.int32, 4), "chunk_mask2": (np.uint8, 1),
 }
 
 

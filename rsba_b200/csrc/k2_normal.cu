@@ -75,8 +75,8 @@ __global__ void point_major_obs_kernel(const int* __restrict__ pt_obs, const int
   const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const long i = pt_obs[e];
-  pt_tau[e] = tau[i];
-  pt_frame[e] = frame[i];
+  if (tau) pt_tau[e] = tau[i];
+  if (pt_frame) pt_frame[e] = frame[i];
 }
 
 __global__ void point_scale_kernel(NormalEq ne, const double* __restrict__ C,
@@ -336,6 +336,10 @@ void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const Jac
   if (first_use_on_device(seen))
     cudaFuncSetAttribute(frame_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrameSmem);
   if (st.n_chunks > 0) frame_blocks_kernel<<<st.n_chunks, kFrameThreads, kFrameSmem, s>>>(st, obs, jv, res, ne);
+  if (n_frames > 0) frame_reduce_kernel<<<n_frames, 192, 0, s>>>(st, ne, n_frames);
+}
+
+void launch_frame_reduce(const SchurStructure& st, NormalEq ne, int n_frames, cudaStream_t s) {
   if (n_frames > 0) frame_reduce_kernel<<<n_frames, 192, 0, s>>>(st, ne, n_frames);
 }
 

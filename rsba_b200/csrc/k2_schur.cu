@@ -71,7 +71,7 @@ phi_build_kernel(SchurStructure st, ObsView obs, JacView jv, NormalEq ne) {
     for (int d = 0; d < cnt; ++d) {
       const long i = st.pt_obs[beg + d];
       double Jf[kJacDoubles];
-      load_full_jacobian(jv, i, Jf);
+      load_full_jacobian(jv, jv.point_major ? (long)(beg + d) : i, Jf);
       const double2* J = reinterpret_cast<const double2*>(Jf);
       const double2 x0 = J[12], x1 = J[13], x2 = J[14];   // Jx rows: (x0.x x0.y x1.x) (x1.y x2.x x2.y)
       // xm[row][k] = sum_c Jx[row][c] s_p[c] L^-1[k][c]

@@ -89,7 +89,7 @@ point_step_kernel(SchurStructure st, JacView jv,
       const long i = st.pt_obs[e];
       // compact record: Jc delta_c = jr . (wr0 d_rot0 + wr1 d_rot1) - jx . ((1-tau) d_c0 + tau d_c1), i.e. the
       // Jacobian of the INTERPOLATED pose applied to the interpolated camera step -- 96 bytes per observation
-      const double2* rp = reinterpret_cast<const double2*>(jv.rec + i * kJacCompact);
+      const double2* rp = reinterpret_cast<const double2*>(jv.rec + (jv.point_major ? (long)e : i) * kJacCompact);
       const double2 a01 = rp[0], a2b0 = rp[1], b12 = rp[2], c01 = rp[3], c2d0 = rp[4], d12 = rp[5];
       const double tau = st.pt_tau[e];
       const double2* dc = reinterpret_cast<const double2*>(delta_c + 12L * st.pt_frame[e]);

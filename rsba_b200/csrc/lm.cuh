@@ -14,6 +14,7 @@ struct JacView {
   const double* rec;     // [N][kJacCompact]  jx row 0 | jx row 1 | jr row 0 | jr row 1
   const double* tau;     // [N]
   int rot_interp;        // shutter != GLOBAL && interpolateRotation: rotation columns weigh (1-tau, tau), else (1, 0)
+  int point_major;       // records / tau are indexed by the position e in the point-major list (k2_fused.cu), not by observation
 };
 // the full 30-double record of observation i (kernels off the hot path)
 __device__ __forceinline__ void load_full_jacobian(const JacView& jv, long i, double* __restrict__ J) {
@@ -81,6 +82,17 @@ constexpr int kPanelDoubles = 3 * kPanelLd;   // one bulk copy of 1248 bytes
 constexpr int kSchurSegPoints = 512;
 constexpr int kPointRec = 12;
 
+// device view of the tile-pair regrouping of the SYRK (structure.cuh; k2_schur2.cu)
+struct Syrk2View {
+  const int4* items;              // (slot, first entry, entry count, diagonal tile pair)
+  const int4* entries;            // (row-side incidences of sub-tiles 2B, 2B+1 | column-side 2A, 2A+1); n_inc = absent
+  const unsigned char* chunk_mask;   // per 4-entry chunk: populated 2-frame halves, column side | row side << 4
+  const int* pair_tp;             // [sub-tile pairs] tile pair of the pair
+  const int* tp_item_ptr;         // [tile pairs + 1] slots of the tile pair's work items
+  double* partial;                // [n_items][4 quadrants][48 x 48]
+  int n_items;
+};
+
 struct NormalEq {
   // unscaled blocks of J^T J and J^T r
   double* B;        // [F][144] camera diagonal blocks (full 12x12, row-major)
@@ -123,9 +135,20 @@ struct LmOptionsDev {
 void launch_point_blocks(const SchurStructure& st, const JacView& jv, const double* res, NormalEq ne, cudaStream_t s);
 void launch_frame_blocks(const SchurStructure& st, const ObsView& obs, const JacView& jv, const double* res,
                          int n_frames, NormalEq ne, cudaStream_t s);
-// point-major copies of tau / frame (once per solve, after the first K1)
+// point-major copies of tau / frame (tau == NULL: frames only)
 void launch_point_major_obs(const SchurStructure& st, const ObsView& obs, const double* tau, long n, double* pt_tau,
                             int* pt_frame, cudaStream_t s);
+void launch_frame_reduce(const SchurStructure& st, NormalEq ne, int n_frames, cudaStream_t s);
+// fused linearisation passes (k2_fused.cu): calibrated scenes
+// `packed`: the observations' constants in point-major order ([N] records of point_pass_record_bytes() bytes,
+// filled once per scene by launch_pack_point_major)
+size_t point_pass_record_bytes();
+void launch_pack_point_major(const SchurStructure& st, const ObsView& obs, long n, void* packed, cudaStream_t s);
+void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, const double* poses,
+                       const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
+                       double* rec_pt, double* tau_pt, double* xt, bool write_phi /* Schur panel rows */, cudaStream_t s);
+void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,
+                       const double* xt, NormalEq ne, double* cost_partials, int* invalid_count, cudaStream_t s);
 // n_frames > 0: the camera parameters; points: the owned points (two calls: the point part runs before the
 // all-reduce, the camera part after it)
 void launch_jacobi_scale(int n_frames, bool points, NormalEq ne, bool enabled, cudaStream_t s);
@@ -158,6 +181,9 @@ void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s);
 // cam_frame: index of the intrinsics pseudo-frame (uncalibrated variant) or -1
 void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, int cam_frame, double* S,
                          const int* tile_slot, int n_tiles, cudaStream_t s);
+void launch_schur_syrk2(const SchurStructure& st, const Syrk2View& sv, NormalEq ne, cudaStream_t s);
+void launch_schur_reduce2(const SchurStructure& st, const Syrk2View& sv, NormalEq ne, const PriorView& pv, int cam_frame,
+                          double* S, const int* tile_slot, int n_tiles, cudaStream_t s);
 // after the (optional) all-reduce: Jacobi scaling, LM diagonal, constant rows, padding; d2_c and rhs
 struct TileSchedule;
 void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,

@@ -31,6 +31,13 @@ struct LmState {
   DeviceBuffer<int> owned_ids;
   DeviceBuffer<int4> items;
   DeviceBuffer<int2> entries;
+  // the SYRK by Cholesky-tile pairs (k2_schur2.cu; RSBA_CUDA_SYRK=1 selects the sub-tile-pair kernel of k2_schur.cu)
+  bool syrk2 = false;
+  DeviceBuffer<int4> items2, entries2;
+  DeviceBuffer<unsigned char> chunk_mask2;
+  DeviceBuffer<int> pair_tp, tp_item_ptr;
+  DeviceBuffer<double> partial2;
+  Syrk2View sv{};
   DeviceBuffer<int2> nz_tiles, trsm;
   DeviceBuffer<int4> upd;
   DeviceBuffer<int> tile_slot, row_ptr, rows, lrow_ptr, lrow_cols, panels;
@@ -53,7 +60,12 @@ struct LmState {
   DeviceBuffer<double> B, C, gp, Cinv, tp, Minv, Phi, partial, scale_c, scale_p, d2_c, d2_p, partials;
   DeviceBuffer<double> prec, pt_tau;      // per-point gather record; point-major tau (refreshed once per solve)
   DeviceBuffer<int> pt_frame;
+  DeviceBuffer<unsigned char> pt_packed;  // fused point pass: (x, y, frame, phi_off, obs) per observation, point-major
   bool pt_major_valid = false;
+  // calibrated scenes: the linearisation is the two fused passes of k2_fused.cu (RSBA_CUDA_FUSED=0: the
+  // K1 -> point_blocks -> frame_blocks sequence, which the uncalibrated variant always uses)
+  bool fused = false;
+  DeviceBuffer<double> rec_pt, xt;        // point-major compact records [N][12]; (X_p | t_p) [P][6]
   // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
   DeviceBuffer<double> solve_partials, fwd_partials;
   DeviceBuffer<int> fwd_slot;
@@ -124,6 +136,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   topo.g_obs_frame = h->g_obs_frame.data(); topo.g_obs_point = h->g_obs_point.data();
   topo.dense = dense; topo.reorder = h->reorder_tiles;
   topo.sparse_keys = getenv("RSBA_CUDA_SPARSE_KEYS") != nullptr;   // (env: test hook)
+  { const char* e = getenv("RSBA_CUDA_SYRK"); topo.tile_pair_lists = e && e[0] == '2'; }
   HostStructure hs;
   {
     std::string err;
@@ -145,9 +158,21 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(chunk_cnt, hs.chunk_cnt); UP(frame_chunk_ptr, hs.frame_chunk_ptr);
   UP(inc_point, hs.inc_point); UP(inc_tile, hs.inc_tile); UP(slot_beg, hs.slot_beg); UP(slot_cnt, hs.slot_cnt);
   UP(obs_phi_off, hs.obs_phi_off); UP(dup_inc, hs.dup_inc); UP(cam_inc, hs.cam_inc);
-  UP(pair_a, hs.pair_a); UP(pair_b, hs.pair_b); UP(pair_item_ptr, hs.pair_item_ptr); UP(items, hs.items);
+  UP(pair_a, hs.pair_a); UP(pair_b, hs.pair_b);
+  {
+    // measured (profiles/r02_notes.md): the tile-pair regrouping halves the panel fill but loses more to idle warps
+    // (C3 2.40 vs 2.22 ms, scattered tracks 35 vs 18 ms) -- it stays an experiment, RSBA_CUDA_SYRK=2
+    const char* e = getenv("RSBA_CUDA_SYRK");
+    lm->syrk2 = e && e[0] == '2';
+  }
+  if (lm->syrk2) {
+    UP(items2, hs.items2); UP(entries2, hs.entries2); UP(chunk_mask2, hs.chunk_mask2); UP(pair_tp, hs.pair_tp);
+    UP(tp_item_ptr, hs.tp_item_ptr);
+  } else {
+    UP(pair_item_ptr, hs.pair_item_ptr); UP(items, hs.items); UP(entries, hs.entries);
+  }
   UP(tile_pos, plan.tile_pos); UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
-  UP(entries, hs.entries); UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
+  UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
   UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
   UP(panels, plan.panels); UP(trsm, plan.trsm); UP(fwd_slot, hs.fwd_slot);
   {
@@ -209,9 +234,31 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(lm->pt_tau.resize(std::max<size_t>((size_t)h->n_obs, 1)));
   RSBA_CUDA_TRY(lm->pt_frame.resize(std::max<size_t>((size_t)h->n_obs, 1)));
   lm->st.pt_tau = lm->pt_tau.ptr; lm->st.pt_frame = lm->pt_frame.ptr;
+  {
+    const char* e = getenv("RSBA_CUDA_FUSED");
+    lm->fused = !free_cam && !(e && e[0] == '0');
+  }
+  if (lm->fused) {
+    const size_t Nz = std::max<size_t>((size_t)h->n_obs, 1);
+    RSBA_CUDA_TRY(lm->pt_packed.resize(Nz * point_pass_record_bytes()));
+    launch_pack_point_major(lm->st, h->obs_view(), h->n_obs, lm->pt_packed.ptr, s);
+    RSBA_CUDA_TRY(lm->rec_pt.resize(Nz * kJacCompact));
+    RSBA_CUDA_TRY(lm->xt.resize(Pz * 6));
+    RSBA_CUDA_TRY(cudaMemsetAsync(lm->xt.ptr, 0, lm->xt.bytes(), s));
+    // the frames in point-major order are a constant of the scene (tau follows from the first point pass)
+    launch_point_major_obs(lm->st, h->obs_view(), nullptr, h->n_obs, nullptr, lm->pt_frame.ptr, s);
+  }
   RSBA_CUDA_TRY(lm->Phi.resize((size_t)(n_inc + 1) * kPanelDoubles));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->Phi.ptr, 0, lm->Phi.bytes(), s));   // pad columns + the zero panel
-  RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kSub * kSub));
+  if (lm->syrk2) {
+    const int n2 = hs.tp_item_ptr.empty() ? 0 : hs.tp_item_ptr.back();
+    RSBA_CUDA_TRY(lm->partial2.resize((size_t)std::max(n2, 1) * 4 * kSub * kSub));
+    RSBA_CUDA_TRY(lm->partial.resize(1));
+    lm->sv = Syrk2View{lm->items2.ptr, lm->entries2.ptr, lm->chunk_mask2.ptr, lm->pair_tp.ptr, lm->tp_item_ptr.ptr,
+                       lm->partial2.ptr, n2};
+  } else {
+    RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kSub * kSub));
+  }
   RSBA_CUDA_TRY(lm->scale_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->scale_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->d2_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->d2_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 168));
@@ -301,17 +348,38 @@ __global__ void pack_cost_kernel(const double* __restrict__ cost, const int* __r
 }
 
 JacView jac_view(const rsba_problem* h) {
-  return JacView{h->d_jacc.ptr, h->d_tau.ptr, (h->cm.shutter != 0 && h->cm.interp_rot) ? 1 : 0};
+  const int rot = (h->cm.shutter != 0 && h->cm.interp_rot) ? 1 : 0;
+  if (h->lm && h->lm->fused) return JacView{h->lm->rec_pt.ptr, h->lm->pt_tau.ptr, rot, 1};
+  return JacView{h->d_jacc.ptr, h->d_tau.ptr, rot, 0};
 }
 
 // Normal equations + Schur complement for `radius` from the compact Jacobian in h->d_jacc (and, when
 // new_jacobian, the cost / invalid count of the evaluation that produced it, in h->d_scalars).
+// want_S = false: only what the convergence tests of the LAST iteration need (cost, gradient, norms) -- the Schur
+// complement of a linearisation that no step will use is not formed (2.3 of 4.7 ms at C3).
 int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, double radius, bool new_jacobian,
-              bool compute_scale) {
+              bool compute_scale, bool want_S = true) {
   cudaStream_t s = h->stream;
   const ObsView obs = h->obs_view();
   const LmOptionsDev o{radius, opt.min_lm_diagonal, opt.max_lm_diagonal};
   const JacView jv = jac_view(h);
+  if (lm->fused) {
+    // the two fused passes re-evaluate the functor at the current point (also for a new damping of the same
+    // point: rejected steps are rare, and nothing of the old Jacobian is kept in observation order)
+    cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), s);
+    stage_begin(h, kStageJacobian);
+    launch_point_pass(h->cm, lm->st, lm->pt_packed.ptr, h->d_poses.ptr, h->d_points.ptr, lm->ne, o, compute_scale, opt.jacobi_scaling != 0,
+                      lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, want_S, s);
+    stage_end(h, kStageJacobian);
+    stage_begin(h, kStageSchur);
+    stage_begin(h, kStageFrameBlocks);
+    launch_frame_pass(h->cm, lm->st, obs, h->d_poses.ptr, lm->xt.ptr, lm->ne, h->d_cost_partials.ptr, h->d_invalid.ptr, s);
+    launch_frame_reduce(lm->st, lm->ne, lm->n_cam_frames, s);
+    stage_end(h, kStageFrameBlocks);
+    int rc = eval_tail(h, true, h->d_poses.ptr, lm->st.n_chunks);   // priors' residuals + cost -> d_scalars[0]
+    if (rc) return rc;
+    h->launches += 4;
+  } else {
   stage_begin(h, kStageSchur);
   if (new_jacobian && !lm->pt_major_valid) {   // tau is a constant of the observation: once per solve
     launch_point_major_obs(lm->st, obs, h->d_tau.ptr, h->n_obs, lm->pt_tau.ptr, lm->pt_frame.ptr, s);
@@ -330,6 +398,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   launch_frame_blocks(lm->st, obs, jv, h->d_res.ptr, lm->n_cam_frames, lm->ne, s);
   stage_end(h, kStageFrameBlocks);
   h->launches += 3;
+  }
   if (lm->free_cam) {   // blocks of the intrinsics pseudo-frame and its couplings with the frames
     launch_cam_blocks(lm->st, obs, jv, h->d_jac_cam.ptr, h->d_res.ptr, lm->ne, h->n_frames,
                       lm->cam_partials.ptr, lm->cam_scratch.ptr, s);
@@ -345,6 +414,9 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     launch_pose_prior_blocks(ppv, lm->ne, o, opt.jacobi_scaling != 0, h->rank == 0, s);
     h->launches += 1;
   }
+  PriorView pvr = pv;
+  if (h->rank != 0) pvr.n = 0;
+  if (want_S) {
   launch_clear_tiles(lm->S.ptr, lm->ts, s);
   stage_begin(h, kStagePhiBuild);
   launch_phi_build(lm->st, obs, jv, lm->ne, s);
@@ -354,14 +426,16 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     h->launches += 1;
   }
   stage_begin(h, kStageSchurSyrk);
-  launch_schur_syrk(lm->st, lm->ne, s);
+  if (lm->syrk2) launch_schur_syrk2(lm->st, lm->sv, lm->ne, s);
+  else launch_schur_syrk(lm->st, lm->ne, s);
   stage_end(h, kStageSchurSyrk);
   stage_begin(h, kStageSchurReduce);
-  PriorView pvr = pv;
-  if (h->rank != 0) pvr.n = 0;
-  launch_schur_reduce(lm->st, lm->ne, pvr, lm->n_cam_frames > h->n_frames ? h->n_frames : -1, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
+  const int cam_frame_idx = lm->n_cam_frames > h->n_frames ? h->n_frames : -1;
+  if (lm->syrk2) launch_schur_reduce2(lm->st, lm->sv, lm->ne, pvr, cam_frame_idx, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
+  else launch_schur_reduce(lm->st, lm->ne, pvr, cam_frame_idx, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
   stage_end(h, kStageSchurReduce);
   h->launches += 4;
+  }
   if (new_jacobian) {   // scalars of the current point that ride in the same buffer
     pack_cost_kernel<<<1, 1, 0, s>>>(h->d_scalars.ptr, h->d_invalid.ptr, lm->misc_local.ptr);
     launch_point_norms(lm->ne, h->n_points, h->d_points.ptr, lm->misc_local.ptr + 2, lm->misc_local.ptr + 8 + h->rank,
@@ -372,13 +446,15 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
   stage_end(h, kStageSchur);
   if (h->world > 1) {   // the one exchange step: partial S | gc | wf | diag(B) | scalars
     stage_begin(h, kStageAllreduce);
-    int rc = allreduce_sum(h, lm->S.ptr, lm->comm_count);
+    // (without S: only the tail  gc | wf | diag(B) | scalars)
+    const size_t tail = 3 * (size_t)std::max(lm->n_cam_frames, 1) * 12 + lm->misc_count;
+    int rc = want_S ? allreduce_sum(h, lm->S.ptr, lm->comm_count) : allreduce_sum(h, lm->S.ptr + (lm->comm_count - tail), tail);
     stage_end(h, kStageAllreduce);
     if (rc) return rc;
   }
   stage_begin(h, kStageFinalize);
   if (compute_scale) { launch_jacobi_scale(lm->n_cam_frames, false, lm->ne, opt.jacobi_scaling != 0, s); h->launches += 1; }
-  launch_schur_finalize(lm->st, lm->ne, o, lm->S.ptr, lm->ts, lm->n_cam_frames, lm->rhs.ptr, s);
+  if (want_S) launch_schur_finalize(lm->st, lm->ne, o, lm->S.ptr, lm->ts, lm->n_cam_frames, lm->rhs.ptr, s);
   launch_camera_norms(lm->ne, lm->n_cam_frames, h->d_poses.ptr, lm->scalars.ptr, s);
   if (ppv.n > 0) { launch_pose_prior_norms(ppv, lm->scalars.ptr, s); h->launches += 1; }
   h->launches += 3;
@@ -546,12 +622,13 @@ int prepare_solve(rsba_problem* h, const rsba_solve_options* opt) {
   if (rc) return rc;
   rc = upload_pose_priors(h);
   if (rc) return rc;
-  rc = ensure_eval_buffers(h, true, true);
-  if (rc) return rc;
   h->reorder_tiles = opt->reorder_tiles != 0;
+  rc = ensure_eval_buffers(h, false);
+  if (rc) return rc;
   rc = ensure_lm(h, opt->dense_cholesky != 0);
-  if (!rc) h->lm->pt_major_valid = false;   // the camera model (hence tau) may have changed since the last solve
-  return rc;
+  if (rc) return rc;
+  h->lm->pt_major_valid = false;   // the camera model (hence tau) may have changed since the last solve
+  return ensure_eval_buffers(h, !h->lm->fused, true);
 }
 
 }  // namespace
@@ -571,7 +648,7 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   int rc = prepare_solve(h, opt);
   if (rc) { snprintf(sum->message, sizeof(sum->message), "%s", rsba_cuda_last_error()); return rc; }
   LmState* lm = h->lm;
-  h->fine_timers = getenv("RSBA_CUDA_TRACE") != nullptr;
+  h->fine_timers = getenv("RSBA_CUDA_TRACE") != nullptr || getenv("RSBA_CUDA_FINE_TIMERS") != nullptr;
   for (auto& t : h->timers) t.total_ms = 0.0;
   sum->num_residual_blocks = h->n_obs;
   sum->num_parameters_reduced = lm->num_free_params + h->free_pose_prior_params();
@@ -604,8 +681,10 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
   const int max_invalid = opt->max_num_consecutive_invalid_steps > 0 ? opt->max_num_consecutive_invalid_steps
                                                                       : RSBA_CERES_MAX_NUM_CONSECUTIVE_INVALID_STEPS;
   // ---- iteration 0: evaluate, linearise (fixes the Jacobi scaling), gradient check
-  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
-  if (rc) return rc;
+  if (!lm->fused) {
+    rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
+    if (rc) return rc;
+  }
   sum->num_jacobian_evaluations = 1;
   if ((rc = linearize(h, lm, *opt, radius, true, true))) return rc;
   if ((rc = fetch(h, lm, &hs))) return rc;
@@ -688,10 +767,12 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         radius = std::min(opt->max_trust_region_radius,
                           radius / std::max(RSBA_CERES_LM_MIN_RADIUS_SHRINK, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
         decrease = RSBA_CERES_LM_INITIAL_DECREASE_FACTOR;
-        rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
-        if (rc) return rc;
+        if (!lm->fused) {
+          rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
+          if (rc) return rc;
+        }
         sum->num_jacobian_evaluations++;
-        if ((rc = linearize(h, lm, *opt, radius, true, false))) return rc;
+        if ((rc = linearize(h, lm, *opt, radius, true, false, it < opt->max_num_iterations))) return rc;
         if ((rc = fetch(h, lm, &hs))) return rc;
         const double old = cost;
         cost = hs.cost; x_norm = hs.x_norm; gmax = hs.gmax;
@@ -740,8 +821,10 @@ int rsba_cuda_linearize_and_step(rsba_problem* h, const rsba_solve_options* opt,
   if (!(radius > 0.0)) return fail(RSBA_ERR_INVALID_ARGUMENT, "radius must be positive");
   LmState* lm = h->lm;
   h->fine_timers = true;
-  rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
-  if (rc) return rc;
+  if (!lm->fused) {
+    rc = run_evaluate(h, true, h->d_poses.ptr, h->d_points.ptr, nullptr, nullptr, true);
+    if (rc) return rc;
+  }
   if ((rc = linearize(h, lm, *opt, radius, true, true))) return rc;
   const long n = 12L * lm->n_cam_frames;   // uncalibrated variant: the intrinsics pseudo-frame comes last
   RSBA_CUDA_TRY(cudaStreamSynchronize(h->stream));

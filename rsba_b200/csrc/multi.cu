@@ -69,6 +69,12 @@ int rsba_cuda_create_multi(rsba_multi** out, const int* devices, int n_devices) 
   });
 }
 
+int rsba_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 int rsba_cuda_multi_size(const rsba_multi* m) { return m ? (int)m->ranks.size() : 0; }
 
 rsba_problem* rsba_cuda_multi_handle(rsba_multi* m, int rank) {

@@ -111,7 +111,8 @@ int ensure_eval_buffers(rsba_problem* h, bool jac, bool compact) {
   const size_t n = (size_t)h->n_obs;
   RSBA_CUDA_TRY(h->d_res.resize(2 * n));
   RSBA_CUDA_TRY(h->d_valid.resize(n));
-  RSBA_CUDA_TRY(h->d_cost_partials.resize((size_t)k1_num_partials(h->n_obs) + 2));
+  // one partial per K1 CTA, or per frame chunk of the fused frame pass (<= one extra chunk per frame), + the priors' two
+  RSBA_CUDA_TRY(h->d_cost_partials.resize((size_t)k1_num_partials(h->n_obs) + (size_t)h->n_frames + 4));
   RSBA_CUDA_TRY(h->d_scalars.resize(16));
   RSBA_CUDA_TRY(h->d_invalid.resize(4));
   if (jac && !compact) RSBA_CUDA_TRY(h->d_jac.resize((size_t)kJacDoubles * n));
@@ -120,6 +121,32 @@ int ensure_eval_buffers(rsba_problem* h, bool jac, bool compact) {
     RSBA_CUDA_TRY(h->d_tau.resize(n));
   }
   if (jac && h->free_cam) RSBA_CUDA_TRY(h->d_jac_cam.resize((size_t)18 * n));
+  return RSBA_OK;
+}
+
+// Camera-only blocks and the final sum of an evaluation whose observation kernel has left `np` cost partials in
+// d_cost_partials: the priors' cost rides in the two extra slots, then one fixed-order sum -> d_scalars[0].
+int eval_tail(rsba_problem* h, bool store, const double* poses, int np) {
+  // the priors' cost rides in the extra partial slot (rank 0 only: they are not sharded)
+  const PriorView pv = h->prior_view();
+  if (pv.n > 0 && h->rank == 0) {
+    launch_prior_eval(pv, poses, h->cm.huber, h->d_cost_partials.ptr + np, store, h->d_invalid.ptr, h->stream);
+    h->launches += 1;
+  } else {
+    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np, 0, sizeof(double), h->stream));
+  }
+  // ... and the pose priors' (GoodPosePrior) in the next one; they go with the point the poses belong to
+  const PosePriorView ppv = h->pose_prior_view();
+  if (ppv.n > 0) {
+    // every rank needs the residuals (the prior blocks are back-substituted everywhere, identically); the cost
+    // is counted once, by rank 0
+    launch_pose_prior_eval(ppv, poses, poses == h->d_poses.ptr ? ppv.val : ppv.trial, h->d_cost_partials.ptr + np + 1,
+                           store, h->d_invalid.ptr, h->stream);
+    h->launches += 1;
+  }
+  if (ppv.n == 0 || h->rank != 0)
+    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np + 1, 0, sizeof(double), h->stream));
+  launch_reduce_partials(h->d_cost_partials.ptr, np + 2, h->d_scalars.ptr, h->stream);
   return RSBA_OK;
 }
 
@@ -140,27 +167,8 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
     launch_k1r(h->cm, h->obs_view(), poses, points, h->d_cost_partials.ptr, h->d_invalid.ptr, h->stream,
                store_residuals ? h->d_res.ptr : nullptr, store_residuals ? h->d_valid.ptr : nullptr);
   }
-  // the priors' cost rides in the extra partial slot (rank 0 only: they are not sharded)
-  const int np = k1_num_partials(h->n_obs);
-  const PriorView pv = h->prior_view();
-  if (pv.n > 0 && h->rank == 0) {
-    launch_prior_eval(pv, poses, h->cm.huber, h->d_cost_partials.ptr + np, jac, h->d_invalid.ptr, h->stream);
-    h->launches += 1;
-  } else {
-    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np, 0, sizeof(double), h->stream));
-  }
-  // ... and the pose priors' (GoodPosePrior) in the next one; they go with the point the poses belong to
-  const PosePriorView ppv = h->pose_prior_view();
-  if (ppv.n > 0) {
-    // every rank needs the residuals (the prior blocks are back-substituted everywhere, identically); the cost
-    // is counted once, by rank 0
-    launch_pose_prior_eval(ppv, poses, poses == h->d_poses.ptr ? ppv.val : ppv.trial, h->d_cost_partials.ptr + np + 1,
-                           jac, h->d_invalid.ptr, h->stream);
-    h->launches += 1;
-  }
-  if (ppv.n == 0 || h->rank != 0)
-    RSBA_CUDA_TRY(cudaMemsetAsync(h->d_cost_partials.ptr + np + 1, 0, sizeof(double), h->stream));
-  launch_reduce_partials(h->d_cost_partials.ptr, np + 2, h->d_scalars.ptr, h->stream);
+  rc = eval_tail(h, jac, poses, k1_num_partials(h->n_obs));
+  if (rc) return rc;
   stage_end(h, st);
   h->launches += 2;
   RSBA_CUDA_TRY(cudaGetLastError());

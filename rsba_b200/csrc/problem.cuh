@@ -213,5 +213,8 @@ int run_evaluate(rsba_problem* h, bool jac, const double* poses, const double* p
                  double* cost_out_host, long* invalid_out_host, bool compact = false,
                  bool store_residuals = false /* without jac: also write d_res / d_valid */);
 
+// priors' cost into the slots behind `np` observation partials, then the fixed-order sum -> d_scalars[0]
+int eval_tail(rsba_problem* h, bool store, const double* poses, int np);
+
 void lm_state_free(LmState* s);
 }  // namespace rsba

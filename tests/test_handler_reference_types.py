@@ -29,7 +29,8 @@ pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "rsba", "ge
 def tool():
     src = os.path.join(ROOT, "tests", "tools", "handler_ref_check.cc")
     deps = [src] + [os.path.join(ROOT, "include", h) for h in
-                    ("rsba_cuda_handler.hpp", "rsba_cuda_functors.hpp", "rsba_reproj_math.h", "rsba_cuda.h")]
+                    ("rsba_cuda_handler.hpp", "rsba_cuda_session.hpp", "rsba_cuda_functors.hpp", "rsba_reproj_math.h",
+                     "rsba_cuda.h")]
     if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(p) for p in deps):
         subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(ROOT, "tests", "shim"), "-I", os.path.join(ROOT, "oracle", "shim"), "-I", REF,
@@ -177,3 +178,80 @@ def test_priors_and_a_frame_that_carries_priors_only(tool, tmp_path):
     assert ["frame", f"f{F - 1}p0", f"f{F - 1}p1"] in tail and not [ln for ln in tail if ln[0] == "rs"]
     # frame 0 is the fixed camera; the prior of frame 1 also fixes it through its previous-frame blocks (:182-186)
     assert [ln[1] for ln in log if ln[0] == "const"].count("f0p0") >= 1
+
+
+def test_session_soa_gathers_in_add_order_and_scatters_back(tool, tmp_path):
+    """rsba_cuda_session.hpp's SessionSoA on the reference's own gen::Session: the flat arrays hold every
+    observation with a usable track, frame by frame in insertion order (the order CeresHandler::Add feeds ceres,
+    CeresHandler.h:208), fixFirstNCameras becomes the frame mask, and scatter() writes poses / points back."""
+    sc = make_scene(6, 40, 4, name="soa")
+    out = run(tool, tmp_path, sc, "soa")
+    head = out[0]
+    order = frame_major(sc)
+    keep = [i for i in order if sc.obs_point[i] != 1]          # track 1 was made invalid
+    first = order[0]                                              # frame 0, observation 0 lost its track
+    keep = [i for i in keep if i != first]
+    assert head == ["soa", str(sc.num_frames), str(len(set(sc.obs_point[keep]))), str(len(keep))]
+    obs = [ln for ln in out if ln[0] == "obs"]
+    in_frame = np.zeros(sc.num_obs, int)
+    for f in range(sc.num_frames):
+        idx = order[sc.obs_frame[order] == f]
+        in_frame[idx] = np.arange(idx.size)
+    assert len(obs) == len(keep)
+    for ln, i in zip(obs, keep):
+        assert [int(ln[1]), int(ln[2]), int(ln[3])] == [sc.obs_frame[i], in_frame[i], sc.obs_point[i]]
+        assert float(ln[4]) == sc.obs_xy[i, 0] and float(ln[5]) == sc.obs_xy[i, 1]
+    masks = {int(ln[1]): int(ln[2]) for ln in out if ln[0] == "mask"}
+    assert masks[0] == 0xFFF and all(masks[k] == 0 for k in range(1, sc.num_frames))
+    for ln in out:
+        if ln[0] == "pose":
+            k = int(ln[1])
+            assert float(ln[2]) == sc.poses[k, 0] + 0.5 and float(ln[3]) == sc.poses[k, 11] + 0.5
+        if ln[0] == "pt":
+            q = int(ln[1])
+            moved = q in set(sc.obs_point[keep])
+            assert float(ln[2]) == sc.points[q, 2] - (0.25 if moved else 0.0)
+
+
+def test_eval_tracks_bookkeeping_follows_the_reference(tool, tmp_path):
+    """applyEvalTracks against a transcription of VideoSfMHandler::evalTracks (VideoSfMHandler.cc:381-405) on the
+    reference's gen::Session: an observation with a track whose predicate equals `drop_when` (TRUE in the reference
+    as published, :390) loses its track flag, its reference leaves the track's list, and a valid track that falls
+    below minReprojections turns invalid; both polarities are driven (even frames: the reference's, odd: the other)."""
+    sc = make_scene(6, 40, 4, name="evaltracks")
+    out = run(tool, tmp_path, sc, "evaltracks")
+    order = frame_major(sc)
+    F = sc.num_frames
+    frames = [[] for _ in range(F)]           # per frame: [track, has_track]
+    tracks = {p: {"valid": True, "obs": []} for p in range(sc.num_points)}
+    for i in order:
+        f = int(sc.obs_frame[i])
+        tracks[int(sc.obs_point[i])]["obs"].append((f, len(frames[f])))
+        frames[f].append([int(sc.obs_point[i]), True])
+    want_counts = []
+    for k in range(F):
+        n_obs = n_tr = 0
+        for oi, (tr, has) in enumerate(frames[k]):
+            if not has:
+                continue
+            ok = (k + oi) % 3 == 0
+            if ok != (k % 2 == 0):
+                continue
+            frames[k][oi][1] = False
+            n_obs += 1
+            t = tracks[tr]
+            if (k, oi) in t["obs"]:
+                t["obs"].remove((k, oi))
+                if t["valid"] and len(t["obs"]) < 4:
+                    t["valid"] = False
+                    n_tr += 1
+        want_counts.append((n_obs, n_tr))
+    got_counts = [(int(ln[2]), int(ln[3])) for ln in out if ln[0] == "frame"]
+    assert got_counts == want_counts
+    for ln in out:
+        if ln[0] == "o":
+            assert bool(int(ln[3])) == frames[int(ln[1])][int(ln[2])][1]
+        if ln[0] == "t":
+            t = tracks[int(ln[1])]
+            assert bool(int(ln[2])) == t["valid"]
+            assert [tuple(int(v) for v in r.split(":")) for r in ln[3:]] == t["obs"]

@@ -10,13 +10,19 @@
 //    gs = 4: GoodPosePrior on every frame past the first, priorPoses = the initial poses + a fixed offset --
 //            the (free, hence moved) prior blocks are appended;
 //    gs = 5: as 4, and the LAST frame loses its observations: a frame that carries pose priors only, which Ceres
-//            accepts (its poses move to where the priors pull them))
+//            accepts (its poses move to where the priors pull them);
+//    gs = 6: the sweeps of include/rsba_cuda_session.hpp -- every third observation is pushed 60 px away, then per frame
+//            validateFrame (device) is compared with the host validate() of rsba_cuda_handler.hpp, evalTracks runs with
+//            the reference's polarity, reprojectPoints is compared with the observations; prints "session ..." lines;
+//    gs = 7: bulk path -- SessionSoA gather / upload / rsba_cuda_solve / download / scatter instead of Add();
+//    gs = 8: Handler over MultiGpuProblem with every visible GPU (one host thread, N devices))
 #include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <vector>
 
 #include "rsba_cuda_handler.hpp"
+#include "rsba_cuda_session.hpp"
 
 namespace mock {
 struct IsSetObs { bool track = false; };
@@ -36,7 +42,7 @@ struct Session {
 };
 struct Options {
   struct { bool use3Dpoints = true, calibrated = true, constVelocity = false, interpolateRotation = true, rolling_shutter = true; } model;
-  struct { double sqrdThreshold = 16.0; unsigned minDistanceToCamera = 0; } tracks;
+  struct { double sqrdThreshold = 16.0; unsigned minDistanceToCamera = 0, minReprojections = 3; } tracks;
   struct {
     double huberLoss = 0, constFrameVelocity = 0, constFrameAcceleration = 0, interFrameRatio = 1;
     double trustPriorCamRotation = 0, trustPriorCamPosition = 0;
@@ -123,14 +129,77 @@ int main(int argc, char** argv) {
   double ratio_out = 1.0;
   const size_t startFrame = argc > 5 ? (size_t)atol(argv[5]) : 0;
 
+  const int mode = argc > 6 ? atoi(argv[6]) : 0;
+  if (mode == 6) {
+    try {
+      for (long k = 0; k < F; ++k)
+        for (size_t oi = 0; oi < sess.frames[k].obs.size(); ++oi)
+          if ((k + (long)oi) % 3 == 0) { sess.frames[k].obs[oi].x += 60.0; sess.frames[k].obs[oi].y -= 45.0; }
+      rsba_cuda::Problem pb(0);
+      long mismatches = 0, checked = 0, dropped = 0, bad_tracks = 0, reproj_bad = 0;
+      for (long k = 0; k < F; ++k) {
+        const std::vector<unsigned char> ok = rsba_cuda::validateFrame(pb.handle(), sess, (size_t)k, opt);
+        for (size_t oi = 0; oi < sess.frames[k].obs.size(); ++oi) {
+          const mock::Observation& o = sess.frames[k].obs[oi];
+          const double obs[2] = {o.x, o.y};
+          const bool want = rsba_cuda::validate(sess, sess.frames[k], opt, sess.getTrack(o.track).pt.data(), obs);
+          mismatches += (want != (ok[oi] != 0));
+          ++checked;
+        }
+        // re-projection of the frame's tracks: lands on the (unperturbed) observation within the noise
+        std::vector<int> trk;
+        for (const auto& o : sess.frames[k].obs) trk.push_back(o.track);
+        std::vector<double> proj;
+        std::vector<unsigned char> pok;
+        rsba_cuda::reprojectPoints(pb.handle(), sess, (size_t)k, opt, trk, &proj, &pok);
+        for (size_t oi = 0; oi < trk.size(); ++oi) {
+          if ((k + (long)oi) % 3 == 0) continue;
+          const double dx = proj[2 * oi] - sess.frames[k].obs[oi].x, dy = proj[2 * oi + 1] - sess.frames[k].obs[oi].y;
+          if (!pok[oi] || dx * dx + dy * dy > 25.0) ++reproj_bad;
+        }
+        const rsba_cuda::EvalTracksCount n = rsba_cuda::evalTracks(pb.handle(), sess, (size_t)k, opt, false);
+        dropped += n.observations;
+        bad_tracks += n.tracks;
+      }
+      long still = 0;
+      for (long k = 0; k < F; ++k)
+        for (const auto& o : sess.frames[k].obs) still += o.__isset.track;
+      printf("session checked %ld mismatches %ld dropped %ld bad_tracks %ld kept %ld reproj_bad %ld\n", checked, mismatches,
+             dropped, bad_tracks, still, reproj_bad);
+      return 0;
+    } catch (const std::exception& e) {
+      fprintf(stderr, "handler_check: %s\n", e.what());
+      return 1;
+    }
+  }
   rsba_solve_summary s;
   try {
+    if (mode == 7) {
+      rsba_cuda::SessionSoA<mock::Session> soa;
+      soa.gather(sess, 0, (size_t)F - 1, opt.ceres.useOnlyValidMatches, opt.ceres.fixFirstNCameras, startFrame);
+      rsba_cuda::Problem pb(0);
+      soa.upload(pb.handle(), sess, opt);
+      rsba_solve_options o = rsba_cuda::Problem::DefaultOptions();
+      o.max_num_iterations = atoi(argv[4]);
+      s = pb.Solve(o);
+      soa.download(pb.handle());
+      soa.scatter(sess);
+    } else if (mode == 8) {
+      const int n_gpus = rsba_cuda_device_count();
+      rsba_cuda::Handler<mock::Session, mock::Options, rsba_cuda::MultiGpuProblem> cs(opt, startFrame, n_gpus);
+      for (size_t fi = startFrame; fi < (size_t)F; ++fi) cs.Add(fi, sess);
+      rsba_solve_options o = rsba_cuda::Problem::DefaultOptions();
+      o.max_num_iterations = atoi(argv[4]);
+      s = cs.solve(&o);
+      printf("gpus %d\n", cs.problem.size());
+    } else {
     rsba_cuda::Handler<mock::Session, mock::Options> cs(opt, startFrame);
     for (size_t fi = startFrame; fi < (size_t)F; ++fi) cs.Add(fi, sess);    // VideoSfMHandler.cc:586-590
     rsba_solve_options o = rsba_cuda::Problem::DefaultOptions();
     o.max_num_iterations = atoi(argv[4]);
     s = cs.solve(&o);                                                        // VideoSfMHandler.cc:592
     ratio_out = cs.opt.ceres.interFrameRatio;
+    }
   } catch (const std::exception& e) {
     fprintf(stderr, "handler_check: %s\n", e.what());
     return 1;

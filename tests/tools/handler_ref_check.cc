@@ -19,6 +19,7 @@
 #include "rsba/gen-cpp/sfm_types.h"
 
 #include "rsba_cuda_handler.hpp"
+#include "rsba_cuda_session.hpp"
 
 namespace gen = vision::sfm::gen;
 
@@ -191,6 +192,43 @@ int main(int argc, char** argv) {
       sess.frames[k].__isset.priorPoses = true;
     }
     sess.frames[F - 1].obs.clear();                     // a frame that carries pose priors only
+  } else if (mode == "soa") {
+    // rsba_cuda_session.hpp with the reference's own types: gather all frames, print what would be uploaded,
+    // move every parameter, scatter, print the session's blocks
+    sess.tracks[1].valid = false;                       // dropped with only_valid (CeresHandler.h:217-220)
+    sess.frames[0].obs[0].__isset.track = false;        // an observation without a track
+    rsba_cuda::SessionSoA<Session> soa;
+    soa.gather(sess, 0, (size_t)F - 1, true, 1, 0);
+    printf("soa %d %d %ld\n", soa.num_frames(), soa.num_points(), soa.num_obs());
+    for (long i = 0; i < soa.num_obs(); ++i)
+      printf("obs %d %d %d %.17g %.17g\n", soa.obs_frame[i], soa.obs_key[i], soa.point_track[soa.obs_point[i]], soa.obs_xy[2 * i],
+             soa.obs_xy[2 * i + 1]);
+    for (int k = 0; k < soa.num_frames(); ++k) printf("mask %d %u\n", k, (unsigned)soa.pose_mask[k]);
+    for (double& v : soa.poses) v += 0.5;
+    for (double& v : soa.points) v -= 0.25;
+    soa.scatter(sess);
+    for (long k = 0; k < F; ++k) printf("pose %ld %.17g %.17g\n", k, sess.frames[k].poses[0][0], sess.frames[k].poses[1][5]);
+    for (long q = 0; q < P; ++q) printf("pt %ld %.17g\n", q, sess.tracks[q].pt[2]);
+    return 0;
+  } else if (mode == "evaltracks") {
+    // the bookkeeping of VideoSfMHandler::evalTracks (VideoSfMHandler.cc:381-405) on the reference's types, driven
+    // by a fixed predicate pattern; the default drops on TRUE, as the reference's line 390 reads
+    opt.tracks.minReprojections = 4;
+    for (long k = 0; k < F; ++k) {
+      std::vector<unsigned char> ok(sess.frames[k].obs.size());
+      for (size_t oi = 0; oi < ok.size(); ++oi) ok[oi] = ((k + (long)oi) % 3 == 0) ? 1 : 0;
+      const rsba_cuda::EvalTracksCount n = rsba_cuda::applyEvalTracks(sess, (size_t)k, ok, opt, (k % 2) == 0);
+      printf("frame %ld %u %u\n", k, n.observations, n.tracks);
+    }
+    for (long k = 0; k < F; ++k)
+      for (size_t oi = 0; oi < sess.frames[k].obs.size(); ++oi)
+        printf("o %ld %zu %d\n", k, oi, (int)sess.frames[k].obs[oi].__isset.track);
+    for (long q = 0; q < P; ++q) {
+      printf("t %ld %d", q, (int)sess.tracks[q].valid);
+      for (const auto& r : sess.tracks[q].obs) printf(" %d:%d", r.frame, r.obs);
+      printf("\n");
+    }
+    return 0;
   } else if (mode != "plain") {
     return 2;
   }
