@@ -26,17 +26,17 @@
 // is bound by the FP64 pipe (tcgen05 has no FP64 kind: DMMA == DFMA rate, 37.1 TFLOP/s measured).
 #include "lm.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace rsba {
 namespace {
 
-constexpr int kChunkPts = 8;                       // points per pipeline stage (24 K columns)
-constexpr int kStages = 3;
-constexpr int kOperandDoubles = kChunkPts * kPanelDoubles;       // 1248 doubles
-constexpr int kStageDoubles = 2 * kOperandDoubles;               // row side | column side
 constexpr unsigned kPanelBytes = kPanelDoubles * sizeof(double);
-constexpr size_t kSyrkSmem = (size_t)kStages * kStageDoubles * sizeof(double) + 64;
+// pipeline shape: points per stage (CHUNK: 8 = 24 K columns), stages, CTAs per SM -- the shipped variant and the
+// ones measured beside it (profiles/r02_notes.md) are instantiated at the bottom
+template <int CHUNK, int STAGES>
+constexpr size_t syrk_smem() { return (size_t)STAGES * 2 * CHUNK * kPanelDoubles * sizeof(double) + 64; }
 
 // ---------------------------------------------------------------- panels
 // The panel rows of an observation are normally written by frame_blocks_kernel (k2_normal.cu), which
@@ -139,9 +139,12 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 // ---------------------------------------------------------------- sub-tile-pair SYRK
 // One CTA (4 warps) per work item.  60 KB of shared memory per CTA: three CTAs per SM keep 12 warps on
 // the FP64 pipe.
-__global__ void __launch_bounds__(128, 3)
+template <int kChunkPts, int kStages, int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS)
 schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entries,
                   const int4* __restrict__ items, double* __restrict__ partial) {
+  constexpr int kOperandDoubles = kChunkPts * kPanelDoubles;       // one side of a stage
+  constexpr int kStageDoubles = 2 * kOperandDoubles;               // row side | column side
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kStages * kStageDoubles * sizeof(double));
@@ -168,7 +171,7 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
   // wait on a global load.
   int2 e_next = make_int2(0, 0);
   auto load_entry = [&](int c) {
-    if (lane < (diag ? 8 : 16) && c < nchunks) e_next = entries[beg + c * kChunkPts + (lane & 7)];
+    if (lane < (diag ? kChunkPts : 2 * kChunkPts) && c < nchunks) e_next = entries[beg + c * kChunkPts + (lane % kChunkPts)];
   };
   auto issue = [&](int c) {
     const int s = c % kStages;
@@ -177,8 +180,8 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
     __syncwarp();
     const int2 e = e_next;
     load_entry(c + 1);
-    if (lane < (diag ? 8 : 16)) {
-      const int q = lane & 7, side = lane >> 3;
+    if (lane < (diag ? kChunkPts : 2 * kChunkPts)) {
+      const int q = lane % kChunkPts, side = lane / kChunkPts;
       const int inc = side ? e.y : e.x;
       double* dst = stage_base + (size_t)s * kStageDoubles + side * kOperandDoubles + q * kPanelDoubles;
       tma_load_1d(smem_u32(dst), Phi + (long)inc * kPanelDoubles, kPanelBytes, bar);
@@ -212,7 +215,10 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
   constexpr unsigned kRows34 = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4);       // window (3, 0)
   constexpr unsigned kRows45 = (1u << 5) | (1u << 6) | (1u << 7) | (1u << 8);                   // window (3, 0)
   double* out = partial + (long)blockIdx.x * kSub * kSub;
-  auto run = [&](auto mask_tag, int r0, int c0) {
+  // ksplit: the warp only multiplies the chunks with (c & 1) == kphase -- the K-split of an item with two live
+  // patches, whose other two warps would otherwise idle (13.7 % of the DMMAs but 23.5 % of the CTA time at C3); the
+  // two halves of a patch are added in a fixed order through shared memory behind the loop.
+  auto run = [&](auto mask_tag, int r0, int c0, bool ksplit, int kphase, int zr0, int zc0) {
     constexpr unsigned MASK = decltype(mask_tag)::value;
     const int m0 = 8 * r0, n0 = 8 * c0;
     const int fr = lane >> 2, fc = lane & 3;
@@ -227,6 +233,7 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
       mbar_wait(smem_u32(&bars[s]), (unsigned)((c / kStages) & 1));
       const double* R = stage_base + (size_t)s * kStageDoubles;
       const double* Cc = diag ? R : R + kOperandDoubles;
+      if (!ksplit || (c & 1) == kphase)
 #pragma unroll
       for (int ks = 0; ks < (3 * kChunkPts) / 4; ++ks) {
         const int krow = (4 * ks + fc) * kPanelLd + fr;
@@ -244,6 +251,33 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
             if ((MASK >> (3 * mi + ni)) & 1u) dmma8x8x4(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
       }
       release(s);
+    }
+    if (ksplit) {   // CTA-uniform: every warp of a two-patch item comes through here
+      __syncthreads();                       // all stages consumed: the ring is free
+      double2* buf = reinterpret_cast<double2*>(stage_base) + ((r0 + c0) & 1 ? 288 : 0);   // one slab per live patch
+      if (kphase == 1) {
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 3; ++ni) buf[(3 * mi + ni) * 32 + lane] = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+      }
+      __syncthreads();
+      if (kphase == 1) {                     // this warp's own patch of the 48 x 48 block is structurally zero
+#pragma unroll
+        for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 3; ++ni)
+            *reinterpret_cast<double2*>(out + (8 * zr0 + 8 * mi + fr) * kSub + 8 * zc0 + 8 * ni + 2 * fc) = make_double2(0.0, 0.0);
+        return;
+      }
+#pragma unroll
+      for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 3; ++ni) {
+          const double2 o = buf[(3 * mi + ni) * 32 + lane];
+          acc[mi][ni][0] += o.x;
+          acc[mi][ni][1] += o.y;
+        }
     }
 #pragma unroll
     for (int mi = 0; mi < 3; ++mi)
@@ -271,13 +305,24 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
         *reinterpret_cast<double2*>(out + (8 * r0 + 8 * mi + fr) * kSub + 8 * c0 + 8 * ni + 2 * fc) = make_double2(0.0, 0.0);
   };
   if (!diag) {
-    const bool live = ((half_b >> (warp >> 1)) & 1u) && ((half_a >> (warp & 1)) & 1u);
-    if (live) run(std::integral_constant<unsigned, kAll>{}, 3 * (warp >> 1), 3 * (warp & 1));
-    else idle(3 * (warp >> 1), 3 * (warp & 1));
+    const bool one_b = half_b == 1u || half_b == 2u, one_a = half_a == 1u || half_a == 2u;
+    if (one_b != one_a) {
+      // two live patches (one side has a single populated half): warp = (patch, K half).  The patch a warp owns
+      // in the plain layout but not here -- (zr, zc) -- is structurally zero and written as such.
+      int pr, pc, kphase, zr, zc;
+      if (one_b) { pr = half_b == 2u; pc = warp & 1; kphase = warp >> 1; zr = 1 - pr; zc = pc; }
+      else       { pc = half_a == 2u; pr = warp >> 1; kphase = warp & 1; zr = pr; zc = 1 - pc; }
+      if (kphase == 0) { zr = pr; zc = pc; }   // (unused: the first half writes the sum into the live patch)
+      run(std::integral_constant<unsigned, kAll>{}, 3 * pr, 3 * pc, true, kphase, 3 * zr, 3 * zc);
+    } else {
+      const bool live = ((half_b >> (warp >> 1)) & 1u) && ((half_a >> (warp & 1)) & 1u);
+      if (live) run(std::integral_constant<unsigned, kAll>{}, 3 * (warp >> 1), 3 * (warp & 1), false, 0, 0, 0);
+      else idle(3 * (warp >> 1), 3 * (warp & 1));
+    }
   }
-  else if (warp < 2) run(std::integral_constant<unsigned, kLower>{}, 3 * warp, 3 * warp);
-  else if (warp == 2) run(std::integral_constant<unsigned, kRows34>{}, 3, 0);
-  else run(std::integral_constant<unsigned, kRows45>{}, 3, 0);
+  else if (warp < 2) run(std::integral_constant<unsigned, kLower>{}, 3 * warp, 3 * warp, false, 0, 0, 0);
+  else if (warp == 2) run(std::integral_constant<unsigned, kRows34>{}, 3, 0, false, 0, 0, 0);
+  else run(std::integral_constant<unsigned, kRows45>{}, 3, 0, false, 0, 0, 0);
 }
 
 // ---------------------------------------------------------------- reduce
@@ -380,12 +425,29 @@ void launch_phi_build(const SchurStructure& st, const ObsView& obs, const JacVie
   phi_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, obs, jv, ne);
 }
 
-void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
+template <int CHUNK, int STAGES, int MIN_CTAS>
+static void launch_syrk_variant(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
   static bool seen[64] = {};
+  constexpr size_t smem = syrk_smem<CHUNK, STAGES>();
   if (first_use_on_device(seen))
-    cudaFuncSetAttribute(schur_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem);
+    cudaFuncSetAttribute(schur_syrk_kernel<CHUNK, STAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  schur_syrk_kernel<CHUNK, STAGES, MIN_CTAS><<<st.n_items, 128, smem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
+}
+
+void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
   if (st.n_items <= 0) return;
-  schur_syrk_kernel<<<st.n_items, 128, kSyrkSmem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
+  static const int var = [] { const char* e = getenv("RSBA_CUDA_SYRK_VAR"); return e ? atoi(e) : 0; }();   // (experiment hook)
+  // measured at C3 (profiles/r02_notes.md): <8,3,3> 2.16 ms (round 1's shape), <8,2,5> 1.85, <4,3,5> 1.99, <4,4,5> 1.97:
+  // warps per SM sub-partition, not ring depth, is what keeps the FP64 pipe fed
+  switch (var) {
+    case 1: launch_syrk_variant<8, 3, 3>(st, ne, s); break;
+    case 2: launch_syrk_variant<4, 3, 5>(st, ne, s); break;
+    case 3: launch_syrk_variant<4, 4, 5>(st, ne, s); break;
+    case 5: launch_syrk_variant<4, 2, 6>(st, ne, s); break;
+    case 6: launch_syrk_variant<4, 2, 7>(st, ne, s); break;
+    case 7: launch_syrk_variant<4, 3, 6>(st, ne, s); break;
+    default: launch_syrk_variant<8, 2, 5>(st, ne, s); break;
+  }
 }
 
 void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, int cam_frame, double* S,

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from rsba_b200.scene import make_scene
+from rsba_b200.scene import Scene, make_scene
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "tools", "handler_check")
@@ -221,3 +221,68 @@ def test_handler_frame_with_pose_priors_only(tmp_path):
     assert np.abs(poses[-1] - blocks[-1]).max() <= 1e-6
     assert np.abs(poses[-1] - sc.poses[-1].reshape(2, 6)).max() > 1e-5      # ... by moving both ends
     assert not poses[0].any()
+
+
+@pytest.mark.gpu
+def test_session_sweeps_on_the_device_match_the_host_predicate(tmp_path):
+    """include/rsba_cuda_session.hpp: validateFrame (one rsba_cuda_validate sweep per frame) against the host
+    validate() of rsba_cuda_handler.hpp on every observation -- a third of them pushed 60 px off --, evalTracks'
+    bookkeeping on top of it, and reprojectPoints landing on the untouched observations."""
+    sc = make_scene(10, 300, 8, name="session")
+    # at the TRUE parameters only the 0.5 px observation noise separates projection and observation
+    sc = Scene(**{**sc.__dict__, "poses": sc.poses_true, "points": sc.points_true})
+    src, dst = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    write_scene(src, sc)
+    r = subprocess.run([BIN, src, dst, "1", "1", "0", "6"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("session")][0].split()
+    got = {line[i]: int(line[i + 1]) for i in range(1, len(line), 2)}
+    assert got["checked"] == sc.num_obs and got["mismatches"] == 0
+    # the pushed observations fail the predicate and (polarity: drop what FAILS) lose their track
+    order = np.argsort(sc.obs_frame, kind="stable")
+    pushed = 0
+    for f in range(sc.num_frames):
+        n = int((sc.obs_frame == f).sum())
+        pushed += sum(1 for oi in range(n) if (f + oi) % 3 == 0)
+    assert got["dropped"] >= pushed and got["kept"] == sc.num_obs - got["dropped"]
+    assert got["dropped"] <= pushed + sc.num_obs // 50          # + a few noisy ones beyond 4 px
+    assert got["reproj_bad"] <= sc.num_obs // 50
+    assert order.size == sc.num_obs
+
+
+@pytest.mark.gpu
+def test_session_soa_bulk_path_equals_the_pointer_path(tmp_path):
+    """SessionSoA gather -> upload -> rsba_cuda_solve -> download -> scatter gives what Handler::Add + solve gives."""
+    sc = make_scene(12, 400, 8, name="soa-gpu")
+    src = str(tmp_path / "scene.bin")
+    write_scene(src, sc)
+    outs = []
+    for mode in ("0", "7"):
+        dst = str(tmp_path / f"out{mode}.bin")
+        r = subprocess.run([BIN, src, dst, "1", "6", "0", mode], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(np.fromfile(dst))
+    a, b = outs
+    assert a[0] == 1 and b[0] == 1 and a[1] == b[1]
+    assert abs(a[3] - b[3]) <= 1e-9 * a[3]
+    assert np.linalg.norm(a[4:] - b[4:]) <= 1e-7 * np.linalg.norm(a[4:])
+
+
+@pytest.mark.gpu
+def test_handler_over_every_gpu_of_the_box_from_one_thread(tmp_path):
+    """Handler<..., MultiGpuProblem> (rsba_cuda_create_multi underneath) with all visible devices -- one on the
+    single-GPU test box, where it must equal the plain handler bit for bit; N > 1 elsewhere, to 1e-9."""
+    sc = make_scene(16, 600, 8, name="multi-handler")
+    src = str(tmp_path / "scene.bin")
+    write_scene(src, sc)
+    outs = []
+    for mode in ("0", "8"):
+        dst = str(tmp_path / f"out{mode}.bin")
+        r = subprocess.run([BIN, src, dst, "1", "6", "0", mode], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs.append(np.fromfile(dst))
+        if mode == "8":
+            assert any(ln.startswith("gpus ") for ln in r.stdout.splitlines())
+    a, b = outs
+    assert a[1] == b[1] and abs(a[3] - b[3]) <= 1e-9 * a[3]
+    assert np.linalg.norm(a[4:] - b[4:]) <= 1e-9 * np.linalg.norm(a[4:])
