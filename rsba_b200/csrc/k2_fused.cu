@@ -68,7 +68,7 @@ constexpr int kPointPassWarps = 4;
 // index -> observation gather on the critical path of a warp (it was 13 k of the 17.7 k cycles a point took).
 struct __align__(16) PtObsRec {
   double x, y;
-  int frame, phi_off, obs, pad;
+  int frame, phi_off, obs, point;
 };
 static_assert(sizeof(PtObsRec) == 32, "one sector");
 
@@ -79,16 +79,60 @@ __global__ void pack_point_major_kernel(const int* __restrict__ pt_obs, ObsView 
   const int i = pt_obs[e];
   const double2 xy = obs.xy[i];
   PtObsRec r;
-  r.x = xy.x; r.y = xy.y; r.frame = obs.frame[i]; r.phi_off = obs_phi_off[i]; r.obs = i; r.pad = 0;
+  r.x = xy.x; r.y = xy.y; r.frame = obs.frame[i]; r.phi_off = obs_phi_off[i]; r.obs = i; r.point = obs.point[i];
   out[e] = r;
 }
 
-template <int MIN_CTAS>
+// point_eval (one thread per observation, point-major order): the functor + Jacobian of every observation, written as
+// point-major compact records + residuals + tau.  With it the point pass below runs in its PRE form -- it reads
+// the records back (coalesced) instead of evaluating, needs half the registers and keeps 1.5 x the warps in flight;
+// the warp-per-point pass with the evaluation inside was latency-bound at 16 warps per SM (0.68 ms at C3).
+constexpr int kEvalThreads = 128;
+
+__global__ void __launch_bounds__(kEvalThreads)
+point_eval_kernel(const CameraModel cm, const PtObsRec* __restrict__ prec_pm, long n, const double* __restrict__ poses,
+                  const double* __restrict__ points, double* __restrict__ rec_pt, double* __restrict__ res_pt,
+                  double* __restrict__ tau_pt) {
+  extern __shared__ __align__(128) double s_rec[];   // [warps][32][kJacCompact]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long e = (long)blockIdx.x * kEvalThreads + threadIdx.x;
+  double* row = s_rec + (warp * 32 + lane) * kJacCompact;
+  if (e < n) {
+    const PtObsRec pr = prec_pm[e];
+    const double* pp = points + 3L * pr.point;
+    const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
+    double pose[kFrameParams];
+    load_pose(poses, pr.frame, pose);
+    ObsEval ev;
+    eval_observation(cm, pr.x, pr.y, pose, X0, X1, X2, ev);
+#pragma unroll
+    for (int k = 0; k < kJacCompact; ++k) row[k] = ev.rec[k];
+    reinterpret_cast<double2*>(res_pt)[e] = make_double2(ev.r0, ev.r1);
+    tau_pt[e] = ev.tau;
+  }
+  // the warp's 32 x 12 records leave as one bulk store (as K1's Jacobian tile does)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const long wbase = (long)blockIdx.x * kEvalThreads + warp * 32;
+  if (lane == 0 && wbase < n) {
+    const int wcnt = (int)min(32L, n - wbase);
+    const unsigned bytes = (unsigned)(wcnt * kJacCompact * sizeof(double));
+    const unsigned src = (unsigned)__cvta_generic_to_shared(s_rec + warp * 32 * kJacCompact);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec_pt + wbase * kJacCompact), "r"(src),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+// PRE: the observations were evaluated by point_eval_kernel (rec_pt / res_pt / tau_pt hold them); else evaluate here.
+template <int MIN_CTAS, bool PRE>
 __global__ void __launch_bounds__(kPointPassWarps * 32, MIN_CTAS)
 point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __restrict__ prec_pm, const double* __restrict__ poses,
                   const double* __restrict__ points, NormalEq ne, LmOptionsDev o, int compute_scale, int jacobi,
                   int rot_interp, int write_phi, double* __restrict__ rec_pt, double* __restrict__ tau_pt,
-                  double* __restrict__ xt) {
+                  double* __restrict__ xt, const double* __restrict__ res_pt) {
   const int lane = threadIdx.x & 31;
   const int kk = blockIdx.x * kPointPassWarps + (threadIdx.x >> 5);
   if (kk >= ne.n_owned) return;
@@ -106,6 +150,18 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
     if (e < end) {
+      if (PRE) {
+        const int2 fo = reinterpret_cast<const int2*>(prec_pm + e)[2];     // (frame, phi_off)
+        frame = fo.x;
+        off = fo.y;
+        const double2* rp = reinterpret_cast<const double2*>(rec_pt + (long)e * kJacCompact);
+#pragma unroll
+        for (int k = 0; k < kJacCompact / 2; ++k) { const double2 q = rp[k]; ev.rec[2 * k] = q.x; ev.rec[2 * k + 1] = q.y; }
+        const double2 rr = reinterpret_cast<const double2*>(res_pt)[e];
+        ev.r0 = rr.x; ev.r1 = rr.y;
+        ev.tau = tau_pt[e];
+        mask = ne.pose_mask[frame];
+      } else {
       const PtObsRec pr = prec_pm[e];
       frame = pr.frame;
       off = pr.phi_off;
@@ -113,6 +169,7 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
       load_pose(poses, frame, pose);
       mask = ne.pose_mask[frame];
       eval_observation(cm, pr.x, pr.y, pose, X0, X1, X2, ev);
+      }
       const double a0 = ev.rec[0], a1 = ev.rec[1], a2 = ev.rec[2], b0 = ev.rec[3], b1 = ev.rec[4], b2 = ev.rec[5];
       v[0] += a0 * a0 + b0 * b0;
       v[1] += a0 * a1 + b0 * b1;
@@ -198,7 +255,17 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
     const bool mine = e < end;
-    if (mine && !reuse) {   // a track longer than a warp: evaluate again
+    if (mine && !reuse) {   // a track longer than a warp: fetch / evaluate again
+      if (PRE) {
+        const int2 fo = reinterpret_cast<const int2*>(prec_pm + e)[2];
+        frame = fo.x;
+        off = fo.y;
+        const double2* rq = reinterpret_cast<const double2*>(rec_pt + (long)e * kJacCompact);
+#pragma unroll
+        for (int k = 0; k < kJacCompact / 2; ++k) { const double2 q = rq[k]; ev.rec[2 * k] = q.x; ev.rec[2 * k + 1] = q.y; }
+        ev.tau = tau_pt[e];
+        mask = ne.pose_mask[frame];
+      } else {
       const PtObsRec pr = prec_pm[e];
       frame = pr.frame;
       off = pr.phi_off;
@@ -206,12 +273,15 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
       load_pose(poses, frame, pose);
       mask = ne.pose_mask[frame];
       eval_observation(cm, pr.x, pr.y, pose, X0, X1, X2, ev);
+      }
     }
     if (!mine) continue;
-    double2* rp = reinterpret_cast<double2*>(rec_pt + (long)e * kJacCompact);
+    if (!PRE) {
+      double2* rp = reinterpret_cast<double2*>(rec_pt + (long)e * kJacCompact);
 #pragma unroll
-    for (int k = 0; k < kJacCompact / 2; ++k) rp[k] = make_double2(ev.rec[2 * k], ev.rec[2 * k + 1]);
-    tau_pt[e] = ev.tau;
+      for (int k = 0; k < kJacCompact / 2; ++k) rp[k] = make_double2(ev.rec[2 * k], ev.rec[2 * k + 1]);
+      tau_pt[e] = ev.tau;
+    }
     if (off < 0 || !write_phi) continue;
     const double* jx0 = ev.rec, *jx1 = ev.rec + 3, *jr0 = ev.rec + 6, *jr1 = ev.rec + 9;
     const double xa[3] = {jx0[0] * W[0], jx0[0] * W[1] + jx0[1] * W[2], jx0[0] * W[3] + jx0[1] * W[4] + jx0[2] * W[5]};
@@ -358,19 +428,35 @@ void launch_pack_point_major(const SchurStructure& st, const ObsView& obs, long 
                                                                         static_cast<PtObsRec*>(packed));
 }
 
-void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, const double* poses,
+void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, long n_obs, const double* poses,
                        const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
-                       double* rec_pt, double* tau_pt, double* xt, bool write_phi, cudaStream_t s) {
+                       double* rec_pt, double* tau_pt, double* xt, double* res_pt, bool write_phi, cudaStream_t s) {
   if (ne.n_owned <= 0) return;
   const int rot_interp = (cm.shutter != 0 && cm.interp_rot) ? 1 : 0;
-  static const int occ = [] { const char* e = getenv("RSBA_CUDA_KP_OCC"); return e ? atoi(e) : 4; }();   // (experiment hook)
+  // Default: the evaluation inside the warp-per-point pass (one launch, 0.68 ms at C3).  RSBA_CUDA_KP=split runs
+  // point_eval_kernel (0.15 ms) + the PRE form of the pass (0.52-0.56 ms): measured equal (profiles/r02_notes.md) --
+  // the pass is bound by the latency of its per-point chain either way -- and kept as an experiment hook.
+  static const bool fused_eval = [] { const char* e = getenv("RSBA_CUDA_KP"); return !(e && e[0] == 's'); }();
   const int grid = (ne.n_owned + kPointPassWarps - 1) / kPointPassWarps;
-  if (occ <= 4)
-    point_pass_kernel<4><<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, static_cast<const PtObsRec*>(packed), poses, points, ne, o,
-                                                               compute_scale ? 1 : 0, jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt, tau_pt, xt);
+  const PtObsRec* pk = static_cast<const PtObsRec*>(packed);
+  if (fused_eval) {
+    point_pass_kernel<4, false><<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, pk, poses, points, ne, o, compute_scale ? 1 : 0,
+                                                                      jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt,
+                                                                      tau_pt, xt, res_pt);
+    return;
+  }
+  if (n_obs > 0)
+    point_eval_kernel<<<(unsigned)((n_obs + kEvalThreads - 1) / kEvalThreads), kEvalThreads,
+                        (size_t)kEvalThreads * kJacCompact * sizeof(double), s>>>(cm, pk, n_obs, poses, points, rec_pt, res_pt, tau_pt);
+  static const int occ = [] { const char* e = getenv("RSBA_CUDA_KP_OCC"); return e ? atoi(e) : 5; }();   // (experiment hook)
+  if (occ <= 5)
+    point_pass_kernel<5, true><<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, pk, poses, points, ne, o, compute_scale ? 1 : 0,
+                                                                     jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt, tau_pt,
+                                                                     xt, res_pt);
   else
-    point_pass_kernel<5><<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, static_cast<const PtObsRec*>(packed), poses, points, ne, o,
-                                                               compute_scale ? 1 : 0, jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt, tau_pt, xt);
+    point_pass_kernel<6, true><<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, pk, poses, points, ne, o, compute_scale ? 1 : 0,
+                                                                     jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt, tau_pt,
+                                                                     xt, res_pt);
 }
 
 void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,

@@ -144,9 +144,11 @@ void launch_frame_reduce(const SchurStructure& st, NormalEq ne, int n_frames, cu
 // filled once per scene by launch_pack_point_major)
 size_t point_pass_record_bytes();
 void launch_pack_point_major(const SchurStructure& st, const ObsView& obs, long n, void* packed, cudaStream_t s);
-void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, const double* poses,
+// (res_pt: [N][2] scratch for the residuals in point-major order)
+void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, long n_obs, const double* poses,
                        const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
-                       double* rec_pt, double* tau_pt, double* xt, bool write_phi /* Schur panel rows */, cudaStream_t s);
+                       double* rec_pt, double* tau_pt, double* xt, double* res_pt, bool write_phi /* Schur panel rows */,
+                       cudaStream_t s);
 void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,
                        const double* xt, NormalEq ne, double* cost_partials, int* invalid_count, cudaStream_t s);
 // n_frames > 0: the camera parameters; points: the owned points (two calls: the point part runs before the

@@ -368,8 +368,8 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     // point: rejected steps are rare, and nothing of the old Jacobian is kept in observation order)
     cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), s);
     stage_begin(h, kStageJacobian);
-    launch_point_pass(h->cm, lm->st, lm->pt_packed.ptr, h->d_poses.ptr, h->d_points.ptr, lm->ne, o, compute_scale, opt.jacobi_scaling != 0,
-                      lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, want_S, s);
+    launch_point_pass(h->cm, lm->st, lm->pt_packed.ptr, h->n_obs, h->d_poses.ptr, h->d_points.ptr, lm->ne, o, compute_scale,
+                      opt.jacobi_scaling != 0, lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, h->d_res.ptr, want_S, s);
     stage_end(h, kStageJacobian);
     stage_begin(h, kStageSchur);
     stage_begin(h, kStageFrameBlocks);
@@ -378,7 +378,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     stage_end(h, kStageFrameBlocks);
     int rc = eval_tail(h, true, h->d_poses.ptr, lm->st.n_chunks);   // priors' residuals + cost -> d_scalars[0]
     if (rc) return rc;
-    h->launches += 4;
+    h->launches += 5;
   } else {
   stage_begin(h, kStageSchur);
   if (new_jacobian && !lm->pt_major_valid) {   // tau is a constant of the observation: once per solve
