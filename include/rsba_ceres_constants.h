@@ -36,6 +36,10 @@
  * a step is valid iff model_cost_change > 0; a linear-solver failure or an invalid step counts towards
  * max_num_consecutive_invalid_steps and shrinks the radius like a rejected step. */
 
+/* ceres/solver.h, line search defaults (used by the trust-region minimizer on bound-constrained problems):
+ * ARMIJO, sufficient_function_decrease 1e-4, the search starts at step size 1 */
+#define RSBA_CERES_ARMIJO_SUFFICIENT_DECREASE 1e-4
+
 /* ceres/loss_function.h, HuberLoss(a): rho(s) = s for s <= a^2, else 2 a sqrt(s) - a^2 */
 
 #endif  /* RSBA_CERES_CONSTANTS_H_ */

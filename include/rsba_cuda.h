@@ -97,6 +97,11 @@ typedef struct rsba_solve_summary {
                                   symbolic analysis of this scene executes: potrf n^3/3, trsm n^3, update 2 n^3 per tile) */
   int reduced_levels;          /* elimination levels (length of the dependent panel chain) */
   int reduced_tiles;           /* non-zero 96 x 96 tiles of the factor after fill */
+  /* Bounded problems (the free interFrameRatio, SetParameterLowerBound at CeresHandler.h:161,172): Ceres 1.9 follows
+   * the projected trust-region step with an Armijo line search that starts at step size 1 and only contracts when
+   * f(x + d) > f(x) + 1e-4 g.d.  The loop here takes the projected step as it is and counts the steps on which that
+   * search would NOT have accepted step size 1: 0 means the missing line search was a no-op for this solve. */
+  int num_armijo_violations;
 } rsba_solve_summary;
 
 /* ------------------------------------------------------------------ lifecycle */

@@ -98,6 +98,7 @@ class SolveSummary(C.Structure):
         ("tile_flops", C.c_double),
         ("reduced_levels", C.c_int),
         ("reduced_tiles", C.c_int),
+        ("num_armijo_violations", C.c_int),
     ]
 
     def as_dict(self):

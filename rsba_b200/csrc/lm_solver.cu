@@ -757,6 +757,9 @@ int rsba_cuda_solve(rsba_problem* h, const rsba_solve_options* opt, rsba_solve_s
         }
         rho = (cost - new_cost) / mcc;
         accepted = rho > opt->min_relative_decrease;
+        // what Ceres' bounded-problem line search tests at step size 1 (rsba_solve_summary::num_armijo_violations)
+        if (lm->free_ratio && !(new_cost <= cost + RSBA_CERES_ARMIJO_SUFFICIENT_DECREASE * hs.g_dot_delta))
+          sum->num_armijo_violations++;
       }
       if (accepted) {
         sum->num_successful_steps++;

@@ -66,6 +66,27 @@ const NcclApi* nccl_api() {
   return state == 1 ? &api : nullptr;
 }
 
+bool device_pool_enabled() {
+  static const bool on = getenv("RSBA_CUDA_NO_POOL") == nullptr;
+  if (!on) return false;
+  static bool prepared[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (!prepared[dev & 63]) {
+    int supported = 0;
+    cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
+    cudaMemPool_t pool;
+    if (!supported || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    unsigned long long keep = ~0ull;    // never trim: freed blocks serve the next handle
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    prepared[dev & 63] = true;
+  }
+  return true;
+}
+
 int allreduce_sum(rsba_problem* h, double* buf, size_t count) {
   if (h->world <= 1 || count == 0) return RSBA_OK;
   const NcclApi* api = nccl_api();

@@ -22,17 +22,33 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (e__ != cudaSuccess) return ::rsba::cuda_fail(e__, #expr, __FILE__, __LINE__); \
   } while (0)
 
+// Device memory comes from the device's default stream-ordered pool with the release threshold lifted: the
+// reference builds a new CeresHandler for every BA call (VideoSfMHandler.cc:585), i.e. a fresh problem handle per
+// call in one long-lived process, and cudaMalloc / cudaFree of the handle's ~3 GB were 40-380 ms of a 240 ms cold
+// call at C3 (profiles/r02_notes.md).  The pool keeps what a handle frees for the next one.  Allocation and release
+// are ordered on the legacy default stream behind a device-wide synchronise, which is what cudaFree implied.
+// RSBA_CUDA_NO_POOL=1 goes back to cudaMalloc / cudaFree.
+bool device_pool_enabled();   // problem.cu: also lifts the release threshold of the current device's pool, once
+
 // Simple owning device buffer.
 template <typename T>
 struct DeviceBuffer {
   T* ptr = nullptr;
   size_t count = 0;
+  bool pooled = false;
   ~DeviceBuffer() { release(); }
   DeviceBuffer() = default;
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) {
+      if (pooled) {
+        cudaDeviceSynchronize();          // nothing in flight on any stream may still use the buffer
+        cudaFreeAsync(ptr, 0);
+      } else {
+        cudaFree(ptr);
+      }
+    }
     ptr = nullptr;
     count = 0;
   }
@@ -40,8 +56,16 @@ struct DeviceBuffer {
     if (n == count) return cudaSuccess;
     release();
     if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&ptr, n * sizeof(T));
+    cudaError_t e;
+    pooled = device_pool_enabled();
+    if (pooled) {
+      e = cudaMallocAsync(reinterpret_cast<void**>(&ptr), n * sizeof(T), 0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(0);   // usable from every stream from here on
+    } else {
+      e = cudaMalloc(&ptr, n * sizeof(T));
+    }
     if (e == cudaSuccess) count = n;
+    else ptr = nullptr;
     return e;
   }
   size_t bytes() const { return count * sizeof(T); }
