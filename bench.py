@@ -292,8 +292,11 @@ def dram_traffic(kernel, config, world):
     `ncu --set full` summary (profiles/traffic.json: {kernel: {config, bytes, source, commit}}); None when there is
     no capture of this kernel on this workload."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
-    except (OSError, KeyError, ValueError):
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        # template instances are keyed with their arguments ("schur_syrk_kernel<8, 2, 5>"): match by prefix
+        key = kernel if kernel in table else next(k for k in sorted(table) if k.startswith(kernel + "<"))
+        t = table[key]
+    except (OSError, KeyError, ValueError, StopIteration):
         return None, None
     if t.get("config") != config or world != 1:
         return None, None
