@@ -259,7 +259,7 @@ WORKLOADS = {
     "C2dense": "C2dense: 100 frames / 20k points / 500k observations, every frame pair covisible (orbit): dense reduced system",
     "C3dense": "C3dense: 1000 frames / 200k points / 5M observations, every frame pair covisible (orbit): dense reduced system",
 }
-STEP_DESC = ("one Levenberg-Marquardt iteration of rsba_cuda_solve: residual+Jacobian (K1), block normal "
+STEP_DESC = ("one Levenberg-Marquardt iteration of rsba_cuda_solve: residual+Jacobian of every observation, block normal "
              "equations + Schur complement (K2), tile Cholesky + solves (K3), back-substitution/step (K4), "
              "cost at the trial point (K1r), accept/reject")
 
