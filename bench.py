@@ -429,17 +429,23 @@ def run_ours(args):
     # ---------------- the same, cold: a fresh handle pays the scene upload (120 MB of observations at C3) and the
     # one-off structure analysis (ordering, symbolic factorisation, pair lists) -- what ONE BA call of the
     # reference's driver would see (CeresHandler::Add for every frame + ceres::Solve's preprocessing)
-    cold_ms = None
+    # Twice: the first fresh handle also grows the device-memory pool (the bench's own handle is still alive and holds
+    # its 3 GB); the second finds the blocks the first one freed -- the steady state of a driver that builds one handle
+    # per BA call, as the reference does (VideoSfMHandler.cc:585).
+    cold_ms = cold_first_ms = None
     if world == 1:
-        barrier()
-        t0 = time.perf_counter()
-        with api.Problem(local) as pc:
-            pc.set_stream(stream.cuda_stream)
-            pc.load_scene(scene)
-            pc.solve(bench_options(api, args.steps))
-            pc.get_parameters(out_poses, out_points)
-        barrier()
-        cold_ms = (time.perf_counter() - t0) * 1e3
+        for rep in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            with api.Problem(local) as pc:
+                pc.set_stream(stream.cuda_stream)
+                pc.load_scene(scene)
+                pc.solve(bench_options(api, args.steps))
+                pc.get_parameters(out_poses, out_points)
+            barrier()
+            cold_ms = (time.perf_counter() - t0) * 1e3
+            if rep == 0:
+                cold_first_ms = cold_ms
     clocks = sampler.stop() if rank == 0 else None
     # ---------------- parity of the sharded solve with the single-GPU one (outside every timed region): rank 0
     # re-solves the same K iterations from the same initial estimate on its own GPU alone and compares
@@ -532,7 +538,7 @@ def run_ours(args):
         "e2e": {"value": n_total / (e2e_ms * 1e-3) / 1e6, "unit": "M evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                 "call": "rsba_cuda_set_parameters(pinned host) + rsba_cuda_solve(K iterations) + rsba_cuda_get_parameters(pinned host)",
-                "cold_call_ms_total": cold_ms,
+                "cold_call_ms_total": cold_ms, "cold_call_ms_first_in_process": cold_first_ms,
                 "cold_call": "fresh handle: rsba_cuda_create + set_camera + set_scene (observations H2D) + set_parameters + "
                              "solve(K iterations, incl. structure analysis) + get_parameters + destroy"},
         "gpu_launches": launches, "clocks": clocks,

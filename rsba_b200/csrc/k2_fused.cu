@@ -140,6 +140,9 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
   const int beg = st.pt_ptr[p], end = st.pt_ptr[p + 1];
   const double X0 = points[3L * p], X1 = points[3L * p + 1], X2 = points[3L * p + 2];
   const bool cst = ne.point_const[p] != 0;
+  // the fixed Jacobi scaling of later linearisations, requested now (it is consumed behind the butterfly)
+  double sp_in[3] = {1.0, 1.0, 1.0};
+  if (!compute_scale) { sp_in[0] = ne.scale_p[3L * p]; sp_in[1] = ne.scale_p[3L * p + 1]; sp_in[2] = ne.scale_p[3L * p + 2]; }
 
   // ---- phase A: C_p, g_p over all observations (one per lane and round; the last round stays in registers)
   ObsEval ev;
@@ -194,7 +197,7 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
     s1 = (cst || !jacobi) ? 1.0 : 1.0 / (1.0 + sqrt(v[3]));
     s2 = (cst || !jacobi) ? 1.0 : 1.0 / (1.0 + sqrt(v[5]));
   } else {
-    s0 = ne.scale_p[3L * p]; s1 = ne.scale_p[3L * p + 1]; s2 = ne.scale_p[3L * p + 2];
+    s0 = sp_in[0]; s1 = sp_in[1]; s2 = sp_in[2];
   }
   double W[6] = {0, 0, 0, 0, 0, 0}, t[3] = {0, 0, 0};   // W = s_p L^-T entries (frame side), t_p = Cinv g_p
   double ci[6] = {0, 0, 0, 0, 0, 0}, mi[6] = {0, 0, 0, 0, 0, 0}, d2[3] = {1.0, 1.0, 1.0};

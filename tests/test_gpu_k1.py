@@ -243,3 +243,21 @@ def test_k1_uncalibrated_intrinsics_jacobian(api, oracle_built, shutter, interp)
     if oracle_built.ref_available():
         _, _, Jref, vref = oracle_built.evaluate_cam_ref(sc)
         assert np.array_equal(v, vref) and rel_block_err(Jc[ok], Jref[ok]).max() <= TOL
+
+
+@pytest.mark.gpu
+def test_residual_only_evaluate_skips_the_jacobian_kernel_and_agrees():
+    """rsba_cuda_evaluate without a Jacobian (problem.Evaluate(&cost, &residuals), CeresHandler.h:386) runs the cost-only
+    kernel -- no 240 bytes per observation are allocated or written: the device Jacobian buffer stays NULL -- and gives
+    the residuals, valid flags and cost of the full evaluation bit for bit, Huber loss included."""
+    import rsba_b200.api as api
+    from rsba_b200.scene import make_scene
+    sc = make_scene(20, 1500, 10, name="res-only")
+    with api.Problem(0) as pb:
+        pb.load_scene(sc)
+        pb.set_loss(2.0)
+        c0, r0, _, v0 = pb.evaluate(jacobian=False)
+        assert pb.device_buffers()["jacobian"] is None          # nothing allocated for it
+        c1, r1, J1, v1 = pb.evaluate()
+        assert pb.device_buffers()["jacobian"] is not None
+    assert c0 == c1 and np.array_equal(r0, r1) and np.array_equal(v0, v1) and np.abs(J1).max() > 0
