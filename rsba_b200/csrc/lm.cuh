@@ -68,6 +68,7 @@ struct SchurStructure {
   // with the all-zero panel (index n_inc)
   int n_items;
   const int4* items;       // [n_items] (pair, first entry, entry count, A == B)
+  const int* item_order;   // [n_items] launch order of the work items (NULL = as stored): pairs by anti-diagonals a + b
   const int2* entries;     // (incidence on the row side B, incidence on the column side A)
   long n_entries;
   long n_cam_params;       // 12 * frames (rows of the last tile beyond it are padding)

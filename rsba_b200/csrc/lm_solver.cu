@@ -30,6 +30,7 @@ struct LmState {
   DeviceBuffer<unsigned char> slot_cnt, point_owned;
   DeviceBuffer<int> owned_ids;
   DeviceBuffer<int4> items;
+  DeviceBuffer<int> item_order;
   DeviceBuffer<int2> entries;
   // the SYRK by Cholesky-tile pairs (k2_schur2.cu; RSBA_CUDA_SYRK=1 selects the sub-tile-pair kernel of k2_schur.cu)
   bool syrk2 = false;
@@ -170,6 +171,19 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     UP(tp_item_ptr, hs.tp_item_ptr);
   } else {
     UP(pair_item_ptr, hs.pair_item_ptr); UP(items, hs.items); UP(entries, hs.entries);
+    // (experiment hook) RSBA_CUDA_SYRK_ORDER=1: launch the work items by anti-diagonals a + b instead of pair-major --
+    // measured: DRAM traffic 5.25 -> 5.16 GB, L2 hit rate 44.1 -> 44.7 %, 1.850 -> 1.851 ms: no effect, off by default
+    const char* eo = getenv("RSBA_CUDA_SYRK_ORDER");
+    if (eo && eo[0] == '1' && hs.n_items > 0) {
+      std::vector<int> order(hs.n_items);
+      for (int k = 0; k < hs.n_items; ++k) order[k] = k;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        const int px = hs.items[x].x, py = hs.items[y].x;
+        const int sx = hs.pair_a[px] + hs.pair_b[px], sy = hs.pair_a[py] + hs.pair_b[py];
+        return sx != sy ? sx < sy : hs.pair_a[px] < hs.pair_a[py];
+      });
+      UP(item_order, order);
+    }
   }
   UP(tile_pos, plan.tile_pos); UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
   UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
@@ -210,6 +224,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.cam_inc = lm->cam_inc.ptr;
   st.n_pairs = (int)pair_a.size(); st.pair_a = lm->pair_a.ptr; st.pair_b = lm->pair_b.ptr;
   st.pair_item_ptr = lm->pair_item_ptr.ptr; st.n_items = n_items; st.items = lm->items.ptr;
+  st.item_order = lm->item_order.ptr;
   st.entries = lm->entries.ptr; st.n_entries = (long)hs.entries.size(); st.tile_pos = lm->tile_pos.ptr;
   st.pos_tile = lm->pos_tile.ptr; st.n_cam_params = 12L * Fc;
   lm->free_cam = free_cam;
