@@ -10,6 +10,8 @@
 //  (J'^T J' + D^2) delta' = -g').  All reductions are two-stage with a fixed order.
 #include "lm.cuh"
 
+#include <cstdlib>
+
 namespace rsba {
 namespace {
 
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(kPointStepWarps * 32)
 point_step_kernel(SchurStructure st, JacView jv,
                   const double* __restrict__ jac_cam, int cam_frame, NormalEq ne,
                   const double* __restrict__ delta_c, int n_points, const double* __restrict__ points,
-                  double* __restrict__ delta_p, double* __restrict__ trial, double* __restrict__ scratch) {
+                  double* __restrict__ delta_p, double* __restrict__ trial, double* __restrict__ scratch, int block_offset) {
   __shared__ double sh[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * kPointStepWarps + warp;
@@ -130,6 +132,82 @@ point_step_kernel(SchurStructure st, JacView jv,
       trial[3L * p + 1] = points[3L * p + 1] + d1;
       trial[3L * p + 2] = points[3L * p + 2] + d2;
       gd = g[0] * d0 + g[1] * d1 + g[2] * d2;
+      nn = d0 * d0 + d1 * d1 + d2 * d2;
+      const double* sp = ne.scale_p + 3L * p;
+      const double* e2 = ne.d2_p + 3L * p;
+      const double u0 = d0 / sp[0], u1 = d1 / sp[1], u2 = d2 / sp[2];
+      dd = e2[0] * u0 * u0 + e2[1] * u1 * u1 + e2[2] * u2 * u2;
+    }
+  }
+  gd = block_sum(gd, sh);
+  dd = block_sum(dd, sh);
+  nn = block_sum(nn, sh);
+  if (threadIdx.x == 0) {
+    double* o = scratch + 3 + 3L * (blockIdx.x + block_offset);
+    o[0] = gd; o[1] = dd; o[2] = nn;
+  }
+}
+
+// The same back-substitution with one thread per observation over groups of whole points (k2_fused.cu's point_group_kernel
+// describes the grouping): the observation's term Jx^T (Jc delta_c) goes to shared memory, (component, point) pairs are
+// summed serially in observation order, one thread per point finishes.  Reads the point-major records coalesced.
+constexpr int kStepGroupThreads = 256;
+constexpr int kStepGroupMaxPoints = 128;
+
+__global__ void __launch_bounds__(kStepGroupThreads)
+point_step_group_kernel(SchurStructure st, const int2* __restrict__ groups, JacView jv, NormalEq ne,
+                        const double* __restrict__ delta_c, const double* __restrict__ points, double* __restrict__ delta_p,
+                        double* __restrict__ trial, double* __restrict__ scratch) {
+  __shared__ double prod[3][kStepGroupThreads];
+  __shared__ double sums[3][kStepGroupMaxPoints];
+  __shared__ int s_ptr[kStepGroupMaxPoints + 1];
+  __shared__ double sh[32];
+  const int tid = threadIdx.x;
+  const int2 g = groups[blockIdx.x];
+  const int p_lo = g.x, npts = g.y - g.x;
+  const int e_lo = st.pt_ptr[p_lo], e_hi = st.pt_ptr[g.y];
+  if (tid <= npts) s_ptr[tid] = st.pt_ptr[p_lo + tid] - e_lo;
+  const int e = e_lo + tid;
+  double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+  if (e < e_hi) {
+    const double2* rp = reinterpret_cast<const double2*>(jv.rec + (long)e * kJacCompact);
+    const double2 a01 = rp[0], a2b0 = rp[1], b12 = rp[2], c01 = rp[3], c2d0 = rp[4], d12 = rp[5];
+    const double tau = st.pt_tau[e];
+    const double2* dc = reinterpret_cast<const double2*>(delta_c + 12L * st.pt_frame[e]);
+    const double2 u0 = dc[0], u1 = dc[1], u2 = dc[2], u3 = dc[3], u4 = dc[4], u5 = dc[5];
+    const double th0 = 1.0 - tau, wr0 = jv.rot_interp ? th0 : 1.0, wr1 = jv.rot_interp ? tau : 0.0;
+    const double dr0 = wr0 * u0.x + wr1 * u3.x, dr1 = wr0 * u0.y + wr1 * u3.y, dr2 = wr0 * u1.x + wr1 * u4.x;
+    const double dq0 = th0 * u1.y + tau * u4.y, dq1 = th0 * u2.x + tau * u5.x, dq2 = th0 * u2.y + tau * u5.y;
+    const double m0 = c01.x * dr0 + c01.y * dr1 + c2d0.x * dr2 - (a01.x * dq0 + a01.y * dq1 + a2b0.x * dq2);
+    const double m1 = c2d0.y * dr0 + d12.x * dr1 + d12.y * dr2 - (a2b0.y * dq0 + b12.x * dq1 + b12.y * dq2);
+    c0 = a01.x * m0 + a2b0.y * m1;
+    c1 = a01.y * m0 + b12.x * m1;
+    c2 = a2b0.x * m0 + b12.y * m1;
+  }
+  prod[0][tid] = c0; prod[1][tid] = c1; prod[2][tid] = c2;
+  __syncthreads();
+  for (int u = tid; u < 3 * npts; u += kStepGroupThreads) {
+    const int comp = u / npts, pq = u - comp * npts;
+    double sum = 0.0;
+    for (int j = s_ptr[pq]; j < s_ptr[pq + 1]; ++j) sum += prod[comp][j];
+    sums[comp][pq] = sum;
+  }
+  __syncthreads();
+  double gd = 0.0, dd = 0.0, nn = 0.0;
+  if (tid < npts) {
+    const int p = p_lo + tid;
+    if (ne.point_owned[p]) {
+      const double* gp = ne.gp + 3L * p;
+      const double a0 = sums[0][tid] + gp[0], a1 = sums[1][tid] + gp[1], a2 = sums[2][tid] + gp[2];
+      const double* Ci = ne.Cinv + 6L * p;
+      const double d0 = -(Ci[0] * a0 + Ci[1] * a1 + Ci[2] * a2);
+      const double d1 = -(Ci[1] * a0 + Ci[3] * a1 + Ci[4] * a2);
+      const double d2 = -(Ci[2] * a0 + Ci[4] * a1 + Ci[5] * a2);
+      delta_p[3L * p] = d0; delta_p[3L * p + 1] = d1; delta_p[3L * p + 2] = d2;
+      trial[3L * p] = points[3L * p] + d0;
+      trial[3L * p + 1] = points[3L * p + 1] + d1;
+      trial[3L * p + 2] = points[3L * p + 2] + d2;
+      gd = gp[0] * d0 + gp[1] * d1 + gp[2] * d2;
       nn = d0 * d0 + d1 * d1 + d2 * d2;
       const double* sp = ne.scale_p + 3L * p;
       const double* e2 = ne.d2_p + 3L * p;
@@ -229,12 +307,33 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const JacV
                         const double* y_c, int n_frames, int n_points, const double* poses,
                         const double* points, double* delta_c, double* delta_p, double* trial_poses,
                         double* trial_points, double* scalars, double* scratch, int bounded_param,
-                        double lower_bound, cudaStream_t s) {
+                        double lower_bound, const PointGroups& pg, cudaStream_t s) {
   frame_step_kernel<<<1, kWideThreads, 0, s>>>(ne, st.tile_pos, y_c, 12 * n_frames, poses, delta_c, trial_poses, scratch,
                                                bounded_param, lower_bound);
+  // (RSBA_CUDA_STEP=warp: the warp-per-point kernel, 0.277 against 0.248 ms at C3)
+  static const bool use_groups = [] { const char* e = getenv("RSBA_CUDA_STEP"); return !(e && e[0] == 'w'); }();
+  if (use_groups && pg.groups && jv.point_major && !jac_cam) {
+    // one thread per observation over groups of whole points; tracks longer than a CTA through the warp-per-point kernel
+    if (pg.n_groups > 0)
+      point_step_group_kernel<<<pg.n_groups, kStepGroupThreads, 0, s>>>(st, pg.groups, jv, ne, delta_c, points, delta_p,
+                                                                       trial_points, scratch);
+    int nb = pg.n_groups;
+    if (pg.n_big > 0) {
+      NormalEq nbig = ne;
+      nbig.owned_ids = pg.big_ids;
+      nbig.n_owned = pg.n_big;
+      const int blocks = (pg.n_big + kPointStepWarps - 1) / kPointStepWarps;
+      point_step_kernel<<<blocks, kPointStepWarps * 32, 0, s>>>(st, jv, jac_cam, cam_frame, nbig, delta_c, n_points, points,
+                                                                delta_p, trial_points, scratch, nb);
+      nb += blocks;
+    }
+    step_final_kernel<<<1, kWideThreads, 0, s>>>(scratch, nb, scalars);
+    return;
+  }
   const int nb = (ne.n_owned + kPointStepWarps - 1) / kPointStepWarps;
   if (nb > 0)
-    point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, jv, jac_cam, cam_frame, ne, delta_c, n_points, points, delta_p, trial_points, scratch);
+    point_step_kernel<<<nb, kPointStepWarps * 32, 0, s>>>(st, jv, jac_cam, cam_frame, ne, delta_c, n_points, points, delta_p,
+                                                          trial_points, scratch, 0);
   step_final_kernel<<<1, kWideThreads, 0, s>>>(scratch, nb, scalars);
 }
 

@@ -145,11 +145,20 @@ void launch_frame_reduce(const SchurStructure& st, NormalEq ne, int n_frames, cu
 // filled once per scene by launch_pack_point_major)
 size_t point_pass_record_bytes();
 void launch_pack_point_major(const SchurStructure& st, const ObsView& obs, long n, void* packed, cudaStream_t s);
+// Groups of whole points for the thread-per-observation form of the point pass: groups[g] = (first point, one past the
+// last), <= 256 observations and <= 128 points each; big_ids = the points with more than 256 observations.
+struct PointGroups {
+  const int2* groups = nullptr;
+  int n_groups = 0;
+  const int* big_ids = nullptr;
+  int n_big = 0;
+};
+constexpr int kPointGroupObs = 256, kPointGroupPoints = 128;
 // (res_pt: [N][2] scratch for the residuals in point-major order)
 void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, long n_obs, const double* poses,
                        const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
                        double* rec_pt, double* tau_pt, double* xt, double* res_pt, bool write_phi /* Schur panel rows */,
-                       cudaStream_t s);
+                       const PointGroups& pg, cudaStream_t s);
 void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,
                        const double* xt, NormalEq ne, double* cost_partials, int* invalid_count, cudaStream_t s);
 // n_frames > 0: the camera parameters; points: the owned points (two calls: the point part runs before the
@@ -254,7 +263,7 @@ void launch_step_update(const SchurStructure& st, const ObsView& obs, const JacV
                         double* trial_points, double* scalars /* [16]: [0..2] camera part, [8..10] point part */,
                         double* scratch,
                         int bounded_param /* index into the camera parameters with a lower bound, or -1 */,
-                        double lower_bound, cudaStream_t s);
+                        double lower_bound, const PointGroups& pg /* groups == NULL: one warp per point */, cudaStream_t s);
 // |x|^2 and max|g| split into the point part (local to the rank; before the all-reduce) and the
 // camera part (replicated; after it).  out_points: [0] += |x_p|^2 over owned free points, [1] = max|g_p|
 void launch_point_norms(NormalEq ne, int n_points, const double* points, double* out_xx, double* out_gmax,

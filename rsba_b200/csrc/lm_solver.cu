@@ -67,6 +67,9 @@ struct LmState {
   // K1 -> point_blocks -> frame_blocks sequence, which the uncalibrated variant always uses)
   bool fused = false;
   DeviceBuffer<double> rec_pt, xt;        // point-major compact records [N][12]; (X_p | t_p) [P][6]
+  DeviceBuffer<int2> pt_groups;           // thread-per-observation point pass: groups of whole points (lm.cuh)
+  DeviceBuffer<int> pt_big;
+  PointGroups pg{};
   // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
   DeviceBuffer<double> solve_partials, fwd_partials;
   DeviceBuffer<int> fwd_slot;
@@ -260,6 +263,29 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     RSBA_CUDA_TRY(lm->rec_pt.resize(Nz * kJacCompact));
     RSBA_CUDA_TRY(lm->xt.resize(Pz * 6));
     RSBA_CUDA_TRY(cudaMemsetAsync(lm->xt.ptr, 0, lm->xt.bytes(), s));
+    {   // groups of whole points: <= 256 observations, <= 128 points; longer tracks go to the warp-per-point kernel
+      std::vector<int2> groups;
+      std::vector<int> big;
+      int lo = 0;
+      long acc = 0;
+      auto flush = [&](int hi) { if (hi > lo) groups.push_back(make_int2(lo, hi)); lo = hi; acc = 0; };
+      for (int p = 0; p < P; ++p) {
+        const long n = hs.pt_ptr[p + 1] - hs.pt_ptr[p];
+        if (n > kPointGroupObs) {            // its observations sit between the neighbours': the group ends here
+          flush(p);
+          if (h->point_owned[p]) big.push_back(p);
+          lo = p + 1;
+          continue;
+        }
+        if (acc + n > kPointGroupObs || p - lo >= kPointGroupPoints) flush(p);
+        acc += n;
+      }
+      flush(P);
+      if ((rc = upload(lm->pt_groups, groups, s))) return rc;
+      if ((rc = upload(lm->pt_big, big, s))) return rc;
+      lm->pg.groups = lm->pt_groups.ptr; lm->pg.n_groups = (int)groups.size();
+      lm->pg.big_ids = lm->pt_big.ptr; lm->pg.n_big = (int)big.size();
+    }
     // the frames in point-major order are a constant of the scene (tau follows from the first point pass)
     launch_point_major_obs(lm->st, h->obs_view(), nullptr, h->n_obs, nullptr, lm->pt_frame.ptr, s);
   }
@@ -292,7 +318,8 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   RSBA_CUDA_TRY(lm->trial_poses.resize(Fz * 12)); RSBA_CUDA_TRY(lm->trial_points.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->scalars.resize(16));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->scalars.ptr, 0, lm->scalars.bytes(), s));
-  RSBA_CUDA_TRY(lm->scratch.resize(std::max<size_t>(3 + 3 * ((Pz + 7) / 8), 1024)));
+  // (step partials: one triple per CTA of the point back-substitution -- per 8 points, or per group of whole points)
+  RSBA_CUDA_TRY(lm->scratch.resize(std::max<size_t>(3 + 3 * ((Pz + 7) / 8) + 3 * (size_t)(lm->pg.n_groups + 8), 1024)));
   RSBA_CUDA_TRY(lm->info.resize(4));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->rhs.ptr, 0, lm->rhs.bytes(), s));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->d2_c.ptr, 0, lm->d2_c.bytes(), s));
@@ -384,7 +411,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), s);
     stage_begin(h, kStageJacobian);
     launch_point_pass(h->cm, lm->st, lm->pt_packed.ptr, h->n_obs, h->d_poses.ptr, h->d_points.ptr, lm->ne, o, compute_scale,
-                      opt.jacobi_scaling != 0, lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, h->d_res.ptr, want_S, s);
+                      opt.jacobi_scaling != 0, lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, h->d_res.ptr, want_S, lm->pg, s);
     stage_end(h, kStageJacobian);
     stage_begin(h, kStageSchur);
     stage_begin(h, kStageFrameBlocks);
@@ -547,7 +574,7 @@ void step_update(rsba_problem* h, LmState* lm) {
                      lm->free_cam ? h->n_frames : -1, lm->ne, lm->y.ptr, lm->n_cam_frames, h->n_points,
                      h->d_poses.ptr, h->d_points.ptr, lm->delta_c.ptr, lm->delta_p.ptr, lm->trial_poses.ptr,
                      lm->trial_points.ptr, lm->scalars.ptr, lm->scratch.ptr,
-                     lm->free_ratio ? 12 * h->n_frames + 9 : -1, h->ratio_lower_bound(), h->stream);
+                     lm->free_ratio ? 12 * h->n_frames + 9 : -1, h->ratio_lower_bound(), lm->pg, h->stream);
   h->launches += 3;
   const PosePriorView ppv = h->pose_prior_view();
   if (ppv.n > 0) { launch_pose_prior_step(ppv, lm->delta_c.ptr, lm->scalars.ptr, h->stream); h->launches += 1; }
