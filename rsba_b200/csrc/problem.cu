@@ -1,5 +1,7 @@
 // C ABI: lifecycle, problem construction, evaluation (include/rsba_cuda.h).
 #include "problem.cuh"
+
+#include <mutex>
 #include "nccl_dl.cuh"
 
 #include <dlfcn.h>
@@ -70,8 +72,10 @@ bool device_pool_enabled() {
   static const bool on = getenv("RSBA_CUDA_NO_POOL") == nullptr;
   if (!on) return false;
   static bool prepared[64] = {};
+  static std::mutex mu;      // rsba_cuda_multi_solve runs the ranks on worker threads
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lock(mu);
   if (!prepared[dev & 63]) {
     int supported = 0;
     cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev);
