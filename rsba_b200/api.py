@@ -743,8 +743,6 @@ _STRUCTURE_ARRAYS = {
     "plan.panel_ptr": (np.int32, 1), "plan.trsm": (np.int32, 2), "plan.trsm_ptr": (np.int32, 1),
     "plan.upd": (np.int32, 4), "plan.lrow_ptr": (np.int32, 1), "plan.lrow_cols": (np.int32, 1),
     "local_ids": (np.int64, 1), "point_owned": (np.uint8, 1),
-    "tp_a": (np.int32, 1), "tp_b": (np.int32, 1), "tp_item_ptr": (np.int32, 1), "pair_tp": (np.int32, 1),
-    "items2": (np.int32, 4), "entries2": (np.int32, 4), "chunk_mask2": (np.uint8, 1),
 }
 
 

@@ -21,8 +21,6 @@
 // CeresHandler.h:403,419).  Every sum has a fixed order: results are bit-reproducible.
 #include "lm.cuh"
 
-#include <cstdlib>
-
 namespace rsba {
 namespace {
 
@@ -83,56 +81,11 @@ __global__ void pack_point_major_kernel(const int* __restrict__ pt_obs, ObsView 
   out[e] = r;
 }
 
-// point_eval (one thread per observation, point-major order): the functor + Jacobian of every observation, written as
-// point-major compact records + residuals + tau.  With it the point pass below runs in its PRE form -- it reads
-// the records back (coalesced) instead of evaluating, needs half the registers and keeps 1.5 x the warps in flight;
-// the warp-per-point pass with the evaluation inside was latency-bound at 16 warps per SM (0.68 ms at C3).
-constexpr int kEvalThreads = 128;
-
-__global__ void __launch_bounds__(kEvalThreads)
-point_eval_kernel(const CameraModel cm, const PtObsRec* __restrict__ prec_pm, long n, const double* __restrict__ poses,
-                  const double* __restrict__ points, double* __restrict__ rec_pt, double* __restrict__ res_pt,
-                  double* __restrict__ tau_pt) {
-  extern __shared__ __align__(128) double s_rec[];   // [warps][32][kJacCompact]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long e = (long)blockIdx.x * kEvalThreads + threadIdx.x;
-  double* row = s_rec + (warp * 32 + lane) * kJacCompact;
-  if (e < n) {
-    const PtObsRec pr = prec_pm[e];
-    const double* pp = points + 3L * pr.point;
-    const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
-    double pose[kFrameParams];
-    load_pose(poses, pr.frame, pose);
-    ObsEval ev;
-    eval_observation(cm, pr.x, pr.y, pose, X0, X1, X2, ev);
-#pragma unroll
-    for (int k = 0; k < kJacCompact; ++k) row[k] = ev.rec[k];
-    reinterpret_cast<double2*>(res_pt)[e] = make_double2(ev.r0, ev.r1);
-    tau_pt[e] = ev.tau;
-  }
-  // the warp's 32 x 12 records leave as one bulk store (as K1's Jacobian tile does)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncwarp();
-  const long wbase = (long)blockIdx.x * kEvalThreads + warp * 32;
-  if (lane == 0 && wbase < n) {
-    const int wcnt = (int)min(32L, n - wbase);
-    const unsigned bytes = (unsigned)(wcnt * kJacCompact * sizeof(double));
-    const unsigned src = (unsigned)__cvta_generic_to_shared(s_rec + warp * 32 * kJacCompact);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec_pt + wbase * kJacCompact), "r"(src),
-                 "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  }
-}
-
-// PRE: the observations were evaluated by point_eval_kernel (rec_pt / res_pt / tau_pt hold them); else evaluate here.
-template <int MIN_CTAS, bool PRE>
-__global__ void __launch_bounds__(kPointPassWarps * 32, MIN_CTAS)
+__global__ void __launch_bounds__(kPointPassWarps * 32, 4)
 point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __restrict__ prec_pm, const double* __restrict__ poses,
                   const double* __restrict__ points, NormalEq ne, LmOptionsDev o, int compute_scale, int jacobi,
                   int rot_interp, int write_phi, double* __restrict__ rec_pt, double* __restrict__ tau_pt,
-                  double* __restrict__ xt, const double* __restrict__ res_pt) {
+                  double* __restrict__ xt) {
   const int lane = threadIdx.x & 31;
   const int kk = blockIdx.x * kPointPassWarps + (threadIdx.x >> 5);
   if (kk >= ne.n_owned) return;
@@ -153,18 +106,6 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
     if (e < end) {
-      if (PRE) {
-        const int2 fo = reinterpret_cast<const int2*>(prec_pm + e)[2];     // (frame, phi_off)
-        frame = fo.x;
-        off = fo.y;
-        const double2* rp = reinterpret_cast<const double2*>(rec_pt + (long)e * kJacCompact);
-#pragma unroll
-        for (int k = 0; k < kJacCompact / 2; ++k) { const double2 q = rp[k]; ev.rec[2 * k] = q.x; ev.rec[2 * k + 1] = q.y; }
-        const double2 rr = reinterpret_cast<const double2*>(res_pt)[e];
-        ev.r0 = rr.x; ev.r1 = rr.y;
-        ev.tau = tau_pt[e];
-        mask = ne.pose_mask[frame];
-      } else {
       const PtObsRec pr = prec_pm[e];
       frame = pr.frame;
       off = pr.phi_off;
@@ -172,7 +113,6 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
       load_pose(poses, frame, pose);
       mask = ne.pose_mask[frame];
       eval_observation(cm, pr.x, pr.y, pose, X0, X1, X2, ev);
-      }
       const double a0 = ev.rec[0], a1 = ev.rec[1], a2 = ev.rec[2], b0 = ev.rec[3], b1 = ev.rec[4], b2 = ev.rec[5];
       v[0] += a0 * a0 + b0 * b0;
       v[1] += a0 * a1 + b0 * b1;
@@ -258,17 +198,7 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
   for (int e0 = beg; e0 < end; e0 += 32) {
     const int e = e0 + lane;
     const bool mine = e < end;
-    if (mine && !reuse) {   // a track longer than a warp: fetch / evaluate again
-      if (PRE) {
-        const int2 fo = reinterpret_cast<const int2*>(prec_pm + e)[2];
-        frame = fo.x;
-        off = fo.y;
-        const double2* rq = reinterpret_cast<const double2*>(rec_pt + (long)e * kJacCompact);
-#pragma unroll
-        for (int k = 0; k < kJacCompact / 2; ++k) { const double2 q = rq[k]; ev.rec[2 * k] = q.x; ev.rec[2 * k + 1] = q.y; }
-        ev.tau = tau_pt[e];
-        mask = ne.pose_mask[frame];
-      } else {
+    if (mine && !reuse) {   // a track longer than a warp: evaluate again
       const PtObsRec pr = prec_pm[e];
       frame = pr.frame;
       off = pr.phi_off;
@@ -276,15 +206,12 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
       load_pose(poses, frame, pose);
       mask = ne.pose_mask[frame];
       eval_observation(cm, pr.x, pr.y, pose, X0, X1, X2, ev);
-      }
     }
     if (!mine) continue;
-    if (!PRE) {
-      double2* rp = reinterpret_cast<double2*>(rec_pt + (long)e * kJacCompact);
+    double2* rp = reinterpret_cast<double2*>(rec_pt + (long)e * kJacCompact);
 #pragma unroll
-      for (int k = 0; k < kJacCompact / 2; ++k) rp[k] = make_double2(ev.rec[2 * k], ev.rec[2 * k + 1]);
-      tau_pt[e] = ev.tau;
-    }
+    for (int k = 0; k < kJacCompact / 2; ++k) rp[k] = make_double2(ev.rec[2 * k], ev.rec[2 * k + 1]);
+    tau_pt[e] = ev.tau;
     if (off < 0 || !write_phi) continue;
     const double* jx0 = ev.rec, *jx1 = ev.rec + 3, *jr0 = ev.rec + 6, *jr1 = ev.rec + 9;
     const double xa[3] = {jx0[0] * W[0], jx0[0] * W[1] + jx0[1] * W[2], jx0[0] * W[3] + jx0[1] * W[4] + jx0[2] * W[5]};
@@ -313,192 +240,6 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
                      : "memory");
     }
   }
-}
-
-// ---------------------------------------------------------------- point pass, one thread per observation
-// The warp-per-point pass above is bound by the latency of its per-point chain at 16 warps per SM and 25 of 32 lanes
-// (0.68 ms at C3, 0.49 of the copy bandwidth).  Here a CTA of 256 threads takes a GROUP of whole points with <= 256
-// observations between them (host: greedy over the point-major order, ~10 points at C3), one thread per observation:
-//   (a) evaluate the functor + compact Jacobian; the nine products of C_p / g_p go to shared memory,
-//   (b) (component, point) pairs are summed serially in observation order by one thread each (fixed order),
-//   (c) one thread per point: scaling, LM diagonal, 3x3 Cholesky inverse, per-point outputs, W / t to shared memory,
-//   (d) every thread writes its observation's Schur panel rows and point-major record.
-// All lanes work, the per-point serial section runs for ~10 points at once, and there is no butterfly.  Points with
-// more than 256 observations (and nothing else) go through the warp-per-point kernel.
-constexpr int kGroupThreads = 256;
-constexpr int kGroupMaxPoints = 128;
-
-struct PointBlock {   // what the inverse of a damped point block leaves
-  double s[3], W[6], t[3], ci[6], mi[6], d2[3];
-};
-
-__device__ __forceinline__ void invert_point_block(const double (&v)[9], bool cst, bool compute_scale, bool jacobi,
-                                                   const double (&sp_in)[3], const LmOptionsDev& o, PointBlock& b) {
-#pragma unroll
-  for (int k = 0; k < 6; ++k) b.W[k] = b.ci[k] = b.mi[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { b.t[k] = 0.0; b.d2[k] = 1.0; }
-  if (compute_scale) {
-    b.s[0] = (cst || !jacobi) ? 1.0 : 1.0 / (1.0 + sqrt(v[0]));
-    b.s[1] = (cst || !jacobi) ? 1.0 : 1.0 / (1.0 + sqrt(v[3]));
-    b.s[2] = (cst || !jacobi) ? 1.0 : 1.0 / (1.0 + sqrt(v[5]));
-  } else {
-    b.s[0] = sp_in[0]; b.s[1] = sp_in[1]; b.s[2] = sp_in[2];
-  }
-  if (cst) return;
-  const double s0 = b.s[0], s1 = b.s[1], s2 = b.s[2];
-  double c00 = s0 * v[0] * s0, c10 = s1 * v[1] * s0, c20 = s2 * v[2] * s0;
-  double c11 = s1 * v[3] * s1, c21 = s2 * v[4] * s1, c22 = s2 * v[5] * s2;
-  b.d2[0] = fmin(fmax(c00, o.min_diag), o.max_diag) / o.radius;
-  b.d2[1] = fmin(fmax(c11, o.min_diag), o.max_diag) / o.radius;
-  b.d2[2] = fmin(fmax(c22, o.min_diag), o.max_diag) / o.radius;
-  c00 += b.d2[0]; c11 += b.d2[1]; c22 += b.d2[2];
-  const double l00 = sqrt(c00);
-  const double m00 = 1.0 / l00;
-  const double l10 = c10 * m00, l20 = c20 * m00;
-  const double l11 = sqrt(c11 - l10 * l10);
-  const double m11 = 1.0 / l11;
-  const double l21 = (c21 - l20 * l10) * m11;
-  const double l22 = sqrt(c22 - l20 * l20 - l21 * l21);
-  const double m22 = 1.0 / l22;
-  const double m10 = -l10 * m00 * m11;
-  const double m21 = -l21 * m11 * m22;
-  const double m20 = -(l20 * m00 + l21 * m10) * m22;
-  b.mi[0] = m00; b.mi[1] = m10; b.mi[2] = m11; b.mi[3] = m20; b.mi[4] = m21; b.mi[5] = m22;
-  b.ci[0] = (m00 * m00 + m10 * m10 + m20 * m20) * s0 * s0;
-  b.ci[1] = (m10 * m11 + m20 * m21) * s1 * s0;
-  b.ci[2] = (m20 * m22) * s2 * s0;
-  b.ci[3] = (m11 * m11 + m21 * m21) * s1 * s1;
-  b.ci[4] = (m21 * m22) * s2 * s1;
-  b.ci[5] = (m22 * m22) * s2 * s2;
-  b.t[0] = b.ci[0] * v[6] + b.ci[1] * v[7] + b.ci[2] * v[8];
-  b.t[1] = b.ci[1] * v[6] + b.ci[3] * v[7] + b.ci[4] * v[8];
-  b.t[2] = b.ci[2] * v[6] + b.ci[4] * v[7] + b.ci[5] * v[8];
-  b.W[0] = s0 * m00; b.W[1] = s0 * m10; b.W[2] = s1 * m11; b.W[3] = s0 * m20; b.W[4] = s1 * m21; b.W[5] = s2 * m22;
-}
-
-// the observation's 12 x 3 panel rows  F = Jc^T (Jx W)  into its (sub-tile, point) panel
-__device__ __forceinline__ void write_panel_rows(const double* rec, double tau, const double* W, int rot_interp, unsigned mask,
-                                                 double* __restrict__ dst) {
-  const double* jx0 = rec, *jx1 = rec + 3, *jr0 = rec + 6, *jr1 = rec + 9;
-  const double xa[3] = {jx0[0] * W[0], jx0[0] * W[1] + jx0[1] * W[2], jx0[0] * W[3] + jx0[1] * W[4] + jx0[2] * W[5]};
-  const double xb[3] = {jx1[0] * W[0], jx1[0] * W[1] + jx1[1] * W[2], jx1[0] * W[3] + jx1[1] * W[4] + jx1[2] * W[5]};
-  const double th0 = 1.0 - tau, th1 = tau;
-  const double wgt[4] = {rot_interp ? th0 : 1.0, -th0, rot_interp ? th1 : 0.0, -th1};
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    double gr[3], gc3[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      gr[j] = jr0[j] * xa[k] + jr1[j] * xb[k];
-      gc3[j] = jx0[j] * xa[k] + jx1[j] * xb[k];
-    }
-    double f[12];
-#pragma unroll
-    for (int a = 0; a < 12; ++a) {
-      const double g = ((a / 3) & 1) ? gc3[a % 3] : gr[a % 3];
-      f[a] = ((mask >> a) & 1) ? 0.0 : wgt[a / 3] * g;
-    }
-#pragma unroll
-    for (int a = 0; a < 12; a += 4)
-      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * kPanelLd + a), "d"(f[a]), "d"(f[a + 1]),
-                   "d"(f[a + 2]), "d"(f[a + 3])
-                   : "memory");
-  }
-}
-
-__global__ void __launch_bounds__(kGroupThreads, 2)
-point_group_kernel(const CameraModel cm, SchurStructure st, const int2* __restrict__ groups, const PtObsRec* __restrict__ prec_pm,
-                   const double* __restrict__ poses, const double* __restrict__ points, NormalEq ne, LmOptionsDev o,
-                   int compute_scale, int jacobi, int rot_interp, int write_phi, double* __restrict__ rec_pt,
-                   double* __restrict__ tau_pt, double* __restrict__ xt) {
-  __shared__ double prod[9][kGroupThreads];          // per observation: C_p (6) and g_p (3) terms
-  __shared__ double sums[9][kGroupMaxPoints];
-  __shared__ double wt[kGroupMaxPoints][9];           // W (6) | t (3) of the group's points
-  __shared__ int s_ptr[kGroupMaxPoints + 1];          // the points' observation ranges, relative to the group's first
-  const int tid = threadIdx.x;
-  const int2 g = groups[blockIdx.x];
-  const int p_lo = g.x, npts = g.y - g.x;
-  const int e_lo = st.pt_ptr[p_lo], e_hi = st.pt_ptr[g.y];
-  if (tid <= npts) s_ptr[tid] = st.pt_ptr[p_lo + tid] - e_lo;
-  // ---- (a)
-  const int e = e_lo + tid;
-  const bool active = e < e_hi;
-  ObsEval ev;
-  int q = 0, off = -1;
-  unsigned mask = 0;
-  double pr9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (active) {
-    const PtObsRec pr = prec_pm[e];
-    q = pr.point - p_lo;
-    off = pr.phi_off;
-    const double* pp = points + 3L * pr.point;
-    const double X0 = pp[0], X1 = pp[1], X2 = pp[2];
-    double pose[kFrameParams];
-    load_pose(poses, pr.frame, pose);
-    mask = ne.pose_mask[pr.frame];
-    eval_observation(cm, pr.x, pr.y, pose, X0, X1, X2, ev);
-    const double a0 = ev.rec[0], a1 = ev.rec[1], a2 = ev.rec[2], b0 = ev.rec[3], b1 = ev.rec[4], b2 = ev.rec[5];
-    pr9[0] = a0 * a0 + b0 * b0; pr9[1] = a0 * a1 + b0 * b1; pr9[2] = a0 * a2 + b0 * b2;
-    pr9[3] = a1 * a1 + b1 * b1; pr9[4] = a1 * a2 + b1 * b2; pr9[5] = a2 * a2 + b2 * b2;
-    pr9[6] = a0 * ev.r0 + b0 * ev.r1; pr9[7] = a1 * ev.r0 + b1 * ev.r1; pr9[8] = a2 * ev.r0 + b2 * ev.r1;
-  }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) prod[k][tid] = pr9[k];
-  __syncthreads();
-  // ---- (b) adjacent threads = adjacent points of one component
-  for (int u = tid; u < 9 * npts; u += kGroupThreads) {
-    const int comp = u / npts, pq = u - comp * npts;
-    double sum = 0.0;
-    for (int j = s_ptr[pq]; j < s_ptr[pq + 1]; ++j) sum += prod[comp][j];
-    sums[comp][pq] = sum;
-  }
-  __syncthreads();
-  // ---- (c)
-  if (tid < npts) {
-    const int p = p_lo + tid;
-    if (ne.point_owned[p]) {
-      double v[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) v[k] = sums[k][tid];
-      double sp_in[3] = {1.0, 1.0, 1.0};
-      if (!compute_scale) { sp_in[0] = ne.scale_p[3L * p]; sp_in[1] = ne.scale_p[3L * p + 1]; sp_in[2] = ne.scale_p[3L * p + 2]; }
-      PointBlock b;
-      invert_point_block(v, ne.point_const[p] != 0, compute_scale != 0, jacobi != 0, sp_in, o, b);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        ne.C[6L * p + k] = v[k];
-        ne.Cinv[6L * p + k] = b.ci[k];
-        ne.Minv[6L * p + k] = b.mi[k];
-        wt[tid][k] = b.W[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        ne.gp[3L * p + k] = v[6 + k];
-        ne.tp[3L * p + k] = b.t[k];
-        ne.d2_p[3L * p + k] = b.d2[k];
-        if (compute_scale) ne.scale_p[3L * p + k] = b.s[k];
-        wt[tid][6 + k] = b.t[k];
-      }
-      double2* x = reinterpret_cast<double2*>(xt + 6L * p);   // what the frame pass gathers: X_p | t_p
-      const double* pp = points + 3L * p;
-      x[0] = make_double2(pp[0], pp[1]);
-      x[1] = make_double2(pp[2], b.t[0]);
-      x[2] = make_double2(b.t[1], b.t[2]);
-    }
-  }
-  __syncthreads();
-  // ---- (d)
-  if (!active) return;
-  double2* rp = reinterpret_cast<double2*>(rec_pt + (long)e * kJacCompact);
-#pragma unroll
-  for (int k = 0; k < kJacCompact / 2; ++k) rp[k] = make_double2(ev.rec[2 * k], ev.rec[2 * k + 1]);
-  tau_pt[e] = ev.tau;
-  if (off < 0 || !write_phi) return;
-  double W[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) W[k] = wt[q][k];
-  write_panel_rows(ev.rec, ev.tau, W, rot_interp, mask, ne.Phi + off);
 }
 
 // ---------------------------------------------------------------- frame pass
@@ -617,45 +358,18 @@ void launch_pack_point_major(const SchurStructure& st, const ObsView& obs, long 
                                                                         static_cast<PtObsRec*>(packed));
 }
 
-void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, long n_obs, const double* poses,
+void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, const double* poses,
                        const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
-                       double* rec_pt, double* tau_pt, double* xt, double* res_pt, bool write_phi,
-                       const PointGroups& pg, cudaStream_t s) {
+                       double* rec_pt, double* tau_pt, double* xt, bool write_phi, cudaStream_t s) {
   if (ne.n_owned <= 0) return;
   const int rot_interp = (cm.shutter != 0 && cm.interp_rot) ? 1 : 0;
-  const PtObsRec* pk = static_cast<const PtObsRec*>(packed);
-  // RSBA_CUDA_KP = warp (default): one warp per point with the evaluation inside, 0.68 ms at C3; groups: one thread per
-  // observation, whole points per CTA, 0.70 ms (half the instructions, but three CTA-wide barriers around a serial
-  // per-point section at 2 CTAs per SM); split: point_eval_kernel + the PRE form of the warp-per-point pass, 0.67-0.70 ms.
-  // All three are measured in profiles/r02_notes.md; the back-substitution (k4_update.cu) does use the groups.
-  static const int mode = [] { const char* e = getenv("RSBA_CUDA_KP"); return !e ? 1 : (e[0] == 'g' ? 0 : (e[0] == 's' ? 2 : 1)); }();
-  if (mode == 0 && pg.groups) {
-    if (pg.n_groups > 0)
-      point_group_kernel<<<pg.n_groups, kGroupThreads, 0, s>>>(cm, st, pg.groups, pk, poses, points, ne, o, compute_scale ? 1 : 0,
-                                                               jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt, tau_pt, xt);
-    if (pg.n_big > 0) {   // tracks longer than a CTA: the warp-per-point pass over just those points
-      NormalEq nb = ne;
-      nb.owned_ids = pg.big_ids;
-      nb.n_owned = pg.n_big;
-      point_pass_kernel<4, false><<<(pg.n_big + kPointPassWarps - 1) / kPointPassWarps, kPointPassWarps * 32, 0, s>>>(
-          cm, st, pk, poses, points, nb, o, compute_scale ? 1 : 0, jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt, tau_pt,
-          xt, res_pt);
-    }
-    return;
-  }
+  // Measured beside this form and not kept (profiles/r02_notes.md, code at commit b6103ee): the evaluation in a kernel of
+  // its own + this pass reading the records back (0.67-0.70 ms), and one thread per observation over groups of whole
+  // points (0.70 ms; that grouping is what the back-substitution in k4_update.cu uses).
   const int grid = (ne.n_owned + kPointPassWarps - 1) / kPointPassWarps;
-  if (mode != 2) {
-    point_pass_kernel<4, false><<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, pk, poses, points, ne, o, compute_scale ? 1 : 0,
-                                                                      jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt,
-                                                                      tau_pt, xt, res_pt);
-    return;
-  }
-  if (n_obs > 0)
-    point_eval_kernel<<<(unsigned)((n_obs + kEvalThreads - 1) / kEvalThreads), kEvalThreads,
-                        (size_t)kEvalThreads * kJacCompact * sizeof(double), s>>>(cm, pk, n_obs, poses, points, rec_pt, res_pt, tau_pt);
-  point_pass_kernel<5, true><<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, pk, poses, points, ne, o, compute_scale ? 1 : 0,
-                                                                   jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0, rec_pt, tau_pt,
-                                                                   xt, res_pt);
+  point_pass_kernel<<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, static_cast<const PtObsRec*>(packed), poses, points, ne, o,
+                                                          compute_scale ? 1 : 0, jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0,
+                                                          rec_pt, tau_pt, xt);
 }
 
 void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,

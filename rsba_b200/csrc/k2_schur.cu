@@ -26,15 +26,13 @@
 // is bound by the FP64 pipe (tcgen05 has no FP64 kind: DMMA == DFMA rate, 37.1 TFLOP/s measured).
 #include "lm.cuh"
 
-#include <cstdlib>
 #include <type_traits>
 
 namespace rsba {
 namespace {
 
 constexpr unsigned kPanelBytes = kPanelDoubles * sizeof(double);
-// pipeline shape: points per stage (CHUNK: 8 = 24 K columns), stages, CTAs per SM -- the shipped variant and the
-// ones measured beside it (profiles/r02_notes.md) are instantiated at the bottom
+// pipeline shape: points per stage (CHUNK: 8 = 24 K columns), stages, CTAs per SM (the launcher at the bottom picks it)
 template <int CHUNK, int STAGES>
 constexpr size_t syrk_smem() { return (size_t)STAGES * 2 * CHUNK * kPanelDoubles * sizeof(double) + 64; }
 
@@ -142,17 +140,14 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 template <int kChunkPts, int kStages, int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS)
 schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entries,
-                  const int4* __restrict__ items, const int* __restrict__ order, double* __restrict__ partial) {
+                  const int4* __restrict__ items, double* __restrict__ partial) {
   constexpr int kOperandDoubles = kChunkPts * kPanelDoubles;       // one side of a stage
   constexpr int kStageDoubles = 2 * kOperandDoubles;               // row side | column side
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stage_base = reinterpret_cast<double*>(smem_raw);
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)kStages * kStageDoubles * sizeof(double));
 
-  // CTAs are dealt to the SMs in blockIdx order; `order` (optional) permutes the work items -- an experiment hook: walking
-  // the pairs by anti-diagonals (a + b) did not change the L2 hit rate (44 %) or the time (lm_solver.cu)
-  const int item_id = order ? order[blockIdx.x] : (int)blockIdx.x;
-  const int4 item = items[item_id];
+  const int4 item = items[blockIdx.x];
   const int beg = item.y, nchunks = item.z / kChunkPts;
   const bool diag = (item.w & 1) != 0;
   // off-diagonal items: which 2-frame halves of the column (A) / row (B) side are populated for EVERY entry
@@ -217,7 +212,7 @@ schur_syrk_kernel(const double* __restrict__ Phi, const int2* __restrict__ entri
   constexpr unsigned kLower = (1u << 0) | (1u << 3) | (1u << 4) | (1u << 6) | (1u << 7) | (1u << 8);
   constexpr unsigned kRows34 = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4);       // window (3, 0)
   constexpr unsigned kRows45 = (1u << 5) | (1u << 6) | (1u << 7) | (1u << 8);                   // window (3, 0)
-  double* out = partial + (long)item_id * kSub * kSub;
+  double* out = partial + (long)blockIdx.x * kSub * kSub;
   // ksplit: the warp only multiplies the chunks with (c & 1) == kphase -- the K-split of an item with two live
   // patches, whose other two warps would otherwise idle (13.7 % of the DMMAs but 23.5 % of the CTA time at C3); the
   // two halves of a patch are added in a fixed order through shared memory behind the loop.
@@ -428,29 +423,18 @@ void launch_phi_build(const SchurStructure& st, const ObsView& obs, const JacVie
   phi_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st, obs, jv, ne);
 }
 
-template <int CHUNK, int STAGES, int MIN_CTAS>
-static void launch_syrk_variant(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
-  static bool seen[64] = {};
-  constexpr size_t smem = syrk_smem<CHUNK, STAGES>();
-  if (first_use_on_device(seen))
-    cudaFuncSetAttribute(schur_syrk_kernel<CHUNK, STAGES, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  schur_syrk_kernel<CHUNK, STAGES, MIN_CTAS><<<st.n_items, 128, smem, s>>>(ne.Phi, st.entries, st.items, st.item_order, ne.partial);
-}
+// Pipeline shape: 8-point chunks, a 2-stage ring, 5 CTAs per SM.  Measured at C3 (profiles/r02_notes.md): <8,3,3> 2.16 ms
+// (round 1's shape), <8,2,5> 1.85, <4,3,5> 1.99, <4,4,5> 1.97, <4,2,6> 1.91, <4,2,7> 1.92, <4,3,6> 1.93: the number of live warps
+// per SM sub-partition, not the ring depth, is what keeps the FP64 pipe fed.
+constexpr int kSyrkChunk = 8, kSyrkStages = 2, kSyrkCtasPerSm = 5;
 
 void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s) {
   if (st.n_items <= 0) return;
-  static const int var = [] { const char* e = getenv("RSBA_CUDA_SYRK_VAR"); return e ? atoi(e) : 0; }();   // (experiment hook)
-  // measured at C3 (profiles/r02_notes.md): <8,3,3> 2.16 ms (round 1's shape), <8,2,5> 1.85, <4,3,5> 1.99, <4,4,5> 1.97:
-  // warps per SM sub-partition, not ring depth, is what keeps the FP64 pipe fed
-  switch (var) {
-    case 1: launch_syrk_variant<8, 3, 3>(st, ne, s); break;
-    case 2: launch_syrk_variant<4, 3, 5>(st, ne, s); break;
-    case 3: launch_syrk_variant<4, 4, 5>(st, ne, s); break;
-    case 5: launch_syrk_variant<4, 2, 6>(st, ne, s); break;
-    case 6: launch_syrk_variant<4, 2, 7>(st, ne, s); break;
-    case 7: launch_syrk_variant<4, 3, 6>(st, ne, s); break;
-    default: launch_syrk_variant<8, 2, 5>(st, ne, s); break;
-  }
+  static bool seen[64] = {};
+  constexpr size_t smem = syrk_smem<kSyrkChunk, kSyrkStages>();
+  auto kernel = schur_syrk_kernel<kSyrkChunk, kSyrkStages, kSyrkCtasPerSm>;
+  if (first_use_on_device(seen)) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kernel<<<st.n_items, 128, smem, s>>>(ne.Phi, st.entries, st.items, ne.partial);
 }
 
 void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, int cam_frame, double* S,

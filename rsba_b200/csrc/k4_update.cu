@@ -148,8 +148,8 @@ point_step_kernel(SchurStructure st, JacView jv,
   }
 }
 
-// The same back-substitution with one thread per observation over groups of whole points (k2_fused.cu's point_group_kernel
-// describes the grouping): the observation's term Jx^T (Jc delta_c) goes to shared memory, (component, point) pairs are
+// The same back-substitution with one thread per observation over GROUPS of whole points (host: greedy over the
+// point-major order, <= 256 observations and <= 128 points per CTA, ~10 points at C3; PointGroups in lm.cuh): the observation's term Jx^T (Jc delta_c) goes to shared memory, (component, point) pairs are
 // summed serially in observation order, one thread per point finishes.  Reads the point-major records coalesced.
 constexpr int kStepGroupThreads = 256;
 constexpr int kStepGroupMaxPoints = 128;

@@ -68,7 +68,6 @@ struct SchurStructure {
   // with the all-zero panel (index n_inc)
   int n_items;
   const int4* items;       // [n_items] (pair, first entry, entry count, A == B)
-  const int* item_order;   // [n_items] launch order of the work items (NULL = as stored): pairs by anti-diagonals a + b
   const int2* entries;     // (incidence on the row side B, incidence on the column side A)
   long n_entries;
   long n_cam_params;       // 12 * frames (rows of the last tile beyond it are padding)
@@ -82,17 +81,6 @@ constexpr int kPanelLd = kSub + 4;            // 48 rows + 4 pad: conflict-free 
 constexpr int kPanelDoubles = 3 * kPanelLd;   // one bulk copy of 1248 bytes
 constexpr int kSchurSegPoints = 512;
 constexpr int kPointRec = 12;
-
-// device view of the tile-pair regrouping of the SYRK (structure.cuh; k2_schur2.cu)
-struct Syrk2View {
-  const int4* items;              // (slot, first entry, entry count, diagonal tile pair)
-  const int4* entries;            // (row-side incidences of sub-tiles 2B, 2B+1 | column-side 2A, 2A+1); n_inc = absent
-  const unsigned char* chunk_mask;   // per 4-entry chunk: populated 2-frame halves, column side | row side << 4
-  const int* pair_tp;             // [sub-tile pairs] tile pair of the pair
-  const int* tp_item_ptr;         // [tile pairs + 1] slots of the tile pair's work items
-  double* partial;                // [n_items][4 quadrants][48 x 48]
-  int n_items;
-};
 
 struct NormalEq {
   // unscaled blocks of J^T J and J^T r
@@ -145,8 +133,8 @@ void launch_frame_reduce(const SchurStructure& st, NormalEq ne, int n_frames, cu
 // filled once per scene by launch_pack_point_major)
 size_t point_pass_record_bytes();
 void launch_pack_point_major(const SchurStructure& st, const ObsView& obs, long n, void* packed, cudaStream_t s);
-// Groups of whole points for the thread-per-observation form of the point pass: groups[g] = (first point, one past the
-// last), <= 256 observations and <= 128 points each; big_ids = the points with more than 256 observations.
+// Groups of whole points for the thread-per-observation back-substitution (k4_update.cu): groups[g] = (first point, one
+// past the last), <= 256 observations and <= 128 points each; big_ids = the points with more than 256 observations.
 struct PointGroups {
   const int2* groups = nullptr;
   int n_groups = 0;
@@ -154,11 +142,9 @@ struct PointGroups {
   int n_big = 0;
 };
 constexpr int kPointGroupObs = 256, kPointGroupPoints = 128;
-// (res_pt: [N][2] scratch for the residuals in point-major order)
-void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, long n_obs, const double* poses,
+void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, const double* poses,
                        const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
-                       double* rec_pt, double* tau_pt, double* xt, double* res_pt, bool write_phi /* Schur panel rows */,
-                       const PointGroups& pg, cudaStream_t s);
+                       double* rec_pt, double* tau_pt, double* xt, bool write_phi /* Schur panel rows */, cudaStream_t s);
 void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,
                        const double* xt, NormalEq ne, double* cost_partials, int* invalid_count, cudaStream_t s);
 // n_frames > 0: the camera parameters; points: the owned points (two calls: the point part runs before the
@@ -193,9 +179,6 @@ void launch_schur_syrk(const SchurStructure& st, NormalEq ne, cudaStream_t s);
 // cam_frame: index of the intrinsics pseudo-frame (uncalibrated variant) or -1
 void launch_schur_reduce(const SchurStructure& st, NormalEq ne, const PriorView& pv, int cam_frame, double* S,
                          const int* tile_slot, int n_tiles, cudaStream_t s);
-void launch_schur_syrk2(const SchurStructure& st, const Syrk2View& sv, NormalEq ne, cudaStream_t s);
-void launch_schur_reduce2(const SchurStructure& st, const Syrk2View& sv, NormalEq ne, const PriorView& pv, int cam_frame,
-                          double* S, const int* tile_slot, int n_tiles, cudaStream_t s);
 // after the (optional) all-reduce: Jacobi scaling, LM diagonal, constant rows, padding; d2_c and rhs
 struct TileSchedule;
 void launch_schur_finalize(const SchurStructure& st, NormalEq ne, LmOptionsDev o, double* S,

@@ -30,15 +30,8 @@ struct LmState {
   DeviceBuffer<unsigned char> slot_cnt, point_owned;
   DeviceBuffer<int> owned_ids;
   DeviceBuffer<int4> items;
-  DeviceBuffer<int> item_order;
   DeviceBuffer<int2> entries;
-  // the SYRK by Cholesky-tile pairs (k2_schur2.cu; RSBA_CUDA_SYRK=1 selects the sub-tile-pair kernel of k2_schur.cu)
-  bool syrk2 = false;
-  DeviceBuffer<int4> items2, entries2;
-  DeviceBuffer<unsigned char> chunk_mask2;
-  DeviceBuffer<int> pair_tp, tp_item_ptr;
-  DeviceBuffer<double> partial2;
-  Syrk2View sv{};
+
   DeviceBuffer<int2> nz_tiles, trsm;
   DeviceBuffer<int4> upd;
   DeviceBuffer<int> tile_slot, row_ptr, rows, lrow_ptr, lrow_cols, panels;
@@ -67,7 +60,7 @@ struct LmState {
   // K1 -> point_blocks -> frame_blocks sequence, which the uncalibrated variant always uses)
   bool fused = false;
   DeviceBuffer<double> rec_pt, xt;        // point-major compact records [N][12]; (X_p | t_p) [P][6]
-  DeviceBuffer<int2> pt_groups;           // thread-per-observation point pass: groups of whole points (lm.cuh)
+  DeviceBuffer<int2> pt_groups;           // thread-per-observation back-substitution: groups of whole points (lm.cuh)
   DeviceBuffer<int> pt_big;
   PointGroups pg{};
   // S is followed by the tail  gc | wf | diagB | misc  -- one buffer, one all-reduce (multi-GPU)
@@ -140,7 +133,6 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   topo.g_obs_frame = h->g_obs_frame.data(); topo.g_obs_point = h->g_obs_point.data();
   topo.dense = dense; topo.reorder = h->reorder_tiles;
   topo.sparse_keys = getenv("RSBA_CUDA_SPARSE_KEYS") != nullptr;   // (env: test hook)
-  { const char* e = getenv("RSBA_CUDA_SYRK"); topo.tile_pair_lists = e && e[0] == '2'; }
   HostStructure hs;
   {
     std::string err;
@@ -163,31 +155,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   UP(inc_point, hs.inc_point); UP(inc_tile, hs.inc_tile); UP(slot_beg, hs.slot_beg); UP(slot_cnt, hs.slot_cnt);
   UP(obs_phi_off, hs.obs_phi_off); UP(dup_inc, hs.dup_inc); UP(cam_inc, hs.cam_inc);
   UP(pair_a, hs.pair_a); UP(pair_b, hs.pair_b);
-  {
-    // measured (profiles/r02_notes.md): the tile-pair regrouping halves the panel fill but loses more to idle warps
-    // (C3 2.40 vs 2.22 ms, scattered tracks 35 vs 18 ms) -- it stays an experiment, RSBA_CUDA_SYRK=2
-    const char* e = getenv("RSBA_CUDA_SYRK");
-    lm->syrk2 = e && e[0] == '2';
-  }
-  if (lm->syrk2) {
-    UP(items2, hs.items2); UP(entries2, hs.entries2); UP(chunk_mask2, hs.chunk_mask2); UP(pair_tp, hs.pair_tp);
-    UP(tp_item_ptr, hs.tp_item_ptr);
-  } else {
-    UP(pair_item_ptr, hs.pair_item_ptr); UP(items, hs.items); UP(entries, hs.entries);
-    // (experiment hook) RSBA_CUDA_SYRK_ORDER=1: launch the work items by anti-diagonals a + b instead of pair-major --
-    // measured: DRAM traffic 5.25 -> 5.16 GB, L2 hit rate 44.1 -> 44.7 %, 1.850 -> 1.851 ms: no effect, off by default
-    const char* eo = getenv("RSBA_CUDA_SYRK_ORDER");
-    if (eo && eo[0] == '1' && hs.n_items > 0) {
-      std::vector<int> order(hs.n_items);
-      for (int k = 0; k < hs.n_items; ++k) order[k] = k;
-      std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-        const int px = hs.items[x].x, py = hs.items[y].x;
-        const int sx = hs.pair_a[px] + hs.pair_b[px], sy = hs.pair_a[py] + hs.pair_b[py];
-        return sx != sy ? sx < sy : hs.pair_a[px] < hs.pair_a[py];
-      });
-      UP(item_order, order);
-    }
-  }
+  UP(pair_item_ptr, hs.pair_item_ptr); UP(items, hs.items); UP(entries, hs.entries);
   UP(tile_pos, plan.tile_pos); UP(pos_tile, plan.pos_tile); UP(point_owned, h->point_owned);
   UP(nz_tiles, plan.nz_tiles); UP(upd, plan.upd); UP(tile_slot, plan.tile_slot);
   UP(row_ptr, plan.row_ptr); UP(rows, plan.rows); UP(lrow_ptr, plan.lrow_ptr); UP(lrow_cols, plan.lrow_cols);
@@ -227,7 +195,6 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   st.cam_inc = lm->cam_inc.ptr;
   st.n_pairs = (int)pair_a.size(); st.pair_a = lm->pair_a.ptr; st.pair_b = lm->pair_b.ptr;
   st.pair_item_ptr = lm->pair_item_ptr.ptr; st.n_items = n_items; st.items = lm->items.ptr;
-  st.item_order = lm->item_order.ptr;
   st.entries = lm->entries.ptr; st.n_entries = (long)hs.entries.size(); st.tile_pos = lm->tile_pos.ptr;
   st.pos_tile = lm->pos_tile.ptr; st.n_cam_params = 12L * Fc;
   lm->free_cam = free_cam;
@@ -291,15 +258,7 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
   }
   RSBA_CUDA_TRY(lm->Phi.resize((size_t)(n_inc + 1) * kPanelDoubles));
   RSBA_CUDA_TRY(cudaMemsetAsync(lm->Phi.ptr, 0, lm->Phi.bytes(), s));   // pad columns + the zero panel
-  if (lm->syrk2) {
-    const int n2 = hs.tp_item_ptr.empty() ? 0 : hs.tp_item_ptr.back();
-    RSBA_CUDA_TRY(lm->partial2.resize((size_t)std::max(n2, 1) * 4 * kSub * kSub));
-    RSBA_CUDA_TRY(lm->partial.resize(1));
-    lm->sv = Syrk2View{lm->items2.ptr, lm->entries2.ptr, lm->chunk_mask2.ptr, lm->pair_tp.ptr, lm->tp_item_ptr.ptr,
-                       lm->partial2.ptr, n2};
-  } else {
-    RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kSub * kSub));
-  }
+  RSBA_CUDA_TRY(lm->partial.resize((size_t)std::max(n_items, 1) * kSub * kSub));
   RSBA_CUDA_TRY(lm->scale_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->scale_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->d2_c.resize(Fz * 12)); RSBA_CUDA_TRY(lm->d2_p.resize(Pz * 3));
   RSBA_CUDA_TRY(lm->partials.resize(std::max<size_t>(chunk_frame.size(), 1) * 168));
@@ -410,8 +369,8 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     // point: rejected steps are rare, and nothing of the old Jacobian is kept in observation order)
     cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), s);
     stage_begin(h, kStageJacobian);
-    launch_point_pass(h->cm, lm->st, lm->pt_packed.ptr, h->n_obs, h->d_poses.ptr, h->d_points.ptr, lm->ne, o, compute_scale,
-                      opt.jacobi_scaling != 0, lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, h->d_res.ptr, want_S, lm->pg, s);
+    launch_point_pass(h->cm, lm->st, lm->pt_packed.ptr, h->d_poses.ptr, h->d_points.ptr, lm->ne, o, compute_scale,
+                      opt.jacobi_scaling != 0, lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, want_S, s);
     stage_end(h, kStageJacobian);
     stage_begin(h, kStageSchur);
     stage_begin(h, kStageFrameBlocks);
@@ -420,7 +379,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     stage_end(h, kStageFrameBlocks);
     int rc = eval_tail(h, true, h->d_poses.ptr, lm->st.n_chunks);   // priors' residuals + cost -> d_scalars[0]
     if (rc) return rc;
-    h->launches += 5;
+    h->launches += 4;
   } else {
   stage_begin(h, kStageSchur);
   if (new_jacobian && !lm->pt_major_valid) {   // tau is a constant of the observation: once per solve
@@ -468,13 +427,11 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     h->launches += 1;
   }
   stage_begin(h, kStageSchurSyrk);
-  if (lm->syrk2) launch_schur_syrk2(lm->st, lm->sv, lm->ne, s);
-  else launch_schur_syrk(lm->st, lm->ne, s);
+  launch_schur_syrk(lm->st, lm->ne, s);
   stage_end(h, kStageSchurSyrk);
   stage_begin(h, kStageSchurReduce);
   const int cam_frame_idx = lm->n_cam_frames > h->n_frames ? h->n_frames : -1;
-  if (lm->syrk2) launch_schur_reduce2(lm->st, lm->sv, lm->ne, pvr, cam_frame_idx, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
-  else launch_schur_reduce(lm->st, lm->ne, pvr, cam_frame_idx, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
+  launch_schur_reduce(lm->st, lm->ne, pvr, cam_frame_idx, lm->S.ptr, lm->ts.tile_slot, lm->ts.n_tiles, s);
   stage_end(h, kStageSchurReduce);
   h->launches += 4;
   }

@@ -326,139 +326,6 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
   out->n_items = (int)pair_item_ptr.back();
   if (items.empty()) items.push_back(make_int4(0, 0, 0, 1));
   lap("entry lists");
-  // ---- the tile-pair regrouping of the same products (structure.cuh; k2_schur2.cu)
-  if (sc.tile_pair_lists) {
-    std::vector<int>& tp_a = out->tp_a;
-    std::vector<int>& tp_b = out->tp_b;
-    std::vector<int>& pair_tp = out->pair_tp;
-    tp_a.clear(); tp_b.clear();
-    pair_tp.assign(n_pairs_h, 0);
-    // sub-tile pairs are sorted by (a, b): collect the distinct (a/2, b/2) and sort them
-    std::vector<long> tkeys;
-    tkeys.reserve(n_pairs_h);
-    for (int q = 0; q < n_pairs_h; ++q) tkeys.push_back((long)(pair_a[q] / 2) * T + pair_b[q] / 2);
-    std::vector<long> tsorted(tkeys);
-    std::sort(tsorted.begin(), tsorted.end());
-    tsorted.erase(std::unique(tsorted.begin(), tsorted.end()), tsorted.end());
-    const int n_tp = (int)tsorted.size();
-    auto tp_of = [&](long key) { return (int)(std::lower_bound(tsorted.begin(), tsorted.end(), key) - tsorted.begin()); };
-    for (int q = 0; q < n_pairs_h; ++q) pair_tp[q] = tp_of(tkeys[q]);
-    for (long k : tsorted) { tp_a.push_back((int)(k / T)); tp_b.push_back((int)(k % T)); }
-    const bool dense_tp = (long)T * T <= (1L << 24);
-    std::vector<int> tp_table;
-    if (dense_tp) {
-      tp_table.assign((size_t)T * T, -1);
-      for (int q = 0; q < n_tp; ++q) tp_table[(size_t)tsorted[q]] = q;
-    }
-    auto tp_lookup = [&](int A, int B) { return dense_tp ? tp_table[(size_t)A * T + B] : tp_of((long)A * T + B); };
-    // the tiles of a point: (incidence of sub-tile 2A or n_inc, of 2A+1 or n_inc, half mask of the 8 frames)
-    struct PtTile { int tile, i0, i1; unsigned half; };
-    auto tiles_of_point = [&](int p, PtTile* tl) {
-      int n = 0;
-      for (int x = pt_inc_ptr[p]; x < pt_inc_ptr[p + 1]; ++x) {
-        const int sub = inc_tile[x], A = sub / 2;
-        if (n == 0 || tl[n - 1].tile != A) { tl[n].tile = A; tl[n].i0 = tl[n].i1 = n_inc; tl[n].half = 0; ++n; }
-        const unsigned hm = inc_half[x] ? inc_half[x] : 3u;
-        if (sub & 1) { tl[n - 1].i1 = x; tl[n - 1].half |= hm << 2; }
-        else { tl[n - 1].i0 = x; tl[n - 1].half |= hm; }
-      }
-      return n;
-    };
-    int max_tiles = 1;
-    for (int p = 0; p < P; ++p) max_tiles = std::max(max_tiles, pt_inc_ptr[p + 1] - pt_inc_ptr[p]);
-    // pass 1: entries per (tile pair, thread) -> write cursors (a tile pair's entries stay in point order)
-    std::vector<std::vector<long>> cnt1(pool.n);
-    pool.run([&](int t) {
-      cnt1[t].assign(n_tp + 1, 0);
-      std::vector<PtTile> tl(max_tiles);
-      for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p) {
-        const int n = tiles_of_point(p, tl.data());
-        for (int x = 0; x < n; ++x)
-          for (int y = x; y < n; ++y) cnt1[t][tp_lookup(tl[x].tile, tl[y].tile)]++;
-      }
-    });
-    std::vector<long> raw_beg(n_tp + 1, 0);
-    {
-      long run = 0;
-      for (int q = 0; q < n_tp; ++q) {
-        raw_beg[q] = run;
-        for (int t = 0; t < pool.n; ++t) { const long c = cnt1[t][q]; cnt1[t][q] = run; run += c; }
-      }
-      raw_beg[n_tp] = run;
-    }
-    // pass 2: the raw (unsorted by class) entries
-    HostVec<int4> raw_e((size_t)std::max<long>(raw_beg[n_tp], 1));
-    HostVec<unsigned char> raw_c((size_t)std::max<long>(raw_beg[n_tp], 1));
-    pool.run([&](int t) {
-      std::vector<PtTile> tl(max_tiles);
-      long* cur = cnt1[t].data();
-      for (int p = pt_cut[t]; p < pt_cut[t + 1]; ++p) {
-        const int n = tiles_of_point(p, tl.data());
-        for (int x = 0; x < n; ++x)
-          for (int y = x; y < n; ++y) {
-            const long at = cur[tp_lookup(tl[x].tile, tl[y].tile)]++;
-            raw_e[at] = make_int4(tl[y].i0, tl[y].i1, tl[x].i0, tl[x].i1);   // rows = the later tile, columns = the earlier
-            raw_c[at] = (unsigned char)(tl[x].half | (tl[y].half << 4));
-          }
-      }
-    });
-    // pass 3: class histogram of every tile pair -> padded sizes, items
-    std::vector<long> padded(n_tp + 1, 0);
-    {
-      const int nt = pool.n;
-      pool.run([&](int t) {
-        for (int q = (int)((long)n_tp * t / nt); q < (int)((long)n_tp * (t + 1) / nt); ++q) {
-          long hist[256] = {0};
-          for (long x = raw_beg[q]; x < raw_beg[q + 1]; ++x) hist[raw_c[x]]++;
-          long tot = 0;
-          for (int c = 0; c < 256; ++c) tot += (hist[c] + kSyrk2Chunk - 1) / kSyrk2Chunk * kSyrk2Chunk;
-          padded[q] = tot;
-        }
-      });
-      long run = 0;
-      for (int q = 0; q <= n_tp; ++q) { const long c = q < n_tp ? padded[q] : 0; padded[q] = run; run += c; }
-      if (run > 2147483647L) return fail(error, RSBA_ERR_INVALID_ARGUMENT, "Schur entry list exceeds 2^31");
-    }
-    std::vector<int>& tp_item_ptr = out->tp_item_ptr;
-    std::vector<int4>& items2 = out->items2;
-    tp_item_ptr.assign(n_tp + 1, 0);
-    items2.clear();
-    for (int q = 0; q < n_tp; ++q) {
-      tp_item_ptr[q] = (int)items2.size();
-      const int dg = tp_a[q] == tp_b[q] ? 1 : 0;
-      for (long b = padded[q]; b < padded[q + 1]; b += kSyrk2SegPoints)
-        items2.push_back(make_int4((int)items2.size(), (int)b, (int)std::min<long>(kSyrk2SegPoints, padded[q + 1] - b), dg));
-    }
-    tp_item_ptr[n_tp] = (int)items2.size();
-    // longest first: the CTAs are dealt to the SMs in this order, the short tails of the pairs fill the end
-    std::stable_sort(items2.begin(), items2.end(), [](const int4& a, const int4& b) { return a.z > b.z; });
-    // pass 4: stable scatter by class into the padded lists
-    HostVec<int4>& entries2 = out->entries2;
-    HostVec<unsigned char>& chunk_mask2 = out->chunk_mask2;
-    const long n_e2 = padded[n_tp];
-    pool.resize_fill(entries2, (size_t)std::max<long>(n_e2, 1), make_int4(n_inc, n_inc, n_inc, n_inc));
-    pool.resize_fill(chunk_mask2, (size_t)std::max<long>(n_e2 / kSyrk2Chunk, 1), (unsigned char)0);
-    {
-      const int nt = pool.n;
-      pool.run([&](int t) {
-        for (int q = (int)((long)n_tp * t / nt); q < (int)((long)n_tp * (t + 1) / nt); ++q) {
-          long cur[256];
-          long hist[256] = {0};
-          for (long x = raw_beg[q]; x < raw_beg[q + 1]; ++x) hist[raw_c[x]]++;
-          long at = padded[q];
-          for (int c = 0; c < 256; ++c) {
-            cur[c] = at;
-            const long pc = (hist[c] + kSyrk2Chunk - 1) / kSyrk2Chunk * kSyrk2Chunk;
-            for (long k = at / kSyrk2Chunk; k < (at + pc) / kSyrk2Chunk; ++k) chunk_mask2[k] = (unsigned char)c;
-            at += pc;
-          }
-          for (long x = raw_beg[q]; x < raw_beg[q + 1]; ++x) entries2[cur[raw_c[x]]++] = raw_e[x];
-        }
-      });
-    }
-    if (items2.empty()) items2.push_back(make_int4(0, 0, 0, 1));
-  }
-  lap("tile-pair lists");
   // ---- ordering, symbolic factorisation, elimination levels (tile_plan.cu)
   // (the plan is a function of the WHOLE scene, so every rank of a multi-GPU run derives the same one)
   TilePlan& plan = out->plan;
@@ -560,7 +427,6 @@ int rsba_cuda_analyze_structure(long n_obs, const int* obs_frame, const int* obs
   }
   sc.n_obs_global = n_obs; sc.g_obs_frame = obs_frame; sc.g_obs_point = obs_point;
   sc.dense = dense != 0; sc.reorder = reorder != 0; sc.sparse_keys = sparse_keys != 0;
-  sc.tile_pair_lists = true;   // the device-free API hands out every list
   rsba_structure* s = new rsba_structure;
   if (world_size > 1) {
     // this rank's share as materialize_local_share (problem.cu) forms it: all observations of the points it owns
@@ -616,7 +482,6 @@ long rsba_cuda_structure_array(const rsba_structure* s, const char* name, const 
   RSBA_ARR(frame_chunk_ptr); RSBA_ARR(inc_point); RSBA_ARR(inc_tile); RSBA_ARR(slot_beg); RSBA_ARR(slot_cnt);
   RSBA_ARR(pt_inc_ptr); RSBA_ARR(cam_inc); RSBA_ARR(inc_half); RSBA_ARR(obs_phi_off); RSBA_ARR(dup_inc);
   RSBA_ARR(pair_a); RSBA_ARR(pair_b); RSBA_ARR(pair_item_ptr); RSBA_ARR(items); RSBA_ARR(entries); RSBA_ARR(fwd_slot);
-  RSBA_ARR(tp_a); RSBA_ARR(tp_b); RSBA_ARR(tp_item_ptr); RSBA_ARR(pair_tp); RSBA_ARR(items2); RSBA_ARR(entries2); RSBA_ARR(chunk_mask2);
 #undef RSBA_ARR
 #define RSBA_PLAN(field) if (n == "plan." #field) return give(h.plan.field)
   RSBA_PLAN(tile_pos); RSBA_PLAN(pos_tile); RSBA_PLAN(nz_tiles); RSBA_PLAN(tile_slot); RSBA_PLAN(panels);

@@ -31,12 +31,8 @@ struct SceneTopology {
   const int* g_obs_frame = nullptr;
   const int* g_obs_point = nullptr;
   bool dense = false, reorder = true, sparse_keys = false;
-  bool tile_pair_lists = false;   // also build items2 / entries2 (the experimental SYRK by Cholesky-tile pairs)
   int n_cam_frames() const { return n_frames + ((free_cam || free_ratio) ? 1 : 0); }
 };
-
-constexpr int kSyrk2Chunk = 4;        // points per pipeline stage of schur_syrk2_kernel
-constexpr int kSyrk2SegPoints = 512;  // entries per work item
 
 struct HostStructure {
   std::vector<int> pt_ptr;                                           // point-major CSR
@@ -54,16 +50,6 @@ struct HostStructure {
   std::vector<int4> items;
   HostVec<int2> entries;
   int n_items = 0;
-  // ---- the same SYRK regrouped by CHOLESKY-TILE pairs (2 x 2 sub-tile pairs from <= 4 panels per point): what
-  // schur_syrk2_kernel (k2_schur2.cu) executes.  entries2 = (row-side incidences of sub-tiles 2B, 2B+1 | column-side
-  // 2A, 2A+1), n_inc = absent (the all-zero panel); runs of equal class (which 2-frame halves of the 8 + 8 frames
-  // are populated: mask A | mask B << 4) are padded to multiples of kSyrk2Chunk, chunk_mask2 has one class per chunk.
-  // items2 = (slot in the partial buffer, first entry, entry count, 1 if A == B), sorted by decreasing length (the
-  // order CTAs are dealt to the SMs); the items of tile pair q own slots tp_item_ptr[q] .. tp_item_ptr[q+1].
-  std::vector<int> tp_a, tp_b, tp_item_ptr, pair_tp;   // pair_tp[sub-tile pair] = its tile pair
-  std::vector<int4> items2;
-  HostVec<int4> entries2;
-  HostVec<unsigned char> chunk_mask2;
   TilePlan plan;
   std::vector<int> fwd_slot;   // where each trsm tile (i, k) leaves its forward-substitution term in row i's list
 };

@@ -75,74 +75,6 @@ def execute_work_lists(st, Phi):
     return blocks, n_real_entries, pos
 
 
-def execute_tile_pair_lists(st, Phi):
-    """The tile-pair regrouping (items2 / entries2 / chunk_mask2) executed the way schur_syrk2_kernel + schur_reduce
-    do: every work item leaves up to four 48 x 48 quadrant partials (one per sub-tile pair of the Cholesky-tile
-    pair), the kernel computes only the 24 x 24 patches whose 2-frame halves the chunk's class mask marks populated
-    and only the sub-tile pairs with a <= b; the reduction sums the items of the pair's tile pair in slot order."""
-    CH = 4
-    n_inc = st["n_inc"]
-    it = st["inc_tile"]
-    tpa, tpb, tptr, ptp = st["tp_a"], st["tp_b"], st["tp_item_ptr"], st["pair_tp"]
-    items2, e2, cm = st["items2"], st["entries2"], st["chunk_mask2"]
-    pa, pb = st["pair_a"], st["pair_b"]
-    T = st["T"]
-    assert np.all(tpa <= tpb) and np.all(np.diff(tpa.astype(np.int64) * T + tpb) > 0)
-    assert tptr.size == tpa.size + 1
-    n_items = int(tptr[-1])
-    part = np.zeros((max(n_items, 1), 4, SUB * FP, SUB * FP))
-    slots = sorted(int(v[0]) for v in items2[:n_items]) if n_items else []
-    assert slots == list(range(n_items)), "every slot has exactly one work item"
-    if n_items:
-        assert np.all(np.diff(items2[:n_items, 2]) <= 0), "longest items first"
-    n_real = 0
-    covered = np.zeros(e2.shape[0], bool)
-    for j in range(n_items):
-        slot, beg, cnt, dg = (int(v) for v in items2[j])
-        q = int(np.searchsorted(tptr, slot, side="right") - 1)
-        assert dg == int(tpa[q] == tpb[q]) and cnt % CH == 0 and 0 < cnt <= SEG
-        assert not covered[beg:beg + cnt].any()
-        covered[beg:beg + cnt] = True
-        for e in range(beg, beg + cnt):
-            mask = int(cm[e // CH])
-            mA, mB = mask & 15, mask >> 4
-            b0, b1, a0, a1 = (int(v) for v in e2[e])
-            if (b0, b1, a0, a1) == (n_inc,) * 4:
-                continue                                   # padding
-            n_real += 1
-            for inc, sub in ((b0, 2 * tpb[q]), (b1, 2 * tpb[q] + 1), (a0, 2 * tpa[q]), (a1, 2 * tpa[q] + 1)):
-                assert inc == n_inc or it[inc] == sub
-            # what the class mask marks empty must really be empty (the kernel never reads it)
-            for inc, m in ((b0, mB & 3), (b1, mB >> 2), (a0, mA & 3), (a1, mA >> 2)):
-                if inc != n_inc:
-                    for hf in range(2):
-                        if not (m >> hf & 1):
-                            assert not Phi[inc][24 * hf:24 * hf + 24].any()
-                else:
-                    assert m == 0
-            B = [b0, b1]
-            A = [a0, a1]
-            for bi in range(2):
-                for aj in range(2):
-                    if dg and aj > bi:
-                        continue                           # sub-tile pairs with a <= b only
-                    hb, ha = (mB >> 2 * bi) & 3, (mA >> 2 * aj) & 3
-                    if not hb or not ha:
-                        continue
-                    rows = np.concatenate([np.arange(24) + 24 * k for k in range(2) if hb >> k & 1])
-                    cols = np.concatenate([np.arange(24) + 24 * k for k in range(2) if ha >> k & 1])
-                    part[slot, 2 * bi + aj][np.ix_(rows, cols)] += Phi[B[bi]][rows] @ Phi[A[aj]][cols].T
-    assert covered[:e2.shape[0] if n_items else 0].all() or not n_items
-    blocks = {}
-    for pr in range(pa.size):
-        q = int(ptp[pr])
-        assert tpa[q] == pa[pr] // 2 and tpb[q] == pb[pr] // 2
-        quad = (int(pb[pr]) & 1) * 2 + (int(pa[pr]) & 1)
-        blocks[(int(pa[pr]), int(pb[pr]))] = part[tptr[q]:tptr[q + 1], quad].sum(axis=0) if tptr[q + 1] > tptr[q] \
-            else np.zeros((SUB * FP, SUB * FP))
-    return blocks, n_real
-
-
 def check_structure(fr, pt, F, P, const_point=None, free_cam=False, free_ratio=False, priors=(), seed=0, **kw):
     const_point = np.zeros(P, np.uint8) if const_point is None else const_point
     pf = [a for a, _ in priors]
@@ -241,25 +173,6 @@ def check_structure(fr, pt, F, P, const_point=None, free_cam=False, free_ratio=F
     assert n_real_entries == sum((pip[p + 1] - pip[p]) * (pip[p + 1] - pip[p] + 1) // 2 for p in range(P))
     assert entries.shape[0] == max(pos, 1)
 
-    # ---- the same products regrouped by Cholesky-tile pairs (what schur_syrk2_kernel executes)
-    direct2 = {}
-    n_tile_entries = 0
-    for p in range(P):
-        for x in range(pip[p], pip[p + 1]):
-            for y in range(x, pip[p + 1]):
-                key = (int(it[x]), int(it[y]))
-                direct2[key] = direct2.get(key, 0) + Phi[y] @ Phi[x].T
-        nt = len(set(int(t) // 2 for t in it[pip[p]:pip[p + 1]]))
-        n_tile_entries += nt * (nt + 1) // 2
-    blocks2, n_real2 = execute_tile_pair_lists(st, Phi)
-    for (a, b), acc in blocks2.items():
-        want = direct2.pop((a, b), np.zeros_like(acc))
-        if a == b:
-            acc, want = np.tril(acc), np.tril(want)
-        assert np.allclose(acc, want, rtol=1e-12, atol=1e-12), ("tile-pair lists", a, b)
-    assert not direct2
-    assert n_real2 == n_tile_entries
-
     # ---- every diagonal sub-tile with a frame, and every prior coupling, is a pair (even without a Schur term)
     have = set(zip(pa.tolist(), pb.tolist()))
     for t in range((Fc + SUB - 1) // SUB):
@@ -315,8 +228,6 @@ def test_structure_long_tracks_split_into_segments_of_512_entries():
     pt = np.tile(np.arange(P, dtype=np.int32), F)
     st = check_structure(fr, pt, F, P)
     assert st["n_items"] == 3 * 2 and np.array_equal(st["items"][:, 2], [512, 192] * 3)
-    # tile-pair lists: one Cholesky-tile pair (0, 0), 700 entries of one class -> two work items, longest first
-    assert np.array_equal(st["items2"][:, 2], [512, 188]) and np.array_equal(st["items2"][:, 0], [0, 1])
 
 
 def test_structure_sparse_key_path_is_identical():
