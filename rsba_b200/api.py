@@ -743,6 +743,7 @@ _STRUCTURE_ARRAYS = {
     "plan.panel_ptr": (np.int32, 1), "plan.trsm": (np.int32, 2), "plan.trsm_ptr": (np.int32, 1),
     "plan.upd": (np.int32, 4), "plan.lrow_ptr": (np.int32, 1), "plan.lrow_cols": (np.int32, 1),
     "local_ids": (np.int64, 1), "point_owned": (np.uint8, 1),
+    "point_groups": (np.int32, 2), "point_big": (np.int32, 1),
 }
 
 

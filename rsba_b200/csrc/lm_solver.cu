@@ -230,27 +230,13 @@ int build_structure(rsba_problem* h, LmState* lm, bool dense) {
     RSBA_CUDA_TRY(lm->rec_pt.resize(Nz * kJacCompact));
     RSBA_CUDA_TRY(lm->xt.resize(Pz * 6));
     RSBA_CUDA_TRY(cudaMemsetAsync(lm->xt.ptr, 0, lm->xt.bytes(), s));
-    {   // groups of whole points: <= 256 observations, <= 128 points; longer tracks go to the warp-per-point kernel
-      std::vector<int2> groups;
+    {   // groups of whole points for the back-substitution (structure.cu); long tracks of OWNED points: warp-per-point
       std::vector<int> big;
-      int lo = 0;
-      long acc = 0;
-      auto flush = [&](int hi) { if (hi > lo) groups.push_back(make_int2(lo, hi)); lo = hi; acc = 0; };
-      for (int p = 0; p < P; ++p) {
-        const long n = hs.pt_ptr[p + 1] - hs.pt_ptr[p];
-        if (n > kPointGroupObs) {            // its observations sit between the neighbours': the group ends here
-          flush(p);
-          if (h->point_owned[p]) big.push_back(p);
-          lo = p + 1;
-          continue;
-        }
-        if (acc + n > kPointGroupObs || p - lo >= kPointGroupPoints) flush(p);
-        acc += n;
-      }
-      flush(P);
-      if ((rc = upload(lm->pt_groups, groups, s))) return rc;
+      for (int p : hs.point_big)
+        if (h->point_owned[p]) big.push_back(p);
+      if ((rc = upload(lm->pt_groups, hs.point_groups, s))) return rc;
       if ((rc = upload(lm->pt_big, big, s))) return rc;
-      lm->pg.groups = lm->pt_groups.ptr; lm->pg.n_groups = (int)groups.size();
+      lm->pg.groups = lm->pt_groups.ptr; lm->pg.n_groups = (int)hs.point_groups.size();
       lm->pg.big_ids = lm->pt_big.ptr; lm->pg.n_big = (int)big.size();
     }
     // the frames in point-major order are a constant of the scene (tau follows from the first point pass)

@@ -96,6 +96,27 @@ int analyze_structure(const SceneTopology& sc, HostStructure* out, std::string* 
     }
     for (int f = F; f <= Fc; ++f) frame_chunk_ptr[f] = (int)chunk_frame.size();   // the pseudo-frame has no observations
   }
+  // groups of whole points (their observations are one contiguous run of the point-major order)
+  {
+    std::vector<int2>& groups = out->point_groups;
+    std::vector<int>& big = out->point_big;
+    groups.clear(); big.clear();
+    int lo = 0;
+    long acc = 0;
+    auto flush = [&](int hi) { if (hi > lo) groups.push_back(make_int2(lo, hi)); lo = hi; acc = 0; };
+    for (int p = 0; p < P; ++p) {
+      const long n = pt_ptr[p + 1] - pt_ptr[p];
+      if (n > kPointGroupObs) {            // its observations sit between the neighbours': the group ends here
+        flush(p);
+        big.push_back(p);
+        lo = p + 1;
+        continue;
+      }
+      if (acc + n > kPointGroupObs || p - lo >= kPointGroupPoints) flush(p);
+      acc += n;
+    }
+    flush(P);
+  }
   lap("point CSR + frame chunks");
   // ---- Schur SYRK structure: (frame tile, point) incidences, tile pairs, work items
   const int T = (int)((12L * Fc + kTile - 1) / kTile);
@@ -482,6 +503,7 @@ long rsba_cuda_structure_array(const rsba_structure* s, const char* name, const 
   RSBA_ARR(frame_chunk_ptr); RSBA_ARR(inc_point); RSBA_ARR(inc_tile); RSBA_ARR(slot_beg); RSBA_ARR(slot_cnt);
   RSBA_ARR(pt_inc_ptr); RSBA_ARR(cam_inc); RSBA_ARR(inc_half); RSBA_ARR(obs_phi_off); RSBA_ARR(dup_inc);
   RSBA_ARR(pair_a); RSBA_ARR(pair_b); RSBA_ARR(pair_item_ptr); RSBA_ARR(items); RSBA_ARR(entries); RSBA_ARR(fwd_slot);
+  RSBA_ARR(point_groups); RSBA_ARR(point_big);
 #undef RSBA_ARR
 #define RSBA_PLAN(field) if (n == "plan." #field) return give(h.plan.field)
   RSBA_PLAN(tile_pos); RSBA_PLAN(pos_tile); RSBA_PLAN(nz_tiles); RSBA_PLAN(tile_slot); RSBA_PLAN(panels);

@@ -50,6 +50,11 @@ struct HostStructure {
   std::vector<int4> items;
   HostVec<int2> entries;
   int n_items = 0;
+  // groups of whole points for the thread-per-observation back-substitution (lm.cuh, PointGroups): (first point, one past
+  // the last), <= kPointGroupObs observations and <= kPointGroupPoints points each; point_big = the points with more
+  // observations than one group holds (they go through the warp-per-point kernel)
+  std::vector<int2> point_groups;
+  std::vector<int> point_big;
   TilePlan plan;
   std::vector<int> fwd_slot;   // where each trsm tile (i, k) leaves its forward-substitution term in row i's list
 };

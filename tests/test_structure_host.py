@@ -125,6 +125,18 @@ def check_structure(fr, pt, F, P, const_point=None, free_cam=False, free_ratio=F
                 assert sc_[i, fs] == len(mine)
                 assert sb[i, fs] == (mine[0] if mine else -1)
 
+    # ---- groups of whole points for the thread-per-observation back-substitution: every point in exactly one group or
+    # in the long-track list, <= 256 observations and <= 128 points per group
+    grp, big = st["point_groups"], st["point_big"]
+    counts = np.diff(st["pt_ptr"])
+    seen_pt = np.zeros(P, int)
+    for lo, hi in grp:
+        assert 0 <= lo < hi <= P and hi - lo <= 128 and counts[lo:hi].sum() <= 256
+        seen_pt[lo:hi] += 1
+    seen_pt[big] += 1
+    assert np.all(seen_pt == 1) and np.all(counts[big] > 256) and np.all(counts[seen_pt == 1][counts[seen_pt == 1] > 256] > 0)
+    assert set(big.tolist()) == set(np.nonzero(counts > 256)[0].tolist())
+
     # ---- where frame_blocks writes each observation's 12 panel rows
     dup = set(int(i) for i in st["dup_inc"])
     assert dup == set(int(i) for i in np.nonzero((sc_ > 1).any(axis=1))[0])
@@ -412,3 +424,17 @@ def test_k2_algorithm_over_the_real_work_lists_gives_the_restated_reduced_system
     rhs = np.where(act, sv * (gc - wf).reshape(-1), 0.0)
     assert np.linalg.norm(S - want["S"]) <= 1e-11 * np.linalg.norm(want["S"])
     assert np.linalg.norm(-rhs - want["rhs"]) <= 1e-11 * np.linalg.norm(want["rhs"])
+
+
+def test_point_groups_with_long_tracks_and_the_point_limit():
+    """A track longer than a group (300 observations of one point) goes to the long-track list and splits its
+    neighbours into two groups; 400 single-observation points need four groups of <= 128 points."""
+    F = 300
+    fr = np.concatenate([np.arange(5), np.arange(F), np.arange(7)]).astype(np.int32)
+    pt = np.concatenate([np.zeros(5), np.ones(F), np.full(7, 2)]).astype(np.int32)
+    order = np.argsort(fr, kind="stable")
+    st = api.analyze_structure(fr[order], pt[order], F, 3)
+    assert st["point_big"].tolist() == [1] and st["point_groups"].tolist() == [[0, 1], [2, 3]]
+    P = 400
+    st = api.analyze_structure(np.zeros(P, np.int32), np.arange(P, dtype=np.int32), 4, P)
+    assert st["point_groups"].tolist() == [[0, 128], [128, 256], [256, 384], [384, 400]] and st["point_big"].size == 0
