@@ -130,9 +130,10 @@ phi_cam_kernel(SchurStructure st, JacView jv, const double* __restrict__ jac_cam
     for (int o = 16; o > 0; o >>= 1) F[k] += __shfl_xor_sync(0xffffffffu, F[k], o);
   // rows 12*slot .. 12*slot+8 of the panel (k-major); rows 9..11 of the pseudo-frame stay zero
   double* dst = ne.Phi + (long)inc * kPanelDoubles + slot * kFrameParams;
+  if (lane == 0) {   // (one store per lane compiled to a jump table of 27 divergent paths)
 #pragma unroll
-  for (int k = 0; k < 27; ++k)
-    if (lane == k) dst[(k % 3) * kPanelLd + k / 3] = F[k];
+    for (int k = 0; k < 27; ++k) dst[(k % 3) * kPanelLd + k / 3] = F[k];
+  }
 }
 
 }  // namespace

@@ -171,23 +171,26 @@ point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __res
     t[2] = ci[2] * v[6] + ci[4] * v[7] + ci[5] * v[8];
     W[0] = s0 * m00; W[1] = s0 * m10; W[2] = s1 * m11; W[3] = s0 * m20; W[4] = s1 * m21; W[5] = s2 * m22;
   }
-  // per-point outputs, spread over the lanes (what K4, the norms and the dup / intrinsics kernels read)
+  // per-point outputs (what K4, the norms and the dup / intrinsics kernels read): every lane holds all of them and
+  // lane 0 stores them.  "lane k stores element k" compiles to jump tables -- ten divergent paths behind indirect
+  // branches per point (the same pattern cost K3's panel 800 cycles: profiles/r02_notes.md)
+  if (lane == 0) {
+    double2* c2 = reinterpret_cast<double2*>(ne.C + 6L * p);
+    double2* ci2 = reinterpret_cast<double2*>(ne.Cinv + 6L * p);
+    double2* mi2 = reinterpret_cast<double2*>(ne.Minv + 6L * p);
 #pragma unroll
-  for (int k = 0; k < 6; ++k)
-    if (lane == k) {
-      ne.C[6L * p + k] = v[k];
-      ne.Cinv[6L * p + k] = ci[k];
-      ne.Minv[6L * p + k] = mi[k];
+    for (int k = 0; k < 3; ++k) {
+      c2[k] = make_double2(v[2 * k], v[2 * k + 1]);
+      ci2[k] = make_double2(ci[2 * k], ci[2 * k + 1]);
+      mi2[k] = make_double2(mi[2 * k], mi[2 * k + 1]);
     }
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-    if (lane == 6 + k) {
+    for (int k = 0; k < 3; ++k) {
       ne.gp[3L * p + k] = v[6 + k];
       ne.tp[3L * p + k] = t[k];
       ne.d2_p[3L * p + k] = d2[k];
-      if (compute_scale) ne.scale_p[3L * p + k] = (k == 0 ? s0 : (k == 1 ? s1 : s2));
     }
-  if (lane == 9) {
+    if (compute_scale) { ne.scale_p[3L * p] = s0; ne.scale_p[3L * p + 1] = s1; ne.scale_p[3L * p + 2] = s2; }
     double2* x = reinterpret_cast<double2*>(xt + 6L * p);   // what the frame pass gathers: X_p | t_p
     x[0] = make_double2(X0, X1);
     x[1] = make_double2(X2, t[0]);

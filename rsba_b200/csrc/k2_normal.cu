@@ -60,12 +60,12 @@ point_blocks_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_o
   for (int k = 0; k < 9; ++k)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if (lane == 0) {   // every lane holds the full sums ("lane k stores element k" compiles to a jump table of divergent paths)
 #pragma unroll
-  for (int k = 0; k < 9; ++k)                        // every lane holds the full sums
-    if (lane == k) {
-      if (k < 6) C[6L * p + k] = v[k];
-      else gp[3L * p + (k - 6)] = v[k];
-    }
+    for (int k = 0; k < 3; ++k) reinterpret_cast<double2*>(C + 6L * p)[k] = make_double2(v[2 * k], v[2 * k + 1]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gp[3L * p + k] = v[6 + k];
+  }
 }
 
 // tau and frame of every observation in point-major order (coalesced for the warp-per-point kernels)
