@@ -61,6 +61,11 @@ __device__ __forceinline__ void load_pose(const double* __restrict__ poses, int 
 
 // ---------------------------------------------------------------- point pass
 constexpr int kPointPassWarps = 4;
+constexpr int kPointPassAhead = 148 * 4 * kPointPassWarps;   // points of one resident wave (4 CTAs per SM)
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // What the point pass needs of an observation, in point-major order and one 32-byte sector: no dependent
 // index -> observation gather on the critical path of a warp (it was 13 k of the 17.7 k cycles a point took).
@@ -85,12 +90,27 @@ __global__ void __launch_bounds__(kPointPassWarps * 32, 4)
 point_pass_kernel(const CameraModel cm, SchurStructure st, const PtObsRec* __restrict__ prec_pm, const double* __restrict__ poses,
                   const double* __restrict__ points, NormalEq ne, LmOptionsDev o, int compute_scale, int jacobi,
                   int rot_interp, int write_phi, double* __restrict__ rec_pt, double* __restrict__ tau_pt,
-                  double* __restrict__ xt) {
+                  double* __restrict__ xt, long n_obs, int n_points) {
   const int lane = threadIdx.x & 31;
   const int kk = blockIdx.x * kPointPassWarps + (threadIdx.x >> 5);
   if (kk >= ne.n_owned) return;
   const int p = owned_point(ne, kk);
   const int beg = st.pt_ptr[p], end = st.pt_ptr[p + 1];
+  // The top stall of this kernel is the chain of global round trips at a warp's start (CSR pointers -> records ->
+  // pose) at 16 warps per SM.  CTAs run in blockIdx order, about one resident wave at a time, and the records are
+  // point-major, so every warp pulls into L2 what the warp one wave behind it will ask for: its records (this
+  // track's length as the estimate of the others'), its point, its CSR pointers.
+  {
+    const long ahead = (long)kPointPassAhead * (end - beg);
+    const long e = beg + ahead + 4L * lane;                      // 4 records of 32 bytes per 128-byte line
+    if (4 * lane < end - beg && e < n_obs) prefetch_l2(prec_pm + e);
+    const int pa = p + kPointPassAhead;
+    if (lane == 0 && pa < n_points) {
+      prefetch_l2(points + 3L * pa);
+      prefetch_l2(st.pt_ptr + pa);
+      if (!compute_scale) prefetch_l2(ne.scale_p + 3L * pa);
+    }
+  }
   const double X0 = points[3L * p], X1 = points[3L * p + 1], X2 = points[3L * p + 2];
   const bool cst = ne.point_const[p] != 0;
   // the fixed Jacobi scaling of later linearisations, requested now (it is consumed behind the butterfly)
@@ -363,7 +383,8 @@ void launch_pack_point_major(const SchurStructure& st, const ObsView& obs, long 
 
 void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, const double* poses,
                        const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
-                       double* rec_pt, double* tau_pt, double* xt, bool write_phi, cudaStream_t s) {
+                       double* rec_pt, double* tau_pt, double* xt, bool write_phi, long n_obs, int n_points,
+                       cudaStream_t s) {
   if (ne.n_owned <= 0) return;
   const int rot_interp = (cm.shutter != 0 && cm.interp_rot) ? 1 : 0;
   // Measured beside this form and not kept (profiles/r02_notes.md, code at commit b6103ee): the evaluation in a kernel of
@@ -372,7 +393,7 @@ void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const vo
   const int grid = (ne.n_owned + kPointPassWarps - 1) / kPointPassWarps;
   point_pass_kernel<<<grid, kPointPassWarps * 32, 0, s>>>(cm, st, static_cast<const PtObsRec*>(packed), poses, points, ne, o,
                                                           compute_scale ? 1 : 0, jacobi ? 1 : 0, rot_interp, write_phi ? 1 : 0,
-                                                          rec_pt, tau_pt, xt);
+                                                          rec_pt, tau_pt, xt, n_obs, n_points);
 }
 
 void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,

@@ -144,7 +144,8 @@ struct PointGroups {
 constexpr int kPointGroupObs = 256, kPointGroupPoints = 128;
 void launch_point_pass(const CameraModel& cm, const SchurStructure& st, const void* packed, const double* poses,
                        const double* points, NormalEq ne, LmOptionsDev o, bool compute_scale, bool jacobi,
-                       double* rec_pt, double* tau_pt, double* xt, bool write_phi /* Schur panel rows */, cudaStream_t s);
+                       double* rec_pt, double* tau_pt, double* xt, bool write_phi /* Schur panel rows */, long n_obs,
+                       int n_points, cudaStream_t s);
 void launch_frame_pass(const CameraModel& cm, const SchurStructure& st, const ObsView& obs, const double* poses,
                        const double* xt, NormalEq ne, double* cost_partials, int* invalid_count, cudaStream_t s);
 // n_frames > 0: the camera parameters; points: the owned points (two calls: the point part runs before the

@@ -356,7 +356,7 @@ int linearize(rsba_problem* h, LmState* lm, const rsba_solve_options& opt, doubl
     cudaMemsetAsync(h->d_invalid.ptr, 0, sizeof(int), s);
     stage_begin(h, kStageJacobian);
     launch_point_pass(h->cm, lm->st, lm->pt_packed.ptr, h->d_poses.ptr, h->d_points.ptr, lm->ne, o, compute_scale,
-                      opt.jacobi_scaling != 0, lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, want_S, s);
+                      opt.jacobi_scaling != 0, lm->rec_pt.ptr, lm->pt_tau.ptr, lm->xt.ptr, want_S, h->n_obs, h->n_points, s);
     stage_end(h, kStageJacobian);
     stage_begin(h, kStageSchur);
     stage_begin(h, kStageFrameBlocks);
