@@ -1,0 +1,111 @@
+"""CPU suite: a third, independent pin of the oracle's residuals and Jacobians.
+
+The oracle's Jacobian comes from forward-mode `Jet<15>` arithmetic in a stand-in for Ceres (oracle/shim); it is checked
+against the reference's golden vectors and central finite differences in test_oracle_cpu.py.  Here the functor is restated
+once more in torch.float64 and differentiated by REVERSE-mode autograd -- no code shared with the shim, the port or the
+CUDA kernel:
+  interpolate_rs  cam.h:316-349  (tau from observed x, clamped; GLOBAL copies pose0)
+  interpolate     cam.h:294-311  (component-wise lerp; the rotation only if useSlerp)
+  w2c             cam.h:355-366  (ceres::AngleAxisRotatePoint: Rodrigues, first-order branch for tiny angles)
+  w2i / c2i       cam.h:372-419  (z < 1e-8 fails; dehomogenise, distort, focal length, principal point)
+  distort         cam.h:49-72
+  residual        video_bundler_free.h:45-65 (projection - observation)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_block_err
+from helpers import edge_scene, small_scene
+
+
+def _rotate(aa, p):
+    """ceres::AngleAxisRotatePoint (third-party; call site cam.h:365)."""
+    theta2 = (aa * aa).sum(-1, keepdim=True)
+    big = theta2 > np.finfo(np.float64).eps
+    t2 = torch.where(big, theta2, torch.ones_like(theta2))        # keeps sqrt's gradient finite in the other branch
+    theta = torch.sqrt(t2)
+    w = aa / theta
+    c, s = torch.cos(theta), torch.sin(theta)
+    wxp = torch.linalg.cross(w, p)
+    wdp = (w * p).sum(-1, keepdim=True)
+    rodrigues = p * c + wxp * s + w * wdp * (1.0 - c)
+    small = p + torch.linalg.cross(aa, p)
+    return torch.where(big, rodrigues, small)
+
+
+def _residuals(sc, p0, p1, X, xy):
+    cam = torch.tensor(np.asarray(sc.cam, dtype=np.float64))
+    x_obs = xy[:, 0:1]
+    if int(sc.shutter) == 0:                                       # GLOBAL
+        pose = p0
+    else:
+        s0, s1 = float(sc.scanlines[0]), float(sc.scanlines[1])
+        tau = ((x_obs - s0) / (s1 - s0)).clamp(0.0, 1.0)           # obs = {x, x}: x for both shutter directions
+        centre = p0[:, 3:] + (p1[:, 3:] - p0[:, 3:]) * tau
+        rot = p0[:, :3] + (p1[:, :3] - p0[:, :3]) * tau if sc.interpolate_rotation else p0[:, :3]
+        pose = torch.cat([rot, centre], dim=1)
+    pt = _rotate(pose[:, :3], X - pose[:, 3:])
+    z = pt[:, 2:3]
+    valid = (z >= 1e-8).squeeze(1)
+    zs = torch.where(z >= 1e-8, z, torch.ones_like(z))
+    u = pt[:, :2] / zs
+    xp, yp = u[:, 0:1], u[:, 1:2]
+    fx, fy, k1, k2, p1_, p2_, k3, cx, cy = [cam[i] for i in range(9)]
+    r2 = xp * xp + yp * yp
+    d = 1.0 + r2 * (k1 + r2 * (k2 + r2 * k3))
+    xy_ = xp * yp
+    px = d * xp + (2.0 * p1_ * xy_ + p2_ * (r2 + 2.0 * xp * xp))
+    py = d * yp + (p1_ * (r2 + 2.0 * yp * yp) + 2.0 * p2_ * xy_)
+    proj = torch.cat([px * fx + cx, py * fy + cy], dim=1)
+    return proj - xy, valid
+
+
+def _autograd_eval(sc):
+    fr = torch.as_tensor(np.asarray(sc.obs_frame, dtype=np.int64))
+    pi = torch.as_tensor(np.asarray(sc.obs_point, dtype=np.int64))
+    poses = torch.tensor(np.asarray(sc.poses, dtype=np.float64))
+    points = torch.tensor(np.asarray(sc.points, dtype=np.float64))
+    xy = torch.tensor(np.asarray(sc.obs_xy, dtype=np.float64))
+    p0 = poses[fr, :6].clone().requires_grad_(True)                # one copy per observation: rows are independent
+    p1 = poses[fr, 6:].clone().requires_grad_(True)
+    X = points[pi].clone().requires_grad_(True)
+    res, valid = _residuals(sc, p0, p1, X, xy)
+    n = res.shape[0]
+    J = np.zeros((n, 30))
+    for row in range(2):
+        g0, g1, gx = torch.autograd.grad(res[:, row].sum(), (p0, p1, X), retain_graph=True, allow_unused=True)
+        J[:, 6 * row:6 * row + 6] = g0.numpy()                     # J_pose0[2][6] | J_pose1[2][6] | J_point[2][3]
+        if g1 is not None:                                         # (a global shutter never reads pose1)
+            J[:, 12 + 6 * row:12 + 6 * row + 6] = g1.numpy()
+        J[:, 24 + 3 * row:24 + 3 * row + 3] = gx.numpy()
+    return res.detach().numpy(), J, valid.numpy()
+
+
+SCENES = [("C1", lambda: small_scene())] + [
+    (f"edge_shutter{s}_rot{int(r)}", (lambda s=s, r=r: edge_scene(s, r))) for s in (0, 1, 2) for r in (False, True)]
+
+
+@pytest.mark.parametrize("name,make", SCENES, ids=[n for n, _ in SCENES])
+def test_oracle_matches_reverse_mode_autograd(oracle_built, name, make):
+    sc = make()
+    res_t, J_t, valid_t = _autograd_eval(sc)
+    impls = ["port"] + (["ref"] if oracle_built.ref_available() else [])
+    for impl in impls:
+        res, J, valid = oracle_built.evaluate(sc, impl=impl)
+        res, J = np.asarray(res).reshape(-1, 2), np.asarray(J).reshape(-1, 30)
+        ok = np.asarray(valid).reshape(-1) == 1
+        assert np.array_equal(ok, valid_t), f"{impl}: the z >= 1e-8 gate disagrees"
+        assert ok.sum() > 0.5 * ok.size or name.startswith("edge")
+        # relative 1e-6 is the north star's bar; two FP64 evaluations of the same formulas agree far better
+        assert np.max(np.abs(res[ok] - res_t[ok]) / np.maximum(1.0, np.abs(res_t[ok]))) <= 1e-9, impl
+        assert rel_block_err(J[ok], J_t[ok]).max() <= 1e-9, impl
+
+
+def test_pose1_block_vanishes_for_a_global_shutter(oracle_built):
+    sc = edge_scene(0, True)
+    _, J_t, valid_t = _autograd_eval(sc)
+    assert not J_t[valid_t, 12:24].any()
+    _, J, valid = oracle_built.evaluate(sc, impl="port")
+    J = np.asarray(J).reshape(-1, 30)
+    assert not J[np.asarray(valid).reshape(-1) == 1, 12:24].any()
