@@ -34,8 +34,8 @@ def _rotate(aa, p):
     return torch.where(big, rodrigues, small)
 
 
-def _residuals(sc, p0, p1, X, xy):
-    cam = torch.tensor(np.asarray(sc.cam, dtype=np.float64))
+def _residuals(sc, p0, p1, X, xy, cam_rows=None):
+    cam = torch.tensor(np.asarray(sc.cam, dtype=np.float64)) if cam_rows is None else cam_rows.T.unsqueeze(-1)
     x_obs = xy[:, 0:1]
     if int(sc.shutter) == 0:                                       # GLOBAL
         pose = p0
@@ -59,6 +59,24 @@ def _residuals(sc, p0, p1, X, xy):
     py = d * yp + (p1_ * (r2 + 2.0 * yp * yp) + 2.0 * p2_ * xy_)
     proj = torch.cat([px * fx + cx, py * fy + cy], dim=1)
     return proj - xy, valid
+
+
+def _autograd_eval_cam(sc):
+    """d residual / d (fx fy k1 k2 p1 p2 k3 cx cy): the 9-block of the uncalibrated variant <2; 9, 6, 6, 3>
+    (VideoSfmBaRs.h:38-49, ReprojectionError::operator()(camera, pose, point, residuals) video_bundler_free.h:33-41)."""
+    fr = torch.as_tensor(np.asarray(sc.obs_frame, dtype=np.int64))
+    pi = torch.as_tensor(np.asarray(sc.obs_point, dtype=np.int64))
+    poses = torch.tensor(np.asarray(sc.poses, dtype=np.float64))
+    points = torch.tensor(np.asarray(sc.points, dtype=np.float64))
+    xy = torch.tensor(np.asarray(sc.obs_xy, dtype=np.float64))
+    n = xy.shape[0]
+    cam = torch.tensor(np.asarray(sc.cam, dtype=np.float64)).repeat(n, 1).requires_grad_(True)   # one copy per observation
+    res, valid = _residuals(sc, poses[fr, :6], poses[fr, 6:], points[pi], xy, cam_rows=cam)
+    Jc = np.zeros((n, 18))
+    for row in range(2):
+        (g,) = torch.autograd.grad(res[:, row].sum(), (cam,), retain_graph=True)
+        Jc[:, 9 * row:9 * row + 9] = g.numpy()
+    return Jc, valid.numpy()
 
 
 def _autograd_eval(sc):
@@ -109,3 +127,17 @@ def test_pose1_block_vanishes_for_a_global_shutter(oracle_built):
     _, J, valid = oracle_built.evaluate(sc, impl="port")
     J = np.asarray(J).reshape(-1, 30)
     assert not J[np.asarray(valid).reshape(-1) == 1, 12:24].any()
+
+
+@pytest.mark.parametrize("name,make", SCENES, ids=[n for n, _ in SCENES])
+def test_intrinsics_block_matches_reverse_mode_autograd(oracle_built, name, make):
+    sc = make()
+    Jc_t, valid_t = _autograd_eval_cam(sc)
+    Jc = np.asarray(oracle_built.intrinsics_jacobian(sc)).reshape(-1, 18)           # closed form, travels everywhere
+    assert rel_block_err(Jc[valid_t], Jc_t[valid_t]).max() <= 1e-9
+    assert not Jc[~valid_t].any()
+    if oracle_built.ref_available():                                                # the reference functor under Jet<24>
+        _, _, Jc_ref, valid = oracle_built.evaluate_cam_ref(sc)
+        ok = np.asarray(valid).reshape(-1) == 1
+        assert np.array_equal(ok, valid_t)
+        assert rel_block_err(np.asarray(Jc_ref).reshape(-1, 18)[ok], Jc_t[ok]).max() <= 1e-9
