@@ -141,3 +141,46 @@ def test_intrinsics_block_matches_reverse_mode_autograd(oracle_built, name, make
         ok = np.asarray(valid).reshape(-1) == 1
         assert np.array_equal(ok, valid_t)
         assert rel_block_err(np.asarray(Jc_ref).reshape(-1, 18)[ok], Jc_t[ok]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("a", [0.5, 2.0])
+def test_huber_correction_is_the_gradient_of_the_robustified_cost(oracle_built, a):
+    """ceres::HuberLoss on every residual block (CeresHandler.h:85-90).  Ceres' Corrector is third-party and restated in
+    oracle.apply_huber (rho'' <= 0: residual and Jacobian times sqrt(rho')); what can be pinned without Ceres is that the
+    corrected quantities are consistent with the DEFINITION of the robustified problem: cost = 1/2 sum rho(|r_i|^2) with
+    rho(s) = s (s <= a^2), 2 a sqrt(s) - a^2 otherwise, and J_w^T r_w = its exact gradient (reverse-mode autograd)."""
+    from rsba_b200.scene import Scene
+    sc = small_scene()
+    xy = sc.obs_xy.copy()
+    xy[::9] += 25.0                                   # gross outliers: both branches of rho are exercised
+    sc = Scene(**{**sc.__dict__, "obs_xy": xy})
+    r0, J0, v0 = oracle_built.evaluate(sc, impl="port")
+    r0, J0 = np.asarray(r0).reshape(-1, 2), np.asarray(J0).reshape(-1, 30)
+    ok = np.asarray(v0).reshape(-1) == 1
+    rw, Jw, cost_w = oracle_built.apply_huber(r0, J0, a)
+    s_np = np.sum(r0 * r0, axis=1)
+    assert (s_np[ok] > a * a).sum() > 100 and (s_np[ok] <= a * a).sum() > 100
+
+    fr = torch.as_tensor(np.asarray(sc.obs_frame, dtype=np.int64))
+    pi = torch.as_tensor(np.asarray(sc.obs_point, dtype=np.int64))
+    poses = torch.tensor(np.asarray(sc.poses, dtype=np.float64), requires_grad=True)
+    points = torch.tensor(np.asarray(sc.points, dtype=np.float64), requires_grad=True)
+    res, valid = _residuals(sc, poses[fr, :6], poses[fr, 6:], points[pi], torch.tensor(xy))
+    assert np.array_equal(valid.numpy(), ok)
+    sq = (res * res).sum(1)
+    rho = torch.where(sq > a * a, 2.0 * a * torch.sqrt(torch.where(sq > a * a, sq, torch.ones_like(sq))) - a * a, sq)
+    cost = 0.5 * rho[valid].sum()
+    g_poses, g_points = torch.autograd.grad(cost, (poses, points))
+    assert abs(float(cost.detach()) - cost_w) <= 1e-12 * cost_w
+
+    # J_w^T r_w scattered to the parameter blocks (J = J_pose0[2][6] | J_pose1[2][6] | J_point[2][3])
+    gp = np.zeros_like(g_poses.numpy())
+    gx = np.zeros_like(g_points.numpy())
+    f_np, p_np = np.asarray(sc.obs_frame), np.asarray(sc.obs_point)
+    for row in range(2):
+        np.add.at(gp[:, :6], f_np[ok], Jw[ok, 6 * row:6 * row + 6] * rw[ok, row:row + 1])
+        np.add.at(gp[:, 6:], f_np[ok], Jw[ok, 12 + 6 * row:12 + 6 * row + 6] * rw[ok, row:row + 1])
+        np.add.at(gx, p_np[ok], Jw[ok, 24 + 3 * row:24 + 3 * row + 3] * rw[ok, row:row + 1])
+    scale = max(np.abs(g_poses.numpy()).max(), np.abs(g_points.numpy()).max())
+    assert np.abs(gp - g_poses.numpy()).max() <= 1e-9 * scale
+    assert np.abs(gx - g_points.numpy()).max() <= 1e-9 * scale
