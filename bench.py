@@ -525,7 +525,7 @@ def run_ours(args):
         "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(args.config),
-        "l2": "no flush needed: every iteration streams > 4 GB through HBM (J alone is 1.2 GB > 126 MB L2)",
+        "l2": "no flush needed: every iteration streams > 8 GB through HBM (ncu, C3: point pass 2.1 GB, SYRK 5.5 GB, back-substitution 0.6 GB; the Schur panels alone are 1.8 GB against 126 MB of L2)",
         "parallelism": "single GPU" if world == 1 else f"observations sharded by point owner x{world}, one NCCL allreduce of the reduced system per linear solve",
         "setup_ms": {"scene_upload": upload_ms, "warmup_solve_incl_structure": warm_ms},
         "lm_iters_per_sec": 1e3 / ms_per_step,
